@@ -1,0 +1,141 @@
+/*
+ * ppm_b200.h -- C ABI of the B200-native PPM likelihood engine.
+ *
+ * Drop-in boundary for the objective function of JasmineGamblin/PPMmodelPangenome: the lambda handed to
+ * nelder_mead (reference source/functions.cpp:404-412, :437-445) does
+ *     tLik.clearLikValues(); return -logLik(par[0..5], {par[6],par[6],par[6],par[7]});
+ * and the same engine state is read by computeI2 (functions.cpp:334-344; callers :397, :420, :453),
+ * assignCat (:489-520) and nb0/nb1/nb2 (:522-541).  Each entry point below names what it replaces.
+ *
+ * Conventions: plain pointers and sizes only, no C++/torch types; every call returns 0 on success or a
+ * PPM_E* code (message via ppm_last_error); no exception crosses the ABI; one handle owns one CUDA
+ * device context, its streams and all device memory; calls on one handle are serialised by the caller
+ * (the reference object is not re-entrant either).  There is NO CPU fallback: without a usable sm_100
+ * device every compute entry point fails with PPM_ECUDA.
+ *
+ * Parameter vectors are 8 doubles in the reference's boundary order
+ *     [N0, l0, i1, l1, g2, l2, s_10, s_01]            (functions.cpp:409; inference.cpp:43-44)
+ * s_10 (false negative, the reference's error2) is used by all three categories, s_01 (false positive,
+ * error1) by the Mobile category only (functions.cpp:356).
+ */
+#ifndef PPM_B200_H
+#define PPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ppm_engine* ppm_handle;
+
+enum {
+  PPM_OK = 0,
+  PPM_EINVAL = 1,  /* bad argument / malformed input                                    */
+  PPM_EIO = 2,     /* file could not be read                                             */
+  PPM_ECUDA = 3,   /* CUDA error, no device, or the device is not sm_100                 */
+  PPM_ENOMEM = 4,
+  PPM_ESTATE = 5   /* call not valid in the handle's current state                       */
+};
+
+/* Flattened species tree in the reference's PREORDER numbering (RecTree::addNodeID, objects.cpp:104-114):
+ * node 0 is the root, children have larger ids than their parent. */
+typedef struct {
+  int32_t n_nodes;          /* 2*n_leaves-1                                                          */
+  const int32_t* left;      /* [n_nodes] id of the left child, -1 for a leaf   (objects.cpp:375)      */
+  const int32_t* right;     /* [n_nodes] id of the right child, -1 for a leaf                         */
+  const double* branch_len; /* [n_nodes] length of the branch above the node, [0] ignored (functions.cpp:95-96) */
+} ppm_tree;
+
+/* Model dimensions and constants, mirroring the private fields of Inference (functions.hpp:78-94). */
+typedef struct {
+  int32_t n_nodes, n_leaves;
+  int64_t n_genes;       /* rows of the input matrix (nRep of an uncompressed input)   */
+  int64_t n_patterns;    /* unique patterns held on the device (== n_genes without dedupe) */
+  int64_t n_obs;         /* sum of multiplicities (nObs, functions.cpp:83)              */
+  int32_t n_words;       /* 32-bit words per bit-packed pattern                          */
+  int32_t n_slices;      /* S: midpoint-rule slices of the Mobile integral (functions.cpp:256) */
+  int64_t n_terms;       /* W: sum over slices of alive lineages (functions.cpp:250-262) */
+  double H, L, mean_genes; /* functions.cpp:108, :86, :123-127                           */
+  int32_t device;        /* CUDA ordinal */
+  int32_t shard_rank, shard_world;
+  int64_t shard_first, shard_count; /* the slice of patterns this handle evaluates      */
+} ppm_info;
+
+/* ---- construction ---------------------------------------------------------------------------------- */
+
+/* Replaces Inference::Inference (functions.cpp:76-156) for callers that already hold flat data.
+ * packed_patterns: n_patterns rows of n_words=ceil(n_leaves/32) uint32, row-major; bit k of a row is the
+ * 0/1 observation of the k-th LEAF IN PREORDER (left-to-right in the Newick string).
+ * counts: multiplicities (PAmatrix::counts, objects.cpp:175-187,210-213), NULL = all ones.
+ * dedupe != 0 merges identical rows keeping first-occurrence order (PAmatrix::compress, objects.cpp:254-273).
+ * device: CUDA ordinal; device < 0 creates a HOST-ONLY handle (model inspection through ppm_get_info /
+ * ppm_get_*_array only; every compute call returns PPM_ESTATE).  shard_rank/shard_world: this handle evaluates the shard_rank-th of shard_world
+ * contiguous slices of the (deduplicated) patterns; pass 0,1 for everything. */
+int ppm_create(ppm_handle* out, const ppm_tree* tree, const uint32_t* packed_patterns, const int32_t* counts,
+               int64_t n_patterns, int dedupe, int device, int shard_rank, int shard_world);
+
+/* Same, reading the reference's input files: RecTree::readTree (objects.cpp:123-131, first line, binary,
+ * every node ':length', internal labels skipped) and PAmatrix(path) (objects.cpp:164-214, incl. the "ccc"
+ * compressed header). */
+int ppm_create_from_files(ppm_handle* out, const char* tree_path, const char* matrix_path, int dedupe, int device,
+                          int shard_rank, int shard_world);
+
+void ppm_destroy(ppm_handle h);
+const char* ppm_last_error(ppm_handle h); /* h may be NULL: error of the last failed create on this thread */
+int ppm_get_info(ppm_handle h, ppm_info* out);
+
+/* Integer model arrays for bit-exact checks against the reference's fields (functions.hpp:78-94):
+ * which = 0 mrca[n_patterns] (preorder node id), 1 freq[n_patterns], 2 counts[n_patterns],
+ *         3 order[n_nodes], 4 gene_to_pattern[n_genes], 5 nSub per interval rank [n_nodes-1],
+ *         6 alive lineages per interval rank [n_nodes-1] (|subtrees[rank]|, functions.cpp:130-141). */
+int ppm_get_int_array(ppm_handle h, int which, int32_t* out, int64_t capacity);
+/* which = 0 height[n_nodes] (functions.cpp:106-109), 1 branch_len[n_nodes]. */
+int ppm_get_double_array(ppm_handle h, int which, double* out, int64_t capacity);
+
+/* ---- the objective ----------------------------------------------------------------------------------- */
+
+/* Replaces clearLikValues()+Inference::logLik (functions.cpp:359-372, objective body :404-412) for P
+ * parameter vectors at once: out_ll[p] = sum_patterns count*log-mixture, or -1e9+i2 when i2<0 (:362-364).
+ * With shard_world>1 out_ll holds this shard's PARTIAL sum (and the penalty is NOT applied): add the
+ * partials over shards, then call ppm_finalize_ll.  out_i2 may be NULL.  Host pointers. */
+int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, double* out_i2);
+
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the
+ * handle's own stream): d_params [P][8], d_out_partial [P] per-shard partial sums (no penalty),
+ * d_out_i2 [P].  This is the entry used with inputs resident in HBM and with an external all-reduce
+ * (NCCL through torch.distributed) between it and ppm_finalize_ll_device. */
+int ppm_loglik_device(ppm_handle h, const double* d_params, int32_t P, double* d_out_partial, double* d_out_i2,
+                      void* stream);
+/* ll[p] = i2[p] < 0 ? -1e9 + i2[p] : ll[p]   (functions.cpp:362-364), in place. */
+int ppm_finalize_ll(const double* i2, double* ll, int32_t P);
+int ppm_finalize_ll_device(ppm_handle h, const double* d_i2, double* d_ll, int32_t P, void* stream);
+
+/* Replaces Inference::computeI2 (functions.cpp:334-344); out_p0p1AB [P][4] = p0, p1, A (getPobs1 :284-299),
+ * B (getPobs2 :300-333), the inputs of nb0/nb1/nb2 (:522-541); may be NULL. */
+int ppm_compute_i2(ppm_handle h, const double* params, int32_t P, double* out_i2, double* out_p0p1AB);
+
+/* Replaces the per-pattern body of Inference::assignCat (functions.cpp:495-510): argmax over
+ * {Persistent, Private (root + below-root), Mobile} with the reference's strict '>' tie-break, evaluated
+ * at params8 with the given i2 (the reference passes its stored MLEi2).  out_cat has one value in {0,1,2}
+ * per GENE of the input, in input order (shard_world must be 1). */
+int ppm_assign_cat(ppm_handle h, const double* params8, double i2, int8_t* out_cat);
+
+/* The three category log-terms of one parameter vector, per PATTERN of this shard:
+ * out[3*r+0] = lik0r, out[3*r+1] = logSumExp(lik1r, lik1), out[3*r+2] = lik2 (functions.cpp:348-356, :497-505). */
+int ppm_components(ppm_handle h, const double* params8, double i2, double* out /*[shard_count*3]*/);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------- */
+
+/* Counters of the last ppm_loglik*(): [0] kernels launched, [1] device ms of the main kernel (CUDA events
+ * on the launching stream; valid after the stream is synchronised), [2] algorithmic flops per pattern-eval
+ * F = 5W + 28(n-1) + 2S, [3] FP64 instructions per pattern-eval actually issued by the main
+ * kernel's arithmetic (model count). */
+int ppm_get_counters(ppm_handle h, double* out4);
+/* DFMA micro-benchmark: measured FP64 FMA throughput of the device in TFLOP/s (2 flop per FMA). */
+int ppm_measure_fp64_peak(int device, double* out_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPM_B200_H */

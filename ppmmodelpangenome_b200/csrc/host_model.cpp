@@ -1,0 +1,470 @@
+// Host-side model builder.  Everything the reference's Inference constructor derives from its inputs
+// (reference source/functions.cpp:76-156) is rebuilt here on flat arrays, in the same floating-point order
+// where integers depend on it (heights -> order -> nSub).  No recursion: a 10,000-leaf caterpillar tree is
+// 10,000 levels deep.
+#include "host_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace ppm {
+
+static void finish_tree(Tree& t);
+
+// RecTree(string) (objects.cpp:51-78) accepts: binary nodes only, ':length' after every node, an optional
+// label after ')' which is skipped (firstPoint, objects.cpp:38-50), and ignores whatever follows the last ')'
+// (the root's own ':0;').  Lengths go through stold then narrow to double (objects.cpp:71-72).
+Tree parse_newick(const std::string& line) {
+  Tree t;
+  const char* s = line.c_str();
+  size_t n = line.size(), pos = 0;
+  std::vector<int> open;  // internal nodes whose children are still being read
+  auto attach = [&](int v) {
+    if (open.empty()) {
+      if (v != 0) throw std::runtime_error("newick: more than one top-level node");
+      return;
+    }
+    int p = open.back();
+    t.parent[v] = p;
+    if (t.left[p] < 0) t.left[p] = v;
+    else if (t.right[p] < 0) t.right[p] = v;
+    else throw std::runtime_error("newick: node with more than two children (the model needs a binary tree)");
+  };
+  auto add = [&]() {
+    t.left.push_back(-1); t.right.push_back(-1); t.parent.push_back(-1);
+    t.bl.push_back(0.); t.label.emplace_back();
+    return (int)t.left.size() - 1;
+  };
+  auto read_len = [&](int v) {
+    if (pos < n && s[pos] == ':') {
+      char* end = nullptr;
+      long double x = strtold(s + pos + 1, &end);
+      if (end == s + pos + 1) throw std::runtime_error("newick: missing branch length");
+      t.bl[v] = (double)x;
+      pos = end - s;
+    } else if (!open.empty()) {
+      throw std::runtime_error("newick: every node needs ':length'");
+    }
+  };
+  bool done = false;
+  while (pos < n && !done) {
+    char c = s[pos];
+    if (c == '(') {
+      int v = add(); attach(v); open.push_back(v); pos++;
+    } else if (c == ',') {
+      pos++;
+    } else if (c == ')') {
+      if (open.empty()) throw std::runtime_error("newick: unbalanced ')'");
+      int v = open.back(); open.pop_back(); pos++;
+      if (t.right[v] < 0) throw std::runtime_error("newick: node with fewer than two children");
+      while (pos < n && s[pos] != ':' && s[pos] != ',' && s[pos] != ')' && s[pos] != ';') pos++;  // label
+      read_len(v);
+      if (open.empty()) done = true;
+    } else if (c == ';' || c == ' ' || c == '\r' || c == '\t') {
+      pos++;
+    } else {
+      size_t j = pos;
+      while (j < n && s[j] != ':' && s[j] != ',' && s[j] != ')' && s[j] != '(' && s[j] != ';') j++;
+      int v = add(); attach(v);
+      t.label[v] = line.substr(pos, j - pos);
+      pos = j;
+      read_len(v);
+      if (open.empty()) done = true;
+    }
+  }
+  if (!open.empty()) throw std::runtime_error("newick: unbalanced '('");
+  if (t.left.empty()) throw std::runtime_error("newick: empty tree");
+  finish_tree(t);
+  return t;
+}
+
+Tree tree_from_arrays(int n_nodes, const int32_t* left, const int32_t* right, const double* bl) {
+  if (n_nodes < 1 || n_nodes % 2 == 0) throw std::runtime_error("tree: n_nodes must be odd and positive");
+  Tree t;
+  t.left.assign(left, left + n_nodes);
+  t.right.assign(right, right + n_nodes);
+  t.bl.assign(bl, bl + n_nodes);
+  t.parent.assign(n_nodes, -1);
+  t.label.assign(n_nodes, "");
+  for (int v = 0; v < n_nodes; v++) {
+    int a = t.left[v], b = t.right[v];
+    if ((a < 0) != (b < 0)) throw std::runtime_error("tree: a node needs zero or two children");
+    if (a >= 0) {
+      if (a <= v || b <= a || b >= n_nodes) throw std::runtime_error("tree: ids are not a preorder numbering");
+      t.parent[a] = v; t.parent[b] = v;
+    }
+  }
+  for (int v = 1; v < n_nodes; v++)
+    if (t.parent[v] < 0) throw std::runtime_error("tree: node without parent");
+  finish_tree(t);
+  // preorder check: left child is v+1, right child is last(left)+1
+  for (int v = 0; v < n_nodes; v++)
+    if (t.left[v] >= 0 && (t.left[v] != v + 1 || t.right[v] != t.last[t.left[v]] + 1))
+      throw std::runtime_error("tree: ids are not a preorder numbering");
+  return t;
+}
+
+Tree read_tree_file(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("cannot open tree file " + path);
+  std::string line;
+  std::getline(f, line);  // only the first line is read (objects.cpp:123-131)
+  if (line.empty()) throw std::runtime_error("tree file is empty: " + path);
+  return parse_newick(line);
+}
+
+static void finish_tree(Tree& t) {
+  const int nn = (int)t.left.size();
+  t.n_nodes = nn;
+  t.n_leaves = (nn + 1) / 2;
+  t.bl[0] = 0.;
+  int n_leaf_found = 0;
+  t.leaf_pos.assign(nn, -1);
+  t.leaf_node.clear();
+  for (int v = 0; v < nn; v++)
+    if (t.left[v] < 0) { t.leaf_pos[v] = n_leaf_found++; t.leaf_node.push_back(v); }
+  if (n_leaf_found != t.n_leaves) throw std::runtime_error("tree: not a full binary tree");
+
+  // depths root -> leaf (functions.cpp:66-75), H = max depth, height = H - depth (:108-109)
+  std::vector<double> depth(nn, 0.);
+  for (int v = 0; v < nn; v++)
+    if (t.left[v] >= 0) {
+      depth[t.left[v]] = depth[v] + t.bl[t.left[v]];
+      depth[t.right[v]] = depth[v] + t.bl[t.right[v]];
+    }
+  t.H = *std::max_element(depth.begin(), depth.end());
+  t.height.resize(nn);
+  for (int v = 0; v < nn; v++) t.height[v] = t.H - depth[v];
+
+  // subtree extents and treeLength in the reference's summation order (objects.cpp:115-122)
+  t.last.assign(nn, 0);
+  std::vector<double> tl(nn, 0.);
+  for (int v = nn - 1; v >= 0; v--) {
+    if (t.left[v] < 0) { t.last[v] = v; continue; }
+    t.last[v] = t.last[t.right[v]];
+    tl[v] = ((t.bl[t.left[v]] + tl[t.left[v]]) + t.bl[t.right[v]]) + tl[t.right[v]];
+  }
+  t.L = tl[0];
+
+  // order by increasing height (functions.cpp:112-114).  std::sort leaves ties unspecified; we break them
+  // children-first (larger preorder id first), which every consistent sweep needs ("ties").
+  t.order.resize(nn);
+  for (int i = 0; i < nn; i++) t.order[i] = i;
+  std::sort(t.order.begin(), t.order.end(), [&](int a, int b) {
+    if (t.height[a] != t.height[b]) return t.height[a] < t.height[b];
+    return a > b;
+  });
+  t.rank.resize(nn);
+  for (int i = 0; i < nn; i++) t.rank[t.order[i]] = i;
+
+  // breadth-first last node (what computeMRCA returns for an all-zero pattern, functions.cpp:52-64)
+  {
+    std::vector<int> q{0};
+    for (size_t k = 0; k < q.size(); k++)
+      if (t.left[q[k]] >= 0) { q.push_back(t.left[q[k]]); q.push_back(t.right[q[k]]); }
+    t.bfs_last = q.back();
+  }
+
+  // Mobile integral grid (functions.cpp:250-260) and alive-lineage counts (functions.cpp:130-141)
+  t.nsub.assign(std::max(nn - 1, 0), 0);
+  t.alive.assign(std::max(nn - 1, 0), 0);
+  t.slice_start.assign(nn, 0);
+  t.slice_t.clear(); t.slice_wt.clear();
+  {
+    // alive count of interval r = lineages v (non-root) with rank[v] <= r < rank[parent[v]]
+    std::vector<int> delta(nn + 1, 0);
+    for (int v = 1; v < nn; v++) { delta[t.rank[v]]++; delta[t.rank[t.parent[v]]]--; }
+    int run = 0;
+    for (int r = 0; r < nn - 1; r++) { run += delta[r]; t.alive[r] = run; }
+  }
+  t.n_terms = 0;
+  for (int r = 0; r < nn - 1; r++) {
+    t.slice_start[r] = (int)t.slice_t.size();
+    if (r < t.n_leaves - 1) continue;  // the integral starts at the last leaf (functions.cpp:250)
+    double h0 = t.height[t.order[r]];
+    double w = t.height[t.order[r + 1]] - h0;
+    if (!(w > 0.)) continue;
+    int ns = std::max(1, (int)std::ceil(w * 100 / t.H));
+    t.nsub[r] = ns;
+    for (int i = 0; i < ns; i++) {
+      t.slice_t.push_back(h0 + (2 * i + 1) * w / (2 * ns));
+      t.slice_wt.push_back(w / ns);
+    }
+    t.n_terms += (int64_t)ns * t.alive[r];
+  }
+  if (nn >= 1) t.slice_start[nn - 1] = (int)t.slice_t.size();
+  t.n_slices = (int)t.slice_t.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct RowHash {
+  const uint32_t* base; int nw;
+  size_t operator()(int64_t i) const {
+    uint64_t h = 1469598103934665603ull;
+    const uint32_t* p = base + (size_t)i * nw;
+    for (int k = 0; k < nw; k++) { h ^= p[k]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+struct RowEq {
+  const uint32_t* base; int nw;
+  bool operator()(int64_t a, int64_t b) const {
+    return std::memcmp(base + (size_t)a * nw, base + (size_t)b * nw, sizeof(uint32_t) * nw) == 0;
+  }
+};
+}  // namespace
+
+Patterns build_patterns(const Tree& t, const uint32_t* rows, const int32_t* counts, int64_t n_rows, bool dedupe) {
+  Patterns p;
+  const int nw = (t.n_leaves + 31) / 32;
+  p.n_words = nw;
+  p.n_genes = n_rows;
+  if (n_rows <= 0) throw std::runtime_error("matrix: no gene columns");
+  // bits beyond n_leaves must be clear
+  if (t.n_leaves % 32) {
+    uint32_t mask = ~0u << (t.n_leaves % 32);
+    for (int64_t i = 0; i < n_rows; i++)
+      if (rows[(size_t)i * nw + nw - 1] & mask) throw std::runtime_error("patterns: bits set beyond n_leaves");
+  }
+  p.gene_to_pattern.resize(n_rows);
+  std::vector<int64_t> keep;
+  if (dedupe) {  // PAmatrix::compress keeps first-occurrence order (objects.cpp:254-273)
+    std::unordered_map<int64_t, int32_t, RowHash, RowEq> seen((size_t)n_rows * 2, RowHash{rows, nw}, RowEq{rows, nw});
+    for (int64_t i = 0; i < n_rows; i++) {
+      auto it = seen.find(i);
+      if (it == seen.end()) {
+        seen.emplace(i, (int32_t)keep.size());
+        p.gene_to_pattern[i] = (int32_t)keep.size();
+        keep.push_back(i);
+        p.counts.push_back(counts ? counts[i] : 1);
+      } else {
+        p.gene_to_pattern[i] = it->second;
+        p.counts[it->second] += counts ? counts[i] : 1;
+      }
+    }
+  } else {
+    keep.resize(n_rows);
+    p.counts.resize(n_rows);
+    for (int64_t i = 0; i < n_rows; i++) { keep[i] = i; p.gene_to_pattern[i] = (int32_t)i; p.counts[i] = counts ? counts[i] : 1; }
+  }
+  p.n_patterns = (int64_t)keep.size();
+  p.words.resize((size_t)p.n_patterns * nw);
+  for (int64_t j = 0; j < p.n_patterns; j++)
+    std::memcpy(&p.words[(size_t)j * nw], rows + (size_t)keep[j] * nw, sizeof(uint32_t) * nw);
+
+  // binary lifting over parents for the MRCA
+  int LOG = 1;
+  while ((1 << LOG) < t.n_nodes) LOG++;
+  std::vector<std::vector<int>> up(LOG, std::vector<int>(t.n_nodes, 0));
+  for (int v = 0; v < t.n_nodes; v++) up[0][v] = v ? t.parent[v] : 0;
+  for (int k = 1; k < LOG; k++)
+    for (int v = 0; v < t.n_nodes; v++) up[k][v] = up[k - 1][up[k - 1][v]];
+
+  p.mrca.resize(p.n_patterns);
+  p.freq.resize(p.n_patterns);
+  p.n_obs = 0;
+  long double gene_sum = 0;
+  for (int64_t j = 0; j < p.n_patterns; j++) {
+    const uint32_t* w = &p.words[(size_t)j * nw];
+    int f = 0, lo = -1, hi = -1;
+    for (int k = 0; k < nw; k++) {
+      if (!w[k]) continue;
+      f += __builtin_popcount(w[k]);
+      if (lo < 0) lo = 32 * k + __builtin_ctz(w[k]);
+      hi = 32 * k + 31 - __builtin_clz(w[k]);
+    }
+    p.freq[j] = f;  // functions.cpp:117-122
+    // computeMRCA (functions.cpp:46-65): the last node in breadth-first order containing every present leaf,
+    // i.e. their deepest common ancestor; leaves in preorder => it is the LCA of the first and last present leaf.
+    int m;
+    if (f == 0) m = t.bfs_last;
+    else {
+      int a = t.leaf_node[lo], b = t.leaf_node[hi];
+      for (int k = LOG - 1; k >= 0; k--)
+        if (t.last[up[k][a]] < b) a = up[k][a];
+      m = (t.last[a] >= b) ? a : t.parent[a];
+    }
+    p.mrca[j] = m;
+    p.n_obs += p.counts[j];                                  // functions.cpp:83
+    gene_sum += (long double)f * p.counts[j];                // functions.cpp:123-126
+  }
+  p.mean_genes = (double)gene_sum / t.n_leaves;              // functions.cpp:127 (integers: exact in double)
+  return p;
+}
+
+// PAmatrix(path) (objects.cpp:164-214): first line = header (ignored) or "ccc,count,count,..."; then one
+// line per genome: name,v,v,...  Genome rows are matched to tree leaves by name (objects.cpp:240-249).
+Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("cannot open matrix file " + path);
+  std::string line;
+  if (!std::getline(f, line)) throw std::runtime_error("matrix file is empty: " + path);
+  std::vector<int32_t> counts;
+  auto strip = [](std::string& s) { while (!s.empty() && (s.back() == '\r' || s.back() == '\n')) s.pop_back(); };
+  strip(line);
+  if (line.size() >= 3 && line[0] == 'c' && line[1] == 'c' && line[2] == 'c') {
+    size_t pos = line.find(',');
+    while (pos != std::string::npos) {
+      counts.push_back((int32_t)strtol(line.c_str() + pos + 1, nullptr, 10));
+      pos = line.find(',', pos + 1);
+    }
+  }
+  std::unordered_map<std::string, int> leaf_of;
+  for (int k = 0; k < t.n_leaves; k++) leaf_of[t.label[t.leaf_node[k]]] = k;
+  const int nw = (t.n_leaves + 31) / 32;
+  std::vector<uint32_t> rows;
+  int64_t n_genes = -1;
+  std::vector<char> seen(t.n_leaves, 0);
+  while (std::getline(f, line)) {
+    strip(line);
+    if (line.empty()) continue;
+    size_t c = line.find(',');
+    if (c == std::string::npos) throw std::runtime_error("matrix: line without values");
+    std::string name = line.substr(0, c);
+    auto it = leaf_of.find(name);
+    const char* p = line.c_str() + c + 1;
+    // count values on the first data line
+    if (n_genes < 0) {
+      n_genes = 1;
+      for (const char* q = p; *q; q++) n_genes += (*q == ',');
+      rows.assign((size_t)n_genes * nw, 0u);
+    }
+    if (it == leaf_of.end()) continue;  // genome not in the tree: unused by the likelihood
+    int k = it->second;
+    if (seen[k]) {  // a later row with the same name wins (std::map assignment, objects.cpp:195)
+      for (int64_t g = 0; g < n_genes; g++) rows[(size_t)g * nw + (k >> 5)] &= ~(1u << (k & 31));
+    }
+    seen[k] = 1;
+    int64_t g = 0;
+    while (true) {
+      char* end;
+      long v = strtol(p, &end, 10);
+      if (end == p) throw std::runtime_error("matrix: empty value in row " + name);
+      if (v != 0 && v != 1) throw std::runtime_error("matrix: values must be 0 or 1 (row " + name + ")");
+      if (g >= n_genes) throw std::runtime_error("matrix: row " + name + " is longer than the first row");
+      if (v) rows[(size_t)g * nw + (k >> 5)] |= 1u << (k & 31);
+      g++;
+      if (*end == ',') p = end + 1; else break;
+    }
+    if (g != n_genes) throw std::runtime_error("matrix: row " + name + " is shorter than the first row");
+  }
+  if (n_genes <= 0) throw std::runtime_error("matrix: no genome rows");
+  for (int k = 0; k < t.n_leaves; k++)
+    if (!seen[k]) throw std::runtime_error("matrix: no row for tree leaf '" + t.label[t.leaf_node[k]] + "'");
+  if (!counts.empty() && (int64_t)counts.size() != n_genes) throw std::runtime_error("matrix: ccc header length differs from the rows");
+  return build_patterns(t, rows.data(), counts.empty() ? nullptr : counts.data(), n_genes, dedupe);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+Program build_program(const Tree& t, int R) {
+  Program pg;
+  pg.R = R;
+  const int nn = t.n_nodes, S = t.n_slices, nl = t.n_leaves;
+  const int nb = (S + R - 1) / R;
+  pg.n_blocks = nb;
+  pg.blk_slice0.resize(nb); pg.blk_nslices.resize(nb);
+  for (int b = 0; b < nb; b++) { pg.blk_slice0[b] = b * R; pg.blk_nslices[b] = std::min(R, S - b * R); }
+
+  // alive slice range of every non-root lineage: intervals [max(rank, nl-1), rank(parent)-1]
+  std::vector<int> js0(nn, S), js1(nn, S);
+  for (int v = 1; v < nn; v++) {
+    js0[v] = t.slice_start[std::max(t.rank[v], nl - 1)];
+    js1[v] = t.slice_start[t.rank[t.parent[v]]];
+  }
+  // node ops: internal nodes in rank order; op block = block of the node's first alive slice
+  std::vector<int> op_block(nn, nb);
+  for (int v = 1; v < nn; v++)
+    if (t.left[v] >= 0 && js0[v] < S) op_block[v] = js0[v] / R;  // (a node with an empty alive range still merges here)
+  // slots: allocated at the op, released after the block in which the parent is formed
+  std::vector<int> slot(nn, -1);
+  std::vector<std::vector<int>> release(nb + 2);
+  std::vector<int> free_slots;
+  int n_slots = 0;
+  pg.blk_op0.assign(nb + 2, 0);
+  int cur_block = -1;
+  auto open_blocks_to = [&](int b) {  // op lists are emitted in block order
+    while (cur_block < b) {
+      cur_block++;
+      pg.blk_op0[cur_block] = (int)pg.ops.size();
+      if (cur_block >= 1)
+        for (int s : release[cur_block - 1]) free_slots.push_back(s);
+    }
+  };
+  for (int r = 0; r < nn; r++) {
+    int v = t.order[r];
+    if (t.left[v] < 0) continue;
+    int b = op_block[v];
+    // children are formed in an earlier-or-equal block; keep the sequence monotone
+    b = std::max(b, std::max(0, cur_block));
+    op_block[v] = b;
+    open_blocks_to(b);
+    NodeOp op{};
+    op.node = v; op.lnode = t.left[v]; op.rnode = t.right[v];
+    op.lref = t.left[op.lnode] < 0 ? -(t.leaf_pos[op.lnode] + 1) : slot[op.lnode];
+    op.rref = t.left[op.rnode] < 0 ? -(t.leaf_pos[op.rnode] + 1) : slot[op.rnode];
+    if (v == 0) { op.dst = -1; op.i0 = R; }
+    else {
+      if (free_slots.empty()) free_slots.push_back(n_slots++);
+      slot[v] = free_slots.back(); free_slots.pop_back();
+      op.dst = slot[v];
+      op.i0 = (b < nb && js0[v] < std::min(S, (b + 1) * R)) ? std::max(0, js0[v] - b * R) : R;
+    }
+    // the children's slots die with the block in which this node is formed
+    for (int c : {op.lnode, op.rnode})
+      if (slot[c] >= 0) release[std::min(b, nb)].push_back(slot[c]);
+    pg.ops.push_back(op);
+  }
+  open_blocks_to(nb);
+  pg.blk_op0[nb + 1] = (int)pg.ops.size();
+  pg.n_slots = std::max(n_slots, 1);
+
+  // entries
+  std::vector<std::vector<uint32_t>> ent(nb);
+  std::vector<std::vector<int32_t>> entn(nb);
+  for (int v = 1; v < nn; v++) {
+    if (js0[v] >= js1[v]) continue;
+    int ref = t.left[v] < 0 ? -(t.leaf_pos[v] + 1) : slot[v];
+    if (ref < -32768 || ref > 32767) throw std::runtime_error("program: tree too large for 16-bit lineage references");
+    for (int b = js0[v] / R; b <= (js1[v] - 1) / R; b++) {
+      int jb = b * R, je = std::min(S, jb + R);
+      int i0 = std::max(js0[v], jb) - jb, i1 = std::min(js1[v], je) - jb;
+      ent[b].push_back(((uint32_t)(uint16_t)(int16_t)ref) | ((uint32_t)i0 << 16) | ((uint32_t)i1 << 24));
+      entn[b].push_back(v);
+    }
+  }
+  pg.blk_ent0.assign(nb + 1, 0);
+  double fp64 = 0;
+  for (int b = 0; b < nb; b++) {
+    pg.blk_ent0[b] = (int)pg.entries.size();
+    std::vector<int> idx(ent[b].size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    auto key = [&](int i) {
+      uint32_t e = ent[b][i];
+      int i0 = (e >> 16) & 0xff, i1 = (e >> 24) & 0xff;
+      bool partial = !(i0 == 0 && i1 == R);
+      bool is_slot = (int16_t)(e & 0xffff) >= 0;
+      return std::make_tuple(partial, is_slot, (int)(int16_t)(e & 0xffff));
+    };
+    std::sort(idx.begin(), idx.end(), [&](int a, int c) { return key(a) < key(c); });
+    for (int i : idx) {
+      uint32_t e = ent[b][i];
+      int i0 = (e >> 16) & 0xff, i1 = (e >> 24) & 0xff;
+      if (i0 == 0 && i1 == R) pg.n_full++; else pg.n_partial++;
+      fp64 += 1 + 2 * (i1 - i0);
+      pg.entries.push_back(e);
+      pg.entry_node.push_back(entn[b][i]);
+    }
+  }
+  pg.blk_ent0[nb] = (int)pg.entries.size();
+  // + node ops (8 merge + 2 renorm + 4 class adds), block ends (~3 per slice), epilogue (~60)
+  pg.fp64_instr_per_eval = fp64 + 14.0 * (nl - 1) + 3.0 * S + 60;
+  return pg;
+}
+
+}  // namespace ppm

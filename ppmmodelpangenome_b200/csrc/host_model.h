@@ -1,0 +1,76 @@
+// Host-side model of the PPM likelihood engine: Newick -> flat preorder arrays, 0/1 matrix -> bit-packed
+// deduplicated patterns, and the topology-only "sweep program" the CUDA kernels execute.
+// Mirrors what Inference::Inference builds (reference source/functions.cpp:76-156) -- see host_model.cpp.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ppm {
+
+struct Tree {
+  int n_nodes = 0, n_leaves = 0;
+  std::vector<int> left, right, parent;  // preorder ids (objects.cpp:104-114); -1 = none
+  std::vector<double> bl;                // branch above node (functions.cpp:95-96); bl[0] = 0
+  std::vector<std::string> label;        // leaf labels, "" for internal nodes (objects.cpp:141-149)
+  std::vector<double> height;            // H - depth (functions.cpp:106-109)
+  std::vector<int> order, rank;          // nodes by increasing height (functions.cpp:112-114) and its inverse
+  std::vector<int> last;                 // largest preorder id inside the subtree of each node
+  std::vector<int> leaf_pos;             // node -> bit position (k-th leaf in preorder), -1 internal
+  std::vector<int> leaf_node;            // bit position -> node id
+  int bfs_last = 0;                      // last node of a breadth-first walk (computeMRCA of an empty pattern)
+  double H = 0, L = 0;                   // functions.cpp:108, objects.cpp:115-122
+  // Mobile integral grid (functions.cpp:250-260)
+  std::vector<int> nsub;                 // [n_nodes-1] slices of interval rank (0 where skipped)
+  std::vector<int> slice_start;          // [n_nodes] prefix sums of nsub
+  std::vector<int> alive;                // [n_nodes-1] |subtrees[rank]| (functions.cpp:130-141)
+  std::vector<double> slice_t, slice_wt; // [S] midpoint times and weights w/nSub
+  int n_slices = 0;
+  int64_t n_terms = 0;                   // W
+};
+
+Tree parse_newick(const std::string& first_line);
+Tree tree_from_arrays(int n_nodes, const int32_t* left, const int32_t* right, const double* bl);
+Tree read_tree_file(const std::string& path);
+
+struct Patterns {
+  int n_words = 0;
+  int64_t n_genes = 0, n_patterns = 0, n_obs = 0;
+  std::vector<uint32_t> words;        // [n_patterns][n_words] row-major, bit k = k-th leaf in preorder
+  std::vector<int32_t> counts, mrca, freq;
+  std::vector<int32_t> gene_to_pattern;
+  double mean_genes = 0;
+};
+
+// rows: n_rows x n_words packed rows; counts may be null (all ones)
+Patterns build_patterns(const Tree& t, const uint32_t* rows, const int32_t* counts, int64_t n_rows, bool dedupe);
+Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe);
+
+// ---- sweep program ---------------------------------------------------------------------------------------
+// The tree is swept once in height order.  Slices of the Mobile integral are grouped into blocks of at most
+// R consecutive slices; before a block runs, every node born before the block's last slice is merged from
+// its children ("node op"); then every lineage alive somewhere in the block contributes one "entry".
+struct NodeOp {
+  int32_t node;         // preorder id of the node being formed
+  int32_t lnode, rnode; // preorder ids of its children (index the per-parameter node tables)
+  int32_t lref, rref;   // >=0: slot holding the child's Mobile partials; <0: leaf, bit position = -(ref+1)
+  int32_t dst;          // slot of the new node, -1 for the root (never alive in an interval)
+  int32_t i0;           // first slice of the current block at which the node is alive (0..R); R = none
+  int32_t pad;
+};
+struct Program {
+  int R = 8;
+  int n_blocks = 0, n_slots = 0;
+  std::vector<int32_t> blk_slice0, blk_nslices;   // [n_blocks]
+  std::vector<int32_t> blk_op0;                   // [n_blocks+2] node ops before block b: [op0[b], op0[b+1]); tail ops after the last block
+  std::vector<int32_t> blk_ent0;                  // [n_blocks+1]
+  std::vector<NodeOp> ops;
+  std::vector<uint32_t> entries;                  // ref(16 bit signed) | i0<<16 | i1<<24
+  std::vector<int32_t> entry_node;                // node id of each entry (for the K table)
+  int64_t n_full = 0, n_partial = 0;
+  // modelled FP64 instruction count per pattern-eval of the main kernel
+  double fp64_instr_per_eval = 0;
+};
+Program build_program(const Tree& t, int R);
+
+}  // namespace ppm

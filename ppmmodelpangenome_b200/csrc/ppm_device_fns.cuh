@@ -1,0 +1,357 @@
+// Device functions of the PPM likelihood engine, written once as __host__ __device__ so that the very same
+// source is (1) the body of the CUDA kernels in ppm_kernels.cu and (2) compiled by g++ into the single-lane
+// emulator under tests/emu/, which lets the CPU-only test tier check the kernel arithmetic against the
+// oracle.  The product library (libppm_b200.so) contains ONLY the CUDA instantiation: there is no host path.
+#pragma once
+#include "ppm_kernels.cuh"
+
+#include <cmath>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define PPM_HD __host__ __device__ __forceinline__
+#else
+#define PPM_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define PPM_LANES 32
+#define ppm_syncwarp() __syncwarp()
+#define ppm_ballot(pred) __ballot_sync(0xffffffffu, (pred))
+#define ppm_any(pred) __any_sync(0xffffffffu, (pred))
+#define ppm_hiloint2double(hi, lo) __hiloint2double((hi), (lo))
+#define ppm_double2hiint(x) __double2hiint(x)
+#else  // single-lane emulation
+#define PPM_LANES 1
+#define ppm_syncwarp() ((void)0)
+#define ppm_ballot(pred) ((pred) ? 1u : 0u)
+#define ppm_any(pred) (pred)
+static inline double ppm_hiloint2double(int hi, int lo) {
+  unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double d; std::memcpy(&d, &u, 8); return d;
+}
+static inline int ppm_double2hiint(double x) {
+  unsigned long long u; std::memcpy(&u, &x, 8); return (int)(u >> 32);
+}
+#endif
+
+namespace ppm {
+
+// ------------------------------------------------------------------------------------------------ helpers
+PPM_HD double lse2(double a, double b) {  // logSumExp (objects.cpp:21-33) without the +-100 cut
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  double m = fmax(a, b), d = fmin(a, b) - m;
+  return m + log1p(exp(d));
+}
+PPM_HD double pow2i(int k) {  // 2^k for k in [-1022, 1023]
+  return ppm_hiloint2double((1023 + k) << 20, 0);
+}
+PPM_HD int biased_exp(double x) { return (ppm_double2hiint(x) >> 20) & 0x7ff; }
+
+// ------------------------------------------------------------------------------------------------ prepass
+// One thread per parameter vector: per-node tables that need a tree recursion (zero-row pruning of the two
+// pure-loss categories, getPobs1, likUpper1).  Serial in the nodes; it is O(1 pattern) of work.
+PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p) {
+  const double* par = t.params + 8 * (size_t)p;
+  const double l0 = par[1], l1 = par[3], g2 = par[4], l2 = par[5], e2 = par[6], e1 = par[7];
+  const int nn = m.n_nodes;
+  double4* cls = t.cls + (size_t)p * nn;
+  double2* kap = t.kap + (size_t)p * nn;
+  double2* d1u = t.d1u + (size_t)p * nn;
+  double* z0 = t.zeta + (size_t)p * 2 * nn;
+  double* z1 = z0 + nn;
+  double* sc = t.scal + (size_t)p * SC_COUNT;
+
+  const double lam = g2 + l2;
+  const double pi1 = (g2 == 0.) ? 0. : g2 / lam;           // functions.cpp:227-231
+  const double pi0 = (g2 == 0.) ? 1. : l2 / lam;
+  const double log_e2 = log(e2), log_1me2 = log(1 - e2);
+
+  // bottom-up (children have larger preorder ids): zero-row log p1 per node, branch factor tables
+  for (int v = nn - 1; v >= 0; v--) {
+    const bool leaf = m.left[v] < 0;
+    double zl0, zl1;  // log P(all-zero below v | present at v) for l0 / l1      (objects.cpp:404-426 on the zero row)
+    if (leaf) { zl0 = log_e2; zl1 = log_e2; }
+    else {
+      int a = m.left[v], b = m.right[v];
+      zl0 = cls[a].y + cls[b].y;
+      zl1 = cls[a].w + cls[b].w;
+    }
+    z0[v] = zl0; z1[v] = zl1;
+    const double bl = m.bl[v];
+    double4 c;
+    // active branch (a present leaf below): survive the branch; a leaf adds its own log(1-e2)   (objects.cpp:408,423)
+    c.x = -l0 * bl + (leaf ? log_1me2 : 0.);
+    c.z = -l1 * bl + (leaf ? log_1me2 : 0.);
+    // frontier branch (all-zero subtree under an active parent): lost on the branch, or kept and unobserved
+    c.y = lse2(log(1 - exp(-l0 * bl)), -l0 * bl + zl0);
+    c.w = lse2(log(1 - exp(-l1 * bl)), -l1 * bl + zl1);
+    if (v == 0) c = make_double4(0., 0., 0., 0.);
+    cls[v] = c;
+    const double E = exp(-lam * bl);
+    kap[v] = make_double2(pi1 * E, pi0 * E);
+  }
+  // computeI2 pieces that do not need the Mobile integral (functions.cpp:337-341, 284-299)
+  double p0 = (l0 == 0.) ? 1 - pow(e2, (double)m.n_leaves) : 1 - exp(z0[0]);
+  double p1 = 1 - exp(z1[0]);
+  double A = 0;
+  for (int v = 1; v < nn; v++) {
+    double lost = 1 - exp(-l1 * m.bl[v]);
+    A += (m.left[v] < 0) ? lost * (1 - e2) : lost * (1 - exp(z1[v]));
+  }
+  A /= l1;
+  // top-down: U (likUpper1, functions.cpp:176-209, as the recursion U(v) = lost_v + sigma_v*T(sib)*U(parent),
+  // U(child of root) = lost_v) and V(v) = prod over the path of sigma_c*T(sib c) in log domain.
+  // z0 is reused as log V, z1 as U (both only needed for ancestors, which precede v in preorder).
+  z0[0] = 0.; z1[0] = 0.;
+  d1u[0] = make_double2(0., -INFINITY);
+  for (int v = 1; v < nn; v++) {
+    int par_ = m.parent[v];
+    int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];
+    double sig = exp(-l1 * m.bl[v]);
+    double U = (1 - sig) + sig * exp(cls[sib].w) * z1[par_];
+    double logV = z0[par_] + (-l1 * m.bl[v]) + cls[sib].w;
+    z1[v] = U; z0[v] = logV;
+    double logU = log(U);
+    d1u[v] = make_double2(lse2(logV, logU) - logV, logU);
+  }
+  sc[SC_PI1] = pi1;
+  double m0 = 1 - e1, m1 = e2;           // leaf observed 0 (objects.cpp:407-408)
+  sc[SC_LD0] = m1 - m0; sc[SC_LA0] = m0 + pi1 * (m1 - m0);
+  m0 = e1; m1 = 1 - e2;                  // leaf observed 1
+  sc[SC_LD1] = m1 - m0; sc[SC_LA1] = m0 + pi1 * (m1 - m0);
+  sc[SC_P0] = p0; sc[SC_P1] = p1; sc[SC_A] = A;
+  sc[SC_LOG1ME2] = log_1me2;
+  sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
+  sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
+}
+
+// One thread per (parameter vector, entry or slice): the exp tables of the Mobile integral.
+PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, int i) {
+  const double* par = t.params + 8 * (size_t)p;
+  const double g2 = par[4], l2 = par[5];
+  const double lam = g2 + l2;
+  const double pi1 = (g2 == 0.) ? 0. : g2 / lam;
+  if (i < m.n_entries) {
+    int b = m.entry_block[i];
+    double tb = m.slice_t[m.blk_slice0[b]];
+    double hs = m.height[m.entry_node[i]];
+    t.kent[(size_t)p * m.n_entries + i] = pi1 * exp(-lam * (tb - hs));
+  } else if (i < m.n_entries + m.n_slices) {
+    int j = i - m.n_entries;
+    double tb = m.slice_t[(j / m.R) * m.R];
+    t.yy[(size_t)p * m.n_slices + j] = exp(-lam * (m.slice_t[j] - tb));
+  }
+}
+
+// i2 and the three log prefactors (functions.cpp:342-343, 348, 354, 356)
+PPM_HD void prepass_i2_body(const ModelDev& m, const TablesDev& t, const double* i2_override, int p) {
+  const double* par = t.params + 8 * (size_t)p;
+  double* sc = t.scal + (size_t)p * SC_COUNT;
+  const double N0 = par[0], i1 = par[2], l1 = par[3];
+  double IZ = sc[SC_IZ_M] == 0. ? 0. : ldexp(sc[SC_IZ_M], -(int)sc[SC_IZ_E]);
+  double B = m.H - IZ;
+  double i2 = ((double)m.n_obs - N0 * sc[SC_P0] - i1 / l1 * sc[SC_P1] - i1 * sc[SC_A]) / B;
+  sc[SC_B] = B;
+  if (i2_override) i2 = i2_override[p];
+  sc[SC_I2] = i2;
+  sc[SC_C0] = log(N0 / (double)m.n_obs);
+  sc[SC_C1] = log(i1 / (l1 * (double)m.n_obs));
+  sc[SC_C2] = log(i2 / (double)m.n_obs);
+}
+
+// ------------------------------------------------------------------------------------------------ sweep
+template <bool SMEM_SLOTS>
+struct SlotStore {
+  double2* base;  // [slot][32]
+  PPM_HD double2 ld(int slot, int lane) const { return base[slot * PPM_LANES + lane]; }
+  PPM_HD void st(int slot, int lane, double2 v) const { base[slot * PPM_LANES + lane] = v; }
+};
+
+// One work item = 32 patterns (one per lane) x one parameter vector.  Returns this lane's count*log-mixture.
+// sw: per-warp pattern words [n_words][PPM_LANES]; zw: per-warp all-zero-subtree masks per slot.
+template <int R, class Slots>
+PPM_HD double sweep_item(const SweepArgs& a, long long item, int lane, uint32_t* sw, uint32_t* zw, const Slots& slots) {
+  const ModelDev& m = a.m;
+  const int p = (int)(item / a.n_batches);
+  const long long batch = item % a.n_batches;
+  const double* sc = a.t.scal + (size_t)p * SC_COUNT;
+  const bool skip = (a.mode == 0) && !a.force && (sc[SC_I2] < 0.);  // penalty branch: no pattern work (functions.cpp:362-364)
+
+  const long long pat = a.first + batch * PPM_LANES + lane;
+  const bool active = pat < a.first + a.count;
+  double contrib = 0.;
+
+  if (!skip) {
+    for (int w = 0; w < m.n_words; w++) {
+      const uint32_t* src = (a.mode == 1) ? m.zero_words : m.words + (size_t)w * m.n_pat_pad;
+      sw[w * PPM_LANES + lane] = (a.mode == 1) ? 0u : (active ? src[pat] : 0u);
+    }
+    ppm_syncwarp();
+
+    const double pi1 = sc[SC_PI1];
+    const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
+    const double4* cls = a.t.cls + (size_t)p * m.n_nodes;
+    const double2* kap = a.t.kap + (size_t)p * m.n_nodes;
+    const double* kent = a.t.kent + (size_t)p * m.n_entries;
+    const double* yy = a.t.yy + (size_t)p * m.n_slices;
+
+    double A0 = 0., A1 = 0.;  // log p1(root) of the two pure-loss categories
+    int X = 0;                // sum of renormalisation shifts of all lineages formed so far
+    double Im = 0.; int Ie = 0;  // Mobile integral = Im * 2^-Ie
+
+    double prod[R], Y[R];
+    int ex[R];
+
+    for (int b = 0; b <= m.n_blocks; b++) {
+      const bool real = b < m.n_blocks;
+      int nsl = 0, j0 = 0;
+      if (real) {
+        nsl = m.blk_nslices[b]; j0 = m.blk_slice0[b];
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          prod[i] = 1.; ex[i] = X;
+          Y[i] = (i < nsl) ? yy[j0 + i] : 0.;
+        }
+      }
+      // ---- node ops: form every node born before the end of this block
+      const int op_end = m.blk_op0[b + 1];
+      for (int o = m.blk_op0[b]; o < op_end; o++) {
+        const NodeOpDev op = m.ops[o];
+        double2 L, Rr;
+        uint32_t zwl, zwr;
+        if (op.lref < 0) {
+          int pos = -(op.lref + 1);
+          bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
+          L = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
+          zwl = ~ppm_ballot(bit);
+        } else { L = slots.ld(op.lref, lane); zwl = zw[op.lref]; }
+        if (op.rref < 0) {
+          int pos = -(op.rref + 1);
+          bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
+          Rr = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
+          zwr = ~ppm_ballot(bit);
+        } else { Rr = slots.ld(op.rref, lane); zwr = zw[op.rref]; }
+        const uint32_t zwv = zwl & zwr;
+        // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
+        {
+          const bool zl = (zwl >> lane) & 1u, zr = (zwr >> lane) & 1u;
+          const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
+          const double4 cl = cls[op.lnode], cr = cls[op.rnode];
+          A0 += zl ? (zv ? 0. : cl.y) : cl.x;
+          A1 += zl ? (zv ? 0. : cl.w) : cl.z;
+          A0 += zr ? (zv ? 0. : cr.y) : cr.x;
+          A1 += zr ? (zv ? 0. : cr.w) : cr.z;
+        }
+        if (op.dst >= 0) {
+          // Mobile merge (objects.cpp:427-435 in linear domain)
+          const double2 kl = kap[op.lnode], kr = kap[op.rnode];
+          double m0 = fma(-kl.x, L.y, L.x) * fma(-kr.x, Rr.y, Rr.x);
+          double m1 = fma(kl.y, L.y, L.x) * fma(kr.y, Rr.y, Rr.x);
+          double d = m1 - m0;
+          double av = fma(pi1, d, m0);
+          // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
+          int be = biased_exp(fmax(fabs(av), fabs(d)));
+          int k = (be != 0 && be < 1023 - 40) ? 1022 - be : 0;
+          if (ppm_any(k != 0)) {
+            double s = pow2i(k);
+            av *= s; d *= s;
+            X += k;
+            if (real) {
+#pragma unroll
+              for (int i = 0; i < R; i++) if (i >= op.i0) ex[i] += k;
+            }
+          }
+          ppm_syncwarp();
+          slots.st(op.dst, lane, make_double2(av, d));
+          if (lane == 0) zw[op.dst] = zwv;
+          ppm_syncwarp();
+        }
+      }
+      if (!real) break;
+      // ---- entries: every lineage alive somewhere in this block
+      const int e_end = m.blk_ent0[b + 1];
+      int since = 0;
+      for (int e = m.blk_ent0[b]; e < e_end; e++) {
+        const uint32_t code = m.entries[e];
+        const int ref = (int)(short)(code & 0xffffu);
+        const int i0 = (code >> 16) & 0xff, i1 = (code >> 24) & 0xff;
+        double2 ad;
+        if (ref < 0) {
+          int pos = -(ref + 1);
+          bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
+          ad = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
+        } else ad = slots.ld(ref, lane);
+        const double bb = ad.y * kent[e];
+        if (i0 == 0 && i1 == R) {
+#pragma unroll
+          for (int i = 0; i < R; i++) prod[i] *= fma(-bb, Y[i], ad.x);
+        } else {
+#pragma unroll
+          for (int i = 0; i < R; i++)
+            if (i >= i0 && i < i1) prod[i] *= fma(-bb, Y[i], ad.x);
+        }
+        if (++since == 16) {  // keep the running products away from the denormal range
+          since = 0;
+          int mn = 2047;
+#pragma unroll
+          for (int i = 0; i < R; i++) { int be = biased_exp(prod[i]); int bq = be == 0 ? 2047 : be; mn = bq < mn ? bq : mn; }
+          if (ppm_any(mn < 1023 - 480)) {
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+              int be = biased_exp(prod[i]);
+              if (be != 0 && be < 1023 - 480) { prod[i] *= pow2i(480); ex[i] += 480; }
+            }
+          }
+        }
+      }
+      // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        if (i < nsl) {
+          double v = prod[i] * m.slice_wt[j0 + i];
+          if (v != 0.) {
+            int e = ex[i];
+            if (Im == 0.) { Im = v; Ie = e; }
+            else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
+            else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
+          }
+        }
+      }
+    }
+
+    if (a.mode == 1) {
+      if (active) {
+        double* scw = a.t.scal + (size_t)p * SC_COUNT;
+        // renormalise the mantissa so that ldexp in prepass_i2 stays in range
+        scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
+      }
+      return 0.;
+    }
+    // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
+    if (active) {
+      const double lik0 = sc[SC_C0] + A0;
+      const int mr = m.mrca[pat];
+      const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];
+      double lik1;
+      if (m.freq[pat] == 0) lik1 = lse2(sc[SC_C1] + A1, sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
+      else lik1 = sc[SC_C1] + (A1 + du.x);
+      const double lik2 = (Im > 0.) ? sc[SC_C2] + (log(Im) - (double)Ie * 0.693147180559945309417232) : -INFINITY;
+      double mx = fmax(lik0, fmax(lik1, lik2));
+      double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));
+      contrib = tot * (double)m.counts[pat];
+      if (a.mode == 2) {
+        int c = 0;
+        if (lik1 > lik0) c = 1;
+        if (lik2 > (c ? lik1 : lik0)) c = 2;
+        long long r = pat - a.first;
+        if (a.cat) a.cat[r] = (signed char)c;
+        if (a.comp) { a.comp[3 * r] = lik0; a.comp[3 * r + 1] = lik1; a.comp[3 * r + 2] = lik2; }
+      }
+    }
+  }
+  return contrib;
+}
+
+}  // namespace ppm

@@ -1,0 +1,443 @@
+// Engine object behind the C ABI of include/ppm_b200.h: owns the device copy of the model, the per-launch
+// parameter tables, a stream and timing events.  No CPU fallback: every compute entry point needs an sm_100 GPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ppm_b200.h"
+#include "host_model.h"
+#include "ppm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    if (count <= n) return;
+    release();
+    CK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    n = count;
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s) {
+    alloc(v.size());
+    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct ppm_engine {
+  ppm::Tree tree;
+  ppm::Patterns pat;
+  ppm::Program prog;
+  int device = 0, n_sm = 148;
+  int shard_rank = 0, shard_world = 1;
+  long long first = 0, count = 0;  // this shard's pattern slice
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  double n_launches = 0;
+
+  // device model
+  DevBuf<int> d_left, d_right, d_parent, d_blk_slice0, d_blk_nslices, d_blk_op0, d_blk_ent0, d_entry_node, d_entry_block;
+  DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt;
+  DevBuf<ppm::NodeOpDev> d_ops;
+  DevBuf<uint32_t> d_entries, d_words, d_zero_words;
+  DevBuf<int> d_counts, d_mrca, d_freq;
+  long long n_pat_pad = 0;
+  ppm::ModelDev md{};
+
+  // per-launch tables
+  int P_cap = 0;
+  DevBuf<double> d_params, d_kent, d_yy, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
+  DevBuf<double4> d_cls;
+  DevBuf<double2> d_kap, d_d1u, d_gslots;
+  DevBuf<signed char> d_cat;
+  size_t partial_cap = 0;
+
+  ~ppm_engine() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  void init_device(int dev) {
+    device = dev;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (dev < 0 || dev >= ndev) throw CudaError("no CUDA device with ordinal " + std::to_string(dev));
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (this library carries sm_100a code only)");
+    n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+  }
+
+  void upload_model() {
+    prog = ppm::build_program(tree, 8);
+    // shard: contiguous, equal-sized slices of the deduplicated patterns (work per pattern is uniform)
+    long long np = pat.n_patterns;
+    first = np * shard_rank / shard_world;
+    count = np * (shard_rank + 1) / shard_world - first;
+    d_left.upload(tree.left, stream); d_right.upload(tree.right, stream); d_parent.upload(tree.parent, stream);
+    d_bl.upload(tree.bl, stream); d_height.upload(tree.height, stream);
+    d_slice_t.upload(tree.slice_t, stream); d_slice_wt.upload(tree.slice_wt, stream);
+    d_blk_slice0.upload(prog.blk_slice0, stream); d_blk_nslices.upload(prog.blk_nslices, stream);
+    d_blk_op0.upload(prog.blk_op0, stream); d_blk_ent0.upload(prog.blk_ent0, stream);
+    std::vector<ppm::NodeOpDev> ops(prog.ops.size());
+    static_assert(sizeof(ppm::NodeOpDev) == sizeof(ppm::NodeOp), "NodeOp layout");
+    if (!ops.empty()) std::memcpy(ops.data(), prog.ops.data(), ops.size() * sizeof(ppm::NodeOp));
+    d_ops.upload(ops, stream);
+    d_entries.upload(prog.entries, stream);
+    d_entry_node.upload(prog.entry_node, stream);
+    std::vector<int> eb(prog.entries.size());
+    for (int b = 0; b < prog.n_blocks; b++)
+      for (int e = prog.blk_ent0[b]; e < prog.blk_ent0[b + 1]; e++) eb[e] = b;
+    d_entry_block.upload(eb, stream);
+    // patterns of this shard, word-major so that lanes (= consecutive patterns) read consecutive addresses
+    n_pat_pad = (count + 31) / 32 * 32;
+    std::vector<uint32_t> wm((size_t)pat.n_words * std::max<long long>(n_pat_pad, 32), 0u);
+    for (long long j = 0; j < count; j++)
+      for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * n_pat_pad + j] = pat.words[(size_t)(first + j) * pat.n_words + w];
+    d_words.upload(wm, stream);
+    std::vector<uint32_t> zeros((size_t)pat.n_words * 32, 0u);
+    d_zero_words.upload(zeros, stream);
+    std::vector<int> c(pat.counts.begin() + first, pat.counts.begin() + first + count);
+    std::vector<int> mr(pat.mrca.begin() + first, pat.mrca.begin() + first + count);
+    std::vector<int> fr(pat.freq.begin() + first, pat.freq.begin() + first + count);
+    d_counts.upload(c, stream); d_mrca.upload(mr, stream); d_freq.upload(fr, stream);
+    CK(cudaStreamSynchronize(stream));
+
+    md.n_nodes = tree.n_nodes; md.n_leaves = tree.n_leaves; md.n_words = pat.n_words; md.n_slices = tree.n_slices;
+    md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entries.size();
+    md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
+    md.left = d_left.p; md.right = d_right.p; md.parent = d_parent.p; md.bl = d_bl.p; md.height = d_height.p;
+    md.slice_t = d_slice_t.p; md.slice_wt = d_slice_wt.p;
+    md.blk_slice0 = d_blk_slice0.p; md.blk_nslices = d_blk_nslices.p; md.blk_op0 = d_blk_op0.p; md.blk_ent0 = d_blk_ent0.p;
+    md.ops = d_ops.p; md.entries = d_entries.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
+    md.words = d_words.p; md.n_pat = count; md.n_pat_pad = n_pat_pad;
+    md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
+  }
+
+  ppm::TablesDev tables(int P, const double* d_par) {
+    if (P > P_cap) {
+      size_t nn = tree.n_nodes;
+      d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
+      d_kent.alloc((size_t)P * std::max<size_t>(prog.entries.size(), 1)); d_yy.alloc((size_t)P * std::max(tree.n_slices, 1));
+      d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 2 * nn);
+      d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
+      P_cap = P;
+    }
+    ppm::TablesDev t{};
+    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.kent = d_kent.p; t.yy = d_yy.p;
+    t.scal = d_scal.p; t.zeta = d_zeta.p;
+    return t;
+  }
+
+  // prepass + zero row + i2 (functions.cpp:334-344).  After this, scal[p] is complete.
+  void run_prepass(const ppm::TablesDev& t, const double* d_i2_ovr, cudaStream_t s) {
+    ppm::launch_prepass_nodes(md, t, s);
+    ppm::launch_prepass_tables(md, t, s);
+    ppm::SweepArgs z{};
+    z.m = md; z.t = t; z.mode = 1; z.first = 0; z.count = 1; z.n_batches = 1; z.n_items = t.P; z.force = 1;
+    int wpc; size_t smem; bool ss;
+    int gx = ppm::sweep_grid_x(md, z.n_items, n_sm, &wpc, &smem, &ss);
+    if (!ss) { d_gslots.alloc((size_t)std::max(gx, n_sm * 2) * 8 * prog.n_slots * 32); z.gslots = d_gslots.p; }
+    ppm::launch_sweep(z, gx, wpc, smem, ss, s);
+    ppm::launch_prepass_i2(md, t, d_i2_ovr, s);
+    n_launches += 4;
+  }
+
+  // mode 0: partial sums into d_out[P]; mode 2: categories/components for P == 1
+  void run_sweep(const ppm::TablesDev& t, int mode, double* d_out, signed char* d_cat_out, double* d_comp_out, cudaStream_t s) {
+    ppm::SweepArgs a{};
+    a.m = md; a.t = t; a.mode = mode; a.first = 0; a.count = count;
+    a.n_batches = (count + 31) / 32; a.n_items = a.n_batches * t.P;
+    a.cat = d_cat_out; a.comp = d_comp_out; a.force = (mode == 2);
+    size_t need = (size_t)std::max<long long>(a.n_items, 1);
+    if (need > partial_cap) { d_partial.alloc(need); partial_cap = need; }
+    a.partial = d_partial.p;
+    if (a.n_items > 0) {
+      int wpc; size_t smem; bool ss;
+      int gx = ppm::sweep_grid_x(md, a.n_items, n_sm, &wpc, &smem, &ss);
+      if (!ss) { d_gslots.alloc((size_t)std::max(gx, n_sm * 2) * 8 * prog.n_slots * 32); a.gslots = d_gslots.p; }
+      CK(cudaEventRecord(ev0, s));
+      ppm::launch_sweep(a, gx, wpc, smem, ss, s);
+      CK(cudaEventRecord(ev1, s));
+      timed = true;
+      n_launches += 1;
+    }
+    ppm::launch_reduce(d_partial.p, t.P, (int)a.n_batches, d_out, s);
+    n_launches += 1;
+    CK(cudaGetLastError());
+  }
+
+  void extract_i2(const ppm::TablesDev& t, double* d_i2_out, double* d_parts_out, cudaStream_t s) {
+    // strided copies out of scal
+    if (d_i2_out)
+      CK(cudaMemcpy2DAsync(d_i2_out, sizeof(double), d_scal.p + ppm::SC_I2, ppm::SC_COUNT * sizeof(double), sizeof(double), t.P,
+                           cudaMemcpyDeviceToDevice, s));
+    if (d_parts_out) {  // p0 p1 A B are contiguous in scal
+      CK(cudaMemcpy2DAsync(d_parts_out, 4 * sizeof(double), d_scal.p + ppm::SC_P0, ppm::SC_COUNT * sizeof(double), 4 * sizeof(double),
+                           t.P, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------- C ABI
+#define GUARD_BEGIN try { if (h->device < 0) { h->err = "host-only handle (created with device < 0): no compute"; return PPM_ESTATE; }
+#define GUARD_END(h)                                                  \
+  }                                                                   \
+  catch (const CudaError& e) { (h)->err = e.what(); return PPM_ECUDA; } \
+  catch (const std::bad_alloc&) { (h)->err = "out of host memory"; return PPM_ENOMEM; } \
+  catch (const std::exception& e) { (h)->err = e.what(); return PPM_EINVAL; }
+
+static int finish_create(ppm_handle* out, std::unique_ptr<ppm_engine>& e, int device, int rank, int world) {
+  if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad shard rank/world");
+  e->shard_rank = rank; e->shard_world = world;
+  if (device < 0) {  // host-only handle: model inspection, no compute
+    e->device = -1;
+    e->prog = ppm::build_program(e->tree, 8);
+    long long np = e->pat.n_patterns;
+    e->first = np * rank / world;
+    e->count = np * (rank + 1) / world - e->first;
+  } else {
+    e->init_device(device);
+    e->upload_model();
+  }
+  *out = e.release();
+  return PPM_OK;
+}
+
+extern "C" {
+
+int ppm_create(ppm_handle* out, const ppm_tree* tree, const uint32_t* packed, const int32_t* counts, int64_t n_patterns,
+               int dedupe, int device, int shard_rank, int shard_world) {
+  if (!out || !tree || !packed) { g_create_error = "null argument"; return PPM_EINVAL; }
+  *out = nullptr;
+  std::unique_ptr<ppm_engine> e(new ppm_engine);
+  try {
+    e->tree = ppm::tree_from_arrays(tree->n_nodes, tree->left, tree->right, tree->branch_len);
+    e->pat = ppm::build_patterns(e->tree, packed, counts, n_patterns, dedupe != 0);
+    return finish_create(out, e, device, shard_rank, shard_world);
+  } catch (const CudaError& x) { g_create_error = x.what(); return PPM_ECUDA; }
+  catch (const std::bad_alloc&) { g_create_error = "out of host memory"; return PPM_ENOMEM; }
+  catch (const std::exception& x) { g_create_error = x.what(); return PPM_EINVAL; }
+}
+
+int ppm_create_from_files(ppm_handle* out, const char* tree_path, const char* matrix_path, int dedupe, int device,
+                          int shard_rank, int shard_world) {
+  if (!out || !tree_path || !matrix_path) { g_create_error = "null argument"; return PPM_EINVAL; }
+  *out = nullptr;
+  std::unique_ptr<ppm_engine> e(new ppm_engine);
+  try {
+    try {
+      e->tree = ppm::read_tree_file(tree_path);
+      e->pat = ppm::read_matrix_file(e->tree, matrix_path, dedupe != 0);
+    } catch (const std::runtime_error& x) {
+      g_create_error = x.what();
+      return (g_create_error.rfind("cannot open", 0) == 0) ? PPM_EIO : PPM_EINVAL;
+    }
+    return finish_create(out, e, device, shard_rank, shard_world);
+  } catch (const CudaError& x) { g_create_error = x.what(); return PPM_ECUDA; }
+  catch (const std::bad_alloc&) { g_create_error = "out of host memory"; return PPM_ENOMEM; }
+  catch (const std::exception& x) { g_create_error = x.what(); return PPM_EINVAL; }
+}
+
+void ppm_destroy(ppm_handle h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  delete h;
+}
+
+const char* ppm_last_error(ppm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ppm_get_info(ppm_handle h, ppm_info* o) {
+  if (!h || !o) return PPM_EINVAL;
+  o->n_nodes = h->tree.n_nodes; o->n_leaves = h->tree.n_leaves;
+  o->n_genes = h->pat.n_genes; o->n_patterns = h->pat.n_patterns; o->n_obs = h->pat.n_obs;
+  o->n_words = h->pat.n_words; o->n_slices = h->tree.n_slices; o->n_terms = h->tree.n_terms;
+  o->H = h->tree.H; o->L = h->tree.L; o->mean_genes = h->pat.mean_genes;
+  o->device = h->device; o->shard_rank = h->shard_rank; o->shard_world = h->shard_world;
+  o->shard_first = h->first; o->shard_count = h->count;
+  return PPM_OK;
+}
+
+int ppm_get_int_array(ppm_handle h, int which, int32_t* out, int64_t cap) {
+  if (!h || !out) return PPM_EINVAL;
+  const std::vector<int32_t>* v = nullptr;
+  std::vector<int32_t> tmp;
+  switch (which) {
+    case 0: v = &h->pat.mrca; break;
+    case 1: v = &h->pat.freq; break;
+    case 2: v = &h->pat.counts; break;
+    case 3: tmp.assign(h->tree.order.begin(), h->tree.order.end()); v = &tmp; break;
+    case 4: v = &h->pat.gene_to_pattern; break;
+    case 5: tmp.assign(h->tree.nsub.begin(), h->tree.nsub.end()); v = &tmp; break;
+    case 6: tmp.assign(h->tree.alive.begin(), h->tree.alive.end()); v = &tmp; break;
+    default: h->err = "unknown int array"; return PPM_EINVAL;
+  }
+  if ((int64_t)v->size() > cap) { h->err = "output buffer too small"; return PPM_EINVAL; }
+  std::copy(v->begin(), v->end(), out);
+  return PPM_OK;
+}
+
+int ppm_get_double_array(ppm_handle h, int which, double* out, int64_t cap) {
+  if (!h || !out) return PPM_EINVAL;
+  const std::vector<double>& v = which == 0 ? h->tree.height : h->tree.bl;
+  if (which < 0 || which > 1) { h->err = "unknown double array"; return PPM_EINVAL; }
+  if ((int64_t)v.size() > cap) { h->err = "output buffer too small"; return PPM_EINVAL; }
+  std::copy(v.begin(), v.end(), out);
+  return PPM_OK;
+}
+
+int ppm_loglik_device(ppm_handle h, const double* d_params, int32_t P, double* d_out_partial, double* d_out_i2, void* stream) {
+  if (!h || !d_params || !d_out_partial || P < 1) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  GUARD_BEGIN
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  h->n_launches = 0;
+  ppm::TablesDev t = h->tables(P, d_params);
+  h->run_prepass(t, nullptr, s);
+  h->run_sweep(t, 0, d_out_partial, nullptr, nullptr, s);
+  if (d_out_i2) h->extract_i2(t, d_out_i2, nullptr, s);
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_finalize_ll(const double* i2, double* ll, int32_t P) {
+  if (!i2 || !ll) return PPM_EINVAL;
+  for (int p = 0; p < P; p++)
+    if (i2[p] < 0.) ll[p] = -1e9 * 1. + i2[p];
+  return PPM_OK;
+}
+
+int ppm_finalize_ll_device(ppm_handle h, const double* d_i2, double* d_ll, int32_t P, void* stream) {
+  if (!h || !d_i2 || !d_ll) return PPM_EINVAL;
+  GUARD_BEGIN
+  CK(cudaSetDevice(h->device));
+  ppm::launch_finalize(d_i2, d_ll, P, stream ? (cudaStream_t)stream : h->stream);
+  CK(cudaGetLastError());
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, double* out_i2) {
+  if (!h || !params || !out_ll || P < 1) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  GUARD_BEGIN
+  CK(cudaSetDevice(h->device));
+  h->tables(P, nullptr);
+  CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, h->stream));
+  int rc = ppm_loglik_device(h, h->d_params.p, P, h->d_ll.p, h->d_i2.p, h->stream);
+  if (rc) return rc;
+  std::vector<double> i2(P);
+  CK(cudaMemcpyAsync(out_ll, h->d_ll.p, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(i2.data(), h->d_i2.p, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->shard_world == 1) ppm_finalize_ll(i2.data(), out_ll, P);
+  if (out_i2) std::copy(i2.begin(), i2.end(), out_i2);
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_compute_i2(ppm_handle h, const double* params, int32_t P, double* out_i2, double* out_parts) {
+  if (!h || !params || !out_i2 || P < 1) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  GUARD_BEGIN
+  CK(cudaSetDevice(h->device));
+  h->n_launches = 0;
+  h->tables(P, nullptr);
+  CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, h->stream));
+  ppm::TablesDev t = h->tables(P, h->d_params.p);
+  h->run_prepass(t, nullptr, h->stream);
+  std::vector<double> sc((size_t)P * ppm::SC_COUNT);
+  CK(cudaMemcpyAsync(sc.data(), h->d_scal.p, sc.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < P; p++) {
+    const double* s = &sc[(size_t)p * ppm::SC_COUNT];
+    out_i2[p] = s[ppm::SC_I2];
+    if (out_parts) { out_parts[4 * p] = s[ppm::SC_P0]; out_parts[4 * p + 1] = s[ppm::SC_P1]; out_parts[4 * p + 2] = s[ppm::SC_A]; out_parts[4 * p + 3] = s[ppm::SC_B]; }
+  }
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+static int eval_one(ppm_handle h, const double* params8, double i2, int8_t* out_cat_genes, double* out_comp) {
+  GUARD_BEGIN
+  CK(cudaSetDevice(h->device));
+  h->n_launches = 0;
+  h->tables(1, nullptr);
+  CK(cudaMemcpyAsync(h->d_params.p, params8, sizeof(double) * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_i2_override.p, &i2, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  ppm::TablesDev t = h->tables(1, h->d_params.p);
+  h->run_prepass(t, h->d_i2_override.p, h->stream);
+  h->d_cat.alloc((size_t)std::max<long long>(h->count, 1));
+  h->d_comp.alloc((size_t)std::max<long long>(h->count, 1) * 3);
+  h->run_sweep(t, 2, h->d_ll.p, h->d_cat.p, h->d_comp.p, h->stream);
+  if (out_comp) CK(cudaMemcpyAsync(out_comp, h->d_comp.p, sizeof(double) * 3 * h->count, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<signed char> cat(h->count);
+  if (out_cat_genes && h->count) CK(cudaMemcpyAsync(cat.data(), h->d_cat.p, h->count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (out_cat_genes)  // scatter back to the genes of the input, in input order (inf_cat.txt has one value per input row)
+    for (int64_t g = 0; g < h->pat.n_genes; g++) out_cat_genes[g] = cat[h->pat.gene_to_pattern[g]];
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_assign_cat(ppm_handle h, const double* params8, double i2, int8_t* out_cat) {
+  if (!h || !params8 || !out_cat) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  if (h->shard_world != 1) { h->err = "ppm_assign_cat needs an unsharded handle"; return PPM_ESTATE; }
+  return eval_one(h, params8, i2, out_cat, nullptr);
+}
+
+int ppm_components(ppm_handle h, const double* params8, double i2, double* out) {
+  if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  return eval_one(h, params8, i2, nullptr, out);
+}
+
+int ppm_get_counters(ppm_handle h, double* out4) {
+  if (!h || !out4) return PPM_EINVAL;
+  try {
+  out4[0] = h->n_launches;
+  float ms = 0;
+  if (h->timed) { CK(cudaEventSynchronize(h->ev1)); CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); }
+  out4[1] = ms;
+  const ppm::Tree& t = h->tree;
+  out4[2] = 5.0 * (double)t.n_terms + 28.0 * (t.n_leaves - 1) + 2.0 * t.n_slices;
+  out4[3] = h->prog.fp64_instr_per_eval;
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_measure_fp64_peak(int device, double* out_tflops) {
+  if (!out_tflops) return PPM_EINVAL;
+  double v = ppm::run_fp64_peak(device);
+  if (v <= 0) return PPM_ECUDA;
+  *out_tflops = v;
+  return PPM_OK;
+}
+
+}  // extern "C"

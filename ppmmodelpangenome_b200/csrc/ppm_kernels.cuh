@@ -1,0 +1,78 @@
+// Device-side data layout and kernel launchers of the PPM likelihood engine (sm_100a, FP64 CUDA cores).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ppm {
+
+// Per-parameter-vector scalars written by the prepass (index into ParamScal::v)
+enum {
+  SC_PI1 = 0,   // g2/(g2+l2), 0 when g2 == 0 (functions.cpp:227-231)
+  SC_LA0, SC_LD0,  // Mobile leaf partials for observation 0: a = m0 + pi1*(m1-m0), d = m1-m0
+  SC_LA1, SC_LD1,  // ... observation 1
+  SC_C0, SC_C1, SC_C2,  // log(N0/nObs), log(i1/(l1 nObs)), log(i2/nObs)  (functions.cpp:348,354,356)
+  SC_I2, SC_P0, SC_P1, SC_A, SC_B,  // computeI2 (functions.cpp:334-344)
+  SC_LOG1ME2,  // log(1 - s_10)
+  SC_IZ_M, SC_IZ_E,  // zero-row Mobile integral as mantissa * 2^-exp
+  SC_COUNT = 16
+};
+
+struct NodeOpDev {  // == ppm::NodeOp
+  int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
+};
+
+struct ModelDev {
+  int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
+  double H;
+  long long n_obs;
+  // tree (preorder ids)
+  const int* left; const int* right; const int* parent;
+  const double* bl; const double* height;
+  // slices
+  const double* slice_t; const double* slice_wt;
+  // program
+  const int* blk_slice0; const int* blk_nslices; const int* blk_op0; const int* blk_ent0;
+  const NodeOpDev* ops; const uint32_t* entries; const int* entry_node; const int* entry_block;
+  // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq
+  const uint32_t* words; long long n_pat, n_pat_pad;
+  const int* counts; const int* mrca; const int* freq;
+  const uint32_t* zero_words;  // n_words * 32 zeros (the all-zero row of add0(), objects.cpp:274-281)
+};
+
+// Per-launch tables, one row per parameter vector
+struct TablesDev {
+  int P;
+  const double* params;  // [P][8]
+  double4* cls;          // [P][n_nodes]  {S0,T0,S1,T1} log-domain pure-loss factors of the branch above a node
+  double2* kap;          // [P][n_nodes]  {pi1*E, (1-pi1)*E}, E = exp(-(g2+l2)*bl)
+  double2* d1u;          // [P][n_nodes]  {log(V+U)-log V, log U}: Private "gained below the root" tables
+  double* kent;          // [P][n_entries] pi1*exp(-(g2+l2)*(t_block - h_lineage))
+  double* yy;            // [P][n_slices]  exp(-(g2+l2)*(t_slice - t_block))
+  double* scal;          // [P][SC_COUNT]
+  double* zeta;          // [P][2][n_nodes] scratch: zero-row log p1 per node for cat 0 / cat 1
+};
+
+struct SweepArgs {
+  ModelDev m;
+  TablesDev t;
+  int mode;              // 0: log-likelihood partial sums, 1: zero row (writes SC_IZ_*), 2: + categories/components
+  long long first, count;  // pattern range
+  long long n_batches, n_items;  // ceil(count/32) and P * n_batches
+  double* partial;       // [P][n_batches]
+  signed char* cat;      // [count] (mode 2, P == 1)
+  double* comp;          // [count][3] (mode 2)
+  double2* gslots;       // global slot storage when slots do not fit in shared memory
+  int force;             // evaluate even when i2 < 0
+};
+
+void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s);
+void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
+void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
+// returns the grid size in x; smem_slots tells whether the shared-memory variant was used
+int sweep_grid_x(const ModelDev& m, long long n_items, int n_sm, int* warps_per_cta, size_t* smem_bytes, bool* smem_slots);
+void launch_sweep(const SweepArgs& a, int grid_x, int warps_per_cta, size_t smem_bytes, bool smem_slots, cudaStream_t s);
+void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s);
+void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
+double run_fp64_peak(int device);
+
+}  // namespace ppm

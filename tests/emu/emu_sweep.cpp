@@ -1,0 +1,110 @@
+// TEST INFRASTRUCTURE ONLY.  Single-lane CPU emulation of the CUDA kernels: compiles the SAME device
+// functions (ppmmodelpangenome_b200/csrc/ppm_device_fns.cuh) with g++, one "lane" per warp, so that the
+// CPU-only test tier can check the kernel arithmetic and the sweep program against the oracle and the
+// golden vectors.  Never part of libppm_b200.so; the product has no host compute path.
+#include <cuda_runtime.h>  // vector types only (double2/double4)
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../ppmmodelpangenome_b200/csrc/host_model.h"
+#include "../../ppmmodelpangenome_b200/csrc/ppm_device_fns.cuh"
+
+using namespace ppm;
+
+struct HostSlots {
+  double2* base;
+  double2 ld(int slot, int lane) const { return base[slot + lane]; }
+  void st(int slot, int lane, double2 v) const { base[slot + lane] = v; }
+};
+
+static std::string g_err;
+
+extern "C" const char* emu_error() { return g_err.c_str(); }
+
+// out_ll[P], out_i2[P], out_parts[P][4]; out_comp [n_patterns][3] / out_cat [n_patterns] for params[0] (may be NULL)
+// i2_override: NULL, or the i2 to use for comp/cat (as assignCat receives MLEi2)
+extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, int R, const double* params, int P,
+                        double* out_ll, double* out_i2, double* out_parts, double* out_comp, signed char* out_cat,
+                        long long* out_npat) {
+  try {
+    Tree tree = read_tree_file(tree_path);
+    Patterns pat = read_matrix_file(tree, pa_path, dedupe != 0);
+    Program prog = build_program(tree, R);
+    const long long count = pat.n_patterns;
+    if (out_npat) *out_npat = count;
+    std::vector<uint32_t> wm((size_t)pat.n_words * count);
+    for (long long j = 0; j < count; j++)
+      for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * count + j] = pat.words[(size_t)j * pat.n_words + w];
+    std::vector<uint32_t> zeros(pat.n_words * 32, 0u);
+    std::vector<int> eb(prog.entries.size());
+    for (int b = 0; b < prog.n_blocks; b++)
+      for (int e = prog.blk_ent0[b]; e < prog.blk_ent0[b + 1]; e++) eb[e] = b;
+    static_assert(sizeof(NodeOpDev) == sizeof(NodeOp), "layout");
+    ModelDev md{};
+    md.n_nodes = tree.n_nodes; md.n_leaves = tree.n_leaves; md.n_words = pat.n_words; md.n_slices = tree.n_slices;
+    md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entries.size();
+    md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
+    md.left = tree.left.data(); md.right = tree.right.data(); md.parent = tree.parent.data();
+    md.bl = tree.bl.data(); md.height = tree.height.data();
+    md.slice_t = tree.slice_t.data(); md.slice_wt = tree.slice_wt.data();
+    md.blk_slice0 = prog.blk_slice0.data(); md.blk_nslices = prog.blk_nslices.data();
+    md.blk_op0 = prog.blk_op0.data(); md.blk_ent0 = prog.blk_ent0.data();
+    md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data()); md.entries = prog.entries.data();
+    md.entry_node = prog.entry_node.data(); md.entry_block = eb.data();
+    md.words = wm.data(); md.n_pat = count; md.n_pat_pad = count;
+    md.counts = pat.counts.data(); md.mrca = pat.mrca.data(); md.freq = pat.freq.data(); md.zero_words = zeros.data();
+
+    const size_t nn = tree.n_nodes;
+    std::vector<double4> cls(P * nn);
+    std::vector<double2> kap(P * nn), d1u(P * nn);
+    std::vector<double> kent((size_t)P * std::max<size_t>(prog.entries.size(), 1)), yy((size_t)P * std::max(tree.n_slices, 1));
+    std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 2 * nn), i2ovr(P);
+    TablesDev t{};
+    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.kent = kent.data();
+    t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
+
+    std::vector<uint32_t> sw(pat.n_words), zw(prog.n_slots);
+    std::vector<double2> slotmem(prog.n_slots);
+    HostSlots slots{slotmem.data()};
+    auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
+      SweepArgs a{};
+      a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
+      a.n_batches = a.count; a.n_items = a.n_batches * nP; a.comp = comp; a.cat = cat; a.force = force;
+      for (int p = 0; p < nP; p++) {
+        double s = 0;
+        for (long long bt = 0; bt < a.n_batches; bt++) {
+          long long item = (long long)p * a.n_batches + bt;
+          if (prog.R == 8) s += sweep_item<8>(a, item, 0, sw.data(), zw.data(), slots);
+          else if (prog.R == 4) s += sweep_item<4>(a, item, 0, sw.data(), zw.data(), slots);
+          else throw std::runtime_error("emulator built for R in {4,8}");
+        }
+        if (ll) ll[p] = s;
+      }
+    };
+    for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p);
+    for (int p = 0; p < P; p++)
+      for (int i = 0; i < md.n_entries + md.n_slices; i++) prepass_tables_body(md, t, p, i);
+    run(1, P, nullptr, nullptr, nullptr, true);
+    for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
+    run(0, P, out_ll, nullptr, nullptr, false);
+    for (int p = 0; p < P; p++) {
+      const double* s = &scal[(size_t)p * SC_COUNT];
+      out_i2[p] = s[SC_I2];
+      if (out_parts) { out_parts[4 * p] = s[SC_P0]; out_parts[4 * p + 1] = s[SC_P1]; out_parts[4 * p + 2] = s[SC_A]; out_parts[4 * p + 3] = s[SC_B]; }
+      if (s[SC_I2] < 0.) out_ll[p] = -1e9 * 1. + s[SC_I2];
+    }
+    if (out_comp || out_cat) {
+      std::vector<double> dummy(1);
+      run(2, 1, dummy.data(), out_comp, out_cat, true);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
