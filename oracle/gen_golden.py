@@ -9,6 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref, model  # noqa: E402
+from ppmmodelpangenome_b200 import simulate  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 REF_TEST = "/root/reference/test"
@@ -55,14 +56,14 @@ def dump_case(name, tree_path, pa_path, vectors, compress):
 
 def synth(name, n, genes, seed, caterpillar=False, nvec=3):
     rng = np.random.default_rng(seed)
-    nwk = model.sim_tree(n, rng, caterpillar=caterpillar)
-    names, M, truth = model.sim_genes(nwk, genes, rng)
+    nwk = simulate.sim_tree(n, rng, caterpillar=caterpillar)
+    names, M, truth = simulate.sim_genes(nwk, genes, rng)
     tpath = os.path.join(GOLD, name + ".nwk")
     ppath = os.path.join(GOLD, name + ".pa.txt")
     with open(tpath, "w") as f:
         f.write(nwk + "\n")
-    model.write_matrix(ppath, names, M)
-    vecs = [model.start_params(truth, genes)] + [model.start_params(truth, genes, rng) for _ in range(nvec - 1)]
+    simulate.write_matrix(ppath, names, M)
+    vecs = [simulate.start_params(truth, genes)] + [simulate.start_params(truth, genes, rng) for _ in range(nvec - 1)]
     # edge cases on synthetic trees too
     e = list(vecs[0]); e[1] = 0.0; vecs.append(e)            # l0 == 0
     e = list(vecs[0]); e[4] = 0.0; vecs.append(e)            # g2 == 0

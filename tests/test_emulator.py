@@ -1,0 +1,60 @@
+"""CPU tier: the kernel bodies (ppm_device_fns.cuh) compiled by g++ as a single-lane emulation
+(tests/emu/emu_sweep.cpp, test infrastructure) reproduce the reference's golden outputs.  This checks the
+linear-domain arithmetic, the prepass tables and the sweep program on the CPU; the CUDA instantiation of the
+same source is checked on the GPU by tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    L = C.CDLL(os.path.join(EMU_DIR, "libppm_emu.so"))
+    L.emu_error.restype = C.c_char_p
+    L.emu_eval.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+
+    def run(tree, pa, dedupe, params, R=8, want_comp=True, n_rows=0):
+        p = np.ascontiguousarray(params, np.float64).reshape(-1, 8)
+        P = len(p)
+        ll, i2, parts = np.zeros(P), np.zeros(P), np.zeros((P, 4))
+        npat = C.c_longlong()
+        comp = np.zeros((max(n_rows, 1), 3)); cat = np.zeros(max(n_rows, 1), np.int8)
+        rc = L.emu_eval(tree.encode(), pa.encode(), int(dedupe), R, p.ctypes.data, P, ll.ctypes.data, i2.ctypes.data,
+                        parts.ctypes.data, comp.ctypes.data if want_comp else None, cat.ctypes.data if want_comp else None,
+                        C.byref(npat))
+        if rc:
+            raise RuntimeError(L.emu_error().decode())
+        return ll, i2, parts, comp[:npat.value], cat[:npat.value]
+
+    return run
+
+
+@pytest.mark.parametrize("name", ["ref_test", "syn12", "syn100", "cat40", "syn300"])
+@pytest.mark.parametrize("R", [8, 4])
+def test_kernel_bodies_reproduce_reference_golden(golden, emu, name, R):
+    g = golden(name)
+    ll, i2, parts, comp, cat = emu(g.tree, g.pa, False, g.params, R=R, n_rows=g.meta["nRep"])
+    for k, r in enumerate(g.results):
+        assert rel(ll[k], r["ll"]) <= 1e-12, (name, k, ll[k], r["ll"])
+        assert rel(i2[k], r["i2"]) <= 1e-12
+        assert np.allclose(parts[k], r["parts"], rtol=1e-12, atol=1e-13)  # p1 = 1-exp(.) cancels: absolute bound
+    ref3 = g.ref3(0)
+    fin = np.isfinite(ref3)
+    assert np.allclose(comp[fin], ref3[fin], rtol=1e-10, atol=1e-10)
+    ok = np.isfinite(g.z["components"][0][:, 3])   # reference lik2 = -inf where its exp(f_aux) underflows
+    assert np.array_equal(cat[ok], g.z["cats"][0][ok])
+
+
+def test_deduplicated_input_gives_the_same_loglik(golden, emu):
+    g = golden("ref_test")
+    a = emu(g.tree, g.pa, False, g.params[:2], want_comp=False)[0]
+    b = emu(g.tree, g.pa, True, g.params[:2], want_comp=False)[0]
+    assert np.allclose(a, b, rtol=1e-13, atol=0)
