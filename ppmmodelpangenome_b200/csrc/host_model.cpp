@@ -368,8 +368,9 @@ Program build_program(const Tree& t, int R) {
   const int nn = t.n_nodes, S = t.n_slices, nl = t.n_leaves;
   const int nb = (S + R - 1) / R;
   pg.n_blocks = nb;
-  pg.blk_slice0.resize(nb); pg.blk_nslices.resize(nb);
-  for (int b = 0; b < nb; b++) { pg.blk_slice0[b] = b * R; pg.blk_nslices[b] = std::min(R, S - b * R); }
+  pg.blk.assign(nb + 1, BlockDescHost{});
+  for (int b = 0; b < nb; b++) { pg.blk[b].slice0 = b * R; pg.blk[b].nslices = std::min(R, S - b * R); }
+  pg.blk[nb].slice0 = S; pg.blk[nb].nslices = 0;
 
   // alive slice range of every non-root lineage: intervals [max(rank, nl-1), rank(parent)-1]
   std::vector<int> js0(nn, S), js1(nn, S);
@@ -386,12 +387,12 @@ Program build_program(const Tree& t, int R) {
   std::vector<std::vector<int>> release(nb + 2);
   std::vector<int> free_slots;
   int n_slots = 0;
-  pg.blk_op0.assign(nb + 2, 0);
+  std::vector<int> blk_op0(nb + 2, 0);
   int cur_block = -1;
   auto open_blocks_to = [&](int b) {  // op lists are emitted in block order
     while (cur_block < b) {
       cur_block++;
-      pg.blk_op0[cur_block] = (int)pg.ops.size();
+      blk_op0[cur_block] = (int)pg.ops.size();
       if (cur_block >= 1)
         for (int s : release[cur_block - 1]) free_slots.push_back(s);
     }
@@ -421,47 +422,57 @@ Program build_program(const Tree& t, int R) {
     pg.ops.push_back(op);
   }
   open_blocks_to(nb);
-  pg.blk_op0[nb + 1] = (int)pg.ops.size();
+  blk_op0[nb + 1] = (int)pg.ops.size();
+  for (int b = 0; b <= nb; b++) { pg.blk[b].op0 = blk_op0[b]; pg.blk[b].op1 = blk_op0[b + 1]; }
   pg.n_slots = std::max(n_slots, 1);
 
-  // entries
-  std::vector<std::vector<uint32_t>> ent(nb);
-  std::vector<std::vector<int32_t>> entn(nb);
+  // entries: per block, [full leaves | full slots | partial], each sorted by reference
+  struct Ent { int ref, i0, i1, node; bool leaf; };
+  std::vector<std::vector<Ent>> ent(nb);
   for (int v = 1; v < nn; v++) {
     if (js0[v] >= js1[v]) continue;
-    int ref = t.left[v] < 0 ? -(t.leaf_pos[v] + 1) : slot[v];
-    if (ref < -32768 || ref > 32767) throw std::runtime_error("program: tree too large for 16-bit lineage references");
+    const bool leaf = t.left[v] < 0;
     for (int b = js0[v] / R; b <= (js1[v] - 1) / R; b++) {
       int jb = b * R, je = std::min(S, jb + R);
-      int i0 = std::max(js0[v], jb) - jb, i1 = std::min(js1[v], je) - jb;
-      ent[b].push_back(((uint32_t)(uint16_t)(int16_t)ref) | ((uint32_t)i0 << 16) | ((uint32_t)i1 << 24));
-      entn[b].push_back(v);
+      Ent e;
+      e.i0 = std::max(js0[v], jb) - jb; e.i1 = std::min(js1[v], je) - jb;
+      e.node = v; e.leaf = leaf; e.ref = leaf ? t.leaf_pos[v] : slot[v];
+      if (e.ref > 65535) throw std::runtime_error("program: tree too large for 16-bit lineage references");
+      ent[b].push_back(e);
     }
   }
-  pg.blk_ent0.assign(nb + 1, 0);
   double fp64 = 0;
   for (int b = 0; b < nb; b++) {
-    pg.blk_ent0[b] = (int)pg.entries.size();
-    std::vector<int> idx(ent[b].size());
-    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
-    auto key = [&](int i) {
-      uint32_t e = ent[b][i];
-      int i0 = (e >> 16) & 0xff, i1 = (e >> 24) & 0xff;
-      bool partial = !(i0 == 0 && i1 == R);
-      bool is_slot = (int16_t)(e & 0xffff) >= 0;
-      return std::make_tuple(partial, is_slot, (int)(int16_t)(e & 0xffff));
-    };
-    std::sort(idx.begin(), idx.end(), [&](int a, int c) { return key(a) < key(c); });
-    for (int i : idx) {
-      uint32_t e = ent[b][i];
-      int i0 = (e >> 16) & 0xff, i1 = (e >> 24) & 0xff;
-      if (i0 == 0 && i1 == R) pg.n_full++; else pg.n_partial++;
-      fp64 += 1 + 2 * (i1 - i0);
-      pg.entries.push_back(e);
-      pg.entry_node.push_back(entn[b][i]);
+    auto cls_of = [&](const Ent& e) { return (e.i0 == 0 && e.i1 == R) ? (e.leaf ? 0 : 1) : 2; };
+    std::stable_sort(ent[b].begin(), ent[b].end(), [&](const Ent& x, const Ent& y) {
+      int cx = cls_of(x), cy = cls_of(y);
+      if (cx != cy) return cx < cy;
+      if (x.leaf != y.leaf) return x.leaf;
+      return x.ref < y.ref;
+    });
+    BlockDescHost& bd = pg.blk[b];
+    bd.e_leaf0 = (int)pg.entry_ref.size();
+    bd.e_slot0 = bd.e_part0 = -1;
+    for (const Ent& e : ent[b]) {
+      int c = cls_of(e), at = (int)pg.entry_ref.size();
+      if (c >= 1 && bd.e_slot0 < 0) bd.e_slot0 = at;
+      if (c >= 2 && bd.e_part0 < 0) bd.e_part0 = at;
+      if (c == 2) pg.n_partial++; else pg.n_full++;
+      fp64 += 1 + 2 * (e.i1 - e.i0);
+      pg.entry_ref.push_back(c == 2 && e.leaf ? -(e.ref + 1) : e.ref);
+      pg.entry_mask.push_back(((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+      pg.entry_node.push_back(e.node);
+      pg.entry_block.push_back(b);
     }
+    bd.e_end = (int)pg.entry_ref.size();
+    if (bd.e_part0 < 0) bd.e_part0 = bd.e_end;
+    if (bd.e_slot0 < 0) bd.e_slot0 = bd.e_part0;
+    // upper 16 mask bits: the next record's reference within the same full segment (0 = always-valid dummy),
+    // which lets the kernel issue the next operand load before it has read the next record
+    for (int e = bd.e_leaf0; e + 1 < bd.e_slot0; e++) pg.entry_mask[e] |= (uint32_t)pg.entry_ref[e + 1] << 16;
+    for (int e = bd.e_slot0; e + 1 < bd.e_part0; e++) pg.entry_mask[e] |= (uint32_t)pg.entry_ref[e + 1] << 16;
   }
-  pg.blk_ent0[nb] = (int)pg.entries.size();
+  pg.blk[nb].e_leaf0 = pg.blk[nb].e_slot0 = pg.blk[nb].e_part0 = pg.blk[nb].e_end = (int)pg.entry_ref.size();
   // + node ops (8 merge + 2 renorm + 4 class adds), block ends (~3 per slice), epilogue (~60)
   pg.fp64_instr_per_eval = fp64 + 14.0 * (nl - 1) + 3.0 * S + 60;
   return pg;

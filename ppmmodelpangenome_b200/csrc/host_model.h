@@ -58,15 +58,17 @@ struct NodeOp {
   int32_t i0;           // first slice of the current block at which the node is alive (0..R); R = none
   int32_t pad;
 };
+struct BlockDescHost {  // entry segments: full leaves [e_leaf0,e_slot0), full slots [e_slot0,e_part0), partial [e_part0,e_end)
+  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_part0, e_end;
+};
 struct Program {
   int R = 8;
   int n_blocks = 0, n_slots = 0;
-  std::vector<int32_t> blk_slice0, blk_nslices;   // [n_blocks]
-  std::vector<int32_t> blk_op0;                   // [n_blocks+2] node ops before block b: [op0[b], op0[b+1]); tail ops after the last block
-  std::vector<int32_t> blk_ent0;                  // [n_blocks+1]
+  std::vector<BlockDescHost> blk;                 // [n_blocks+1]; blk[n_blocks] carries the node ops after the last block
   std::vector<NodeOp> ops;
-  std::vector<uint32_t> entries;                  // ref(16 bit signed) | i0<<16 | i1<<24
-  std::vector<int32_t> entry_node;                // node id of each entry (for the K table)
+  std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
+  std::vector<uint32_t> entry_mask;               // alive slices of the block
+  std::vector<int32_t> entry_node, entry_block;   // node id / block of each entry (for the K table)
   int64_t n_full = 0, n_partial = 0;
   // modelled FP64 instruction count per pattern-eval of the main kernel
   double fp64_instr_per_eval = 0;

@@ -127,21 +127,35 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p) {
   sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
 }
 
-// One thread per (parameter vector, entry or slice): the exp tables of the Mobile integral.
+// One thread per (parameter vector, entry or padded slice): the exp tables of the Mobile integral.
+// recs[e] = { K = pi1*exp(-(g2+l2)*(t_block - h_lineage)), ref, slice mask }; yy[j] = exp(-(g2+l2)*(t_j - t_block)),
+// zero for the padding slices of the last block.
 PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, int i) {
   const double* par = t.params + 8 * (size_t)p;
   const double g2 = par[4], l2 = par[5];
   const double lam = g2 + l2;
   const double pi1 = (g2 == 0.) ? 0. : g2 / lam;
+  const int n_pad = m.n_blocks * m.R;
   if (i < m.n_entries) {
     int b = m.entry_block[i];
-    double tb = m.slice_t[m.blk_slice0[b]];
+    double tb = m.slice_t[m.blk[b].slice0];
     double hs = m.height[m.entry_node[i]];
-    t.kent[(size_t)p * m.n_entries + i] = pi1 * exp(-lam * (tb - hs));
-  } else if (i < m.n_entries + m.n_slices) {
-    int j = i - m.n_entries;
-    double tb = m.slice_t[(j / m.R) * m.R];
-    t.yy[(size_t)p * m.n_slices + j] = exp(-lam * (m.slice_t[j] - tb));
+    EntryRec r;
+    r.K = pi1 * exp(-lam * (tb - hs));
+    r.ref = m.entry_ref[i];
+    r.mask = m.entry_mask[i];
+    t.recs[(size_t)p * (m.n_entries + 1) + i] = r;
+  } else if (i == m.n_entries) {
+    EntryRec r; r.K = 0.; r.ref = 0; r.mask = 0u;  // padding record: the prefetch of the last entry reads it
+    t.recs[(size_t)p * (m.n_entries + 1) + i] = r;
+  } else if (i <= m.n_entries + n_pad) {
+    int j = i - m.n_entries - 1;
+    double v = 0.;
+    if (j < m.n_slices) {
+      double tb = m.slice_t[(j / m.R) * m.R];
+      v = exp(-lam * (m.slice_t[j] - tb));
+    }
+    t.yy[(size_t)p * n_pad + j] = v;
   }
 }
 
@@ -164,191 +178,234 @@ PPM_HD void prepass_i2_body(const ModelDev& m, const TablesDev& t, const double*
 // ------------------------------------------------------------------------------------------------ sweep
 template <bool SMEM_SLOTS>
 struct SlotStore {
-  double2* base;  // [slot][32]
+  double2* base;  // [slot][lanes]
   PPM_HD double2 ld(int slot, int lane) const { return base[slot * PPM_LANES + lane]; }
   PPM_HD void st(int slot, int lane, double2 v) const { base[slot * PPM_LANES + lane] = v; }
 };
 
-// One work item = 32 patterns (one per lane) x one parameter vector.  Returns this lane's count*log-mixture.
+// Where one work item reads its topology program and per-parameter tables from (shared memory copies in the
+// staged variant, global memory otherwise).
+struct ItemTables {
+  const EntryRec* recs;   // [n_entries + 1]
+  const BlockDesc* blk;   // [n_blocks + 1]
+  const NodeOpDev* ops;
+  const double4* cls;     // [n_nodes]
+  const double2* kap;     // [n_nodes]
+  const double* yy;       // [n_blocks * R]
+  const double* wt;       // [n_blocks * R]
+};
+
+// One 16-byte load per record: K | ref | (next_ref << 16 | slice mask)
+PPM_HD void load_rec(const EntryRec* recs, int e, double& K, int& ref, uint32_t& mask) {
+#if defined(__CUDA_ARCH__)
+  const double2 v = reinterpret_cast<const double2*>(recs)[e];
+  K = v.x; ref = __double2loint(v.y); mask = (uint32_t)__double2hiint(v.y);
+#else
+  K = recs[e].K; ref = recs[e].ref; mask = recs[e].mask;
+#endif
+}
+
+template <int R>
+PPM_HD void rescale_products(double (&prod)[R], int (&ex)[R]) {
+  // keep the running products away from the denormal range (rare path)
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    int be = biased_exp(prod[i]);
+    if (be != 0 && be < 1023 - 480) { prod[i] *= pow2i(480); ex[i] += 480; }
+  }
+}
+template <int R>
+PPM_HD bool products_small(const double (&prod)[R]) {
+  // all products are >= 0, so their high words order like the values; an exact zero also lands here (harmless)
+  int mn = ppm_double2hiint(prod[0]);
+#pragma unroll
+  for (int i = 1; i < R; i++) { int h = ppm_double2hiint(prod[i]); mn = h < mn ? h : mn; }
+  return mn < ((1023 - 480) << 20);
+}
+
+// One work item = PPM_LANES patterns (one per lane) x one parameter vector.  Returns this lane's count*log-mixture.
 // sw: per-warp pattern words [n_words][PPM_LANES]; zw: per-warp all-zero-subtree masks per slot.
 template <int R, class Slots>
-PPM_HD double sweep_item(const SweepArgs& a, long long item, int lane, uint32_t* sw, uint32_t* zw, const Slots& slots) {
+PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long long batch, int lane, uint32_t* sw,
+                         uint32_t* zw, const Slots& slots) {
   const ModelDev& m = a.m;
-  const int p = (int)(item / a.n_batches);
-  const long long batch = item % a.n_batches;
   const double* sc = a.t.scal + (size_t)p * SC_COUNT;
   const bool skip = (a.mode == 0) && !a.force && (sc[SC_I2] < 0.);  // penalty branch: no pattern work (functions.cpp:362-364)
-
   const long long pat = a.first + batch * PPM_LANES + lane;
   const bool active = pat < a.first + a.count;
   double contrib = 0.;
+  if (skip) return 0.;
 
-  if (!skip) {
-    for (int w = 0; w < m.n_words; w++) {
-      const uint32_t* src = (a.mode == 1) ? m.zero_words : m.words + (size_t)w * m.n_pat_pad;
-      sw[w * PPM_LANES + lane] = (a.mode == 1) ? 0u : (active ? src[pat] : 0u);
+  for (int w = 0; w < m.n_words; w++)
+    sw[w * PPM_LANES + lane] = (a.mode == 1 || !active) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat];
+  ppm_syncwarp();
+
+  const double pi1 = sc[SC_PI1];
+  const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
+
+  double A0 = 0., A1 = 0.;     // log p1(root) of the two pure-loss categories
+  int X = 0;                   // sum of renormalisation shifts of all lineages formed so far
+  double Im = 0.; int Ie = 0;  // Mobile integral = Im * 2^-Ie
+
+  double prod[R], Y[R];
+  int ex[R];
+
+  for (int b = 0; b <= m.n_blocks; b++) {
+    const BlockDesc bd = T.blk[b];
+    const bool real = b < m.n_blocks;
+    if (real) {
+#pragma unroll
+      for (int i = 0; i < R; i++) { prod[i] = 1.; ex[i] = X; Y[i] = T.yy[b * R + i]; }
     }
-    ppm_syncwarp();
-
-    const double pi1 = sc[SC_PI1];
-    const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
-    const double4* cls = a.t.cls + (size_t)p * m.n_nodes;
-    const double2* kap = a.t.kap + (size_t)p * m.n_nodes;
-    const double* kent = a.t.kent + (size_t)p * m.n_entries;
-    const double* yy = a.t.yy + (size_t)p * m.n_slices;
-
-    double A0 = 0., A1 = 0.;  // log p1(root) of the two pure-loss categories
-    int X = 0;                // sum of renormalisation shifts of all lineages formed so far
-    double Im = 0.; int Ie = 0;  // Mobile integral = Im * 2^-Ie
-
-    double prod[R], Y[R];
-    int ex[R];
-
-    for (int b = 0; b <= m.n_blocks; b++) {
-      const bool real = b < m.n_blocks;
-      int nsl = 0, j0 = 0;
-      if (real) {
-        nsl = m.blk_nslices[b]; j0 = m.blk_slice0[b];
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-          prod[i] = 1.; ex[i] = X;
-          Y[i] = (i < nsl) ? yy[j0 + i] : 0.;
-        }
+    // ---- node ops: form every node born before the end of this block
+    for (int o = bd.op0; o < bd.op1; o++) {
+      const NodeOpDev op = T.ops[o];
+      double2 L, Rr;
+      uint32_t zwl, zwr;
+      if (op.lref < 0) {
+        int pos = -(op.lref + 1);
+        bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
+        L = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
+        zwl = ~ppm_ballot(bit);
+      } else { L = slots.ld(op.lref, lane); zwl = zw[op.lref]; }
+      if (op.rref < 0) {
+        int pos = -(op.rref + 1);
+        bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
+        Rr = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
+        zwr = ~ppm_ballot(bit);
+      } else { Rr = slots.ld(op.rref, lane); zwr = zw[op.rref]; }
+      const uint32_t zwv = zwl & zwr;
+      // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
+      {
+        const bool zl = (zwl >> lane) & 1u, zr = (zwr >> lane) & 1u;
+        const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
+        const double4 cl = T.cls[op.lnode], cr = T.cls[op.rnode];
+        A0 += zl ? (zv ? 0. : cl.y) : cl.x;
+        A1 += zl ? (zv ? 0. : cl.w) : cl.z;
+        A0 += zr ? (zv ? 0. : cr.y) : cr.x;
+        A1 += zr ? (zv ? 0. : cr.w) : cr.z;
       }
-      // ---- node ops: form every node born before the end of this block
-      const int op_end = m.blk_op0[b + 1];
-      for (int o = m.blk_op0[b]; o < op_end; o++) {
-        const NodeOpDev op = m.ops[o];
-        double2 L, Rr;
-        uint32_t zwl, zwr;
-        if (op.lref < 0) {
-          int pos = -(op.lref + 1);
-          bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
-          L = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
-          zwl = ~ppm_ballot(bit);
-        } else { L = slots.ld(op.lref, lane); zwl = zw[op.lref]; }
-        if (op.rref < 0) {
-          int pos = -(op.rref + 1);
-          bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
-          Rr = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
-          zwr = ~ppm_ballot(bit);
-        } else { Rr = slots.ld(op.rref, lane); zwr = zw[op.rref]; }
-        const uint32_t zwv = zwl & zwr;
-        // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
-        {
-          const bool zl = (zwl >> lane) & 1u, zr = (zwr >> lane) & 1u;
-          const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
-          const double4 cl = cls[op.lnode], cr = cls[op.rnode];
-          A0 += zl ? (zv ? 0. : cl.y) : cl.x;
-          A1 += zl ? (zv ? 0. : cl.w) : cl.z;
-          A0 += zr ? (zv ? 0. : cr.y) : cr.x;
-          A1 += zr ? (zv ? 0. : cr.w) : cr.z;
-        }
-        if (op.dst >= 0) {
-          // Mobile merge (objects.cpp:427-435 in linear domain)
-          const double2 kl = kap[op.lnode], kr = kap[op.rnode];
-          double m0 = fma(-kl.x, L.y, L.x) * fma(-kr.x, Rr.y, Rr.x);
-          double m1 = fma(kl.y, L.y, L.x) * fma(kr.y, Rr.y, Rr.x);
-          double d = m1 - m0;
-          double av = fma(pi1, d, m0);
-          // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
-          int be = biased_exp(fmax(fabs(av), fabs(d)));
-          int k = (be != 0 && be < 1023 - 40) ? 1022 - be : 0;
-          if (ppm_any(k != 0)) {
-            double s = pow2i(k);
-            av *= s; d *= s;
-            X += k;
-            if (real) {
+      if (op.dst >= 0) {
+        // Mobile merge (objects.cpp:427-435 in linear domain)
+        const double2 kl = T.kap[op.lnode], kr = T.kap[op.rnode];
+        double m0 = fma(-kl.x, L.y, L.x) * fma(-kr.x, Rr.y, Rr.x);
+        double m1 = fma(kl.y, L.y, L.x) * fma(kr.y, Rr.y, Rr.x);
+        double d = m1 - m0;
+        double av = fma(pi1, d, m0);
+        // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
+        int be = biased_exp(fmax(fabs(av), fabs(d)));
+        int k = (be != 0 && be < 1023 - 40) ? 1022 - be : 0;
+        if (ppm_any(k != 0)) {
+          double s = pow2i(k);
+          av *= s; d *= s;
+          X += k;
+          if (real) {
 #pragma unroll
-              for (int i = 0; i < R; i++) if (i >= op.i0) ex[i] += k;
-            }
-          }
-          ppm_syncwarp();
-          slots.st(op.dst, lane, make_double2(av, d));
-          if (lane == 0) zw[op.dst] = zwv;
-          ppm_syncwarp();
-        }
-      }
-      if (!real) break;
-      // ---- entries: every lineage alive somewhere in this block
-      const int e_end = m.blk_ent0[b + 1];
-      int since = 0;
-      for (int e = m.blk_ent0[b]; e < e_end; e++) {
-        const uint32_t code = m.entries[e];
-        const int ref = (int)(short)(code & 0xffffu);
-        const int i0 = (code >> 16) & 0xff, i1 = (code >> 24) & 0xff;
-        double2 ad;
-        if (ref < 0) {
-          int pos = -(ref + 1);
-          bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
-          ad = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
-        } else ad = slots.ld(ref, lane);
-        const double bb = ad.y * kent[e];
-        if (i0 == 0 && i1 == R) {
-#pragma unroll
-          for (int i = 0; i < R; i++) prod[i] *= fma(-bb, Y[i], ad.x);
-        } else {
-#pragma unroll
-          for (int i = 0; i < R; i++)
-            if (i >= i0 && i < i1) prod[i] *= fma(-bb, Y[i], ad.x);
-        }
-        if (++since == 16) {  // keep the running products away from the denormal range
-          since = 0;
-          int mn = 2047;
-#pragma unroll
-          for (int i = 0; i < R; i++) { int be = biased_exp(prod[i]); int bq = be == 0 ? 2047 : be; mn = bq < mn ? bq : mn; }
-          if (ppm_any(mn < 1023 - 480)) {
-#pragma unroll
-            for (int i = 0; i < R; i++) {
-              int be = biased_exp(prod[i]);
-              if (be != 0 && be < 1023 - 480) { prod[i] *= pow2i(480); ex[i] += 480; }
-            }
+            for (int i = 0; i < R; i++) if (i >= op.i0) ex[i] += k;
           }
         }
-      }
-      // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
-#pragma unroll
-      for (int i = 0; i < R; i++) {
-        if (i < nsl) {
-          double v = prod[i] * m.slice_wt[j0 + i];
-          if (v != 0.) {
-            int e = ex[i];
-            if (Im == 0.) { Im = v; Ie = e; }
-            else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
-            else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
-          }
-        }
+        ppm_syncwarp();
+        slots.st(op.dst, lane, make_double2(av, d));
+        if (lane == 0) zw[op.dst] = zwv;
+        ppm_syncwarp();
       }
     }
+    if (!real) break;
 
-    if (a.mode == 1) {
-      if (active) {
-        double* scw = a.t.scal + (size_t)p * SC_COUNT;
-        // renormalise the mantissa so that ldexp in prepass_i2 stays in range
-        scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
+    // ---- entries alive in every slice of the block: leaves (partials selected by the pattern bit) ...
+    // Each record names the NEXT record's reference in its upper mask bits, so the next operand load is issued
+    // before the current products (software prefetch); chunks of 16 entries are followed by a range check.
+    for (int e = bd.e_leaf0; e < bd.e_slot0;) {
+      const int ce = (e + 16 < bd.e_slot0) ? e + 16 : bd.e_slot0;
+      double K; int ref; uint32_t mk;
+      load_rec(T.recs, e, K, ref, mk);
+      uint32_t wv = sw[(ref >> 5) * PPM_LANES + lane];
+#pragma unroll 2
+      for (; e < ce; e++) {
+        const int nref = (int)(mk >> 16);
+        const uint32_t wn = sw[(nref >> 5) * PPM_LANES + lane];
+        const bool bit = (wv >> (ref & 31)) & 1u;
+        const double aa = bit ? la1 : la0;
+        const double bb = (bit ? ld1 : ld0) * K;
+        load_rec(T.recs, e + 1, K, ref, mk);  // the table carries one padding record
+#pragma unroll
+        for (int i = 0; i < R; i++) prod[i] *= fma(-bb, Y[i], aa);
+        wv = wn;
       }
-      return 0.;
+      if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
-    // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
+    // ... internal lineages (partials in slots)
+    for (int e = bd.e_slot0; e < bd.e_part0;) {
+      const int ce = (e + 16 < bd.e_part0) ? e + 16 : bd.e_part0;
+      double K; int ref; uint32_t mk;
+      load_rec(T.recs, e, K, ref, mk);
+      double2 ad = slots.ld(ref, lane);
+#pragma unroll 2
+      for (; e < ce; e++) {
+        const double2 an = slots.ld((int)(mk >> 16), lane);
+        const double bb = ad.y * K;
+        load_rec(T.recs, e + 1, K, ref, mk);
+#pragma unroll
+        for (int i = 0; i < R; i++) prod[i] *= fma(-bb, Y[i], ad.x);
+        ad = an;
+      }
+      if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
+    }
+    // ---- entries alive in part of the block (lineages born or merged inside it): slice mask
+    for (int e = bd.e_part0; e < bd.e_end; e++) {
+      double K; int ref; uint32_t mk;
+      load_rec(T.recs, e, K, ref, mk);
+      double2 ad;
+      if (ref < 0) {
+        int pos = -(ref + 1);
+        bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
+        ad = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
+      } else ad = slots.ld(ref, lane);
+      const double bb = ad.y * K;
+#pragma unroll
+      for (int i = 0; i < R; i++)
+        if (mk & (1u << i)) prod[i] *= fma(-bb, Y[i], ad.x);
+      if ((e & 15) == 15 && ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
+    }
+    // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      double v = prod[i] * T.wt[b * R + i];   // padding slices carry weight 0
+      if (v != 0.) {
+        int e = ex[i];
+        if (Im == 0.) { Im = v; Ie = e; }
+        else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
+        else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
+      }
+    }
+  }
+
+  if (a.mode == 1) {
     if (active) {
-      const double lik0 = sc[SC_C0] + A0;
-      const int mr = m.mrca[pat];
-      const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];
-      double lik1;
-      if (m.freq[pat] == 0) lik1 = lse2(sc[SC_C1] + A1, sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
-      else lik1 = sc[SC_C1] + (A1 + du.x);
-      const double lik2 = (Im > 0.) ? sc[SC_C2] + (log(Im) - (double)Ie * 0.693147180559945309417232) : -INFINITY;
-      double mx = fmax(lik0, fmax(lik1, lik2));
-      double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));
-      contrib = tot * (double)m.counts[pat];
-      if (a.mode == 2) {
-        int c = 0;
-        if (lik1 > lik0) c = 1;
-        if (lik2 > (c ? lik1 : lik0)) c = 2;
-        long long r = pat - a.first;
-        if (a.cat) a.cat[r] = (signed char)c;
-        if (a.comp) { a.comp[3 * r] = lik0; a.comp[3 * r + 1] = lik1; a.comp[3 * r + 2] = lik2; }
-      }
+      double* scw = a.t.scal + (size_t)p * SC_COUNT;
+      scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
+    }
+    return 0.;
+  }
+  // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
+  if (active) {
+    const double lik0 = sc[SC_C0] + A0;
+    const int mr = m.mrca[pat];
+    const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];
+    double lik1;
+    if (m.freq[pat] == 0) lik1 = lse2(sc[SC_C1] + A1, sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
+    else lik1 = sc[SC_C1] + (A1 + du.x);
+    const double lik2 = (Im > 0.) ? sc[SC_C2] + (log(Im) - (double)Ie * 0.693147180559945309417232) : -INFINITY;
+    double mx = fmax(lik0, fmax(lik1, lik2));
+    double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));
+    contrib = tot * (double)m.counts[pat];
+    if (a.mode == 2) {
+      int c = 0;
+      if (lik1 > lik0) c = 1;
+      if (lik2 > (c ? lik1 : lik0)) c = 2;
+      long long r = pat - a.first;
+      if (a.cat) a.cat[r] = (signed char)c;
+      if (a.comp) { a.comp[3 * r] = lik0; a.comp[3 * r + 1] = lik1; a.comp[3 * r + 2] = lik2; }
     }
   }
   return contrib;

@@ -60,17 +60,20 @@ struct ppm_engine {
   double n_launches = 0;
 
   // device model
-  DevBuf<int> d_left, d_right, d_parent, d_blk_slice0, d_blk_nslices, d_blk_op0, d_blk_ent0, d_entry_node, d_entry_block;
+  DevBuf<int> d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block;
+  DevBuf<ppm::BlockDesc> d_blk;
+  DevBuf<uint32_t> d_entry_mask;
   DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt;
   DevBuf<ppm::NodeOpDev> d_ops;
-  DevBuf<uint32_t> d_entries, d_words, d_zero_words;
+  DevBuf<uint32_t> d_words, d_zero_words;
   DevBuf<int> d_counts, d_mrca, d_freq;
   long long n_pat_pad = 0;
   ppm::ModelDev md{};
 
   // per-launch tables
   int P_cap = 0;
-  DevBuf<double> d_params, d_kent, d_yy, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
+  DevBuf<ppm::EntryRec> d_recs;
+  DevBuf<double> d_params, d_yy, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
   DevBuf<double4> d_cls;
   DevBuf<double2> d_kap, d_d1u, d_gslots;
   DevBuf<signed char> d_cat;
@@ -105,19 +108,20 @@ struct ppm_engine {
     count = np * (shard_rank + 1) / shard_world - first;
     d_left.upload(tree.left, stream); d_right.upload(tree.right, stream); d_parent.upload(tree.parent, stream);
     d_bl.upload(tree.bl, stream); d_height.upload(tree.height, stream);
-    d_slice_t.upload(tree.slice_t, stream); d_slice_wt.upload(tree.slice_wt, stream);
-    d_blk_slice0.upload(prog.blk_slice0, stream); d_blk_nslices.upload(prog.blk_nslices, stream);
-    d_blk_op0.upload(prog.blk_op0, stream); d_blk_ent0.upload(prog.blk_ent0, stream);
-    std::vector<ppm::NodeOpDev> ops(prog.ops.size());
+    d_slice_t.upload(tree.slice_t, stream);
+    std::vector<double> wt_pad((size_t)std::max(prog.n_blocks, 1) * prog.R, 0.);
+    std::copy(tree.slice_wt.begin(), tree.slice_wt.end(), wt_pad.begin());
+    d_slice_wt.upload(wt_pad, stream);
     static_assert(sizeof(ppm::NodeOpDev) == sizeof(ppm::NodeOp), "NodeOp layout");
+    static_assert(sizeof(ppm::BlockDesc) == sizeof(ppm::BlockDescHost), "BlockDesc layout");
+    std::vector<ppm::NodeOpDev> ops(prog.ops.size());
     if (!ops.empty()) std::memcpy(ops.data(), prog.ops.data(), ops.size() * sizeof(ppm::NodeOp));
     d_ops.upload(ops, stream);
-    d_entries.upload(prog.entries, stream);
-    d_entry_node.upload(prog.entry_node, stream);
-    std::vector<int> eb(prog.entries.size());
-    for (int b = 0; b < prog.n_blocks; b++)
-      for (int e = prog.blk_ent0[b]; e < prog.blk_ent0[b + 1]; e++) eb[e] = b;
-    d_entry_block.upload(eb, stream);
+    std::vector<ppm::BlockDesc> blk(prog.blk.size());
+    std::memcpy(blk.data(), prog.blk.data(), blk.size() * sizeof(ppm::BlockDesc));
+    d_blk.upload(blk, stream);
+    d_entry_ref.upload(prog.entry_ref, stream); d_entry_mask.upload(prog.entry_mask, stream);
+    d_entry_node.upload(prog.entry_node, stream); d_entry_block.upload(prog.entry_block, stream);
     // patterns of this shard, word-major so that lanes (= consecutive patterns) read consecutive addresses
     n_pat_pad = (count + 31) / 32 * 32;
     std::vector<uint32_t> wm((size_t)pat.n_words * std::max<long long>(n_pat_pad, 32), 0u);
@@ -133,12 +137,12 @@ struct ppm_engine {
     CK(cudaStreamSynchronize(stream));
 
     md.n_nodes = tree.n_nodes; md.n_leaves = tree.n_leaves; md.n_words = pat.n_words; md.n_slices = tree.n_slices;
-    md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entries.size();
+    md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entry_ref.size();
     md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
     md.left = d_left.p; md.right = d_right.p; md.parent = d_parent.p; md.bl = d_bl.p; md.height = d_height.p;
-    md.slice_t = d_slice_t.p; md.slice_wt = d_slice_wt.p;
-    md.blk_slice0 = d_blk_slice0.p; md.blk_nslices = d_blk_nslices.p; md.blk_op0 = d_blk_op0.p; md.blk_ent0 = d_blk_ent0.p;
-    md.ops = d_ops.p; md.entries = d_entries.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
+    md.slice_t = d_slice_t.p; md.slice_wt_pad = d_slice_wt.p;
+    md.blk = d_blk.p; md.ops = d_ops.p;
+    md.entry_ref = d_entry_ref.p; md.entry_mask = d_entry_mask.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
     md.words = d_words.p; md.n_pat = count; md.n_pat_pad = n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
   }
@@ -147,13 +151,13 @@ struct ppm_engine {
     if (P > P_cap) {
       size_t nn = tree.n_nodes;
       d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
-      d_kent.alloc((size_t)P * std::max<size_t>(prog.entries.size(), 1)); d_yy.alloc((size_t)P * std::max(tree.n_slices, 1));
+      d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
       d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 2 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }
     ppm::TablesDev t{};
-    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.kent = d_kent.p; t.yy = d_yy.p;
+    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p;
     return t;
   }
@@ -164,10 +168,9 @@ struct ppm_engine {
     ppm::launch_prepass_tables(md, t, s);
     ppm::SweepArgs z{};
     z.m = md; z.t = t; z.mode = 1; z.first = 0; z.count = 1; z.n_batches = 1; z.n_items = t.P; z.force = 1;
-    int wpc; size_t smem; bool ss;
-    int gx = ppm::sweep_grid_x(md, z.n_items, n_sm, &wpc, &smem, &ss);
-    if (!ss) { d_gslots.alloc((size_t)std::max(gx, n_sm * 2) * 8 * prog.n_slots * 32); z.gslots = d_gslots.p; }
-    ppm::launch_sweep(z, gx, wpc, smem, ss, s);
+    ppm::SweepPlan pl = ppm::plan_sweep(md, 1, t.P, n_sm);
+    d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); z.gslots = d_gslots.p;
+    ppm::launch_sweep(z, pl, s);
     ppm::launch_prepass_i2(md, t, d_i2_ovr, s);
     n_launches += 4;
   }
@@ -182,11 +185,10 @@ struct ppm_engine {
     if (need > partial_cap) { d_partial.alloc(need); partial_cap = need; }
     a.partial = d_partial.p;
     if (a.n_items > 0) {
-      int wpc; size_t smem; bool ss;
-      int gx = ppm::sweep_grid_x(md, a.n_items, n_sm, &wpc, &smem, &ss);
-      if (!ss) { d_gslots.alloc((size_t)std::max(gx, n_sm * 2) * 8 * prog.n_slots * 32); a.gslots = d_gslots.p; }
+      ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm);
+      d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
       CK(cudaEventRecord(ev0, s));
-      ppm::launch_sweep(a, gx, wpc, smem, ss, s);
+      ppm::launch_sweep(a, pl, s);
       CK(cudaEventRecord(ev1, s));
       timed = true;
       n_launches += 1;

@@ -13,6 +13,7 @@
 // masks; per-lineage partials live in shared memory as slots[slot][lane].
 #include "ppm_device_fns.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 
@@ -31,29 +32,92 @@ __global__ void prepass_i2_kernel(ModelDev m, TablesDev t, const double* i2_over
   if (p < t.P) prepass_i2_body(m, t, i2_override, p);
 }
 
-template <int R, bool SMEM_SLOTS>
-__global__ void __launch_bounds__(256, 2) sweep_kernel(SweepArgs a) {
+__device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes) {
+  // cooperative CTA copy, 16 B per thread per step; all staged arrays are 16-byte multiples and 16-byte aligned
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
+}
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+struct StageLayout {
+  size_t recs, blk, ops, cls, kap, yy, wt, total;
+};
+__host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
+  StageLayout L;
+  size_t o = 0;
+  L.recs = o; o += align16((size_t)(m.n_entries + 1) * sizeof(EntryRec));
+  L.blk = o;  o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
+  L.ops = o;  o += align16((size_t)m.n_ops * sizeof(NodeOpDev));
+  L.cls = o;  o += align16((size_t)m.n_nodes * sizeof(double4));
+  L.kap = o;  o += align16((size_t)m.n_nodes * sizeof(double2));
+  L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
+  L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
+  L.total = o;
+  return L;
+}
+__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16(((size_t)m.n_words * 32 + m.n_slots) * 4); }
+
+// CTA work unit = (parameter vector p, chunk of warps*items_per_warp pattern batches).  STAGED: the topology
+// program and p's tables are copied to shared memory once per unit and per-lineage partials live in shared
+// memory; otherwise everything is read from global memory (L1/L2) and the partials live in a global scratch.
+template <int R, bool STAGED>
+__global__ void __launch_bounds__(384, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  // shared memory: per warp { words[n_words][32] u32 | zw[n_slots] u32 | slots[n_slots][32] double2 }
-  const size_t slot_bytes = SMEM_SLOTS ? (size_t)m.n_slots * 32 * sizeof(double2) : 0;
-  const size_t head_bytes = (((size_t)m.n_words * 32 + m.n_slots) * 4 + 15) & ~(size_t)15;
-  unsigned char* wbase = smem_raw + (size_t)warp * (head_bytes + slot_bytes);
+  const StageLayout L = stage_layout(m);
+  const size_t head = warp_head_bytes(m);
+  const size_t per_warp = head + (STAGED ? (size_t)m.n_slots * 32 * sizeof(double2) : 0);
+  unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_warp;
   uint32_t* sw = reinterpret_cast<uint32_t*>(wbase);
   uint32_t* zw = sw + m.n_words * 32;
-  SlotStore<SMEM_SLOTS> slots;
-  if (SMEM_SLOTS) slots.base = reinterpret_cast<double2*>(wbase + head_bytes);
+  SlotStore<STAGED> slots;
+  if (STAGED) slots.base = reinterpret_cast<double2*>(wbase + head);
   else slots.base = a.gslots + ((size_t)blockIdx.x * wpc + warp) * (size_t)m.n_slots * 32;
-  // work item = (parameter vector, batch of 32 patterns); warps stride over the items
-  for (long long item = (long long)blockIdx.x * wpc + warp; item < a.n_items; item += (long long)gridDim.x * wpc) {
-    double contrib = sweep_item<R>(a, item, lane, sw, zw, slots);
-    if (a.mode == 1) continue;
-    // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
+  const int nbR = m.n_blocks * R;
+
+  const long long n_units = (long long)a.t.P * a.n_chunks;
+  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int p = (int)(unit / a.n_chunks);
+    const int chunk = (int)(unit % a.n_chunks);
+    ItemTables T;
+    if (STAGED) {
+      __syncthreads();  // the previous unit's readers are done
+      copy16(smem_raw + L.recs, a.t.recs + (size_t)p * (m.n_entries + 1), align16((size_t)(m.n_entries + 1) * sizeof(EntryRec)));
+      copy16(smem_raw + L.blk, m.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc)));
+      copy16(smem_raw + L.ops, m.ops, align16((size_t)m.n_ops * sizeof(NodeOpDev)));
+      copy16(smem_raw + L.cls, a.t.cls + (size_t)p * m.n_nodes, align16((size_t)m.n_nodes * sizeof(double4)));
+      copy16(smem_raw + L.kap, a.t.kap + (size_t)p * m.n_nodes, align16((size_t)m.n_nodes * sizeof(double2)));
+      copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
+      copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
+      __syncthreads();
+      T.recs = reinterpret_cast<const EntryRec*>(smem_raw + L.recs);
+      T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + L.blk);
+      T.ops = reinterpret_cast<const NodeOpDev*>(smem_raw + L.ops);
+      T.cls = reinterpret_cast<const double4*>(smem_raw + L.cls);
+      T.kap = reinterpret_cast<const double2*>(smem_raw + L.kap);
+      T.yy = reinterpret_cast<const double*>(smem_raw + L.yy);
+      T.wt = reinterpret_cast<const double*>(smem_raw + L.wt);
+    } else {
+      T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
+      T.blk = m.blk; T.ops = m.ops;
+      T.cls = a.t.cls + (size_t)p * m.n_nodes;
+      T.kap = a.t.kap + (size_t)p * m.n_nodes;
+      T.yy = a.t.yy + (size_t)p * nbR;
+      T.wt = m.slice_wt_pad;
+    }
+    for (int k = 0; k < a.items_per_warp; k++) {
+      const long long batch = ((long long)chunk * a.items_per_warp + k) * wpc + warp;
+      if (batch >= a.n_batches) break;
+      double contrib = sweep_item<R>(a, T, p, batch, lane, sw, zw, slots);
+      if (a.mode == 1) continue;
+      // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    if (lane == 0) a.partial[item] = contrib;
-    __syncwarp();
+      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+      if (lane == 0) a.partial[(size_t)p * a.n_batches + batch] = contrib;
+      __syncwarp();
+    }
   }
 }
 
@@ -82,7 +146,7 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
   prepass_nodes_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  int n = m.n_entries + m.n_slices;
+  int n = m.n_entries + 1 + m.n_blocks * m.R;
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }
@@ -90,40 +154,45 @@ void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_o
   prepass_i2_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t, i2_override);
 }
 
-static size_t per_warp_smem(const ModelDev& m, bool smem_slots) {
-  size_t head = (((size_t)m.n_words * 32 + m.n_slots) * 4 + 15) & ~(size_t)15;
-  return head + (smem_slots ? (size_t)m.n_slots * 32 * sizeof(double2) : 0);
+SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
+  SweepPlan pl{};
+  const size_t budget = 227 * 1024 - 1024;
+  const StageLayout L = stage_layout(m);
+  const size_t head = warp_head_bytes(m);
+  const size_t per_warp_staged = head + (size_t)m.n_slots * 32 * sizeof(double2);
+  int warps = 0;
+  if (L.total + 4 * per_warp_staged <= budget) warps = (int)std::min<size_t>(12, (budget - L.total) / per_warp_staged);
+  pl.staged = warps >= 4;
+  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(12, budget / std::max<size_t>(head, 1)));
+  if (n_batches < warps) warps = (int)std::max<long long>(1, n_batches);
+  pl.warps = warps;
+  long long total = n_batches * (long long)P;
+  long long ipw = total / ((long long)n_sm * warps * 4);
+  pl.items_per_warp = (int)std::max<long long>(1, std::min<long long>(8, ipw));
+  pl.n_chunks = (int)((n_batches + (long long)warps * pl.items_per_warp - 1) / ((long long)warps * pl.items_per_warp));
+  long long units = (long long)pl.n_chunks * P;
+  pl.grid_x = (int)std::min<long long>(units, pl.staged ? 2147483647LL : (long long)n_sm);
+  pl.smem_bytes = (pl.staged ? L.total + per_warp_staged * warps : head * warps);
+  return pl;
+}
+size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
+  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * m.n_slots * 32;
 }
 
-int sweep_grid_x(const ModelDev& m, long long n_items, int n_sm, int* warps_per_cta, size_t* smem_bytes, bool* smem_slots) {
-  const size_t budget = 100 * 1024;  // two CTAs per SM
-  bool ss = per_warp_smem(m, true) * 2 <= budget;
-  size_t pw = per_warp_smem(m, ss);
-  int wpc = (int)std::min<size_t>(8, budget / pw);
-  if (wpc < 1) wpc = 1;
-  if (n_items < wpc) wpc = (int)std::max<long long>(1, n_items);
-  *warps_per_cta = wpc;
-  *smem_bytes = pw * wpc;
-  *smem_slots = ss;
-  long long ctas = (n_items + wpc - 1) / wpc;
-  // shared-memory variant: one item per warp; global-slot variant: a persistent grid bounds the scratch
-  if (!ss) ctas = std::min<long long>(ctas, (long long)n_sm * 2);
-  return (int)std::min<long long>(ctas, 2147483647LL);
-}
-
-template <int R, bool SS>
-static void launch_sweep_t(const SweepArgs& a, int grid_x, int wpc, size_t smem, cudaStream_t s) {
+template <int R, bool ST>
+static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<R, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(sweep_kernel<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  sweep_kernel<R, SS><<<grid_x, wpc * 32, smem, s>>>(a);
+  sweep_kernel<R, ST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
 
-void launch_sweep(const SweepArgs& a, int grid_x, int wpc, size_t smem, bool smem_slots, cudaStream_t s) {
-  if (smem_slots) launch_sweep_t<8, true>(a, grid_x, wpc, smem, s);
-  else launch_sweep_t<8, false>(a, grid_x, wpc, smem, s);
+void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
+  a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp;
+  if (pl.staged) launch_sweep_t<8, true>(a, pl, s);
+  else launch_sweep_t<8, false>(a, pl, s);
 }
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s) {
   reduce_kernel<<<P, 256, 0, s>>>(partial, nx, out);

@@ -20,6 +20,14 @@ enum {
 struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
 };
+struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block are [e_leaf0,e_slot0) [e_slot0,e_part0) [e_part0,e_end)
+  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_part0, e_end;
+};
+struct __align__(16) EntryRec {
+  double K;       // pi1 * exp(-(g2+l2) * (t_block - h_lineage))   (per parameter vector)
+  int32_t ref;    // full-leaf segment: leaf bit position; full-slot segment: slot; partial segment: slot or -(pos+1)
+  uint32_t mask;  // slices of the block at which the lineage is alive
+};
 
 struct ModelDev {
   int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
@@ -29,10 +37,11 @@ struct ModelDev {
   const int* left; const int* right; const int* parent;
   const double* bl; const double* height;
   // slices
-  const double* slice_t; const double* slice_wt;
+  const double* slice_t; const double* slice_wt_pad;  // [n_slices], [n_blocks*R] (0 for padding slices)
   // program
-  const int* blk_slice0; const int* blk_nslices; const int* blk_op0; const int* blk_ent0;
-  const NodeOpDev* ops; const uint32_t* entries; const int* entry_node; const int* entry_block;
+  const BlockDesc* blk;     // [n_blocks + 1]; the last one only carries the tail node ops
+  const NodeOpDev* ops;
+  const int* entry_ref; const uint32_t* entry_mask; const int* entry_node; const int* entry_block;  // [n_entries]
   // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq
   const uint32_t* words; long long n_pat, n_pat_pad;
   const int* counts; const int* mrca; const int* freq;
@@ -46,8 +55,8 @@ struct TablesDev {
   double4* cls;          // [P][n_nodes]  {S0,T0,S1,T1} log-domain pure-loss factors of the branch above a node
   double2* kap;          // [P][n_nodes]  {pi1*E, (1-pi1)*E}, E = exp(-(g2+l2)*bl)
   double2* d1u;          // [P][n_nodes]  {log(V+U)-log V, log U}: Private "gained below the root" tables
-  double* kent;          // [P][n_entries] pi1*exp(-(g2+l2)*(t_block - h_lineage))
-  double* yy;            // [P][n_slices]  exp(-(g2+l2)*(t_slice - t_block))
+  EntryRec* recs;        // [P][n_entries+1]
+  double* yy;            // [P][n_blocks*R] exp(-(g2+l2)*(t_slice - t_block)), 0 for padding slices
   double* scal;          // [P][SC_COUNT]
   double* zeta;          // [P][2][n_nodes] scratch: zero-row log p1 per node for cat 0 / cat 1
 };
@@ -58,6 +67,7 @@ struct SweepArgs {
   int mode;              // 0: log-likelihood partial sums, 1: zero row (writes SC_IZ_*), 2: + categories/components
   long long first, count;  // pattern range
   long long n_batches, n_items;  // ceil(count/32) and P * n_batches
+  int n_chunks, items_per_warp;  // CTA work unit = (parameter vector, chunk of warps*items_per_warp batches)
   double* partial;       // [P][n_batches]
   signed char* cat;      // [count] (mode 2, P == 1)
   double* comp;          // [count][3] (mode 2)
@@ -69,8 +79,10 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
-int sweep_grid_x(const ModelDev& m, long long n_items, int n_sm, int* warps_per_cta, size_t* smem_bytes, bool* smem_slots);
-void launch_sweep(const SweepArgs& a, int grid_x, int warps_per_cta, size_t smem_bytes, bool smem_slots, cudaStream_t s);
+struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks; size_t smem_bytes; bool staged; };
+SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm);
+size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 elements of global slot scratch (0 if staged)
+void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s);
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s);
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
 double run_fp64_peak(int device);

@@ -41,31 +41,32 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     for (long long j = 0; j < count; j++)
       for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * count + j] = pat.words[(size_t)j * pat.n_words + w];
     std::vector<uint32_t> zeros(pat.n_words * 32, 0u);
-    std::vector<int> eb(prog.entries.size());
-    for (int b = 0; b < prog.n_blocks; b++)
-      for (int e = prog.blk_ent0[b]; e < prog.blk_ent0[b + 1]; e++) eb[e] = b;
     static_assert(sizeof(NodeOpDev) == sizeof(NodeOp), "layout");
+    static_assert(sizeof(BlockDesc) == sizeof(BlockDescHost), "layout");
+    std::vector<double> wt_pad((size_t)std::max(prog.n_blocks, 1) * prog.R, 0.);
+    std::copy(tree.slice_wt.begin(), tree.slice_wt.end(), wt_pad.begin());
     ModelDev md{};
     md.n_nodes = tree.n_nodes; md.n_leaves = tree.n_leaves; md.n_words = pat.n_words; md.n_slices = tree.n_slices;
-    md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entries.size();
+    md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entry_ref.size();
     md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
     md.left = tree.left.data(); md.right = tree.right.data(); md.parent = tree.parent.data();
     md.bl = tree.bl.data(); md.height = tree.height.data();
-    md.slice_t = tree.slice_t.data(); md.slice_wt = tree.slice_wt.data();
-    md.blk_slice0 = prog.blk_slice0.data(); md.blk_nslices = prog.blk_nslices.data();
-    md.blk_op0 = prog.blk_op0.data(); md.blk_ent0 = prog.blk_ent0.data();
-    md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data()); md.entries = prog.entries.data();
-    md.entry_node = prog.entry_node.data(); md.entry_block = eb.data();
+    md.slice_t = tree.slice_t.data(); md.slice_wt_pad = wt_pad.data();
+    md.blk = reinterpret_cast<const BlockDesc*>(prog.blk.data());
+    md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data());
+    md.entry_ref = prog.entry_ref.data(); md.entry_mask = prog.entry_mask.data();
+    md.entry_node = prog.entry_node.data(); md.entry_block = prog.entry_block.data();
     md.words = wm.data(); md.n_pat = count; md.n_pat_pad = count;
     md.counts = pat.counts.data(); md.mrca = pat.mrca.data(); md.freq = pat.freq.data(); md.zero_words = zeros.data();
 
     const size_t nn = tree.n_nodes;
     std::vector<double4> cls(P * nn);
     std::vector<double2> kap(P * nn), d1u(P * nn);
-    std::vector<double> kent((size_t)P * std::max<size_t>(prog.entries.size(), 1)), yy((size_t)P * std::max(tree.n_slices, 1));
+    std::vector<EntryRec> recs((size_t)P * (prog.entry_ref.size() + 1));
+    std::vector<double> yy((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
     std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 2 * nn), i2ovr(P);
     TablesDev t{};
-    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.kent = kent.data();
+    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
 
     std::vector<uint32_t> sw(pat.n_words), zw(prog.n_slots);
@@ -78,9 +79,12 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
       for (int p = 0; p < nP; p++) {
         double s = 0;
         for (long long bt = 0; bt < a.n_batches; bt++) {
-          long long item = (long long)p * a.n_batches + bt;
-          if (prog.R == 8) s += sweep_item<8>(a, item, 0, sw.data(), zw.data(), slots);
-          else if (prog.R == 4) s += sweep_item<4>(a, item, 0, sw.data(), zw.data(), slots);
+          ItemTables T;
+          T.recs = recs.data() + (size_t)p * (md.n_entries + 1); T.blk = md.blk; T.ops = md.ops;
+          T.cls = cls.data() + (size_t)p * nn; T.kap = kap.data() + (size_t)p * nn;
+          T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
+          if (prog.R == 8) s += sweep_item<8>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
+          else if (prog.R == 4) s += sweep_item<4>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else throw std::runtime_error("emulator built for R in {4,8}");
         }
         if (ll) ll[p] = s;
@@ -88,7 +92,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     };
     for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p);
     for (int p = 0; p < P; p++)
-      for (int i = 0; i < md.n_entries + md.n_slices; i++) prepass_tables_body(md, t, p, i);
+      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R; i++) prepass_tables_body(md, t, p, i);
     run(1, P, nullptr, nullptr, nullptr, true);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
     run(0, P, out_ll, nullptr, nullptr, false);
