@@ -443,7 +443,15 @@ Program build_program(const Tree& t, int R) {
   }
   double fp64 = 0;
   for (int b = 0; b < nb; b++) {
-    auto cls_of = [&](const Ent& e) { return (e.i0 == 0 && e.i1 == R) ? (e.leaf ? 0 : 1) : 2; };
+    const int nsl = pg.blk[b].nslices;
+    // 0 leaf alive in every slice, 1 internal alive in every slice, 2 suffix [i0,R), 3 prefix [0,i1), 4 other
+    auto cls_of = [&](const Ent& e) {
+      const bool to_end = e.i1 == nsl;         // in a short last block the padding slices carry weight 0
+      if (e.i0 == 0 && to_end) return e.leaf ? 0 : 1;
+      if (to_end) return 2;
+      if (e.i0 == 0) return 3;
+      return 4;
+    };
     std::stable_sort(ent[b].begin(), ent[b].end(), [&](const Ent& x, const Ent& y) {
       int cx = cls_of(x), cy = cls_of(y);
       if (cx != cy) return cx < cy;
@@ -451,28 +459,37 @@ Program build_program(const Tree& t, int R) {
       return x.ref < y.ref;
     });
     BlockDescHost& bd = pg.blk[b];
-    bd.e_leaf0 = (int)pg.entry_ref.size();
-    bd.e_slot0 = bd.e_part0 = -1;
+    int seg0[6] = {-1, -1, -1, -1, -1, -1};
     for (const Ent& e : ent[b]) {
       int c = cls_of(e), at = (int)pg.entry_ref.size();
-      if (c >= 1 && bd.e_slot0 < 0) bd.e_slot0 = at;
-      if (c >= 2 && bd.e_part0 < 0) bd.e_part0 = at;
-      if (c == 2) pg.n_partial++; else pg.n_full++;
+      for (int k = 0; k <= c; k++) if (seg0[k] < 0) seg0[k] = at;
+      if (c >= 2) pg.n_partial++; else pg.n_full++;
       fp64 += 1 + 2 * (e.i1 - e.i0);
-      pg.entry_ref.push_back(c == 2 && e.leaf ? -(e.ref + 1) : e.ref);
-      pg.entry_mask.push_back(((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+      uint32_t mk = 0; int ref = e.ref;
+      if (c == 0) { ref = e.ref >> 5; mk = 1u << (e.ref & 31); }
+      else if (c == 1) mk = 0;
+      else {
+        if (e.leaf) ref = -(e.ref + 1);
+        mk = c == 2 ? (uint32_t)e.i0 : c == 3 ? (uint32_t)e.i1 : (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+      }
+      pg.entry_ref.push_back(ref);
+      pg.entry_mask.push_back(mk);
       pg.entry_node.push_back(e.node);
       pg.entry_block.push_back(b);
     }
-    bd.e_end = (int)pg.entry_ref.size();
-    if (bd.e_part0 < 0) bd.e_part0 = bd.e_end;
-    if (bd.e_slot0 < 0) bd.e_slot0 = bd.e_part0;
-    // upper 16 mask bits: the next record's reference within the same full segment (0 = always-valid dummy),
-    // which lets the kernel issue the next operand load before it has read the next record
-    for (int e = bd.e_leaf0; e + 1 < bd.e_slot0; e++) pg.entry_mask[e] |= (uint32_t)pg.entry_ref[e + 1] << 16;
-    for (int e = bd.e_slot0; e + 1 < bd.e_part0; e++) pg.entry_mask[e] |= (uint32_t)pg.entry_ref[e + 1] << 16;
+    const int end = (int)pg.entry_ref.size();
+    seg0[5] = end;
+    for (int k = 4; k >= 0; k--) if (seg0[k] < 0) seg0[k] = seg0[k + 1];
+    bd.e_leaf0 = seg0[0]; bd.e_slot0 = seg0[1]; bd.e_suf0 = seg0[2]; bd.e_pre0 = seg0[3]; bd.e_gen0 = seg0[4]; bd.e_end = end;
+    // prefetch hints: leaves name the next leaf's word (upper half of ref), slots the next slot (upper half of mask);
+    // 0 is an always-valid dummy at the end of a segment
+    for (int e = bd.e_leaf0; e + 1 < bd.e_slot0; e++) pg.entry_ref[e] |= pg.entry_ref[e + 1] << 16;
+    for (int e = bd.e_slot0; e + 1 < bd.e_suf0; e++) pg.entry_mask[e] |= (uint32_t)pg.entry_ref[e + 1] << 16;
   }
-  pg.blk[nb].e_leaf0 = pg.blk[nb].e_slot0 = pg.blk[nb].e_part0 = pg.blk[nb].e_end = (int)pg.entry_ref.size();
+  {
+    BlockDescHost& bd = pg.blk[nb];
+    bd.e_leaf0 = bd.e_slot0 = bd.e_suf0 = bd.e_pre0 = bd.e_gen0 = bd.e_end = (int)pg.entry_ref.size();
+  }
   // + node ops (8 merge + 2 renorm + 4 class adds), block ends (~3 per slice), epilogue (~60)
   pg.fp64_instr_per_eval = fp64 + 14.0 * (nl - 1) + 3.0 * S + 60;
   return pg;

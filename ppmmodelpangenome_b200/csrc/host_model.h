@@ -58,8 +58,8 @@ struct NodeOp {
   int32_t i0;           // first slice of the current block at which the node is alive (0..R); R = none
   int32_t pad;
 };
-struct BlockDescHost {  // entry segments: full leaves [e_leaf0,e_slot0), full slots [e_slot0,e_part0), partial [e_part0,e_end)
-  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_part0, e_end;
+struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
+  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_suf0, e_pre0, e_gen0, e_end, pad0, pad1;
 };
 struct Program {
   int R = 8;
@@ -67,7 +67,7 @@ struct Program {
   std::vector<BlockDescHost> blk;                 // [n_blocks+1]; blk[n_blocks] carries the node ops after the last block
   std::vector<NodeOp> ops;
   std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
-  std::vector<uint32_t> entry_mask;               // alive slices of the block
+  std::vector<uint32_t> entry_mask;               // see EntryRec::mask
   std::vector<int32_t> entry_node, entry_block;   // node id / block of each entry (for the K table)
   int64_t n_full = 0, n_partial = 0;
   // modelled FP64 instruction count per pattern-eval of the main kernel

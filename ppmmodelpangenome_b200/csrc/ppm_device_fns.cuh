@@ -19,6 +19,7 @@
 #define ppm_syncwarp() __syncwarp()
 #define ppm_ballot(pred) __ballot_sync(0xffffffffu, (pred))
 #define ppm_any(pred) __any_sync(0xffffffffu, (pred))
+#define ppm_all(pred) __all_sync(0xffffffffu, (pred))
 #define ppm_hiloint2double(hi, lo) __hiloint2double((hi), (lo))
 #define ppm_double2hiint(x) __double2hiint(x)
 #else  // single-lane emulation
@@ -26,6 +27,7 @@
 #define ppm_syncwarp() ((void)0)
 #define ppm_ballot(pred) ((pred) ? 1u : 0u)
 #define ppm_any(pred) (pred)
+#define ppm_all(pred) (pred)
 static inline double ppm_hiloint2double(int hi, int lo) {
   unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
   double d; std::memcpy(&d, &u, 8); return d;
@@ -223,6 +225,31 @@ PPM_HD bool products_small(const double (&prod)[R]) {
   return mn < ((1023 - 480) << 20);
 }
 
+// prod[i] *= a - bb*Y[i] for the slices [i0, R) (suffix: a lineage born inside the block) or [0, i1) (prefix: a
+// lineage merged inside the block).  i0/i1 are warp-uniform: a jump into an unrolled sequence, no masks.
+#define PPM_U(k) if (k < R) prod[k < R ? k : 0] *= fma(-bb, Y[k < R ? k : 0], a);
+template <int R>
+PPM_HD void update_suffix(double (&prod)[R], const double (&Y)[R], double a, double bb, int i0) {
+  switch (i0) {
+    case 0: PPM_U(0) case 1: PPM_U(1) case 2: PPM_U(2) case 3: PPM_U(3)
+    case 4: PPM_U(4) case 5: PPM_U(5) case 6: PPM_U(6) case 7: PPM_U(7)
+    case 8: PPM_U(8) case 9: PPM_U(9) case 10: PPM_U(10) case 11: PPM_U(11)
+    case 12: PPM_U(12) case 13: PPM_U(13) case 14: PPM_U(14) case 15: PPM_U(15)
+    default: break;
+  }
+}
+template <int R>
+PPM_HD void update_prefix(double (&prod)[R], const double (&Y)[R], double a, double bb, int i1) {
+  switch (i1) {
+    case 16: PPM_U(15) case 15: PPM_U(14) case 14: PPM_U(13) case 13: PPM_U(12)
+    case 12: PPM_U(11) case 11: PPM_U(10) case 10: PPM_U(9) case 9: PPM_U(8)
+    case 8: PPM_U(7) case 7: PPM_U(6) case 6: PPM_U(5) case 5: PPM_U(4)
+    case 4: PPM_U(3) case 3: PPM_U(2) case 2: PPM_U(1) case 1: PPM_U(0)
+    default: break;
+  }
+}
+#undef PPM_U
+
 // One work item = PPM_LANES patterns (one per lane) x one parameter vector.  Returns this lane's count*log-mixture.
 // sw: per-warp pattern words [n_words][PPM_LANES]; zw: per-warp all-zero-subtree masks per slot.
 template <int R, class Slots>
@@ -317,14 +344,13 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
     // before the current products (software prefetch); chunks of 16 entries are followed by a range check.
     for (int e = bd.e_leaf0; e < bd.e_slot0;) {
       const int ce = (e + 16 < bd.e_slot0) ? e + 16 : bd.e_slot0;
-      double K; int ref; uint32_t mk;
+      double K; int ref; uint32_t mk;   // leaf records: ref = word | next word << 16, mk = the leaf's bit in that word
       load_rec(T.recs, e, K, ref, mk);
-      uint32_t wv = sw[(ref >> 5) * PPM_LANES + lane];
+      uint32_t wv = sw[(ref & 0xffff) * PPM_LANES + lane];
 #pragma unroll 2
       for (; e < ce; e++) {
-        const int nref = (int)(mk >> 16);
-        const uint32_t wn = sw[(nref >> 5) * PPM_LANES + lane];
-        const bool bit = (wv >> (ref & 31)) & 1u;
+        const uint32_t wn = sw[(int)((uint32_t)ref >> 16) * PPM_LANES + lane];
+        const bool bit = (wv & mk) != 0u;
         const double aa = bit ? la1 : la0;
         const double bb = (bit ? ld1 : ld0) * K;
         load_rec(T.recs, e + 1, K, ref, mk);  // the table carries one padding record
@@ -335,8 +361,8 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
       if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
     // ... internal lineages (partials in slots)
-    for (int e = bd.e_slot0; e < bd.e_part0;) {
-      const int ce = (e + 16 < bd.e_part0) ? e + 16 : bd.e_part0;
+    for (int e = bd.e_slot0; e < bd.e_suf0;) {
+      const int ce = (e + 16 < bd.e_suf0) ? e + 16 : bd.e_suf0;
       double K; int ref; uint32_t mk;
       load_rec(T.recs, e, K, ref, mk);
       double2 ad = slots.ld(ref, lane);
@@ -351,8 +377,8 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
       }
       if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
-    // ---- entries alive in part of the block (lineages born or merged inside it): slice mask
-    for (int e = bd.e_part0; e < bd.e_end; e++) {
+    // ---- entries alive in part of the block: born inside it (suffix), merged inside it (prefix), or both (mask)
+    for (int e = bd.e_suf0; e < bd.e_end; e++) {
       double K; int ref; uint32_t mk;
       load_rec(T.recs, e, K, ref, mk);
       double2 ad;
@@ -362,20 +388,41 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
         ad = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
       } else ad = slots.ld(ref, lane);
       const double bb = ad.y * K;
+      if (e < bd.e_pre0) update_suffix<R>(prod, Y, ad.x, bb, (int)(mk & 0xffffu));
+      else if (e < bd.e_gen0) update_prefix<R>(prod, Y, ad.x, bb, (int)(mk & 0xffffu));
+      else {
 #pragma unroll
-      for (int i = 0; i < R; i++)
-        if (mk & (1u << i)) prod[i] *= fma(-bb, Y[i], ad.x);
+        for (int i = 0; i < R; i++)
+          if (mk & (1u << i)) prod[i] *= fma(-bb, Y[i], ad.x);
+      }
       if ((e & 15) == 15 && ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
     // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
+    {
+      bool same = true;
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-      double v = prod[i] * T.wt[b * R + i];   // padding slices carry weight 0
-      if (v != 0.) {
-        int e = ex[i];
-        if (Im == 0.) { Im = v; Ie = e; }
-        else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
-        else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
+      for (int i = 1; i < R; i++) same = same && (ex[i] == ex[0]);
+      if (ppm_all(same)) {  // usual case: one common exponent, one scaled add
+        double v = 0.;
+#pragma unroll
+        for (int i = 0; i < R; i++) v = fma(prod[i], T.wt[b * R + i], v);  // padding slices carry weight 0
+        if (v != 0.) {
+          int e = ex[0];
+          if (Im == 0.) { Im = v; Ie = e; }
+          else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
+          else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          double v = prod[i] * T.wt[b * R + i];
+          if (v != 0.) {
+            int e = ex[i];
+            if (Im == 0.) { Im = v; Ie = e; }
+            else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
+            else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
+          }
+        }
       }
     }
   }

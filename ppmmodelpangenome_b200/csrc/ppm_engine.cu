@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -45,6 +46,13 @@ struct DevBuf {
 };
 
 }  // namespace
+
+// slices per block of the sweep program: 8 (default) or 16; PPM_R overrides (tuning knob)
+static int program_R() {
+  const char* e = std::getenv("PPM_R");
+  int r = e ? std::atoi(e) : 8;
+  return r == 16 ? 16 : 8;
+}
 
 struct ppm_engine {
   ppm::Tree tree;
@@ -101,7 +109,7 @@ struct ppm_engine {
   }
 
   void upload_model() {
-    prog = ppm::build_program(tree, 8);
+    prog = ppm::build_program(tree, program_R());
     // shard: contiguous, equal-sized slices of the deduplicated patterns (work per pattern is uniform)
     long long np = pat.n_patterns;
     first = np * shard_rank / shard_world;
@@ -223,7 +231,7 @@ static int finish_create(ppm_handle* out, std::unique_ptr<ppm_engine>& e, int de
   e->shard_rank = rank; e->shard_world = world;
   if (device < 0) {  // host-only handle: model inspection, no compute
     e->device = -1;
-    e->prog = ppm::build_program(e->tree, 8);
+    e->prog = ppm::build_program(e->tree, program_R());
     long long np = e->pat.n_patterns;
     e->first = np * rank / world;
     e->count = np * (rank + 1) / world - e->first;

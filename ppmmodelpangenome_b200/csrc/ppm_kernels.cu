@@ -191,8 +191,13 @@ static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t
 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
   a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp;
-  if (pl.staged) launch_sweep_t<8, true>(a, pl, s);
-  else launch_sweep_t<8, false>(a, pl, s);
+  if (a.m.R == 16) {
+    if (pl.staged) launch_sweep_t<16, true>(a, pl, s);
+    else launch_sweep_t<16, false>(a, pl, s);
+  } else {
+    if (pl.staged) launch_sweep_t<8, true>(a, pl, s);
+    else launch_sweep_t<8, false>(a, pl, s);
+  }
 }
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s) {
   reduce_kernel<<<P, 256, 0, s>>>(partial, nx, out);

@@ -20,13 +20,16 @@ enum {
 struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
 };
-struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block are [e_leaf0,e_slot0) [e_slot0,e_part0) [e_part0,e_end)
-  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_part0, e_end;
+struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
+  // [e_leaf0,e_slot0) leaves alive in every slice | [e_slot0,e_suf0) internal lineages alive in every slice |
+  // [e_suf0,e_pre0) born inside the block | [e_pre0,e_gen0) merged inside the block | [e_gen0,e_end) both
+  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_suf0, e_pre0, e_gen0, e_end, pad0, pad1;
 };
 struct __align__(16) EntryRec {
   double K;       // pi1 * exp(-(g2+l2) * (t_block - h_lineage))   (per parameter vector)
-  int32_t ref;    // full-leaf segment: leaf bit position; full-slot segment: slot; partial segment: slot or -(pos+1)
-  uint32_t mask;  // slices of the block at which the lineage is alive
+  int32_t ref;    // leaf segment: word | next word << 16; slot segment: slot; other segments: slot or -(bit position + 1)
+  uint32_t mask;  // leaf segment: the leaf's bit in its word; slot segment: next slot << 16; suffix: first slice;
+                  // prefix: end slice; generic: slice mask
 };
 
 struct ModelDev {
