@@ -444,51 +444,42 @@ Program build_program(const Tree& t, int R) {
   double fp64 = 0;
   for (int b = 0; b < nb; b++) {
     const int nsl = pg.blk[b].nslices;
-    // 0 leaf alive in every slice, 1 internal alive in every slice, 2 suffix [i0,R), 3 prefix [0,i1), 4 other
+    // 0 leaf alive in every slice, 1 internal alive in every slice, 2 leaf merged inside the block,
+    // 3 internal lineage born and/or merged inside the block
     auto cls_of = [&](const Ent& e) {
-      const bool to_end = e.i1 == nsl;         // in a short last block the padding slices carry weight 0
-      if (e.i0 == 0 && to_end) return e.leaf ? 0 : 1;
-      if (to_end) return 2;
-      if (e.i0 == 0) return 3;
-      return 4;
+      const bool full = e.i0 == 0 && e.i1 == nsl;  // in a short last block the padding slices carry weight 0
+      return full ? (e.leaf ? 0 : 1) : (e.leaf ? 2 : 3);
     };
     std::stable_sort(ent[b].begin(), ent[b].end(), [&](const Ent& x, const Ent& y) {
       int cx = cls_of(x), cy = cls_of(y);
       if (cx != cy) return cx < cy;
-      if (x.leaf != y.leaf) return x.leaf;
       return x.ref < y.ref;
     });
     BlockDescHost& bd = pg.blk[b];
-    int seg0[6] = {-1, -1, -1, -1, -1, -1};
+    int seg0[5] = {-1, -1, -1, -1, -1};
     for (const Ent& e : ent[b]) {
       int c = cls_of(e), at = (int)pg.entry_ref.size();
       for (int k = 0; k <= c; k++) if (seg0[k] < 0) seg0[k] = at;
       if (c >= 2) pg.n_partial++; else pg.n_full++;
       fp64 += 1 + 2 * (e.i1 - e.i0);
-      uint32_t mk = 0; int ref = e.ref;
-      if (c == 0) { ref = e.ref >> 5; mk = 1u << (e.ref & 31); }
-      else if (c == 1) mk = 0;
-      else {
-        if (e.leaf) ref = -(e.ref + 1);
-        mk = c == 2 ? (uint32_t)e.i0 : c == 3 ? (uint32_t)e.i1 : (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
-      }
-      pg.entry_ref.push_back(ref);
-      pg.entry_mask.push_back(mk);
+      const uint32_t live = c < 2 ? ((1u << R) - 1u) : (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+      pg.entry_ref.push_back(c == 0 ? (e.ref >> 5) : e.ref);
+      pg.entry_mask.push_back(c == 0 ? (1u << (e.ref & 31)) : live);
       pg.entry_node.push_back(e.node);
       pg.entry_block.push_back(b);
     }
     const int end = (int)pg.entry_ref.size();
-    seg0[5] = end;
-    for (int k = 4; k >= 0; k--) if (seg0[k] < 0) seg0[k] = seg0[k + 1];
-    bd.e_leaf0 = seg0[0]; bd.e_slot0 = seg0[1]; bd.e_suf0 = seg0[2]; bd.e_pre0 = seg0[3]; bd.e_gen0 = seg0[4]; bd.e_end = end;
-    // prefetch hints: leaves name the next leaf's word (upper half of ref), slots the next slot (upper half of mask);
-    // 0 is an always-valid dummy at the end of a segment
-    for (int e = bd.e_leaf0; e + 1 < bd.e_slot0; e++) pg.entry_ref[e] |= pg.entry_ref[e + 1] << 16;
-    for (int e = bd.e_slot0; e + 1 < bd.e_suf0; e++) pg.entry_mask[e] |= (uint32_t)pg.entry_ref[e + 1] << 16;
+    seg0[4] = end;
+    for (int k = 3; k >= 0; k--) if (seg0[k] < 0) seg0[k] = seg0[k + 1];
+    bd.e_leaf0 = seg0[0]; bd.e_slot0 = seg0[1]; bd.e_pleaf0 = seg0[2]; bd.e_pslot0 = seg0[3]; bd.e_end = end;
+    // prefetch hints: the upper half of ref names the next record's operand within the same segment
+    // (0 = an always-valid dummy at the end of a segment)
+    for (int k = 0; k < 4; k++)
+      for (int e = seg0[k]; e + 1 < seg0[k + 1]; e++) pg.entry_ref[e] |= (pg.entry_ref[e + 1] & 0xffff) << 16;
   }
   {
     BlockDescHost& bd = pg.blk[nb];
-    bd.e_leaf0 = bd.e_slot0 = bd.e_suf0 = bd.e_pre0 = bd.e_gen0 = bd.e_end = (int)pg.entry_ref.size();
+    bd.e_leaf0 = bd.e_slot0 = bd.e_pleaf0 = bd.e_pslot0 = bd.e_end = (int)pg.entry_ref.size();
   }
   // + node ops (8 merge + 2 renorm + 4 class adds), block ends (~3 per slice), epilogue (~60)
   pg.fp64_instr_per_eval = fp64 + 14.0 * (nl - 1) + 3.0 * S + 60;

@@ -59,7 +59,7 @@ struct NodeOp {
   int32_t pad;
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
-  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_suf0, e_pre0, e_gen0, e_end, pad0, pad1;
+  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
 };
 struct Program {
   int R = 8;

@@ -158,6 +158,16 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
       v = exp(-lam * (m.slice_t[j] - tb));
     }
     t.yy[(size_t)p * n_pad + j] = v;
+  } else if (i <= m.n_entries + n_pad + m.n_ops) {
+    // per-op record: the branch tables of the two children, contiguous (no dependent index loads in the sweep)
+    int o = i - m.n_entries - n_pad - 1;
+    const NodeOpDev op = m.ops[o];
+    const double2 kl = t.kap[(size_t)p * m.n_nodes + op.lnode], kr = t.kap[(size_t)p * m.n_nodes + op.rnode];
+    const double4 cl = t.cls[(size_t)p * m.n_nodes + op.lnode], cr = t.cls[(size_t)p * m.n_nodes + op.rnode];
+    double* r = t.oprec + ((size_t)p * m.n_ops + o) * OPREC_DOUBLES;
+    r[0] = kl.x; r[1] = kl.y; r[2] = kr.x; r[3] = kr.y;
+    r[4] = cl.x; r[5] = cl.y; r[6] = cl.z; r[7] = cl.w;
+    r[8] = cr.x; r[9] = cr.y; r[10] = cr.z; r[11] = cr.w;
   }
 }
 
@@ -190,20 +200,19 @@ struct SlotStore {
 struct ItemTables {
   const EntryRec* recs;   // [n_entries + 1]
   const BlockDesc* blk;   // [n_blocks + 1]
-  const NodeOpDev* ops;
-  const double4* cls;     // [n_nodes]
-  const double2* kap;     // [n_nodes]
+  const NodeOpDev* ops;   // [n_ops]
+  const double* oprec;    // [n_ops][OPREC_DOUBLES]
   const double* yy;       // [n_blocks * R]
   const double* wt;       // [n_blocks * R]
 };
 
-// One 16-byte load per record: K | ref | (next_ref << 16 | slice mask)
-PPM_HD void load_rec(const EntryRec* recs, int e, double& K, int& ref, uint32_t& mask) {
+// One 16-byte load per record: K | ref | mask
+PPM_HD void load_rec(const EntryRec* recs, int e, double& K, uint32_t& ref, uint32_t& mask) {
 #if defined(__CUDA_ARCH__)
   const double2 v = reinterpret_cast<const double2*>(recs)[e];
-  K = v.x; ref = __double2loint(v.y); mask = (uint32_t)__double2hiint(v.y);
+  K = v.x; ref = (uint32_t)__double2loint(v.y); mask = (uint32_t)__double2hiint(v.y);
 #else
-  K = recs[e].K; ref = recs[e].ref; mask = recs[e].mask;
+  K = recs[e].K; ref = (uint32_t)recs[e].ref; mask = recs[e].mask;
 #endif
 }
 
@@ -225,30 +234,24 @@ PPM_HD bool products_small(const double (&prod)[R]) {
   return mn < ((1023 - 480) << 20);
 }
 
-// prod[i] *= a - bb*Y[i] for the slices [i0, R) (suffix: a lineage born inside the block) or [0, i1) (prefix: a
-// lineage merged inside the block).  i0/i1 are warp-uniform: a jump into an unrolled sequence, no masks.
-#define PPM_U(k) if (k < R) prod[k < R ? k : 0] *= fma(-bb, Y[k < R ? k : 0], a);
+// prod[i] *= a + nbb*Y[i] for the slices i named by the (warp-uniform) mask.  Straight-line: every slice is
+// computed and the dead ones are discarded by a select (ptxas turns predicated FP64 into exactly this anyway).
 template <int R>
-PPM_HD void update_suffix(double (&prod)[R], const double (&Y)[R], double a, double bb, int i0) {
-  switch (i0) {
-    case 0: PPM_U(0) case 1: PPM_U(1) case 2: PPM_U(2) case 3: PPM_U(3)
-    case 4: PPM_U(4) case 5: PPM_U(5) case 6: PPM_U(6) case 7: PPM_U(7)
-    case 8: PPM_U(8) case 9: PPM_U(9) case 10: PPM_U(10) case 11: PPM_U(11)
-    case 12: PPM_U(12) case 13: PPM_U(13) case 14: PPM_U(14) case 15: PPM_U(15)
-    default: break;
+PPM_HD void masked_update(double (&prod)[R], const double (&Y)[R], double a, double nbb, uint32_t mk) {
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    const double t = prod[i] * fma(nbb, Y[i], a);
+    prod[i] = (mk & (1u << i)) ? t : prod[i];
   }
 }
-template <int R>
-PPM_HD void update_prefix(double (&prod)[R], const double (&Y)[R], double a, double bb, int i1) {
-  switch (i1) {
-    case 16: PPM_U(15) case 15: PPM_U(14) case 14: PPM_U(13) case 13: PPM_U(12)
-    case 12: PPM_U(11) case 11: PPM_U(10) case 10: PPM_U(9) case 9: PPM_U(8)
-    case 8: PPM_U(7) case 7: PPM_U(6) case 6: PPM_U(5) case 5: PPM_U(4)
-    case 4: PPM_U(3) case 3: PPM_U(2) case 2: PPM_U(1) case 1: PPM_U(0)
-    default: break;
+
+PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) += v * 2^-e
+  if (v != 0.) {
+    if (Im == 0.) { Im = v; Ie = e; }
+    else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
+    else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
   }
 }
-#undef PPM_U
 
 // One work item = PPM_LANES patterns (one per lane) x one parameter vector.  Returns this lane's count*log-mixture.
 // sw: per-warp pattern words [n_words][PPM_LANES]; zw: per-warp all-zero-subtree masks per slot.
@@ -284,39 +287,37 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
 #pragma unroll
       for (int i = 0; i < R; i++) { prod[i] = 1.; ex[i] = X; Y[i] = T.yy[b * R + i]; }
     }
-    // ---- node ops: form every node born before the end of this block
+    // ---- node ops: form every node born before the end of this block.  Straight-line: both the "leaf" and the
+    // "slot" operand of each child are fetched and one is selected, so all loads of an op issue together.
     for (int o = bd.op0; o < bd.op1; o++) {
       const NodeOpDev op = T.ops[o];
+      const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
+      const bool lleaf = op.lref < 0, rleaf = op.rref < 0;
+      const int lpos = lleaf ? -(op.lref + 1) : 0, rpos = rleaf ? -(op.rref + 1) : 0;
+      const int lslot = lleaf ? 0 : op.lref, rslot = rleaf ? 0 : op.rref;
+      const uint32_t wl = sw[(lpos >> 5) * PPM_LANES + lane], wr = sw[(rpos >> 5) * PPM_LANES + lane];
+      const double2 Ls = slots.ld(lslot, lane), Rs = slots.ld(rslot, lane);
+      const uint32_t zls = zw[lslot], zrs = zw[rslot];
+      const bool bl = (wl >> (lpos & 31)) & 1u, br = (wr >> (rpos & 31)) & 1u;
+      const uint32_t zbl = ~ppm_ballot(bl), zbr = ~ppm_ballot(br);
       double2 L, Rr;
-      uint32_t zwl, zwr;
-      if (op.lref < 0) {
-        int pos = -(op.lref + 1);
-        bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
-        L = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
-        zwl = ~ppm_ballot(bit);
-      } else { L = slots.ld(op.lref, lane); zwl = zw[op.lref]; }
-      if (op.rref < 0) {
-        int pos = -(op.rref + 1);
-        bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
-        Rr = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
-        zwr = ~ppm_ballot(bit);
-      } else { Rr = slots.ld(op.rref, lane); zwr = zw[op.rref]; }
+      L.x = lleaf ? (bl ? la1 : la0) : Ls.x;  L.y = lleaf ? (bl ? ld1 : ld0) : Ls.y;
+      Rr.x = rleaf ? (br ? la1 : la0) : Rs.x; Rr.y = rleaf ? (br ? ld1 : ld0) : Rs.y;
+      const uint32_t zwl = lleaf ? zbl : zls, zwr = rleaf ? zbr : zrs;
       const uint32_t zwv = zwl & zwr;
       // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
       {
         const bool zl = (zwl >> lane) & 1u, zr = (zwr >> lane) & 1u;
         const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
-        const double4 cl = T.cls[op.lnode], cr = T.cls[op.rnode];
-        A0 += zl ? (zv ? 0. : cl.y) : cl.x;
-        A1 += zl ? (zv ? 0. : cl.w) : cl.z;
-        A0 += zr ? (zv ? 0. : cr.y) : cr.x;
-        A1 += zr ? (zv ? 0. : cr.w) : cr.z;
+        A0 += zl ? (zv ? 0. : orc[5]) : orc[4];
+        A1 += zl ? (zv ? 0. : orc[7]) : orc[6];
+        A0 += zr ? (zv ? 0. : orc[9]) : orc[8];
+        A1 += zr ? (zv ? 0. : orc[11]) : orc[10];
       }
       if (op.dst >= 0) {
         // Mobile merge (objects.cpp:427-435 in linear domain)
-        const double2 kl = T.kap[op.lnode], kr = T.kap[op.rnode];
-        double m0 = fma(-kl.x, L.y, L.x) * fma(-kr.x, Rr.y, Rr.x);
-        double m1 = fma(kl.y, L.y, L.x) * fma(kr.y, Rr.y, Rr.x);
+        double m0 = fma(-orc[0], L.y, L.x) * fma(-orc[2], Rr.y, Rr.x);
+        double m1 = fma(orc[1], L.y, L.x) * fma(orc[3], Rr.y, Rr.x);
         double d = m1 - m0;
         double av = fma(pi1, d, m0);
         // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
@@ -331,72 +332,83 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
             for (int i = 0; i < R; i++) if (i >= op.i0) ex[i] += k;
           }
         }
-        ppm_syncwarp();
+        // every lane reads back only what it wrote itself (its slot column; zw gets the same word from all lanes)
         slots.st(op.dst, lane, make_double2(av, d));
-        if (lane == 0) zw[op.dst] = zwv;
-        ppm_syncwarp();
+        zw[op.dst] = zwv;
       }
     }
     if (!real) break;
 
-    // ---- entries alive in every slice of the block: leaves (partials selected by the pattern bit) ...
-    // Each record names the NEXT record's reference in its upper mask bits, so the next operand load is issued
-    // before the current products (software prefetch); chunks of 16 entries are followed by a range check.
+    // ---- entries.  Each record names the NEXT record's operand in its upper bits, so the next operand load is
+    // issued before the current products (software prefetch); chunks of 16 entries end with a range check.
+    // (1) leaves alive in every slice of the block: partials selected by the pattern bit
     for (int e = bd.e_leaf0; e < bd.e_slot0;) {
       const int ce = (e + 16 < bd.e_slot0) ? e + 16 : bd.e_slot0;
-      double K; int ref; uint32_t mk;   // leaf records: ref = word | next word << 16, mk = the leaf's bit in that word
+      double K; uint32_t ref, mk;   // ref = word | next word << 16, mk = the leaf's bit in that word
       load_rec(T.recs, e, K, ref, mk);
-      uint32_t wv = sw[(ref & 0xffff) * PPM_LANES + lane];
+      uint32_t wv = sw[(ref & 0xffffu) * PPM_LANES + lane];
 #pragma unroll 2
       for (; e < ce; e++) {
-        const uint32_t wn = sw[(int)((uint32_t)ref >> 16) * PPM_LANES + lane];
+        const uint32_t wn = sw[(ref >> 16) * PPM_LANES + lane];
         const bool bit = (wv & mk) != 0u;
         const double aa = bit ? la1 : la0;
-        const double bb = (bit ? ld1 : ld0) * K;
+        const double nbb = (bit ? ld1 : ld0) * -K;
         load_rec(T.recs, e + 1, K, ref, mk);  // the table carries one padding record
 #pragma unroll
-        for (int i = 0; i < R; i++) prod[i] *= fma(-bb, Y[i], aa);
+        for (int i = 0; i < R; i++) prod[i] *= fma(nbb, Y[i], aa);
         wv = wn;
       }
       if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
-    // ... internal lineages (partials in slots)
-    for (int e = bd.e_slot0; e < bd.e_suf0;) {
-      const int ce = (e + 16 < bd.e_suf0) ? e + 16 : bd.e_suf0;
-      double K; int ref; uint32_t mk;
+    // (2) internal lineages alive in every slice: partials in slots; ref = slot | next slot << 16
+    for (int e = bd.e_slot0; e < bd.e_pleaf0;) {
+      const int ce = (e + 16 < bd.e_pleaf0) ? e + 16 : bd.e_pleaf0;
+      double K; uint32_t ref, mk;
       load_rec(T.recs, e, K, ref, mk);
-      double2 ad = slots.ld(ref, lane);
+      double2 ad = slots.ld((int)(ref & 0xffffu), lane);
 #pragma unroll 2
       for (; e < ce; e++) {
-        const double2 an = slots.ld((int)(mk >> 16), lane);
-        const double bb = ad.y * K;
+        const double2 an = slots.ld((int)(ref >> 16), lane);
+        const double nbb = ad.y * -K;
         load_rec(T.recs, e + 1, K, ref, mk);
 #pragma unroll
-        for (int i = 0; i < R; i++) prod[i] *= fma(-bb, Y[i], ad.x);
+        for (int i = 0; i < R; i++) prod[i] *= fma(nbb, Y[i], ad.x);
         ad = an;
       }
       if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
-    // ---- entries alive in part of the block: born inside it (suffix), merged inside it (prefix), or both (mask)
-    for (int e = bd.e_suf0; e < bd.e_end; e++) {
-      double K; int ref; uint32_t mk;
-      load_rec(T.recs, e, K, ref, mk);
-      double2 ad;
-      if (ref < 0) {
-        int pos = -(ref + 1);
-        bool bit = (sw[(pos >> 5) * PPM_LANES + lane] >> (pos & 31)) & 1u;
-        ad = bit ? make_double2(la1, ld1) : make_double2(la0, ld0);
-      } else ad = slots.ld(ref, lane);
-      const double bb = ad.y * K;
-      if (e < bd.e_pre0) update_suffix<R>(prod, Y, ad.x, bb, (int)(mk & 0xffffu));
-      else if (e < bd.e_gen0) update_prefix<R>(prod, Y, ad.x, bb, (int)(mk & 0xffffu));
-      else {
-#pragma unroll
-        for (int i = 0; i < R; i++)
-          if (mk & (1u << i)) prod[i] *= fma(-bb, Y[i], ad.x);
+    // (3) leaves merged inside the block: ref = bit position | next << 16, mk = live slices
+    if (bd.e_pleaf0 < bd.e_pslot0) {
+      double K; uint32_t ref, mk;
+      load_rec(T.recs, bd.e_pleaf0, K, ref, mk);
+      uint32_t wv = sw[((ref & 0xffffu) >> 5) * PPM_LANES + lane];
+      for (int e = bd.e_pleaf0; e < bd.e_pslot0; e++) {
+        const uint32_t wn = sw[((ref >> 16) >> 5) * PPM_LANES + lane];
+        const bool bit = (wv >> (ref & 31u)) & 1u;
+        const double aa = bit ? la1 : la0;
+        const double nbb = (bit ? ld1 : ld0) * -K;
+        const uint32_t mcur = mk;
+        load_rec(T.recs, e + 1, K, ref, mk);
+        masked_update<R>(prod, Y, aa, nbb, mcur);
+        wv = wn;
       }
-      if ((e & 15) == 15 && ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
     }
+    // (4) internal lineages born and/or merged inside the block: ref = slot | next slot << 16, mk = live slices
+    if (bd.e_pslot0 < bd.e_end) {
+      double K; uint32_t ref, mk;
+      load_rec(T.recs, bd.e_pslot0, K, ref, mk);
+      double2 ad = slots.ld((int)(ref & 0xffffu), lane);
+      for (int e = bd.e_pslot0; e < bd.e_end; e++) {
+        const double2 an = slots.ld((int)(ref >> 16), lane);
+        const double nbb = ad.y * -K;
+        const uint32_t mcur = mk;
+        load_rec(T.recs, e + 1, K, ref, mk);
+        masked_update<R>(prod, Y, ad.x, nbb, mcur);
+        ad = an;
+      }
+    }
+    if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
+
     // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
     {
       bool same = true;
@@ -406,23 +418,10 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
         double v = 0.;
 #pragma unroll
         for (int i = 0; i < R; i++) v = fma(prod[i], T.wt[b * R + i], v);  // padding slices carry weight 0
-        if (v != 0.) {
-          int e = ex[0];
-          if (Im == 0.) { Im = v; Ie = e; }
-          else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
-          else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
-        }
+        scaled_add(Im, Ie, v, ex[0]);
       } else {
 #pragma unroll
-        for (int i = 0; i < R; i++) {
-          double v = prod[i] * T.wt[b * R + i];
-          if (v != 0.) {
-            int e = ex[i];
-            if (Im == 0.) { Im = v; Ie = e; }
-            else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
-            else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
-          }
-        }
+        for (int i = 0; i < R; i++) scaled_add(Im, Ie, prod[i] * T.wt[b * R + i], ex[i]);
       }
     }
   }

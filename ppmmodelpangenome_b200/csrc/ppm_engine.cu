@@ -81,7 +81,7 @@ struct ppm_engine {
   // per-launch tables
   int P_cap = 0;
   DevBuf<ppm::EntryRec> d_recs;
-  DevBuf<double> d_params, d_yy, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
+  DevBuf<double> d_params, d_yy, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
   DevBuf<double4> d_cls;
   DevBuf<double2> d_kap, d_d1u, d_gslots;
   DevBuf<signed char> d_cat;
@@ -160,12 +160,13 @@ struct ppm_engine {
       size_t nn = tree.n_nodes;
       d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
       d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
+      d_oprec.alloc((size_t)P * std::max<size_t>(prog.ops.size(), 1) * ppm::OPREC_DOUBLES);
       d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 2 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }
     ppm::TablesDev t{};
-    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p;
+    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p;
     return t;
   }

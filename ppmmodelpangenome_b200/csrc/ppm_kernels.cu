@@ -41,7 +41,7 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes)
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 struct StageLayout {
-  size_t recs, blk, ops, cls, kap, yy, wt, total;
+  size_t recs, blk, ops, oprec, yy, wt, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
@@ -49,8 +49,7 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.recs = o; o += align16((size_t)(m.n_entries + 1) * sizeof(EntryRec));
   L.blk = o;  o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
   L.ops = o;  o += align16((size_t)m.n_ops * sizeof(NodeOpDev));
-  L.cls = o;  o += align16((size_t)m.n_nodes * sizeof(double4));
-  L.kap = o;  o += align16((size_t)m.n_nodes * sizeof(double2));
+  L.oprec = o; o += align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double));
   L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.total = o;
@@ -87,23 +86,20 @@ __global__ void __launch_bounds__(384, 1) sweep_kernel(SweepArgs a) {
       copy16(smem_raw + L.recs, a.t.recs + (size_t)p * (m.n_entries + 1), align16((size_t)(m.n_entries + 1) * sizeof(EntryRec)));
       copy16(smem_raw + L.blk, m.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc)));
       copy16(smem_raw + L.ops, m.ops, align16((size_t)m.n_ops * sizeof(NodeOpDev)));
-      copy16(smem_raw + L.cls, a.t.cls + (size_t)p * m.n_nodes, align16((size_t)m.n_nodes * sizeof(double4)));
-      copy16(smem_raw + L.kap, a.t.kap + (size_t)p * m.n_nodes, align16((size_t)m.n_nodes * sizeof(double2)));
+      copy16(smem_raw + L.oprec, a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES, align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)));
       copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
       __syncthreads();
       T.recs = reinterpret_cast<const EntryRec*>(smem_raw + L.recs);
       T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + L.blk);
       T.ops = reinterpret_cast<const NodeOpDev*>(smem_raw + L.ops);
-      T.cls = reinterpret_cast<const double4*>(smem_raw + L.cls);
-      T.kap = reinterpret_cast<const double2*>(smem_raw + L.kap);
+      T.oprec = reinterpret_cast<const double*>(smem_raw + L.oprec);
       T.yy = reinterpret_cast<const double*>(smem_raw + L.yy);
       T.wt = reinterpret_cast<const double*>(smem_raw + L.wt);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
       T.blk = m.blk; T.ops = m.ops;
-      T.cls = a.t.cls + (size_t)p * m.n_nodes;
-      T.kap = a.t.kap + (size_t)p * m.n_nodes;
+      T.oprec = a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES;
       T.yy = a.t.yy + (size_t)p * nbR;
       T.wt = m.slice_wt_pad;
     }
@@ -146,7 +142,7 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
   prepass_nodes_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  int n = m.n_entries + 1 + m.n_blocks * m.R;
+  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops;
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }

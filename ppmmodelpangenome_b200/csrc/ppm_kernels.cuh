@@ -21,16 +21,17 @@ struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
-  // [e_leaf0,e_slot0) leaves alive in every slice | [e_slot0,e_suf0) internal lineages alive in every slice |
-  // [e_suf0,e_pre0) born inside the block | [e_pre0,e_gen0) merged inside the block | [e_gen0,e_end) both
-  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_suf0, e_pre0, e_gen0, e_end, pad0, pad1;
+  // [e_leaf0,e_slot0) leaves alive in every slice | [e_slot0,e_pleaf0) internal lineages alive in every slice |
+  // [e_pleaf0,e_pslot0) leaves merged inside the block | [e_pslot0,e_end) internal lineages born/merged inside it
+  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
 };
 struct __align__(16) EntryRec {
   double K;       // pi1 * exp(-(g2+l2) * (t_block - h_lineage))   (per parameter vector)
-  int32_t ref;    // leaf segment: word | next word << 16; slot segment: slot; other segments: slot or -(bit position + 1)
-  uint32_t mask;  // leaf segment: the leaf's bit in its word; slot segment: next slot << 16; suffix: first slice;
-                  // prefix: end slice; generic: slice mask
+  int32_t ref;    // full leaves: word | next word << 16;  slots: slot | next slot << 16;  partial leaves: bit
+                  // position | next position << 16  ("next" = prefetch hint, 0 at the end of a segment)
+  uint32_t mask;  // full leaves: the leaf's bit inside its word;  otherwise: the live slices of the block
 };
+enum { OPREC_DOUBLES = 12 };  // per (parameter vector, node op): kap_l{x,y} kap_r{x,y} cls_l{S0,T0,S1,T1} cls_r{..}
 
 struct ModelDev {
   int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
@@ -60,6 +61,7 @@ struct TablesDev {
   double2* d1u;          // [P][n_nodes]  {log(V+U)-log V, log U}: Private "gained below the root" tables
   EntryRec* recs;        // [P][n_entries+1]
   double* yy;            // [P][n_blocks*R] exp(-(g2+l2)*(t_slice - t_block)), 0 for padding slices
+  double* oprec;         // [P][n_ops][OPREC_DOUBLES]
   double* scal;          // [P][SC_COUNT]
   double* zeta;          // [P][2][n_nodes] scratch: zero-row log p1 per node for cat 0 / cat 1
 };

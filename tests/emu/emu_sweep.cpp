@@ -64,9 +64,10 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<double2> kap(P * nn), d1u(P * nn);
     std::vector<EntryRec> recs((size_t)P * (prog.entry_ref.size() + 1));
     std::vector<double> yy((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
+    std::vector<double> oprec((size_t)P * std::max<size_t>(prog.ops.size(), 1) * OPREC_DOUBLES);
     std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 2 * nn), i2ovr(P);
     TablesDev t{};
-    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data();
+    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
 
     std::vector<uint32_t> sw(pat.n_words), zw(prog.n_slots);
@@ -81,7 +82,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
         for (long long bt = 0; bt < a.n_batches; bt++) {
           ItemTables T;
           T.recs = recs.data() + (size_t)p * (md.n_entries + 1); T.blk = md.blk; T.ops = md.ops;
-          T.cls = cls.data() + (size_t)p * nn; T.kap = kap.data() + (size_t)p * nn;
+          T.oprec = oprec.data() + (size_t)p * md.n_ops * OPREC_DOUBLES;
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
           if (prog.R == 8) s += sweep_item<8>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else if (prog.R == 4) s += sweep_item<4>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
@@ -93,7 +94,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     };
     for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p);
     for (int p = 0; p < P; p++)
-      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R; i++) prepass_tables_body(md, t, p, i);
+      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops; i++) prepass_tables_body(md, t, p, i);
     run(1, P, nullptr, nullptr, nullptr, true);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
     run(0, P, out_ll, nullptr, nullptr, false);
