@@ -1,0 +1,30 @@
+// TEST INFRASTRUCTURE.  Runs ppmmodelpangenome_b200/csrc/nmkb.h on the analytic test functions and prints the
+// LOGICAL evaluation sequence in the same format as oracle/nm_ref_driver.cpp.
+#include <cstdio>
+#include <cstdlib>
+#include "../../ppmmodelpangenome_b200/csrc/nmkb.h"
+#include "nm_functions.h"
+
+int main(int argc, char** argv) {
+  int which = argc > 1 ? atoi(argv[1]) : 0;
+  bool spec = argc > 2 ? atoi(argv[2]) != 0 : true;
+  std::array<double, 8> start, lower, upper;
+  nm_test_setup(which, start, lower, upper);
+  using NM = ppm::Nmkb<8>;
+  NM::BatchFn f = [&](const std::vector<NM::Point>& x, std::vector<double>& y) {
+    for (size_t i = 0; i < x.size(); i++) y[i] = nm_test_function(which, x[i]);
+  };
+  NM::Observer obs = [&](const NM::Point& x, int k, double y) {
+    printf("eval %d", k);
+    for (double v : x) printf(" %a", v);
+    printf(" %a\n", y);
+  };
+  NM nm(f, obs, lower, upper);
+  nm.speculate = spec;
+  ppm::NmkbResult<8> r = nm.minimize(start, 0.0001, 3000, 10);
+  printf("result %d %a", r.icount, r.ymin);
+  for (double v : r.xmin) printf(" %a", v);
+  printf(" %s\n", r.message.c_str());
+  fprintf(stderr, "evaluated %d launches %d\n", r.evaluated, r.launches);
+  return 0;
+}
