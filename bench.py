@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
@@ -140,7 +140,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--params", type=int, default=256, help="parameter vectors per step (P)")
@@ -187,12 +187,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
     for _ in range(W):
         step_device()
     barrier()
     peak_tf = measure_fp64_peak(local)  # DFMA micro-benchmark on this very GPU
-    sampler = ClockSampler(local)
     sampler.start()
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 5.0:
+        time.sleep(0.01)              # nvidia-smi is up before the timed region starts
+    sampler.rows.clear()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sweep_ms = []
     barrier()
@@ -207,7 +211,6 @@ def main():
             sweep_ms.append(inf.counters()["sweep_ms"])
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    sampler.stop_flag = True
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([float(np.sum(step_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -238,6 +241,7 @@ def main():
             part = np.where(i2h < 0, -1e9 + i2h, part)
         ll_host = part
         t_e2e.append(time.perf_counter() - t0)
+    sampler.stop_flag = True  # sampled through the device-resident AND the end-to-end timed loops
     e2e_t = torch.tensor([float(np.median(t_e2e))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)

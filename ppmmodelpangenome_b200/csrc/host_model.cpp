@@ -162,6 +162,25 @@ static void finish_tree(Tree& t) {
   t.rank.resize(nn);
   for (int i = 0; i < nn; i++) t.rank[t.order[i]] = i;
 
+  // level lists (counting sort by level)
+  {
+    std::vector<int> up(nn, 0), dn(nn, 0);
+    for (int v = nn - 1; v >= 0; v--)
+      if (t.left[v] >= 0) up[v] = 1 + std::max(up[t.left[v]], up[t.right[v]]);
+    for (int v = 1; v < nn; v++) dn[v] = dn[t.parent[v]] + 1;
+    auto bucket = [&](const std::vector<int>& lev, std::vector<int>& off, std::vector<int>& nodes) {
+      int nl = *std::max_element(lev.begin(), lev.end()) + 1;
+      off.assign(nl + 1, 0);
+      for (int v = 0; v < nn; v++) off[lev[v] + 1]++;
+      for (int l = 0; l < nl; l++) off[l + 1] += off[l];
+      nodes.resize(nn);
+      std::vector<int> pos(off.begin(), off.end() - 1);
+      for (int v = 0; v < nn; v++) nodes[pos[lev[v]]++] = v;
+    };
+    bucket(up, t.lev_up_off, t.lev_up_nodes);
+    bucket(dn, t.lev_dn_off, t.lev_dn_nodes);
+  }
+
   // breadth-first last node (what computeMRCA returns for an all-zero pattern, functions.cpp:52-64)
   {
     std::vector<int> q{0};

@@ -18,6 +18,8 @@ struct Tree {
   std::vector<int> last;                 // largest preorder id inside the subtree of each node
   std::vector<int> leaf_pos;             // node -> bit position (k-th leaf in preorder), -1 internal
   std::vector<int> leaf_node;            // bit position -> node id
+  // level lists for level-synchronous recursions: up = by height in edges (leaves first), dn = by depth (root first)
+  std::vector<int> lev_up_off, lev_up_nodes, lev_dn_off, lev_dn_nodes;
   int bfs_last = 0;                      // last node of a breadth-first walk (computeMRCA of an empty pattern)
   double H = 0, L = 0;                   // functions.cpp:108, objects.cpp:115-122
   // Mobile integral grid (functions.cpp:250-260)

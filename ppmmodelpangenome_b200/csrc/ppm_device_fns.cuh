@@ -52,17 +52,26 @@ PPM_HD double pow2i(int k) {  // 2^k for k in [-1022, 1023]
 PPM_HD int biased_exp(double x) { return (ppm_double2hiint(x) >> 20) & 0x7ff; }
 
 // ------------------------------------------------------------------------------------------------ prepass
-// One thread per parameter vector: per-node tables that need a tree recursion (zero-row pruning of the two
-// pure-loss categories, getPobs1, likUpper1).  Serial in the nodes; it is O(1 pattern) of work.
-PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p) {
+#if defined(__CUDA_ARCH__)
+#define PPM_CTA_BARRIER() __syncthreads()
+#else
+#define PPM_CTA_BARRIER() ((void)0)
+#endif
+
+// One CTA per parameter vector (tid/nt = thread and CTA size; the host emulation runs it with nt = 1): per-node
+// tables that need a tree recursion -- zero-row pruning of the two pure-loss categories, getPobs1, likUpper1.
+// Independent per-node transcendentals are spread over the threads; the recursions run level by level
+// (m.lev_up: leaves first; m.lev_dn: root first), so the serial depth is the tree depth, not the node count.
+PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int tid, int nt) {
   const double* par = t.params + 8 * (size_t)p;
   const double l0 = par[1], l1 = par[3], g2 = par[4], l2 = par[5], e2 = par[6], e1 = par[7];
   const int nn = m.n_nodes;
   double4* cls = t.cls + (size_t)p * nn;
   double2* kap = t.kap + (size_t)p * nn;
   double2* d1u = t.d1u + (size_t)p * nn;
-  double* z0 = t.zeta + (size_t)p * 2 * nn;
-  double* z1 = z0 + nn;
+  double* z0 = t.zeta + (size_t)p * 4 * nn;  // zero-row log p1 per node for l0; later log V
+  double* z1 = z0 + nn;                      // ... for l1; later U
+  double* ta = z1 + nn;                      // getPobs1 terms
   double* sc = t.scal + (size_t)p * SC_COUNT;
 
   const double lam = g2 + l2;
@@ -70,63 +79,85 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p) {
   const double pi0 = (g2 == 0.) ? 1. : l2 / lam;
   const double log_e2 = log(e2), log_1me2 = log(1 - e2);
 
-  // bottom-up (children have larger preorder ids): zero-row log p1 per node, branch factor tables
-  for (int v = nn - 1; v >= 0; v--) {
+  // (A) per node, independent: branch survival logs and the Mobile branch factors.
+  //     cls[v] = {S0, log(1-sigma0), S1, log(1-sigma1)} for now; .y/.w become T0/T1 in (B)
+  for (int v = tid; v < nn; v += nt) {
     const bool leaf = m.left[v] < 0;
-    double zl0, zl1;  // log P(all-zero below v | present at v) for l0 / l1      (objects.cpp:404-426 on the zero row)
-    if (leaf) { zl0 = log_e2; zl1 = log_e2; }
-    else {
-      int a = m.left[v], b = m.right[v];
-      zl0 = cls[a].y + cls[b].y;
-      zl1 = cls[a].w + cls[b].w;
-    }
-    z0[v] = zl0; z1[v] = zl1;
     const double bl = m.bl[v];
     double4 c;
     // active branch (a present leaf below): survive the branch; a leaf adds its own log(1-e2)   (objects.cpp:408,423)
     c.x = -l0 * bl + (leaf ? log_1me2 : 0.);
     c.z = -l1 * bl + (leaf ? log_1me2 : 0.);
-    // frontier branch (all-zero subtree under an active parent): lost on the branch, or kept and unobserved
-    c.y = lse2(log(1 - exp(-l0 * bl)), -l0 * bl + zl0);
-    c.w = lse2(log(1 - exp(-l1 * bl)), -l1 * bl + zl1);
-    if (v == 0) c = make_double4(0., 0., 0., 0.);
+    c.y = log(1 - exp(-l0 * bl));
+    c.w = log(1 - exp(-l1 * bl));
     cls[v] = c;
     const double E = exp(-lam * bl);
     kap[v] = make_double2(pi1 * E, pi0 * E);
   }
-  // computeI2 pieces that do not need the Mobile integral (functions.cpp:337-341, 284-299)
-  double p0 = (l0 == 0.) ? 1 - pow(e2, (double)m.n_leaves) : 1 - exp(z0[0]);
-  double p1 = 1 - exp(z1[0]);
-  double A = 0;
-  for (int v = 1; v < nn; v++) {
-    double lost = 1 - exp(-l1 * m.bl[v]);
-    A += (m.left[v] < 0) ? lost * (1 - e2) : lost * (1 - exp(z1[v]));
+  PPM_CTA_BARRIER();
+  // (B) bottom-up by levels: zero-row log p1 per node (objects.cpp:404-426 on the all-zero row) and the frontier
+  //     factor T = LSE(lost on the branch, kept and unobserved below)
+  for (int lv = 0; lv < m.n_lev_up; lv++) {
+    for (int k = m.lev_up_off[lv] + tid; k < m.lev_up_off[lv + 1]; k += nt) {
+      const int v = m.lev_up_nodes[k];
+      const bool leaf = m.left[v] < 0;
+      double zl0, zl1;
+      if (leaf) { zl0 = log_e2; zl1 = log_e2; }
+      else {
+        const int a = m.left[v], b = m.right[v];
+        zl0 = cls[a].y + cls[b].y;
+        zl1 = cls[a].w + cls[b].w;
+      }
+      z0[v] = zl0; z1[v] = zl1;
+      const double bl = m.bl[v];
+      double4 c = cls[v];
+      c.y = lse2(c.y, -l0 * bl + zl0);
+      c.w = lse2(c.w, -l1 * bl + zl1);
+      if (v == 0) c = make_double4(0., 0., 0., 0.);
+      cls[v] = c;
+      // getPobs1 term (functions.cpp:284-299)
+      const double lost = 1 - exp(-l1 * bl);
+      ta[v] = leaf ? lost * (1 - e2) : lost * (1 - exp(zl1));
+    }
+    PPM_CTA_BARRIER();
   }
-  A /= l1;
-  // top-down: U (likUpper1, functions.cpp:176-209, as the recursion U(v) = lost_v + sigma_v*T(sib)*U(parent),
-  // U(child of root) = lost_v) and V(v) = prod over the path of sigma_c*T(sib c) in log domain.
-  // z0 is reused as log V, z1 as U (both only needed for ancestors, which precede v in preorder).
-  z0[0] = 0.; z1[0] = 0.;
-  d1u[0] = make_double2(0., -INFINITY);
-  for (int v = 1; v < nn; v++) {
-    int par_ = m.parent[v];
-    int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];
-    double sig = exp(-l1 * m.bl[v]);
-    double U = (1 - sig) + sig * exp(cls[sib].w) * z1[par_];
-    double logV = z0[par_] + (-l1 * m.bl[v]) + cls[sib].w;
-    z1[v] = U; z0[v] = logV;
-    double logU = log(U);
-    d1u[v] = make_double2(lse2(logV, logU) - logV, logU);
+  // (C) computeI2 pieces that do not need the Mobile integral (functions.cpp:337-341), summed in the reference's order
+  if (tid == 0) {
+    double p0 = (l0 == 0.) ? 1 - pow(e2, (double)m.n_leaves) : 1 - exp(z0[0]);
+    double p1 = 1 - exp(z1[0]);
+    double A = 0;
+    for (int v = 1; v < nn; v++) A += ta[v];
+    A /= l1;
+    sc[SC_PI1] = pi1;
+    double m0 = 1 - e1, m1 = e2;           // leaf observed 0 (objects.cpp:407-408)
+    sc[SC_LD0] = m1 - m0; sc[SC_LA0] = m0 + pi1 * (m1 - m0);
+    m0 = e1; m1 = 1 - e2;                  // leaf observed 1
+    sc[SC_LD1] = m1 - m0; sc[SC_LA1] = m0 + pi1 * (m1 - m0);
+    sc[SC_P0] = p0; sc[SC_P1] = p1; sc[SC_A] = A;
+    sc[SC_LOG1ME2] = log_1me2;
+    sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
+    sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
+    z0[0] = 0.; z1[0] = 0.;
+    d1u[0] = make_double2(0., -INFINITY);
   }
-  sc[SC_PI1] = pi1;
-  double m0 = 1 - e1, m1 = e2;           // leaf observed 0 (objects.cpp:407-408)
-  sc[SC_LD0] = m1 - m0; sc[SC_LA0] = m0 + pi1 * (m1 - m0);
-  m0 = e1; m1 = 1 - e2;                  // leaf observed 1
-  sc[SC_LD1] = m1 - m0; sc[SC_LA1] = m0 + pi1 * (m1 - m0);
-  sc[SC_P0] = p0; sc[SC_P1] = p1; sc[SC_A] = A;
-  sc[SC_LOG1ME2] = log_1me2;
-  sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
-  sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
+  PPM_CTA_BARRIER();
+  // (D) top-down by levels: U (likUpper1, functions.cpp:176-209, as U(v) = lost_v + sigma_v*T(sib)*U(parent),
+  //     U(child of root) = lost_v) and log V(v) = sum over the path of log sigma_c + T(sib c).
+  //     z0 is reused as log V, z1 as U: a node's own zero-row values are dead once level (B) is complete.
+  for (int lv = 1; lv < m.n_lev_dn; lv++) {
+    for (int k = m.lev_dn_off[lv] + tid; k < m.lev_dn_off[lv + 1]; k += nt) {
+      const int v = m.lev_dn_nodes[k];
+      const int par_ = m.parent[v];
+      const int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];
+      const double sig = exp(-l1 * m.bl[v]);
+      const double U = (1 - sig) + sig * exp(cls[sib].w) * z1[par_];
+      const double logV = z0[par_] + (-l1 * m.bl[v]) + cls[sib].w;
+      z1[v] = U; z0[v] = logV;
+      const double logU = log(U);
+      d1u[v] = make_double2(lse2(logV, logU) - logV, logU);
+    }
+    PPM_CTA_BARRIER();
+  }
 }
 
 // One thread per (parameter vector, entry or padded slice): the exp tables of the Mobile integral.

@@ -68,7 +68,7 @@ struct ppm_engine {
   double n_launches = 0;
 
   // device model
-  DevBuf<int> d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block;
+  DevBuf<int> d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
   DevBuf<ppm::BlockDesc> d_blk;
   DevBuf<uint32_t> d_entry_mask;
   DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt;
@@ -116,6 +116,8 @@ struct ppm_engine {
     count = np * (shard_rank + 1) / shard_world - first;
     d_left.upload(tree.left, stream); d_right.upload(tree.right, stream); d_parent.upload(tree.parent, stream);
     d_bl.upload(tree.bl, stream); d_height.upload(tree.height, stream);
+    d_lev_up_off.upload(tree.lev_up_off, stream); d_lev_up_nodes.upload(tree.lev_up_nodes, stream);
+    d_lev_dn_off.upload(tree.lev_dn_off, stream); d_lev_dn_nodes.upload(tree.lev_dn_nodes, stream);
     d_slice_t.upload(tree.slice_t, stream);
     std::vector<double> wt_pad((size_t)std::max(prog.n_blocks, 1) * prog.R, 0.);
     std::copy(tree.slice_wt.begin(), tree.slice_wt.end(), wt_pad.begin());
@@ -148,6 +150,8 @@ struct ppm_engine {
     md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entry_ref.size();
     md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
     md.left = d_left.p; md.right = d_right.p; md.parent = d_parent.p; md.bl = d_bl.p; md.height = d_height.p;
+    md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
+    md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p;
     md.slice_t = d_slice_t.p; md.slice_wt_pad = d_slice_wt.p;
     md.blk = d_blk.p; md.ops = d_ops.p;
     md.entry_ref = d_entry_ref.p; md.entry_mask = d_entry_mask.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
@@ -161,7 +165,7 @@ struct ppm_engine {
       d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
       d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
       d_oprec.alloc((size_t)P * std::max<size_t>(prog.ops.size(), 1) * ppm::OPREC_DOUBLES);
-      d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 2 * nn);
+      d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 4 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }

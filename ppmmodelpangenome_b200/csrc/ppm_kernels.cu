@@ -20,9 +20,8 @@
 namespace ppm {
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void prepass_nodes_kernel(ModelDev m, TablesDev t) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < t.P) prepass_nodes_body(m, t, p);
+__global__ void __launch_bounds__(128) prepass_nodes_kernel(ModelDev m, TablesDev t) {
+  prepass_nodes_body(m, t, blockIdx.x, threadIdx.x, blockDim.x);
 }
 __global__ void prepass_tables_kernel(ModelDev m, TablesDev t) {
   prepass_tables_body(m, t, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
@@ -139,7 +138,7 @@ __global__ void finalize_kernel(const double* i2, double* ll, int P) {
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  prepass_nodes_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t);
+  prepass_nodes_kernel<<<t.P, 128, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
   int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops;

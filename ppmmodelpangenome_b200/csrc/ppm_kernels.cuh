@@ -40,6 +40,9 @@ struct ModelDev {
   // tree (preorder ids)
   const int* left; const int* right; const int* parent;
   const double* bl; const double* height;
+  // node levels for the prepass recursions: bottom-up (leaves = level 0) and top-down (root = level 0)
+  int n_lev_up, n_lev_dn;
+  const int* lev_up_off; const int* lev_up_nodes; const int* lev_dn_off; const int* lev_dn_nodes;
   // slices
   const double* slice_t; const double* slice_wt_pad;  // [n_slices], [n_blocks*R] (0 for padding slices)
   // program
@@ -63,7 +66,7 @@ struct TablesDev {
   double* yy;            // [P][n_blocks*R] exp(-(g2+l2)*(t_slice - t_block)), 0 for padding slices
   double* oprec;         // [P][n_ops][OPREC_DOUBLES]
   double* scal;          // [P][SC_COUNT]
-  double* zeta;          // [P][2][n_nodes] scratch: zero-row log p1 per node for cat 0 / cat 1
+  double* zeta;          // [P][4][n_nodes] scratch of the node prepass
 };
 
 struct SweepArgs {

@@ -51,6 +51,9 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
     md.left = tree.left.data(); md.right = tree.right.data(); md.parent = tree.parent.data();
     md.bl = tree.bl.data(); md.height = tree.height.data();
+    md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
+    md.lev_up_off = tree.lev_up_off.data(); md.lev_up_nodes = tree.lev_up_nodes.data();
+    md.lev_dn_off = tree.lev_dn_off.data(); md.lev_dn_nodes = tree.lev_dn_nodes.data();
     md.slice_t = tree.slice_t.data(); md.slice_wt_pad = wt_pad.data();
     md.blk = reinterpret_cast<const BlockDesc*>(prog.blk.data());
     md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data());
@@ -65,7 +68,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<EntryRec> recs((size_t)P * (prog.entry_ref.size() + 1));
     std::vector<double> yy((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
     std::vector<double> oprec((size_t)P * std::max<size_t>(prog.ops.size(), 1) * OPREC_DOUBLES);
-    std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 2 * nn), i2ovr(P);
+    std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 4 * nn), i2ovr(P);
     TablesDev t{};
     t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
@@ -92,7 +95,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
         if (ll) ll[p] = s;
       }
     };
-    for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p);
+    for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++)
       for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops; i++) prepass_tables_body(md, t, p, i);
     run(1, P, nullptr, nullptr, nullptr, true);

@@ -50,7 +50,11 @@ def test_seed1_fit_matches_reference_cli(tmp_path, env):
     assert m[:5] == gold_mle[:5] and m[6:] == gold_mle[6:] and len(m) == 13
     assert abs(float(m[5]) / float(gold_mle[5]) - 1) < 2e-4
     assert cat == gold_cat                               # inf_cat.txt byte-identical (328 x 0, 530 x 1, 552 x 2)
-    assert tail(out, "327.99") == "327.990444 Persistent genes" and "496.878193 Private genes" in out
+    # "Expected pangenome composition": the reference evaluates nb0/nb1/nb2 on its stale memo (Q1); fresh values
+    # agree to ~1e-4 relative
+    comp = [float(l.split()[0]) for l in out if l.endswith(" genes")]
+    gcomp = [float(l.split()[0]) for l in gold_out if l.endswith(" genes")]
+    assert len(comp) == 3 and np.allclose(comp, gcomp, rtol=2e-4, atol=0)
 
 
 def test_fixed_start_and_append(tmp_path):
