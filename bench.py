@@ -96,6 +96,7 @@ def cpu_reference_time(nwk, names, M, params, sample_patterns, repeats):
     times = []
     if oref.available():
         kind = "reference"
+        oref.set_threads(len(os.sched_getaffinity(0)))  # all host threads, whatever OMP_NUM_THREADS torchrun set
         cores = oref.max_threads()
         R = oref.Reference(tp, pp)
         for k in range(repeats):
@@ -106,6 +107,7 @@ def cpu_reference_time(nwk, names, M, params, sample_patterns, repeats):
     else:
         kind = "port"
         from oracle import cport, model
+        cport.set_threads(len(os.sched_getaffinity(0)))
         cores = cport.max_threads()
         orc = cport.Oracle(model.model_from_files(tp, pp))
         for k in range(repeats):

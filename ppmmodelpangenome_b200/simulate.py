@@ -90,6 +90,17 @@ def sim_tree(n, rng, height=1.0, b=-0.5, caterpillar=False):
     p ~ Beta(b+1,b+1); caterpillar=True makes every split 1|rest. Returns a Newick string whose leaves
     are labelled 1..n. Iterative (no recursion limit)."""
     times = [0.0] + sorted(rng.uniform(0, height, n - 2).tolist()) if n > 2 else [0.0]
+    if caterpillar and n > 200:
+        # every split is 1 | rest: a chain; built directly (the general loop below is quadratic for it)
+        perm = rng.permutation(n) + 1
+        out = []
+        for i in range(n - 1):
+            t_par = times[i - 1] if i > 0 else 0.0
+            out.append("(%d:%s," % (perm[i], _fmt(height - times[i])))
+        out.append("%d:%s" % (perm[n - 1], _fmt(height - times[n - 2])))
+        for i in range(n - 2, -1, -1):
+            out.append("):%s" % _fmt(times[i] - (times[i - 1] if i > 0 else 0.0)))
+        return "".join(out) + ";"
     # each work item: (t_parent, times(list, sorted), leaves(list)) -> builds string pieces
     # build an explicit tree first
     nodes = []  # (left, right, bl, label)
