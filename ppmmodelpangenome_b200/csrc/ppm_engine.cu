@@ -51,7 +51,7 @@ struct DevBuf {
 static int program_R() {
   const char* e = std::getenv("PPM_R");
   int r = e ? std::atoi(e) : 8;
-  return r == 16 ? 16 : 8;
+  return (r == 16 || r == 12) ? r : 8;
 }
 
 struct ppm_engine {

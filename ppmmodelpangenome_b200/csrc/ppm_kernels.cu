@@ -189,6 +189,9 @@ void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
   if (a.m.R == 16) {
     if (pl.staged) launch_sweep_t<16, true>(a, pl, s);
     else launch_sweep_t<16, false>(a, pl, s);
+  } else if (a.m.R == 12) {
+    if (pl.staged) launch_sweep_t<12, true>(a, pl, s);
+    else launch_sweep_t<12, false>(a, pl, s);
   } else {
     if (pl.staged) launch_sweep_t<8, true>(a, pl, s);
     else launch_sweep_t<8, false>(a, pl, s);

@@ -89,6 +89,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
           if (prog.R == 8) s += sweep_item<8>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else if (prog.R == 4) s += sweep_item<4>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
+          else if (prog.R == 12) s += sweep_item<12>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else if (prog.R == 16) s += sweep_item<16>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else throw std::runtime_error("emulator built for R in {4,8,16}");
         }
