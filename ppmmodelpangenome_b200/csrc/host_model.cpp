@@ -483,7 +483,17 @@ Program build_program(const Tree& t, int R) {
       fp64 += 1 + 2 * (e.i1 - e.i0);
       const uint32_t live = c < 2 ? ((1u << R) - 1u) : (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
       pg.entry_ref.push_back(c == 0 ? (e.ref >> 5) : e.ref);
-      pg.entry_mask.push_back(c == 0 ? (1u << (e.ref & 31)) : live);
+      uint32_t mk = live;
+      if (c == 0) mk = 1u << (e.ref & 31);
+      else if (c >= 2) {
+        // code in the low half: i0 for a suffix [i0,end), 16+i1 for a prefix [0,i1), 0 = use the mask in the high half
+        const bool to_end = e.i1 == nsl;
+        uint32_t code = 0;
+        if (to_end && e.i0 > 0 && e.i0 < 16) code = (uint32_t)e.i0;
+        else if (e.i0 == 0 && e.i1 > 0 && e.i1 < 16) code = 16u + (uint32_t)e.i1;
+        mk = code | (live << 16);
+      }
+      pg.entry_mask.push_back(mk);
       pg.entry_node.push_back(e.node);
       pg.entry_block.push_back(b);
     }

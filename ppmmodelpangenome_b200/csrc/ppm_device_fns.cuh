@@ -224,6 +224,7 @@ struct SlotStore {
   double2* base;  // [slot][lanes]
   PPM_HD double2 ld(int slot, int lane) const { return base[slot * PPM_LANES + lane]; }
   PPM_HD void st(int slot, int lane, double2 v) const { base[slot * PPM_LANES + lane] = v; }
+  PPM_HD const double2* ptr(int slot, int lane) const { return base + slot * PPM_LANES + lane; }
 };
 
 // Where one work item reads its topology program and per-parameter tables from (shared memory copies in the
@@ -235,6 +236,7 @@ struct ItemTables {
   const double* oprec;    // [n_ops][OPREC_DOUBLES]
   const double* yy;       // [n_blocks * R]
   const double* wt;       // [n_blocks * R]
+  const double2* leaftab; // [2] leaf partials (a,d) for observation 0 / 1
 };
 
 // One 16-byte load per record: K | ref | mask
@@ -265,22 +267,45 @@ PPM_HD bool products_small(const double (&prod)[R]) {
   return mn < ((1023 - 480) << 20);
 }
 
-// prod[i] *= a + nbb*Y[i] for the slices i named by the (warp-uniform) mask.  Straight-line: every slice is
-// computed and the dead ones are discarded by a select (ptxas turns predicated FP64 into exactly this anyway).
-template <int R>
-PPM_HD void masked_update(double (&prod)[R], const double (&Y)[R], double a, double nbb, uint32_t mk) {
+// prod[i] *= a + nbb*Y[i] for a warp-uniform set of slices.  Lineages born inside a block live on a suffix
+// [i0,R) of its slices, lineages merged inside it on a prefix [0,i1): the record carries a small code and a
+// jump table lands on straight-line code for exactly the live slices (no selects, no wasted FP64); anything
+// else (born AND merged inside one block) falls back to a per-slice select on the mask.
+template <int I0, int I1, int R>
+PPM_HD void update_range(double (&prod)[R], const double (&Y)[R], double a, double nbb) {
 #pragma unroll
-  for (int i = 0; i < R; i++) {
-    const double t = prod[i] * fma(nbb, Y[i], a);
-    prod[i] = (mk & (1u << i)) ? t : prod[i];
+  for (int i = 0; i < R; i++)
+    if (i >= I0 && i < I1) prod[i] *= fma(nbb, Y[i], a);
+}
+template <int R>
+PPM_HD void coded_update(double (&prod)[R], const double (&Y)[R], double a, double nbb, uint32_t mk) {
+  switch (mk & 0xffffu) {
+#define PPM_SUF(k) case k: update_range<k, R, R>(prod, Y, a, nbb); break;
+#define PPM_PRE(k) case 16 + k: update_range<0, k, R>(prod, Y, a, nbb); break;
+    PPM_SUF(1) PPM_SUF(2) PPM_SUF(3) PPM_SUF(4) PPM_SUF(5) PPM_SUF(6) PPM_SUF(7) PPM_SUF(8)
+    PPM_SUF(9) PPM_SUF(10) PPM_SUF(11) PPM_SUF(12) PPM_SUF(13) PPM_SUF(14) PPM_SUF(15)
+    PPM_PRE(1) PPM_PRE(2) PPM_PRE(3) PPM_PRE(4) PPM_PRE(5) PPM_PRE(6) PPM_PRE(7) PPM_PRE(8)
+    PPM_PRE(9) PPM_PRE(10) PPM_PRE(11) PPM_PRE(12) PPM_PRE(13) PPM_PRE(14) PPM_PRE(15)
+#undef PPM_SUF
+#undef PPM_PRE
+    default: {
+      const uint32_t live = mk >> 16;
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        const double t = prod[i] * fma(nbb, Y[i], a);
+        prod[i] = (live & (1u << i)) ? t : prod[i];
+      }
+    }
   }
 }
 
-PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) += v * 2^-e
+PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) += v * 2^-e ; Ie starts at INT_MAX/2
   if (v != 0.) {
-    if (Im == 0.) { Im = v; Ie = e; }
-    else if (e >= Ie) { int df = e - Ie; Im += (df > 1000) ? 0. : v * pow2i(-df); }
-    else { int df = Ie - e; Im = ((df > 1000) ? 0. : Im * pow2i(-df)) + v; Ie = e; }
+    const int en = e < Ie ? e : Ie;
+    int d1 = Ie - en, d2 = e - en;   // one of them is 0
+    d1 = d1 > 1000 ? 1000 : d1; d2 = d2 > 1000 ? 1000 : d2;
+    Im = fma(Im, pow2i(-d1), v * pow2i(-d2));
+    Ie = en;
   }
 }
 
@@ -303,10 +328,12 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
 
   const double pi1 = sc[SC_PI1];
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
+  // T.leaftab[bit] = the leaf partials (a,d) for observation 0 / 1: a child that is a leaf is fetched with one
+  // load through a selected pointer, exactly like an internal lineage (no per-value selects)
 
   double A0 = 0., A1 = 0.;     // log p1(root) of the two pure-loss categories
   int X = 0;                   // sum of renormalisation shifts of all lineages formed so far
-  double Im = 0.; int Ie = 0;  // Mobile integral = Im * 2^-Ie
+  double Im = 0.; int Ie = 0x3fffffff;  // Mobile integral = Im * 2^-Ie (exponent of an empty sum: +inf)
 
   double prod[R], Y[R];
   int ex[R];
@@ -325,15 +352,12 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
       const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
       const bool lleaf = op.lref < 0, rleaf = op.rref < 0;
       const int lpos = lleaf ? -(op.lref + 1) : 0, rpos = rleaf ? -(op.rref + 1) : 0;
-      const int lslot = lleaf ? 0 : op.lref, rslot = rleaf ? 0 : op.rref;
       const uint32_t wl = sw[(lpos >> 5) * PPM_LANES + lane], wr = sw[(rpos >> 5) * PPM_LANES + lane];
-      const double2 Ls = slots.ld(lslot, lane), Rs = slots.ld(rslot, lane);
-      const uint32_t zls = zw[lslot], zrs = zw[rslot];
-      const bool bl = (wl >> (lpos & 31)) & 1u, br = (wr >> (rpos & 31)) & 1u;
-      const uint32_t zbl = ~ppm_ballot(bl), zbr = ~ppm_ballot(br);
-      double2 L, Rr;
-      L.x = lleaf ? (bl ? la1 : la0) : Ls.x;  L.y = lleaf ? (bl ? ld1 : ld0) : Ls.y;
-      Rr.x = rleaf ? (br ? la1 : la0) : Rs.x; Rr.y = rleaf ? (br ? ld1 : ld0) : Rs.y;
+      const uint32_t zls = zw[lleaf ? 0 : op.lref], zrs = zw[rleaf ? 0 : op.rref];
+      const uint32_t bl = (wl >> (lpos & 31)) & 1u, br = (wr >> (rpos & 31)) & 1u;
+      const double2 L = *(lleaf ? T.leaftab + bl : slots.ptr(op.lref, lane));
+      const double2 Rr = *(rleaf ? T.leaftab + br : slots.ptr(op.rref, lane));
+      const uint32_t zbl = ~ppm_ballot(bl != 0u), zbr = ~ppm_ballot(br != 0u);
       const uint32_t zwl = lleaf ? zbl : zls, zwr = rleaf ? zbr : zrs;
       const uint32_t zwv = zwl & zwr;
       // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
@@ -420,7 +444,7 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
         const double nbb = (bit ? ld1 : ld0) * -K;
         const uint32_t mcur = mk;
         load_rec(T.recs, e + 1, K, ref, mk);
-        masked_update<R>(prod, Y, aa, nbb, mcur);
+        coded_update<R>(prod, Y, aa, nbb, mcur);
         wv = wn;
       }
     }
@@ -434,7 +458,7 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
         const double nbb = ad.y * -K;
         const uint32_t mcur = mk;
         load_rec(T.recs, e + 1, K, ref, mk);
-        masked_update<R>(prod, Y, ad.x, nbb, mcur);
+        coded_update<R>(prod, Y, ad.x, nbb, mcur);
         ad = an;
       }
     }
@@ -445,11 +469,15 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
       bool same = true;
 #pragma unroll
       for (int i = 1; i < R; i++) same = same && (ex[i] == ex[0]);
-      if (ppm_all(same)) {  // usual case: one common exponent, one scaled add
-        double v = 0.;
+      if (ppm_all(same)) {  // usual case: one common exponent, one scaled add; pairwise sum keeps the chain short
+        double t[R];
 #pragma unroll
-        for (int i = 0; i < R; i++) v = fma(prod[i], T.wt[b * R + i], v);  // padding slices carry weight 0
-        scaled_add(Im, Ie, v, ex[0]);
+        for (int i = 0; i < R; i++) t[i] = prod[i] * T.wt[b * R + i];  // padding slices carry weight 0
+#pragma unroll
+        for (int st = 1; st < R; st *= 2)
+#pragma unroll
+          for (int i = 0; i + st < R; i += 2 * st) t[i] += t[i + st];
+        scaled_add(Im, Ie, t[0], ex[0]);
       } else {
 #pragma unroll
         for (int i = 0; i < R; i++) scaled_add(Im, Ie, prod[i] * T.wt[b * R + i], ex[i]);

@@ -40,7 +40,7 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes)
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 struct StageLayout {
-  size_t recs, blk, ops, oprec, yy, wt, total;
+  size_t recs, blk, ops, oprec, yy, wt, leaf, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
@@ -51,6 +51,7 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.oprec = o; o += align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double));
   L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
+  L.leaf = o; o += 32;
   L.total = o;
   return L;
 }
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(384, 1) sweep_kernel(SweepArgs a) {
       copy16(smem_raw + L.oprec, a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES, align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)));
       copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
+      copy16(smem_raw + L.leaf, a.t.scal + (size_t)p * SC_COUNT + SC_LA0, 32);
       __syncthreads();
       T.recs = reinterpret_cast<const EntryRec*>(smem_raw + L.recs);
       T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + L.blk);
@@ -95,12 +97,14 @@ __global__ void __launch_bounds__(384, 1) sweep_kernel(SweepArgs a) {
       T.oprec = reinterpret_cast<const double*>(smem_raw + L.oprec);
       T.yy = reinterpret_cast<const double*>(smem_raw + L.yy);
       T.wt = reinterpret_cast<const double*>(smem_raw + L.wt);
+      T.leaftab = reinterpret_cast<const double2*>(smem_raw + L.leaf);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
       T.blk = m.blk; T.ops = m.ops;
       T.oprec = a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES;
       T.yy = a.t.yy + (size_t)p * nbR;
       T.wt = m.slice_wt_pad;
+      T.leaftab = reinterpret_cast<const double2*>(a.t.scal + (size_t)p * SC_COUNT + SC_LA0);
     }
     for (int k = 0; k < a.items_per_warp; k++) {
       const long long batch = ((long long)chunk * a.items_per_warp + k) * wpc + warp;
@@ -171,7 +175,7 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   return pl;
 }
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
-  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * m.n_slots * 32;
+  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * (m.n_slots + 2) * 32;
 }
 
 template <int R, bool ST>

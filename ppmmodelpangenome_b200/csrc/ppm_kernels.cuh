@@ -8,14 +8,17 @@ namespace ppm {
 // Per-parameter-vector scalars written by the prepass (index into ParamScal::v)
 enum {
   SC_PI1 = 0,   // g2/(g2+l2), 0 when g2 == 0 (functions.cpp:227-231)
-  SC_LA0, SC_LD0,  // Mobile leaf partials for observation 0: a = m0 + pi1*(m1-m0), d = m1-m0
+  SC_PAD1,
+  SC_LA0, SC_LD0,  // Mobile leaf partials for observation 0: a = m0 + pi1*(m1-m0), d = m1-m0 (16-byte aligned pair)
   SC_LA1, SC_LD1,  // ... observation 1
   SC_C0, SC_C1, SC_C2,  // log(N0/nObs), log(i1/(l1 nObs)), log(i2/nObs)  (functions.cpp:348,354,356)
   SC_I2, SC_P0, SC_P1, SC_A, SC_B,  // computeI2 (functions.cpp:334-344)
   SC_LOG1ME2,  // log(1 - s_10)
   SC_IZ_M, SC_IZ_E,  // zero-row Mobile integral as mantissa * 2^-exp
-  SC_COUNT = 16
+  SC_COUNT = 20  // even: keeps the (a,d) pairs 16-byte aligned in every row
 };
+
+static_assert(SC_IZ_E < SC_COUNT && SC_COUNT % 2 == 0 && SC_LA0 % 2 == 0, "scal row layout");
 
 struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pad;

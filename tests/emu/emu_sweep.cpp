@@ -20,6 +20,7 @@ struct HostSlots {
   double2* base;
   double2 ld(int slot, int lane) const { return base[slot + lane]; }
   void st(int slot, int lane, double2 v) const { base[slot + lane] = v; }
+  const double2* ptr(int slot, int lane) const { return base + slot + lane; }
 };
 
 static std::string g_err;
@@ -87,6 +88,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.recs = recs.data() + (size_t)p * (md.n_entries + 1); T.blk = md.blk; T.ops = md.ops;
           T.oprec = oprec.data() + (size_t)p * md.n_ops * OPREC_DOUBLES;
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
+          T.leaftab = reinterpret_cast<const double2*>(scal.data() + (size_t)p * SC_COUNT + SC_LA0);
           if (prog.R == 8) s += sweep_item<8>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else if (prog.R == 4) s += sweep_item<4>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
           else if (prog.R == 12) s += sweep_item<12>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
