@@ -219,12 +219,12 @@ PPM_HD void prepass_i2_body(const ModelDev& m, const TablesDev& t, const double*
 }
 
 // ------------------------------------------------------------------------------------------------ sweep
-template <bool SMEM_SLOTS>
-struct SlotStore {
-  double2* base;  // [slot][lanes]
-  PPM_HD double2 ld(int slot, int lane) const { return base[slot * PPM_LANES + lane]; }
-  PPM_HD void st(int slot, int lane, double2 v) const { base[slot * PPM_LANES + lane] = v; }
-  PPM_HD const double2* ptr(int slot, int lane) const { return base + slot * PPM_LANES + lane; }
+// Per work item (32 patterns): its pattern words [n_words][lanes], the all-zero-subtree masks per slot, and the
+// Mobile partials (a,d) of the alive internal lineages [slot][lanes] (shared memory in the staged variant).
+struct ItemMem {
+  uint32_t* sw;
+  uint32_t* zw;
+  double2* slots;
 };
 
 // Where one work item reads its topology program and per-parameter tables from (shared memory copies in the
@@ -277,11 +277,11 @@ PPM_HD void update_range(double (&prod)[R], const double (&Y)[R], double a, doub
   for (int i = 0; i < R; i++)
     if (i >= I0 && i < I1) prod[i] *= fma(nbb, Y[i], a);
 }
-template <int R>
-PPM_HD void coded_update(double (&prod)[R], const double (&Y)[R], double a, double nbb, uint32_t mk) {
+template <int R, int NI>
+PPM_HD void coded_update(double (&prod)[NI][R], const double (&Y)[R], const double (&a)[NI], const double (&nbb)[NI], uint32_t mk) {
   switch (mk & 0xffffu) {
-#define PPM_SUF(k) case k: update_range<k, R, R>(prod, Y, a, nbb); break;
-#define PPM_PRE(k) case 16 + k: update_range<0, k, R>(prod, Y, a, nbb); break;
+#define PPM_SUF(k) case k: _Pragma("unroll") for (int q = 0; q < NI; q++) update_range<k, R, R>(prod[q], Y, a[q], nbb[q]); break;
+#define PPM_PRE(k) case 16 + k: _Pragma("unroll") for (int q = 0; q < NI; q++) update_range<0, k, R>(prod[q], Y, a[q], nbb[q]); break;
     PPM_SUF(1) PPM_SUF(2) PPM_SUF(3) PPM_SUF(4) PPM_SUF(5) PPM_SUF(6) PPM_SUF(7) PPM_SUF(8)
     PPM_SUF(9) PPM_SUF(10) PPM_SUF(11) PPM_SUF(12) PPM_SUF(13) PPM_SUF(14) PPM_SUF(15)
     PPM_PRE(1) PPM_PRE(2) PPM_PRE(3) PPM_PRE(4) PPM_PRE(5) PPM_PRE(6) PPM_PRE(7) PPM_PRE(8)
@@ -291,10 +291,12 @@ PPM_HD void coded_update(double (&prod)[R], const double (&Y)[R], double a, doub
     default: {
       const uint32_t live = mk >> 16;
 #pragma unroll
-      for (int i = 0; i < R; i++) {
-        const double t = prod[i] * fma(nbb, Y[i], a);
-        prod[i] = (live & (1u << i)) ? t : prod[i];
-      }
+      for (int q = 0; q < NI; q++)
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          const double t = prod[q][i] * fma(nbb[q], Y[i], a[q]);
+          prod[q][i] = (live & (1u << i)) ? t : prod[q][i];
+        }
     }
   }
 }
@@ -309,87 +311,111 @@ PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) 
   }
 }
 
-// One work item = PPM_LANES patterns (one per lane) x one parameter vector.  Returns this lane's count*log-mixture.
-// sw: per-warp pattern words [n_words][PPM_LANES]; zw: per-warp all-zero-subtree masks per slot.
-template <int R, class Slots>
-PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long long batch, int lane, uint32_t* sw,
-                         uint32_t* zw, const Slots& slots) {
+// NI work items at once = NI x PPM_LANES patterns (one per lane and item) x one parameter vector.
+// Everything topology-driven (records, block descriptors, node-op descriptors, branches, address arithmetic) is
+// warp-uniform and therefore shared by the NI items; only the per-lane loads and the FP64 work are per item.
+// That halves (NI = 2) the non-FP64 instructions per pattern and gives every warp NI independent dependency
+// chains through the latency-bound parts (node ops, born/merged-in-block lineages).
+// Returns, per item, this lane's count*log-mixture in contrib[].
+template <int R, int NI>
+PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long long batch0, int lane,
+                        const ItemMem (&mem)[NI], double (&contrib)[NI]) {
   const ModelDev& m = a.m;
   const double* sc = a.t.scal + (size_t)p * SC_COUNT;
   const bool skip = (a.mode == 0) && !a.force && (sc[SC_I2] < 0.);  // penalty branch: no pattern work (functions.cpp:362-364)
-  const long long pat = a.first + batch * PPM_LANES + lane;
-  const bool active = pat < a.first + a.count;
-  double contrib = 0.;
-  if (skip) return 0.;
+  long long pat[NI];
+  bool active[NI];
+#pragma unroll
+  for (int q = 0; q < NI; q++) {
+    pat[q] = a.first + (batch0 + q) * PPM_LANES + lane;
+    active[q] = (batch0 + q) < a.n_batches && pat[q] < a.first + a.count;
+    contrib[q] = 0.;
+  }
+  if (skip) return;
 
-  for (int w = 0; w < m.n_words; w++)
-    sw[w * PPM_LANES + lane] = (a.mode == 1 || !active) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat];
+#pragma unroll
+  for (int q = 0; q < NI; q++)
+    for (int w = 0; w < m.n_words; w++)
+      mem[q].sw[w * PPM_LANES + lane] = (a.mode == 1 || !active[q]) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
   ppm_syncwarp();
 
   const double pi1 = sc[SC_PI1];
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
-  // T.leaftab[bit] = the leaf partials (a,d) for observation 0 / 1: a child that is a leaf is fetched with one
-  // load through a selected pointer, exactly like an internal lineage (no per-value selects)
 
-  double A0 = 0., A1 = 0.;     // log p1(root) of the two pure-loss categories
-  int X = 0;                   // sum of renormalisation shifts of all lineages formed so far
-  double Im = 0.; int Ie = 0x3fffffff;  // Mobile integral = Im * 2^-Ie (exponent of an empty sum: +inf)
-
-  double prod[R], Y[R];
-  int ex[R];
+  double A0[NI], A1[NI];    // log p1(root) of the two pure-loss categories
+  int X[NI];                // sum of renormalisation shifts of all lineages formed so far
+  double Im[NI]; int Ie[NI];  // Mobile integral = Im * 2^-Ie (exponent of an empty sum: +inf)
+  double prod[NI][R], Y[R];
+  int ex[NI][R];
+#pragma unroll
+  for (int q = 0; q < NI; q++) { A0[q] = 0.; A1[q] = 0.; X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
 
   for (int b = 0; b <= m.n_blocks; b++) {
     const BlockDesc bd = T.blk[b];
     const bool real = b < m.n_blocks;
     if (real) {
 #pragma unroll
-      for (int i = 0; i < R; i++) { prod[i] = 1.; ex[i] = X; Y[i] = T.yy[b * R + i]; }
+      for (int i = 0; i < R; i++) Y[i] = T.yy[b * R + i];
+#pragma unroll
+      for (int q = 0; q < NI; q++)
+#pragma unroll
+        for (int i = 0; i < R; i++) { prod[q][i] = 1.; ex[q][i] = X[q]; }
     }
-    // ---- node ops: form every node born before the end of this block.  Straight-line: both the "leaf" and the
-    // "slot" operand of each child are fetched and one is selected, so all loads of an op issue together.
+    // ---- node ops: form every node born before the end of this block.  T.leaftab[bit] holds the leaf partials for
+    // observation 0 / 1, so a child that is a leaf is fetched through a selected pointer exactly like an internal
+    // lineage (one load, no per-value selects).
     for (int o = bd.op0; o < bd.op1; o++) {
       const NodeOpDev op = T.ops[o];
       const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
       const bool lleaf = op.lref < 0, rleaf = op.rref < 0;
       const int lpos = lleaf ? -(op.lref + 1) : 0, rpos = rleaf ? -(op.rref + 1) : 0;
-      const uint32_t wl = sw[(lpos >> 5) * PPM_LANES + lane], wr = sw[(rpos >> 5) * PPM_LANES + lane];
-      const uint32_t zls = zw[lleaf ? 0 : op.lref], zrs = zw[rleaf ? 0 : op.rref];
-      const uint32_t bl = (wl >> (lpos & 31)) & 1u, br = (wr >> (rpos & 31)) & 1u;
-      const double2 L = *(lleaf ? T.leaftab + bl : slots.ptr(op.lref, lane));
-      const double2 Rr = *(rleaf ? T.leaftab + br : slots.ptr(op.rref, lane));
-      const uint32_t zbl = ~ppm_ballot(bl != 0u), zbr = ~ppm_ballot(br != 0u);
-      const uint32_t zwl = lleaf ? zbl : zls, zwr = rleaf ? zbr : zrs;
-      const uint32_t zwv = zwl & zwr;
-      // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
-      {
-        const bool zl = (zwl >> lane) & 1u, zr = (zwr >> lane) & 1u;
-        const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
-        A0 += zl ? (zv ? 0. : orc[5]) : orc[4];
-        A1 += zl ? (zv ? 0. : orc[7]) : orc[6];
-        A0 += zr ? (zv ? 0. : orc[9]) : orc[8];
-        A1 += zr ? (zv ? 0. : orc[11]) : orc[10];
-      }
-      if (op.dst >= 0) {
-        // Mobile merge (objects.cpp:427-435 in linear domain)
-        double m0 = fma(-orc[0], L.y, L.x) * fma(-orc[2], Rr.y, Rr.x);
-        double m1 = fma(orc[1], L.y, L.x) * fma(orc[3], Rr.y, Rr.x);
-        double d = m1 - m0;
-        double av = fma(pi1, d, m0);
-        // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
-        int be = biased_exp(fmax(fabs(av), fabs(d)));
-        int k = (be != 0 && be < 1023 - 40) ? 1022 - be : 0;
-        if (ppm_any(k != 0)) {
-          double s = pow2i(k);
-          av *= s; d *= s;
-          X += k;
-          if (real) {
+      const int lslot = lleaf ? 0 : op.lref, rslot = rleaf ? 0 : op.rref;
+      double2 L[NI], Rr[NI];
+      uint32_t zwl[NI], zwr[NI];
 #pragma unroll
-            for (int i = 0; i < R; i++) if (i >= op.i0) ex[i] += k;
-          }
+      for (int q = 0; q < NI; q++) {
+        const uint32_t bl = (mem[q].sw[(lpos >> 5) * PPM_LANES + lane] >> (lpos & 31)) & 1u;
+        const uint32_t br = (mem[q].sw[(rpos >> 5) * PPM_LANES + lane] >> (rpos & 31)) & 1u;
+        L[q] = *(lleaf ? T.leaftab + bl : mem[q].slots + lslot * PPM_LANES + lane);
+        Rr[q] = *(rleaf ? T.leaftab + br : mem[q].slots + rslot * PPM_LANES + lane);
+        const uint32_t zbl = ~ppm_ballot(bl != 0u), zbr = ~ppm_ballot(br != 0u);
+        zwl[q] = lleaf ? zbl : mem[q].zw[lslot];
+        zwr[q] = rleaf ? zbr : mem[q].zw[rslot];
+      }
+#pragma unroll
+      for (int q = 0; q < NI; q++) {
+        const uint32_t zwv = zwl[q] & zwr[q];
+        // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
+        {
+          const bool zl = (zwl[q] >> lane) & 1u, zr = (zwr[q] >> lane) & 1u;
+          const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
+          A0[q] += zl ? (zv ? 0. : orc[5]) : orc[4];
+          A1[q] += zl ? (zv ? 0. : orc[7]) : orc[6];
+          A0[q] += zr ? (zv ? 0. : orc[9]) : orc[8];
+          A1[q] += zr ? (zv ? 0. : orc[11]) : orc[10];
         }
-        // every lane reads back only what it wrote itself (its slot column; zw gets the same word from all lanes)
-        slots.st(op.dst, lane, make_double2(av, d));
-        zw[op.dst] = zwv;
+        if (op.dst >= 0) {
+          // Mobile merge (objects.cpp:427-435 in linear domain)
+          double m0 = fma(-orc[0], L[q].y, L[q].x) * fma(-orc[2], Rr[q].y, Rr[q].x);
+          double m1 = fma(orc[1], L[q].y, L[q].x) * fma(orc[3], Rr[q].y, Rr[q].x);
+          double d = m1 - m0;
+          double av = fma(pi1, d, m0);
+          // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
+          int be = biased_exp(fmax(fabs(av), fabs(d)));
+          int k = (be != 0 && be < 1023 - 40) ? 1022 - be : 0;
+          if (ppm_any(k != 0)) {
+            double sfac = pow2i(k);
+            av *= sfac; d *= sfac;
+            X[q] += k;
+            if (real) {
+#pragma unroll
+              for (int i = 0; i < R; i++) if (i >= op.i0) ex[q][i] += k;
+            }
+          }
+          // every lane reads back only what it wrote itself (its slot column; zw gets the same word from all lanes)
+          mem[q].slots[op.dst * PPM_LANES + lane] = make_double2(av, d);
+          mem[q].zw[op.dst] = zwv;
+        }
       }
     }
     if (!real) break;
@@ -401,119 +427,158 @@ PPM_HD double sweep_item(const SweepArgs& a, const ItemTables& T, int p, long lo
       const int ce = (e + 16 < bd.e_slot0) ? e + 16 : bd.e_slot0;
       double K; uint32_t ref, mk;   // ref = word | next word << 16, mk = the leaf's bit in that word
       load_rec(T.recs, e, K, ref, mk);
-      uint32_t wv = sw[(ref & 0xffffu) * PPM_LANES + lane];
+      uint32_t wv[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) wv[q] = mem[q].sw[(ref & 0xffffu) * PPM_LANES + lane];
 #pragma unroll 2
       for (; e < ce; e++) {
-        const uint32_t wn = sw[(ref >> 16) * PPM_LANES + lane];
-        const bool bit = (wv & mk) != 0u;
-        const double aa = bit ? la1 : la0;
-        const double nbb = (bit ? ld1 : ld0) * -K;
+        uint32_t wn[NI];
+        bool bit[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) { wn[q] = mem[q].sw[(ref >> 16) * PPM_LANES + lane]; bit[q] = (wv[q] & mk) != 0u; }
+        const double nK = -K;
         load_rec(T.recs, e + 1, K, ref, mk);  // the table carries one padding record
 #pragma unroll
-        for (int i = 0; i < R; i++) prod[i] *= fma(nbb, Y[i], aa);
-        wv = wn;
+        for (int q = 0; q < NI; q++) {
+          const double aa = bit[q] ? la1 : la0;
+          const double nbb = (bit[q] ? ld1 : ld0) * nK;
+#pragma unroll
+          for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], aa);
+          wv[q] = wn[q];
+        }
       }
-      if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
+#pragma unroll
+      for (int q = 0; q < NI; q++)
+        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
     // (2) internal lineages alive in every slice: partials in slots; ref = slot | next slot << 16
     for (int e = bd.e_slot0; e < bd.e_pleaf0;) {
       const int ce = (e + 16 < bd.e_pleaf0) ? e + 16 : bd.e_pleaf0;
       double K; uint32_t ref, mk;
       load_rec(T.recs, e, K, ref, mk);
-      double2 ad = slots.ld((int)(ref & 0xffffu), lane);
+      double2 ad[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots[(int)(ref & 0xffffu) * PPM_LANES + lane];
 #pragma unroll 2
       for (; e < ce; e++) {
-        const double2 an = slots.ld((int)(ref >> 16), lane);
-        const double nbb = ad.y * -K;
+        double2 an[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) an[q] = mem[q].slots[(int)(ref >> 16) * PPM_LANES + lane];
+        const double nK = -K;
         load_rec(T.recs, e + 1, K, ref, mk);
 #pragma unroll
-        for (int i = 0; i < R; i++) prod[i] *= fma(nbb, Y[i], ad.x);
-        ad = an;
+        for (int q = 0; q < NI; q++) {
+          const double nbb = ad[q].y * nK;
+#pragma unroll
+          for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], ad[q].x);
+          ad[q] = an[q];
+        }
       }
-      if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
+#pragma unroll
+      for (int q = 0; q < NI; q++)
+        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
-    // (3) leaves merged inside the block: ref = bit position | next << 16, mk = live slices
+    // (3) leaves merged inside the block: ref = bit position | next << 16, mk = code | live slices << 16
     if (bd.e_pleaf0 < bd.e_pslot0) {
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_pleaf0, K, ref, mk);
-      uint32_t wv = sw[((ref & 0xffffu) >> 5) * PPM_LANES + lane];
+      uint32_t wv[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) wv[q] = mem[q].sw[((ref & 0xffffu) >> 5) * PPM_LANES + lane];
       for (int e = bd.e_pleaf0; e < bd.e_pslot0; e++) {
-        const uint32_t wn = sw[((ref >> 16) >> 5) * PPM_LANES + lane];
-        const bool bit = (wv >> (ref & 31u)) & 1u;
-        const double aa = bit ? la1 : la0;
-        const double nbb = (bit ? ld1 : ld0) * -K;
+        uint32_t wn[NI];
+        double aa[NI], nbb[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+          wn[q] = mem[q].sw[((ref >> 16) >> 5) * PPM_LANES + lane];
+          const bool bit = (wv[q] >> (ref & 31u)) & 1u;
+          aa[q] = bit ? la1 : la0;
+          nbb[q] = (bit ? ld1 : ld0) * -K;
+        }
         const uint32_t mcur = mk;
         load_rec(T.recs, e + 1, K, ref, mk);
-        coded_update<R>(prod, Y, aa, nbb, mcur);
-        wv = wn;
+        coded_update<R, NI>(prod, Y, aa, nbb, mcur);
+#pragma unroll
+        for (int q = 0; q < NI; q++) wv[q] = wn[q];
       }
     }
-    // (4) internal lineages born and/or merged inside the block: ref = slot | next slot << 16, mk = live slices
+    // (4) internal lineages born and/or merged inside the block: ref = slot | next slot << 16
     if (bd.e_pslot0 < bd.e_end) {
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_pslot0, K, ref, mk);
-      double2 ad = slots.ld((int)(ref & 0xffffu), lane);
+      double2 ad[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots[(int)(ref & 0xffffu) * PPM_LANES + lane];
       for (int e = bd.e_pslot0; e < bd.e_end; e++) {
-        const double2 an = slots.ld((int)(ref >> 16), lane);
-        const double nbb = ad.y * -K;
+        double2 an[NI];
+        double aa[NI], nbb[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+          an[q] = mem[q].slots[(int)(ref >> 16) * PPM_LANES + lane];
+          aa[q] = ad[q].x;
+          nbb[q] = ad[q].y * -K;
+        }
         const uint32_t mcur = mk;
         load_rec(T.recs, e + 1, K, ref, mk);
-        coded_update<R>(prod, Y, ad.x, nbb, mcur);
-        ad = an;
+        coded_update<R, NI>(prod, Y, aa, nbb, mcur);
+#pragma unroll
+        for (int q = 0; q < NI; q++) ad[q] = an[q];
       }
     }
-    if (ppm_any(products_small<R>(prod))) rescale_products<R>(prod, ex);
-
     // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
-    {
+#pragma unroll
+    for (int q = 0; q < NI; q++) {
+      if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
       bool same = true;
 #pragma unroll
-      for (int i = 1; i < R; i++) same = same && (ex[i] == ex[0]);
+      for (int i = 1; i < R; i++) same = same && (ex[q][i] == ex[q][0]);
       if (ppm_all(same)) {  // usual case: one common exponent, one scaled add; pairwise sum keeps the chain short
         double t[R];
 #pragma unroll
-        for (int i = 0; i < R; i++) t[i] = prod[i] * T.wt[b * R + i];  // padding slices carry weight 0
+        for (int i = 0; i < R; i++) t[i] = prod[q][i] * T.wt[b * R + i];  // padding slices carry weight 0
 #pragma unroll
         for (int st = 1; st < R; st *= 2)
 #pragma unroll
           for (int i = 0; i + st < R; i += 2 * st) t[i] += t[i + st];
-        scaled_add(Im, Ie, t[0], ex[0]);
+        scaled_add(Im[q], Ie[q], t[0], ex[q][0]);
       } else {
 #pragma unroll
-        for (int i = 0; i < R; i++) scaled_add(Im, Ie, prod[i] * T.wt[b * R + i], ex[i]);
+        for (int i = 0; i < R; i++) scaled_add(Im[q], Ie[q], prod[q][i] * T.wt[b * R + i], ex[q][i]);
       }
     }
   }
 
-  if (a.mode == 1) {
-    if (active) {
-      double* scw = a.t.scal + (size_t)p * SC_COUNT;
-      scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
+#pragma unroll
+  for (int q = 0; q < NI; q++) {
+    if (a.mode == 1) {
+      if (active[q]) {
+        double* scw = a.t.scal + (size_t)p * SC_COUNT;
+        scw[SC_IZ_M] = Im[q]; scw[SC_IZ_E] = (double)Ie[q];
+      }
+      continue;
     }
-    return 0.;
-  }
-  // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
-  if (active) {
-    const double lik0 = sc[SC_C0] + A0;
-    const int mr = m.mrca[pat];
-    const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];
-    double lik1;
-    if (m.freq[pat] == 0) lik1 = lse2(sc[SC_C1] + A1, sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
-    else lik1 = sc[SC_C1] + (A1 + du.x);
-    const double lik2 = (Im > 0.) ? sc[SC_C2] + (log(Im) - (double)Ie * 0.693147180559945309417232) : -INFINITY;
-    double mx = fmax(lik0, fmax(lik1, lik2));
-    double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));
-    contrib = tot * (double)m.counts[pat];
-    if (a.mode == 2) {
-      int c = 0;
-      if (lik1 > lik0) c = 1;
-      if (lik2 > (c ? lik1 : lik0)) c = 2;
-      long long r = pat - a.first;
-      if (a.cat) a.cat[r] = (signed char)c;
-      if (a.comp) { a.comp[3 * r] = lik0; a.comp[3 * r + 1] = lik1; a.comp[3 * r + 2] = lik2; }
+    // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
+    if (active[q]) {
+      const double lik0 = sc[SC_C0] + A0[q];
+      const int mr = m.mrca[pat[q]];
+      const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];
+      double lik1;
+      if (m.freq[pat[q]] == 0) lik1 = lse2(sc[SC_C1] + A1[q], sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
+      else lik1 = sc[SC_C1] + (A1[q] + du.x);
+      const double lik2 = (Im[q] > 0.) ? sc[SC_C2] + (log(Im[q]) - (double)Ie[q] * 0.693147180559945309417232) : -INFINITY;
+      double mx = fmax(lik0, fmax(lik1, lik2));
+      double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));
+      contrib[q] = tot * (double)m.counts[pat[q]];
+      if (a.mode == 2) {
+        int c = 0;
+        if (lik1 > lik0) c = 1;
+        if (lik2 > (c ? lik1 : lik0)) c = 2;
+        long long r = pat[q] - a.first;
+        if (a.cat) a.cat[r] = (signed char)c;
+        if (a.comp) { a.comp[3 * r] = lik0; a.comp[3 * r + 1] = lik1; a.comp[3 * r + 2] = lik2; }
+      }
     }
   }
-  return contrib;
 }
 
 }  // namespace ppm

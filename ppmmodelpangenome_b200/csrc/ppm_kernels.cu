@@ -57,23 +57,29 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
 }
 __host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16(((size_t)m.n_words * 32 + m.n_slots) * 4); }
 
-// CTA work unit = (parameter vector p, chunk of warps*items_per_warp pattern batches).  STAGED: the topology
+// CTA work unit = (parameter vector p, chunk of warps*items_per_warp*NI pattern batches).  STAGED: the topology
 // program and p's tables are copied to shared memory once per unit and per-lineage partials live in shared
 // memory; otherwise everything is read from global memory (L1/L2) and the partials live in a global scratch.
-template <int R, bool STAGED>
-__global__ void __launch_bounds__(384, 1) sweep_kernel(SweepArgs a) {
+// Every warp sweeps NI batches (NI x 32 patterns) at once -- see sweep_items.
+template <int R, int NI, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? 256 : 384, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const StageLayout L = stage_layout(m);
   const size_t head = warp_head_bytes(m);
-  const size_t per_warp = head + (STAGED ? (size_t)m.n_slots * 32 * sizeof(double2) : 0);
-  unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_warp;
-  uint32_t* sw = reinterpret_cast<uint32_t*>(wbase);
-  uint32_t* zw = sw + m.n_words * 32;
-  SlotStore<STAGED> slots;
-  if (STAGED) slots.base = reinterpret_cast<double2*>(wbase + head);
-  else slots.base = a.gslots + ((size_t)blockIdx.x * wpc + warp) * (size_t)m.n_slots * 32;
+  const size_t slot_bytes = (size_t)m.n_slots * 32 * sizeof(double2);
+  const size_t per_item = head + (STAGED ? slot_bytes : 0);
+  unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_item * NI;
+  ItemMem mem[NI];
+#pragma unroll
+  for (int q = 0; q < NI; q++) {
+    unsigned char* ib = wbase + (size_t)q * per_item;
+    mem[q].sw = reinterpret_cast<uint32_t*>(ib);
+    mem[q].zw = mem[q].sw + m.n_words * 32;
+    if (STAGED) mem[q].slots = reinterpret_cast<double2*>(ib + head);
+    else mem[q].slots = a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)m.n_slots * 32;
+  }
   const int nbR = m.n_blocks * R;
 
   const long long n_units = (long long)a.t.P * a.n_chunks;
@@ -107,14 +113,19 @@ __global__ void __launch_bounds__(384, 1) sweep_kernel(SweepArgs a) {
       T.leaftab = reinterpret_cast<const double2*>(a.t.scal + (size_t)p * SC_COUNT + SC_LA0);
     }
     for (int k = 0; k < a.items_per_warp; k++) {
-      const long long batch = ((long long)chunk * a.items_per_warp + k) * wpc + warp;
-      if (batch >= a.n_batches) break;
-      double contrib = sweep_item<R>(a, T, p, batch, lane, sw, zw, slots);
+      const long long batch0 = (((long long)chunk * a.items_per_warp + k) * wpc + warp) * NI;
+      if (batch0 >= a.n_batches) break;
+      double contrib[NI];
+      sweep_items<R, NI>(a, T, p, batch0, lane, mem, contrib);
       if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-      if (lane == 0) a.partial[(size_t)p * a.n_batches + batch] = contrib;
+      for (int q = 0; q < NI; q++) {
+        double c = contrib[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0 && batch0 + q < a.n_batches) a.partial[(size_t)p * a.n_batches + batch0 + q] = c;
+      }
       __syncwarp();
     }
   }
@@ -153,39 +164,43 @@ void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_o
   prepass_i2_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t, i2_override);
 }
 
+static const int kItemsPerWarp = 2;  // NI: batches swept simultaneously by one warp
+
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   SweepPlan pl{};
+  const int NI = kItemsPerWarp;
   const size_t budget = 227 * 1024 - 1024;
   const StageLayout L = stage_layout(m);
   const size_t head = warp_head_bytes(m);
-  const size_t per_warp_staged = head + (size_t)m.n_slots * 32 * sizeof(double2);
+  const size_t per_warp_staged = NI * (head + (size_t)m.n_slots * 32 * sizeof(double2));
   int warps = 0;
-  if (L.total + 4 * per_warp_staged <= budget) warps = (int)std::min<size_t>(12, (budget - L.total) / per_warp_staged);
-  pl.staged = warps >= 4;
-  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(12, budget / std::max<size_t>(head, 1)));
-  if (n_batches < warps) warps = (int)std::max<long long>(1, n_batches);
+  if (L.total + 3 * per_warp_staged <= budget) warps = (int)std::min<size_t>(8, (budget - L.total) / per_warp_staged);  // <= 256 threads: up to 255 registers
+  pl.staged = warps >= 3;
+  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(12, budget / std::max<size_t>(NI * head, 1)));
+  long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
+  if (groups < warps) warps = (int)std::max<long long>(1, groups);
   pl.warps = warps;
-  long long total = n_batches * (long long)P;
+  long long total = groups * (long long)P;
   long long ipw = total / ((long long)n_sm * warps * 4);
   pl.items_per_warp = (int)std::max<long long>(1, std::min<long long>(8, ipw));
-  pl.n_chunks = (int)((n_batches + (long long)warps * pl.items_per_warp - 1) / ((long long)warps * pl.items_per_warp));
+  pl.n_chunks = (int)((groups + (long long)warps * pl.items_per_warp - 1) / ((long long)warps * pl.items_per_warp));
   long long units = (long long)pl.n_chunks * P;
   pl.grid_x = (int)std::min<long long>(units, pl.staged ? 2147483647LL : (long long)n_sm);
-  pl.smem_bytes = (pl.staged ? L.total + per_warp_staged * warps : head * warps);
+  pl.smem_bytes = (pl.staged ? L.total + per_warp_staged * warps : NI * head * warps);
   return pl;
 }
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
-  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * (m.n_slots + 2) * 32;
+  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * m.n_slots * 32;
 }
 
 template <int R, bool ST>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  sweep_kernel<R, ST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+  sweep_kernel<R, kItemsPerWarp, ST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {

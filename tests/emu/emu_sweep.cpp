@@ -16,13 +16,6 @@
 
 using namespace ppm;
 
-struct HostSlots {
-  double2* base;
-  double2 ld(int slot, int lane) const { return base[slot + lane]; }
-  void st(int slot, int lane, double2 v) const { base[slot + lane] = v; }
-  const double2* ptr(int slot, int lane) const { return base + slot + lane; }
-};
-
 static std::string g_err;
 
 extern "C" const char* emu_error() { return g_err.c_str(); }
@@ -74,26 +67,31 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
 
-    std::vector<uint32_t> sw(pat.n_words), zw(prog.n_slots);
-    std::vector<double2> slotmem(prog.n_slots);
-    HostSlots slots{slotmem.data()};
+    // two items per "warp" as on the device (NI = 2), one lane each
+    const int NI = 2;
+    std::vector<uint32_t> sw(NI * pat.n_words), zw(NI * prog.n_slots);
+    std::vector<double2> slotmem(NI * prog.n_slots);
+    ItemMem mem[2];
+    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].zw = zw.data() + q * prog.n_slots; mem[q].slots = slotmem.data() + q * prog.n_slots; }
     auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
       SweepArgs a{};
       a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
       a.n_batches = a.count; a.n_items = a.n_batches * nP; a.comp = comp; a.cat = cat; a.force = force;
       for (int p = 0; p < nP; p++) {
         double s = 0;
-        for (long long bt = 0; bt < a.n_batches; bt++) {
+        for (long long bt = 0; bt < a.n_batches; bt += NI) {
           ItemTables T;
           T.recs = recs.data() + (size_t)p * (md.n_entries + 1); T.blk = md.blk; T.ops = md.ops;
           T.oprec = oprec.data() + (size_t)p * md.n_ops * OPREC_DOUBLES;
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
           T.leaftab = reinterpret_cast<const double2*>(scal.data() + (size_t)p * SC_COUNT + SC_LA0);
-          if (prog.R == 8) s += sweep_item<8>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
-          else if (prog.R == 4) s += sweep_item<4>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
-          else if (prog.R == 12) s += sweep_item<12>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
-          else if (prog.R == 16) s += sweep_item<16>(a, T, p, bt, 0, sw.data(), zw.data(), slots);
-          else throw std::runtime_error("emulator built for R in {4,8,16}");
+          double c[2] = {0., 0.};
+          if (prog.R == 8) sweep_items<8, 2>(a, T, p, bt, 0, mem, c);
+          else if (prog.R == 4) sweep_items<4, 2>(a, T, p, bt, 0, mem, c);
+          else if (prog.R == 12) sweep_items<12, 2>(a, T, p, bt, 0, mem, c);
+          else if (prog.R == 16) sweep_items<16, 2>(a, T, p, bt, 0, mem, c);
+          else throw std::runtime_error("emulator built for R in {4,8,12,16}");
+          s += c[0]; s += c[1];
         }
         if (ll) ll[p] = s;
       }
