@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace ppm {
 
@@ -62,7 +63,7 @@ __host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return al
 // memory; otherwise everything is read from global memory (L1/L2) and the partials live in a global scratch.
 // Every warp sweeps NI batches (NI x 32 patterns) at once -- see sweep_items.
 template <int R, int NI, bool STAGED>
-__global__ void __launch_bounds__(STAGED ? 256 : 384, 1) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -164,7 +165,13 @@ void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_o
   prepass_i2_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t, i2_override);
 }
 
-static const int kItemsPerWarp = 2;  // NI: batches swept simultaneously by one warp
+static const int kItemsPerWarp = 1;  // NI: batches swept simultaneously by one warp (2 measured slower: 5 warps/SM)
+
+static int max_warps() {  // tuning knob: PPM_MAX_WARPS caps the warps per CTA (<= 16: 512 threads x 128 registers)
+  const char* e = std::getenv("PPM_MAX_WARPS");
+  int w = e ? std::atoi(e) : 16;
+  return w < 1 ? 1 : (w > 16 ? 16 : w);
+}
 
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   SweepPlan pl{};
@@ -174,9 +181,9 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   const size_t head = warp_head_bytes(m);
   const size_t per_warp_staged = NI * (head + (size_t)m.n_slots * 32 * sizeof(double2));
   int warps = 0;
-  if (L.total + 3 * per_warp_staged <= budget) warps = (int)std::min<size_t>(8, (budget - L.total) / per_warp_staged);  // <= 256 threads: up to 255 registers
+  if (L.total + 3 * per_warp_staged <= budget) warps = (int)std::min<size_t>(max_warps(), (budget - L.total) / per_warp_staged);
   pl.staged = warps >= 3;
-  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(12, budget / std::max<size_t>(NI * head, 1)));
+  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / std::max<size_t>(NI * head, 1)));
   long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
   if (groups < warps) warps = (int)std::max<long long>(1, groups);
   pl.warps = warps;
