@@ -381,9 +381,10 @@ Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-Program build_program(const Tree& t, int R) {
+Program build_program(const Tree& t, int R, bool deep) {
   Program pg;
   pg.R = R;
+  pg.deep = deep;
   const int nn = t.n_nodes, S = t.n_slices, nl = t.n_leaves;
   const int nb = (S + R - 1) / R;
   pg.n_blocks = nb;
@@ -445,8 +446,10 @@ Program build_program(const Tree& t, int R) {
   for (int b = 0; b <= nb; b++) { pg.blk[b].op0 = blk_op0[b]; pg.blk[b].op1 = blk_op0[b + 1]; }
   pg.n_slots = std::max(n_slots, 1);
 
-  // entries: per block, [full leaves | full slots | partial], each sorted by reference
+  // entries: per block, four typed segments (see BlockDesc), each sorted by reference
   struct Ent { int ref, i0, i1, node; bool leaf; };
+  const int kPadRef = 1 << 20;  // marks a padding record (sorts behind every real lineage)
+  if (deep && pg.n_slots + 1 > 65535) throw std::runtime_error("program: tree too large for 16-bit lineage references");
   std::vector<std::vector<Ent>> ent(nb);
   for (int v = 1; v < nn; v++) {
     if (js0[v] >= js1[v]) continue;
@@ -463,12 +466,17 @@ Program build_program(const Tree& t, int R) {
   double fp64 = 0;
   for (int b = 0; b < nb; b++) {
     const int nsl = pg.blk[b].nslices;
-    // 0 leaf alive in every slice, 1 internal alive in every slice, 2 leaf merged inside the block,
+    // 0 internal alive in every slice, 1 leaf alive in every slice, 2 leaf merged inside the block,
     // 3 internal lineage born and/or merged inside the block
     auto cls_of = [&](const Ent& e) {
       const bool full = e.i0 == 0 && e.i1 == nsl;  // in a short last block the padding slices carry weight 0
-      return full ? (e.leaf ? 0 : 1) : (e.leaf ? 2 : 3);
+      return full ? (e.leaf ? 1 : 0) : (e.leaf ? 2 : 3);
     };
+    if (deep) {  // pad the lineage segment to a multiple of 4 with records on the constant row (slot n_slots, K irrelevant)
+      int n0 = 0;
+      for (const Ent& e : ent[b]) n0 += cls_of(e) == 0;
+      for (; n0 % 4; n0++) { Ent e; e.i0 = 0; e.i1 = nsl; e.node = t.leaf_node[0]; e.leaf = false; e.ref = kPadRef; ent[b].push_back(e); }
+    }
     std::stable_sort(ent[b].begin(), ent[b].end(), [&](const Ent& x, const Ent& y) {
       int cx = cls_of(x), cy = cls_of(y);
       if (cx != cy) return cx < cy;
@@ -480,11 +488,12 @@ Program build_program(const Tree& t, int R) {
       int c = cls_of(e), at = (int)pg.entry_ref.size();
       for (int k = 0; k <= c; k++) if (seg0[k] < 0) seg0[k] = at;
       if (c >= 2) pg.n_partial++; else pg.n_full++;
-      fp64 += 1 + 2 * (e.i1 - e.i0);
+      if (e.ref != kPadRef) fp64 += 1 + 2 * (e.i1 - e.i0);
       const uint32_t live = c < 2 ? ((1u << R) - 1u) : (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
-      pg.entry_ref.push_back(c == 0 ? (e.ref >> 5) : e.ref);
+      const bool padrec = (c == 0 && e.ref == kPadRef);
+      pg.entry_ref.push_back(padrec ? pg.n_slots : (c == 1 ? (e.ref >> 5) : e.ref));
       uint32_t mk = live;
-      if (c == 0) mk = 1u << (e.ref & 31);
+      if (c == 1) mk = 1u << (e.ref & 31);
       else if (c >= 2) {
         // code in the low half: i0 for a suffix [i0,end), 16+i1 for a prefix [0,i1), 0 = use the mask in the high half
         const bool to_end = e.i1 == nsl;
@@ -500,7 +509,7 @@ Program build_program(const Tree& t, int R) {
     const int end = (int)pg.entry_ref.size();
     seg0[4] = end;
     for (int k = 3; k >= 0; k--) if (seg0[k] < 0) seg0[k] = seg0[k + 1];
-    bd.e_leaf0 = seg0[0]; bd.e_slot0 = seg0[1]; bd.e_pleaf0 = seg0[2]; bd.e_pslot0 = seg0[3]; bd.e_end = end;
+    bd.e_slot0 = seg0[0]; bd.e_leaf0 = seg0[1]; bd.e_pleaf0 = seg0[2]; bd.e_pslot0 = seg0[3]; bd.e_end = end;
     // prefetch hints: the upper half of ref names the next record's operand within the same segment
     // (0 = an always-valid dummy at the end of a segment)
     for (int k = 0; k < 4; k++)
@@ -508,7 +517,7 @@ Program build_program(const Tree& t, int R) {
   }
   {
     BlockDescHost& bd = pg.blk[nb];
-    bd.e_leaf0 = bd.e_slot0 = bd.e_pleaf0 = bd.e_pslot0 = bd.e_end = (int)pg.entry_ref.size();
+    bd.e_slot0 = bd.e_leaf0 = bd.e_pleaf0 = bd.e_pslot0 = bd.e_end = (int)pg.entry_ref.size();
   }
   // + node ops (8 merge + 2 renorm + 4 class adds), block ends (~3 per slice), epilogue (~60)
   pg.fp64_instr_per_eval = fp64 + 14.0 * (nl - 1) + 3.0 * S + 60;

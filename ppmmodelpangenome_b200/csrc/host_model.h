@@ -61,11 +61,12 @@ struct NodeOp {
   int32_t pad;
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
-  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
+  int32_t slice0, nslices, op0, op1, e_slot0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
 };
 struct Program {
   int R = 8;
   int n_blocks = 0, n_slots = 0;
+  bool deep = false;
   std::vector<BlockDescHost> blk;                 // [n_blocks+1]; blk[n_blocks] carries the node ops after the last block
   std::vector<NodeOp> ops;
   std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
@@ -75,6 +76,8 @@ struct Program {
   // modelled FP64 instruction count per pattern-eval of the main kernel
   double fp64_instr_per_eval = 0;
 };
-Program build_program(const Tree& t, int R);
+// deep: pad every block's fully-alive lineage segment to a multiple of 4 records with padding records that refer
+// to the constant row (slot index n_slots) -- needed by the global-memory sweep variant's four-deep prefetch
+Program build_program(const Tree& t, int R, bool deep = false);
 
 }  // namespace ppm

@@ -37,6 +37,18 @@ static inline int ppm_double2hiint(double x) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define ppm_cp_async16(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define ppm_cp_commit() asm volatile("cp.async.commit_group;" ::: "memory")
+#define ppm_cp_wait1() asm volatile("cp.async.wait_group 1;" ::: "memory")
+#define ppm_cp_wait0() asm volatile("cp.async.wait_group 0;" ::: "memory")
+#else
+#define ppm_cp_async16(dst, src) std::memcpy((dst), (src), 16)
+#define ppm_cp_commit() ((void)0)
+#define ppm_cp_wait1() ((void)0)
+#define ppm_cp_wait0() ((void)0)
+#endif
+
 namespace ppm {
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -317,9 +329,12 @@ PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) 
 // That halves (NI = 2) the non-FP64 instructions per pattern and gives every warp NI independent dependency
 // chains through the latency-bound parts (node ops, born/merged-in-block lineages).
 // Returns, per item, this lane's count*log-mixture in contrib[].
-template <int R, int NI>
+// DEEP (the variant whose tables and lineage slots live in global memory): the records of the fully-alive entries
+// are streamed through a per-warp shared-memory ring (wrec, 3 chunks of 32 records, cp.async two chunks ahead) and
+// lineage partials are fetched four entries ahead, so L2/HBM latency is covered by ~140 cycles of FP64 work each.
+template <int R, int NI, bool DEEP>
 PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long long batch0, int lane,
-                        const ItemMem (&mem)[NI], double (&contrib)[NI]) {
+                        const ItemMem (&mem)[NI], double (&contrib)[NI], EntryRec* wrec) {
   const ModelDev& m = a.m;
   const double* sc = a.t.scal + (size_t)p * SC_COUNT;
   const bool skip = (a.mode == 0) && !a.force && (sc[SC_I2] < 0.);  // penalty branch: no pattern work (functions.cpp:362-364)
@@ -341,6 +356,10 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 
   const double pi1 = sc[SC_PI1];
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
+  if (DEEP) {
+#pragma unroll
+    for (int q = 0; q < NI; q++) mem[q].slots[m.n_slots * PPM_LANES + lane] = make_double2(1., 0.);
+  }
 
   double A0[NI], A1[NI];    // log p1(root) of the two pure-loss categories
   int X[NI];                // sum of renormalisation shifts of all lineages formed so far
@@ -420,12 +439,128 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     }
     if (!real) break;
 
-    // ---- entries.  Each record names the NEXT record's operand in its upper bits, so the next operand load is
-    // issued before the current products (software prefetch); chunks of 16 entries end with a range check.
-    // (1) leaves alive in every slice of the block: partials selected by the pattern bit
-    for (int e = bd.e_leaf0; e < bd.e_slot0;) {
-      const int ce = (e + 16 < bd.e_slot0) ? e + 16 : bd.e_slot0;
-      double K; uint32_t ref, mk;   // ref = word | next word << 16, mk = the leaf's bit in that word
+    // ---- entries alive in every slice of the block: first the internal lineages (partials in slots), then the
+    // leaves (partials selected by the pattern bit).
+    if (DEEP) {
+      // the constant row (1,0) behind the last slot makes padding records multiply by one
+      const int E0 = bd.e_slot0, E1 = bd.e_pleaf0, ES = bd.e_leaf0;
+      const int nch = (E1 - E0 + 31) >> 5;
+      auto stage = [&](int c) {
+        int idx = E0 + c * 32 + lane;
+        idx = idx > m.n_entries ? m.n_entries : idx;  // the table ends with one padding record
+        ppm_cp_async16(wrec + (c % 3) * 32 + lane, T.recs + idx);
+        ppm_cp_commit();
+      };
+      if (PPM_LANES == 32) { stage(0); stage(1); }
+      double2 ring[NI][4];
+      if (nch > 0 && ES > E0) {  // preload the first four lineage partials (ES - E0 is a multiple of 4)
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int sl = T.recs[E0 + u].ref & 0xffff;
+#pragma unroll
+          for (int q = 0; q < NI; q++) ring[q][u] = mem[q].slots[sl * PPM_LANES + lane];
+        }
+      }
+      for (int c = 0; c < nch; c++) {
+        const EntryRec* cur; const EntryRec* nxt;
+        if (PPM_LANES == 32) {
+          stage(c + 2);
+          ppm_cp_wait1();
+          ppm_syncwarp();
+          cur = wrec + (c % 3) * 32; nxt = wrec + ((c + 1) % 3) * 32;
+        } else {  // host emulation reads the table directly
+          cur = T.recs + E0 + c * 32; nxt = cur + 32;
+        }
+        const int base = E0 + c * 32;
+        const int n = (E1 - base < 32) ? E1 - base : 32;
+        int ns = ES - base; ns = ns < 0 ? 0 : (ns > n ? n : ns);  // lineage entries of this chunk: [0, ns), a multiple of 4
+        for (int j0 = 0; j0 < ns; j0 += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int j = j0 + u;
+            double K; uint32_t ref, mk;
+            load_rec(cur, j, K, ref, mk);
+            // slot of the entry four ahead (next chunk if needed); past the segment: the constant row
+            const int ja = j + 4;
+            const int gidx = base + ja;
+            int sl = m.n_slots;
+            if (gidx < ES) sl = (ja < 32) ? (cur[ja].ref & 0xffff) : (nxt[ja - 32].ref & 0xffff);
+            const double nK = -K;
+#pragma unroll
+            for (int q = 0; q < NI; q++) {
+              const double2 ad = ring[q][u];
+              ring[q][u] = mem[q].slots[sl * PPM_LANES + lane];
+              const double nbb = ad.y * nK;
+#pragma unroll
+              for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], ad.x);
+            }
+          }
+          if ((j0 & 15) == 12) {
+#pragma unroll
+            for (int q = 0; q < NI; q++)
+              if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+          }
+        }
+        if (ns < n) {  // leaf entries of this chunk
+          double K; uint32_t ref, mk;
+          load_rec(cur, ns, K, ref, mk);
+          for (int j = ns; j < n; j++) {
+            bool bit[NI];
+#pragma unroll
+            for (int q = 0; q < NI; q++) bit[q] = (mem[q].sw[(ref & 0xffffu) * PPM_LANES + lane] & mk) != 0u;
+            const double nK = -K;
+            if (j + 1 < 32) load_rec(cur, j + 1, K, ref, mk); else load_rec(nxt, 0, K, ref, mk);
+#pragma unroll
+            for (int q = 0; q < NI; q++) {
+              const double aa = bit[q] ? la1 : la0;
+              const double nbb = (bit[q] ? ld1 : ld0) * nK;
+#pragma unroll
+              for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], aa);
+            }
+            if ((j & 15) == 15) {
+#pragma unroll
+              for (int q = 0; q < NI; q++)
+                if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+            }
+          }
+        }
+        ppm_syncwarp();  // the ring slot (c % 3) is refilled two iterations from now
+      }
+      if (PPM_LANES == 32) { ppm_cp_wait0(); ppm_syncwarp(); }
+    } else {
+    // Each record names the NEXT record's operand in its upper bits, so the next operand load is issued before the
+    // current products (software prefetch); chunks of 16 entries end with a range check.
+    // (1) internal lineages alive in every slice: partials in slots; ref = slot | next slot << 16
+    for (int e = bd.e_slot0; e < bd.e_leaf0;) {
+      const int ce = (e + 16 < bd.e_leaf0) ? e + 16 : bd.e_leaf0;
+      double K; uint32_t ref, mk;
+      load_rec(T.recs, e, K, ref, mk);
+      double2 ad[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots[(int)(ref & 0xffffu) * PPM_LANES + lane];
+#pragma unroll 2
+      for (; e < ce; e++) {
+        double2 an[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) an[q] = mem[q].slots[(int)(ref >> 16) * PPM_LANES + lane];
+        const double nK = -K;
+        load_rec(T.recs, e + 1, K, ref, mk);
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+          const double nbb = ad[q].y * nK;
+#pragma unroll
+          for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], ad[q].x);
+          ad[q] = an[q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NI; q++)
+        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+    }
+    // (2) leaves alive in every slice of the block: ref = word | next word << 16, mk = the leaf's bit in that word
+    for (int e = bd.e_leaf0; e < bd.e_pleaf0;) {
+      const int ce = (e + 16 < bd.e_pleaf0) ? e + 16 : bd.e_pleaf0;
+      double K; uint32_t ref, mk;
       load_rec(T.recs, e, K, ref, mk);
       uint32_t wv[NI];
 #pragma unroll
@@ -451,32 +586,6 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       for (int q = 0; q < NI; q++)
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
-    // (2) internal lineages alive in every slice: partials in slots; ref = slot | next slot << 16
-    for (int e = bd.e_slot0; e < bd.e_pleaf0;) {
-      const int ce = (e + 16 < bd.e_pleaf0) ? e + 16 : bd.e_pleaf0;
-      double K; uint32_t ref, mk;
-      load_rec(T.recs, e, K, ref, mk);
-      double2 ad[NI];
-#pragma unroll
-      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots[(int)(ref & 0xffffu) * PPM_LANES + lane];
-#pragma unroll 2
-      for (; e < ce; e++) {
-        double2 an[NI];
-#pragma unroll
-        for (int q = 0; q < NI; q++) an[q] = mem[q].slots[(int)(ref >> 16) * PPM_LANES + lane];
-        const double nK = -K;
-        load_rec(T.recs, e + 1, K, ref, mk);
-#pragma unroll
-        for (int q = 0; q < NI; q++) {
-          const double nbb = ad[q].y * nK;
-#pragma unroll
-          for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], ad[q].x);
-          ad[q] = an[q];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < NI; q++)
-        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
     // (3) leaves merged inside the block: ref = bit position | next << 16, mk = code | live slices << 16
     if (bd.e_pleaf0 < bd.e_pslot0) {

@@ -108,8 +108,10 @@ struct ppm_engine {
     CK(cudaEventCreate(&ev1));
   }
 
-  void upload_model() {
-    prog = ppm::build_program(tree, program_R());
+  void upload_model() { upload_model_impl(false); if (!ppm::sweep_is_staged(md)) upload_model_impl(true); }
+
+  void upload_model_impl(bool deep) {
+    prog = ppm::build_program(tree, program_R(), deep);
     // shard: contiguous, equal-sized slices of the deduplicated patterns (work per pattern is uniform)
     long long np = pat.n_patterns;
     first = np * shard_rank / shard_world;
@@ -148,7 +150,7 @@ struct ppm_engine {
 
     md.n_nodes = tree.n_nodes; md.n_leaves = tree.n_leaves; md.n_words = pat.n_words; md.n_slices = tree.n_slices;
     md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entry_ref.size();
-    md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
+    md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.deep = prog.deep ? 1 : 0; md.H = tree.H; md.n_obs = pat.n_obs;
     md.left = d_left.p; md.right = d_right.p; md.parent = d_parent.p; md.bl = d_bl.p; md.height = d_height.p;
     md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
     md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p;

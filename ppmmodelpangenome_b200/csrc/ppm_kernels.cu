@@ -40,6 +40,8 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, size_t bytes)
 }
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+static const size_t kRecRingBytes = 3 * 32 * sizeof(EntryRec);  // per-warp record ring of the global-memory variant
+
 struct StageLayout {
   size_t recs, blk, ops, oprec, yy, wt, leaf, total;
 };
@@ -63,7 +65,7 @@ __host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return al
 // memory; otherwise everything is read from global memory (L1/L2) and the partials live in a global scratch.
 // Every warp sweeps NI batches (NI x 32 patterns) at once -- see sweep_items.
 template <int R, int NI, bool STAGED>
-__global__ void __launch_bounds__(512, 1) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(STAGED ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -71,7 +73,9 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(SweepArgs a) {
   const size_t head = warp_head_bytes(m);
   const size_t slot_bytes = (size_t)m.n_slots * 32 * sizeof(double2);
   const size_t per_item = head + (STAGED ? slot_bytes : 0);
-  unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_item * NI;
+  const size_t per_warp = per_item * NI + (STAGED ? 0 : kRecRingBytes);
+  unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_warp;
+  EntryRec* wrec = STAGED ? nullptr : reinterpret_cast<EntryRec*>(wbase + per_item * NI);
   ItemMem mem[NI];
 #pragma unroll
   for (int q = 0; q < NI; q++) {
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(SweepArgs a) {
     mem[q].sw = reinterpret_cast<uint32_t*>(ib);
     mem[q].zw = mem[q].sw + m.n_words * 32;
     if (STAGED) mem[q].slots = reinterpret_cast<double2*>(ib + head);
-    else mem[q].slots = a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)m.n_slots * 32;
+    else mem[q].slots = a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32;
   }
   const int nbR = m.n_blocks * R;
 
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(SweepArgs a) {
       const long long batch0 = (((long long)chunk * a.items_per_warp + k) * wpc + warp) * NI;
       if (batch0 >= a.n_batches) break;
       double contrib[NI];
-      sweep_items<R, NI>(a, T, p, batch0, lane, mem, contrib);
+      sweep_items<R, NI, !STAGED>(a, T, p, batch0, lane, mem, contrib, wrec);
       if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
@@ -181,9 +185,9 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   const size_t head = warp_head_bytes(m);
   const size_t per_warp_staged = NI * (head + (size_t)m.n_slots * 32 * sizeof(double2));
   int warps = 0;
-  if (L.total + 3 * per_warp_staged <= budget) warps = (int)std::min<size_t>(max_warps(), (budget - L.total) / per_warp_staged);
+  if (L.total + 3 * per_warp_staged <= budget) warps = (int)std::min<size_t>(std::min(max_warps(), 12), (budget - L.total) / per_warp_staged);
   pl.staged = warps >= 3;
-  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / std::max<size_t>(NI * head, 1)));
+  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / (NI * head + kRecRingBytes)));
   long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
   if (groups < warps) warps = (int)std::max<long long>(1, groups);
   pl.warps = warps;
@@ -193,11 +197,12 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   pl.n_chunks = (int)((groups + (long long)warps * pl.items_per_warp - 1) / ((long long)warps * pl.items_per_warp));
   long long units = (long long)pl.n_chunks * P;
   pl.grid_x = (int)std::min<long long>(units, pl.staged ? 2147483647LL : (long long)n_sm);
-  pl.smem_bytes = (pl.staged ? L.total + per_warp_staged * warps : NI * head * warps);
+  pl.smem_bytes = (pl.staged ? L.total + per_warp_staged * warps : (NI * head + kRecRingBytes) * warps);
   return pl;
 }
+bool sweep_is_staged(const ModelDev& m) { return plan_sweep(m, 1 << 20, 1, 148).staged; }
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
-  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * m.n_slots * 32;
+  return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * (m.n_slots + 1) * 32;
 }
 
 template <int R, bool ST>

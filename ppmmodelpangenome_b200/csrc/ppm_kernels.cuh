@@ -24,9 +24,9 @@ struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
-  // [e_leaf0,e_slot0) leaves alive in every slice | [e_slot0,e_pleaf0) internal lineages alive in every slice |
+  // [e_slot0,e_leaf0) internal lineages alive in every slice | [e_leaf0,e_pleaf0) leaves alive in every slice |
   // [e_pleaf0,e_pslot0) leaves merged inside the block | [e_pslot0,e_end) internal lineages born/merged inside it
-  int32_t slice0, nslices, op0, op1, e_leaf0, e_slot0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
+  int32_t slice0, nslices, op0, op1, e_slot0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
 };
 struct __align__(16) EntryRec {
   double K;       // pi1 * exp(-(g2+l2) * (t_block - h_lineage))   (per parameter vector)
@@ -38,6 +38,7 @@ enum { OPREC_DOUBLES = 12 };  // per (parameter vector, node op): kap_l{x,y} kap
 
 struct ModelDev {
   int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
+  int deep;  // program built for the global-memory variant: lineage segments padded to multiples of 4 records
   double H;
   long long n_obs;
   // tree (preorder ids)
@@ -92,6 +93,7 @@ void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_o
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
 struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks; size_t smem_bytes; bool staged; };
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm);
+bool sweep_is_staged(const ModelDev& m);  // depends on the tree/program sizes only
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 elements of global slot scratch (0 if staged)
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s);
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s);

@@ -22,13 +22,16 @@ extern "C" const char* emu_error() { return g_err.c_str(); }
 
 // out_ll[P], out_i2[P], out_parts[P][4]; out_comp [n_patterns][3] / out_cat [n_patterns] for params[0] (may be NULL)
 // i2_override: NULL, or the i2 to use for comp/cat (as assignCat receives MLEi2)
+// R < 0 selects the deep-prefetch code path (global-memory variant) with |R| slices per block
 extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, int R, const double* params, int P,
                         double* out_ll, double* out_i2, double* out_parts, double* out_comp, signed char* out_cat,
                         long long* out_npat) {
   try {
     Tree tree = read_tree_file(tree_path);
     Patterns pat = read_matrix_file(tree, pa_path, dedupe != 0);
-    Program prog = build_program(tree, R);
+    const bool deep = R < 0;
+    if (deep) R = -R;
+    Program prog = build_program(tree, R, deep);
     const long long count = pat.n_patterns;
     if (out_npat) *out_npat = count;
     std::vector<uint32_t> wm((size_t)pat.n_words * count);
@@ -70,9 +73,9 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     // two items per "warp" as on the device (NI = 2), one lane each
     const int NI = 2;
     std::vector<uint32_t> sw(NI * pat.n_words), zw(NI * prog.n_slots);
-    std::vector<double2> slotmem(NI * prog.n_slots);
+    std::vector<double2> slotmem(NI * (prog.n_slots + 1));
     ItemMem mem[2];
-    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].zw = zw.data() + q * prog.n_slots; mem[q].slots = slotmem.data() + q * prog.n_slots; }
+    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].zw = zw.data() + q * prog.n_slots; mem[q].slots = slotmem.data() + q * (prog.n_slots + 1); }
     auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
       SweepArgs a{};
       a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
@@ -86,10 +89,12 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
           T.leaftab = reinterpret_cast<const double2*>(scal.data() + (size_t)p * SC_COUNT + SC_LA0);
           double c[2] = {0., 0.};
-          if (prog.R == 8) sweep_items<8, 2>(a, T, p, bt, 0, mem, c);
-          else if (prog.R == 4) sweep_items<4, 2>(a, T, p, bt, 0, mem, c);
-          else if (prog.R == 12) sweep_items<12, 2>(a, T, p, bt, 0, mem, c);
-          else if (prog.R == 16) sweep_items<16, 2>(a, T, p, bt, 0, mem, c);
+          if (deep && prog.R == 8) sweep_items<8, 2, true>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (deep) throw std::runtime_error("deep emulation built for R = 8");
+          else if (prog.R == 8) sweep_items<8, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 4) sweep_items<4, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 12) sweep_items<12, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 16) sweep_items<16, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
           else throw std::runtime_error("emulator built for R in {4,8,12,16}");
           s += c[0]; s += c[1];
         }
