@@ -125,6 +125,11 @@ int ppm_assign_cat(ppm_handle h, const double* params8, double i2, int8_t* out_c
  * out[3*r+0] = lik0r, out[3*r+1] = logSumExp(lik1r, lik1), out[3*r+2] = lik2 (functions.cpp:348-356, :497-505). */
 int ppm_components(ppm_handle h, const double* params8, double i2, double* out /*[shard_count*3]*/);
 
+/* Replaces the per-pattern body of Inference::computeProbaCat (functions.cpp:556-581): the log posterior
+ * probabilities of the three categories, out[3*g+k] = lik_k - logSumExp(lik_0, lik_1, lik_2), one row per GENE of
+ * the input in input order (shard_world must be 1).  The reference writes them as "p0 p1 p2\n" per row. */
+int ppm_proba_cat(ppm_handle h, const double* params8, double i2, double* out /*[n_genes*3]*/);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------- */
 
 /* Counters of the last ppm_loglik*(): [0] kernels launched, [1] device ms of the main kernel (CUDA events

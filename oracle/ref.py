@@ -37,6 +37,8 @@ def lib():
         L.ref_components.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_assign_cat.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_char_p]
         L.ref_assign_cat.restype = C.c_int
+        L.ref_proba_cat.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_char_p]
+        L.ref_proba_cat.restype = C.c_int
         L.ref_set_threads.argtypes = [C.c_int]
         L.ref_max_threads.restype = C.c_int
         _lib = L
@@ -114,6 +116,19 @@ class Reference:
         n = lib().ref_assign_cat(self.h, p.ctypes.data, float(i2), out.ctypes.data, tmp.encode())
         assert n == self.nRep
         return out
+
+
+def _proba_cat(self, params, i2):
+    p = np.ascontiguousarray(params, np.float64)
+    out = np.zeros((self.nRep, 3), np.float64)
+    fd, tmp = tempfile.mkstemp(prefix="ppm_pc_")
+    os.close(fd)
+    n = lib().ref_proba_cat(self.h, p.ctypes.data, float(i2), out.ctypes.data, tmp.encode())
+    assert n == self.nRep
+    return out
+
+
+Reference.proba_cat = _proba_cat
 
 
 def set_threads(n):

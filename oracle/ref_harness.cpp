@@ -152,4 +152,17 @@ int ref_assign_cat(void* hv, const double* p, double i2, int* out, const char* t
   return n;
 }
 
+// computeProbaCat (functions.cpp:556-581) with a fresh memo, parsed back from the file the reference writes
+int ref_proba_cat(void* hv, const double* p, double i2, double* out /*[nRep*3]*/, const char* tmpfile) {
+  Inference* inf = ((RefHandle*)hv)->inf;
+  inf->tLik.clearLikValues();
+  inf->computeI2(p[0], p[1], p[2], p[3], p[4], p[5], svec(p));
+  inf->computeProbaCat(std::string(tmpfile), p[0], p[1], p[2], p[3], i2, p[4], p[5], p[7], p[6]);
+  std::ifstream f(tmpfile);
+  int n = 0; std::string tok;
+  while (f >> tok) out[n++] = std::stod(tok) ;
+  std::remove(tmpfile);
+  return n / 3;
+}
+
 }  // extern "C"

@@ -8,11 +8,11 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libppm_b200.so")
+LIB = os.path.join(HERE, os.environ.get("PPM_LIB_NAME", "libppm_b200.so"))
 CLI = os.path.join(HERE, "inference")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("PPM_EXTRA_NVCC_FLAGS", "").split()
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
 
 

@@ -435,6 +435,21 @@ int ppm_components(ppm_handle h, const double* params8, double i2, double* out) 
   return eval_one(h, params8, i2, nullptr, out);
 }
 
+int ppm_proba_cat(ppm_handle h, const double* params8, double i2, double* out) {
+  if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  if (h->shard_world != 1) { h->err = "ppm_proba_cat needs an unsharded handle"; return PPM_ESTATE; }
+  std::vector<double> comp((size_t)std::max<long long>(h->count, 1) * 3);
+  int rc = eval_one(h, params8, i2, nullptr, comp.data());
+  if (rc) return rc;
+  for (int64_t g = 0; g < h->pat.n_genes; g++) {
+    const double* c = &comp[(size_t)h->pat.gene_to_pattern[g] * 3];
+    double mx = std::max(c[0], std::max(c[1], c[2]));
+    double den = mx + std::log(std::exp(c[0] - mx) + std::exp(c[1] - mx) + std::exp(c[2] - mx));
+    for (int k = 0; k < 3; k++) out[3 * g + k] = c[k] - den;
+  }
+  return PPM_OK;
+}
+
 int ppm_get_counters(ppm_handle h, double* out4) {
   if (!h || !out4) return PPM_EINVAL;
   try {

@@ -32,7 +32,7 @@ class Info(C.Structure):
 
 SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_destroy", "ppm_last_error", "ppm_get_info",
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
-           "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_get_counters",
+           "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_get_counters",
            "ppm_measure_fp64_peak"]
 
 
@@ -64,6 +64,7 @@ def lib():
         L.ppm_compute_i2.argtypes = [vp, vp, i32, vp, vp]
         L.ppm_assign_cat.argtypes = [vp, vp, dbl, vp]
         L.ppm_components.argtypes = [vp, vp, dbl, vp]
+        L.ppm_proba_cat.argtypes = [vp, vp, dbl, vp]
         L.ppm_get_counters.argtypes = [vp, vp]
         L.ppm_measure_fp64_peak.argtypes = [C.c_int, vp]
         _LIB = L
@@ -207,6 +208,15 @@ class Inference:
         out = np.zeros((max(n, 1), 3))
         self._ck(lib().ppm_components(self._h, p.ctypes.data, float(i2), out.ctypes.data))
         return out[:n]
+
+    def computeProbaCat(self, params8, i2=None):
+        """Log posterior category probabilities per input gene (functions.cpp:556-581), shape [nGenes, 3]."""
+        p = _params(params8)
+        if i2 is None:
+            i2 = self.computeI2(p[0])
+        out = np.zeros((max(self.nGenes, 1), 3))
+        self._ck(lib().ppm_proba_cat(self._h, p.ctypes.data, float(i2), out.ctypes.data))
+        return out[:self.nGenes]
 
     # device-pointer entry points (bench / multi-GPU plumbing)
     def loglik_device(self, d_params_ptr, P, d_out_ptr, d_i2_ptr, stream_ptr=None):

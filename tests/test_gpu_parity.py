@@ -161,3 +161,22 @@ def test_penalty_and_errors(ppm, golden, tmp_path):
     bad.write_text("((a:1,b:1,c:1):1,d:2);\n")
     with pytest.raises(ppm.PPMError):
         ppm.Inference(str(bad), g.pa)
+
+
+def test_posterior_category_probabilities(ppm, golden):
+    """ppm_proba_cat == computeProbaCat (functions.cpp:556-581): normalised log posteriors per input gene."""
+    from oracle import cport, model
+    for name, dedupe in (("ref_test", True), ("syn100", False)):
+        g = golden(name)
+        k = 2 if name == "ref_test" else 0
+        p, i2 = g.params[k], g.results[k]["i2"]
+        inf = _engine(ppm, g, dedupe)
+        got = inf.computeProbaCat(p, i2)
+        c = cport.Oracle(model.model_from_files(g.tree, g.pa)).eval(p, components=True)["comp"]
+        c3 = np.stack([c[:, 0], np.logaddexp(c[:, 1], c[:, 2]), c[:, 3]], axis=1)
+        lp = c3 - np.logaddexp(np.logaddexp(c3[:, 0], c3[:, 1]), c3[:, 2])[:, None]
+        fin = np.isfinite(c3).all(axis=1)
+        assert got.shape == lp.shape
+        assert np.allclose(got[fin], lp[fin], rtol=1e-9, atol=1e-9)
+        assert np.allclose(np.exp(got).sum(axis=1), 1.0, atol=1e-12)
+        inf.close()

@@ -82,3 +82,18 @@ def test_oracle_against_live_reference_on_seeded_inputs(tmp_path):
             assert rel(orc.loglik(p), R.loglik(p)) <= 1e-13
             assert rel(orc.eval(p)["i2"], R.compute_i2(p)) <= 1e-13
         R.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref (the compiled reference) is not present")
+def test_posterior_category_probabilities_match_reference_file(golden):
+    """computeProbaCat (functions.cpp:556-581) writes log posteriors at 6 significant digits."""
+    g = golden("ref_test")
+    p = g.params[2]
+    R = ref.Reference(g.tree, g.pa)
+    i2 = R.compute_i2(p)
+    pc = R.proba_cat(p, i2)
+    c = cport.Oracle(model.model_from_files(g.tree, g.pa)).eval(p, components=True)["comp"]
+    c3 = np.stack([c[:, 0], np.logaddexp(c[:, 1], c[:, 2]), c[:, 3]], axis=1)
+    lp = c3 - np.logaddexp(np.logaddexp(c3[:, 0], c3[:, 1]), c3[:, 2])[:, None]
+    assert np.allclose(pc, lp, rtol=2e-5, atol=1e-12)
+    R.close()
