@@ -233,10 +233,60 @@ PPM_HD void prepass_i2_body(const ModelDev& m, const TablesDev& t, const double*
 // ------------------------------------------------------------------------------------------------ sweep
 // Per work item (32 patterns): its pattern words [n_words][lanes], the all-zero-subtree masks per slot, and the
 // Mobile partials (a,d) of the alive internal lineages [slot][lanes] (shared memory in the staged variant).
+// Lineage partials live either in ordinary memory (shared in the classic staged variant, global in the deep
+// variant, host memory in the emulator) ...
+struct SlotsMem {
+  double2* base;  // [slot][lanes]
+  PPM_HD double2 ld(int slot, int lane) const { return base[slot * PPM_LANES + lane]; }
+  PPM_HD void st(int slot, int lane, double2 v) const { base[slot * PPM_LANES + lane] = v; }
+  PPM_HD void ld_async(int slot, int lane, double2& dst) const { dst = base[slot * PPM_LANES + lane]; }
+  PPM_HD void wait_async(double2&) const {}
+};
+#if defined(__CUDACC__)
+// ... or in Blackwell tensor memory: TMEM is 128 lanes x 512 columns x 32 bit per SM and a warp reaches the 32 lanes of
+// its quarter (warp % 4), i.e. it is per-lane private scratch -- exactly the shape of slots[slot][lane].  A slot is 4
+// columns (16 bytes per lane), moved with tcgen05.st / tcgen05.ld .32x32b.x4 (SASS STTM / LDTM).  The first `nt` slots of
+// a warp live in its column range, the rest (if any) in a shared-memory overflow.  This frees ~17 KB of shared memory
+// per warp, which is what bounds the resident warps of the classic variant.
+struct SlotsTmem {
+  uint32_t taddr;  // lane base << 16 | first column of this warp
+  int nt;          // slots held in TMEM
+  double2* ovf;    // [slot - nt][32]
+  __device__ __forceinline__ void ld_async(int slot, int lane, double2& dst) const {
+    if (slot < nt) {
+      uint32_t r0, r1, r2, r3;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr + 4u * (uint32_t)slot));
+      dst.x = __hiloint2double((int)r1, (int)r0);
+      dst.y = __hiloint2double((int)r3, (int)r2);
+    } else dst = ovf[(slot - nt) * 32 + lane];
+  }
+  // the loaded registers may only be consumed after the wait: tie them to it
+  __device__ __forceinline__ void wait_async(double2& v) const {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+d"(v.x), "+d"(v.y));
+  }
+  __device__ __forceinline__ double2 ld(int slot, int lane) const {
+    double2 v;
+    ld_async(slot, lane, v);
+    wait_async(v);
+    return v;
+  }
+  __device__ __forceinline__ void st(int slot, int lane, double2 v) const {
+    if (slot < nt) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                   :: "r"(taddr + 4u * (uint32_t)slot), "r"((uint32_t)__double2loint(v.x)), "r"((uint32_t)__double2hiint(v.x)),
+                      "r"((uint32_t)__double2loint(v.y)), "r"((uint32_t)__double2hiint(v.y)));
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    } else ovf[(slot - nt) * 32 + lane] = v;
+  }
+};
+#endif
+
+template <class Slots>
 struct ItemMem {
   uint32_t* sw;
   uint32_t* zw;
-  double2* slots;
+  Slots slots;
 };
 
 // Where one work item reads its topology program and per-parameter tables from (shared memory copies in the
@@ -336,9 +386,9 @@ PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) 
 // DEEP (the variant whose tables and lineage slots live in global memory): the records of the fully-alive entries
 // are streamed through a per-warp shared-memory ring (wrec, 3 chunks of 32 records, cp.async two chunks ahead) and
 // lineage partials are fetched four entries ahead, so L2/HBM latency is covered by ~140 cycles of FP64 work each.
-template <int R, int NI, bool DEEP>
+template <int R, int NI, bool DEEP, class Slots>
 PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long long batch0, int lane,
-                        const ItemMem (&mem)[NI], double (&contrib)[NI], EntryRec* wrec) {
+                        const ItemMem<Slots> (&mem)[NI], double (&contrib)[NI], EntryRec* wrec) {
   const ModelDev& m = a.m;
   const double* sc = a.t.scal + (size_t)p * SC_COUNT;
   const bool skip = (a.mode == 0) && !a.force && (sc[SC_I2] < 0.);  // penalty branch: no pattern work (functions.cpp:362-364)
@@ -362,7 +412,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
   if (DEEP) {
 #pragma unroll
-    for (int q = 0; q < NI; q++) mem[q].slots[m.n_slots * PPM_LANES + lane] = make_double2(1., 0.);
+    for (int q = 0; q < NI; q++) mem[q].slots.st(m.n_slots, lane, make_double2(1., 0.));
   }
 
   double A0[NI], A1[NI];    // log p1(root) of the two pure-loss categories
@@ -399,8 +449,16 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       for (int q = 0; q < NI; q++) {
         const uint32_t bl = (mem[q].sw[(lpos >> 5) * PPM_LANES + lane] >> (lpos & 31)) & 1u;
         const uint32_t br = (mem[q].sw[(rpos >> 5) * PPM_LANES + lane] >> (rpos & 31)) & 1u;
-        L[q] = *(lleaf ? T.leaftab + bl : mem[q].slots + lslot * PPM_LANES + lane);
-        Rr[q] = *(rleaf ? T.leaftab + br : mem[q].slots + rslot * PPM_LANES + lane);
+        {  // leaf children come from the two-entry leaf table, internal ones from their slot (both fetched, one kept)
+          double2 ls, rs;
+          mem[q].slots.ld_async(lslot, lane, ls);
+          mem[q].slots.ld_async(rslot, lane, rs);
+          const double2 lt = T.leaftab[bl], rt = T.leaftab[br];
+          mem[q].slots.wait_async(ls);
+          mem[q].slots.wait_async(rs);
+          L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
+          Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
+        }
         const uint32_t zbl = ~ppm_ballot(bl != 0u), zbr = ~ppm_ballot(br != 0u);
         zwl[q] = lleaf ? zbl : mem[q].zw[lslot];
         zwr[q] = rleaf ? zbr : mem[q].zw[rslot];
@@ -436,7 +494,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
             }
           }
           // every lane reads back only what it wrote itself (its slot column; zw gets the same word from all lanes)
-          mem[q].slots[op.dst * PPM_LANES + lane] = make_double2(av, d);
+          mem[q].slots.st(op.dst, lane, make_double2(av, d));
           mem[q].zw[op.dst] = zwv;
         }
       }
@@ -462,7 +520,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         for (int u = 0; u < 4; u++) {
           const int sl = T.recs[E0 + u].ref & 0xffff;
 #pragma unroll
-          for (int q = 0; q < NI; q++) ring[q][u] = mem[q].slots[sl * PPM_LANES + lane];
+          for (int q = 0; q < NI; q++) ring[q][u] = mem[q].slots.ld(sl, lane);
         }
       }
       for (int c = 0; c < nch; c++) {
@@ -493,7 +551,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
             for (int q = 0; q < NI; q++) {
               const double2 ad = ring[q][u];
-              ring[q][u] = mem[q].slots[sl * PPM_LANES + lane];
+              ring[q][u] = mem[q].slots.ld(sl, lane);
               const double nbb = ad.y * nK;
 #pragma unroll
               for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], ad.x);
@@ -541,12 +599,12 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       load_rec(T.recs, e, K, ref, mk);
       double2 ad[NI];
 #pragma unroll
-      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots[(int)(ref & 0xffffu) * PPM_LANES + lane];
+      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots.ld((int)(ref & 0xffffu), lane);
 #pragma unroll 2
       for (; e < ce; e++) {
         double2 an[NI];
 #pragma unroll
-        for (int q = 0; q < NI; q++) an[q] = mem[q].slots[(int)(ref >> 16) * PPM_LANES + lane];
+        for (int q = 0; q < NI; q++) mem[q].slots.ld_async((int)(ref >> 16), lane, an[q]);
         const double nK = -K;
         load_rec(T.recs, e + 1, K, ref, mk);
 #pragma unroll
@@ -554,8 +612,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           const double nbb = ad[q].y * nK;
 #pragma unroll
           for (int i = 0; i < R; i++) prod[q][i] *= fma(nbb, Y[i], ad[q].x);
-          ad[q] = an[q];
         }
+#pragma unroll
+        for (int q = 0; q < NI; q++) { mem[q].slots.wait_async(an[q]); ad[q] = an[q]; }
       }
 #pragma unroll
       for (int q = 0; q < NI; q++)
@@ -621,13 +680,13 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       load_rec(T.recs, bd.e_pslot0, K, ref, mk);
       double2 ad[NI];
 #pragma unroll
-      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots[(int)(ref & 0xffffu) * PPM_LANES + lane];
+      for (int q = 0; q < NI; q++) ad[q] = mem[q].slots.ld((int)(ref & 0xffffu), lane);
       for (int e = bd.e_pslot0; e < bd.e_end; e++) {
         double2 an[NI];
         double aa[NI], nbb[NI];
 #pragma unroll
         for (int q = 0; q < NI; q++) {
-          an[q] = mem[q].slots[(int)(ref >> 16) * PPM_LANES + lane];
+          mem[q].slots.ld_async((int)(ref >> 16), lane, an[q]);
           aa[q] = ad[q].x;
           nbb[q] = ad[q].y * -K;
         }
@@ -635,7 +694,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         load_rec(T.recs, e + 1, K, ref, mk);
         coded_update<R, NI>(prod, Y, aa, nbb, mcur);
 #pragma unroll
-        for (int q = 0; q < NI; q++) ad[q] = an[q];
+        for (int q = 0; q < NI; q++) { mem[q].slots.wait_async(an[q]); ad[q] = an[q]; }
       }
     }
     // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned

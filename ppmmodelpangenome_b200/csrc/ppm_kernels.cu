@@ -60,30 +60,65 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
 }
 __host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16(((size_t)m.n_words * 32 + m.n_slots) * 4); }
 
-// CTA work unit = (parameter vector p, chunk of warps*items_per_warp*NI pattern batches).  STAGED: the topology
-// program and p's tables are copied to shared memory once per unit and per-lineage partials live in shared
-// memory; otherwise everything is read from global memory (L1/L2) and the partials live in a global scratch.
+template <int MODE>
+__device__ __forceinline__ void init_slots(SlotsMem& s, double2* smem_slots, double2* global_slots, uint32_t, int, int, int, int) {
+  s.base = (MODE == 2) ? global_slots : smem_slots;
+}
+template <int MODE>
+__device__ __forceinline__ void init_slots(SlotsTmem& s, double2* smem_slots, double2*, uint32_t tmem_base, int warp, int wpc, int q, int nt) {
+  const int cols_per_warp = (512 / ((wpc + 3) >> 2)) & ~3;
+  s.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * cols_per_warp + q * nt * 4);
+  s.nt = nt;
+  s.ovf = smem_slots;
+}
+
+// CTA work unit = (parameter vector p, chunk of warps*items_per_warp*NI pattern batches).
+// MODE 0: tables + program staged in shared memory, lineage partials in shared memory (<= 12 warps).
+// MODE 1: tables + program staged in shared memory, lineage partials in TENSOR MEMORY (tcgen05.ld/st; 16 warps):
+//         TMEM is idle in this FP64 kernel and is per-lane private like the slots, so moving them there frees the
+//         ~17 KB of shared memory per warp that bounds the resident warps of MODE 0.
+// MODE 2: everything read from global memory (L1/L2), partials in a global scratch, deep prefetch (big trees).
 // Every warp sweeps NI batches (NI x 32 patterns) at once -- see sweep_items.
-template <int R, int NI, bool STAGED>
-__global__ void __launch_bounds__(STAGED ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
+template <int MODE> struct SlotsOf { typedef SlotsMem type; };
+template <> struct SlotsOf<1> { typedef SlotsTmem type; };
+
+template <int R, int NI, int MODE>
+__global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t tmem_base_s;
+  typedef typename SlotsOf<MODE>::type Slots;
+  constexpr bool STAGED = MODE != 2;
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const StageLayout L = stage_layout(m);
   const size_t head = warp_head_bytes(m);
-  const size_t slot_bytes = (size_t)m.n_slots * 32 * sizeof(double2);
-  const size_t per_item = head + (STAGED ? slot_bytes : 0);
+  // lineage slots per item: MODE 0 all in shared memory; MODE 1 the first nt in TMEM, the rest in shared memory
+  int nt = 0;
+  if (MODE == 1) {
+    const int cols_per_warp = (512 / ((wpc + 3) >> 2)) & ~3;
+    nt = cols_per_warp / 4 / NI;
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
+  const int smem_slots = MODE == 0 ? m.n_slots : (MODE == 1 ? (m.n_slots > nt ? m.n_slots - nt : 0) : 0);
+  const size_t per_item = head + (size_t)smem_slots * 32 * sizeof(double2);
   const size_t per_warp = per_item * NI + (STAGED ? 0 : kRecRingBytes);
   unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_warp;
   EntryRec* wrec = STAGED ? nullptr : reinterpret_cast<EntryRec*>(wbase + per_item * NI);
-  ItemMem mem[NI];
+  ItemMem<Slots> mem[NI];
 #pragma unroll
   for (int q = 0; q < NI; q++) {
     unsigned char* ib = wbase + (size_t)q * per_item;
     mem[q].sw = reinterpret_cast<uint32_t*>(ib);
     mem[q].zw = mem[q].sw + m.n_words * 32;
-    if (STAGED) mem[q].slots = reinterpret_cast<double2*>(ib + head);
-    else mem[q].slots = a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32;
+    init_slots<MODE>(mem[q].slots, reinterpret_cast<double2*>(ib + head),
+                     a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32,
+                     tmem_base_s, warp, wpc, q, nt);
   }
   const int nbR = m.n_blocks * R;
 
@@ -121,7 +156,7 @@ __global__ void __launch_bounds__(STAGED ? 384 : 512, 1) sweep_kernel(SweepArgs 
       const long long batch0 = (((long long)chunk * a.items_per_warp + k) * wpc + warp) * NI;
       if (batch0 >= a.n_batches) break;
       double contrib[NI];
-      sweep_items<R, NI, !STAGED>(a, T, p, batch0, lane, mem, contrib, wrec);
+      sweep_items<R, NI, MODE == 2, Slots>(a, T, p, batch0, lane, mem, contrib, wrec);
       if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
@@ -133,6 +168,11 @@ __global__ void __launch_bounds__(STAGED ? 384 : 512, 1) sweep_kernel(SweepArgs 
       }
       __syncwarp();
     }
+  }
+  if (MODE == 1) {
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(512));
   }
 }
 
@@ -177,19 +217,40 @@ static int max_warps() {  // tuning knob: PPM_MAX_WARPS caps the warps per CTA (
   return w < 1 ? 1 : (w > 16 ? 16 : w);
 }
 
+static bool tmem_enabled() { const char* e = std::getenv("PPM_NO_TMEM"); return !(e && std::atoi(e) != 0); }
+
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   SweepPlan pl{};
   const int NI = kItemsPerWarp;
   const size_t budget = 227 * 1024 - 1024;
   const StageLayout L = stage_layout(m);
   const size_t head = warp_head_bytes(m);
-  const size_t per_warp_staged = NI * (head + (size_t)m.n_slots * 32 * sizeof(double2));
+  const size_t slot_row = 32 * sizeof(double2);
   int warps = 0;
-  if (L.total + 3 * per_warp_staged <= budget) warps = (int)std::min<size_t>(std::min(max_warps(), 12), (budget - L.total) / per_warp_staged);
-  pl.staged = warps >= 3;
-  if (!pl.staged) warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / (NI * head + kRecRingBytes)));
+  pl.mode = 2;
+  // MODE 1: lineage slots in tensor memory (first nt per warp) + shared-memory overflow; most warps that fit
+  if (tmem_enabled()) {
+    for (int w = std::min(max_warps(), 16); w >= 8 && !warps; w -= 4) {
+      const int nt = ((512 / ((w + 3) / 4)) & ~3) / 4 / NI;
+      const size_t ovf = m.n_slots > nt ? (size_t)(m.n_slots - nt) : 0;
+      if (L.total + (size_t)w * NI * (head + ovf * slot_row) <= budget) { warps = w; pl.mode = 1; pl.per_warp_bytes = NI * (head + ovf * slot_row); }
+    }
+  }
+  // MODE 0: lineage slots in shared memory
+  if (!warps) {
+    const size_t per_warp_staged = NI * (head + (size_t)m.n_slots * slot_row);
+    if (L.total + 3 * per_warp_staged <= budget) {
+      warps = (int)std::min<size_t>(std::min(max_warps(), 12), (budget - L.total) / per_warp_staged);
+      pl.mode = 0; pl.per_warp_bytes = per_warp_staged;
+    }
+  }
+  pl.staged = pl.mode != 2;
+  if (!pl.staged) {
+    pl.per_warp_bytes = NI * head + kRecRingBytes;
+    warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / pl.per_warp_bytes));
+  }
   long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
-  if (groups < warps) warps = (int)std::max<long long>(1, groups);
+  if (pl.mode != 1 && groups < warps) warps = (int)std::max<long long>(1, groups);  // (MODE 1 keeps its TMEM column split)
   pl.warps = warps;
   long long total = groups * (long long)P;
   long long ipw = total / ((long long)n_sm * warps * 4);
@@ -197,7 +258,7 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   pl.n_chunks = (int)((groups + (long long)warps * pl.items_per_warp - 1) / ((long long)warps * pl.items_per_warp));
   long long units = (long long)pl.n_chunks * P;
   pl.grid_x = (int)std::min<long long>(units, pl.staged ? 2147483647LL : (long long)n_sm);
-  pl.smem_bytes = (pl.staged ? L.total + per_warp_staged * warps : (NI * head + kRecRingBytes) * warps);
+  pl.smem_bytes = (pl.staged ? L.total : 0) + pl.per_warp_bytes * warps;
   return pl;
 }
 bool sweep_is_staged(const ModelDev& m) { return plan_sweep(m, 1 << 20, 1, 148).staged; }
@@ -205,28 +266,28 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
   return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * (m.n_slots + 1) * 32;
 }
 
-template <int R, bool ST>
+template <int R, int MODE>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  sweep_kernel<R, kItemsPerWarp, ST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+  sweep_kernel<R, kItemsPerWarp, MODE><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+}
+
+template <int R>
+static void launch_sweep_r(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
+  if (pl.mode == 1) launch_sweep_t<R, 1>(a, pl, s);
+  else if (pl.mode == 0) launch_sweep_t<R, 0>(a, pl, s);
+  else launch_sweep_t<R, 2>(a, pl, s);
 }
 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
   a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp;
-  if (a.m.R == 16) {
-    if (pl.staged) launch_sweep_t<16, true>(a, pl, s);
-    else launch_sweep_t<16, false>(a, pl, s);
-  } else if (a.m.R == 12) {
-    if (pl.staged) launch_sweep_t<12, true>(a, pl, s);
-    else launch_sweep_t<12, false>(a, pl, s);
-  } else {
-    if (pl.staged) launch_sweep_t<8, true>(a, pl, s);
-    else launch_sweep_t<8, false>(a, pl, s);
-  }
+  if (a.m.R == 16) launch_sweep_r<16>(a, pl, s);
+  else if (a.m.R == 12) launch_sweep_r<12>(a, pl, s);
+  else launch_sweep_r<8>(a, pl, s);
 }
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s) {
   reduce_kernel<<<P, 256, 0, s>>>(partial, nx, out);

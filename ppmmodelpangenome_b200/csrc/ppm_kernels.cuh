@@ -91,7 +91,7 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
-struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks; size_t smem_bytes; bool staged; };
+struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks, mode; size_t smem_bytes, per_warp_bytes; bool staged; };
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm);
 bool sweep_is_staged(const ModelDev& m);  // depends on the tree/program sizes only
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 elements of global slot scratch (0 if staged)

@@ -74,8 +74,8 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     const int NI = 2;
     std::vector<uint32_t> sw(NI * pat.n_words), zw(NI * prog.n_slots);
     std::vector<double2> slotmem(NI * (prog.n_slots + 1));
-    ItemMem mem[2];
-    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].zw = zw.data() + q * prog.n_slots; mem[q].slots = slotmem.data() + q * (prog.n_slots + 1); }
+    ItemMem<SlotsMem> mem[2];
+    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].zw = zw.data() + q * prog.n_slots; mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
     auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
       SweepArgs a{};
       a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
@@ -89,12 +89,12 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
           T.leaftab = reinterpret_cast<const double2*>(scal.data() + (size_t)p * SC_COUNT + SC_LA0);
           double c[2] = {0., 0.};
-          if (deep && prog.R == 8) sweep_items<8, 2, true>(a, T, p, bt, 0, mem, c, nullptr);
+          if (deep && prog.R == 8) sweep_items<8, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (deep) throw std::runtime_error("deep emulation built for R = 8");
-          else if (prog.R == 8) sweep_items<8, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
-          else if (prog.R == 4) sweep_items<4, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
-          else if (prog.R == 12) sweep_items<12, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
-          else if (prog.R == 16) sweep_items<16, 2, false>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 8) sweep_items<8, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 4) sweep_items<4, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 12) sweep_items<12, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (prog.R == 16) sweep_items<16, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else throw std::runtime_error("emulator built for R in {4,8,12,16}");
           s += c[0]; s += c[1];
         }
