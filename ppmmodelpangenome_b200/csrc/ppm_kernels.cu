@@ -270,7 +270,7 @@ template <int R, int MODE>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
     configured = true;
   }
   sweep_kernel<R, kItemsPerWarp, MODE><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
