@@ -211,7 +211,53 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     r[0] = kl.x; r[1] = kl.y; r[2] = kr.x; r[3] = kr.y;
     r[4] = cl.x; r[5] = cl.y; r[6] = cl.z; r[7] = cl.w;
     r[8] = cr.x; r[9] = cr.y; r[10] = cr.z; r[11] = cr.w;
+  } else if (i <= m.n_entries + n_pad + m.n_ops + m.n_nodes) {
+    // pure-loss branch factors transposed for the class-sum kernel (lanes = parameter vectors):
+    // clsT[(v*2 + 0)*P + p] = {S0, S1} (active branch), clsT[(v*2 + 1)*P + p] = {T0, T1} (frontier branch)
+    int v = i - m.n_entries - n_pad - m.n_ops - 1;
+    const double4 c = t.cls[(size_t)p * m.n_nodes + v];
+    t.clsT[((size_t)v * 2 + 0) * t.P + p] = make_double2(c.x, c.z);
+    t.clsT[((size_t)v * 2 + 1) * t.P + p] = make_double2(c.y, c.w);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ class sums
+// log p1(root) of the two pure-loss categories (Persistent l0, Private l1) for one pattern and one parameter
+// vector: sum over branches of S (a present leaf below), T (all-zero subtree under an active parent) or nothing
+// (all-zero subtree under an all-zero parent) -- objects.cpp:404-426 collapsed, see DESIGN.md.  The class of a
+// branch depends on the pattern only, the value on the parameter vector only: with one PATTERN per warp and the
+// lanes over parameter vectors the class tests are warp-uniform and the loads coalesced.
+// zbits: per-warp scratch, one bit per node ("subtree all zero"); pw: the pattern's words.
+PPM_HD double2 class_sums_body(const ModelDev& m, const TablesDev& t, const uint32_t* pw, int pw_stride, int p, uint32_t* zbits) {
+  double a0 = 0., a1 = 0.;
+  const bool lane_ok = p < t.P;
+  const int pp = lane_ok ? p : 0;
+  for (int o = 0; o < m.n_ops; o++) {
+    const NodeOpDev op = m.ops[o];
+    bool zl, zr;
+    if (op.lref < 0) { int pos = -(op.lref + 1); zl = !((pw[(size_t)(pos >> 5) * pw_stride] >> (pos & 31)) & 1u); }
+    else zl = (zbits[op.lnode >> 5] >> (op.lnode & 31)) & 1u;
+    if (op.rref < 0) { int pos = -(op.rref + 1); zr = !((pw[(size_t)(pos >> 5) * pw_stride] >> (pos & 31)) & 1u); }
+    else zr = (zbits[op.rnode >> 5] >> (op.rnode & 31)) & 1u;
+    const bool zv = zl && zr;
+    // every lane updates its own copy of the (identical) bit array in the host build; on the device the array is per warp
+    const uint32_t bit = 1u << (op.node & 31);
+    uint32_t w = zbits[op.node >> 5];
+    w = zv ? (w | bit) : (w & ~bit);
+    ppm_syncwarp();
+    zbits[op.node >> 5] = w;
+    ppm_syncwarp();
+    const bool par_zero = zv && op.node != 0;  // the root always counts as active
+    if (!(zl && par_zero)) {
+      const double2 c = t.clsT[((size_t)op.lnode * 2 + (zl ? 1 : 0)) * t.P + pp];
+      a0 += c.x; a1 += c.y;
+    }
+    if (!(zr && par_zero)) {
+      const double2 c = t.clsT[((size_t)op.rnode * 2 + (zr ? 1 : 0)) * t.P + pp];
+      a0 += c.x; a1 += c.y;
+    }
+  }
+  return make_double2(a0, a1);
 }
 
 // i2 and the three log prefactors (functions.cpp:342-343, 348, 354, 356)
@@ -415,13 +461,12 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     for (int q = 0; q < NI; q++) mem[q].slots.st(m.n_slots, lane, make_double2(1., 0.));
   }
 
-  double A0[NI], A1[NI];    // log p1(root) of the two pure-loss categories
   int X[NI];                // sum of renormalisation shifts of all lineages formed so far
   double Im[NI]; int Ie[NI];  // Mobile integral = Im * 2^-Ie (exponent of an empty sum: +inf)
   double prod[NI][R], Y[R];
   int ex[NI][R];
 #pragma unroll
-  for (int q = 0; q < NI; q++) { A0[q] = 0.; A1[q] = 0.; X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
+  for (int q = 0; q < NI; q++) { X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
 
   for (int b = 0; b <= m.n_blocks; b++) {
     const BlockDesc bd = T.blk[b];
@@ -444,37 +489,22 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       const int lpos = lleaf ? -(op.lref + 1) : 0, rpos = rleaf ? -(op.rref + 1) : 0;
       const int lslot = lleaf ? 0 : op.lref, rslot = rleaf ? 0 : op.rref;
       double2 L[NI], Rr[NI];
-      uint32_t zwl[NI], zwr[NI];
 #pragma unroll
       for (int q = 0; q < NI; q++) {
         const uint32_t bl = (mem[q].sw[(lpos >> 5) * PPM_LANES + lane] >> (lpos & 31)) & 1u;
         const uint32_t br = (mem[q].sw[(rpos >> 5) * PPM_LANES + lane] >> (rpos & 31)) & 1u;
-        {  // leaf children come from the two-entry leaf table, internal ones from their slot (both fetched, one kept)
-          double2 ls, rs;
-          mem[q].slots.ld_async(lslot, lane, ls);
-          mem[q].slots.ld_async(rslot, lane, rs);
-          const double2 lt = T.leaftab[bl], rt = T.leaftab[br];
-          mem[q].slots.wait_async(ls);
-          mem[q].slots.wait_async(rs);
-          L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
-          Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
-        }
-        const uint32_t zbl = ~ppm_ballot(bl != 0u), zbr = ~ppm_ballot(br != 0u);
-        zwl[q] = lleaf ? zbl : mem[q].zw[lslot];
-        zwr[q] = rleaf ? zbr : mem[q].zw[rslot];
+        // leaf children come from the two-entry leaf table, internal ones from their slot (both fetched, one kept)
+        double2 ls, rs;
+        mem[q].slots.ld_async(lslot, lane, ls);
+        mem[q].slots.ld_async(rslot, lane, rs);
+        const double2 lt = T.leaftab[bl], rt = T.leaftab[br];
+        mem[q].slots.wait_async(ls);
+        mem[q].slots.wait_async(rs);
+        L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
+        Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
       }
 #pragma unroll
       for (int q = 0; q < NI; q++) {
-        const uint32_t zwv = zwl[q] & zwr[q];
-        // pure-loss categories: add the log factor of each child branch (objects.cpp:420-426 collapsed)
-        {
-          const bool zl = (zwl[q] >> lane) & 1u, zr = (zwr[q] >> lane) & 1u;
-          const bool zv = (op.node != 0) && ((zwv >> lane) & 1u);  // the root always counts as active
-          A0[q] += zl ? (zv ? 0. : orc[5]) : orc[4];
-          A1[q] += zl ? (zv ? 0. : orc[7]) : orc[6];
-          A0[q] += zr ? (zv ? 0. : orc[9]) : orc[8];
-          A1[q] += zr ? (zv ? 0. : orc[11]) : orc[10];
-        }
         if (op.dst >= 0) {
           // Mobile merge (objects.cpp:427-435 in linear domain)
           double m0 = fma(-orc[0], L[q].y, L[q].x) * fma(-orc[2], Rr[q].y, Rr[q].x);
@@ -493,9 +523,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
               for (int i = 0; i < R; i++) if (i >= op.i0) ex[q][i] += k;
             }
           }
-          // every lane reads back only what it wrote itself (its slot column; zw gets the same word from all lanes)
-          mem[q].slots.st(op.dst, lane, make_double2(av, d));
-          mem[q].zw[op.dst] = zwv;
+          mem[q].slots.st(op.dst, lane, make_double2(av, d));  // every lane reads back only its own slot column
         }
       }
     }
@@ -731,12 +759,14 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     }
     // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
     if (active[q]) {
-      const double lik0 = sc[SC_C0] + A0[q];
+      // log p1(root) of the two pure-loss categories, from the class-sum kernel
+      const double2 A01 = a.t.a01[(size_t)p * m.n_pat_pad + (pat[q] - a.first)];
+      const double lik0 = sc[SC_C0] + A01.x;
       const int mr = m.mrca[pat[q]];
       const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];
       double lik1;
-      if (m.freq[pat[q]] == 0) lik1 = lse2(sc[SC_C1] + A1[q], sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
-      else lik1 = sc[SC_C1] + (A1[q] + du.x);
+      if (m.freq[pat[q]] == 0) lik1 = lse2(sc[SC_C1] + A01.y, sc[SC_C1] + (du.y + sc[SC_LOG1ME2]));  // all-zero gene row: mrca is a leaf (functions.cpp:216)
+      else lik1 = sc[SC_C1] + (A01.y + du.x);
       const double lik2 = (Im[q] > 0.) ? sc[SC_C2] + (log(Im[q]) - (double)Ie[q] * 0.693147180559945309417232) : -INFINITY;
       double mx = fmax(lik0, fmax(lik1, lik2));
       double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));

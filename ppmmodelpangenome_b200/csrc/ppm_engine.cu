@@ -83,7 +83,7 @@ struct ppm_engine {
   DevBuf<ppm::EntryRec> d_recs;
   DevBuf<double> d_params, d_yy, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
   DevBuf<double4> d_cls;
-  DevBuf<double2> d_kap, d_d1u, d_gslots;
+  DevBuf<double2> d_kap, d_d1u, d_gslots, d_clsT, d_a01;
   DevBuf<signed char> d_cat;
   size_t partial_cap = 0;
 
@@ -167,12 +167,13 @@ struct ppm_engine {
       d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
       d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
       d_oprec.alloc((size_t)P * std::max<size_t>(prog.ops.size(), 1) * ppm::OPREC_DOUBLES);
+      d_clsT.alloc((size_t)P * nn * 2); d_a01.alloc((size_t)P * std::max<long long>(n_pat_pad, 32));
       d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 4 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }
     ppm::TablesDev t{};
-    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p;
+    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p;
     return t;
   }
@@ -200,6 +201,8 @@ struct ppm_engine {
     if (need > partial_cap) { d_partial.alloc(need); partial_cap = need; }
     a.partial = d_partial.p;
     if (a.n_items > 0) {
+      ppm::launch_class_sums(md, t, 0, count, s);
+      n_launches += 1;
       ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm);
       d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
       CK(cudaEventRecord(ev0, s));

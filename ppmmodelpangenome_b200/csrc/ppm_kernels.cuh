@@ -69,6 +69,8 @@ struct TablesDev {
   EntryRec* recs;        // [P][n_entries+1]
   double* yy;            // [P][n_blocks*R] exp(-(g2+l2)*(t_slice - t_block)), 0 for padding slices
   double* oprec;         // [P][n_ops][OPREC_DOUBLES]
+  double2* clsT;         // [n_nodes][2][P] {cat0, cat1} log branch factors: [.][0] active, [.][1] frontier
+  double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)
   double* scal;          // [P][SC_COUNT]
   double* zeta;          // [P][4][n_nodes] scratch of the node prepass
 };
@@ -89,6 +91,7 @@ struct SweepArgs {
 
 void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
+void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s);
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
 struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks, mode; size_t smem_bytes, per_warp_bytes; bool staged; };
