@@ -81,9 +81,11 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   double4* cls = t.cls + (size_t)p * nn;
   double2* kap = t.kap + (size_t)p * nn;
   double2* d1u = t.d1u + (size_t)p * nn;
-  double* z0 = t.zeta + (size_t)p * 4 * nn;  // zero-row log p1 per node for l0; later log V
+  double* z0 = t.zeta + (size_t)p * 6 * nn;  // zero-row log p1 per node for l0; later log V
   double* z1 = z0 + nn;                      // ... for l1; later U
   double* ta = z1 + nn;                      // getPobs1 terms
+  double* ss0 = ta + nn;                     // sum of the "active" factors S over the subtree of each node (l0)
+  double* ss1 = ss0 + nn;                    // ... (l1)
   double* sc = t.scal + (size_t)p * SC_COUNT;
 
   const double lam = g2 + l2;
@@ -127,6 +129,12 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       c.w = lse2(c.w, -l1 * bl + zl1);
       if (v == 0) c = make_double4(0., 0., 0., 0.);
       cls[v] = c;
+      // class-sum tables: with Stot = sum of S over ALL branches, log p1(root) = Stot + sum over the maximal all-zero
+      // subtrees c of F_c, F_c = T_c - (sum of S over the subtree of c)
+      const double s0 = c.x + (leaf ? 0. : ss0[m.left[v]] + ss0[m.right[v]]);
+      const double s1 = c.z + (leaf ? 0. : ss1[m.left[v]] + ss1[m.right[v]]);
+      ss0[v] = s0; ss1[v] = s1;
+      t.clsT[(size_t)v * t.P + p] = make_double2(c.y - s0, c.w - s1);
       // getPobs1 term (functions.cpp:284-299)
       const double lost = 1 - exp(-l1 * bl);
       ta[v] = leaf ? lost * (1 - e2) : lost * (1 - exp(zl1));
@@ -147,6 +155,7 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     sc[SC_LD1] = m1 - m0; sc[SC_LA1] = m0 + pi1 * (m1 - m0);
     sc[SC_P0] = p0; sc[SC_P1] = p1; sc[SC_A] = A;
     sc[SC_LOG1ME2] = log_1me2;
+    sc[SC_STOT0] = ss0[0]; sc[SC_STOT1] = ss1[0];
     sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
     sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
     z0[0] = 0.; z1[0] = 0.;
@@ -211,27 +220,18 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     r[0] = kl.x; r[1] = kl.y; r[2] = kr.x; r[3] = kr.y;
     r[4] = cl.x; r[5] = cl.y; r[6] = cl.z; r[7] = cl.w;
     r[8] = cr.x; r[9] = cr.y; r[10] = cr.z; r[11] = cr.w;
-  } else if (i <= m.n_entries + n_pad + m.n_ops + m.n_nodes) {
-    // pure-loss branch factors transposed for the class-sum kernel (lanes = parameter vectors):
-    // clsT[(v*2 + 0)*P + p] = {S0, S1} (active branch), clsT[(v*2 + 1)*P + p] = {T0, T1} (frontier branch)
-    int v = i - m.n_entries - n_pad - m.n_ops - 1;
-    const double4 c = t.cls[(size_t)p * m.n_nodes + v];
-    t.clsT[((size_t)v * 2 + 0) * t.P + p] = make_double2(c.x, c.z);
-    t.clsT[((size_t)v * 2 + 1) * t.P + p] = make_double2(c.y, c.w);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ class sums
-// log p1(root) of the two pure-loss categories (Persistent l0, Private l1) for one pattern and one parameter
-// vector: sum over branches of S (a present leaf below), T (all-zero subtree under an active parent) or nothing
-// (all-zero subtree under an all-zero parent) -- objects.cpp:404-426 collapsed, see DESIGN.md.  The class of a
-// branch depends on the pattern only, the value on the parameter vector only: with one PATTERN per warp and the
-// lanes over parameter vectors the class tests are warp-uniform and the loads coalesced.
-// zbits: per-warp scratch, one bit per node ("subtree all zero"); pw: the pattern's words.
-PPM_HD double2 class_sums_body(const ModelDev& m, const TablesDev& t, const uint32_t* pw, int pw_stride, int p, uint32_t* zbits) {
-  double a0 = 0., a1 = 0.;
-  const bool lane_ok = p < t.P;
-  const int pp = lane_ok ? p : 0;
+// log p1(root) of the two pure-loss categories (Persistent l0, Private l1): objects.cpp:404-426 collapsed.
+// Per branch the factor is S (a present leaf below), T (all-zero subtree under an active parent) or nothing; hence
+//   log p1(root) = Stot + sum over the pattern's FRONTIER nodes c (roots of maximal all-zero subtrees) of F_c,
+// with Stot and F_c = T_c - sum_{subtree c} S per parameter vector (prepass) and the frontier per pattern only.
+// Step 1 (pattern only, warp-uniform): one pass over the node ops marks all-zero subtrees and lists the frontier.
+// zbits: one bit per node; frontier: up to n_nodes node ids.  Returns the frontier length.
+PPM_HD int class_frontier(const ModelDev& m, const uint32_t* pw, size_t pw_stride, uint32_t* zbits, uint16_t* frontier) {
+  int nf = 0;
   for (int o = 0; o < m.n_ops; o++) {
     const NodeOpDev op = m.ops[o];
     bool zl, zr;
@@ -240,22 +240,25 @@ PPM_HD double2 class_sums_body(const ModelDev& m, const TablesDev& t, const uint
     if (op.rref < 0) { int pos = -(op.rref + 1); zr = !((pw[(size_t)(pos >> 5) * pw_stride] >> (pos & 31)) & 1u); }
     else zr = (zbits[op.rnode >> 5] >> (op.rnode & 31)) & 1u;
     const bool zv = zl && zr;
-    // every lane updates its own copy of the (identical) bit array in the host build; on the device the array is per warp
     const uint32_t bit = 1u << (op.node & 31);
     uint32_t w = zbits[op.node >> 5];
     w = zv ? (w | bit) : (w & ~bit);
     ppm_syncwarp();
-    zbits[op.node >> 5] = w;
+    zbits[op.node >> 5] = w;   // (all lanes write the same word)
+    const bool parent_active = !zv || op.node == 0;  // the root always counts as active
+    if (parent_active && zl) frontier[nf++] = (uint16_t)op.lnode;
+    if (parent_active && zr) frontier[nf++] = (uint16_t)op.rnode;
     ppm_syncwarp();
-    const bool par_zero = zv && op.node != 0;  // the root always counts as active
-    if (!(zl && par_zero)) {
-      const double2 c = t.clsT[((size_t)op.lnode * 2 + (zl ? 1 : 0)) * t.P + pp];
-      a0 += c.x; a1 += c.y;
-    }
-    if (!(zr && par_zero)) {
-      const double2 c = t.clsT[((size_t)op.rnode * 2 + (zr ? 1 : 0)) * t.P + pp];
-      a0 += c.x; a1 += c.y;
-    }
+  }
+  return nf;
+}
+// Step 2 (one parameter vector per lane): Stot + sum of F over the frontier.
+PPM_HD double2 class_sums(const TablesDev& t, int p, const uint16_t* frontier, int nf) {
+  const double* sc = t.scal + (size_t)p * SC_COUNT;
+  double a0 = sc[SC_STOT0], a1 = sc[SC_STOT1];
+  for (int k = 0; k < nf; k++) {
+    const double2 f = t.clsT[(size_t)frontier[k] * t.P + p];
+    a0 += f.x; a1 += f.y;
   }
   return make_double2(a0, a1);
 }

@@ -167,8 +167,8 @@ struct ppm_engine {
       d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
       d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
       d_oprec.alloc((size_t)P * std::max<size_t>(prog.ops.size(), 1) * ppm::OPREC_DOUBLES);
-      d_clsT.alloc((size_t)P * nn * 2); d_a01.alloc((size_t)P * std::max<long long>(n_pat_pad, 32));
-      d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 4 * nn);
+      d_clsT.alloc((size_t)P * nn); d_a01.alloc((size_t)P * std::max<long long>(n_pat_pad, 32));
+      d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 6 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }

@@ -27,17 +27,18 @@ __global__ void __launch_bounds__(128) prepass_nodes_kernel(ModelDev m, TablesDe
 __global__ void prepass_tables_kernel(ModelDev m, TablesDev t) {
   prepass_tables_body(m, t, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
-// one warp per (pattern, 32 parameter vectors); grid.x over patterns (8 per CTA), grid.y over parameter chunks
+// one warp per pattern: the frontier once, then all parameter vectors 32 at a time (coalesced table rows)
 __global__ void __launch_bounds__(256) class_sums_kernel(ModelDev m, TablesDev t, long long count) {
-  extern __shared__ uint32_t zb_all[];
+  extern __shared__ uint32_t cs_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int zwords = (m.n_nodes + 31) >> 5;
-  uint32_t* zbits = zb_all + (size_t)warp * zwords;
+  const int zwords = (m.n_nodes + 31) >> 5, fwords = (m.n_nodes + 1) >> 1;
+  uint32_t* zbits = cs_smem + (size_t)warp * (zwords + fwords);
+  uint16_t* frontier = reinterpret_cast<uint16_t*>(zbits + zwords);
   const long long pat = (long long)blockIdx.x * wpc + warp;
   if (pat >= count) return;
-  const int p = blockIdx.y * 32 + lane;
-  const double2 a = class_sums_body(m, t, m.words + pat, (int)m.n_pat_pad, p, zbits);
-  if (p < t.P) t.a01[(size_t)p * m.n_pat_pad + pat] = a;
+  const int nf = class_frontier(m, m.words + pat, (size_t)m.n_pat_pad, zbits, frontier);
+  __syncwarp();
+  for (int p = lane; p < t.P; p += 32) t.a01[(size_t)p * m.n_pat_pad + pat] = class_sums(t, p, frontier, nf);
 }
 
 __global__ void prepass_i2_kernel(ModelDev m, TablesDev t, const double* i2_override) {
@@ -214,17 +215,18 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
   prepass_nodes_kernel<<<t.P, 128, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops + m.n_nodes;
+  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops;
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s) {
   (void)first;
   if (count <= 0) return;
-  const int wpc = 8;
-  dim3 g((unsigned)((count + wpc - 1) / wpc), (unsigned)((t.P + 31) / 32));
-  size_t smem = (size_t)wpc * ((m.n_nodes + 31) / 32) * sizeof(uint32_t);
-  class_sums_kernel<<<g, wpc * 32, smem, s>>>(m, t, count);
+  const size_t per_warp = ((size_t)((m.n_nodes + 31) / 32) + (size_t)((m.n_nodes + 1) / 2)) * sizeof(uint32_t);
+  int wpc = (int)std::min<size_t>(8, (48 * 1024) / per_warp);
+  if (wpc < 1) wpc = 1;
+  dim3 g((unsigned)((count + wpc - 1) / wpc));
+  class_sums_kernel<<<g, wpc * 32, per_warp * wpc, s>>>(m, t, count);
 }
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s) {
   prepass_i2_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t, i2_override);

@@ -15,6 +15,7 @@ enum {
   SC_I2, SC_P0, SC_P1, SC_A, SC_B,  // computeI2 (functions.cpp:334-344)
   SC_LOG1ME2,  // log(1 - s_10)
   SC_IZ_M, SC_IZ_E,  // zero-row Mobile integral as mantissa * 2^-exp
+  SC_STOT0, SC_STOT1,  // sum over all branches of the "active" log factor S, categories 0 / 1
   SC_COUNT = 20  // even: keeps the (a,d) pairs 16-byte aligned in every row
 };
 
@@ -69,10 +70,10 @@ struct TablesDev {
   EntryRec* recs;        // [P][n_entries+1]
   double* yy;            // [P][n_blocks*R] exp(-(g2+l2)*(t_slice - t_block)), 0 for padding slices
   double* oprec;         // [P][n_ops][OPREC_DOUBLES]
-  double2* clsT;         // [n_nodes][2][P] {cat0, cat1} log branch factors: [.][0] active, [.][1] frontier
+  double2* clsT;         // [n_nodes][P] {cat0, cat1} frontier factors F_c = T_c - sum of S over the subtree of c
   double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)
   double* scal;          // [P][SC_COUNT]
-  double* zeta;          // [P][4][n_nodes] scratch of the node prepass
+  double* zeta;          // [P][6][n_nodes] scratch of the node prepass
 };
 
 struct SweepArgs {

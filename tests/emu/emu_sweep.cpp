@@ -65,9 +65,10 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<EntryRec> recs((size_t)P * (prog.entry_ref.size() + 1));
     std::vector<double> yy((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
     std::vector<double> oprec((size_t)P * std::max<size_t>(prog.ops.size(), 1) * OPREC_DOUBLES);
-    std::vector<double2> clsT((size_t)P * nn * 2), a01((size_t)P * std::max<long long>(count, 1));
+    std::vector<double2> clsT((size_t)P * nn), a01((size_t)P * std::max<long long>(count, 1));
     std::vector<uint32_t> zbits((nn + 31) / 32);
-    std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 4 * nn), i2ovr(P);
+    std::vector<uint16_t> frontier(nn);
+    std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 6 * nn), i2ovr(P);
     TablesDev t{};
     t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data(); t.clsT = clsT.data(); t.a01 = a01.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
@@ -105,9 +106,11 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     };
     for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++)
-      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops + md.n_nodes; i++) prepass_tables_body(md, t, p, i);
-    for (int p = 0; p < P; p++)
-      for (long long j = 0; j < count; j++) a01[(size_t)p * count + j] = class_sums_body(md, t, md.words + j, (int)md.n_pat_pad, p, zbits.data());
+      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops; i++) prepass_tables_body(md, t, p, i);
+    for (long long j = 0; j < count; j++) {
+      const int nf = class_frontier(md, md.words + j, (size_t)md.n_pat_pad, zbits.data(), frontier.data());
+      for (int p = 0; p < P; p++) a01[(size_t)p * count + j] = class_sums(t, p, frontier.data(), nf);
+    }
     run(1, P, nullptr, nullptr, nullptr, true);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
     run(0, P, out_ll, nullptr, nullptr, false);
