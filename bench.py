@@ -271,11 +271,11 @@ def main():
             "wall_s_timed_region": t_wall,
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P * 8 * 8), "d2h_bytes_per_step": int(P * 8 * 2)},
-            "gpu_launches": int(cnt["launches"] + 1) * K,
+            "gpu_launches": int(cnt["launches"] + 1) * K,  # 7 kernels in ppm_loglik_device + finalize
             "roofline": {"bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach / peak_tf) if ach else None,
-                         "traffic": 8.69e6 if (P == 256 and world == 1) else None,  # dram read+write bytes per launch, ncu --set full (profiles/)
-                         "kernel": "ppm::sweep_kernel<8,true>", "kernel_ms": sweep,
+                         "traffic": 4.98e7 if (P == 256 and world == 1) else None,  # dram read+write bytes per launch, ncu --set full (profiles/)
+                         "kernel": "ppm::sweep_kernel<8,1,0>", "kernel_ms": sweep,
                          "peak_source": "DFMA micro-benchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_pattern_eval": F,
                          "fp64_pipe_tflops_issued": pipe, "fp64_pipe_frac": (pipe / peak_tf) if pipe else None},
