@@ -449,6 +449,7 @@ Program build_program(const Tree& t, int R, bool deep) {
   // entries: per block, four typed segments (see BlockDesc), each sorted by reference
   struct Ent { int ref, i0, i1, node; bool leaf; };
   const int kPadRef = 1 << 20;  // marks a padding record (sorts behind every real lineage)
+  const int kPairRef = 1 << 21; // marks a leaf-pair entry (ref - kPairRef = pair id)
   if (deep && pg.n_slots + 1 > 65535) throw std::runtime_error("program: tree too large for 16-bit lineage references");
   std::vector<std::vector<Ent>> ent(nb);
   for (int v = 1; v < nn; v++) {
@@ -463,38 +464,81 @@ Program build_program(const Tree& t, int R, bool deep) {
       ent[b].push_back(e);
     }
   }
+  // static leaf pairs for the u-form: cherries first (they merge together), then the remaining leaves by merge time
+  double max_leaf_h = 0;
+  for (int k = 0; k < nl; k++) max_leaf_h = std::max(max_leaf_h, std::fabs(t.height[t.leaf_node[k]]));
+  pg.leaf_u = max_leaf_h <= 1e-6 * t.H;
+  std::vector<int> pair_of(nl, -1);
+  if (pg.leaf_u) {
+    for (int v = 0; v < nn; v++)
+      if (t.left[v] >= 0 && t.left[t.left[v]] < 0 && t.left[t.right[v]] < 0) {
+        int a = t.leaf_pos[t.left[v]], bq = t.leaf_pos[t.right[v]];
+        pair_of[a] = pair_of[bq] = (int)pg.pair_pos.size() / 2;
+        pg.pair_pos.push_back(a); pg.pair_pos.push_back(bq);
+      }
+    std::vector<int> rest;
+    for (int k = 0; k < nl; k++) if (pair_of[k] < 0 && nn > 1) rest.push_back(k);
+    std::sort(rest.begin(), rest.end(), [&](int x, int y) {
+      int dx = js1[t.leaf_node[x]], dy = js1[t.leaf_node[y]];
+      return dx != dy ? dx < dy : x < y;
+    });
+    for (size_t i = 0; i + 1 < rest.size(); i += 2) {
+      pair_of[rest[i]] = pair_of[rest[i + 1]] = (int)pg.pair_pos.size() / 2;
+      pg.pair_pos.push_back(rest[i]); pg.pair_pos.push_back(rest[i + 1]);
+    }
+    if (pg.pair_pos.size() / 2 > 65535) throw std::runtime_error("program: too many leaf pairs for 16-bit references");
+  }
   double fp64 = 0;
   for (int b = 0; b < nb; b++) {
     const int nsl = pg.blk[b].nslices;
-    // 0 internal alive in every slice, 1 leaf alive in every slice, 2 leaf merged inside the block,
-    // 3 internal lineage born and/or merged inside the block
+    auto is_full = [&](const Ent& e) { return e.i0 == 0 && e.i1 == nsl; };  // in a short last block the padding slices carry weight 0
+    // pairs: both members alive in every slice of the block -> one entry for the two
+    std::vector<Ent> list;
+    if (pg.leaf_u) {
+      std::vector<int> full_member(pg.pair_pos.size() / 2, 0);
+      for (const Ent& e : ent[b]) if (e.leaf && is_full(e) && e.ref != kPadRef && pair_of[e.ref] >= 0) full_member[pair_of[e.ref]]++;
+      std::vector<char> emitted(pg.pair_pos.size() / 2, 0);
+      for (const Ent& e : ent[b]) {
+        if (e.leaf && is_full(e) && pair_of[e.ref] >= 0 && full_member[pair_of[e.ref]] == 2) {
+          if (emitted[pair_of[e.ref]]) continue;
+          emitted[pair_of[e.ref]] = 1;
+          Ent pe = e; pe.ref = kPairRef + pair_of[e.ref];
+          list.push_back(pe);
+        } else list.push_back(e);
+      }
+    } else list = ent[b];
+    // 0 internal full, 1 leaf pair (u), 2 single leaf full (u), 3 single leaf full (K/Y), 4 leaf partial, 5 internal partial
     auto cls_of = [&](const Ent& e) {
-      const bool full = e.i0 == 0 && e.i1 == nsl;  // in a short last block the padding slices carry weight 0
-      return full ? (e.leaf ? 1 : 0) : (e.leaf ? 2 : 3);
+      if (!e.leaf) return is_full(e) ? 0 : 5;
+      if (e.ref >= kPairRef) return 1;
+      if (!is_full(e)) return 4;
+      return pg.leaf_u ? 2 : 3;
     };
     if (deep) {  // pad the lineage segment to a multiple of 4 with records on the constant row (slot n_slots, K irrelevant)
       int n0 = 0;
-      for (const Ent& e : ent[b]) n0 += cls_of(e) == 0;
-      for (; n0 % 4; n0++) { Ent e; e.i0 = 0; e.i1 = nsl; e.node = t.leaf_node[0]; e.leaf = false; e.ref = kPadRef; ent[b].push_back(e); }
+      for (const Ent& e : list) n0 += cls_of(e) == 0;
+      for (; n0 % 4; n0++) { Ent e; e.i0 = 0; e.i1 = nsl; e.node = t.leaf_node[0]; e.leaf = false; e.ref = kPadRef; list.push_back(e); }
     }
-    std::stable_sort(ent[b].begin(), ent[b].end(), [&](const Ent& x, const Ent& y) {
+    std::stable_sort(list.begin(), list.end(), [&](const Ent& x, const Ent& y) {
       int cx = cls_of(x), cy = cls_of(y);
       if (cx != cy) return cx < cy;
       return x.ref < y.ref;
     });
     BlockDescHost& bd = pg.blk[b];
-    int seg0[5] = {-1, -1, -1, -1, -1};
-    for (const Ent& e : ent[b]) {
+    int seg0[7] = {-1, -1, -1, -1, -1, -1, -1};
+    for (const Ent& e : list) {
       int c = cls_of(e), at = (int)pg.entry_ref.size();
       for (int k = 0; k <= c; k++) if (seg0[k] < 0) seg0[k] = at;
-      if (c >= 2) pg.n_partial++; else pg.n_full++;
-      if (e.ref != kPadRef) fp64 += 1 + 2 * (e.i1 - e.i0);
-      const uint32_t live = c < 2 ? ((1u << R) - 1u) : (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+      if (c >= 4) pg.n_partial++; else pg.n_full++;
       const bool padrec = (c == 0 && e.ref == kPadRef);
-      pg.entry_ref.push_back(padrec ? pg.n_slots : (c == 1 ? (e.ref >> 5) : e.ref));
-      uint32_t mk = live;
-      if (c == 1) mk = 1u << (e.ref & 31);
-      else if (c >= 2) {
+      if (!padrec) fp64 += (c == 1) ? 3 * (e.i1 - e.i0) : (c == 2 ? 2 * (e.i1 - e.i0) : 1 + 2 * (e.i1 - e.i0));
+      const uint32_t live = (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+      int ref = e.ref; uint32_t mk = live;
+      if (padrec) ref = pg.n_slots;
+      else if (c == 1) { int pid = e.ref - kPairRef; ref = pid; mk = (uint32_t)pg.pair_pos[2 * pid] | ((uint32_t)pg.pair_pos[2 * pid + 1] << 16); }
+      else if (c == 2) { mk = 0; }                        // ref = bit position
+      else if (c == 3) { ref = e.ref >> 5; mk = 1u << (e.ref & 31); }
+      else if (c >= 4) {
         // code in the low half: i0 for a suffix [i0,end), 16+i1 for a prefix [0,i1), 0 = use the mask in the high half
         const bool to_end = e.i1 == nsl;
         uint32_t code = 0;
@@ -502,25 +546,28 @@ Program build_program(const Tree& t, int R, bool deep) {
         else if (e.i0 == 0 && e.i1 > 0 && e.i1 < 16) code = 16u + (uint32_t)e.i1;
         mk = code | (live << 16);
       }
+      pg.entry_ref.push_back(ref);
       pg.entry_mask.push_back(mk);
       pg.entry_node.push_back(e.node);
       pg.entry_block.push_back(b);
     }
     const int end = (int)pg.entry_ref.size();
-    seg0[4] = end;
-    for (int k = 3; k >= 0; k--) if (seg0[k] < 0) seg0[k] = seg0[k + 1];
-    bd.e_slot0 = seg0[0]; bd.e_leaf0 = seg0[1]; bd.e_pleaf0 = seg0[2]; bd.e_pslot0 = seg0[3]; bd.e_end = end;
+    seg0[6] = end;
+    for (int k = 5; k >= 0; k--) if (seg0[k] < 0) seg0[k] = seg0[k + 1];
+    bd.e_slot0 = seg0[0]; bd.e_pair0 = seg0[1]; bd.e_leafu0 = seg0[2]; bd.e_leaf0 = seg0[3]; bd.e_pleaf0 = seg0[4]; bd.e_pslot0 = seg0[5]; bd.e_end = end;
     // prefetch hints: the upper half of ref names the next record's operand within the same segment
-    // (0 = an always-valid dummy at the end of a segment)
-    for (int k = 0; k < 4; k++)
+    // (0 = an always-valid dummy at the end of a segment); pair records keep the whole word for the pair id
+    for (int k = 0; k < 6; k++) {
+      if (k == 1) continue;
       for (int e = seg0[k]; e + 1 < seg0[k + 1]; e++) pg.entry_ref[e] |= (pg.entry_ref[e + 1] & 0xffff) << 16;
+    }
   }
   {
     BlockDescHost& bd = pg.blk[nb];
-    bd.e_slot0 = bd.e_leaf0 = bd.e_pleaf0 = bd.e_pslot0 = bd.e_end = (int)pg.entry_ref.size();
+    bd.e_slot0 = bd.e_pair0 = bd.e_leafu0 = bd.e_leaf0 = bd.e_pleaf0 = bd.e_pslot0 = bd.e_end = (int)pg.entry_ref.size();
   }
-  // + node ops (8 merge + 2 renorm + 4 class adds), block ends (~3 per slice), epilogue (~60)
-  pg.fp64_instr_per_eval = fp64 + 14.0 * (nl - 1) + 3.0 * S + 60;
+  // + node ops (8 merge + 2 renorm), block ends (~3 per slice), epilogue (~60), class sums (~2 per frontier node)
+  pg.fp64_instr_per_eval = fp64 + 10.0 * (nl - 1) + 3.0 * S + 60 + 0.4 * nl;
   return pg;
 }
 

@@ -61,7 +61,7 @@ struct NodeOp {
   int32_t pad;
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
-  int32_t slice0, nslices, op0, op1, e_slot0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
+  int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0;
 };
 struct Program {
   int R = 8;
@@ -72,6 +72,8 @@ struct Program {
   std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
   std::vector<uint32_t> entry_mask;               // see EntryRec::mask
   std::vector<int32_t> entry_node, entry_block;   // node id / block of each entry (for the K table)
+  std::vector<int32_t> pair_pos;                  // [2*n_pairs] bit positions of the leaves paired for the u-form quadratics
+  bool leaf_u = false;                            // leaves are (numerically) at height 0: u-form entries are used
   int64_t n_full = 0, n_partial = 0;
   // modelled FP64 instruction count per pattern-eval of the main kernel
   double fp64_instr_per_eval = 0;

@@ -156,6 +156,7 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     sc[SC_P0] = p0; sc[SC_P1] = p1; sc[SC_A] = A;
     sc[SC_LOG1ME2] = log_1me2;
     sc[SC_STOT0] = ss0[0]; sc[SC_STOT1] = ss1[0];
+    sc[SC_FACTORED] = (pi1 > 0.95) ? 1. : 0.;
     sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
     sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
     z0[0] = 0.; z1[0] = 0.;
@@ -210,16 +211,43 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
       v = exp(-lam * (m.slice_t[j] - tb));
     }
     t.yy[(size_t)p * n_pad + j] = v;
+    // u_j = 1 - exp(-(g2+l2) t_j) = p01(t_j)/pi1 (functions.cpp:227-231): the variable of the u-form leaf terms
+    t.uu[(size_t)p * n_pad + j] = (j < m.n_slices) ? 1. - exp(-lam * m.slice_t[j]) : 0.;
   } else if (i <= m.n_entries + n_pad + m.n_ops) {
     // per-op record: the branch tables of the two children, contiguous (no dependent index loads in the sweep)
     int o = i - m.n_entries - n_pad - 1;
     const NodeOpDev op = m.ops[o];
     const double2 kl = t.kap[(size_t)p * m.n_nodes + op.lnode], kr = t.kap[(size_t)p * m.n_nodes + op.rnode];
-    const double4 cl = t.cls[(size_t)p * m.n_nodes + op.lnode], cr = t.cls[(size_t)p * m.n_nodes + op.rnode];
     double* r = t.oprec + ((size_t)p * m.n_ops + o) * OPREC_DOUBLES;
     r[0] = kl.x; r[1] = kl.y; r[2] = kr.x; r[3] = kr.y;
-    r[4] = cl.x; r[5] = cl.y; r[6] = cl.z; r[7] = cl.w;
-    r[8] = cr.x; r[9] = cr.y; r[10] = cr.z; r[11] = cr.w;
+  } else if (i <= m.n_entries + n_pad + m.n_ops + m.n_leaves + m.n_pairs) {
+    // u-form leaf terms.  A leaf s at height h_s (numerically 0) observed as x contributes, at time t,
+    //   (1-q) m0_x + q m1_x,  q = pi1 (1 - exp(-lam (t - h_s)))                       (functions.cpp:232-240)
+    // = alpha + beta * u(t),  alpha = m0_x - pi1 d_x expm1(lam h_s),  beta = pi1 d_x exp(lam h_s),  u = 1 - exp(-lam t).
+    // A pair of leaves is the product of two such terms: a quadratic in u for each of the 4 observation pairs.
+    const double e2 = par[6], e1 = par[7];
+    int k = i - m.n_entries - n_pad - m.n_ops - 1;
+    auto leaf_term = [&](int pos, int x, double& alpha, double& beta) {
+      const double hs = m.height[m.leaf_node[pos]];
+      const double m0 = x ? e1 : 1 - e1, m1 = x ? 1 - e2 : e2, d = m1 - m0;  // objects.cpp:407-408
+      alpha = m0 - pi1 * d * expm1(lam * hs);
+      beta = pi1 * d * exp(lam * hs);
+    };
+    if (k < m.n_leaves) {
+      for (int x = 0; x < 2; x++) {
+        double al, be;
+        leaf_term(k, x, al, be);
+        t.leafab[((size_t)p * m.n_leaves + k) * 2 + x] = make_double2(al, be);
+      }
+    } else {
+      const int pr = k - m.n_leaves;
+      for (int c = 0; c < 4; c++) {
+        double a1, b1, a2, b2;
+        leaf_term(m.pair_pos[2 * pr], c & 1, a1, b1);
+        leaf_term(m.pair_pos[2 * pr + 1], c >> 1, a2, b2);
+        t.pairq[((size_t)p * m.n_pairs + pr) * 4 + c] = make_double4(a1 * a2, a1 * b2 + a2 * b1, b1 * b2, 0.);
+      }
+    }
   }
 }
 
@@ -334,7 +362,6 @@ struct SlotsTmem {
 template <class Slots>
 struct ItemMem {
   uint32_t* sw;
-  uint32_t* zw;
   Slots slots;
 };
 
@@ -348,6 +375,9 @@ struct ItemTables {
   const double* yy;       // [n_blocks * R]
   const double* wt;       // [n_blocks * R]
   const double2* leaftab; // [2] leaf partials (a,d) for observation 0 / 1
+  const double* uu;       // [n_blocks * R]
+  const double2* leafab;  // [n_leaves][2] u-form leaf terms {alpha, beta}
+  const double4* pairq;   // [n_pairs][4] u-form pair quadratics
 };
 
 // One 16-byte load per record: K | ref | mask
@@ -466,8 +496,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 
   int X[NI];                // sum of renormalisation shifts of all lineages formed so far
   double Im[NI]; int Ie[NI];  // Mobile integral = Im * 2^-Ie (exponent of an empty sum: +inf)
-  double prod[NI][R], Y[R];
+  double prod[NI][R], Y[R], U[R];
   int ex[NI][R];
+  const bool factored = sc[SC_FACTORED] != 0.;
 #pragma unroll
   for (int q = 0; q < NI; q++) { X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
 
@@ -476,7 +507,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     const bool real = b < m.n_blocks;
     if (real) {
 #pragma unroll
-      for (int i = 0; i < R; i++) Y[i] = T.yy[b * R + i];
+      for (int i = 0; i < R; i++) { Y[i] = T.yy[b * R + i]; U[i] = T.uu[b * R + i]; }
 #pragma unroll
       for (int q = 0; q < NI; q++)
 #pragma unroll
@@ -536,7 +567,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // leaves (partials selected by the pattern bit).
     if (DEEP) {
       // the constant row (1,0) behind the last slot makes padding records multiply by one
-      const int E0 = bd.e_slot0, E1 = bd.e_pleaf0, ES = bd.e_leaf0;
+      const int E0 = bd.e_slot0, E1 = bd.e_pair0, ES = bd.e_pair0;  // (leaves: u-form loops below; K/Y leaves: generic loop)
       const int nch = (E1 - E0 + 31) >> 5;
       auto stage = [&](int c) {
         int idx = E0 + c * 32 + lane;
@@ -624,8 +655,8 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // Each record names the NEXT record's operand in its upper bits, so the next operand load is issued before the
     // current products (software prefetch); chunks of 16 entries end with a range check.
     // (1) internal lineages alive in every slice: partials in slots; ref = slot | next slot << 16
-    for (int e = bd.e_slot0; e < bd.e_leaf0;) {
-      const int ce = (e + 16 < bd.e_leaf0) ? e + 16 : bd.e_leaf0;
+    for (int e = bd.e_slot0; e < bd.e_pair0;) {
+      const int ce = (e + 16 < bd.e_pair0) ? e + 16 : bd.e_pair0;
       double K; uint32_t ref, mk;
       load_rec(T.recs, e, K, ref, mk);
       double2 ad[NI];
@@ -651,7 +682,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       for (int q = 0; q < NI; q++)
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
-    // (2) leaves alive in every slice of the block: ref = word | next word << 16, mk = the leaf's bit in that word
+    }
+    // (2) single leaves alive in every slice in block-relative K/Y form (only trees whose leaves are not at height 0):
+    // ref = word | next word << 16, mk = the leaf's bit in that word
     for (int e = bd.e_leaf0; e < bd.e_pleaf0;) {
       const int ce = (e + 16 < bd.e_pleaf0) ? e + 16 : bd.e_pleaf0;
       double K; uint32_t ref, mk;
@@ -680,6 +713,97 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       for (int q = 0; q < NI; q++)
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
+    // ---- u-form leaves (all variants).  Pairs: one record per two leaves, their two pattern bits pick one of four
+    // quadratics q.x + q.y u + q.z u^2 (3 FP64 per slice for two leaf terms, no selects); the next record's bits and
+    // table row are fetched while the current products run.
+    if (bd.e_pair0 < bd.e_leafu0) {
+      double K; uint32_t ref, mk;
+      load_rec(T.recs, bd.e_pair0, K, ref, mk);
+      double4 qv[NI];
+      uint32_t bits[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) {
+        const uint32_t pa = mk & 0xffffu, pb = mk >> 16;
+        const uint32_t ba = (mem[q].sw[(pa >> 5) * PPM_LANES + lane] >> (pa & 31u)) & 1u;
+        const uint32_t bb = (mem[q].sw[(pb >> 5) * PPM_LANES + lane] >> (pb & 31u)) & 1u;
+        bits[q] = ba | (bb << 1);
+        qv[q] = T.pairq[(ref & 0xffffu) * 4 + bits[q]];
+      }
+      for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
+        const uint32_t pa0 = mk & 0xffffu, pb0 = mk >> 16;   // (for the factored form)
+        double4 qn[NI];
+        uint32_t bn[NI];
+        load_rec(T.recs, e + 1, K, ref, mk);
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+          uint32_t pa = mk & 0xffffu, pb = mk >> 16;
+          pa = pa < (uint32_t)m.n_leaves ? pa : 0u; pb = pb < (uint32_t)m.n_leaves ? pb : 0u;  // (the record after the segment)
+          const uint32_t ba = (mem[q].sw[(pa >> 5) * PPM_LANES + lane] >> (pa & 31u)) & 1u;
+          const uint32_t bb = (mem[q].sw[(pb >> 5) * PPM_LANES + lane] >> (pb & 31u)) & 1u;
+          bn[q] = ba | (bb << 1);
+          const uint32_t pid = (ref & 0xffffu) < (uint32_t)m.n_pairs ? (ref & 0xffffu) : 0u;
+          qn[q] = T.pairq[pid * 4 + bn[q]];
+        }
+        if (!factored) {
+#pragma unroll
+          for (int q = 0; q < NI; q++)
+#pragma unroll
+            for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
+        } else {  // pi1 close to 1: two linear factors keep full accuracy
+#pragma unroll
+          for (int q = 0; q < NI; q++) {
+            const double2 fa = T.leafab[pa0 * 2 + (bits[q] & 1u)], fb = T.leafab[pb0 * 2 + (bits[q] >> 1)];
+#pragma unroll
+            for (int i = 0; i < R; i++) prod[q][i] *= fma(fa.y, U[i], fa.x) * fma(fb.y, U[i], fb.x);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NI; q++) { qv[q] = qn[q]; bits[q] = bn[q]; }
+        if (((e - bd.e_pair0) & 7) == 7) {
+#pragma unroll
+          for (int q = 0; q < NI; q++)
+            if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NI; q++)
+        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+    }
+    // single leaves in u-form: ref = bit position | next << 16; the term alpha + beta u comes from a per-lane table row
+    if (bd.e_leafu0 < bd.e_leaf0) {
+      double K; uint32_t ref, mk;
+      load_rec(T.recs, bd.e_leafu0, K, ref, mk);
+      double2 fv[NI];
+#pragma unroll
+      for (int q = 0; q < NI; q++) {
+        const uint32_t ps = ref & 0xffffu;
+        const uint32_t bt = (mem[q].sw[(ps >> 5) * PPM_LANES + lane] >> (ps & 31u)) & 1u;
+        fv[q] = T.leafab[ps * 2 + bt];
+      }
+      for (int e = bd.e_leafu0; e < bd.e_leaf0; e++) {
+        double2 fn[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+          const uint32_t ps = ref >> 16;
+          const uint32_t bt = (mem[q].sw[(ps >> 5) * PPM_LANES + lane] >> (ps & 31u)) & 1u;
+          fn[q] = T.leafab[ps * 2 + bt];
+        }
+        load_rec(T.recs, e + 1, K, ref, mk);
+#pragma unroll
+        for (int q = 0; q < NI; q++) {
+#pragma unroll
+          for (int i = 0; i < R; i++) prod[q][i] *= fma(fv[q].y, U[i], fv[q].x);
+          fv[q] = fn[q];
+        }
+        if (((e - bd.e_leafu0) & 15) == 15) {
+#pragma unroll
+          for (int q = 0; q < NI; q++)
+            if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NI; q++)
+        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
     // (3) leaves merged inside the block: ref = bit position | next << 16, mk = code | live slices << 16
     if (bd.e_pleaf0 < bd.e_pslot0) {

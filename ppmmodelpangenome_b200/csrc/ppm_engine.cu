@@ -68,7 +68,7 @@ struct ppm_engine {
   double n_launches = 0;
 
   // device model
-  DevBuf<int> d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
+  DevBuf<int> d_leaf_node, d_pair_pos, d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
   DevBuf<ppm::BlockDesc> d_blk;
   DevBuf<uint32_t> d_entry_mask;
   DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt;
@@ -81,7 +81,9 @@ struct ppm_engine {
   // per-launch tables
   int P_cap = 0;
   DevBuf<ppm::EntryRec> d_recs;
-  DevBuf<double> d_params, d_yy, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
+  DevBuf<double4> d_pairq;
+  DevBuf<double2> d_leafab;
+  DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
   DevBuf<double4> d_cls;
   DevBuf<double2> d_kap, d_d1u, d_gslots, d_clsT, d_a01;
   DevBuf<signed char> d_cat;
@@ -134,6 +136,8 @@ struct ppm_engine {
     d_blk.upload(blk, stream);
     d_entry_ref.upload(prog.entry_ref, stream); d_entry_mask.upload(prog.entry_mask, stream);
     d_entry_node.upload(prog.entry_node, stream); d_entry_block.upload(prog.entry_block, stream);
+    d_leaf_node.upload(tree.leaf_node, stream);
+    { std::vector<int> pp(prog.pair_pos.begin(), prog.pair_pos.end()); if (pp.empty()) pp.assign(2, 0); d_pair_pos.upload(pp, stream); }
     // patterns of this shard, word-major so that lanes (= consecutive patterns) read consecutive addresses
     n_pat_pad = (count + 31) / 32 * 32;
     std::vector<uint32_t> wm((size_t)pat.n_words * std::max<long long>(n_pat_pad, 32), 0u);
@@ -156,6 +160,7 @@ struct ppm_engine {
     md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p;
     md.slice_t = d_slice_t.p; md.slice_wt_pad = d_slice_wt.p;
     md.blk = d_blk.p; md.ops = d_ops.p;
+    md.n_pairs = (int)prog.pair_pos.size() / 2; md.leaf_node = d_leaf_node.p; md.pair_pos = d_pair_pos.p;
     md.entry_ref = d_entry_ref.p; md.entry_mask = d_entry_mask.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
     md.words = d_words.p; md.n_pat = count; md.n_pat_pad = n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
@@ -167,13 +172,15 @@ struct ppm_engine {
       d_cls.alloc((size_t)P * nn); d_kap.alloc((size_t)P * nn); d_d1u.alloc((size_t)P * nn);
       d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
       d_oprec.alloc((size_t)P * std::max<size_t>(prog.ops.size(), 1) * ppm::OPREC_DOUBLES);
+      d_uu.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
+      d_leafab.alloc((size_t)P * tree.n_leaves * 2); d_pairq.alloc((size_t)P * std::max<size_t>(prog.pair_pos.size() / 2, 1) * 4);
       d_clsT.alloc((size_t)P * nn); d_a01.alloc((size_t)P * std::max<long long>(n_pat_pad, 32));
       d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 6 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }
     ppm::TablesDev t{};
-    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p;
+    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p;
     return t;
   }

@@ -57,7 +57,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 static const size_t kRecRingBytes = 3 * 32 * sizeof(EntryRec);  // per-warp record ring of the global-memory variant
 
 struct StageLayout {
-  size_t recs, blk, ops, oprec, yy, wt, leaf, total;
+  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, leaf, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
@@ -68,11 +68,14 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.oprec = o; o += align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double));
   L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
+  L.uu = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
+  L.leafab = o; o += align16((size_t)m.n_leaves * 2 * sizeof(double2));
+  L.pairq = o; o += align16((size_t)m.n_pairs * 4 * sizeof(double4));
   L.leaf = o; o += 32;
   L.total = o;
   return L;
 }
-__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16(((size_t)m.n_words * 32 + m.n_slots) * 4); }
+__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16((size_t)m.n_words * 32 * 4); }
 
 template <int MODE>
 __device__ __forceinline__ void init_slots(SlotsMem& s, double2* smem_slots, double2* global_slots, uint32_t, int, int, int, int) {
@@ -129,7 +132,6 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
   for (int q = 0; q < NI; q++) {
     unsigned char* ib = wbase + (size_t)q * per_item;
     mem[q].sw = reinterpret_cast<uint32_t*>(ib);
-    mem[q].zw = mem[q].sw + m.n_words * 32;
     init_slots<MODE>(mem[q].slots, reinterpret_cast<double2*>(ib + head),
                      a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32,
                      tmem_base_s, warp, wpc, q, nt);
@@ -149,6 +151,9 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       copy16(smem_raw + L.oprec, a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES, align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)));
       copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
+      copy16(smem_raw + L.uu, a.t.uu + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
+      copy16(smem_raw + L.leafab, a.t.leafab + (size_t)p * m.n_leaves * 2, align16((size_t)m.n_leaves * 2 * sizeof(double2)));
+      copy16(smem_raw + L.pairq, a.t.pairq + (size_t)p * m.n_pairs * 4, align16((size_t)m.n_pairs * 4 * sizeof(double4)));
       copy16(smem_raw + L.leaf, a.t.scal + (size_t)p * SC_COUNT + SC_LA0, 32);
       __syncthreads();
       T.recs = reinterpret_cast<const EntryRec*>(smem_raw + L.recs);
@@ -158,6 +163,9 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       T.yy = reinterpret_cast<const double*>(smem_raw + L.yy);
       T.wt = reinterpret_cast<const double*>(smem_raw + L.wt);
       T.leaftab = reinterpret_cast<const double2*>(smem_raw + L.leaf);
+      T.uu = reinterpret_cast<const double*>(smem_raw + L.uu);
+      T.leafab = reinterpret_cast<const double2*>(smem_raw + L.leafab);
+      T.pairq = reinterpret_cast<const double4*>(smem_raw + L.pairq);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
       T.blk = m.blk; T.ops = m.ops;
@@ -165,6 +173,9 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       T.yy = a.t.yy + (size_t)p * nbR;
       T.wt = m.slice_wt_pad;
       T.leaftab = reinterpret_cast<const double2*>(a.t.scal + (size_t)p * SC_COUNT + SC_LA0);
+      T.uu = a.t.uu + (size_t)p * nbR;
+      T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
+      T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
     }
     for (int k = 0; k < a.items_per_warp; k++) {
       const long long batch0 = (((long long)chunk * a.items_per_warp + k) * wpc + warp) * NI;
@@ -215,7 +226,7 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
   prepass_nodes_kernel<<<t.P, 128, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops;
+  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops + m.n_leaves + m.n_pairs;
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }

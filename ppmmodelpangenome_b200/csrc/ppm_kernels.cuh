@@ -15,6 +15,7 @@ enum {
   SC_I2, SC_P0, SC_P1, SC_A, SC_B,  // computeI2 (functions.cpp:334-344)
   SC_LOG1ME2,  // log(1 - s_10)
   SC_IZ_M, SC_IZ_E,  // zero-row Mobile integral as mantissa * 2^-exp
+  SC_FACTORED,         // != 0: evaluate leaf pairs as two linear factors (pi1 close to 1: the expanded quadratic loses digits)
   SC_STOT0, SC_STOT1,  // sum over all branches of the "active" log factor S, categories 0 / 1
   SC_COUNT = 20  // even: keeps the (a,d) pairs 16-byte aligned in every row
 };
@@ -25,20 +26,27 @@ struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
-  // [e_slot0,e_leaf0) internal lineages alive in every slice | [e_leaf0,e_pleaf0) leaves alive in every slice |
+  // [e_slot0,e_pair0)   internal lineages alive in every slice (partials in slots)
+  // [e_pair0,e_leafu0)  PAIRS of leaves alive in every slice, as one quadratic in u = 1 - exp(-(g2+l2) t)
+  // [e_leafu0,e_leaf0)  single leaves alive in every slice, linear in u
+  // [e_leaf0,e_pleaf0)  single leaves alive in every slice, block-relative K/Y form (trees with tall leaves only)
   // [e_pleaf0,e_pslot0) leaves merged inside the block | [e_pslot0,e_end) internal lineages born/merged inside it
-  int32_t slice0, nslices, op0, op1, e_slot0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0, pad1, pad2;
+  int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0;
 };
 struct __align__(16) EntryRec {
   double K;       // pi1 * exp(-(g2+l2) * (t_block - h_lineage))   (per parameter vector)
-  int32_t ref;    // full leaves: word | next word << 16;  slots: slot | next slot << 16;  partial leaves: bit
-                  // position | next position << 16  ("next" = prefetch hint, 0 at the end of a segment)
-  uint32_t mask;  // full leaves: the leaf's bit inside its word;  otherwise: the live slices of the block
+  int32_t ref;    // slots: slot | next slot << 16;  K/Y leaves: word | next word << 16;  partial leaves and u-form
+                  // leaves: bit position | next position << 16;  pairs: pair id  ("next" = prefetch hint)
+  uint32_t mask;  // K/Y leaves: the leaf's bit inside its word;  pairs: position A | position B << 16;
+                  // partial entries: code | live slices << 16;  otherwise unused
 };
-enum { OPREC_DOUBLES = 12 };  // per (parameter vector, node op): kap_l{x,y} kap_r{x,y} cls_l{S0,T0,S1,T1} cls_r{..}
+enum { OPREC_DOUBLES = 4 };  // per (parameter vector, node op): kap_l{x,y} kap_r{x,y}
 
 struct ModelDev {
   int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
+  int n_pairs;  // static leaf pairs (u-form quadratics)
+  const int* leaf_node;  // [n_leaves] bit position -> node id
+  const int* pair_pos;   // [2*n_pairs] bit positions of the two leaves of a pair
   int deep;  // program built for the global-memory variant: lineage segments padded to multiples of 4 records
   double H;
   long long n_obs;
@@ -70,6 +78,9 @@ struct TablesDev {
   EntryRec* recs;        // [P][n_entries+1]
   double* yy;            // [P][n_blocks*R] exp(-(g2+l2)*(t_slice - t_block)), 0 for padding slices
   double* oprec;         // [P][n_ops][OPREC_DOUBLES]
+  double* uu;            // [P][n_blocks*R] u_j = 1 - exp(-(g2+l2) t_j), 0 for padding slices
+  double2* leafab;       // [P][n_leaves][2] leaf term = alpha + beta*u for observation 0 / 1
+  double4* pairq;        // [P][n_pairs][4] pair term = q.x + q.y*u + q.z*u^2 for the 4 bit combinations (A | B<<1)
   double2* clsT;         // [n_nodes][P] {cat0, cat1} frontier factors F_c = T_c - sum of S over the subtree of c
   double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)
   double* scal;          // [P][SC_COUNT]

@@ -26,6 +26,10 @@ CASES = {
                            [[1, 1, 0, 0, 0], [0, 0, 1, 1, 0], [1, 1, 1, 1, 1], [0, 0, 0, 0, 1], [1, 0, 1, 0, 1], [0, 1, 0, 0, 0]]),
     "all_zero_gene": ("((A:0.4,B:0.4):0.6,(C:0.8,D:0.8):0.2);", list("ABCD"),
                       [[0, 0, 0, 0], [1, 0, 0, 0], [1, 1, 1, 1], [0, 0, 1, 1], [0, 0, 0, 0]]),
+    # not ultrametric: leaves B and D sit above height 0, so the engine uses the block-relative K/Y leaf entries
+    # instead of the u-form pairs (the reference still evaluates such trees)
+    "tall_leaf": ("((A:0.4,B:0.3):0.6,(C:0.8,D:0.5):0.2);", list("ABCD"),
+                  [[1, 0, 0, 0], [1, 1, 1, 1], [0, 0, 1, 1], [0, 1, 0, 1], [1, 0, 1, 0], [0, 0, 0, 1]]),
 }
 PARAMS = [
     [3, 0.3, 2, 1.5, 2.0, 30.0, 0.02, 0.05],
@@ -34,6 +38,9 @@ PARAMS = [
     [3, 0.3, 2, 1.5, 2.0, 30.0, 0.0, 0.0],          # no errors at all
     [3, 0.3, 2, 1.5, 2.0, 30.0, 1e-12, 1e-12],      # vanishing error rates
     [2, 3.0, 1, 150.0, 160.0, 8000.0, 0.2, 0.2],    # optimiser upper bounds: (g2+l2)*H ~ 8000
+    [1, 0.3, 0.5, 1.5, 2.0, 30.0, 0.02, 0.05],      # feasible (i2 > 0) on the tiny inputs
+    [1, 0.3, 0.5, 1.5, 40.0, 0.2, 0.02, 0.05],      # pi1 = 0.995: leaf pairs evaluated as two linear factors
+    [1, 0.0, 0.5, 1.5, 3.0, 0.0, 1e-9, 0.0],        # l0 = 0, l2 = 0 (pi1 = 1), vanishing s_10, s_01 = 0
 ]
 
 
