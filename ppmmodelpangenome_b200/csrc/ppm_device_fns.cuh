@@ -362,6 +362,7 @@ struct SlotsTmem {
 template <class Slots>
 struct ItemMem {
   uint32_t* sw;
+  uint32_t* cw;   // [ceil(n_pairs/16)][lanes]: the 2-bit observation pair of every leaf pair, 16 pairs per word
   Slots slots;
 };
 
@@ -378,6 +379,7 @@ struct ItemTables {
   const double* uu;       // [n_blocks * R]
   const double2* leafab;  // [n_leaves][2] u-form leaf terms {alpha, beta}
   const double4* pairq;   // [n_pairs][4] u-form pair quadratics
+  const int* pair_pos;    // [2*n_pairs] bit positions of the leaves of each pair
 };
 
 // One 16-byte load per record: K | ref | mask
@@ -485,6 +487,23 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   for (int q = 0; q < NI; q++)
     for (int w = 0; w < m.n_words; w++)
       mem[q].sw[w * PPM_LANES + lane] = (a.mode == 1 || !active[q]) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
+  ppm_syncwarp();
+  // observation pair (bit A | bit B << 1) of every static leaf pair, packed 16 pairs per word: the pair entries of all
+  // blocks then need one load + shift instead of two bit extractions each
+#pragma unroll
+  for (int q = 0; q < NI; q++) {
+    for (int w0 = 0; w0 < m.n_pairs; w0 += 16) {
+      uint32_t acc = 0u;
+      const int w1 = (w0 + 16 < m.n_pairs) ? w0 + 16 : m.n_pairs;
+      for (int pr = w0; pr < w1; pr++) {
+        const int pa = T.pair_pos[2 * pr], pb = T.pair_pos[2 * pr + 1];
+        const uint32_t ba = (mem[q].sw[(pa >> 5) * PPM_LANES + lane] >> (pa & 31)) & 1u;
+        const uint32_t bb = (mem[q].sw[(pb >> 5) * PPM_LANES + lane] >> (pb & 31)) & 1u;
+        acc |= (ba | (bb << 1)) << (2 * (pr - w0));
+      }
+      mem[q].cw[(w0 >> 4) * PPM_LANES + lane] = acc;
+    }
+  }
   ppm_syncwarp();
 
   const double pi1 = sc[SC_PI1];
@@ -717,52 +736,59 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // quadratics q.x + q.y u + q.z u^2 (3 FP64 per slice for two leaf terms, no selects); the next record's bits and
     // table row are fetched while the current products run.
     if (bd.e_pair0 < bd.e_leafu0) {
+      const int pmax = m.n_pairs - 1;
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_pair0, K, ref, mk);
-      double4 qv[NI];
-      uint32_t bits[NI];
+      uint32_t cb[NI];   // observation pair of the current record's pair, per item
+      int pid = (int)(ref & 0xffffu);
 #pragma unroll
-      for (int q = 0; q < NI; q++) {
-        const uint32_t pa = mk & 0xffffu, pb = mk >> 16;
-        const uint32_t ba = (mem[q].sw[(pa >> 5) * PPM_LANES + lane] >> (pa & 31u)) & 1u;
-        const uint32_t bb = (mem[q].sw[(pb >> 5) * PPM_LANES + lane] >> (pb & 31u)) & 1u;
-        bits[q] = ba | (bb << 1);
-        qv[q] = T.pairq[(ref & 0xffffu) * 4 + bits[q]];
-      }
-      for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
-        const uint32_t pa0 = mk & 0xffffu, pb0 = mk >> 16;   // (for the factored form)
-        double4 qn[NI];
-        uint32_t bn[NI];
-        load_rec(T.recs, e + 1, K, ref, mk);
+      for (int q = 0; q < NI; q++) cb[q] = (mem[q].cw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
+      if (!factored) {
+        double4 qv[NI];
 #pragma unroll
-        for (int q = 0; q < NI; q++) {
-          uint32_t pa = mk & 0xffffu, pb = mk >> 16;
-          pa = pa < (uint32_t)m.n_leaves ? pa : 0u; pb = pb < (uint32_t)m.n_leaves ? pb : 0u;  // (the record after the segment)
-          const uint32_t ba = (mem[q].sw[(pa >> 5) * PPM_LANES + lane] >> (pa & 31u)) & 1u;
-          const uint32_t bb = (mem[q].sw[(pb >> 5) * PPM_LANES + lane] >> (pb & 31u)) & 1u;
-          bn[q] = ba | (bb << 1);
-          const uint32_t pid = (ref & 0xffffu) < (uint32_t)m.n_pairs ? (ref & 0xffffu) : 0u;
-          qn[q] = T.pairq[pid * 4 + bn[q]];
-        }
-        if (!factored) {
-#pragma unroll
-          for (int q = 0; q < NI; q++)
-#pragma unroll
-            for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
-        } else {  // pi1 close to 1: two linear factors keep full accuracy
+        for (int q = 0; q < NI; q++) qv[q] = T.pairq[pid * 4 + (int)cb[q]];
+#pragma unroll 2
+        for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
+          load_rec(T.recs, e + 1, K, ref, mk);
+          int pn = (int)(ref & 0xffffu);
+          pn = pn < pmax ? pn : pmax;  // (the record behind the segment is not a pair)
+          double4 qn[NI];
 #pragma unroll
           for (int q = 0; q < NI; q++) {
-            const double2 fa = T.leafab[pa0 * 2 + (bits[q] & 1u)], fb = T.leafab[pb0 * 2 + (bits[q] >> 1)];
+            const uint32_t cn = (mem[q].cw[(pn >> 4) * PPM_LANES + lane] >> (2 * (pn & 15))) & 3u;
+            qn[q] = T.pairq[pn * 4 + (int)cn];
+          }
+#pragma unroll
+          for (int q = 0; q < NI; q++) {
+#pragma unroll
+            for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
+            qv[q] = qn[q];
+          }
+          if (((e - bd.e_pair0) & 15) == 15) {
+#pragma unroll
+            for (int q = 0; q < NI; q++)
+              if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+          }
+        }
+      } else {  // pi1 close to 1: two linear factors keep full accuracy
+        for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
+          const int pa = T.pair_pos[2 * pid], pb = T.pair_pos[2 * pid + 1];
+#pragma unroll
+          for (int q = 0; q < NI; q++) {
+            const double2 fa = T.leafab[pa * 2 + (int)(cb[q] & 1u)], fb = T.leafab[pb * 2 + (int)(cb[q] >> 1)];
 #pragma unroll
             for (int i = 0; i < R; i++) prod[q][i] *= fma(fa.y, U[i], fa.x) * fma(fb.y, U[i], fb.x);
           }
-        }
+          load_rec(T.recs, e + 1, K, ref, mk);
+          pid = (int)(ref & 0xffffu);
+          pid = pid < pmax ? pid : pmax;
 #pragma unroll
-        for (int q = 0; q < NI; q++) { qv[q] = qn[q]; bits[q] = bn[q]; }
-        if (((e - bd.e_pair0) & 7) == 7) {
+          for (int q = 0; q < NI; q++) cb[q] = (mem[q].cw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
+          if (((e - bd.e_pair0) & 7) == 7) {
 #pragma unroll
-          for (int q = 0; q < NI; q++)
-            if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+            for (int q = 0; q < NI; q++)
+              if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+          }
         }
       }
 #pragma unroll

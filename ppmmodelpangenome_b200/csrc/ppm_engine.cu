@@ -137,7 +137,7 @@ struct ppm_engine {
     d_entry_ref.upload(prog.entry_ref, stream); d_entry_mask.upload(prog.entry_mask, stream);
     d_entry_node.upload(prog.entry_node, stream); d_entry_block.upload(prog.entry_block, stream);
     d_leaf_node.upload(tree.leaf_node, stream);
-    { std::vector<int> pp(prog.pair_pos.begin(), prog.pair_pos.end()); if (pp.empty()) pp.assign(2, 0); d_pair_pos.upload(pp, stream); }
+    { std::vector<int> pp(prog.pair_pos.begin(), prog.pair_pos.end()); if (pp.empty()) pp.assign(2, 0); pp.resize((pp.size() + 3) / 4 * 4, 0); d_pair_pos.upload(pp, stream); }  // (padded: copied 16 bytes at a time)
     // patterns of this shard, word-major so that lanes (= consecutive patterns) read consecutive addresses
     n_pat_pad = (count + 31) / 32 * 32;
     std::vector<uint32_t> wm((size_t)pat.n_words * std::max<long long>(n_pat_pad, 32), 0u);

@@ -57,7 +57,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 static const size_t kRecRingBytes = 3 * 32 * sizeof(EntryRec);  // per-warp record ring of the global-memory variant
 
 struct StageLayout {
-  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, leaf, total;
+  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, pairpos, leaf, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
@@ -71,11 +71,13 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.uu = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.leafab = o; o += align16((size_t)m.n_leaves * 2 * sizeof(double2));
   L.pairq = o; o += align16((size_t)m.n_pairs * 4 * sizeof(double4));
+  L.pairpos = o; o += align16((size_t)(m.n_pairs > 0 ? m.n_pairs : 1) * 2 * sizeof(int));
   L.leaf = o; o += 32;
   L.total = o;
   return L;
 }
-__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16((size_t)m.n_words * 32 * 4); }
+// per item and warp: pattern words [n_words][32] + observation-pair words [ceil(n_pairs/16)][32]
+__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16(((size_t)m.n_words + (size_t)((m.n_pairs + 15) / 16)) * 32 * 4); }
 
 template <int MODE>
 __device__ __forceinline__ void init_slots(SlotsMem& s, double2* smem_slots, double2* global_slots, uint32_t, int, int, int, int) {
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
   for (int q = 0; q < NI; q++) {
     unsigned char* ib = wbase + (size_t)q * per_item;
     mem[q].sw = reinterpret_cast<uint32_t*>(ib);
+    mem[q].cw = mem[q].sw + m.n_words * 32;
     init_slots<MODE>(mem[q].slots, reinterpret_cast<double2*>(ib + head),
                      a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32,
                      tmem_base_s, warp, wpc, q, nt);
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       copy16(smem_raw + L.uu, a.t.uu + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.leafab, a.t.leafab + (size_t)p * m.n_leaves * 2, align16((size_t)m.n_leaves * 2 * sizeof(double2)));
       copy16(smem_raw + L.pairq, a.t.pairq + (size_t)p * m.n_pairs * 4, align16((size_t)m.n_pairs * 4 * sizeof(double4)));
+      copy16(smem_raw + L.pairpos, m.pair_pos, align16((size_t)(m.n_pairs > 0 ? m.n_pairs : 1) * 2 * sizeof(int)));
       copy16(smem_raw + L.leaf, a.t.scal + (size_t)p * SC_COUNT + SC_LA0, 32);
       __syncthreads();
       T.recs = reinterpret_cast<const EntryRec*>(smem_raw + L.recs);
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       T.uu = reinterpret_cast<const double*>(smem_raw + L.uu);
       T.leafab = reinterpret_cast<const double2*>(smem_raw + L.leafab);
       T.pairq = reinterpret_cast<const double4*>(smem_raw + L.pairq);
+      T.pair_pos = reinterpret_cast<const int*>(smem_raw + L.pairpos);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
       T.blk = m.blk; T.ops = m.ops;
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       T.uu = a.t.uu + (size_t)p * nbR;
       T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
       T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
+      T.pair_pos = m.pair_pos;
     }
     for (int k = 0; k < a.items_per_warp; k++) {
       const long long batch0 = (((long long)chunk * a.items_per_warp + k) * wpc + warp) * NI;

@@ -81,10 +81,10 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
 
     // two items per "warp" as on the device (NI = 2), one lane each
     const int NI = 2;
-    std::vector<uint32_t> sw(NI * pat.n_words);
+    std::vector<uint32_t> sw(NI * pat.n_words), cw(NI * ((prog.pair_pos.size() / 2 + 15) / 16 + 1));
     std::vector<double2> slotmem(NI * (prog.n_slots + 1));
     ItemMem<SlotsMem> mem[2];
-    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
+    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].cw = cw.data() + q * ((prog.pair_pos.size() / 2 + 15) / 16 + 1); mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
     auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
       SweepArgs a{};
       a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
@@ -100,6 +100,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.uu = uu.data() + (size_t)p * md.n_blocks * md.R;
           T.leafab = leafab.data() + (size_t)p * md.n_leaves * 2;
           T.pairq = pairq.data() + (size_t)p * md.n_pairs * 4;
+          T.pair_pos = md.pair_pos;
           double c[2] = {0., 0.};
           if (deep && prog.R == 8) sweep_items<8, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (deep) throw std::runtime_error("deep emulation built for R = 8");
