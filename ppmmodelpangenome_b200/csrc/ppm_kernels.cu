@@ -105,6 +105,7 @@ template <int R, int NI, int MODE>
 __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int next_group;  // dynamic hand-out of the unit's warp items: the 4 schedulers of an SM rarely hold equally many warps
   typedef typename SlotsOf<MODE>::type Slots;
   constexpr bool STAGED = MODE != 2;
   const ModelDev& m = a.m;
@@ -141,13 +142,22 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
   }
   const int nbR = m.n_blocks * R;
 
-  const long long n_units = (long long)a.t.P * a.n_chunks;
-  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int p = (int)(unit / a.n_chunks);
-    const int chunk = (int)(unit % a.n_chunks);
+  // Persistent CTAs: the (parameter vector, batch) items form one line, cut into gridDim.x equal contiguous
+  // ranges (every item costs the same); a range touches at most a few parameter vectors, staged one after the other.
+  const long long groups = (a.n_batches + NI - 1) / NI;
+  const long long total = groups * a.t.P;
+  const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
+  const long long g_begin = per_cta * blockIdx.x;
+  const long long g_end = g_begin + per_cta < total ? g_begin + per_cta : total;
+  for (long long g0 = g_begin; g0 < g_end;) {
+    const int p = (int)(g0 / groups);
+    const long long b_begin = g0 - (long long)p * groups;
+    const long long b_end = (g_end - g0 < groups - b_begin) ? b_begin + (g_end - g0) : groups;
+    g0 += b_end - b_begin;
     ItemTables T;
+    __syncthreads();  // the previous unit's readers (tables, work counter) are done
+    if (threadIdx.x == 0) next_group = 0;
     if (STAGED) {
-      __syncthreads();  // the previous unit's readers are done
       copy16(smem_raw + L.recs, a.t.recs + (size_t)p * (m.n_entries + 1), align16((size_t)(m.n_entries + 1) * sizeof(EntryRec)));
       copy16(smem_raw + L.blk, m.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc)));
       copy16(smem_raw + L.ops, m.ops, align16((size_t)m.n_ops * sizeof(NodeOpDev)));
@@ -182,10 +192,14 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
       T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
       T.pair_pos = m.pair_pos;
+      __syncthreads();
     }
-    for (int k = 0; k < a.items_per_warp; k++) {
-      const long long batch0 = (((long long)chunk * a.items_per_warp + k) * wpc + warp) * NI;
-      if (batch0 >= a.n_batches) break;
+    while (true) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(&next_group, 1);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (b_begin + g >= b_end) break;
+      const long long batch0 = (b_begin + g) * NI;
       double contrib[NI];
       sweep_items<R, NI, MODE == 2, Slots>(a, T, p, batch0, lane, mem, contrib, wrec);
       if (a.mode == 1) continue;
@@ -293,12 +307,10 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
   if (pl.mode != 1 && groups < warps) warps = (int)std::max<long long>(1, groups);  // (MODE 1 keeps its TMEM column split)
   pl.warps = warps;
-  long long total = groups * (long long)P;
-  long long ipw = total / ((long long)n_sm * warps * 4);
-  pl.items_per_warp = (int)std::max<long long>(1, std::min<long long>(8, ipw));
-  pl.n_chunks = (int)((groups + (long long)warps * pl.items_per_warp - 1) / ((long long)warps * pl.items_per_warp));
-  long long units = (long long)pl.n_chunks * P;
-  pl.grid_x = (int)std::min<long long>(units, pl.staged ? 2147483647LL : (long long)n_sm);
+  const long long total = groups * (long long)P;
+  pl.grid_x = (int)std::max<long long>(1, std::min<long long>(n_sm, (total + warps - 1) / warps));
+  pl.items_per_warp = (int)((total + (long long)pl.grid_x * warps - 1) / ((long long)pl.grid_x * warps));  // informational
+  pl.n_chunks = 1;
   pl.smem_bytes = (pl.staged ? L.total : 0) + pl.per_warp_bytes * warps;
   return pl;
 }
