@@ -185,6 +185,12 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
 // One thread per (parameter vector, entry or padded slice): the exp tables of the Mobile integral.
 // recs[e] = { K = pi1*exp(-(g2+l2)*(t_block - h_lineage)), ref, slice mask }; yy[j] = exp(-(g2+l2)*(t_j - t_block)),
 // zero for the padding slices of the last block.
+PPM_HD double pack2i(int lo, int hi) {
+  const long long b = ((long long)hi << 32) | (long long)(uint32_t)lo;
+  double d; memcpy(&d, &b, 8);
+  return d;
+}
+
 PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, int i) {
   const double* par = t.params + 8 * (size_t)p;
   const double g2 = par[4], l2 = par[5];
@@ -199,6 +205,14 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     r.K = pi1 * exp(-lam * (tb - hs));
     r.ref = m.entry_ref[i];
     r.mask = m.entry_mask[i];
+    if (i >= m.blk[b].e_pair0 && i < m.blk[b].e_leafu0) {
+      // leaf-pair record: K is not needed (u-form); its 8 bytes carry the byte offsets the sweep would otherwise
+      // compute per entry -- low word: the pair's observation word row in the item's `cw` block, high word: the pair's
+      // row in pairq -- and mask the rotation that lands the 2-bit observation pair on bits 5..6 (x 32 bytes)
+      const int pid = r.ref;
+      r.K = pack2i((pid >> 4) * PPM_LANES * 4, pid * 4 * (int)sizeof(double4));
+      r.mask = (uint32_t)((2 * (pid & 15) - 5) & 31);
+    }
     t.recs[(size_t)p * (m.n_entries + 1) + i] = r;
   } else if (i == m.n_entries) {
     EntryRec r; r.K = 0.; r.ref = 0; r.mask = 0u;  // padding record: the prefetch of the last entry reads it
@@ -381,6 +395,22 @@ struct ItemTables {
   const double4* pairq;   // [n_pairs][4] u-form pair quadratics
   const int* pair_pos;    // [2*n_pairs] bit positions of the leaves of each pair
 };
+
+// the two 32-bit halves of a record's K field (leaf-pair records)
+PPM_HD void unpack2i(double v, int& lo, int& hi) {
+#if defined(__CUDA_ARCH__)
+  lo = __double2loint(v); hi = __double2hiint(v);
+#else
+  long long b; memcpy(&b, &v, 8); lo = (int)(uint32_t)b; hi = (int)(b >> 32);
+#endif
+}
+PPM_HD uint32_t rotr32(uint32_t v, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(v, v, s);
+#else
+  s &= 31u; return s ? (v >> s) | (v << (32u - s)) : v;
+#endif
+}
 
 // One 16-byte load per record: K | ref | mask
 PPM_HD void load_rec(const EntryRec* recs, int e, double& K, uint32_t& ref, uint32_t& mask) {
@@ -744,19 +774,25 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
       for (int q = 0; q < NI; q++) cb[q] = (mem[q].cw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
       if (!factored) {
+        // record = {cw byte offset, pairq byte offset, pair id, rotation}: word, rotate, mask, row -- no index arithmetic
+        const char* cwl[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) cwl[q] = reinterpret_cast<const char*>(mem[q].cw + lane);
+        const char* pq = reinterpret_cast<const char*>(T.pairq);
         double4 qv[NI];
 #pragma unroll
         for (int q = 0; q < NI; q++) qv[q] = T.pairq[pid * 4 + (int)cb[q]];
+        const int elast = bd.e_leafu0 - 1;
 #pragma unroll 2
         for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
-          load_rec(T.recs, e + 1, K, ref, mk);
-          int pn = (int)(ref & 0xffffu);
-          pn = pn < pmax ? pn : pmax;  // (the record behind the segment is not a pair)
+          load_rec(T.recs, e < elast ? e + 1 : elast, K, ref, mk);  // (the record behind the segment is not a pair)
+          int wo, qo;
+          unpack2i(K, wo, qo);
           double4 qn[NI];
 #pragma unroll
           for (int q = 0; q < NI; q++) {
-            const uint32_t cn = (mem[q].cw[(pn >> 4) * PPM_LANES + lane] >> (2 * (pn & 15))) & 3u;
-            qn[q] = T.pairq[pn * 4 + (int)cn];
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
+            qn[q] = *reinterpret_cast<const double4*>(pq + qo + (rotr32(w, mk) & 0x60u));
           }
 #pragma unroll
           for (int q = 0; q < NI; q++) {

@@ -100,21 +100,23 @@ __device__ __forceinline__ void init_slots(SlotsTmem& s, double2* smem_slots, do
 // Every warp sweeps NI batches (NI x 32 patterns) at once -- see sweep_items.
 template <int MODE> struct SlotsOf { typedef SlotsMem type; };
 template <> struct SlotsOf<1> { typedef SlotsTmem type; };
+template <> struct SlotsOf<3> { typedef SlotsTmem type; };  // MODE 3 = MODE 1 compiled for 12 warps (168 registers)
 
 template <int R, int NI, int MODE>
-__global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   __shared__ int next_group;  // dynamic hand-out of the unit's warp items: the 4 schedulers of an SM rarely hold equally many warps
   typedef typename SlotsOf<MODE>::type Slots;
   constexpr bool STAGED = MODE != 2;
+  constexpr bool TMEM = MODE == 1 || MODE == 3;
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const StageLayout L = stage_layout(m);
   const size_t head = warp_head_bytes(m);
   // lineage slots per item: MODE 0 all in shared memory; MODE 1 the first nt in TMEM, the rest in shared memory
   int nt = 0;
-  if (MODE == 1) {
+  if (TMEM) {
     const int cols_per_warp = (512 / ((wpc + 3) >> 2)) & ~3;
     nt = cols_per_warp / 4 / NI;
     if (warp == 0) {
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
   }
-  const int smem_slots = MODE == 0 ? m.n_slots : (MODE == 1 ? (m.n_slots > nt ? m.n_slots - nt : 0) : 0);
+  const int smem_slots = MODE == 0 ? m.n_slots : (TMEM ? (m.n_slots > nt ? m.n_slots - nt : 0) : 0);
   const size_t per_item = head + (size_t)smem_slots * 32 * sizeof(double2);
   const size_t per_warp = per_item * NI + (STAGED ? 0 : kRecRingBytes);
   unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_warp;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(MODE == 0 ? 384 : 512, 1) sweep_kernel(SweepAr
       __syncwarp();
     }
   }
-  if (MODE == 1) {
+  if (TMEM) {
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(512));
@@ -286,29 +288,36 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   // registers beat 16 warps x 128 registers with the slots in tensor memory by ~1 %)
   const size_t per_warp_staged = NI * (head + (size_t)m.n_slots * slot_row);
   int w0 = 0;
-  if (L.total + 3 * per_warp_staged <= budget) w0 = (int)std::min<size_t>(std::min(max_warps(), 12), (budget - L.total) / per_warp_staged);
+  if (L.total + per_warp_staged <= budget) w0 = (int)std::min<size_t>(std::min(max_warps(), 12), (budget - L.total) / per_warp_staged);
   // MODE 1: lineage slots in tensor memory (first nt per warp) + shared-memory overflow; most warps that fit
   int w1 = 0; size_t pw1 = 0;
   if (tmem_enabled()) {
-    for (int w = std::min(max_warps(), 16); w >= 8 && !w1; w -= 4) {
+    const char* t12 = std::getenv("PPM_TMEM12");
+    for (int w = std::min(max_warps(), (t12 && std::atoi(t12)) ? 12 : 16); w >= 8 && !w1; w -= 4) {
       const int nt = ((512 / ((w + 3) / 4)) & ~3) / 4 / NI;
       const size_t ovf = m.n_slots > nt ? (size_t)(m.n_slots - nt) : 0;
       if (L.total + (size_t)w * NI * (head + ovf * slot_row) <= budget) { w1 = w; pw1 = NI * (head + ovf * slot_row); }
     }
   }
+  const long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
+  const long long total = groups * (long long)P;
   const char* force = std::getenv("PPM_FORCE_TMEM");
-  if (w1 && ((force && std::atoi(force)) || w0 < 10)) { warps = w1; pl.mode = 1; pl.per_warp_bytes = pw1; }
+  const bool tiny = w0 >= 1 && groups <= w0 && (w0 >= 3 || w1);  // e.g. the all-zero row: one small CTA per parameter vector
+  // (only where the big sweep is staged too: both run the same, non-deep, program)
+  if (tiny) { warps = (int)groups; pl.mode = 0; pl.per_warp_bytes = per_warp_staged; }
+  else if (w1 && ((force && std::atoi(force)) || w0 < 10)) { warps = w1; pl.mode = w1 <= 12 ? 3 : 1; pl.per_warp_bytes = pw1; }
   else if (w0 >= 3) { warps = w0; pl.mode = 0; pl.per_warp_bytes = per_warp_staged; }
   pl.staged = pl.mode != 2;
   if (!pl.staged) {
     pl.per_warp_bytes = NI * head + kRecRingBytes;
     warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / pl.per_warp_bytes));
+    if (groups < warps) warps = (int)std::max<long long>(1, groups);
   }
-  long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
-  if (pl.mode != 1 && groups < warps) warps = (int)std::max<long long>(1, groups);  // (MODE 1 keeps its TMEM column split)
   pl.warps = warps;
-  const long long total = groups * (long long)P;
-  pl.grid_x = (int)std::max<long long>(1, std::min<long long>(n_sm, (total + warps - 1) / warps));
+  // persistent CTAs over equal contiguous ranges of the (parameter vector, batch) line; when a parameter vector has
+  // fewer items than a CTA has warps, one (small) CTA per parameter vector instead
+  if (groups <= warps) pl.grid_x = P;
+  else pl.grid_x = (int)std::max<long long>(1, std::min<long long>(n_sm, (total + warps - 1) / warps));
   pl.items_per_warp = (int)((total + (long long)pl.grid_x * warps - 1) / ((long long)pl.grid_x * warps));  // informational
   pl.n_chunks = 1;
   pl.smem_bytes = (pl.staged ? L.total : 0) + pl.per_warp_bytes * warps;
@@ -332,6 +341,7 @@ static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t
 template <int R>
 static void launch_sweep_r(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   if (pl.mode == 1) launch_sweep_t<R, 1>(a, pl, s);
+  else if (pl.mode == 3) launch_sweep_t<R, 3>(a, pl, s);
   else if (pl.mode == 0) launch_sweep_t<R, 0>(a, pl, s);
   else launch_sweep_t<R, 2>(a, pl, s);
 }
