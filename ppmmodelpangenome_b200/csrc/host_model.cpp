@@ -398,6 +398,36 @@ Program build_program(const Tree& t, int R, bool deep) {
     js0[v] = t.slice_start[std::max(t.rank[v], nl - 1)];
     js1[v] = t.slice_start[t.rank[t.parent[v]]];
   }
+  // static leaf pairs for the u-form: cherries first (they merge together), then the remaining leaves by merge time.
+  // The device patterns are stored in PROGRAM leaf order: pair p owns bits 2p and 2p+1 (so the two observations of a
+  // pair are one 2-bit field), unpaired leaves follow.  leaf_perm: preorder leaf index -> device bit position.
+  double max_leaf_h = 0;
+  for (int k = 0; k < nl; k++) max_leaf_h = std::max(max_leaf_h, std::fabs(t.height[t.leaf_node[k]]));
+  pg.leaf_u = max_leaf_h <= 1e-6 * t.H;
+  pg.leaf_perm.assign(nl, -1);
+  pg.n_pairs = 0;
+  if (pg.leaf_u) {
+    auto add_pair = [&](int a, int bq) { pg.leaf_perm[a] = 2 * pg.n_pairs; pg.leaf_perm[bq] = 2 * pg.n_pairs + 1; pg.n_pairs++; };
+    for (int v = 0; v < nn; v++)
+      if (t.left[v] >= 0 && t.left[t.left[v]] < 0 && t.left[t.right[v]] < 0) add_pair(t.leaf_pos[t.left[v]], t.leaf_pos[t.right[v]]);
+    pg.n_cherries = pg.n_pairs;
+    std::vector<int> rest;
+    for (int k = 0; k < nl; k++) if (pg.leaf_perm[k] < 0 && nn > 1) rest.push_back(k);
+    std::sort(rest.begin(), rest.end(), [&](int x, int y) {
+      int dx = js1[t.leaf_node[x]], dy = js1[t.leaf_node[y]];
+      return dx != dy ? dx < dy : x < y;
+    });
+    for (size_t i = 0; i + 1 < rest.size(); i += 2) add_pair(rest[i], rest[i + 1]);
+    if (pg.n_pairs > 65535) throw std::runtime_error("program: too many leaf pairs for 16-bit references");
+  }
+  {
+    int next = 2 * pg.n_pairs;
+    for (int k = 0; k < nl; k++) if (pg.leaf_perm[k] < 0) pg.leaf_perm[k] = next++;
+    pg.leaf_node_dev.assign(nl, 0);
+    for (int k = 0; k < nl; k++) pg.leaf_node_dev[pg.leaf_perm[k]] = t.leaf_node[k];
+  }
+  auto dpos = [&](int v) { return pg.leaf_perm[t.leaf_pos[v]]; };  // device bit position of leaf node v
+  auto pair_of = [&](int pos) { return pos < 2 * pg.n_pairs ? pos / 2 : -1; };
   // node ops: internal nodes in rank order; op block = block of the node's first alive slice
   std::vector<int> op_block(nn, nb);
   for (int v = 1; v < nn; v++)
@@ -427,8 +457,8 @@ Program build_program(const Tree& t, int R, bool deep) {
     open_blocks_to(b);
     NodeOp op{};
     op.node = v; op.lnode = t.left[v]; op.rnode = t.right[v];
-    op.lref = t.left[op.lnode] < 0 ? -(t.leaf_pos[op.lnode] + 1) : slot[op.lnode];
-    op.rref = t.left[op.rnode] < 0 ? -(t.leaf_pos[op.rnode] + 1) : slot[op.rnode];
+    op.lref = t.left[op.lnode] < 0 ? -(dpos(op.lnode) + 1) : slot[op.lnode];
+    op.rref = t.left[op.rnode] < 0 ? -(dpos(op.rnode) + 1) : slot[op.rnode];
     if (v == 0) { op.dst = -1; op.i0 = R; }
     else {
       if (free_slots.empty()) free_slots.push_back(n_slots++);
@@ -444,6 +474,28 @@ Program build_program(const Tree& t, int R, bool deep) {
   open_blocks_to(nb);
   blk_op0[nb + 1] = (int)pg.ops.size();
   for (int b = 0; b <= nb; b++) { pg.blk[b].op0 = blk_op0[b]; pg.blk[b].op1 = blk_op0[b + 1]; }
+  // Within a block no slot is reused and cherries depend on nothing, so they can run first: the sweep serves them
+  // from a per-parameter table indexed by the 2-bit observation pair instead of a merge.
+  pg.cherry_op.assign(pg.n_cherries, 0);
+  for (NodeOp& op : pg.ops) op.pair = (pg.leaf_u && op.lref < 0 && op.rref < 0 && op.dst >= 0) ? pair_of(-(op.lref + 1)) : -1;
+  for (int b = 0; b <= nb; b++) {
+    auto first = pg.ops.begin() + pg.blk[b].op0, last = pg.ops.begin() + pg.blk[b].op1;
+    auto mid = std::stable_partition(first, last, [](const NodeOp& op) { return op.pair >= 0; });
+    pg.blk[b].opc = (int)(mid - pg.ops.begin());
+  }
+  pg.sops.resize(pg.ops.size());
+  for (size_t o = 0; o < pg.ops.size(); o++) {
+    const NodeOp& op = pg.ops[o];
+    SweepOp& s = pg.sops[o];
+    auto leaf_bit = [](int ref) { int pos = -(ref + 1); return ((pos >> 5) << 5) | (((pos & 31) - 4) & 31); };
+    s.lslot = op.lref < 0 ? 0 : op.lref; s.rslot = op.rref < 0 ? 0 : op.rref;
+    s.lbit = op.lref < 0 ? leaf_bit(op.lref) : 0; s.rbit = op.rref < 0 ? leaf_bit(op.rref) : 0;
+    s.dst = op.dst; s.i0 = op.i0; s.flags = (op.lref < 0 ? 1 : 0) | (op.rref < 0 ? 2 : 0); s.pair = op.pair;
+    if (op.pair >= 0) {
+      pg.cherry_op[op.pair] = (int)o;
+      s.lbit = (((2 * op.pair) >> 5) << 5) | ((((2 * op.pair) & 31) - 4) & 31);
+    }
+  }
   pg.n_slots = std::max(n_slots, 1);
 
   // entries: per block, four typed segments (see BlockDesc), each sorted by reference
@@ -459,34 +511,10 @@ Program build_program(const Tree& t, int R, bool deep) {
       int jb = b * R, je = std::min(S, jb + R);
       Ent e;
       e.i0 = std::max(js0[v], jb) - jb; e.i1 = std::min(js1[v], je) - jb;
-      e.node = v; e.leaf = leaf; e.ref = leaf ? t.leaf_pos[v] : slot[v];
+      e.node = v; e.leaf = leaf; e.ref = leaf ? dpos(v) : slot[v];
       if (e.ref > 65535) throw std::runtime_error("program: tree too large for 16-bit lineage references");
       ent[b].push_back(e);
     }
-  }
-  // static leaf pairs for the u-form: cherries first (they merge together), then the remaining leaves by merge time
-  double max_leaf_h = 0;
-  for (int k = 0; k < nl; k++) max_leaf_h = std::max(max_leaf_h, std::fabs(t.height[t.leaf_node[k]]));
-  pg.leaf_u = max_leaf_h <= 1e-6 * t.H;
-  std::vector<int> pair_of(nl, -1);
-  if (pg.leaf_u) {
-    for (int v = 0; v < nn; v++)
-      if (t.left[v] >= 0 && t.left[t.left[v]] < 0 && t.left[t.right[v]] < 0) {
-        int a = t.leaf_pos[t.left[v]], bq = t.leaf_pos[t.right[v]];
-        pair_of[a] = pair_of[bq] = (int)pg.pair_pos.size() / 2;
-        pg.pair_pos.push_back(a); pg.pair_pos.push_back(bq);
-      }
-    std::vector<int> rest;
-    for (int k = 0; k < nl; k++) if (pair_of[k] < 0 && nn > 1) rest.push_back(k);
-    std::sort(rest.begin(), rest.end(), [&](int x, int y) {
-      int dx = js1[t.leaf_node[x]], dy = js1[t.leaf_node[y]];
-      return dx != dy ? dx < dy : x < y;
-    });
-    for (size_t i = 0; i + 1 < rest.size(); i += 2) {
-      pair_of[rest[i]] = pair_of[rest[i + 1]] = (int)pg.pair_pos.size() / 2;
-      pg.pair_pos.push_back(rest[i]); pg.pair_pos.push_back(rest[i + 1]);
-    }
-    if (pg.pair_pos.size() / 2 > 65535) throw std::runtime_error("program: too many leaf pairs for 16-bit references");
   }
   double fp64 = 0;
   for (int b = 0; b < nb; b++) {
@@ -495,14 +523,14 @@ Program build_program(const Tree& t, int R, bool deep) {
     // pairs: both members alive in every slice of the block -> one entry for the two
     std::vector<Ent> list;
     if (pg.leaf_u) {
-      std::vector<int> full_member(pg.pair_pos.size() / 2, 0);
-      for (const Ent& e : ent[b]) if (e.leaf && is_full(e) && e.ref != kPadRef && pair_of[e.ref] >= 0) full_member[pair_of[e.ref]]++;
-      std::vector<char> emitted(pg.pair_pos.size() / 2, 0);
+      std::vector<int> full_member(pg.n_pairs, 0);
+      for (const Ent& e : ent[b]) if (e.leaf && is_full(e) && e.ref != kPadRef && pair_of(e.ref) >= 0) full_member[pair_of(e.ref)]++;
+      std::vector<char> emitted(pg.n_pairs, 0);
       for (const Ent& e : ent[b]) {
-        if (e.leaf && is_full(e) && pair_of[e.ref] >= 0 && full_member[pair_of[e.ref]] == 2) {
-          if (emitted[pair_of[e.ref]]) continue;
-          emitted[pair_of[e.ref]] = 1;
-          Ent pe = e; pe.ref = kPairRef + pair_of[e.ref];
+        if (e.leaf && is_full(e) && pair_of(e.ref) >= 0 && full_member[pair_of(e.ref)] == 2) {
+          if (emitted[pair_of(e.ref)]) continue;
+          emitted[pair_of(e.ref)] = 1;
+          Ent pe = e; pe.ref = kPairRef + pair_of(e.ref);
           list.push_back(pe);
         } else list.push_back(e);
       }
@@ -535,7 +563,7 @@ Program build_program(const Tree& t, int R, bool deep) {
       const uint32_t live = (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
       int ref = e.ref; uint32_t mk = live;
       if (padrec) ref = pg.n_slots;
-      else if (c == 1) { int pid = e.ref - kPairRef; ref = pid; mk = (uint32_t)pg.pair_pos[2 * pid] | ((uint32_t)pg.pair_pos[2 * pid + 1] << 16); }
+      else if (c == 1) { ref = e.ref - kPairRef; mk = 0; }
       else if (c == 2) { mk = 0; }                        // ref = bit position
       else if (c == 3) { ref = e.ref >> 5; mk = 1u << (e.ref & 31); }
       else if (c >= 4) {
@@ -569,6 +597,24 @@ Program build_program(const Tree& t, int R, bool deep) {
   // + node ops (8 merge + 2 renorm), block ends (~3 per slice), epilogue (~60), class sums (~2 per frontier node)
   pg.fp64_instr_per_eval = fp64 + 10.0 * (nl - 1) + 3.0 * S + 60 + 0.4 * nl;
   return pg;
+}
+
+std::vector<uint32_t> permute_patterns(const Program& pg, const uint32_t* rows, long long n, int n_words) {
+  std::vector<uint32_t> out((size_t)n * n_words, 0u);
+  const int nl = (int)pg.leaf_perm.size();
+  for (long long j = 0; j < n; j++) {
+    const uint32_t* src = rows + (size_t)j * n_words;
+    uint32_t* dst = out.data() + (size_t)j * n_words;
+    for (int w = 0; w < n_words; w++) {
+      uint32_t bits = src[w];
+      while (bits) {  // set bits only: pangenome rows are sparse
+        const int k = w * 32 + __builtin_ctz(bits);
+        bits &= bits - 1;
+        if (k < nl) { const int d = pg.leaf_perm[k]; dst[d >> 5] |= 1u << (d & 31); }
+      }
+    }
+  }
+  return out;
 }
 
 }  // namespace ppm

@@ -58,10 +58,20 @@ struct NodeOp {
   int32_t lref, rref;   // >=0: slot holding the child's Mobile partials; <0: leaf, bit position = -(ref+1)
   int32_t dst;          // slot of the new node, -1 for the root (never alive in an interval)
   int32_t i0;           // first slice of the current block at which the node is alive (0..R); R = none
-  int32_t pad;
+  int32_t pair;         // cherries of a u-form program (both children leaves): their static pair id, else -1
+};
+// What the sweep reads per node op (the NodeOp fields above serve the prepass and the class sums)
+struct SweepOp {
+  int32_t lslot, rslot;  // slot of an internal child (0 for a leaf child)
+  int32_t lbit, rbit;    // leaf child: (pattern word << 5) | rotation that lands its bit on bit 4; 0 for an internal child
+                         // cherry: (pattern word << 5) | rotation that lands its 2-bit observation pair on bits 4..5
+  int32_t dst, i0;       // as NodeOp
+  int32_t flags;         // bit 0: left child is a leaf, bit 1: right child is a leaf
+  int32_t pair;          // as NodeOp
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
-  int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0;
+  int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end;
+  int32_t opc;  // [op0,opc): cherries served from the per-parameter cherry table, [opc,op1): general node ops
 };
 struct Program {
   int R = 8;
@@ -69,10 +79,16 @@ struct Program {
   bool deep = false;
   std::vector<BlockDescHost> blk;                 // [n_blocks+1]; blk[n_blocks] carries the node ops after the last block
   std::vector<NodeOp> ops;
+  std::vector<SweepOp> sops;                      // [ops.size()]
+  std::vector<int32_t> cherry_op;                 // [n_cherries] op index of each cherry pair
   std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
   std::vector<uint32_t> entry_mask;               // see EntryRec::mask
   std::vector<int32_t> entry_node, entry_block;   // node id / block of each entry (for the K table)
-  std::vector<int32_t> pair_pos;                  // [2*n_pairs] bit positions of the leaves paired for the u-form quadratics
+  // Device patterns are stored in PROGRAM leaf order: the two leaves of static pair p (u-form quadratics; cherries
+  // are the first n_cherries pairs) own bits 2p, 2p+1, unpaired leaves follow.
+  std::vector<int32_t> leaf_perm;                 // [n_leaves] preorder leaf index -> device bit position
+  std::vector<int32_t> leaf_node_dev;             // [n_leaves] device bit position -> node id
+  int n_pairs = 0, n_cherries = 0;
   bool leaf_u = false;                            // leaves are (numerically) at height 0: u-form entries are used
   int64_t n_full = 0, n_partial = 0;
   // modelled FP64 instruction count per pattern-eval of the main kernel
@@ -81,5 +97,7 @@ struct Program {
 // deep: pad every block's fully-alive lineage segment to a multiple of 4 records with padding records that refer
 // to the constant row (slot index n_slots) -- needed by the global-memory sweep variant's four-deep prefetch
 Program build_program(const Tree& t, int R, bool deep = false);
+// rows: n row-major bit-packed patterns in preorder leaf order (Patterns::words) -> the same rows in program leaf order
+std::vector<uint32_t> permute_patterns(const Program& pg, const uint32_t* rows, long long n, int n_words);
 
 }  // namespace ppm

@@ -185,6 +185,16 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
 // One thread per (parameter vector, entry or padded slice): the exp tables of the Mobile integral.
 // recs[e] = { K = pi1*exp(-(g2+l2)*(t_block - h_lineage)), ref, slice mask }; yy[j] = exp(-(g2+l2)*(t_j - t_block)),
 // zero for the padding slices of the last block.
+// Mobile merge of two child lineages given as (a, d) = (m0 + pi1 (m1-m0), m1-m0) ... the children's stored form is
+// (x, y) with m0 = x - k0 y, m1 = x + k1 y along their branches (objects.cpp:427-435 in the linear domain);
+// orc = {k0_l, k1_l, k0_r, k1_r}.  Returns the parent's (a, d), not yet renormalised.
+PPM_HD void merge_children(double2 L, double2 Rr, const double* orc, double pi1, double& av, double& d) {
+  const double m0 = fma(-orc[0], L.y, L.x) * fma(-orc[2], Rr.y, Rr.x);
+  const double m1 = fma(orc[1], L.y, L.x) * fma(orc[3], Rr.y, Rr.x);
+  d = m1 - m0;
+  av = fma(pi1, d, m0);
+}
+
 PPM_HD double pack2i(int lo, int hi) {
   const long long b = ((long long)hi << 32) | (long long)(uint32_t)lo;
   double d; memcpy(&d, &b, 8);
@@ -207,7 +217,7 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     r.mask = m.entry_mask[i];
     if (i >= m.blk[b].e_pair0 && i < m.blk[b].e_leafu0) {
       // leaf-pair record: K is not needed (u-form); its 8 bytes carry the byte offsets the sweep would otherwise
-      // compute per entry -- low word: the pair's observation word row in the item's `cw` block, high word: the pair's
+      // compute per entry -- low word: the pair's observation word row in the item's pattern block, high word: the pair's
       // row in pairq -- and mask the rotation that lands the 2-bit observation pair on bits 5..6 (x 32 bytes)
       const int pid = r.ref;
       r.K = pack2i((pid >> 4) * PPM_LANES * 4, pid * 4 * (int)sizeof(double4));
@@ -257,10 +267,22 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
       const int pr = k - m.n_leaves;
       for (int c = 0; c < 4; c++) {
         double a1, b1, a2, b2;
-        leaf_term(m.pair_pos[2 * pr], c & 1, a1, b1);
-        leaf_term(m.pair_pos[2 * pr + 1], c >> 1, a2, b2);
+        leaf_term(2 * pr, c & 1, a1, b1);  // pair pr owns pattern bits 2pr, 2pr+1
+        leaf_term(2 * pr + 1, c >> 1, a2, b2);
         t.pairq[((size_t)p * m.n_pairs + pr) * 4 + c] = make_double4(a1 * a2, a1 * b2 + a2 * b1, b1 * b2, 0.);
       }
+    }
+  } else if (i <= m.n_entries + n_pad + m.n_ops + m.n_leaves + m.n_pairs + m.n_cherries) {
+    // cherry node = merge of two leaf tables (same arithmetic as merge_children in the sweep), for the 4 observation pairs
+    const int c = i - m.n_entries - n_pad - m.n_ops - m.n_leaves - m.n_pairs - 1;
+    const NodeOpDev op = m.ops[m.cherry_op[c]];
+    const double2 kl = t.kap[(size_t)p * m.n_nodes + op.lnode], kr = t.kap[(size_t)p * m.n_nodes + op.rnode];
+    const double orc[4] = {kl.x, kl.y, kr.x, kr.y};
+    const double2* leaftab = reinterpret_cast<const double2*>(t.scal + (size_t)p * SC_COUNT + SC_LA0);
+    for (int x = 0; x < 4; x++) {
+      double av, d;
+      merge_children(leaftab[x & 1], leaftab[x >> 1], orc, pi1, av, d);
+      t.cherry[((size_t)p * m.n_cherries + c) * 4 + x] = make_double2(av, d);
     }
   }
 }
@@ -375,8 +397,7 @@ struct SlotsTmem {
 
 template <class Slots>
 struct ItemMem {
-  uint32_t* sw;
-  uint32_t* cw;   // [ceil(n_pairs/16)][lanes]: the 2-bit observation pair of every leaf pair, 16 pairs per word
+  uint32_t* sw;   // [n_words][lanes] the item's patterns in program leaf order (pair p = bits 2p, 2p+1)
   Slots slots;
 };
 
@@ -385,7 +406,7 @@ struct ItemMem {
 struct ItemTables {
   const EntryRec* recs;   // [n_entries + 1]
   const BlockDesc* blk;   // [n_blocks + 1]
-  const NodeOpDev* ops;   // [n_ops]
+  const SweepOpDev* ops;   // [n_ops]
   const double* oprec;    // [n_ops][OPREC_DOUBLES]
   const double* yy;       // [n_blocks * R]
   const double* wt;       // [n_blocks * R]
@@ -393,7 +414,7 @@ struct ItemTables {
   const double* uu;       // [n_blocks * R]
   const double2* leafab;  // [n_leaves][2] u-form leaf terms {alpha, beta}
   const double4* pairq;   // [n_pairs][4] u-form pair quadratics
-  const int* pair_pos;    // [2*n_pairs] bit positions of the leaves of each pair
+  const double2* cherry;  // [n_cherries][4] cherry node partials by observation pair
 };
 
 // the two 32-bit halves of a record's K field (leaf-pair records)
@@ -518,24 +539,6 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     for (int w = 0; w < m.n_words; w++)
       mem[q].sw[w * PPM_LANES + lane] = (a.mode == 1 || !active[q]) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
   ppm_syncwarp();
-  // observation pair (bit A | bit B << 1) of every static leaf pair, packed 16 pairs per word: the pair entries of all
-  // blocks then need one load + shift instead of two bit extractions each
-#pragma unroll
-  for (int q = 0; q < NI; q++) {
-    for (int w0 = 0; w0 < m.n_pairs; w0 += 16) {
-      uint32_t acc = 0u;
-      const int w1 = (w0 + 16 < m.n_pairs) ? w0 + 16 : m.n_pairs;
-      for (int pr = w0; pr < w1; pr++) {
-        const int pa = T.pair_pos[2 * pr], pb = T.pair_pos[2 * pr + 1];
-        const uint32_t ba = (mem[q].sw[(pa >> 5) * PPM_LANES + lane] >> (pa & 31)) & 1u;
-        const uint32_t bb = (mem[q].sw[(pb >> 5) * PPM_LANES + lane] >> (pb & 31)) & 1u;
-        acc |= (ba | (bb << 1)) << (2 * (pr - w0));
-      }
-      mem[q].cw[(w0 >> 4) * PPM_LANES + lane] = acc;
-    }
-  }
-  ppm_syncwarp();
-
   const double pi1 = sc[SC_PI1];
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
   if (DEEP) {
@@ -562,51 +565,62 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
         for (int i = 0; i < R; i++) { prod[q][i] = 1.; ex[q][i] = X[q]; }
     }
-    // ---- node ops: form every node born before the end of this block.  T.leaftab[bit] holds the leaf partials for
-    // observation 0 / 1, so a child that is a leaf is fetched through a selected pointer exactly like an internal
-    // lineage (one load, no per-value selects).
-    for (int o = bd.op0; o < bd.op1; o++) {
-      const NodeOpDev op = T.ops[o];
+    // ---- node ops: form every node born before the end of this block.
+    // store a new lineage (a, d); when it has become small its mantissa is brought back to [0.5,1) and the shift
+    // goes to X / ex[] (one integer test per lane on the high words; the exact shift only on the rare path)
+    auto store_node = [&](int q, int dst, int i0, double av, double d) {
+      const int ha = ppm_double2hiint(av) & 0x7fffffff, hd = ppm_double2hiint(d) & 0x7fffffff;
+      const int h = ha > hd ? ha : hd;
+      const bool small = (uint32_t)(h - 0x00100000) < (uint32_t)(((1023 - 40) << 20) - 0x00100000);  // 0 < exponent < 983
+      if (ppm_any(small)) {
+        const int k = small ? 1022 - (h >> 20) : 0;
+        const double sfac = pow2i(k);
+        av *= sfac; d *= sfac;
+        X[q] += k;
+        if (real) {
+#pragma unroll
+          for (int i = 0; i < R; i++) if (i >= i0) ex[q][i] += k;
+        }
+      }
+      mem[q].slots.st(dst, lane, make_double2(av, d));  // every lane reads back only its own slot column
+    };
+    // cherries: both children are leaves, so the node is one of four per-parameter values picked by the 2-bit
+    // observation pair (bits 2p, 2p+1 of the pattern; the record carries word and rotation)
+    for (int o = bd.op0; o < bd.opc; o++) {
+      const SweepOpDev op = T.ops[o];
+#pragma unroll
+      for (int q = 0; q < NI; q++) {
+        const uint32_t w = mem[q].sw[(op.lbit >> 5) * PPM_LANES + lane];
+        const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.cherry + op.pair * 4) + (rotr32(w, (uint32_t)op.lbit) & 0x30u));
+        store_node(q, op.dst, op.i0, v.x, v.y);
+      }
+    }
+    // general merges: a leaf child comes from the two-entry leaf table (picked by its pattern bit), an internal one
+    // from its slot; both are fetched, the record's flags keep one (no branches in this latency-bound chain)
+    for (int o = bd.opc; o < bd.op1; o++) {
+      const SweepOpDev op = T.ops[o];
       const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
-      const bool lleaf = op.lref < 0, rleaf = op.rref < 0;
-      const int lpos = lleaf ? -(op.lref + 1) : 0, rpos = rleaf ? -(op.rref + 1) : 0;
-      const int lslot = lleaf ? 0 : op.lref, rslot = rleaf ? 0 : op.rref;
+      const bool lleaf = op.flags & 1, rleaf = op.flags & 2;
       double2 L[NI], Rr[NI];
 #pragma unroll
       for (int q = 0; q < NI; q++) {
-        const uint32_t bl = (mem[q].sw[(lpos >> 5) * PPM_LANES + lane] >> (lpos & 31)) & 1u;
-        const uint32_t br = (mem[q].sw[(rpos >> 5) * PPM_LANES + lane] >> (rpos & 31)) & 1u;
-        // leaf children come from the two-entry leaf table, internal ones from their slot (both fetched, one kept)
         double2 ls, rs;
-        mem[q].slots.ld_async(lslot, lane, ls);
-        mem[q].slots.ld_async(rslot, lane, rs);
-        const double2 lt = T.leaftab[bl], rt = T.leaftab[br];
+        mem[q].slots.ld_async(op.lslot, lane, ls);
+        mem[q].slots.ld_async(op.rslot, lane, rs);
+        const uint32_t wl = mem[q].sw[(op.lbit >> 5) * PPM_LANES + lane], wr = mem[q].sw[(op.rbit >> 5) * PPM_LANES + lane];
+        const double2 lt = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.leaftab) + (rotr32(wl, (uint32_t)op.lbit) & 0x10u));
+        const double2 rt = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.leaftab) + (rotr32(wr, (uint32_t)op.rbit) & 0x10u));
         mem[q].slots.wait_async(ls);
         mem[q].slots.wait_async(rs);
         L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
         Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
       }
+      if (op.dst >= 0) {
 #pragma unroll
-      for (int q = 0; q < NI; q++) {
-        if (op.dst >= 0) {
-          // Mobile merge (objects.cpp:427-435 in linear domain)
-          double m0 = fma(-orc[0], L[q].y, L[q].x) * fma(-orc[2], Rr[q].y, Rr[q].x);
-          double m1 = fma(orc[1], L[q].y, L[q].x) * fma(orc[3], Rr[q].y, Rr[q].x);
-          double d = m1 - m0;
-          double av = fma(pi1, d, m0);
-          // renormalise when the lineage has become small: mantissa in [0.5,1), shift goes to X / ex[]
-          int be = biased_exp(fmax(fabs(av), fabs(d)));
-          int k = (be != 0 && be < 1023 - 40) ? 1022 - be : 0;
-          if (ppm_any(k != 0)) {
-            double sfac = pow2i(k);
-            av *= sfac; d *= sfac;
-            X[q] += k;
-            if (real) {
-#pragma unroll
-              for (int i = 0; i < R; i++) if (i >= op.i0) ex[q][i] += k;
-            }
-          }
-          mem[q].slots.st(op.dst, lane, make_double2(av, d));  // every lane reads back only its own slot column
+        for (int q = 0; q < NI; q++) {
+          double av, d;
+          merge_children(L[q], Rr[q], orc, pi1, av, d);
+          store_node(q, op.dst, op.i0, av, d);
         }
       }
     }
@@ -772,12 +786,12 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       uint32_t cb[NI];   // observation pair of the current record's pair, per item
       int pid = (int)(ref & 0xffffu);
 #pragma unroll
-      for (int q = 0; q < NI; q++) cb[q] = (mem[q].cw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
+      for (int q = 0; q < NI; q++) cb[q] = (mem[q].sw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
       if (!factored) {
-        // record = {cw byte offset, pairq byte offset, pair id, rotation}: word, rotate, mask, row -- no index arithmetic
+        // record = {pattern word byte offset, pairq byte offset, pair id, rotation}: word, rotate, mask, row -- no index arithmetic
         const char* cwl[NI];
 #pragma unroll
-        for (int q = 0; q < NI; q++) cwl[q] = reinterpret_cast<const char*>(mem[q].cw + lane);
+        for (int q = 0; q < NI; q++) cwl[q] = reinterpret_cast<const char*>(mem[q].sw + lane);
         const char* pq = reinterpret_cast<const char*>(T.pairq);
         double4 qv[NI];
 #pragma unroll
@@ -808,7 +822,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         }
       } else {  // pi1 close to 1: two linear factors keep full accuracy
         for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
-          const int pa = T.pair_pos[2 * pid], pb = T.pair_pos[2 * pid + 1];
+          const int pa = 2 * pid, pb = 2 * pid + 1;
 #pragma unroll
           for (int q = 0; q < NI; q++) {
             const double2 fa = T.leafab[pa * 2 + (int)(cb[q] & 1u)], fb = T.leafab[pb * 2 + (int)(cb[q] >> 1)];
@@ -819,7 +833,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           pid = (int)(ref & 0xffffu);
           pid = pid < pmax ? pid : pmax;
 #pragma unroll
-          for (int q = 0; q < NI; q++) cb[q] = (mem[q].cw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
+          for (int q = 0; q < NI; q++) cb[q] = (mem[q].sw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
           if (((e - bd.e_pair0) & 7) == 7) {
 #pragma unroll
             for (int q = 0; q < NI; q++)

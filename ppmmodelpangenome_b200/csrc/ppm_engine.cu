@@ -68,7 +68,7 @@ struct ppm_engine {
   double n_launches = 0;
 
   // device model
-  DevBuf<int> d_leaf_node, d_pair_pos, d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
+  DevBuf<int> d_leaf_node, d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
   DevBuf<ppm::BlockDesc> d_blk;
   DevBuf<uint32_t> d_entry_mask;
   DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt;
@@ -82,6 +82,9 @@ struct ppm_engine {
   int P_cap = 0;
   DevBuf<ppm::EntryRec> d_recs;
   DevBuf<double4> d_pairq;
+  DevBuf<double2> d_cherry;
+  DevBuf<ppm::SweepOpDev> d_sops;
+  DevBuf<int> d_cherry_op;
   DevBuf<double2> d_leafab;
   DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
   DevBuf<double4> d_cls;
@@ -131,18 +134,25 @@ struct ppm_engine {
     std::vector<ppm::NodeOpDev> ops(prog.ops.size());
     if (!ops.empty()) std::memcpy(ops.data(), prog.ops.data(), ops.size() * sizeof(ppm::NodeOp));
     d_ops.upload(ops, stream);
+    static_assert(sizeof(ppm::SweepOpDev) == sizeof(ppm::SweepOp), "SweepOp layout");
+    std::vector<ppm::SweepOpDev> sops(prog.sops.size());
+    if (!sops.empty()) std::memcpy(sops.data(), prog.sops.data(), sops.size() * sizeof(ppm::SweepOp));
+    d_sops.upload(sops, stream);
+    { std::vector<int> co(prog.cherry_op); if (co.empty()) co.assign(1, 0); d_cherry_op.upload(co, stream); }
     std::vector<ppm::BlockDesc> blk(prog.blk.size());
     std::memcpy(blk.data(), prog.blk.data(), blk.size() * sizeof(ppm::BlockDesc));
     d_blk.upload(blk, stream);
     d_entry_ref.upload(prog.entry_ref, stream); d_entry_mask.upload(prog.entry_mask, stream);
     d_entry_node.upload(prog.entry_node, stream); d_entry_block.upload(prog.entry_block, stream);
-    d_leaf_node.upload(tree.leaf_node, stream);
-    { std::vector<int> pp(prog.pair_pos.begin(), prog.pair_pos.end()); if (pp.empty()) pp.assign(2, 0); pp.resize((pp.size() + 3) / 4 * 4, 0); d_pair_pos.upload(pp, stream); }  // (padded: copied 16 bytes at a time)
+    d_leaf_node.upload(prog.leaf_node_dev, stream);
     // patterns of this shard, word-major so that lanes (= consecutive patterns) read consecutive addresses
     n_pat_pad = (count + 31) / 32 * 32;
     std::vector<uint32_t> wm((size_t)pat.n_words * std::max<long long>(n_pat_pad, 32), 0u);
-    for (long long j = 0; j < count; j++)
-      for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * n_pat_pad + j] = pat.words[(size_t)(first + j) * pat.n_words + w];
+    {  // bits in program leaf order (host_model.h: Program::leaf_perm)
+      const std::vector<uint32_t> rows = ppm::permute_patterns(prog, pat.words.data() + (size_t)first * pat.n_words, count, pat.n_words);
+      for (long long j = 0; j < count; j++)
+        for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * n_pat_pad + j] = rows[(size_t)j * pat.n_words + w];
+    }
     d_words.upload(wm, stream);
     std::vector<uint32_t> zeros((size_t)pat.n_words * 32, 0u);
     d_zero_words.upload(zeros, stream);
@@ -159,8 +169,8 @@ struct ppm_engine {
     md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
     md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p;
     md.slice_t = d_slice_t.p; md.slice_wt_pad = d_slice_wt.p;
-    md.blk = d_blk.p; md.ops = d_ops.p;
-    md.n_pairs = (int)prog.pair_pos.size() / 2; md.leaf_node = d_leaf_node.p; md.pair_pos = d_pair_pos.p;
+    md.blk = d_blk.p; md.ops = d_ops.p; md.sops = d_sops.p; md.cherry_op = d_cherry_op.p; md.n_cherries = prog.n_cherries;
+    md.n_pairs = prog.n_pairs; md.leaf_node = d_leaf_node.p;
     md.entry_ref = d_entry_ref.p; md.entry_mask = d_entry_mask.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
     md.words = d_words.p; md.n_pat = count; md.n_pat_pad = n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
@@ -173,14 +183,15 @@ struct ppm_engine {
       d_recs.alloc((size_t)P * (prog.entry_ref.size() + 1)); d_yy.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
       d_oprec.alloc((size_t)P * std::max<size_t>(prog.ops.size(), 1) * ppm::OPREC_DOUBLES);
       d_uu.alloc((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
-      d_leafab.alloc((size_t)P * tree.n_leaves * 2); d_pairq.alloc((size_t)P * std::max<size_t>(prog.pair_pos.size() / 2, 1) * 4);
+      d_leafab.alloc((size_t)P * tree.n_leaves * 2); d_pairq.alloc((size_t)P * std::max<size_t>(prog.n_pairs, 1) * 4);
+      d_cherry.alloc((size_t)P * std::max<size_t>(prog.n_cherries, 1) * 4);
       d_clsT.alloc((size_t)P * nn); d_a01.alloc((size_t)P * std::max<long long>(n_pat_pad, 32));
       d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 6 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       P_cap = P;
     }
     ppm::TablesDev t{};
-    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p;
+    t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p; t.cherry = d_cherry.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p;
     return t;
   }

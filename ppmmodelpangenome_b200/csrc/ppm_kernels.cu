@@ -57,27 +57,27 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 static const size_t kRecRingBytes = 3 * 32 * sizeof(EntryRec);  // per-warp record ring of the global-memory variant
 
 struct StageLayout {
-  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, pairpos, leaf, total;
+  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, cherry, leaf, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
   size_t o = 0;
   L.recs = o; o += align16((size_t)(m.n_entries + 1) * sizeof(EntryRec));
   L.blk = o;  o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
-  L.ops = o;  o += align16((size_t)m.n_ops * sizeof(NodeOpDev));
+  L.ops = o;  o += align16((size_t)m.n_ops * sizeof(SweepOpDev));
   L.oprec = o; o += align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double));
   L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.uu = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.leafab = o; o += align16((size_t)m.n_leaves * 2 * sizeof(double2));
   L.pairq = o; o += align16((size_t)m.n_pairs * 4 * sizeof(double4));
-  L.pairpos = o; o += align16((size_t)(m.n_pairs > 0 ? m.n_pairs : 1) * 2 * sizeof(int));
+  L.cherry = o; o += align16((size_t)m.n_cherries * 4 * sizeof(double2));
   L.leaf = o; o += 32;
   L.total = o;
   return L;
 }
-// per item and warp: pattern words [n_words][32] + observation-pair words [ceil(n_pairs/16)][32]
-__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16(((size_t)m.n_words + (size_t)((m.n_pairs + 15) / 16)) * 32 * 4); }
+// per item and warp: pattern words [n_words][32]
+__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16((size_t)m.n_words * 32 * 4); }
 
 template <int MODE>
 __device__ __forceinline__ void init_slots(SlotsMem& s, double2* smem_slots, double2* global_slots, uint32_t, int, int, int, int) {
@@ -137,7 +137,6 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep
   for (int q = 0; q < NI; q++) {
     unsigned char* ib = wbase + (size_t)q * per_item;
     mem[q].sw = reinterpret_cast<uint32_t*>(ib);
-    mem[q].cw = mem[q].sw + m.n_words * 32;
     init_slots<MODE>(mem[q].slots, reinterpret_cast<double2*>(ib + head),
                      a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32,
                      tmem_base_s, warp, wpc, q, nt);
@@ -162,19 +161,19 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep
     if (STAGED) {
       copy16(smem_raw + L.recs, a.t.recs + (size_t)p * (m.n_entries + 1), align16((size_t)(m.n_entries + 1) * sizeof(EntryRec)));
       copy16(smem_raw + L.blk, m.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc)));
-      copy16(smem_raw + L.ops, m.ops, align16((size_t)m.n_ops * sizeof(NodeOpDev)));
+      copy16(smem_raw + L.ops, m.sops, align16((size_t)m.n_ops * sizeof(SweepOpDev)));
       copy16(smem_raw + L.oprec, a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES, align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)));
       copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.uu, a.t.uu + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.leafab, a.t.leafab + (size_t)p * m.n_leaves * 2, align16((size_t)m.n_leaves * 2 * sizeof(double2)));
       copy16(smem_raw + L.pairq, a.t.pairq + (size_t)p * m.n_pairs * 4, align16((size_t)m.n_pairs * 4 * sizeof(double4)));
-      copy16(smem_raw + L.pairpos, m.pair_pos, align16((size_t)(m.n_pairs > 0 ? m.n_pairs : 1) * 2 * sizeof(int)));
+      copy16(smem_raw + L.cherry, a.t.cherry + (size_t)p * m.n_cherries * 4, align16((size_t)m.n_cherries * 4 * sizeof(double2)));
       copy16(smem_raw + L.leaf, a.t.scal + (size_t)p * SC_COUNT + SC_LA0, 32);
       __syncthreads();
       T.recs = reinterpret_cast<const EntryRec*>(smem_raw + L.recs);
       T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + L.blk);
-      T.ops = reinterpret_cast<const NodeOpDev*>(smem_raw + L.ops);
+      T.ops = reinterpret_cast<const SweepOpDev*>(smem_raw + L.ops);
       T.oprec = reinterpret_cast<const double*>(smem_raw + L.oprec);
       T.yy = reinterpret_cast<const double*>(smem_raw + L.yy);
       T.wt = reinterpret_cast<const double*>(smem_raw + L.wt);
@@ -182,10 +181,10 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep
       T.uu = reinterpret_cast<const double*>(smem_raw + L.uu);
       T.leafab = reinterpret_cast<const double2*>(smem_raw + L.leafab);
       T.pairq = reinterpret_cast<const double4*>(smem_raw + L.pairq);
-      T.pair_pos = reinterpret_cast<const int*>(smem_raw + L.pairpos);
+      T.cherry = reinterpret_cast<const double2*>(smem_raw + L.cherry);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
-      T.blk = m.blk; T.ops = m.ops;
+      T.blk = m.blk; T.ops = m.sops;
       T.oprec = a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES;
       T.yy = a.t.yy + (size_t)p * nbR;
       T.wt = m.slice_wt_pad;
@@ -193,7 +192,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep
       T.uu = a.t.uu + (size_t)p * nbR;
       T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
       T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
-      T.pair_pos = m.pair_pos;
+      T.cherry = a.t.cherry + (size_t)p * m.n_cherries * 4;
       __syncthreads();
     }
     while (true) {
@@ -248,7 +247,7 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
   prepass_nodes_kernel<<<t.P, 128, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops + m.n_leaves + m.n_pairs;
+  int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops + m.n_leaves + m.n_pairs + m.n_cherries;
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }
@@ -320,6 +319,9 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   else pl.grid_x = (int)std::max<long long>(1, std::min<long long>(n_sm, (total + warps - 1) / warps));
   pl.items_per_warp = (int)((total + (long long)pl.grid_x * warps - 1) / ((long long)pl.grid_x * warps));  // informational
   pl.n_chunks = 1;
+  if (std::getenv("PPM_PLAN_DEBUG"))
+    fprintf(stderr, "[ppm plan] tables %zu B, head %zu B, slots %d, per warp %zu B, w0 %d, w1 %d -> mode %d, %d warps, grid %d (budget %zu)\n",
+            L.total, head, m.n_slots, pl.per_warp_bytes, w0, w1, pl.mode, warps, pl.grid_x, budget);
   pl.smem_bytes = (pl.staged ? L.total : 0) + pl.per_warp_bytes * warps;
   return pl;
 }

@@ -23,7 +23,10 @@ enum {
 static_assert(SC_IZ_E < SC_COUNT && SC_COUNT % 2 == 0 && SC_LA0 % 2 == 0, "scal row layout");
 
 struct NodeOpDev {  // == ppm::NodeOp
-  int32_t node, lnode, rnode, lref, rref, dst, i0, pad;
+  int32_t node, lnode, rnode, lref, rref, dst, i0, pair;
+};
+struct __align__(16) SweepOpDev {  // == ppm::SweepOp (host_model.h): what the sweep reads per node op
+  int32_t lslot, rslot, lbit, rbit, dst, i0, flags, pair;
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
   // [e_slot0,e_pair0)   internal lineages alive in every slice (partials in slots)
@@ -31,7 +34,8 @@ struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in orde
   // [e_leafu0,e_leaf0)  single leaves alive in every slice, linear in u
   // [e_leaf0,e_pleaf0)  single leaves alive in every slice, block-relative K/Y form (trees with tall leaves only)
   // [e_pleaf0,e_pslot0) leaves merged inside the block | [e_pslot0,e_end) internal lineages born/merged inside it
-  int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end, pad0;
+  // node ops: [op0,opc) cherries read from the cherry table, [opc,op1) general merges
+  int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end, opc;
 };
 struct __align__(16) EntryRec {
   double K;       // pi1 * exp(-(g2+l2) * (t_block - h_lineage))   (per parameter vector)
@@ -45,8 +49,7 @@ enum { OPREC_DOUBLES = 4 };  // per (parameter vector, node op): kap_l{x,y} kap_
 struct ModelDev {
   int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
   int n_pairs;  // static leaf pairs (u-form quadratics)
-  const int* leaf_node;  // [n_leaves] bit position -> node id
-  const int* pair_pos;   // [2*n_pairs] bit positions of the two leaves of a pair
+  const int* leaf_node;  // [n_leaves] pattern bit position (program leaf order: pair p = bits 2p, 2p+1) -> node id
   int deep;  // program built for the global-memory variant: lineage segments padded to multiples of 4 records
   double H;
   long long n_obs;
@@ -61,6 +64,8 @@ struct ModelDev {
   // program
   const BlockDesc* blk;     // [n_blocks + 1]; the last one only carries the tail node ops
   const NodeOpDev* ops;
+  const SweepOpDev* sops;   // [n_ops]
+  const int* cherry_op; int n_cherries;  // op index of each cherry (the first n_cherries static pairs)
   const int* entry_ref; const uint32_t* entry_mask; const int* entry_node; const int* entry_block;  // [n_entries]
   // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq
   const uint32_t* words; long long n_pat, n_pat_pad;
@@ -80,6 +85,7 @@ struct TablesDev {
   double* oprec;         // [P][n_ops][OPREC_DOUBLES]
   double* uu;            // [P][n_blocks*R] u_j = 1 - exp(-(g2+l2) t_j), 0 for padding slices
   double2* leafab;       // [P][n_leaves][2] leaf term = alpha + beta*u for observation 0 / 1
+  double2* cherry;       // [P][n_cherries][4] (a, d) of a cherry node for the 4 observation pairs (left | right << 1)
   double4* pairq;        // [P][n_pairs][4] pair term = q.x + q.y*u + q.z*u^2 for the 4 bit combinations (A | B<<1)
   double2* clsT;         // [n_nodes][P] {cat0, cat1} frontier factors F_c = T_c - sum of S over the subtree of c
   double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)

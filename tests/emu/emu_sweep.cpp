@@ -35,8 +35,11 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     const long long count = pat.n_patterns;
     if (out_npat) *out_npat = count;
     std::vector<uint32_t> wm((size_t)pat.n_words * count);
-    for (long long j = 0; j < count; j++)
-      for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * count + j] = pat.words[(size_t)j * pat.n_words + w];
+    {
+      const std::vector<uint32_t> rows = permute_patterns(prog, pat.words.data(), count, pat.n_words);
+      for (long long j = 0; j < count; j++)
+        for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * count + j] = rows[(size_t)j * pat.n_words + w];
+    }
     std::vector<uint32_t> zeros(pat.n_words * 32, 0u);
     static_assert(sizeof(NodeOpDev) == sizeof(NodeOp), "layout");
     static_assert(sizeof(BlockDesc) == sizeof(BlockDescHost), "layout");
@@ -54,11 +57,13 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     md.slice_t = tree.slice_t.data(); md.slice_wt_pad = wt_pad.data();
     md.blk = reinterpret_cast<const BlockDesc*>(prog.blk.data());
     md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data());
+    static_assert(sizeof(SweepOpDev) == sizeof(SweepOp), "layout");
+    md.sops = reinterpret_cast<const SweepOpDev*>(prog.sops.data());
+    std::vector<int> cherry_op(prog.cherry_op); if (cherry_op.empty()) cherry_op.assign(1, 0);
+    md.cherry_op = cherry_op.data(); md.n_cherries = prog.n_cherries;
     md.entry_ref = prog.entry_ref.data(); md.entry_mask = prog.entry_mask.data();
     md.entry_node = prog.entry_node.data(); md.entry_block = prog.entry_block.data();
-    std::vector<int> pair_pos(prog.pair_pos.begin(), prog.pair_pos.end());
-    if (pair_pos.empty()) pair_pos.assign(2, 0);
-    md.n_pairs = (int)prog.pair_pos.size() / 2; md.leaf_node = tree.leaf_node.data(); md.pair_pos = pair_pos.data();
+    md.n_pairs = prog.n_pairs; md.leaf_node = prog.leaf_node_dev.data();
     md.words = wm.data(); md.n_pat = count; md.n_pat_pad = count;
     md.counts = pat.counts.data(); md.mrca = pat.mrca.data(); md.freq = pat.freq.data(); md.zero_words = zeros.data();
 
@@ -73,18 +78,19 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<uint16_t> frontier(nn);
     std::vector<double> uu((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
     std::vector<double2> leafab((size_t)P * tree.n_leaves * 2);
-    std::vector<double4> pairq((size_t)P * std::max<size_t>(prog.pair_pos.size() / 2, 1) * 4);
+    std::vector<double4> pairq((size_t)P * std::max<size_t>(prog.n_pairs, 1) * 4);
+    std::vector<double2> cherry((size_t)P * std::max<size_t>(prog.n_cherries, 1) * 4);
     std::vector<double> scal((size_t)P * SC_COUNT), zeta((size_t)P * 6 * nn), i2ovr(P);
     TablesDev t{};
-    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data(); t.clsT = clsT.data(); t.a01 = a01.data(); t.uu = uu.data(); t.leafab = leafab.data(); t.pairq = pairq.data();
+    t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data(); t.clsT = clsT.data(); t.a01 = a01.data(); t.uu = uu.data(); t.leafab = leafab.data(); t.pairq = pairq.data(); t.cherry = cherry.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
 
     // two items per "warp" as on the device (NI = 2), one lane each
     const int NI = 2;
-    std::vector<uint32_t> sw(NI * pat.n_words), cw(NI * ((prog.pair_pos.size() / 2 + 15) / 16 + 1));
+    std::vector<uint32_t> sw(NI * pat.n_words);
     std::vector<double2> slotmem(NI * (prog.n_slots + 1));
     ItemMem<SlotsMem> mem[2];
-    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].cw = cw.data() + q * ((prog.pair_pos.size() / 2 + 15) / 16 + 1); mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
+    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
     auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
       SweepArgs a{};
       a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
@@ -93,14 +99,14 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
         double s = 0;
         for (long long bt = 0; bt < a.n_batches; bt += NI) {
           ItemTables T;
-          T.recs = recs.data() + (size_t)p * (md.n_entries + 1); T.blk = md.blk; T.ops = md.ops;
+          T.recs = recs.data() + (size_t)p * (md.n_entries + 1); T.blk = md.blk; T.ops = md.sops;
           T.oprec = oprec.data() + (size_t)p * md.n_ops * OPREC_DOUBLES;
           T.yy = yy.data() + (size_t)p * md.n_blocks * md.R; T.wt = md.slice_wt_pad;
           T.leaftab = reinterpret_cast<const double2*>(scal.data() + (size_t)p * SC_COUNT + SC_LA0);
           T.uu = uu.data() + (size_t)p * md.n_blocks * md.R;
           T.leafab = leafab.data() + (size_t)p * md.n_leaves * 2;
           T.pairq = pairq.data() + (size_t)p * md.n_pairs * 4;
-          T.pair_pos = md.pair_pos;
+          T.cherry = cherry.data() + (size_t)p * md.n_cherries * 4;
           double c[2] = {0., 0.};
           if (deep && prog.R == 8) sweep_items<8, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (deep) throw std::runtime_error("deep emulation built for R = 8");
@@ -116,7 +122,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     };
     for (int p = 0; p < P; p++) prepass_nodes_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++)
-      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops + md.n_leaves + md.n_pairs; i++) prepass_tables_body(md, t, p, i);
+      for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops + md.n_leaves + md.n_pairs + md.n_cherries; i++) prepass_tables_body(md, t, p, i);
     for (long long j = 0; j < count; j++) {
       const int nf = class_frontier(md, md.words + j, (size_t)md.n_pat_pad, zbits.data(), frontier.data());
       for (int p = 0; p < P; p++) a01[(size_t)p * count + j] = class_sums(t, p, frontier.data(), nf);
