@@ -796,29 +796,46 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         double4 qv[NI];
 #pragma unroll
         for (int q = 0; q < NI; q++) qv[q] = T.pairq[pid * 4 + (int)cb[q]];
+        // three-stage software pipeline (record -> pattern word -> table row are dependent shared-memory loads):
+        // iteration e fetches the record of e+3, the word of e+2 and the row of e+1 while pair e is multiplied in
         const int elast = bd.e_leafu0 - 1;
-#pragma unroll 2
-        for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
-          load_rec(T.recs, e < elast ? e + 1 : elast, K, ref, mk);  // (the record behind the segment is not a pair)
+        double K1, K2; uint32_t rot1, rot2;
+        load_rec(T.recs, bd.e_pair0 + 1 < elast ? bd.e_pair0 + 1 : elast, K1, ref, rot1);  // (the record behind the segment is not a pair)
+        load_rec(T.recs, bd.e_pair0 + 2 < elast ? bd.e_pair0 + 2 : elast, K2, ref, rot2);
+        uint32_t w1[NI];
+        {
           int wo, qo;
-          unpack2i(K, wo, qo);
-          double4 qn[NI];
+          unpack2i(K1, wo, qo);
 #pragma unroll
-          for (int q = 0; q < NI; q++) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
-            qn[q] = *reinterpret_cast<const double4*>(pq + qo + (rotr32(w, mk) & 0x60u));
+          for (int q = 0; q < NI; q++) w1[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
+        }
+        for (int e = bd.e_pair0; e <= elast;) {
+          const int ce = (e + 16 <= elast) ? e + 16 : elast + 1;
+#pragma unroll 2
+          for (; e < ce; e++) {
+            double K3; uint32_t rot3;
+            load_rec(T.recs, e + 3 < elast ? e + 3 : elast, K3, ref, rot3);
+            int wo1, qo1, wo2, qo2;
+            unpack2i(K1, wo1, qo1);
+            unpack2i(K2, wo2, qo2);
+            double4 qn[NI];
+            uint32_t w2[NI];
+#pragma unroll
+            for (int q = 0; q < NI; q++) {
+              qn[q] = *reinterpret_cast<const double4*>(pq + qo1 + (rotr32(w1[q], rot1) & 0x60u));
+              w2[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo2);
+            }
+#pragma unroll
+            for (int q = 0; q < NI; q++) {
+#pragma unroll
+              for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
+              qv[q] = qn[q]; w1[q] = w2[q];
+            }
+            K1 = K2; rot1 = rot2; K2 = K3; rot2 = rot3;
           }
 #pragma unroll
-          for (int q = 0; q < NI; q++) {
-#pragma unroll
-            for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
-            qv[q] = qn[q];
-          }
-          if (((e - bd.e_pair0) & 15) == 15) {
-#pragma unroll
-            for (int q = 0; q < NI; q++)
-              if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
-          }
+          for (int q = 0; q < NI; q++)
+            if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
         }
       } else {  // pi1 close to 1: two linear factors keep full accuracy
         for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
