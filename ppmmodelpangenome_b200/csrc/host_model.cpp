@@ -483,7 +483,7 @@ Program build_program(const Tree& t, int R, bool deep) {
     auto mid = std::stable_partition(first, last, [](const NodeOp& op) { return op.pair >= 0; });
     pg.blk[b].opc = (int)(mid - pg.ops.begin());
   }
-  pg.sops.resize(pg.ops.size());
+  pg.sops.assign(pg.ops.size() + 1, SweepOp{});  // + one padding record: the sweep fetches one op ahead
   for (size_t o = 0; o < pg.ops.size(); o++) {
     const NodeOp& op = pg.ops[o];
     SweepOp& s = pg.sops[o];
@@ -594,8 +594,10 @@ Program build_program(const Tree& t, int R, bool deep) {
     BlockDescHost& bd = pg.blk[nb];
     bd.e_slot0 = bd.e_pair0 = bd.e_leafu0 = bd.e_leaf0 = bd.e_pleaf0 = bd.e_pslot0 = bd.e_end = (int)pg.entry_ref.size();
   }
-  // + node ops (8 merge + 2 renorm), block ends (~3 per slice), epilogue (~60), class sums (~2 per frontier node)
-  pg.fp64_instr_per_eval = fp64 + 10.0 * (nl - 1) + 3.0 * S + 60 + 0.4 * nl;
+  // + general node ops (8 per merge; cherries come from a table), block ends (~3 per slice), epilogue (~60)
+  int n_cherry_ops = 0;
+  for (const NodeOp& op : pg.ops) n_cherry_ops += op.pair >= 0;
+  pg.fp64_instr_per_eval = fp64 + 8.0 * ((double)pg.ops.size() - n_cherry_ops) + 3.0 * S + 60;
   return pg;
 }
 

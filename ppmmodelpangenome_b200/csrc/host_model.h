@@ -79,7 +79,7 @@ struct Program {
   bool deep = false;
   std::vector<BlockDescHost> blk;                 // [n_blocks+1]; blk[n_blocks] carries the node ops after the last block
   std::vector<NodeOp> ops;
-  std::vector<SweepOp> sops;                      // [ops.size()]
+  std::vector<SweepOp> sops;                      // [ops.size() + 1] (one padding record)
   std::vector<int32_t> cherry_op;                 // [n_cherries] op index of each cherry pair
   std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
   std::vector<uint32_t> entry_mask;               // see EntryRec::mask

@@ -586,8 +586,10 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     };
     // cherries: both children are leaves, so the node is one of four per-parameter values picked by the 2-bit
     // observation pair (bits 2p, 2p+1 of the pattern; the record carries word and rotation)
+    SweepOpDev opn = T.ops[bd.op0];  // records are fetched one op ahead (the table ends with a padding record)
     for (int o = bd.op0; o < bd.opc; o++) {
-      const SweepOpDev op = T.ops[o];
+      const SweepOpDev op = opn;
+      opn = T.ops[o + 1];
 #pragma unroll
       for (int q = 0; q < NI; q++) {
         const uint32_t w = mem[q].sw[(op.lbit >> 5) * PPM_LANES + lane];
@@ -598,7 +600,8 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // general merges: a leaf child comes from the two-entry leaf table (picked by its pattern bit), an internal one
     // from its slot; both are fetched, the record's flags keep one (no branches in this latency-bound chain)
     for (int o = bd.opc; o < bd.op1; o++) {
-      const SweepOpDev op = T.ops[o];
+      const SweepOpDev op = opn;
+      opn = T.ops[o + 1];
       const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
       const bool lleaf = op.flags & 1, rleaf = op.flags & 2;
       double2 L[NI], Rr[NI];

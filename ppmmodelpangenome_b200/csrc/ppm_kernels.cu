@@ -64,7 +64,7 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   size_t o = 0;
   L.recs = o; o += align16((size_t)(m.n_entries + 1) * sizeof(EntryRec));
   L.blk = o;  o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
-  L.ops = o;  o += align16((size_t)m.n_ops * sizeof(SweepOpDev));
+  L.ops = o;  o += align16((size_t)(m.n_ops + 1) * sizeof(SweepOpDev));
   L.oprec = o; o += align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double));
   L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep
     if (STAGED) {
       copy16(smem_raw + L.recs, a.t.recs + (size_t)p * (m.n_entries + 1), align16((size_t)(m.n_entries + 1) * sizeof(EntryRec)));
       copy16(smem_raw + L.blk, m.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc)));
-      copy16(smem_raw + L.ops, m.sops, align16((size_t)m.n_ops * sizeof(SweepOpDev)));
+      copy16(smem_raw + L.ops, m.sops, align16((size_t)(m.n_ops + 1) * sizeof(SweepOpDev)));
       copy16(smem_raw + L.oprec, a.t.oprec + (size_t)p * m.n_ops * OPREC_DOUBLES, align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)));
       copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
