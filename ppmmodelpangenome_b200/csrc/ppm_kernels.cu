@@ -81,7 +81,7 @@ __host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return al
 
 template <int MODE>
 __device__ __forceinline__ void init_slots(SlotsMem& s, double2* smem_slots, double2* global_slots, uint32_t, int, int, int, int) {
-  s.base = (MODE == 2) ? global_slots : smem_slots;
+  s.base = (MODE == 2 || MODE == 4) ? global_slots : smem_slots;
 }
 template <int MODE>
 __device__ __forceinline__ void init_slots(SlotsTmem& s, double2* smem_slots, double2*, uint32_t tmem_base, int warp, int wpc, int q, int nt) {
@@ -103,12 +103,12 @@ template <> struct SlotsOf<1> { typedef SlotsTmem type; };
 template <> struct SlotsOf<3> { typedef SlotsTmem type; };  // MODE 3 = MODE 1 compiled for 12 warps (168 registers)
 
 template <int R, int NI, int MODE>
-__global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   __shared__ int next_group;  // dynamic hand-out of the unit's warp items: the 4 schedulers of an SM rarely hold equally many warps
   typedef typename SlotsOf<MODE>::type Slots;
-  constexpr bool STAGED = MODE != 2;
+  constexpr bool STAGED = MODE != 2 && MODE != 4;  // MODE 4 = MODE 2 compiled for 12 warps (168 registers)
   constexpr bool TMEM = MODE == 1 || MODE == 3;
   const ModelDev& m = a.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3) ? 384 : 512, 1) sweep
       if (b_begin + g >= b_end) break;
       const long long batch0 = (b_begin + g) * NI;
       double contrib[NI];
-      sweep_items<R, NI, MODE == 2, Slots>(a, T, p, batch0, lane, mem, contrib, wrec);
+      sweep_items<R, NI, !STAGED, Slots>(a, T, p, batch0, lane, mem, contrib, wrec);
       if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
@@ -309,7 +309,9 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   pl.staged = pl.mode != 2;
   if (!pl.staged) {
     pl.per_warp_bytes = NI * head + kRecRingBytes;
-    warps = (int)std::max<size_t>(1, std::min<size_t>(max_warps(), budget / pl.per_warp_bytes));
+    const char* d16 = std::getenv("PPM_DEEP16");
+    warps = (int)std::max<size_t>(1, std::min<size_t>(std::min(max_warps(), (d16 && std::atoi(d16)) ? 16 : 12), budget / pl.per_warp_bytes));
+    if (warps <= 12) pl.mode = 4;
     if (groups < warps) warps = (int)std::max<long long>(1, groups);
   }
   pl.warps = warps;
@@ -345,6 +347,7 @@ static void launch_sweep_r(const SweepArgs& a, const SweepPlan& pl, cudaStream_t
   if (pl.mode == 1) launch_sweep_t<R, 1>(a, pl, s);
   else if (pl.mode == 3) launch_sweep_t<R, 3>(a, pl, s);
   else if (pl.mode == 0) launch_sweep_t<R, 0>(a, pl, s);
+  else if (pl.mode == 4) launch_sweep_t<R, 4>(a, pl, s);
   else launch_sweep_t<R, 2>(a, pl, s);
 }
 
