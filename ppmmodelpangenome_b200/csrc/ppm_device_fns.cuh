@@ -800,11 +800,26 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
         for (int q = 0; q < NI; q++) qv[q] = T.pairq[pid * 4 + (int)cb[q]];
         // three-stage software pipeline (record -> pattern word -> table row are dependent shared-memory loads):
-        // iteration e fetches the record of e+3, the word of e+2 and the row of e+1 while pair e is multiplied in
+        // iteration e fetches the record of e+3, the word of e+2 and the row of e+1 while pair e is multiplied in.
+        // Global-memory variant: the pair records stream through the per-warp ring as well (chunks of 32, two chunks
+        // ahead), so the loop never waits on L2 for a record.
         const int elast = bd.e_leafu0 - 1;
+        const int B0 = bd.e_pair0;
+        const bool ring = DEEP && PPM_LANES == 32;
+        auto pstage = [&](int c) {
+          int idx = B0 + c * 32 + lane;
+          idx = idx > m.n_entries ? m.n_entries : idx;  // the table ends with one padding record
+          ppm_cp_async16(wrec + (c % 3) * 32 + lane, T.recs + idx);
+          ppm_cp_commit();
+        };
+        auto prec = [&](int idx, double& Kx, uint32_t& refx, uint32_t& mkx) {
+          if (ring) { const int o = idx - B0; load_rec(wrec, ((o >> 5) % 3) * 32 + (o & 31), Kx, refx, mkx); }
+          else load_rec(T.recs, idx, Kx, refx, mkx);
+        };
+        if (ring) { pstage(0); pstage(1); ppm_cp_wait1(); ppm_syncwarp(); }
         double K1, K2; uint32_t rot1, rot2;
-        load_rec(T.recs, bd.e_pair0 + 1 < elast ? bd.e_pair0 + 1 : elast, K1, ref, rot1);  // (the record behind the segment is not a pair)
-        load_rec(T.recs, bd.e_pair0 + 2 < elast ? bd.e_pair0 + 2 : elast, K2, ref, rot2);
+        prec(B0 + 1 < elast ? B0 + 1 : elast, K1, ref, rot1);  // (the record behind the segment is not a pair)
+        prec(B0 + 2 < elast ? B0 + 2 : elast, K2, ref, rot2);
         uint32_t w1[NI];
         {
           int wo, qo;
@@ -812,12 +827,19 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
           for (int q = 0; q < NI; q++) w1[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
         }
-        for (int e = bd.e_pair0; e <= elast;) {
+        for (int e = B0; e <= elast;) {
+          if (ring && ((e - B0) & 31) == 0) {
+            // chunk boundary: the ring slot of the previous chunk is free again, the next chunk must have landed
+            ppm_syncwarp();
+            pstage(((e - B0) >> 5) + 2);
+            ppm_cp_wait1();
+            ppm_syncwarp();
+          }
           const int ce = (e + 16 <= elast) ? e + 16 : elast + 1;
 #pragma unroll 2
           for (; e < ce; e++) {
             double K3; uint32_t rot3;
-            load_rec(T.recs, e + 3 < elast ? e + 3 : elast, K3, ref, rot3);
+            prec(e + 3 < elast ? e + 3 : elast, K3, ref, rot3);
             int wo1, qo1, wo2, qo2;
             unpack2i(K1, wo1, qo1);
             unpack2i(K2, wo2, qo2);
@@ -840,6 +862,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           for (int q = 0; q < NI; q++)
             if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
         }
+        if (ring) { ppm_cp_wait0(); ppm_syncwarp(); }
       } else {  // pi1 close to 1: two linear factors keep full accuracy
         for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
           const int pa = 2 * pid, pb = 2 * pid + 1;

@@ -47,8 +47,9 @@ struct DevBuf {
 
 }  // namespace
 
-// slices per block of the sweep program: 8 (default) or 16; PPM_R overrides (tuning knob)
-static int program_R() {
+// slices per block of the sweep program: 8 (default), 12 or 16; PPM_R overrides (tuning knob; 16 halves the record and
+// lineage-slot traffic per term of the global-memory variant but its register need costs as much: no gain measured)
+static int program_R(bool = false) {
   const char* e = std::getenv("PPM_R");
   int r = e ? std::atoi(e) : 8;
   return (r == 16 || r == 12) ? r : 8;
@@ -116,7 +117,7 @@ struct ppm_engine {
   void upload_model() { upload_model_impl(false); if (!ppm::sweep_is_staged(md)) upload_model_impl(true); }
 
   void upload_model_impl(bool deep) {
-    prog = ppm::build_program(tree, program_R(), deep);
+    prog = ppm::build_program(tree, program_R(deep), deep);
     // shard: contiguous, equal-sized slices of the deduplicated patterns (work per pattern is uniform)
     long long np = pat.n_patterns;
     first = np * shard_rank / shard_world;

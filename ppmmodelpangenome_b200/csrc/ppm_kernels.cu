@@ -76,6 +76,39 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.total = o;
   return L;
 }
+// global-memory variant: the small tables named by `mask` (DS_* bits) are staged in shared memory all the same
+struct DeepStage { size_t pairq, yy, wt, uu, blk, cherry, leafab, oprec, ops, total; };
+__host__ __device__ inline size_t deep_stage_bytes(const ModelDev& m, int bit) {
+  const size_t nbR = (size_t)m.n_blocks * m.R;
+  switch (bit) {
+    case DS_PAIRQ: return align16((size_t)m.n_pairs * 4 * sizeof(double4));
+    case DS_SLICES: return 3 * align16(nbR * sizeof(double)) + align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
+    case DS_CHERRY: return align16((size_t)m.n_cherries * 4 * sizeof(double2));
+    case DS_LEAFAB: return align16((size_t)m.n_leaves * 2 * sizeof(double2));
+    case DS_OPS: return align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)) + align16((size_t)(m.n_ops + 1) * sizeof(SweepOpDev));
+  }
+  return 0;
+}
+__host__ __device__ inline DeepStage deep_stage_layout(const ModelDev& m, int mask) {
+  DeepStage D{};
+  const size_t nbR = (size_t)m.n_blocks * m.R;
+  size_t o = 0;
+  if (mask & DS_PAIRQ) { D.pairq = o; o += deep_stage_bytes(m, DS_PAIRQ); }
+  if (mask & DS_SLICES) {
+    D.yy = o; o += align16(nbR * sizeof(double));
+    D.wt = o; o += align16(nbR * sizeof(double));
+    D.uu = o; o += align16(nbR * sizeof(double));
+    D.blk = o; o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
+  }
+  if (mask & DS_CHERRY) { D.cherry = o; o += deep_stage_bytes(m, DS_CHERRY); }
+  if (mask & DS_LEAFAB) { D.leafab = o; o += deep_stage_bytes(m, DS_LEAFAB); }
+  if (mask & DS_OPS) {
+    D.oprec = o; o += align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double));
+    D.ops = o; o += align16((size_t)(m.n_ops + 1) * sizeof(SweepOpDev));
+  }
+  D.total = o;
+  return D;
+}
 // per item and warp: pattern words [n_words][32]
 __host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16((size_t)m.n_words * 32 * 4); }
 
@@ -130,7 +163,8 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
   const int smem_slots = MODE == 0 ? m.n_slots : (TMEM ? (m.n_slots > nt ? m.n_slots - nt : 0) : 0);
   const size_t per_item = head + (size_t)smem_slots * 32 * sizeof(double2);
   const size_t per_warp = per_item * NI + (STAGED ? 0 : kRecRingBytes);
-  unsigned char* wbase = smem_raw + (STAGED ? L.total : 0) + (size_t)warp * per_warp;
+  const DeepStage DS = deep_stage_layout(m, STAGED ? 0 : a.stage_mask);
+  unsigned char* wbase = smem_raw + (STAGED ? L.total : DS.total) + (size_t)warp * per_warp;
   EntryRec* wrec = STAGED ? nullptr : reinterpret_cast<EntryRec*>(wbase + per_item * NI);
   ItemMem<Slots> mem[NI];
 #pragma unroll
@@ -193,6 +227,20 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
       T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
       T.cherry = a.t.cherry + (size_t)p * m.n_cherries * 4;
+      const int sm = a.stage_mask;
+      if (sm & DS_PAIRQ) { copy16(smem_raw + DS.pairq, T.pairq, deep_stage_bytes(m, DS_PAIRQ)); T.pairq = reinterpret_cast<const double4*>(smem_raw + DS.pairq); }
+      if (sm & DS_SLICES) {
+        copy16(smem_raw + DS.yy, T.yy, align16((size_t)nbR * sizeof(double))); T.yy = reinterpret_cast<const double*>(smem_raw + DS.yy);
+        copy16(smem_raw + DS.wt, T.wt, align16((size_t)nbR * sizeof(double))); T.wt = reinterpret_cast<const double*>(smem_raw + DS.wt);
+        copy16(smem_raw + DS.uu, T.uu, align16((size_t)nbR * sizeof(double))); T.uu = reinterpret_cast<const double*>(smem_raw + DS.uu);
+        copy16(smem_raw + DS.blk, T.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc))); T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + DS.blk);
+      }
+      if (sm & DS_CHERRY) { copy16(smem_raw + DS.cherry, T.cherry, deep_stage_bytes(m, DS_CHERRY)); T.cherry = reinterpret_cast<const double2*>(smem_raw + DS.cherry); }
+      if (sm & DS_LEAFAB) { copy16(smem_raw + DS.leafab, T.leafab, deep_stage_bytes(m, DS_LEAFAB)); T.leafab = reinterpret_cast<const double2*>(smem_raw + DS.leafab); }
+      if (sm & DS_OPS) {
+        copy16(smem_raw + DS.oprec, T.oprec, align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double))); T.oprec = reinterpret_cast<const double*>(smem_raw + DS.oprec);
+        copy16(smem_raw + DS.ops, T.ops, align16((size_t)(m.n_ops + 1) * sizeof(SweepOpDev))); T.ops = reinterpret_cast<const SweepOpDev*>(smem_raw + DS.ops);
+      }
       __syncthreads();
     }
     while (true) {
@@ -313,6 +361,15 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
     warps = (int)std::max<size_t>(1, std::min<size_t>(std::min(max_warps(), (d16 && std::atoi(d16)) ? 16 : 12), budget / pl.per_warp_bytes));
     if (warps <= 12) pl.mode = 4;
     if (groups < warps) warps = (int)std::max<long long>(1, groups);
+    // whatever small tables still fit are staged in shared memory per parameter vector (the records stay in global
+    // memory and stream through the per-warp rings)
+    const char* ns = std::getenv("PPM_NO_DEEP_STAGE");
+    size_t left = budget - pl.per_warp_bytes * warps;
+    if (!(ns && std::atoi(ns)))
+      for (int bit : {DS_SLICES, DS_PAIRQ, DS_CHERRY, DS_LEAFAB, DS_OPS}) {
+        const size_t need = deep_stage_bytes(m, bit);
+        if (need <= left) { pl.stage_mask |= bit; left -= need; }
+      }
   }
   pl.warps = warps;
   // persistent CTAs over equal contiguous ranges of the (parameter vector, batch) line; when a parameter vector has
@@ -322,9 +379,9 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   pl.items_per_warp = (int)((total + (long long)pl.grid_x * warps - 1) / ((long long)pl.grid_x * warps));  // informational
   pl.n_chunks = 1;
   if (std::getenv("PPM_PLAN_DEBUG"))
-    fprintf(stderr, "[ppm plan] tables %zu B, head %zu B, slots %d, per warp %zu B, w0 %d, w1 %d -> mode %d, %d warps, grid %d (budget %zu)\n",
-            L.total, head, m.n_slots, pl.per_warp_bytes, w0, w1, pl.mode, warps, pl.grid_x, budget);
-  pl.smem_bytes = (pl.staged ? L.total : 0) + pl.per_warp_bytes * warps;
+    fprintf(stderr, "[ppm plan] tables %zu B, head %zu B, slots %d, per warp %zu B, w0 %d, w1 %d -> mode %d, %d warps, grid %d, deep stage mask %d (budget %zu)\n",
+            L.total, head, m.n_slots, pl.per_warp_bytes, w0, w1, pl.mode, warps, pl.grid_x, pl.stage_mask, budget);
+  pl.smem_bytes = (pl.staged ? L.total : deep_stage_layout(m, pl.stage_mask).total) + pl.per_warp_bytes * warps;
   return pl;
 }
 bool sweep_is_staged(const ModelDev& m) { return plan_sweep(m, 1 << 20, 1, 148).staged; }
@@ -352,7 +409,7 @@ static void launch_sweep_r(const SweepArgs& a, const SweepPlan& pl, cudaStream_t
 }
 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
-  a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp;
+  a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp; a.stage_mask = pl.stage_mask;
   if (a.m.R == 16) launch_sweep_r<16>(a, pl, s);
   else if (a.m.R == 12) launch_sweep_r<12>(a, pl, s);
   else launch_sweep_r<8>(a, pl, s);

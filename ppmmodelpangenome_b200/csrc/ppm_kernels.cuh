@@ -105,14 +105,17 @@ struct SweepArgs {
   double* comp;          // [count][3] (mode 2)
   double2* gslots;       // global slot storage when slots do not fit in shared memory
   int force;             // evaluate even when i2 < 0
+  int stage_mask;        // global-memory variant: which small tables are staged in shared memory anyway (DS_* bits)
 };
+// small tables the global-memory variant stages per parameter vector when they fit (priority order)
+enum { DS_PAIRQ = 1, DS_SLICES = 2, DS_CHERRY = 4, DS_LEAFAB = 8, DS_OPS = 16 };
 
 void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s);
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
-struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks, mode; size_t smem_bytes, per_warp_bytes; bool staged; };
+struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks, mode, stage_mask; size_t smem_bytes, per_warp_bytes; bool staged; };
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm);
 bool sweep_is_staged(const ModelDev& m);  // depends on the tree/program sizes only
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 elements of global slot scratch (0 if staged)

@@ -109,7 +109,8 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.cherry = cherry.data() + (size_t)p * md.n_cherries * 4;
           double c[2] = {0., 0.};
           if (deep && prog.R == 8) sweep_items<8, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
-          else if (deep) throw std::runtime_error("deep emulation built for R = 8");
+          else if (deep && prog.R == 16) sweep_items<16, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (deep) throw std::runtime_error("deep emulation built for R in {8,16}");
           else if (prog.R == 8) sweep_items<8, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (prog.R == 4) sweep_items<4, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (prog.R == 12) sweep_items<12, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);

@@ -38,7 +38,7 @@ def emu():
 
 
 @pytest.mark.parametrize("name", ["ref_test", "syn12", "syn100", "cat40", "syn300"])
-@pytest.mark.parametrize("R", [8, 4, 12, 16, -8])  # -8: the deep-prefetch path of the global-memory variant
+@pytest.mark.parametrize("R", [8, 4, 12, 16, -8, -16])  # < 0: the deep-prefetch path of the global-memory variant (default there: 16)
 def test_kernel_bodies_reproduce_reference_golden(golden, emu, name, R):
     g = golden(name)
     ll, i2, parts, comp, cat = emu(g.tree, g.pa, False, g.params, R=R, n_rows=g.meta["nRep"])
