@@ -130,6 +130,21 @@ int ppm_components(ppm_handle h, const double* params8, double i2, double* out /
  * the input in input order (shard_world must be 1).  The reference writes them as "p0 p1 p2\n" per row. */
 int ppm_proba_cat(ppm_handle h, const double* params8, double i2, double* out /*[n_genes*3]*/);
 
+/* Replaces Inference::expectedTime1 / expectedTime1_store (functions.cpp:637-708): the expected introduction time of
+ * each PATTERN of this shard were it a Private gene, at l1 = params8[3], e = params8[6].  It depends on the pattern only
+ * through its MRCA, so the engine fills a per-node table with a top-down recursion and gathers by mrca. */
+int ppm_expected_time1(ppm_handle h, const double* params8, double* out /*[shard_count]*/);
+
+/* Replaces Inference::expectedTime2_times (functions.cpp:709-725: out_times[n_slices], the slice mid-points; may be
+ * NULL) and expectedTime2_aux + the denominator column of expectedTime2_store (:727-757): out_dist[r*(n_slices+1) + j]
+ * = the Mobile integrand exp(f_aux) of pattern r at slice j, out_dist[r*(n_slices+1) + n_slices] = exp(likRep2) (the
+ * integral).  out_dist may be NULL. */
+int ppm_expected_time2(ppm_handle h, const double* params8, double* out_times, double* out_dist);
+
+/* Replaces Inference::expectedGains (functions.cpp:593-615): expected number of Mobile gains along the tree for g2
+ * (a function of the tree only; evaluated by the host model, no GPU needed). */
+int ppm_expected_gains(ppm_handle h, double g2, double* out);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------- */
 
 /* Counters of the last ppm_loglik*(): [0] kernels launched, [1] device ms of the main kernel (CUDA events

@@ -39,6 +39,11 @@ def lib():
         L.ref_assign_cat.restype = C.c_int
         L.ref_proba_cat.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_char_p]
         L.ref_proba_cat.restype = C.c_int
+        L.ref_expected_time1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_expected_time2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_expected_time2.restype = C.c_int
+        L.ref_expected_gains.argtypes = [C.c_void_p, C.c_double]
+        L.ref_expected_gains.restype = C.c_double
         L.ref_set_threads.argtypes = [C.c_int]
         L.ref_max_threads.restype = C.c_int
         _lib = L
@@ -137,3 +142,30 @@ def set_threads(n):
 
 def max_threads():
     return int(lib().ref_max_threads())
+
+
+def _expected_time1(self, params):
+    """expectedTime1 (functions.cpp:637-690) per pattern."""
+    p = np.ascontiguousarray(params, np.float64)
+    out = np.zeros(self.nRep, np.float64)
+    lib().ref_expected_time1(self.h, p.ctypes.data, out.ctypes.data)
+    return out
+
+
+def _expected_time2(self, params):
+    """(times[S], dist[nRep][S+1]): expectedTime2_times, expectedTime2_aux + exp(likRep2) (functions.cpp:709-757)."""
+    p = np.ascontiguousarray(params, np.float64)
+    S = lib().ref_expected_time2(self.h, p.ctypes.data, None, None)
+    times = np.zeros(S, np.float64)
+    dist = np.zeros((self.nRep, S + 1), np.float64)
+    lib().ref_expected_time2(self.h, p.ctypes.data, times.ctypes.data, dist.ctypes.data)
+    return times, dist
+
+
+def _expected_gains(self, g2):
+    return float(lib().ref_expected_gains(self.h, float(g2)))
+
+
+Reference.expected_time1 = _expected_time1
+Reference.expected_time2 = _expected_time2
+Reference.expected_gains = _expected_gains

@@ -165,4 +165,31 @@ int ref_proba_cat(void* hv, const double* p, double i2, double* out /*[nRep*3]*/
   return n / 3;
 }
 
+// expectedTime1 (functions.cpp:637-690) per pattern, fresh memo (the zero row is evaluated first, serially)
+void ref_expected_time1(void* hv, const double* p, double* out /*[nRep]*/) {
+  Inference* inf = ((RefHandle*)hv)->inf;
+  inf->tLik.clearLikValues();
+  inf->computeI2(p[0], p[1], p[2], p[3], p[4], p[5], svec(p));
+  for (int rep = 0; rep < inf->nRep; rep++) out[rep] = inf->expectedTime1(rep, p[3], p[6]);
+}
+// expectedTime2_times (:709-725) and, per pattern, expectedTime2_aux (:727-757) followed by exp(likRep2) as
+// expectedTime2_store appends it (:756).  Returns the number of slices S; dist is [nRep][S+1] (may be NULL: count only)
+int ref_expected_time2(void* hv, const double* p, double* times, double* dist) {
+  Inference* inf = ((RefHandle*)hv)->inf;
+  std::vector<double> tt = inf->expectedTime2_times();
+  const int S = (int)tt.size();
+  if (times) std::copy(tt.begin(), tt.end(), times);
+  if (!dist) return S;
+  inf->tLik.clearLikValues();
+  inf->computeI2(p[0], p[1], p[2], p[3], p[4], p[5], svec(p));
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int rep = 0; rep < inf->nRep; rep++) {
+    std::vector<double> f = inf->expectedTime2_aux(rep, p[4], p[5], p[7], p[6]);
+    std::copy(f.begin(), f.end(), dist + (size_t)rep * (S + 1));
+    dist[(size_t)rep * (S + 1) + S] = exp(inf->likRep2(rep, p[4], p[5], p[7], p[6]));
+  }
+  return S;
+}
+double ref_expected_gains(void* hv, double g2) { return ((RefHandle*)hv)->inf->expectedGains(g2); }
+
 }  // extern "C"

@@ -118,6 +118,25 @@ Tree read_tree_file(const std::string& path) {
   return parse_newick(line);
 }
 
+double expected_gains(const Tree& t, double g2) {
+  // sumGains(st) (functions.cpp:582-592) = sum over the internal nodes v of the subtree of exp(g2 * height[v]) minus its leaves;
+  // children have larger preorder ids than their parent, so one reverse pass fills it
+  std::vector<double> G(t.n_nodes, 0.);
+  for (int v = t.n_nodes - 1; v >= 0; v--)
+    G[v] = t.left[v] < 0 ? -1. : std::exp(g2 * t.height[v]) + G[t.left[v]] + G[t.right[v]];
+  // a lineage st is in subtrees[rank] for every interval between its own height and its parent's (functions.cpp:130-141);
+  // sum over those intervals of  w + G (e^{-g2 h_lo} - e^{-g2 h_hi}) / g2  telescopes to the two ends of its branch
+  double sum = 0.;
+  // (the reference starts at interval rank nLeaves-1, functions.cpp:598: anything below the last leaf is skipped)
+  for (int v = 1; v < t.n_nodes; v++) {
+    const int r0 = std::max(t.rank[v], t.n_leaves - 1), r1 = t.rank[t.parent[v]];
+    if (r1 <= r0) continue;
+    const double lo = t.height[t.order[r0]], hi = t.height[t.parent[v]];
+    if (hi > lo) sum += (hi - lo) + G[v] * (std::exp(-g2 * lo) - std::exp(-g2 * hi)) / g2;
+  }
+  return sum / t.H;
+}
+
 static void finish_tree(Tree& t) {
   const int nn = (int)t.left.size();
   t.n_nodes = nn;

@@ -34,6 +34,9 @@ struct Tree {
 Tree parse_newick(const std::string& first_line);
 Tree tree_from_arrays(int n_nodes, const int32_t* left, const int32_t* right, const double* bl);
 Tree read_tree_file(const std::string& path);
+// Inference::expectedGains (functions.cpp:593-615): expected number of Mobile gains along the tree, a function of the tree
+// and g2 only.  The reference's double sum over (interval, alive lineage) telescopes per lineage: O(nodes).
+double expected_gains(const Tree& t, double g2);
 
 struct Patterns {
   int n_words = 0;

@@ -161,6 +161,10 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
     z0[0] = 0.; z1[0] = 0.;
     d1u[0] = make_double2(0., -INFINITY);
+    // expectedTime1 (functions.cpp:637-690) as a top-down recursion: for a gain node g with parent p, branch b, sibling s,
+    //   D(g) = (1 - e^{-l1 b}) + e^{-l1 b} T(s) D(p),   N(g) = (1/l1 - e^{-l1 b}(b + 1/l1)) + e^{-l1 b} T(s) (N(p) + b D(p)),
+    // D(root) = 1, N(root) = 1/l1, expected time = N/D (the reference's sums over the root path, regrouped)
+    if (t.et1) { t.et1[(size_t)p * nn] = 1. / l1; ss0[0] = 1.; }
   }
   PPM_CTA_BARRIER();
   // (D) top-down by levels: U (likUpper1, functions.cpp:176-209, as U(v) = lost_v + sigma_v*T(sib)*U(parent),
@@ -177,8 +181,17 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       z1[v] = U; z0[v] = logV;
       const double logU = log(U);
       d1u[v] = make_double2(lse2(logV, logU) - logV, logU);
+      if (t.et1) {  // ss0 is dead after level (B)/(C): reused as D
+        const double b = m.bl[v], sT = sig * exp(cls[sib].w);
+        const double Dp = ss0[par_], Np = t.et1[(size_t)p * nn + par_];
+        ss0[v] = (1 - sig) + sT * Dp;
+        t.et1[(size_t)p * nn + v] = (1. / l1 - sig * (b + 1. / l1)) + sT * (Np + b * Dp);
+      }
     }
     PPM_CTA_BARRIER();
+  }
+  if (t.et1) {
+    for (int v = tid; v < nn; v += nt) t.et1[(size_t)p * nn + v] /= ss0[v];
   }
 }
 
@@ -518,7 +531,7 @@ PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) 
 // DEEP (the variant whose tables and lineage slots live in global memory): the records of the fully-alive entries
 // are streamed through a per-warp shared-memory ring (wrec, 3 chunks of 32 records, cp.async two chunks ahead) and
 // lineage partials are fetched four entries ahead, so L2/HBM latency is covered by ~140 cycles of FP64 work each.
-template <int R, int NI, bool DEEP, class Slots>
+template <int R, int NI, bool DEEP, class Slots, bool DIST = false>
 PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long long batch0, int lane,
                         const ItemMem<Slots> (&mem)[NI], double (&contrib)[NI], EntryRec* wrec) {
   const ModelDev& m = a.m;
@@ -975,6 +988,14 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
     for (int q = 0; q < NI; q++) {
       if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+      if (DIST) {  // expectedTime2_aux (functions.cpp:713-746): the integrand exp(f_aux) of every slice
+        if (a.dist && active[q]) {
+          double* row = a.dist + (size_t)(pat[q] - a.first) * (m.n_slices + 1);
+#pragma unroll
+          for (int i = 0; i < R; i++)
+            if (b * R + i < m.n_slices) row[b * R + i] = ldexp(prod[q][i], -ex[q][i]);
+        }
+      }
       bool same = true;
 #pragma unroll
       for (int i = 1; i < R; i++) same = same && (ex[q][i] == ex[q][0]);
@@ -1002,6 +1023,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         scw[SC_IZ_M] = Im[q]; scw[SC_IZ_E] = (double)Ie[q];
       }
       continue;
+    }
+    if (DIST) {  // last column: exp(likRep2) = the integral itself (functions.cpp:756)
+      if (a.dist && active[q]) a.dist[(size_t)(pat[q] - a.first) * (m.n_slices + 1) + m.n_slices] = ldexp(Im[q], -Ie[q]);
     }
     // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
     if (active[q]) {

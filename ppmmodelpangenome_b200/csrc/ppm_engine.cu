@@ -87,7 +87,7 @@ struct ppm_engine {
   DevBuf<ppm::SweepOpDev> d_sops;
   DevBuf<int> d_cherry_op;
   DevBuf<double2> d_leafab;
-  DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override;
+  DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override, d_et1, d_dist;
   DevBuf<double4> d_cls;
   DevBuf<double2> d_kap, d_d1u, d_gslots, d_clsT, d_a01;
   DevBuf<signed char> d_cat;
@@ -193,7 +193,7 @@ struct ppm_engine {
     }
     ppm::TablesDev t{};
     t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p; t.cherry = d_cherry.p;
-    t.scal = d_scal.p; t.zeta = d_zeta.p;
+    t.scal = d_scal.p; t.zeta = d_zeta.p; t.et1 = nullptr;  // expectedTime1 tables only on request
     return t;
   }
 
@@ -211,8 +211,10 @@ struct ppm_engine {
   }
 
   // mode 0: partial sums into d_out[P]; mode 2: categories/components for P == 1
-  void run_sweep(const ppm::TablesDev& t, int mode, double* d_out, signed char* d_cat_out, double* d_comp_out, cudaStream_t s) {
+  void run_sweep(const ppm::TablesDev& t, int mode, double* d_out, signed char* d_cat_out, double* d_comp_out, cudaStream_t s,
+                 double* d_dist_out = nullptr) {
     ppm::SweepArgs a{};
+    a.dist = d_dist_out;
     a.m = md; a.t = t; a.mode = mode; a.first = 0; a.count = count;
     a.n_batches = (count + 31) / 32; a.n_items = a.n_batches * t.P;
     a.cat = d_cat_out; a.comp = d_comp_out; a.force = (mode == 2);
@@ -222,7 +224,7 @@ struct ppm_engine {
     if (a.n_items > 0) {
       ppm::launch_class_sums(md, t, 0, count, s);
       n_launches += 1;
-      ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm);
+      ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm, d_dist_out != nullptr);
       d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
       CK(cudaEventRecord(ev0, s));
       ppm::launch_sweep(a, pl, s);
@@ -469,6 +471,56 @@ int ppm_proba_cat(ppm_handle h, const double* params8, double i2, double* out) {
     double den = mx + std::log(std::exp(c[0] - mx) + std::exp(c[1] - mx) + std::exp(c[2] - mx));
     for (int k = 0; k < 3; k++) out[3 * g + k] = c[k] - den;
   }
+  return PPM_OK;
+}
+
+int ppm_expected_time1(ppm_handle h, const double* params8, double* out) {
+  if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  GUARD_BEGIN
+  CK(cudaSetDevice(h->device));
+  h->n_launches = 0;
+  h->tables(1, nullptr);
+  CK(cudaMemcpyAsync(h->d_params.p, params8, sizeof(double) * 8, cudaMemcpyHostToDevice, h->stream));
+  ppm::TablesDev t = h->tables(1, h->d_params.p);
+  h->d_et1.alloc((size_t)h->tree.n_nodes);
+  t.et1 = h->d_et1.p;
+  ppm::launch_prepass_nodes(h->md, t, h->stream);
+  h->d_comp.alloc((size_t)std::max<long long>(h->count, 1) * 3);
+  ppm::launch_gather(h->d_et1.p, h->d_mrca.p, h->count, h->d_comp.p, h->stream);
+  h->n_launches += 2;
+  CK(cudaGetLastError());
+  if (h->count) CK(cudaMemcpyAsync(out, h->d_comp.p, sizeof(double) * h->count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_expected_time2(ppm_handle h, const double* params8, double* out_times, double* out_dist) {
+  if (!h || !params8) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  if (out_times) std::copy(h->tree.slice_t.begin(), h->tree.slice_t.end(), out_times);  // host model: expectedTime2_times
+  if (!out_dist) return PPM_OK;
+  GUARD_BEGIN
+  if (h->md.R != 8) { h->err = "ppm_expected_time2 needs the default program (PPM_R unset)"; return PPM_ESTATE; }
+  CK(cudaSetDevice(h->device));
+  h->n_launches = 0;
+  h->tables(1, nullptr);
+  CK(cudaMemcpyAsync(h->d_params.p, params8, sizeof(double) * 8, cudaMemcpyHostToDevice, h->stream));
+  ppm::TablesDev t = h->tables(1, h->d_params.p);
+  h->run_prepass(t, nullptr, h->stream);
+  const size_t row = (size_t)h->tree.n_slices + 1;
+  h->d_dist.alloc((size_t)std::max<long long>(h->count, 1) * row);
+  h->d_cat.alloc((size_t)std::max<long long>(h->count, 1));
+  h->d_comp.alloc((size_t)std::max<long long>(h->count, 1) * 3);
+  h->run_sweep(t, 2, h->d_ll.p, h->d_cat.p, h->d_comp.p, h->stream, h->d_dist.p);
+  if (h->count) CK(cudaMemcpyAsync(out_dist, h->d_dist.p, sizeof(double) * row * h->count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PPM_OK;
+  GUARD_END(h)
+}
+
+int ppm_expected_gains(ppm_handle h, double g2, double* out) {
+  if (!h || !out) return PPM_EINVAL;
+  *out = ppm::expected_gains(h->tree, g2);
   return PPM_OK;
 }
 

@@ -135,7 +135,7 @@ template <int MODE> struct SlotsOf { typedef SlotsMem type; };
 template <> struct SlotsOf<1> { typedef SlotsTmem type; };
 template <> struct SlotsOf<3> { typedef SlotsTmem type; };  // MODE 3 = MODE 1 compiled for 12 warps (168 registers)
 
-template <int R, int NI, int MODE>
+template <int R, int NI, int MODE, bool DIST = false>
 __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       if (b_begin + g >= b_end) break;
       const long long batch0 = (b_begin + g) * NI;
       double contrib[NI];
-      sweep_items<R, NI, !STAGED, Slots>(a, T, p, batch0, lane, mem, contrib, wrec);
+      sweep_items<R, NI, !STAGED, Slots, DIST>(a, T, p, batch0, lane, mem, contrib, wrec);
       if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
@@ -322,7 +322,7 @@ static int max_warps() {  // tuning knob: PPM_MAX_WARPS caps the warps per CTA (
 
 static bool tmem_enabled() { const char* e = std::getenv("PPM_NO_TMEM"); return !(e && std::atoi(e) != 0); }
 
-SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
+SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm, bool dist) {
   SweepPlan pl{};
   const int NI = kItemsPerWarp;
   const size_t budget = 227 * 1024 - 1024;
@@ -340,7 +340,7 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   int w1 = 0; size_t pw1 = 0;
   if (tmem_enabled()) {
     const char* t12 = std::getenv("PPM_TMEM12");
-    for (int w = std::min(max_warps(), (t12 && std::atoi(t12)) ? 12 : 16); w >= 8 && !w1; w -= 4) {
+    for (int w = std::min(max_warps(), ((t12 && std::atoi(t12)) || dist) ? 12 : 16); w >= 8 && !w1; w -= 4) {
       const int nt = ((512 / ((w + 3) / 4)) & ~3) / 4 / NI;
       const size_t ovf = m.n_slots > nt ? (size_t)(m.n_slots - nt) : 0;
       if (L.total + (size_t)w * NI * (head + ovf * slot_row) <= budget) { w1 = w; pw1 = NI * (head + ovf * slot_row); }
@@ -352,13 +352,14 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm) {
   const bool tiny = w0 >= 1 && groups <= w0 && (w0 >= 3 || w1);  // e.g. the all-zero row: one small CTA per parameter vector
   // (only where the big sweep is staged too: both run the same, non-deep, program)
   if (tiny) { warps = (int)groups; pl.mode = 0; pl.per_warp_bytes = per_warp_staged; }
+  else if (dist && w0 >= 1 && (w0 >= 3 || w1)) { warps = w0; pl.mode = 0; pl.per_warp_bytes = per_warp_staged; }  // DIST kernels exist for modes 0, 3, 4
   else if (w1 && ((force && std::atoi(force)) || w0 < 10)) { warps = w1; pl.mode = w1 <= 12 ? 3 : 1; pl.per_warp_bytes = pw1; }
   else if (w0 >= 3) { warps = w0; pl.mode = 0; pl.per_warp_bytes = per_warp_staged; }
   pl.staged = pl.mode != 2;
   if (!pl.staged) {
     pl.per_warp_bytes = NI * head + kRecRingBytes;
     const char* d16 = std::getenv("PPM_DEEP16");
-    warps = (int)std::max<size_t>(1, std::min<size_t>(std::min(max_warps(), (d16 && std::atoi(d16)) ? 16 : 12), budget / pl.per_warp_bytes));
+    warps = (int)std::max<size_t>(1, std::min<size_t>(std::min(max_warps(), (d16 && std::atoi(d16) && !dist) ? 16 : 12), budget / pl.per_warp_bytes));
     if (warps <= 12) pl.mode = 4;
     if (groups < warps) warps = (int)std::max<long long>(1, groups);
     // whatever small tables still fit are staged in shared memory per parameter vector (the records stay in global
@@ -389,14 +390,14 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
   return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * (m.n_slots + 1) * 32;
 }
 
-template <int R, int MODE>
+template <int R, int MODE, bool DIST = false>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
     configured = true;
   }
-  sweep_kernel<R, kItemsPerWarp, MODE><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+  sweep_kernel<R, kItemsPerWarp, MODE, DIST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
 
 template <int R>
@@ -410,12 +411,25 @@ static void launch_sweep_r(const SweepArgs& a, const SweepPlan& pl, cudaStream_t
 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
   a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp; a.stage_mask = pl.stage_mask;
+  if (a.dist) {  // per-slice integrand output (expectedTime2): R = 8 programs, modes 0 / 3 / 4 (plan_sweep(dist = true))
+    if (pl.mode == 0) launch_sweep_t<8, 0, true>(a, pl, s);
+    else if (pl.mode == 3) launch_sweep_t<8, 3, true>(a, pl, s);
+    else launch_sweep_t<8, 4, true>(a, pl, s);
+    return;
+  }
   if (a.m.R == 16) launch_sweep_r<16>(a, pl, s);
   else if (a.m.R == 12) launch_sweep_r<12>(a, pl, s);
   else launch_sweep_r<8>(a, pl, s);
 }
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s) {
   reduce_kernel<<<P, 256, 0, s>>>(partial, nx, out);
+}
+__global__ void gather_kernel(const double* table, const int* index, long long n, double* out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = table[index[j]];
+}
+void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s) {
+  if (n > 0) gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(table, index, n, out);
 }
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s) {
   finalize_kernel<<<(P + 127) / 128, 128, 0, s>>>(i2, ll, P);

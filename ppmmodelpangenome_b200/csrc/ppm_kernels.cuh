@@ -91,6 +91,7 @@ struct TablesDev {
   double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)
   double* scal;          // [P][SC_COUNT]
   double* zeta;          // [P][6][n_nodes] scratch of the node prepass
+  double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 
 struct SweepArgs {
@@ -105,6 +106,7 @@ struct SweepArgs {
   double* comp;          // [count][3] (mode 2)
   double2* gslots;       // global slot storage when slots do not fit in shared memory
   int force;             // evaluate even when i2 < 0
+  double* dist;          // [count][n_slices+1] per-slice Mobile integrand + the integral (expectedTime2_aux; DIST kernels only)
   int stage_mask;        // global-memory variant: which small tables are staged in shared memory anyway (DS_* bits)
 };
 // small tables the global-memory variant stages per parameter vector when they fit (priority order)
@@ -116,12 +118,13 @@ void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, l
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
 struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks, mode, stage_mask; size_t smem_bytes, per_warp_bytes; bool staged; };
-SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm);
+SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm, bool dist = false);  // dist: a launch that writes SweepArgs::dist
 bool sweep_is_staged(const ModelDev& m);  // depends on the tree/program sizes only
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 elements of global slot scratch (0 if staged)
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s);
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s);
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
+void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]
 double run_fp64_peak(int device);
 
 }  // namespace ppm

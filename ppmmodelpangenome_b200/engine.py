@@ -32,7 +32,8 @@ class Info(C.Structure):
 
 SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_destroy", "ppm_last_error", "ppm_get_info",
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
-           "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_get_counters",
+           "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_expected_time1",
+           "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters",
            "ppm_measure_fp64_peak"]
 
 
@@ -65,6 +66,9 @@ def lib():
         L.ppm_assign_cat.argtypes = [vp, vp, dbl, vp]
         L.ppm_components.argtypes = [vp, vp, dbl, vp]
         L.ppm_proba_cat.argtypes = [vp, vp, dbl, vp]
+        L.ppm_expected_time1.argtypes = [vp, vp, vp]
+        L.ppm_expected_time2.argtypes = [vp, vp, vp, vp]
+        L.ppm_expected_gains.argtypes = [vp, dbl, vp]
         L.ppm_get_counters.argtypes = [vp, vp]
         L.ppm_measure_fp64_peak.argtypes = [C.c_int, vp]
         _LIB = L
@@ -217,6 +221,30 @@ class Inference:
         out = np.zeros((max(self.nGenes, 1), 3))
         self._ck(lib().ppm_proba_cat(self._h, p.ctypes.data, float(i2), out.ctypes.data))
         return out[:self.nGenes]
+
+    def expectedTime1(self, params8):
+        """Expected introduction time of every pattern of this shard taken as a Private gene (functions.cpp:637-708)."""
+        p = _params(params8)
+        n = self.info.shard_count
+        out = np.zeros(max(n, 1))
+        self._ck(lib().ppm_expected_time1(self._h, p.ctypes.data, out.ctypes.data))
+        return out[:n]
+
+    def expectedTime2(self, params8):
+        """(times[S], dist[nPatterns, S+1]): slice mid-points (expectedTime2_times), the Mobile integrand per slice
+        (expectedTime2_aux) and, last column, exp(likRep2) (functions.cpp:709-757)."""
+        p = _params(params8)
+        n, S = self.info.shard_count, self.info.n_slices
+        times = np.zeros(max(S, 1))
+        dist = np.zeros((max(n, 1), S + 1))
+        self._ck(lib().ppm_expected_time2(self._h, p.ctypes.data, times.ctypes.data, dist.ctypes.data))
+        return times[:S], dist[:n]
+
+    def expectedGains(self, g2):
+        """Expected number of Mobile gains along the tree (functions.cpp:593-615); host model, no GPU needed."""
+        v = C.c_double()
+        self._ck(lib().ppm_expected_gains(self._h, float(g2), C.byref(v)))
+        return v.value
 
     # device-pointer entry points (bench / multi-GPU plumbing)
     def loglik_device(self, d_params_ptr, P, d_out_ptr, d_i2_ptr, stream_ptr=None):

@@ -20,6 +20,13 @@ static std::string g_err;
 
 extern "C" const char* emu_error() { return g_err.c_str(); }
 
+// optional posterior outputs of the next emu_eval call (params[0] only): expectedTime1 per pattern [n_patterns],
+// expectedTime2 rows [n_patterns][n_slices+1], expectedGains(g2)
+static double* g_et1 = nullptr; static double* g_dist = nullptr; static double g_gains_g2 = 0.; static double* g_gains = nullptr;
+extern "C" void emu_set_posterior_outputs(double* et1, double* dist, double gains_g2, double* gains) {
+  g_et1 = et1; g_dist = dist; g_gains_g2 = gains_g2; g_gains = gains;
+}
+
 // out_ll[P], out_i2[P], out_parts[P][4]; out_comp [n_patterns][3] / out_cat [n_patterns] for params[0] (may be NULL)
 // i2_override: NULL, or the i2 to use for comp/cat (as assignCat receives MLEi2)
 // R < 0 selects the deep-prefetch code path (global-memory variant) with |R| slices per block
@@ -91,8 +98,12 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<double2> slotmem(NI * (prog.n_slots + 1));
     ItemMem<SlotsMem> mem[2];
     for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
-    auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force) {
+    std::vector<double> et1v(g_et1 ? (size_t)P * nn : 0);
+    if (g_et1) t.et1 = et1v.data();
+    if (g_gains) *g_gains = expected_gains(tree, g_gains_g2);
+    auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force, double* dist = nullptr) {
       SweepArgs a{};
+      a.dist = dist;
       a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = (mode == 1) ? 1 : count;
       a.n_batches = a.count; a.n_items = a.n_batches * nP; a.comp = comp; a.cat = cat; a.force = force;
       for (int p = 0; p < nP; p++) {
@@ -108,7 +119,10 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.pairq = pairq.data() + (size_t)p * md.n_pairs * 4;
           T.cherry = cherry.data() + (size_t)p * md.n_cherries * 4;
           double c[2] = {0., 0.};
-          if (deep && prog.R == 8) sweep_items<8, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
+          if (dist && prog.R == 8 && deep) sweep_items<8, 2, true, SlotsMem, true>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (dist && prog.R == 8) sweep_items<8, 2, false, SlotsMem, true>(a, T, p, bt, 0, mem, c, nullptr);
+          else if (dist) throw std::runtime_error("per-slice output emulated for R = 8");
+          else if (deep && prog.R == 8) sweep_items<8, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (deep && prog.R == 16) sweep_items<16, 2, true, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
           else if (deep) throw std::runtime_error("deep emulation built for R in {8,16}");
           else if (prog.R == 8) sweep_items<8, 2, false, SlotsMem>(a, T, p, bt, 0, mem, c, nullptr);
@@ -137,10 +151,12 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
       if (out_parts) { out_parts[4 * p] = s[SC_P0]; out_parts[4 * p + 1] = s[SC_P1]; out_parts[4 * p + 2] = s[SC_A]; out_parts[4 * p + 3] = s[SC_B]; }
       if (s[SC_I2] < 0.) out_ll[p] = -1e9 * 1. + s[SC_I2];
     }
-    if (out_comp || out_cat) {
+    if (out_comp || out_cat || g_dist) {
       std::vector<double> dummy(1);
-      run(2, 1, dummy.data(), out_comp, out_cat, true);
+      run(2, 1, dummy.data(), out_comp, out_cat, true, g_dist);
     }
+    if (g_et1) for (long long j = 0; j < count; j++) g_et1[j] = et1v[pat.mrca[j]];
+    g_et1 = nullptr; g_dist = nullptr; g_gains = nullptr;
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

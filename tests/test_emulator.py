@@ -34,6 +34,7 @@ def emu():
             raise RuntimeError(L.emu_error().decode())
         return ll, i2, parts, comp[:npat.value], cat[:npat.value]
 
+    run.lib = L
     return run
 
 
@@ -58,3 +59,21 @@ def test_deduplicated_input_gives_the_same_loglik(golden, emu):
     a = emu(g.tree, g.pa, False, g.params[:2], want_comp=False)[0]
     b = emu(g.tree, g.pa, True, g.params[:2], want_comp=False)[0]
     assert np.allclose(a, b, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("name", ["ref_test", "syn12", "syn100", "cat40"])
+@pytest.mark.parametrize("R", [8, -8])
+def test_posterior_outputs_reproduce_reference(golden, emu, name, R):
+    """expectedTime1 / expectedTime2_aux / expectedGains (functions.cpp:582-757) from the kernel bodies against
+    tests/golden/posterior_*.npz (written by the unmodified reference, oracle/gen_golden_posterior.py)."""
+    g = golden(name)
+    z = np.load(os.path.join(os.path.dirname(g.tree), "posterior_" + name + ".npz"))
+    n, S = g.meta["nRep"], len(z["times"])
+    et1, dist, gains = np.zeros(n), np.zeros((n, S + 1)), C.c_double()
+    for g2, want in zip(z["gains_g2"], z["gains"]):
+        emu.lib.emu_set_posterior_outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        emu.lib.emu_set_posterior_outputs(et1.ctypes.data, dist.ctypes.data, float(g2), C.byref(gains))
+        emu(g.tree, g.pa, False, z["params"], R=R, want_comp=False)
+        assert rel(gains.value, want) <= 1e-10, (g2, gains.value, want)
+    assert np.allclose(et1, z["et1"], rtol=1e-9, atol=0)
+    assert np.allclose(dist, z["dist"], rtol=1e-9, atol=1e-300)

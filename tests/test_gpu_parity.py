@@ -180,3 +180,52 @@ def test_posterior_category_probabilities(ppm, golden):
         assert np.allclose(got[fin], lp[fin], rtol=1e-9, atol=1e-9)
         assert np.allclose(np.exp(got).sum(axis=1), 1.0, atol=1e-12)
         inf.close()
+
+
+@pytest.mark.parametrize("name", ["ref_test", "syn12", "syn100", "cat40"])
+def test_posterior_accessory_outputs_against_reference_golden(ppm, golden, name):
+    """ppm_expected_time1 / ppm_expected_time2 / ppm_expected_gains == expectedTime1, expectedTime2_times / _aux +
+    exp(likRep2), expectedGains (functions.cpp:582-757); goldens by the unmodified reference
+    (oracle/gen_golden_posterior.py)."""
+    g = golden(name)
+    z = np.load(os.path.join(os.path.dirname(g.tree), "posterior_" + name + ".npz"))
+    inf = _engine(ppm, g, dedupe=False)
+    et1 = inf.expectedTime1(z["params"])
+    assert np.allclose(et1, z["et1"], rtol=RTOL, atol=0)
+    times, dist = inf.expectedTime2(z["params"])
+    assert np.allclose(times, z["times"], rtol=1e-12, atol=1e-15)
+    assert dist.shape == z["dist"].shape
+    assert np.allclose(dist, z["dist"], rtol=RTOL, atol=1e-300)
+    # the integral column is the weighted sum of the integrand columns (functions.cpp:273-275)
+    for g2, want in zip(z["gains_g2"], z["gains"]):
+        assert rel(inf.expectedGains(g2), want) <= 1e-10
+    # deduplicated handle: one row per unique pattern, same values
+    d = _engine(ppm, g, dedupe=True)
+    g2p = d.gene_to_pattern
+    assert np.array_equal(d.expectedTime1(z["params"])[g2p], et1)
+    dd = d.expectedTime2(z["params"])[1][g2p]
+    assert np.array_equal(dd[:, :-1], dist[:, :-1])            # per-slice integrands: same arithmetic per lane
+    assert np.allclose(dd[:, -1], dist[:, -1], rtol=1e-13, atol=0)  # the sum's order depends on the neighbouring lanes
+    d.close()
+    inf.close()
+
+
+def test_posterior_outputs_global_memory_variant(ppm, golden):
+    """syn300 runs the global-memory sweep variant: its per-slice integrand must sum to its own integral column and
+    the integral must match the Mobile component of ppm_components."""
+    g = golden("syn300")
+    inf = _engine(ppm, g, dedupe=False)
+    p = g.params[0]
+    times, dist = inf.expectedTime2(p)
+    hgt = np.zeros(inf.info.n_nodes)
+    from ppmmodelpangenome_b200.engine import lib
+    assert lib().ppm_get_double_array(inf._h, 0, hgt.ctypes.data, len(hgt)) == 0
+    assert np.all(np.diff(times) > 0) and times[-1] < hgt.max()
+    i2 = inf.computeI2(p)
+    comp = inf.components(p, i2)
+    with np.errstate(divide="ignore"):
+        lik2 = np.log(i2 / inf.nObs) + np.log(dist[:, -1])
+    fin = np.isfinite(lik2) & (dist[:, -1] > 1e-290)
+    assert fin.sum() > 0
+    assert np.allclose(lik2[fin], comp[fin, 2], rtol=1e-12, atol=1e-12)
+    inf.close()
