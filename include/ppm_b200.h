@@ -60,6 +60,7 @@ typedef struct {
   int32_t device;        /* CUDA ordinal */
   int32_t shard_rank, shard_world;
   int64_t shard_first, shard_count; /* the slice of patterns this handle evaluates      */
+  int32_t group_size;    /* GPUs behind this handle: 1, or n for a group head (ppm_create_group*) */
 } ppm_info;
 
 /* ---- construction ---------------------------------------------------------------------------------- */
@@ -80,6 +81,18 @@ int ppm_create(ppm_handle* out, const ppm_tree* tree, const uint32_t* packed_pat
  * compressed header). */
 int ppm_create_from_files(ppm_handle* out, const char* tree_path, const char* matrix_path, int dedupe, int device,
                           int shard_rank, int shard_world);
+
+/* Pattern-sharded evaluation on several GPUs of one box from ONE process: the handle owns one engine per
+ * entry of gpu_ids (shard k of n_gpus on device gpu_ids[k]; ids may repeat), sharing one host model.  On such a GROUP
+ * handle ppm_loglik evaluates all shards concurrently, each peer stores its P partial sums into the head's buffer over
+ * NVLink (peer copy), the head adds them in rank order (bitwise reproducible) and applies the penalty: out_ll is the
+ * complete objective, exactly as for an unsharded handle.  ppm_assign_cat / ppm_proba_cat / ppm_components /
+ * ppm_expected_time1/2 cover every pattern.  ppm_compute_i2 and the *_device entry points act on shard 0 (device
+ * gpu_ids[0]); with external plumbing (one process per GPU + NCCL) use ppm_create with shard_rank/shard_world instead. */
+int ppm_create_group(ppm_handle* out, const ppm_tree* tree, const uint32_t* packed_patterns, const int32_t* counts,
+                     int64_t n_patterns, int dedupe, const int32_t* gpu_ids, int32_t n_gpus);
+int ppm_create_group_from_files(ppm_handle* out, const char* tree_path, const char* matrix_path, int dedupe,
+                                const int32_t* gpu_ids, int32_t n_gpus);
 
 void ppm_destroy(ppm_handle h);
 const char* ppm_last_error(ppm_handle h); /* h may be NULL: error of the last failed create on this thread */

@@ -3,7 +3,8 @@
 // Same positional arguments, same progress lines on stdout, same output files (mle_param.txt appended with
 // 13 fields, inf_cat.txt one category per input gene followed by a blank).  The objective is evaluated on
 // the GPU through the C ABI (include/ppm_b200.h); the optimiser is the batched nmkb of nmkb.h.
-// Environment: PPM_DEVICE (CUDA ordinal, default 0), PPM_DEDUPE (default 1: unique patterns with
+// Environment: PPM_DEVICE (CUDA ordinal, default 0), PPM_GPUS (default 1: number of GPUs, devices PPM_DEVICE ..
+// PPM_DEVICE+n-1, patterns sharded over them behind one group handle; or PPM_GPU_IDS=0,1,5 for an explicit list), PPM_DEDUPE (default 1: unique patterns with
 // multiplicities; 0 evaluates every gene column like the reference does), PPM_SPECULATE (default 1).
 #include <array>
 #include <cstdio>
@@ -141,7 +142,25 @@ int main(int argc, char* argv[]) {
   time_t debut = time(NULL);
   Fit fit;
   const int dedupe = env_int("PPM_DEDUPE", 1);
-  int rc = ppm_create_from_files(&fit.h, argv[2], argv[3], dedupe, env_int("PPM_DEVICE", 0), 0, 1);
+  const int n_gpus = env_int("PPM_GPUS", 1), dev0 = env_int("PPM_DEVICE", 0);
+  int rc;
+  std::vector<int32_t> ids;
+  if (const char* list = std::getenv("PPM_GPU_IDS")) {
+    for (const char* p = list; *p;) {
+      char* end;
+      long v = std::strtol(p, &end, 10);
+      if (end == p) break;
+      ids.push_back((int32_t)v);
+      p = (*end == ',') ? end + 1 : end;
+    }
+  } else if (n_gpus > 1) {
+    for (int k = 0; k < n_gpus; k++) ids.push_back(dev0 + k);
+  }
+  if (!ids.empty()) {
+    rc = ppm_create_group_from_files(&fit.h, argv[2], argv[3], dedupe, ids.data(), (int32_t)ids.size());
+  } else {
+    rc = ppm_create_from_files(&fit.h, argv[2], argv[3], dedupe, dev0, 0, 1);
+  }
   if (rc) {
     std::cerr << "ppm_b200: cannot build the model (" << rc << "): " << ppm_last_error(nullptr) << std::endl;
     return 2;

@@ -56,9 +56,24 @@ static int program_R(bool = false) {
 }
 
 struct ppm_engine {
-  ppm::Tree tree;
-  ppm::Patterns pat;
+  // host model: owned by the first engine of a group, shared (read-only) by its peers
+  std::shared_ptr<ppm::Tree> tree_own;
+  std::shared_ptr<ppm::Patterns> pat_own;
+  ppm::Tree& tree;
+  ppm::Patterns& pat;
   ppm::Program prog;
+  // group head only (ppm_create_group*): the engines of shards 1..n-1, one per GPU; the head itself is shard 0
+  std::vector<std::unique_ptr<ppm_engine>> peers;
+  cudaEvent_t ev_done = nullptr;  // "this shard's partial sums have reached the head"
+
+  ppm_engine() : tree_own(std::make_shared<ppm::Tree>()), pat_own(std::make_shared<ppm::Patterns>()), tree(*tree_own), pat(*pat_own) {}
+  ppm_engine(const std::shared_ptr<ppm::Tree>& t, const std::shared_ptr<ppm::Patterns>& p) : tree_own(t), pat_own(p), tree(*tree_own), pat(*pat_own) {}
+  std::vector<ppm_engine*> members() {
+    std::vector<ppm_engine*> v{this};
+    for (auto& e : peers) v.push_back(e.get());
+    return v;
+  }
+  bool is_group() const { return !peers.empty(); }
   int device = 0, n_sm = 148;
   int shard_rank = 0, shard_world = 1;
   long long first = 0, count = 0;  // this shard's pattern slice
@@ -87,13 +102,16 @@ struct ppm_engine {
   DevBuf<ppm::SweepOpDev> d_sops;
   DevBuf<int> d_cherry_op;
   DevBuf<double2> d_leafab;
-  DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override, d_et1, d_dist;
+  DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override, d_et1, d_dist, d_gather;
   DevBuf<double4> d_cls;
   DevBuf<double2> d_kap, d_d1u, d_gslots, d_clsT, d_a01;
   DevBuf<signed char> d_cat;
   size_t partial_cap = 0;
 
   ~ppm_engine() {
+    peers.clear();
+    if (device >= 0) cudaSetDevice(device);
+    if (ev_done) cudaEventDestroy(ev_done);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -112,6 +130,7 @@ struct ppm_engine {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
+    CK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
   }
 
   void upload_model() { upload_model_impl(false); if (!ppm::sweep_is_staged(md)) upload_model_impl(true); }
@@ -257,7 +276,7 @@ struct ppm_engine {
   catch (const std::bad_alloc&) { (h)->err = "out of host memory"; return PPM_ENOMEM; } \
   catch (const std::exception& e) { (h)->err = e.what(); return PPM_EINVAL; }
 
-static int finish_create(ppm_handle* out, std::unique_ptr<ppm_engine>& e, int device, int rank, int world) {
+static void finish_one(ppm_engine* e, int device, int rank, int world) {
   if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad shard rank/world");
   e->shard_rank = rank; e->shard_world = world;
   if (device < 0) {  // host-only handle: model inspection, no compute
@@ -269,6 +288,30 @@ static int finish_create(ppm_handle* out, std::unique_ptr<ppm_engine>& e, int de
   } else {
     e->init_device(device);
     e->upload_model();
+  }
+}
+static int finish_create(ppm_handle* out, std::unique_ptr<ppm_engine>& e, int device, int rank, int world) {
+  finish_one(e.get(), device, rank, world);
+  *out = e.release();
+  return PPM_OK;
+}
+// group: shard k of n on gpu_ids[k]; the head (shard 0) owns the host model, the peers share it
+static int finish_create_group(ppm_handle* out, std::unique_ptr<ppm_engine>& e, const int32_t* gpu_ids, int n) {
+  if (!gpu_ids || n < 1) throw std::runtime_error("group: need at least one GPU id");
+  for (int k = 0; k < n; k++) if (gpu_ids[k] < 0) throw std::runtime_error("group: negative GPU id");
+  finish_one(e.get(), gpu_ids[0], 0, n);
+  for (int k = 1; k < n; k++) {
+    std::unique_ptr<ppm_engine> peer(new ppm_engine(e->tree_own, e->pat_own));
+    finish_one(peer.get(), gpu_ids[k], k, n);
+    if (gpu_ids[k] != gpu_ids[0]) {  // direct NVLink stores into the head's gather buffer where the box allows it
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, gpu_ids[k], gpu_ids[0]) == cudaSuccess && can) {
+        cudaSetDevice(gpu_ids[k]);
+        cudaDeviceEnablePeerAccess(gpu_ids[0], 0);
+      }
+      cudaGetLastError();  // "already enabled" is fine; without peer access cudaMemcpyPeerAsync stages through the host
+    }
+    e->peers.push_back(std::move(peer));
   }
   *out = e.release();
   return PPM_OK;
@@ -309,6 +352,39 @@ int ppm_create_from_files(ppm_handle* out, const char* tree_path, const char* ma
   catch (const std::exception& x) { g_create_error = x.what(); return PPM_EINVAL; }
 }
 
+int ppm_create_group(ppm_handle* out, const ppm_tree* tree, const uint32_t* packed, const int32_t* counts, int64_t n_patterns,
+                     int dedupe, const int32_t* gpu_ids, int32_t n_gpus) {
+  if (!out || !tree || !packed) { g_create_error = "null argument"; return PPM_EINVAL; }
+  *out = nullptr;
+  std::unique_ptr<ppm_engine> e(new ppm_engine);
+  try {
+    e->tree = ppm::tree_from_arrays(tree->n_nodes, tree->left, tree->right, tree->branch_len);
+    e->pat = ppm::build_patterns(e->tree, packed, counts, n_patterns, dedupe != 0);
+    return finish_create_group(out, e, gpu_ids, n_gpus);
+  } catch (const CudaError& x) { g_create_error = x.what(); return PPM_ECUDA; }
+  catch (const std::bad_alloc&) { g_create_error = "out of host memory"; return PPM_ENOMEM; }
+  catch (const std::exception& x) { g_create_error = x.what(); return PPM_EINVAL; }
+}
+
+int ppm_create_group_from_files(ppm_handle* out, const char* tree_path, const char* matrix_path, int dedupe,
+                                const int32_t* gpu_ids, int32_t n_gpus) {
+  if (!out || !tree_path || !matrix_path) { g_create_error = "null argument"; return PPM_EINVAL; }
+  *out = nullptr;
+  std::unique_ptr<ppm_engine> e(new ppm_engine);
+  try {
+    try {
+      e->tree = ppm::read_tree_file(tree_path);
+      e->pat = ppm::read_matrix_file(e->tree, matrix_path, dedupe != 0);
+    } catch (const std::runtime_error& x) {
+      g_create_error = x.what();
+      return (g_create_error.rfind("cannot open", 0) == 0) ? PPM_EIO : PPM_EINVAL;
+    }
+    return finish_create_group(out, e, gpu_ids, n_gpus);
+  } catch (const CudaError& x) { g_create_error = x.what(); return PPM_ECUDA; }
+  catch (const std::bad_alloc&) { g_create_error = "out of host memory"; return PPM_ENOMEM; }
+  catch (const std::exception& x) { g_create_error = x.what(); return PPM_EINVAL; }
+}
+
 void ppm_destroy(ppm_handle h) {
   if (!h) return;
   if (h->device >= 0) cudaSetDevice(h->device);
@@ -325,6 +401,7 @@ int ppm_get_info(ppm_handle h, ppm_info* o) {
   o->H = h->tree.H; o->L = h->tree.L; o->mean_genes = h->pat.mean_genes;
   o->device = h->device; o->shard_rank = h->shard_rank; o->shard_world = h->shard_world;
   o->shard_first = h->first; o->shard_count = h->count;
+  o->group_size = (int32_t)h->peers.size() + 1;
   return PPM_OK;
 }
 
@@ -387,8 +464,49 @@ int ppm_finalize_ll_device(ppm_handle h, const double* d_i2, double* d_ll, int32
   GUARD_END(h)
 }
 
+// Group evaluation: every shard runs on its own GPU and stream (one host thread: all launches are asynchronous), each peer
+// stores its P partial sums into the head's gather buffer over NVLink (cudaMemcpyPeerAsync on the peer's stream), the head
+// waits on the peers' events, sums the shards in rank order (bitwise reproducible) and applies the i2 < 0 penalty.
+static int group_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, double* out_i2) {
+  GUARD_BEGIN
+  const std::vector<ppm_engine*> mem = h->members();
+  const int n = (int)mem.size();
+  for (ppm_engine* e : mem) {
+    CK(cudaSetDevice(e->device));
+    e->tables(P, nullptr);
+    CK(cudaMemcpyAsync(e->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, e->stream));
+    int rc = ppm_loglik_device(e, e->d_params.p, P, e->d_ll.p, e->d_i2.p, e->stream);
+    if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
+  }
+  CK(cudaSetDevice(h->device));
+  h->d_gather.alloc((size_t)n * P);
+  for (int k = 1; k < n; k++) {
+    ppm_engine* e = mem[k];
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyPeerAsync(h->d_gather.p + (size_t)k * P, h->device, e->d_ll.p, e->device, sizeof(double) * P, e->stream));
+    CK(cudaEventRecord(e->ev_done, e->stream));
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_gather.p, h->d_ll.p, sizeof(double) * P, cudaMemcpyDeviceToDevice, h->stream));
+  for (int k = 1; k < n; k++) CK(cudaStreamWaitEvent(h->stream, mem[k]->ev_done, 0));
+  ppm::launch_sum_shards(h->d_gather.p, n, P, h->d_ll.p, h->stream);
+  ppm::launch_finalize(h->d_i2.p, h->d_ll.p, P, h->stream);
+  h->n_launches += 2;
+  CK(cudaGetLastError());
+  std::vector<double> i2(P);
+  CK(cudaMemcpyAsync(out_ll, h->d_ll.p, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(i2.data(), h->d_i2.p, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 1; k < n; k++) { CK(cudaSetDevice(mem[k]->device)); CK(cudaStreamSynchronize(mem[k]->stream)); }
+  CK(cudaSetDevice(h->device));
+  if (out_i2) std::copy(i2.begin(), i2.end(), out_i2);
+  return PPM_OK;
+  GUARD_END(h)
+}
+
 int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, double* out_i2) {
   if (!h || !params || !out_ll || P < 1) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  if (h->is_group()) return group_loglik(h, params, P, out_ll, out_i2);
   GUARD_BEGIN
   CK(cudaSetDevice(h->device));
   h->tables(P, nullptr);
@@ -426,7 +544,8 @@ int ppm_compute_i2(ppm_handle h, const double* params, int32_t P, double* out_i2
   GUARD_END(h)
 }
 
-static int eval_one(ppm_handle h, const double* params8, double i2, int8_t* out_cat_genes, double* out_comp) {
+// One shard: categories / components of its slice of the patterns into host buffers (either may be NULL)
+static int eval_shard(ppm_handle h, const double* params8, double i2, signed char* out_cat, double* out_comp) {
   GUARD_BEGIN
   CK(cudaSetDevice(h->device));
   h->n_launches = 0;
@@ -438,32 +557,57 @@ static int eval_one(ppm_handle h, const double* params8, double i2, int8_t* out_
   h->d_cat.alloc((size_t)std::max<long long>(h->count, 1));
   h->d_comp.alloc((size_t)std::max<long long>(h->count, 1) * 3);
   h->run_sweep(t, 2, h->d_ll.p, h->d_cat.p, h->d_comp.p, h->stream);
-  if (out_comp) CK(cudaMemcpyAsync(out_comp, h->d_comp.p, sizeof(double) * 3 * h->count, cudaMemcpyDeviceToHost, h->stream));
-  std::vector<signed char> cat(h->count);
-  if (out_cat_genes && h->count) CK(cudaMemcpyAsync(cat.data(), h->d_cat.p, h->count, cudaMemcpyDeviceToHost, h->stream));
+  if (out_comp && h->count) CK(cudaMemcpyAsync(out_comp, h->d_comp.p, sizeof(double) * 3 * h->count, cudaMemcpyDeviceToHost, h->stream));
+  if (out_cat && h->count) CK(cudaMemcpyAsync(out_cat, h->d_cat.p, h->count, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (out_cat_genes)  // scatter back to the genes of the input, in input order (inf_cat.txt has one value per input row)
-    for (int64_t g = 0; g < h->pat.n_genes; g++) out_cat_genes[g] = cat[h->pat.gene_to_pattern[g]];
   return PPM_OK;
   GUARD_END(h)
 }
+// A plain handle evaluates its own shard; a group head evaluates every shard (contiguous slices in rank order), so the
+// outputs cover all patterns.  Returns the number of patterns covered in *n_out.
+static int eval_members(ppm_handle h, const double* params8, double i2, std::vector<signed char>* cat, std::vector<double>* comp) {
+  long long total = 0;
+  for (ppm_engine* e : h->members()) total += e->count;
+  if (cat) cat->assign((size_t)std::max<long long>(total, 1), 0);
+  if (comp) comp->assign((size_t)std::max<long long>(total, 1) * 3, 0.);
+  long long off = 0;
+  for (ppm_engine* e : h->members()) {
+    int rc = eval_shard(e, params8, i2, cat ? cat->data() + off : nullptr, comp ? comp->data() + 3 * off : nullptr);
+    if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
+    off += e->count;
+  }
+  if (h->device >= 0) cudaSetDevice(h->device);
+  return PPM_OK;
+}
+static bool covers_all(ppm_handle h) { return h->shard_world == 1 || h->is_group(); }
 
 int ppm_assign_cat(ppm_handle h, const double* params8, double i2, int8_t* out_cat) {
   if (!h || !params8 || !out_cat) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
-  if (h->shard_world != 1) { h->err = "ppm_assign_cat needs an unsharded handle"; return PPM_ESTATE; }
-  return eval_one(h, params8, i2, out_cat, nullptr);
+  if (!covers_all(h)) { h->err = "ppm_assign_cat needs an unsharded handle or a group"; return PPM_ESTATE; }
+  std::vector<signed char> cat;
+  int rc = eval_members(h, params8, i2, &cat, nullptr);
+  if (rc) return rc;
+  // scatter back to the genes of the input, in input order (inf_cat.txt has one value per input row)
+  for (int64_t g = 0; g < h->pat.n_genes; g++) out_cat[g] = cat[h->pat.gene_to_pattern[g]];
+  return PPM_OK;
 }
 
 int ppm_components(ppm_handle h, const double* params8, double i2, double* out) {
   if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
-  return eval_one(h, params8, i2, nullptr, out);
+  std::vector<double> comp;
+  int rc = eval_members(h, params8, i2, nullptr, &comp);
+  if (rc) return rc;
+  long long total = 0;
+  for (ppm_engine* e : h->members()) total += e->count;
+  std::copy(comp.begin(), comp.begin() + 3 * total, out);
+  return PPM_OK;
 }
 
 int ppm_proba_cat(ppm_handle h, const double* params8, double i2, double* out) {
   if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
-  if (h->shard_world != 1) { h->err = "ppm_proba_cat needs an unsharded handle"; return PPM_ESTATE; }
-  std::vector<double> comp((size_t)std::max<long long>(h->count, 1) * 3);
-  int rc = eval_one(h, params8, i2, nullptr, comp.data());
+  if (!covers_all(h)) { h->err = "ppm_proba_cat needs an unsharded handle or a group"; return PPM_ESTATE; }
+  std::vector<double> comp;
+  int rc = eval_members(h, params8, i2, nullptr, &comp);
   if (rc) return rc;
   for (int64_t g = 0; g < h->pat.n_genes; g++) {
     const double* c = &comp[(size_t)h->pat.gene_to_pattern[g] * 3];
@@ -474,8 +618,7 @@ int ppm_proba_cat(ppm_handle h, const double* params8, double i2, double* out) {
   return PPM_OK;
 }
 
-int ppm_expected_time1(ppm_handle h, const double* params8, double* out) {
-  if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+static int expected_time1_shard(ppm_handle h, const double* params8, double* out) {
   GUARD_BEGIN
   CK(cudaSetDevice(h->device));
   h->n_launches = 0;
@@ -494,11 +637,19 @@ int ppm_expected_time1(ppm_handle h, const double* params8, double* out) {
   return PPM_OK;
   GUARD_END(h)
 }
+int ppm_expected_time1(ppm_handle h, const double* params8, double* out) {
+  if (!h || !params8 || !out) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  long long off = 0;
+  for (ppm_engine* e : h->members()) {
+    int rc = expected_time1_shard(e, params8, out + off);
+    if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
+    off += e->count;
+  }
+  if (h->device >= 0) cudaSetDevice(h->device);
+  return PPM_OK;
+}
 
-int ppm_expected_time2(ppm_handle h, const double* params8, double* out_times, double* out_dist) {
-  if (!h || !params8) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
-  if (out_times) std::copy(h->tree.slice_t.begin(), h->tree.slice_t.end(), out_times);  // host model: expectedTime2_times
-  if (!out_dist) return PPM_OK;
+static int expected_time2_shard(ppm_handle h, const double* params8, double* out_dist) {
   GUARD_BEGIN
   if (h->md.R != 8) { h->err = "ppm_expected_time2 needs the default program (PPM_R unset)"; return PPM_ESTATE; }
   CK(cudaSetDevice(h->device));
@@ -516,6 +667,20 @@ int ppm_expected_time2(ppm_handle h, const double* params8, double* out_times, d
   CK(cudaStreamSynchronize(h->stream));
   return PPM_OK;
   GUARD_END(h)
+}
+int ppm_expected_time2(ppm_handle h, const double* params8, double* out_times, double* out_dist) {
+  if (!h || !params8) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  if (out_times) std::copy(h->tree.slice_t.begin(), h->tree.slice_t.end(), out_times);  // host model: expectedTime2_times
+  if (!out_dist) return PPM_OK;
+  const size_t row = (size_t)h->tree.n_slices + 1;
+  long long off = 0;
+  for (ppm_engine* e : h->members()) {
+    int rc = expected_time2_shard(e, params8, out_dist + (size_t)off * row);
+    if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
+    off += e->count;
+  }
+  if (h->device >= 0) cudaSetDevice(h->device);
+  return PPM_OK;
 }
 
 int ppm_expected_gains(ppm_handle h, double g2, double* out) {

@@ -431,6 +431,17 @@ __global__ void gather_kernel(const double* table, const int* index, long long n
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s) {
   if (n > 0) gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(table, index, n, out);
 }
+// group evaluation: out[p] = sum over the n shards, in rank order, of gather[k][p]
+__global__ void sum_shards_kernel(const double* gather, int n, int P, double* out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double s = 0.;
+  for (int k = 0; k < n; k++) s += gather[(size_t)k * P + p];
+  out[p] = s;
+}
+void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s) {
+  sum_shards_kernel<<<(P + 127) / 128, 128, 0, s>>>(gather, n, P, out);
+}
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s) {
   finalize_kernel<<<(P + 127) / 128, 128, 0, s>>>(i2, ll, P);
 }

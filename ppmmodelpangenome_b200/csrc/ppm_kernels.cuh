@@ -124,6 +124,7 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s);
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s);
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
+void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s);  // [n][P] -> [P], rank order
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]
 double run_fp64_peak(int device);
 

@@ -27,10 +27,10 @@ class Info(C.Structure):
                 ("n_obs", C.c_int64), ("n_words", C.c_int32), ("n_slices", C.c_int32), ("n_terms", C.c_int64),
                 ("H", C.c_double), ("L", C.c_double), ("mean_genes", C.c_double), ("device", C.c_int32),
                 ("shard_rank", C.c_int32), ("shard_world", C.c_int32), ("shard_first", C.c_int64),
-                ("shard_count", C.c_int64)]
+                ("shard_count", C.c_int64), ("group_size", C.c_int32)]
 
 
-SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_destroy", "ppm_last_error", "ppm_get_info",
+SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_create_group", "ppm_create_group_from_files", "ppm_destroy", "ppm_last_error", "ppm_get_info",
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
            "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_expected_time1",
            "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters",
@@ -51,6 +51,8 @@ def lib():
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         L.ppm_create.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ppm_create_from_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ppm_create_group.argtypes = [vp, vp, vp, vp, i64, C.c_int, vp, i32]
+        L.ppm_create_group_from_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, vp, i32]
         L.ppm_destroy.argtypes = [vp]
         L.ppm_destroy.restype = None
         L.ppm_last_error.argtypes = [vp]
@@ -99,11 +101,19 @@ class Inference:
     Inference.from_arrays(left, right, bl, rows)  flat preorder tree + bit-packed patterns
     """
 
-    def __init__(self, tree_path=None, pa_path=None, dedupe=True, device=0, shard_rank=0, shard_world=1, _handle=None):
+    def __init__(self, tree_path=None, pa_path=None, dedupe=True, device=0, shard_rank=0, shard_world=1, _handle=None,
+                 devices=None):
+        """devices=[ids]: a GROUP handle, one pattern shard per listed GPU behind one object (ppm_create_group*)."""
         self._h = C.c_void_p()
         L = lib()
         if _handle is not None:
             self._h = _handle
+        elif devices is not None:
+            ids = np.ascontiguousarray(devices, np.int32)
+            rc = L.ppm_create_group_from_files(C.byref(self._h), os.fsencode(tree_path), os.fsencode(pa_path), int(dedupe),
+                                               ids.ctypes.data, len(ids))
+            if rc:
+                raise PPMError(rc, L.ppm_last_error(None).decode())
         else:
             rc = L.ppm_create_from_files(C.byref(self._h), os.fsencode(tree_path), os.fsencode(pa_path), int(dedupe),
                                          int(device), int(shard_rank), int(shard_world))
@@ -119,7 +129,7 @@ class Inference:
 
     @classmethod
     def from_arrays(cls, left, right, branch_len, packed_rows, counts=None, dedupe=True, device=0, shard_rank=0,
-                    shard_world=1):
+                    shard_world=1, devices=None):
         left = np.ascontiguousarray(left, np.int32)
         right = np.ascontiguousarray(right, np.int32)
         bl = np.ascontiguousarray(branch_len, np.float64)
@@ -128,8 +138,13 @@ class Inference:
         cnt = None if counts is None else np.ascontiguousarray(counts, np.int32)
         h = C.c_void_p()
         L = lib()
-        rc = L.ppm_create(C.byref(h), C.byref(t), rows.ctypes.data, None if cnt is None else cnt.ctypes.data,
-                          rows.shape[0], int(dedupe), int(device), int(shard_rank), int(shard_world))
+        if devices is not None:
+            ids = np.ascontiguousarray(devices, np.int32)
+            rc = L.ppm_create_group(C.byref(h), C.byref(t), rows.ctypes.data, None if cnt is None else cnt.ctypes.data,
+                                    rows.shape[0], int(dedupe), ids.ctypes.data, len(ids))
+        else:
+            rc = L.ppm_create(C.byref(h), C.byref(t), rows.ctypes.data, None if cnt is None else cnt.ctypes.data,
+                              rows.shape[0], int(dedupe), int(device), int(shard_rank), int(shard_world))
         if rc:
             raise PPMError(rc, L.ppm_last_error(None).decode())
         return cls(_handle=h)
@@ -145,6 +160,10 @@ class Inference:
             self.close()
         except Exception:
             pass
+
+    def _n_out(self):
+        """patterns covered by the per-pattern outputs: this shard's slice, or everything for a group handle"""
+        return self.info.n_patterns if self.info.group_size > 1 else self.info.shard_count
 
     def _ck(self, rc):
         if rc:
@@ -208,7 +227,7 @@ class Inference:
         p = _params(params8)
         if i2 is None:
             i2 = self.computeI2(p[0])
-        n = self.info.shard_count
+        n = self._n_out()
         out = np.zeros((max(n, 1), 3))
         self._ck(lib().ppm_components(self._h, p.ctypes.data, float(i2), out.ctypes.data))
         return out[:n]
@@ -225,7 +244,7 @@ class Inference:
     def expectedTime1(self, params8):
         """Expected introduction time of every pattern of this shard taken as a Private gene (functions.cpp:637-708)."""
         p = _params(params8)
-        n = self.info.shard_count
+        n = self._n_out()
         out = np.zeros(max(n, 1))
         self._ck(lib().ppm_expected_time1(self._h, p.ctypes.data, out.ctypes.data))
         return out[:n]
@@ -234,7 +253,7 @@ class Inference:
         """(times[S], dist[nPatterns, S+1]): slice mid-points (expectedTime2_times), the Mobile integrand per slice
         (expectedTime2_aux) and, last column, exp(likRep2) (functions.cpp:709-757)."""
         p = _params(params8)
-        n, S = self.info.shard_count, self.info.n_slices
+        n, S = self._n_out(), self.info.n_slices
         times = np.zeros(max(S, 1))
         dist = np.zeros((max(n, 1), S + 1))
         self._ck(lib().ppm_expected_time2(self._h, p.ctypes.data, times.ctypes.data, dist.ctypes.data))

@@ -24,7 +24,7 @@ def _run(tmp_path, args, env=None):
     return r.stdout.splitlines(), open(mle).read(), open(cat).read()
 
 
-@pytest.mark.parametrize("env", [{}, {"PPM_DEDUPE": "0", "PPM_SPECULATE": "0"}])
+@pytest.mark.parametrize("env", [{}, {"PPM_DEDUPE": "0", "PPM_SPECULATE": "0"}, {"PPM_GPU_IDS": "0,0"}])  # last: a two-shard group
 def test_seed1_fit_matches_reference_cli(tmp_path, env):
     out, mle, cat = _run(tmp_path, ["1"], env)
     gold_out = open(os.path.join(GOLD, "e2e_seed1.stdout.txt")).read().splitlines()

@@ -229,3 +229,32 @@ def test_posterior_outputs_global_memory_variant(ppm, golden):
     assert fin.sum() > 0
     assert np.allclose(lik2[fin], comp[fin, 2], rtol=1e-12, atol=1e-12)
     inf.close()
+
+
+def test_group_handle_matches_unsharded_handle(ppm, golden):
+    """ppm_create_group*: three pattern shards behind one handle (device ids may repeat, so this also runs on a
+    one-GPU box; on a multi-GPU box the same code shards over NVLink peers).  The objective equals the unsharded one
+    to summation-order accuracy, penalties included; per-pattern outputs are identical."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = [k % ndev for k in range(3)]
+    for name in ("ref_test", "syn300"):
+        g = golden(name)
+        one = _engine(ppm, g, dedupe=True)
+        grp = ppm.Inference(g.tree, g.pa, dedupe=True, devices=devs)
+        assert grp.info.group_size == 3 and grp.nRep == one.nRep
+        ll1, i21 = one.loglik_batch(g.params, return_i2=True)
+        ll3, i23 = grp.loglik_batch(g.params, return_i2=True)
+        assert np.array_equal(i21, i23)
+        assert np.allclose(ll3, ll1, rtol=1e-13, atol=0)
+        for k, r in enumerate(g.results):
+            assert rel(ll3[k], r["ll"]) <= RTOL
+        assert np.array_equal(ll3, grp.loglik_batch(g.params))  # reproducible
+        k = 2 if name == "ref_test" else 0
+        p, i2 = g.params[k], g.results[k]["i2"]
+        assert np.array_equal(grp.assignCat(p, i2), one.assignCat(p, i2))
+        # (the integral's summation order depends on which patterns share a warp: not bitwise)
+        assert np.allclose(grp.components(p, i2), one.components(p, i2), rtol=1e-13, atol=0)
+        assert np.array_equal(grp.expectedTime1(p), one.expectedTime1(p))
+        assert np.allclose(grp.computeProbaCat(p, i2), one.computeProbaCat(p, i2), rtol=1e-12, atol=1e-12)
+        grp.close(); one.close()
