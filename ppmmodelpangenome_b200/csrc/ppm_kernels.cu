@@ -392,10 +392,12 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
 
 template <int R, int MODE, bool DIST = false>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};  // the attribute is per device (group handles launch on several)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   sweep_kernel<R, kItemsPerWarp, MODE, DIST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
