@@ -536,6 +536,47 @@ Program build_program(const Tree& t, int R, bool deep) {
     }
   }
   double fp64 = 0;
+  // Events folded into node ops: a lineage born inside block b multiplies its alive slices of b at its own op (its
+  // partials are in registers there), a lineage that dies inside block b -- when its parent is formed -- multiplies its
+  // prefix of b at the parent's op (the merge has just loaded its partials).  Those entries leave the block's lists; what
+  // stays partial (leaves that start above the first slice: non-ultrametric trees only) keeps the generic partial loops.
+  pg.op_tb.assign(pg.ops.size(), t.H);
+  {
+    std::vector<int> op_of(nn, -1);
+    for (size_t o = 0; o < pg.ops.size(); o++) op_of[pg.ops[o].node] = (int)o;
+    for (size_t o = 0; o < pg.ops.size(); o++) {
+      const int b = op_block[pg.ops[o].node];
+      if (b < nb) pg.op_tb[o] = t.slice_t[pg.blk[b].slice0];
+    }
+    const bool fold = std::getenv("PPM_NO_FOLD") == nullptr;
+    for (int b = 0; b < nb && fold; b++) {
+      const int nsl = pg.blk[b].nslices;
+      std::vector<Ent> keep;
+      for (const Ent& e : ent[b]) {
+        const bool full = e.i0 == 0 && e.i1 == nsl;
+        const uint32_t live = (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
+        const int v = e.node, par = t.parent[v];
+        bool folded = false;
+        if (!full) {
+          if (!e.leaf && op_of[v] >= 0 && op_block[v] == b) {           // born in this block: own op
+            pg.sops[op_of[v]].mself = (int32_t)live; folded = true;
+            fp64 += 1 + 2 * (e.i1 - e.i0);
+          } else if (e.i0 == 0 && op_of[par] >= 0 && op_block[par] == b) {  // dies in this block: the parent's op
+            SweepOp& sp = pg.sops[op_of[par]];
+            if (sp.pair >= 0) {  // cherry: both leaves die together; one quadratic in u for the two (first member counts)
+              if (sp.ml == 0) { sp.ml = (int32_t)live; fp64 += 3 * (e.i1 - e.i0); }
+              folded = true;
+            } else {
+              (t.left[par] == v ? sp.ml : sp.mr) = (int32_t)live; folded = true;
+              fp64 += 1 + 2 * (e.i1 - e.i0);
+            }
+          }
+        }
+        if (!folded) keep.push_back(e);
+      }
+      ent[b].swap(keep);
+    }
+  }
   for (int b = 0; b < nb; b++) {
     const int nsl = pg.blk[b].nslices;
     auto is_full = [&](const Ent& e) { return e.i0 == 0 && e.i1 == nsl; };  // in a short last block the padding slices carry weight 0

@@ -71,6 +71,11 @@ struct SweepOp {
   int32_t dst, i0;       // as NodeOp
   int32_t flags;         // bit 0: left child is a leaf, bit 1: right child is a leaf
   int32_t pair;          // as NodeOp
+  // Events folded into the op (slice masks of the op's block, 0 = nothing to do): the new node's own alive slices when it
+  // is born inside the block, and the alive slices of a child that dies with this op after being born in an EARLIER block
+  // (a prefix of the block).  These lineages have no entry record in that block.
+  int32_t mself, ml, mr;
+  int32_t pad_;
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
   int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end;
@@ -84,6 +89,7 @@ struct Program {
   std::vector<NodeOp> ops;
   std::vector<SweepOp> sops;                      // [ops.size() + 1] (one padding record)
   std::vector<int32_t> cherry_op;                 // [n_cherries] op index of each cherry pair
+  std::vector<double> op_tb;                      // [ops.size()] start time of the op's block (the K of its folded events)
   std::vector<int32_t> entry_ref;                 // see EntryRec::ref (ppm_kernels.cuh)
   std::vector<uint32_t> entry_mask;               // see EntryRec::mask
   std::vector<int32_t> entry_node, entry_block;   // node id / block of each entry (for the K table)

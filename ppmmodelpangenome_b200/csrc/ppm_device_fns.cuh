@@ -257,6 +257,12 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     const double2 kl = t.kap[(size_t)p * m.n_nodes + op.lnode], kr = t.kap[(size_t)p * m.n_nodes + op.rnode];
     double* r = t.oprec + ((size_t)p * m.n_ops + o) * OPREC_DOUBLES;
     r[0] = kl.x; r[1] = kl.y; r[2] = kr.x; r[3] = kr.y;
+    // K of the events folded into the op (children dying, the node being born) for the op's block, as in the entry records
+    const double tb = m.op_tb[o];
+    r[4] = pi1 * exp(-lam * (tb - m.height[op.lnode]));
+    r[5] = pi1 * exp(-lam * (tb - m.height[op.rnode]));
+    r[6] = pi1 * exp(-lam * (tb - m.height[op.node]));
+    r[7] = 0.;
   } else if (i <= m.n_entries + n_pad + m.n_ops + m.n_leaves + m.n_pairs) {
     // u-form leaf terms.  A leaf s at height h_s (numerically 0) observed as x contributes, at time t,
     //   (1-q) m0_x + q m1_x,  q = pi1 (1 - exp(-lam (t - h_s)))                       (functions.cpp:232-240)
@@ -512,6 +518,18 @@ PPM_HD void coded_update(double (&prod)[NI][R], const double (&Y)[R], const doub
   }
 }
 
+// prod[i] *= a + nbb*Y[i] on the slices of a warp-uniform mask (events folded into node ops)
+template <int R, int NI>
+PPM_HD void live_update(double (&prod)[NI][R], const double (&Y)[R], const double (&a)[NI], const double (&nbb)[NI], uint32_t live) {
+#pragma unroll
+  for (int q = 0; q < NI; q++)
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const double t = prod[q][i] * fma(nbb[q], Y[i], a[q]);
+      prod[q][i] = (live & (1u << i)) ? t : prod[q][i];
+    }
+}
+
 PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) += v * 2^-e ; Ie starts at INT_MAX/2
   if (v != 0.) {
     const int en = e < Ie ? e : Ie;
@@ -581,7 +599,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // ---- node ops: form every node born before the end of this block.
     // store a new lineage (a, d); when it has become small its mantissa is brought back to [0.5,1) and the shift
     // goes to X / ex[] (one integer test per lane on the high words; the exact shift only on the rare path)
-    auto store_node = [&](int q, int dst, int i0, double av, double d) {
+    auto store_node = [&](int q, int dst, int i0, double& av, double& d) {
       const int ha = ppm_double2hiint(av) & 0x7fffffff, hd = ppm_double2hiint(d) & 0x7fffffff;
       const int h = ha > hd ? ha : hd;
       const bool small = (uint32_t)(h - 0x00100000) < (uint32_t)(((1023 - 40) << 20) - 0x00100000);  // 0 < exponent < 983
@@ -604,10 +622,38 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       const SweepOpDev op = opn;
       opn = T.ops[o + 1];
 #pragma unroll
+      double av[NI], dd[NI];
+#pragma unroll
       for (int q = 0; q < NI; q++) {
         const uint32_t w = mem[q].sw[(op.lbit >> 5) * PPM_LANES + lane];
-        const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.cherry + op.pair * 4) + (rotr32(w, (uint32_t)op.lbit) & 0x30u));
-        store_node(q, op.dst, op.i0, v.x, v.y);
+        const uint32_t sel = rotr32(w, (uint32_t)op.lbit) & 0x30u;  // observation pair x 16
+        const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.cherry + op.pair * 4) + sel);
+        av[q] = v.x; dd[q] = v.y;
+        if (op.ml) {  // the two leaves die here: their slices of this block as one quadratic in u (as in the pair loop)
+          const double4 qv = *reinterpret_cast<const double4*>(reinterpret_cast<const char*>(T.pairq + op.pair * 4) + 2 * sel);
+          if (!factored) {
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+              const double t = prod[q][i] * fma(fma(qv.z, U[i], qv.y), U[i], qv.x);
+              prod[q][i] = ((uint32_t)op.ml & (1u << i)) ? t : prod[q][i];
+            }
+          } else {
+            const double2 fa = T.leafab[(2 * op.pair) * 2 + (int)((sel >> 4) & 1u)], fb = T.leafab[(2 * op.pair + 1) * 2 + (int)(sel >> 5)];
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+              const double t = prod[q][i] * (fma(fa.y, U[i], fa.x) * fma(fb.y, U[i], fb.x));
+              prod[q][i] = ((uint32_t)op.ml & (1u << i)) ? t : prod[q][i];
+            }
+          }
+        }
+        store_node(q, op.dst, op.i0, av[q], dd[q]);
+      }
+      if (op.mself) {
+        const double nK = -(T.oprec + (size_t)o * OPREC_DOUBLES)[6];
+        double nbb[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) nbb[q] = dd[q] * nK;
+        live_update<R, NI>(prod, Y, av, nbb, (uint32_t)op.mself);
       }
     }
     // general merges: a leaf child comes from the two-entry leaf table (picked by its pattern bit), an internal one
@@ -631,16 +677,37 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
         Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
       }
+      if (op.ml) {  // a child that dies with this op multiplies its slices of the block here (it has no entry record)
+        double aa[NI], nbb[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) { aa[q] = L[q].x; nbb[q] = L[q].y * -orc[4]; }
+        live_update<R, NI>(prod, Y, aa, nbb, (uint32_t)op.ml);
+      }
+      if (op.mr) {
+        double aa[NI], nbb[NI];
+#pragma unroll
+        for (int q = 0; q < NI; q++) { aa[q] = Rr[q].x; nbb[q] = Rr[q].y * -orc[5]; }
+        live_update<R, NI>(prod, Y, aa, nbb, (uint32_t)op.mr);
+      }
       if (op.dst >= 0) {
+        double av[NI], dd[NI];
 #pragma unroll
         for (int q = 0; q < NI; q++) {
-          double av, d;
-          merge_children(L[q], Rr[q], orc, pi1, av, d);
-          store_node(q, op.dst, op.i0, av, d);
+          merge_children(L[q], Rr[q], orc, pi1, av[q], dd[q]);
+          store_node(q, op.dst, op.i0, av[q], dd[q]);
+        }
+        if (op.mself) {  // ... and so does the new node when it is born inside the block
+          double nbb[NI];
+#pragma unroll
+          for (int q = 0; q < NI; q++) nbb[q] = dd[q] * -orc[6];
+          live_update<R, NI>(prod, Y, av, nbb, (uint32_t)op.mself);
         }
       }
     }
     if (!real) break;
+#pragma unroll
+    for (int q = 0; q < NI; q++)
+      if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
 
     // ---- entries alive in every slice of the block: first the internal lineages (partials in slots), then the
     // leaves (partials selected by the pattern bit).

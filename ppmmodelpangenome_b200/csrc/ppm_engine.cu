@@ -87,7 +87,7 @@ struct ppm_engine {
   DevBuf<int> d_leaf_node, d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
   DevBuf<ppm::BlockDesc> d_blk;
   DevBuf<uint32_t> d_entry_mask;
-  DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt;
+  DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt, d_op_tb;
   DevBuf<ppm::NodeOpDev> d_ops;
   DevBuf<uint32_t> d_words, d_zero_words;
   DevBuf<int> d_counts, d_mrca, d_freq;
@@ -158,6 +158,7 @@ struct ppm_engine {
     std::vector<ppm::SweepOpDev> sops(prog.sops.size());
     if (!sops.empty()) std::memcpy(sops.data(), prog.sops.data(), sops.size() * sizeof(ppm::SweepOp));
     d_sops.upload(sops, stream);
+    { std::vector<double> tb(prog.op_tb); if (tb.empty()) tb.assign(1, 0.); d_op_tb.upload(tb, stream); }
     { std::vector<int> co(prog.cherry_op); if (co.empty()) co.assign(1, 0); d_cherry_op.upload(co, stream); }
     std::vector<ppm::BlockDesc> blk(prog.blk.size());
     std::memcpy(blk.data(), prog.blk.data(), blk.size() * sizeof(ppm::BlockDesc));
@@ -189,7 +190,7 @@ struct ppm_engine {
     md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
     md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p;
     md.slice_t = d_slice_t.p; md.slice_wt_pad = d_slice_wt.p;
-    md.blk = d_blk.p; md.ops = d_ops.p; md.sops = d_sops.p; md.cherry_op = d_cherry_op.p; md.n_cherries = prog.n_cherries;
+    md.blk = d_blk.p; md.ops = d_ops.p; md.sops = d_sops.p; md.op_tb = d_op_tb.p; md.cherry_op = d_cherry_op.p; md.n_cherries = prog.n_cherries;
     md.n_pairs = prog.n_pairs; md.leaf_node = d_leaf_node.p;
     md.entry_ref = d_entry_ref.p; md.entry_mask = d_entry_mask.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
     md.words = d_words.p; md.n_pat = count; md.n_pat_pad = n_pat_pad;

@@ -27,6 +27,7 @@ struct NodeOpDev {  // == ppm::NodeOp
 };
 struct __align__(16) SweepOpDev {  // == ppm::SweepOp (host_model.h): what the sweep reads per node op
   int32_t lslot, rslot, lbit, rbit, dst, i0, flags, pair;
+  int32_t mself, ml, mr, pad_;  // slice masks of the events folded into the op (host_model.h)
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
   // [e_slot0,e_pair0)   internal lineages alive in every slice (partials in slots)
@@ -44,7 +45,8 @@ struct __align__(16) EntryRec {
   uint32_t mask;  // K/Y leaves: the leaf's bit inside its word;  pairs: position A | position B << 16;
                   // partial entries: code | live slices << 16;  otherwise unused
 };
-enum { OPREC_DOUBLES = 4 };  // per (parameter vector, node op): kap_l{x,y} kap_r{x,y}
+enum { OPREC_DOUBLES = 8 };  // per (parameter vector, node op): kap_l{x,y} kap_r{x,y} | K of the left child, the right child and the
+                             // new node for the op's block (folded events) | unused
 
 struct ModelDev {
   int n_nodes, n_leaves, n_words, n_slices, n_blocks, n_slots, n_entries, n_ops, R;
@@ -65,6 +67,7 @@ struct ModelDev {
   const BlockDesc* blk;     // [n_blocks + 1]; the last one only carries the tail node ops
   const NodeOpDev* ops;
   const SweepOpDev* sops;   // [n_ops]
+  const double* op_tb;      // [n_ops] start time of each op's block
   const int* cherry_op; int n_cherries;  // op index of each cherry (the first n_cherries static pairs)
   const int* entry_ref; const uint32_t* entry_mask; const int* entry_node; const int* entry_block;  // [n_entries]
   // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq

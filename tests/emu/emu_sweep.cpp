@@ -66,6 +66,8 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data());
     static_assert(sizeof(SweepOpDev) == sizeof(SweepOp), "layout");
     md.sops = reinterpret_cast<const SweepOpDev*>(prog.sops.data());
+    std::vector<double> op_tb(prog.op_tb); if (op_tb.empty()) op_tb.assign(1, 0.);
+    md.op_tb = op_tb.data();
     std::vector<int> cherry_op(prog.cherry_op); if (cherry_op.empty()) cherry_op.assign(1, 0);
     md.cherry_op = cherry_op.data(); md.n_cherries = prog.n_cherries;
     md.entry_ref = prog.entry_ref.data(); md.entry_mask = prog.entry_mask.data();
