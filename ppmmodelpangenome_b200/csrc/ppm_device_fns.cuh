@@ -62,6 +62,24 @@ PPM_HD double pow2i(int k) {  // 2^k for k in [-1022, 1023]
   return ppm_hiloint2double((1023 + k) << 20, 0);
 }
 PPM_HD int biased_exp(double x) { return (ppm_double2hiint(x) >> 20) & 0x7ff; }
+PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) += v * 2^-e ; Ie starts at INT_MAX/2
+  if (v != 0.) {
+    const int en = e < Ie ? e : Ie;
+    int d1 = Ie - en, d2 = e - en;   // one of them is 0
+    d1 = d1 > 1000 ? 1000 : d1; d2 = d2 > 1000 ? 1000 : d2;
+    Im = fma(Im, pow2i(-d1), v * pow2i(-d2));
+    Ie = en;
+  }
+}
+
+// Mobile merge of two child lineages (x, y) = (a, d): m0 = x - k0 y, m1 = x + k1 y along each child's branch, multiplied
+// (objects.cpp:427-435 in the linear domain); orc = {k0_l, k1_l, k0_r, k1_r}.  Returns the parent's (a, d), not renormalised.
+PPM_HD void merge_children(double2 L, double2 Rr, const double* orc, double pi1, double& av, double& d) {
+  const double m0 = fma(-orc[0], L.y, L.x) * fma(-orc[2], Rr.y, Rr.x);
+  const double m1 = fma(orc[1], L.y, L.x) * fma(orc[3], Rr.y, Rr.x);
+  d = m1 - m0;
+  av = fma(pi1, d, m0);
+}
 
 // ------------------------------------------------------------------------------------------------ prepass
 #if defined(__CUDA_ARCH__)
@@ -123,6 +141,27 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
         zl1 = cls[a].w + cls[b].w;
       }
       z0[v] = zl0; z1[v] = zl1;
+      if (t.zrow) {
+        // Mobile partials of the all-zero row (the zero-row integral no longer runs through the sweep): leaves observe 0
+        // (objects.cpp:407-408), internal nodes merge their children as the sweep does, renormalised the same way
+        double2* zr = t.zrow + (size_t)p * nn;
+        int* zk = t.zk + (size_t)p * nn;
+        if (leaf) {
+          const double m0 = 1 - e1, m1 = e2;
+          zr[v] = make_double2(m0 + pi1 * (m1 - m0), m1 - m0); zk[v] = 0;
+        } else {
+          const int a = m.left[v], b = m.right[v];
+          const double orc[4] = {kap[a].x, kap[a].y, kap[b].x, kap[b].y};
+          double av, d;
+          merge_children(zr[a], zr[b], orc, pi1, av, d);
+          const int ha = ppm_double2hiint(av) & 0x7fffffff, hd = ppm_double2hiint(d) & 0x7fffffff;
+          const int h = ha > hd ? ha : hd;
+          const bool small = (uint32_t)(h - 0x00100000) < (uint32_t)(((1023 - 40) << 20) - 0x00100000);
+          const int k = small ? 1022 - (h >> 20) : 0;
+          const double sfac = pow2i(k);
+          zr[v] = make_double2(av * sfac, d * sfac); zk[v] = k;
+        }
+      }
       const double bl = m.bl[v];
       double4 c = cls[v];
       c.y = lse2(c.y, -l0 * bl + zl0);
@@ -201,12 +240,6 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
 // Mobile merge of two child lineages given as (a, d) = (m0 + pi1 (m1-m0), m1-m0) ... the children's stored form is
 // (x, y) with m0 = x - k0 y, m1 = x + k1 y along their branches (objects.cpp:427-435 in the linear domain);
 // orc = {k0_l, k1_l, k0_r, k1_r}.  Returns the parent's (a, d), not yet renormalised.
-PPM_HD void merge_children(double2 L, double2 Rr, const double* orc, double pi1, double& av, double& d) {
-  const double m0 = fma(-orc[0], L.y, L.x) * fma(-orc[2], Rr.y, Rr.x);
-  const double m1 = fma(orc[1], L.y, L.x) * fma(orc[3], Rr.y, Rr.x);
-  d = m1 - m0;
-  av = fma(pi1, d, m0);
-}
 
 PPM_HD double pack2i(int lo, int hi) {
   const long long b = ((long long)hi << 32) | (long long)(uint32_t)lo;
@@ -303,6 +336,120 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
       merge_children(leaftab[x & 1], leaftab[x >> 1], orc, pi1, av, d);
       t.cherry[((size_t)p * m.n_cherries + c) * 4 + x] = make_double2(av, d);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ zero row
+// Mobile integral of the all-zero row (getPobs2, functions.cpp:300-333 = likRep2 on the row add0() appends).  The row's
+// partials are per-parameter constants per node (zrow/zk, node prepass), so its slices are independent: one thread per
+// slice walks the entry records and the folded events of the slice's block and multiplies exactly the factors the sweep
+// would (same tables, same K*Y form), with its own range checks.  One CTA per parameter vector; the slice values are
+// reduced in a fixed order with exponent alignment.
+PPM_HD void zero_row_slice(const ModelDev& m, const TablesDev& t, int p, int j) {
+  const int R = m.R, b = j / R, i = j - b * R;
+  const double* sc = t.scal + (size_t)p * SC_COUNT;
+  const double2* zr = t.zrow + (size_t)p * m.n_nodes;
+  const int* zk = t.zk + (size_t)p * m.n_nodes;
+  const EntryRec* recs = t.recs + (size_t)p * (m.n_entries + 1);
+  const int nbR = m.n_blocks * R;
+  const double Y = t.yy[(size_t)p * nbR + j], U = t.uu[(size_t)p * nbR + j];
+  const bool factored = sc[SC_FACTORED] != 0.;
+  const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], pi1 = sc[SC_PI1];
+  (void)pi1;
+  const BlockDesc bd = m.blk[b];
+  double prod = 1.;
+  int ex = t.zxb[(size_t)p * (m.n_blocks + 1) + b];
+  int nfac = 0;
+  auto mul = [&](double f) {
+    prod *= f;
+    if ((++nfac & 15) == 0) {
+      const int be = biased_exp(prod);
+      if (be != 0 && be < 1023 - 480) { prod *= pow2i(480); ex += 480; }
+    }
+  };
+  const uint32_t bit = 1u << i;
+  // node ops of the block: shifts of the nodes alive from this slice on, and the folded events
+  for (int o = bd.op0; o < bd.op1; o++) {
+    const SweepOpDev op = m.sops[o];
+    const NodeOpDev nd = m.ops[o];
+    const double* orc = t.oprec + ((size_t)p * m.n_ops + o) * OPREC_DOUBLES;
+    if (op.dst >= 0 && i >= op.i0) ex += zk[nd.node];
+    if (op.pair >= 0) {  // cherry: the two leaves as one quadratic in u (observation pair 0)
+      if ((uint32_t)op.ml & bit) {
+        if (!factored) {
+          const double4 q = t.pairq[((size_t)p * m.n_pairs + op.pair) * 4];
+          mul(fma(fma(q.z, U, q.y), U, q.x));
+        } else {
+          const double2 fa = t.leafab[((size_t)p * m.n_leaves + 2 * op.pair) * 2], fb = t.leafab[((size_t)p * m.n_leaves + 2 * op.pair + 1) * 2];
+          mul(fma(fa.y, U, fa.x) * fma(fb.y, U, fb.x));
+        }
+      }
+    } else {
+      if ((uint32_t)op.ml & bit) {
+        const bool lf = op.flags & 1;
+        const double a = lf ? la0 : zr[nd.lnode].x, d = lf ? ld0 : zr[nd.lnode].y;
+        mul(fma(d * -orc[4], Y, a));
+      }
+      if ((uint32_t)op.mr & bit) {
+        const bool lf = op.flags & 2;
+        const double a = lf ? la0 : zr[nd.rnode].x, d = lf ? ld0 : zr[nd.rnode].y;
+        mul(fma(d * -orc[5], Y, a));
+      }
+    }
+    if ((uint32_t)op.mself & bit) mul(fma(zr[nd.node].y * -orc[6], Y, zr[nd.node].x));
+  }
+  // internal lineages alive in the whole block (padding records of the deep program refer to the constant row: skip)
+  for (int e = bd.e_slot0; e < bd.e_pair0; e++) {
+    if ((recs[e].ref & 0xffff) == m.n_slots) continue;
+    const double2 ad = zr[m.entry_node[e]];
+    mul(fma(ad.y * -recs[e].K, Y, ad.x));
+  }
+  // leaf pairs / single leaves in u-form, observation 0
+  for (int e = bd.e_pair0; e < bd.e_leafu0; e++) {
+    const int pid = m.entry_ref[e] & 0xffff;
+    if (!factored) {
+      const double4 q = t.pairq[((size_t)p * m.n_pairs + pid) * 4];
+      mul(fma(fma(q.z, U, q.y), U, q.x));
+    } else {
+      const double2 fa = t.leafab[((size_t)p * m.n_leaves + 2 * pid) * 2], fb = t.leafab[((size_t)p * m.n_leaves + 2 * pid + 1) * 2];
+      mul(fma(fa.y, U, fa.x) * fma(fb.y, U, fb.x));
+    }
+  }
+  for (int e = bd.e_leafu0; e < bd.e_leaf0; e++) {
+    const double2 f = t.leafab[((size_t)p * m.n_leaves + (m.entry_ref[e] & 0xffff)) * 2];
+    mul(fma(f.y, U, f.x));
+  }
+  // leaves in K/Y form (trees with tall leaves), whole block or part of it; internal lineages still listed as partial
+  for (int e = bd.e_leaf0; e < bd.e_pleaf0; e++) mul(fma(ld0 * -recs[e].K, Y, la0));
+  for (int e = bd.e_pleaf0; e < bd.e_pslot0; e++)
+    if ((recs[e].mask >> 16) & bit) mul(fma(ld0 * -recs[e].K, Y, la0));
+  for (int e = bd.e_pslot0; e < bd.e_end; e++)
+    if ((recs[e].mask >> 16) & bit) { const double2 ad = zr[m.entry_node[e]]; mul(fma(ad.y * -recs[e].K, Y, ad.x)); }
+  t.zpart[(size_t)p * m.n_slices + j] = make_double2(prod * m.slice_wt_pad[j], (double)ex);
+}
+
+// CTA-wide: (1) shifts accumulated before each block, (2) the slices, (3) the fixed-order sum.  tid/nt as in the node prepass.
+PPM_HD void zero_row_body(const ModelDev& m, const TablesDev& t, int p, int tid, int nt) {
+  int* zxb = t.zxb + (size_t)p * (m.n_blocks + 1);
+  const int* zk = t.zk + (size_t)p * m.n_nodes;
+  if (tid == 0) {
+    int acc = 0;
+    for (int b = 0; b <= m.n_blocks; b++) {
+      zxb[b] = acc;
+      const BlockDesc bd = m.blk[b];
+      for (int o = bd.op0; o < bd.op1; o++)
+        if (m.sops[o].dst >= 0) acc += zk[m.ops[o].node];
+    }
+  }
+  PPM_CTA_BARRIER();
+  for (int j = tid; j < m.n_slices; j += nt) zero_row_slice(m, t, p, j);
+  PPM_CTA_BARRIER();
+  if (tid == 0) {  // sum of mantissa * 2^-exponent in slice order
+    double Im = 0.; int Ie = 0x3fffffff;
+    const double2* zp = t.zpart + (size_t)p * m.n_slices;
+    for (int j = 0; j < m.n_slices; j++) scaled_add(Im, Ie, zp[j].x, (int)zp[j].y);
+    double* scw = t.scal + (size_t)p * SC_COUNT;
+    scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
   }
 }
 
@@ -530,15 +677,6 @@ PPM_HD void live_update(double (&prod)[NI][R], const double (&Y)[R], const doubl
     }
 }
 
-PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) += v * 2^-e ; Ie starts at INT_MAX/2
-  if (v != 0.) {
-    const int en = e < Ie ? e : Ie;
-    int d1 = Ie - en, d2 = e - en;   // one of them is 0
-    d1 = d1 > 1000 ? 1000 : d1; d2 = d2 > 1000 ? 1000 : d2;
-    Im = fma(Im, pow2i(-d1), v * pow2i(-d2));
-    Ie = en;
-  }
-}
 
 // NI work items at once = NI x PPM_LANES patterns (one per lane and item) x one parameter vector.
 // Everything topology-driven (records, block descriptors, node-op descriptors, branches, address arithmetic) is

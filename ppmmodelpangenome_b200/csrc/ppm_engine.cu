@@ -104,7 +104,8 @@ struct ppm_engine {
   DevBuf<double2> d_leafab;
   DevBuf<double> d_params, d_yy, d_uu, d_oprec, d_scal, d_zeta, d_partial, d_ll, d_i2, d_comp, d_i2_override, d_et1, d_dist, d_gather;
   DevBuf<double4> d_cls;
-  DevBuf<double2> d_kap, d_d1u, d_gslots, d_clsT, d_a01;
+  DevBuf<double2> d_kap, d_d1u, d_gslots, d_clsT, d_a01, d_zrow, d_zpart;
+  DevBuf<int> d_zk, d_zxb;
   DevBuf<signed char> d_cat;
   size_t partial_cap = 0;
 
@@ -209,11 +210,14 @@ struct ppm_engine {
       d_clsT.alloc((size_t)P * nn); d_a01.alloc((size_t)P * std::max<long long>(n_pat_pad, 32));
       d_scal.alloc((size_t)P * ppm::SC_COUNT); d_zeta.alloc((size_t)P * 6 * nn);
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
+      d_zrow.alloc((size_t)P * nn); d_zk.alloc((size_t)P * nn); d_zxb.alloc((size_t)P * (std::max(prog.n_blocks, 1) + 1));
+      d_zpart.alloc((size_t)P * std::max(tree.n_slices, 1));
       P_cap = P;
     }
     ppm::TablesDev t{};
     t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p; t.cherry = d_cherry.p;
-    t.scal = d_scal.p; t.zeta = d_zeta.p; t.et1 = nullptr;  // expectedTime1 tables only on request
+    t.scal = d_scal.p; t.zeta = d_zeta.p; t.et1 = nullptr;
+    t.zrow = d_zrow.p; t.zk = d_zk.p; t.zxb = d_zxb.p; t.zpart = d_zpart.p;  // expectedTime1 tables only on request
     return t;
   }
 
@@ -221,11 +225,7 @@ struct ppm_engine {
   void run_prepass(const ppm::TablesDev& t, const double* d_i2_ovr, cudaStream_t s) {
     ppm::launch_prepass_nodes(md, t, s);
     ppm::launch_prepass_tables(md, t, s);
-    ppm::SweepArgs z{};
-    z.m = md; z.t = t; z.mode = 1; z.first = 0; z.count = 1; z.n_batches = 1; z.n_items = t.P; z.force = 1;
-    ppm::SweepPlan pl = ppm::plan_sweep(md, 1, t.P, n_sm);
-    d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); z.gslots = d_gslots.p;
-    ppm::launch_sweep(z, pl, s);
+    ppm::launch_zero_row(md, t, s);  // the all-zero row of computeI2: slices over threads, not a sweep item
     ppm::launch_prepass_i2(md, t, d_i2_ovr, s);
     n_launches += 4;
   }

@@ -41,6 +41,9 @@ __global__ void __launch_bounds__(256) class_sums_kernel(ModelDev m, TablesDev t
   for (int p = lane; p < t.P; p += 32) t.a01[(size_t)p * m.n_pat_pad + pat] = class_sums(t, p, frontier, nf);
 }
 
+__global__ void __launch_bounds__(256) zero_row_kernel(ModelDev m, TablesDev t) {
+  zero_row_body(m, t, blockIdx.x, threadIdx.x, blockDim.x);
+}
 __global__ void prepass_i2_kernel(ModelDev m, TablesDev t, const double* i2_override) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < t.P) prepass_i2_body(m, t, i2_override, p);
@@ -307,6 +310,9 @@ void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, l
   if (wpc < 1) wpc = 1;
   dim3 g((unsigned)((count + wpc - 1) / wpc));
   class_sums_kernel<<<g, wpc * 32, per_warp * wpc, s>>>(m, t, count);
+}
+void launch_zero_row(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
+  zero_row_kernel<<<t.P, 256, 0, s>>>(m, t);
 }
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s) {
   prepass_i2_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t, i2_override);

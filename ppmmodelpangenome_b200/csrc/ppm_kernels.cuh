@@ -94,6 +94,10 @@ struct TablesDev {
   double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)
   double* scal;          // [P][SC_COUNT]
   double* zeta;          // [P][6][n_nodes] scratch of the node prepass
+  double2* zrow;         // [P][n_nodes] Mobile partials (a, d) of the ALL-ZERO row per node, mantissa-normalised ...
+  int* zk;               // [P][n_nodes] ... and the renormalisation shift of each node (0 for leaves)
+  int* zxb;              // [P][n_blocks+1] sum of the shifts of all nodes formed before each block
+  double2* zpart;        // [P][n_slices] per-slice products of the all-zero row as (mantissa, exponent)
   double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 
@@ -119,6 +123,8 @@ void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s)
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s);
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
+// all-zero row of computeI2/getPobs2 (functions.cpp:300-333): slices spread over the threads; writes SC_IZ_M / SC_IZ_E
+void launch_zero_row(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 // returns the grid size in x; smem_slots tells whether the shared-memory variant was used
 struct SweepPlan { int grid_x, warps, items_per_warp, n_chunks, mode, stage_mask; size_t smem_bytes, per_warp_bytes; bool staged; };
 SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm, bool dist = false);  // dist: a launch that writes SweepArgs::dist

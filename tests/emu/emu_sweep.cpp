@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>  // vector types only (double2/double4)
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <algorithm>
@@ -93,6 +94,9 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     TablesDev t{};
     t.P = P; t.params = params; t.cls = cls.data(); t.kap = kap.data(); t.d1u = d1u.data(); t.recs = recs.data(); t.oprec = oprec.data(); t.clsT = clsT.data(); t.a01 = a01.data(); t.uu = uu.data(); t.leafab = leafab.data(); t.pairq = pairq.data(); t.cherry = cherry.data();
     t.yy = yy.data(); t.scal = scal.data(); t.zeta = zeta.data();
+    std::vector<double2> zrow((size_t)P * nn), zpart((size_t)P * std::max(tree.n_slices, 1));
+    std::vector<int> zk((size_t)P * nn), zxb((size_t)P * (std::max(prog.n_blocks, 1) + 1));
+    t.zrow = zrow.data(); t.zk = zk.data(); t.zxb = zxb.data(); t.zpart = zpart.data();
 
     // two items per "warp" as on the device (NI = 2), one lane each
     const int NI = 2;
@@ -144,7 +148,8 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
       const int nf = class_frontier(md, md.words + j, (size_t)md.n_pat_pad, zbits.data(), frontier.data());
       for (int p = 0; p < P; p++) a01[(size_t)p * count + j] = class_sums(t, p, frontier.data(), nf);
     }
-    run(1, P, nullptr, nullptr, nullptr, true);
+    if (std::getenv("PPM_EMU_ZERO_SWEEP")) run(1, P, nullptr, nullptr, nullptr, true);  // the old path: the zero row as a sweep item
+    else for (int p = 0; p < P; p++) zero_row_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
     run(0, P, out_ll, nullptr, nullptr, false);
     for (int p = 0; p < P; p++) {
