@@ -266,7 +266,7 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
       // compute per entry -- low word: the pair's observation word row in the item's pattern block, high word: the pair's
       // row in pairq -- and mask the rotation that lands the 2-bit observation pair on bits 5..6 (x 32 bytes)
       const int pid = r.ref;
-      r.K = pack2i((pid >> 4) * PPM_LANES * 4, pid * 4 * (int)sizeof(double4));
+      r.K = pack2i((pid >> 4) * (m.word_stride ? m.word_stride : PPM_LANES) * 4, pid * 4 * (int)sizeof(double4));
       r.mask = (uint32_t)((2 * (pid & 15) - 5) & 31);
     }
     t.recs[(size_t)p * (m.n_entries + 1) + i] = r;
@@ -563,7 +563,9 @@ struct SlotsTmem {
 
 template <class Slots>
 struct ItemMem {
-  uint32_t* sw;   // [n_words][lanes] the item's patterns in program leaf order (pair p = bits 2p, 2p+1)
+  const uint32_t* sw;  // the item's patterns in program leaf order (pair p = bits 2p, 2p+1): word w of lane l at sw[w * sws + l];
+  size_t sws;          // a shared-memory copy [n_words][lanes] (sws = lanes) or, for big trees, the device rows themselves
+  uint32_t* sw_copy;   // the shared-memory copy to fill (null when the rows are read in place)
   Slots slots;
 };
 
@@ -687,7 +689,7 @@ PPM_HD void live_update(double (&prod)[NI][R], const double (&Y)[R], const doubl
 // DEEP (the variant whose tables and lineage slots live in global memory): the records of the fully-alive entries
 // are streamed through a per-warp shared-memory ring (wrec, 3 chunks of 32 records, cp.async two chunks ahead) and
 // lineage partials are fetched four entries ahead, so L2/HBM latency is covered by ~140 cycles of FP64 work each.
-template <int R, int NI, bool DEEP, class Slots, bool DIST = false>
+template <int R, int NI, bool DEEP, class Slots, bool DIST = false, bool WG = false>
 PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long long batch0, int lane,
                         const ItemMem<Slots> (&mem)[NI], double (&contrib)[NI], EntryRec* wrec) {
   const ModelDev& m = a.m;
@@ -705,8 +707,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 
 #pragma unroll
   for (int q = 0; q < NI; q++)
-    for (int w = 0; w < m.n_words; w++)
-      mem[q].sw[w * PPM_LANES + lane] = (a.mode == 1 || !active[q]) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
+    if (mem[q].sw_copy)
+      for (int w = 0; w < m.n_words; w++)
+        mem[q].sw_copy[w * PPM_LANES + lane] = (a.mode == 1 || !active[q]) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
   ppm_syncwarp();
   const double pi1 = sc[SC_PI1];
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
@@ -763,7 +766,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       double av[NI], dd[NI];
 #pragma unroll
       for (int q = 0; q < NI; q++) {
-        const uint32_t w = mem[q].sw[(op.lbit >> 5) * PPM_LANES + lane];
+        const uint32_t w = mem[q].sw[(WG ? (size_t)((op.lbit >> 5)) * mem[q].sws : (size_t)(((op.lbit >> 5)) * PPM_LANES)) + lane];
         const uint32_t sel = rotr32(w, (uint32_t)op.lbit) & 0x30u;  // observation pair x 16
         const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.cherry + op.pair * 4) + sel);
         av[q] = v.x; dd[q] = v.y;
@@ -807,7 +810,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         double2 ls, rs;
         mem[q].slots.ld_async(op.lslot, lane, ls);
         mem[q].slots.ld_async(op.rslot, lane, rs);
-        const uint32_t wl = mem[q].sw[(op.lbit >> 5) * PPM_LANES + lane], wr = mem[q].sw[(op.rbit >> 5) * PPM_LANES + lane];
+        const uint32_t wl = mem[q].sw[(WG ? (size_t)((op.lbit >> 5)) * mem[q].sws : (size_t)(((op.lbit >> 5)) * PPM_LANES)) + lane], wr = mem[q].sw[(WG ? (size_t)((op.rbit >> 5)) * mem[q].sws : (size_t)(((op.rbit >> 5)) * PPM_LANES)) + lane];
         const double2 lt = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.leaftab) + (rotr32(wl, (uint32_t)op.lbit) & 0x10u));
         const double2 rt = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.leaftab) + (rotr32(wr, (uint32_t)op.rbit) & 0x10u));
         mem[q].slots.wait_async(ls);
@@ -915,7 +918,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           for (int j = ns; j < n; j++) {
             bool bit[NI];
 #pragma unroll
-            for (int q = 0; q < NI; q++) bit[q] = (mem[q].sw[(ref & 0xffffu) * PPM_LANES + lane] & mk) != 0u;
+            for (int q = 0; q < NI; q++) bit[q] = (mem[q].sw[(WG ? (size_t)((ref & 0xffffu)) * mem[q].sws : (size_t)(((ref & 0xffffu)) * PPM_LANES)) + lane] & mk) != 0u;
             const double nK = -K;
             if (j + 1 < 32) load_rec(cur, j + 1, K, ref, mk); else load_rec(nxt, 0, K, ref, mk);
 #pragma unroll
@@ -975,13 +978,13 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       load_rec(T.recs, e, K, ref, mk);
       uint32_t wv[NI];
 #pragma unroll
-      for (int q = 0; q < NI; q++) wv[q] = mem[q].sw[(ref & 0xffffu) * PPM_LANES + lane];
+      for (int q = 0; q < NI; q++) wv[q] = mem[q].sw[(WG ? (size_t)((ref & 0xffffu)) * mem[q].sws : (size_t)(((ref & 0xffffu)) * PPM_LANES)) + lane];
 #pragma unroll 2
       for (; e < ce; e++) {
         uint32_t wn[NI];
         bool bit[NI];
 #pragma unroll
-        for (int q = 0; q < NI; q++) { wn[q] = mem[q].sw[(ref >> 16) * PPM_LANES + lane]; bit[q] = (wv[q] & mk) != 0u; }
+        for (int q = 0; q < NI; q++) { wn[q] = mem[q].sw[(WG ? (size_t)((ref >> 16)) * mem[q].sws : (size_t)(((ref >> 16)) * PPM_LANES)) + lane]; bit[q] = (wv[q] & mk) != 0u; }
         const double nK = -K;
         load_rec(T.recs, e + 1, K, ref, mk);  // the table carries one padding record
 #pragma unroll
@@ -1007,7 +1010,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       uint32_t cb[NI];   // observation pair of the current record's pair, per item
       int pid = (int)(ref & 0xffffu);
 #pragma unroll
-      for (int q = 0; q < NI; q++) cb[q] = (mem[q].sw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
+      for (int q = 0; q < NI; q++) cb[q] = (mem[q].sw[(WG ? (size_t)((pid >> 4)) * mem[q].sws : (size_t)(((pid >> 4)) * PPM_LANES)) + lane] >> (2 * (pid & 15))) & 3u;
       if (!factored) {
         // record = {pattern word byte offset, pairq byte offset, pair id, rotation}: word, rotate, mask, row -- no index arithmetic
         const char* cwl[NI];
@@ -1094,7 +1097,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           pid = (int)(ref & 0xffffu);
           pid = pid < pmax ? pid : pmax;
 #pragma unroll
-          for (int q = 0; q < NI; q++) cb[q] = (mem[q].sw[(pid >> 4) * PPM_LANES + lane] >> (2 * (pid & 15))) & 3u;
+          for (int q = 0; q < NI; q++) cb[q] = (mem[q].sw[(WG ? (size_t)((pid >> 4)) * mem[q].sws : (size_t)(((pid >> 4)) * PPM_LANES)) + lane] >> (2 * (pid & 15))) & 3u;
           if (((e - bd.e_pair0) & 7) == 7) {
 #pragma unroll
             for (int q = 0; q < NI; q++)
@@ -1114,7 +1117,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
       for (int q = 0; q < NI; q++) {
         const uint32_t ps = ref & 0xffffu;
-        const uint32_t bt = (mem[q].sw[(ps >> 5) * PPM_LANES + lane] >> (ps & 31u)) & 1u;
+        const uint32_t bt = (mem[q].sw[(WG ? (size_t)((ps >> 5)) * mem[q].sws : (size_t)(((ps >> 5)) * PPM_LANES)) + lane] >> (ps & 31u)) & 1u;
         fv[q] = T.leafab[ps * 2 + bt];
       }
       for (int e = bd.e_leafu0; e < bd.e_leaf0; e++) {
@@ -1122,7 +1125,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
         for (int q = 0; q < NI; q++) {
           const uint32_t ps = ref >> 16;
-          const uint32_t bt = (mem[q].sw[(ps >> 5) * PPM_LANES + lane] >> (ps & 31u)) & 1u;
+          const uint32_t bt = (mem[q].sw[(WG ? (size_t)((ps >> 5)) * mem[q].sws : (size_t)(((ps >> 5)) * PPM_LANES)) + lane] >> (ps & 31u)) & 1u;
           fn[q] = T.leafab[ps * 2 + bt];
         }
         load_rec(T.recs, e + 1, K, ref, mk);
@@ -1148,13 +1151,13 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       load_rec(T.recs, bd.e_pleaf0, K, ref, mk);
       uint32_t wv[NI];
 #pragma unroll
-      for (int q = 0; q < NI; q++) wv[q] = mem[q].sw[((ref & 0xffffu) >> 5) * PPM_LANES + lane];
+      for (int q = 0; q < NI; q++) wv[q] = mem[q].sw[(WG ? (size_t)(((ref & 0xffffu) >> 5)) * mem[q].sws : (size_t)((((ref & 0xffffu) >> 5)) * PPM_LANES)) + lane];
       for (int e = bd.e_pleaf0; e < bd.e_pslot0; e++) {
         uint32_t wn[NI];
         double aa[NI], nbb[NI];
 #pragma unroll
         for (int q = 0; q < NI; q++) {
-          wn[q] = mem[q].sw[((ref >> 16) >> 5) * PPM_LANES + lane];
+          wn[q] = mem[q].sw[(WG ? (size_t)(((ref >> 16) >> 5)) * mem[q].sws : (size_t)((((ref >> 16) >> 5)) * PPM_LANES)) + lane];
           const bool bit = (wv[q] >> (ref & 31u)) & 1u;
           aa[q] = bit ? la1 : la0;
           nbb[q] = (bit ? ld1 : ld0) * -K;

@@ -195,6 +195,14 @@ struct ppm_engine {
     md.n_pairs = prog.n_pairs; md.leaf_node = d_leaf_node.p;
     md.entry_ref = d_entry_ref.p; md.entry_mask = d_entry_mask.p; md.entry_node = d_entry_node.p; md.entry_block = d_entry_block.p;
     md.words = d_words.p; md.n_pat = count; md.n_pat_pad = n_pat_pad;
+    // big trees (global-memory variant): a shared-memory copy of the pattern words would cost resident warps (40 KB per
+    // warp at 10,000 genomes: 5 warps; measured 11.3 -> 15.6 TFLOP/s), so the sweep reads the rows in place; the leaf-pair
+    // records then carry byte offsets into the rows, which must fit 31 bits.  Smaller trees keep the copy (5,000 genomes:
+    // 11.9 TFLOP/s with the copy and 10 warps, 9.9 in place).
+    md.word_stride = 0;
+    if (deep && prog.R == 8 && (size_t)pat.n_words * 128 > 24 * 1024 && (size_t)pat.n_words * (size_t)n_pat_pad * 4 < (1ull << 31) &&
+        !std::getenv("PPM_WORDS_SMEM"))
+      md.word_stride = (int)n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
   }
 

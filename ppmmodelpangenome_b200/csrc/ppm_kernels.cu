@@ -113,7 +113,7 @@ __host__ __device__ inline DeepStage deep_stage_layout(const ModelDev& m, int ma
   return D;
 }
 // per item and warp: pattern words [n_words][32]
-__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return align16((size_t)m.n_words * 32 * 4); }
+__host__ __device__ inline size_t warp_head_bytes(const ModelDev& m) { return m.word_stride ? 0 : align16((size_t)m.n_words * 32 * 4); }
 
 template <int MODE>
 __device__ __forceinline__ void init_slots(SlotsMem& s, double2* smem_slots, double2* global_slots, uint32_t, int, int, int, int) {
@@ -138,7 +138,7 @@ template <int MODE> struct SlotsOf { typedef SlotsMem type; };
 template <> struct SlotsOf<1> { typedef SlotsTmem type; };
 template <> struct SlotsOf<3> { typedef SlotsTmem type; };  // MODE 3 = MODE 1 compiled for 12 warps (168 registers)
 
-template <int R, int NI, int MODE, bool DIST = false>
+template <int R, int NI, int MODE, bool DIST = false, bool WG = false>  // WG: pattern rows read in place (global-memory variant, big trees)
 __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
@@ -173,7 +173,10 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
 #pragma unroll
   for (int q = 0; q < NI; q++) {
     unsigned char* ib = wbase + (size_t)q * per_item;
-    mem[q].sw = reinterpret_cast<uint32_t*>(ib);
+    // every variant copies the item's pattern words to shared memory, except WG (big trees: 40 KB per warp at 10,000 genomes
+    // would cost resident warps), which reads the device rows in place
+    mem[q].sw_copy = WG ? nullptr : reinterpret_cast<uint32_t*>(ib);
+    mem[q].sw = WG ? m.words : reinterpret_cast<const uint32_t*>(ib); mem[q].sws = WG ? (size_t)m.n_pat_pad : 32;
     init_slots<MODE>(mem[q].slots, reinterpret_cast<double2*>(ib + head),
                      a.gslots + (((size_t)blockIdx.x * wpc + warp) * NI + q) * (size_t)(m.n_slots + 1) * 32,
                      tmem_base_s, warp, wpc, q, nt);
@@ -252,8 +255,12 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       g = __shfl_sync(0xffffffffu, g, 0);
       if (b_begin + g >= b_end) break;
       const long long batch0 = (b_begin + g) * NI;
+      if (WG) {
+#pragma unroll
+        for (int q = 0; q < NI; q++) mem[q].sw = m.words + (a.first + (batch0 + q) * 32);
+      }
       double contrib[NI];
-      sweep_items<R, NI, !STAGED, Slots, DIST>(a, T, p, batch0, lane, mem, contrib, wrec);
+      sweep_items<R, NI, !STAGED, Slots, DIST, WG>(a, T, p, batch0, lane, mem, contrib, wrec);
       if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
@@ -352,6 +359,7 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm, bo
       if (L.total + (size_t)w * NI * (head + ovf * slot_row) <= budget) { w1 = w; pw1 = NI * (head + ovf * slot_row); }
     }
   }
+  if (m.deep) { w0 = 0; w1 = 0; }  // a program built for the global-memory variant (padded segments, rows read in place) stays there
   const long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
   const long long total = groups * (long long)P;
   const char* force = std::getenv("PPM_FORCE_TMEM");
@@ -365,7 +373,7 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm, bo
   if (!pl.staged) {
     pl.per_warp_bytes = NI * head + kRecRingBytes;
     const char* d16 = std::getenv("PPM_DEEP16");
-    warps = (int)std::max<size_t>(1, std::min<size_t>(std::min(max_warps(), (d16 && std::atoi(d16) && !dist) ? 16 : 12), budget / pl.per_warp_bytes));
+    warps = (int)std::max<size_t>(1, std::min<size_t>(std::min(max_warps(), (d16 && std::atoi(d16) && !dist && !m.word_stride) ? 16 : 12), budget / pl.per_warp_bytes));
     if (warps <= 12) pl.mode = 4;
     if (groups < warps) warps = (int)std::max<long long>(1, groups);
     // whatever small tables still fit are staged in shared memory per parameter vector (the records stay in global
@@ -396,16 +404,16 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
   return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * (m.n_slots + 1) * 32;
 }
 
-template <int R, int MODE, bool DIST = false>
+template <int R, int MODE, bool DIST = false, bool WG = false>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured[64] = {};  // the attribute is per device (group handles launch on several)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  sweep_kernel<R, kItemsPerWarp, MODE, DIST><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+  sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
 
 template <int R>
@@ -419,6 +427,10 @@ static void launch_sweep_r(const SweepArgs& a, const SweepPlan& pl, cudaStream_t
 
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
   a.n_chunks = pl.n_chunks; a.items_per_warp = pl.items_per_warp; a.stage_mask = pl.stage_mask;
+  if (a.m.word_stride) {  // pattern rows in place: R = 8, mode 4 (the engine sets word_stride only then)
+    if (a.dist) launch_sweep_t<8, 4, true, true>(a, pl, s); else launch_sweep_t<8, 4, false, true>(a, pl, s);
+    return;
+  }
   if (a.dist) {  // per-slice integrand output (expectedTime2): R = 8 programs, modes 0 / 3 / 4 (plan_sweep(dist = true))
     if (pl.mode == 0) launch_sweep_t<8, 0, true>(a, pl, s);
     else if (pl.mode == 3) launch_sweep_t<8, 3, true>(a, pl, s);

@@ -72,6 +72,8 @@ struct ModelDev {
   const int* entry_ref; const uint32_t* entry_mask; const int* entry_node; const int* entry_block;  // [n_entries]
   // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq
   const uint32_t* words; long long n_pat, n_pat_pad;
+  int word_stride;  // 0: every warp item copies its pattern words to shared memory [n_words][32]; else the sweep reads the device
+                    // rows in place with this stride (= n_pat_pad; big trees, where the copy would cost resident warps)
   const int* counts; const int* mrca; const int* freq;
   const uint32_t* zero_words;  // n_words * 32 zeros (the all-zero row of add0(), objects.cpp:274-281)
 };

@@ -103,7 +103,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<uint32_t> sw(NI * pat.n_words);
     std::vector<double2> slotmem(NI * (prog.n_slots + 1));
     ItemMem<SlotsMem> mem[2];
-    for (int q = 0; q < NI; q++) { mem[q].sw = sw.data() + q * pat.n_words; mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
+    for (int q = 0; q < NI; q++) { mem[q].sw_copy = sw.data() + q * pat.n_words; mem[q].sw = mem[q].sw_copy; mem[q].sws = 1; mem[q].slots.base = slotmem.data() + q * (prog.n_slots + 1); }
     std::vector<double> et1v(g_et1 ? (size_t)P * nn : 0);
     if (g_et1) t.et1 = et1v.data();
     if (g_gains) *g_gains = expected_gains(tree, g_gains_g2);
