@@ -1038,50 +1038,112 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           else load_rec(T.recs, idx, Kx, refx, mkx);
         };
         if (ring) { pstage(0); pstage(1); ppm_cp_wait1(); ppm_syncwarp(); }
-        double K1, K2; uint32_t rot1, rot2;
-        prec(B0 + 1 < elast ? B0 + 1 : elast, K1, ref, rot1);  // (the record behind the segment is not a pair)
-        prec(B0 + 2 < elast ? B0 + 2 : elast, K2, ref, rot2);
-        uint32_t w1[NI];
-        {
-          int wo, qo;
-          unpack2i(K1, wo, qo);
+        if constexpr (DEEP) {
+          // Global-memory variant: the quadratics' rows come from L2 on big trees (the table exceeds L1), so the pipeline is
+          // deeper: iteration e fetches the record of e+PD+2, the word of e+PD+1 and the row of e+PD (PD = 3 measured best:
+          // 5,000 genomes +16 %, 10,000-leaf caterpillar +24 % over PD = 1; PD = 5 spills and loses at 1,000 genomes).
+          constexpr int PD = 3;
+          double Kr[PD + 2]; uint32_t rt[PD + 2];
+          uint32_t W[NI][PD + 1];
+          double4 Q[NI][PD + 1];
 #pragma unroll
-          for (int q = 0; q < NI; q++) w1[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
-        }
-        for (int e = B0; e <= elast;) {
-          if (ring && ((e - B0) & 31) == 0) {
-            // chunk boundary: the ring slot of the previous chunk is free again, the next chunk must have landed
-            ppm_syncwarp();
-            pstage(((e - B0) >> 5) + 2);
-            ppm_cp_wait1();
-            ppm_syncwarp();
-          }
-          const int ce = (e + 16 <= elast) ? e + 16 : elast + 1;
-#pragma unroll 2
-          for (; e < ce; e++) {
-            double K3; uint32_t rot3;
-            prec(e + 3 < elast ? e + 3 : elast, K3, ref, rot3);
-            int wo1, qo1, wo2, qo2;
-            unpack2i(K1, wo1, qo1);
-            unpack2i(K2, wo2, qo2);
-            double4 qn[NI];
-            uint32_t w2[NI];
+          for (int k = 0; k <= PD; k++) prec(B0 + 1 + k < elast ? B0 + 1 + k : elast, Kr[k], ref, rt[k]);
 #pragma unroll
-            for (int q = 0; q < NI; q++) {
-              qn[q] = *reinterpret_cast<const double4*>(pq + qo1 + (rotr32(w1[q], rot1) & 0x60u));
-              w2[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo2);
-            }
+          for (int k = 0; k < PD; k++) {
+            int wo, qo;
+            unpack2i(Kr[k], wo, qo);
 #pragma unroll
-            for (int q = 0; q < NI; q++) {
-#pragma unroll
-              for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
-              qv[q] = qn[q]; w1[q] = w2[q];
-            }
-            K1 = K2; rot1 = rot2; K2 = K3; rot2 = rot3;
+            for (int q = 0; q < NI; q++) W[q][k] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
           }
 #pragma unroll
-          for (int q = 0; q < NI; q++)
-            if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+          for (int q = 0; q < NI; q++) Q[q][0] = qv[q];
+#pragma unroll
+          for (int k = 1; k < PD; k++) {
+            int wo, qo;
+            unpack2i(Kr[k - 1], wo, qo);
+#pragma unroll
+            for (int q = 0; q < NI; q++) Q[q][k] = *reinterpret_cast<const double4*>(pq + qo + (rotr32(W[q][k - 1], rt[k - 1]) & 0x60u));
+          }
+          for (int e = B0; e <= elast;) {
+            if (ring && ((e - B0) & 31) == 0) {
+              // chunk boundary: the ring slot of the previous chunk is free again, the next chunk must have landed
+              ppm_syncwarp();
+              pstage(((e - B0) >> 5) + 2);
+              ppm_cp_wait1();
+              ppm_syncwarp();
+            }
+            const int ce = (e + 16 <= elast) ? e + 16 : elast + 1;
+#pragma unroll 4
+            for (; e < ce; e++) {
+              prec(e + PD + 2 < elast ? e + PD + 2 : elast, Kr[PD + 1], ref, rt[PD + 1]);
+              int woN, qoN, wo_, qo_;
+              unpack2i(Kr[PD], woN, qo_);
+              unpack2i(Kr[PD - 1], wo_, qoN);
+#pragma unroll
+              for (int q = 0; q < NI; q++) {
+                Q[q][PD] = *reinterpret_cast<const double4*>(pq + qoN + (rotr32(W[q][PD - 1], rt[PD - 1]) & 0x60u));
+                W[q][PD] = *reinterpret_cast<const uint32_t*>(cwl[q] + woN);
+              }
+#pragma unroll
+              for (int q = 0; q < NI; q++) {
+#pragma unroll
+                for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(Q[q][0].z, U[i], Q[q][0].y), U[i], Q[q][0].x);
+#pragma unroll
+                for (int k = 0; k < PD; k++) { Q[q][k] = Q[q][k + 1]; W[q][k] = W[q][k + 1]; }
+              }
+#pragma unroll
+              for (int k = 0; k <= PD; k++) { Kr[k] = Kr[k + 1]; rt[k] = rt[k + 1]; }
+            }
+#pragma unroll
+            for (int q = 0; q < NI; q++)
+              if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+          }
+        } else {
+          double K1, K2; uint32_t rot1, rot2;
+          prec(B0 + 1 < elast ? B0 + 1 : elast, K1, ref, rot1);  // (the record behind the segment is not a pair)
+          prec(B0 + 2 < elast ? B0 + 2 : elast, K2, ref, rot2);
+          uint32_t w1[NI];
+          {
+            int wo, qo;
+            unpack2i(K1, wo, qo);
+  #pragma unroll
+            for (int q = 0; q < NI; q++) w1[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo);
+          }
+          for (int e = B0; e <= elast;) {
+            if (ring && ((e - B0) & 31) == 0) {
+              // chunk boundary: the ring slot of the previous chunk is free again, the next chunk must have landed
+              ppm_syncwarp();
+              pstage(((e - B0) >> 5) + 2);
+              ppm_cp_wait1();
+              ppm_syncwarp();
+            }
+            const int ce = (e + 16 <= elast) ? e + 16 : elast + 1;
+  #pragma unroll 2
+            for (; e < ce; e++) {
+              double K3; uint32_t rot3;
+              prec(e + 3 < elast ? e + 3 : elast, K3, ref, rot3);
+              int wo1, qo1, wo2, qo2;
+              unpack2i(K1, wo1, qo1);
+              unpack2i(K2, wo2, qo2);
+              double4 qn[NI];
+              uint32_t w2[NI];
+  #pragma unroll
+              for (int q = 0; q < NI; q++) {
+                qn[q] = *reinterpret_cast<const double4*>(pq + qo1 + (rotr32(w1[q], rot1) & 0x60u));
+                w2[q] = *reinterpret_cast<const uint32_t*>(cwl[q] + wo2);
+              }
+  #pragma unroll
+              for (int q = 0; q < NI; q++) {
+  #pragma unroll
+                for (int i = 0; i < R; i++) prod[q][i] *= fma(fma(qv[q].z, U[i], qv[q].y), U[i], qv[q].x);
+                qv[q] = qn[q]; w1[q] = w2[q];
+              }
+              K1 = K2; rot1 = rot2; K2 = K3; rot2 = rot3;
+            }
+  #pragma unroll
+            for (int q = 0; q < NI; q++)
+              if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+          }
         }
         if (ring) { ppm_cp_wait0(); ppm_syncwarp(); }
       } else {  // pi1 close to 1: two linear factors keep full accuracy
