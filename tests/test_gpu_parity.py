@@ -258,3 +258,23 @@ def test_group_handle_matches_unsharded_handle(ppm, golden):
         assert np.array_equal(grp.expectedTime1(p), one.expectedTime1(p))
         assert np.allclose(grp.computeProbaCat(p, i2), one.computeProbaCat(p, i2), rtol=1e-12, atol=1e-12)
         grp.close(); one.close()
+
+
+def test_group_with_more_shards_than_patterns_and_bad_device(ppm, golden, tmp_path):
+    """Edge cases of group handles: empty shards (more GPUs than patterns) still give the full objective; an invalid
+    device ordinal is an error, not a crash."""
+    tree = tmp_path / "t.nwk"
+    tree.write_text("((a:1,b:1):1,(c:1.5,d:1.5):0.5);\n")
+    pa = tmp_path / "pa.txt"
+    pa.write_text("genome,g1,g2,g3\na,1,0,1\nb,1,0,0\nc,0,1,1\nd,0,1,1\n")
+    p = np.array([[2.0, 0.05, 1.0, 0.5, 0.5, 2.0, 0.01, 0.02]])
+    one = ppm.Inference(str(tree), str(pa), dedupe=True, device=0)
+    grp = ppm.Inference(str(tree), str(pa), dedupe=True, devices=[0] * 5)   # 3 patterns over 5 shards
+    a, b = one.loglik_batch(p, return_i2=True), grp.loglik_batch(p, return_i2=True)
+    assert np.allclose(a[0], b[0], rtol=1e-13, atol=0) and np.array_equal(a[1], b[1])
+    assert np.array_equal(one.assignCat(p[0], a[1][0]), grp.assignCat(p[0], a[1][0]))
+    assert np.array_equal(one.expectedTime1(p[0]), grp.expectedTime1(p[0]))
+    assert np.array_equal(one.expectedTime2(p[0])[1][:, :-1], grp.expectedTime2(p[0])[1][:, :-1])
+    one.close(); grp.close()
+    with pytest.raises(ppm.PPMError):
+        ppm.Inference(str(tree), str(pa), devices=[0, 99])
