@@ -451,57 +451,54 @@ Program build_program(const Tree& t, int R, bool deep) {
   std::vector<int> op_block(nn, nb);
   for (int v = 1; v < nn; v++)
     if (t.left[v] >= 0 && js0[v] < S) op_block[v] = js0[v] / R;  // (a node with an empty alive range still merges here)
-  // slots: allocated at the op, released after the block in which the parent is formed
+  // Ops per block: internal nodes in rank order; cherries (both children leaves: they depend on nothing and the sweep serves
+  // them from a per-parameter table indexed by the 2-bit observation pair) run first.
+  // Slots: a node takes one at its op.  With folded events a child is last read by its parent's op (merge + its slices of
+  // the block), so its slot is free for that very op's result and for the ops after it; without folding its partial entry
+  // still needs it until the block ends.
+  const bool fold = std::getenv("PPM_NO_FOLD") == nullptr;
+  std::vector<std::vector<int>> block_nodes(nb + 1);
+  {
+    int cur = 0;
+    for (int r = 0; r < nn; r++) {
+      int v = t.order[r];
+      if (t.left[v] < 0) continue;
+      cur = std::max(cur, op_block[v]);  // children are formed in an earlier-or-equal block; keep the sequence monotone
+      op_block[v] = cur;
+      block_nodes[cur].push_back(v);
+    }
+  }
+  auto is_cherry = [&](int v) { return pg.leaf_u && v != 0 && t.left[t.left[v]] < 0 && t.left[t.right[v]] < 0; };
   std::vector<int> slot(nn, -1);
-  std::vector<std::vector<int>> release(nb + 2);
   std::vector<int> free_slots;
   int n_slots = 0;
-  std::vector<int> blk_op0(nb + 2, 0);
-  int cur_block = -1;
-  auto open_blocks_to = [&](int b) {  // op lists are emitted in block order
-    while (cur_block < b) {
-      cur_block++;
-      blk_op0[cur_block] = (int)pg.ops.size();
-      if (cur_block >= 1)
-        for (int s : release[cur_block - 1]) free_slots.push_back(s);
-    }
-  };
-  for (int r = 0; r < nn; r++) {
-    int v = t.order[r];
-    if (t.left[v] < 0) continue;
-    int b = op_block[v];
-    // children are formed in an earlier-or-equal block; keep the sequence monotone
-    b = std::max(b, std::max(0, cur_block));
-    op_block[v] = b;
-    open_blocks_to(b);
-    NodeOp op{};
-    op.node = v; op.lnode = t.left[v]; op.rnode = t.right[v];
-    op.lref = t.left[op.lnode] < 0 ? -(dpos(op.lnode) + 1) : slot[op.lnode];
-    op.rref = t.left[op.rnode] < 0 ? -(dpos(op.rnode) + 1) : slot[op.rnode];
-    if (v == 0) { op.dst = -1; op.i0 = R; }
-    else {
-      if (free_slots.empty()) free_slots.push_back(n_slots++);
-      slot[v] = free_slots.back(); free_slots.pop_back();
-      op.dst = slot[v];
-      op.i0 = (b < nb && js0[v] < std::min(S, (b + 1) * R)) ? std::max(0, js0[v] - b * R) : R;
-    }
-    // the children's slots die with the block in which this node is formed
-    for (int c : {op.lnode, op.rnode})
-      if (slot[c] >= 0) release[std::min(b, nb)].push_back(slot[c]);
-    pg.ops.push_back(op);
-  }
-  open_blocks_to(nb);
-  blk_op0[nb + 1] = (int)pg.ops.size();
-  for (int b = 0; b <= nb; b++) { pg.blk[b].op0 = blk_op0[b]; pg.blk[b].op1 = blk_op0[b + 1]; }
-  // Within a block no slot is reused and cherries depend on nothing, so they can run first: the sweep serves them
-  // from a per-parameter table indexed by the 2-bit observation pair instead of a merge.
-  pg.cherry_op.assign(pg.n_cherries, 0);
-  for (NodeOp& op : pg.ops) op.pair = (pg.leaf_u && op.lref < 0 && op.rref < 0 && op.dst >= 0) ? pair_of(-(op.lref + 1)) : -1;
   for (int b = 0; b <= nb; b++) {
-    auto first = pg.ops.begin() + pg.blk[b].op0, last = pg.ops.begin() + pg.blk[b].op1;
-    auto mid = std::stable_partition(first, last, [](const NodeOp& op) { return op.pair >= 0; });
-    pg.blk[b].opc = (int)(mid - pg.ops.begin());
+    std::stable_partition(block_nodes[b].begin(), block_nodes[b].end(), is_cherry);
+    pg.blk[b].op0 = (int)pg.ops.size();
+    pg.blk[b].opc = pg.blk[b].op0;
+    std::vector<int> release;
+    for (int v : block_nodes[b]) {
+      NodeOp op{};
+      op.node = v; op.lnode = t.left[v]; op.rnode = t.right[v];
+      op.lref = t.left[op.lnode] < 0 ? -(dpos(op.lnode) + 1) : slot[op.lnode];
+      op.rref = t.left[op.rnode] < 0 ? -(dpos(op.rnode) + 1) : slot[op.rnode];
+      for (int c : {op.lnode, op.rnode})
+        if (slot[c] >= 0) (fold ? free_slots : release).push_back(slot[c]);
+      if (v == 0) { op.dst = -1; op.i0 = R; }
+      else {
+        if (free_slots.empty()) free_slots.push_back(n_slots++);
+        slot[v] = free_slots.back(); free_slots.pop_back();
+        op.dst = slot[v];
+        op.i0 = (b < nb && js0[v] < std::min(S, (b + 1) * R)) ? std::max(0, js0[v] - b * R) : R;
+      }
+      op.pair = is_cherry(v) ? pair_of(-(op.lref + 1)) : -1;
+      if (op.pair >= 0) pg.blk[b].opc = (int)pg.ops.size() + 1;
+      pg.ops.push_back(op);
+    }
+    pg.blk[b].op1 = (int)pg.ops.size();
+    for (int sfree : release) free_slots.push_back(sfree);
   }
+  pg.cherry_op.assign(pg.n_cherries, 0);
   pg.sops.assign(pg.ops.size() + 1, SweepOp{});  // + one padding record: the sweep fetches one op ahead
   for (size_t o = 0; o < pg.ops.size(); o++) {
     const NodeOp& op = pg.ops[o];
@@ -548,7 +545,6 @@ Program build_program(const Tree& t, int R, bool deep) {
       const int b = op_block[pg.ops[o].node];
       if (b < nb) pg.op_tb[o] = t.slice_t[pg.blk[b].slice0];
     }
-    const bool fold = std::getenv("PPM_NO_FOLD") == nullptr;
     for (int b = 0; b < nb && fold; b++) {
       const int nsl = pg.blk[b].nslices;
       std::vector<Ent> keep;
