@@ -1167,9 +1167,11 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           }
         }
       }
+      if (factored) {  // (the quadratic loop above ends every chunk with a range check; this one checks every 8 pairs)
 #pragma unroll
-      for (int q = 0; q < NI; q++)
-        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+        for (int q = 0; q < NI; q++)
+          if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+      }
     }
     // single leaves in u-form: ref = bit position | next << 16; the term alpha + beta u comes from a per-lane table row
     if (bd.e_leafu0 < bd.e_leaf0) {
@@ -1257,7 +1259,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // ---- block end: integral += w/nSub * product (functions.cpp:273-275), exponents aligned
 #pragma unroll
     for (int q = 0; q < NI; q++) {
-      if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+      // (every loop above ends with a range check of its own; the generic partial loops and the deep variant's tails do not)
+      if (DEEP || bd.e_pleaf0 < bd.e_end)
+        if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
       if (DIST) {  // expectedTime2_aux (functions.cpp:713-746): the integrand exp(f_aux) of every slice
         if (a.dist && active[q]) {
           double* row = a.dist + (size_t)(pat[q] - a.first) * (m.n_slices + 1);
