@@ -111,7 +111,7 @@ struct ppm_engine {
 
   ~ppm_engine() {
     peers.clear();
-    if (device >= 0) cudaSetDevice(device);
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) cudaGetLastError();  // never leave a sticky error behind
     if (ev_done) cudaEventDestroy(ev_done);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -119,11 +119,12 @@ struct ppm_engine {
   }
 
   void init_device(int dev) {
-    device = dev;
+    device = -1;  // (the destructor must not select a device that was never validated)
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (dev < 0 || dev >= ndev) throw CudaError("no CUDA device with ordinal " + std::to_string(dev));
     CK(cudaSetDevice(dev));
+    device = dev;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100 (this library carries sm_100a code only)");

@@ -278,3 +278,29 @@ def test_group_with_more_shards_than_patterns_and_bad_device(ppm, golden, tmp_pa
     one.close(); grp.close()
     with pytest.raises(ppm.PPMError):
         ppm.Inference(str(tree), str(pa), devices=[0, 99])
+
+
+@pytest.mark.parametrize("n,genes,cat", [(1000, 120, False), (6200, 16, True)])
+def test_big_trees_against_oracle(ppm, tmp_path, n, genes, cat):
+    """The global-memory sweep variant (1,000 genomes: records streamed through the per-warp rings, small tables staged)
+    and its big-tree form (6,200-leaf caterpillar: pattern rows read in place, deeper pair pipeline) against the C oracle
+    on inputs small enough for it: log-likelihood, i2 and categories."""
+    from oracle import cport, model
+    from ppmmodelpangenome_b200 import simulate
+    rng = np.random.default_rng(1000 + n)
+    nwk = simulate.sim_tree(n, rng, caterpillar=cat)
+    names, M, truth = simulate.sim_genes(nwk, genes, rng)
+    tp, pp = str(tmp_path / "t.nwk"), str(tmp_path / "m.txt")
+    open(tp, "w").write(nwk + "\n")
+    simulate.write_matrix(pp, names, M)
+    orc = cport.Oracle(model.model_from_files(tp, pp))
+    inf = ppm.Inference(tp, pp, dedupe=True, device=0)
+    P = np.stack([simulate.start_params(truth, genes), simulate.start_params(truth, genes, rng)])
+    ll, i2 = inf.loglik_batch(P, return_i2=True)
+    for k in range(len(P)):
+        o = orc.eval(P[k], cats=(k == 0))
+        assert rel(ll[k], o["ll"]) <= RTOL, (n, k, ll[k], o["ll"])
+        assert rel(i2[k], o["i2"]) <= RTOL
+        if k == 0 and o["i2"] > 0:
+            assert np.array_equal(inf.assignCat(P[k], o["i2"]), o["cat"])
+    inf.close()
