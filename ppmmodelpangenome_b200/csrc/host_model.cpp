@@ -380,6 +380,22 @@ Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
     }
     seen[k] = 1;
     int64_t g = 0;
+    // fast path: single-digit values separated by commas (what the reference's R scripts write); anything else falls
+    // through to the general strtol loop below at the position reached
+    {
+      uint32_t* col = rows.data() + (k >> 5);
+      const uint32_t bit = 1u << (k & 31);
+      while (g < n_genes && (p[0] == '0' || p[0] == '1') && (p[1] == ',' || p[1] == '\0')) {
+        if (p[0] == '1') col[(size_t)g * nw] |= bit;
+        g++;
+        if (p[1] == '\0') { p += 1; break; }
+        p += 2;
+      }
+      if (*p == '\0' && g > 0) {
+        if (g != n_genes) throw std::runtime_error("matrix: row " + name + " is shorter than the first row");
+        continue;
+      }
+    }
     while (true) {
       char* end;
       long v = strtol(p, &end, 10);
