@@ -709,7 +709,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   for (int q = 0; q < NI; q++)
     if (mem[q].sw_copy)
       for (int w = 0; w < m.n_words; w++)
-        mem[q].sw_copy[w * PPM_LANES + lane] = (a.mode == 1 || !active[q]) ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
+        mem[q].sw_copy[w * PPM_LANES + lane] = !active[q] ? 0u : m.words[(size_t)w * m.n_pat_pad + pat[q]];
   ppm_syncwarp();
   const double pi1 = sc[SC_PI1];
   const double la0 = sc[SC_LA0], ld0 = sc[SC_LD0], la1 = sc[SC_LA1], ld1 = sc[SC_LD1];
@@ -1291,13 +1291,6 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 
 #pragma unroll
   for (int q = 0; q < NI; q++) {
-    if (a.mode == 1) {
-      if (active[q]) {
-        double* scw = a.t.scal + (size_t)p * SC_COUNT;
-        scw[SC_IZ_M] = Im[q]; scw[SC_IZ_E] = (double)Ie[q];
-      }
-      continue;
-    }
     if (DIST) {  // last column: exp(likRep2) = the integral itself (functions.cpp:756)
       if (a.dist && active[q]) a.dist[(size_t)(pat[q] - a.first) * (m.n_slices + 1) + m.n_slices] = ldexp(Im[q], -Ie[q]);
     }

@@ -261,7 +261,6 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       }
       double contrib[NI];
       sweep_items<R, NI, !STAGED, Slots, DIST, WG>(a, T, p, batch0, lane, mem, contrib, wrec);
-      if (a.mode == 1) continue;
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
       for (int q = 0; q < NI; q++) {

@@ -106,7 +106,7 @@ struct TablesDev {
 struct SweepArgs {
   ModelDev m;
   TablesDev t;
-  int mode;              // 0: log-likelihood partial sums, 1: zero row (writes SC_IZ_*), 2: + categories/components
+  int mode;              // 0: log-likelihood partial sums, 2: + categories/components (the all-zero row has its own kernel)
   long long first, count;  // pattern range
   long long n_batches, n_items;  // ceil(count/32) and P * n_batches
   int n_chunks, items_per_warp;  // CTA work unit = (parameter vector, chunk of warps*items_per_warp batches)
