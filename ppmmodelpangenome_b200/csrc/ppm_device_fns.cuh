@@ -1118,7 +1118,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
               ppm_syncwarp();
             }
             const int ce = (e + 16 <= elast) ? e + 16 : elast + 1;
-  #pragma unroll 2
+  #pragma unroll 4
             for (; e < ce; e++) {
               double K3; uint32_t rot3;
               prec(e + 3 < elast ? e + 3 : elast, K3, ref, rot3);
