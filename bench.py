@@ -274,7 +274,7 @@ def main():
             "gpu_launches": int(cnt["launches"] + 1) * K,  # 7 kernels in ppm_loglik_device + finalize
             "roofline": {"bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach / peak_tf) if ach else None,
-                         "traffic": 4.987e7 if (P == 256 and world == 1) else None,  # dram read+write bytes per launch, ncu --set full (profiles/)
+                         "traffic": 4.99e7 if (P == 256 and world == 1) else None,  # dram read+write bytes per launch, ncu --set full (profiles/)
                          "kernel": "ppm::sweep_kernel<8,1,0>", "kernel_ms": sweep,
                          "peak_source": "DFMA micro-benchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_pattern_eval": F,
