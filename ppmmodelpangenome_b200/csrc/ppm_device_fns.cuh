@@ -1297,7 +1297,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // ---- mixture (functions.cpp:345-358) and category argmax (functions.cpp:497-509)
     if (active[q]) {
       // log p1(root) of the two pure-loss categories, from the class-sum kernel
-      const double2 A01 = a.t.a01[(size_t)p * m.n_pat_pad + (pat[q] - a.first)];
+      const double2 A01 = a.t.a01[(size_t)(pat[q] - a.first) * a.t.P + p];  // [pattern][P]: one strided read per item
       const double lik0 = sc[SC_C0] + A01.x;
       const int mr = m.mrca[pat[q]];
       const double2 du = a.t.d1u[(size_t)p * m.n_nodes + mr];

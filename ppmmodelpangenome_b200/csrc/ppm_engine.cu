@@ -89,7 +89,8 @@ struct ppm_engine {
   DevBuf<uint32_t> d_entry_mask;
   DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt, d_op_tb;
   DevBuf<ppm::NodeOpDev> d_ops;
-  DevBuf<uint32_t> d_words, d_zero_words;
+  DevBuf<uint32_t> d_words, d_zero_words, d_fr_off;
+  DevBuf<uint16_t> d_fr_nodes;
   DevBuf<int> d_counts, d_mrca, d_freq;
   long long n_pat_pad = 0;
   ppm::ModelDev md{};
@@ -205,6 +206,27 @@ struct ppm_engine {
         !std::getenv("PPM_WORDS_SMEM"))
       md.word_stride = (int)n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
+    // frontier lists of the class sums: pattern-only, so once per handle (count, prefix sums on the host, fill)
+    md.fr_off = nullptr; md.fr_nodes = nullptr;
+    if (tree.n_nodes <= 65535 && count > 0) {
+      DevBuf<uint32_t> d_nf;
+      d_nf.alloc((size_t)count);
+      ppm::launch_frontier_count(md, count, d_nf.p, stream);
+      std::vector<uint32_t> nf((size_t)count), off((size_t)count + 1, 0u);
+      CK(cudaMemcpyAsync(nf.data(), d_nf.p, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      unsigned long long total = 0;
+      for (long long j = 0; j < count; j++) { off[j] = (uint32_t)total; total += nf[j]; }
+      off[count] = (uint32_t)total;
+      if (total < (1ull << 32)) {
+        d_fr_off.upload(off, stream);
+        d_fr_nodes.alloc((size_t)std::max<unsigned long long>(total, 1));
+        ppm::launch_frontier_fill(md, count, d_fr_off.p, d_fr_nodes.p, stream);
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        md.fr_off = d_fr_off.p; md.fr_nodes = d_fr_nodes.p;
+      }
+    }
   }
 
   ppm::TablesDev tables(int P, const double* d_par) {

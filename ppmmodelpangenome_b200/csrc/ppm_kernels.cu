@@ -27,8 +27,51 @@ __global__ void __launch_bounds__(128) prepass_nodes_kernel(ModelDev m, TablesDe
 __global__ void prepass_tables_kernel(ModelDev m, TablesDev t) {
   prepass_tables_body(m, t, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
-// one warp per pattern: the frontier once, then all parameter vectors 32 at a time (coalesced table rows)
-__global__ void __launch_bounds__(256) class_sums_kernel(ModelDev m, TablesDev t, long long count) {
+// Class sums.  The frontier of a pattern depends on the pattern only, so it is listed once per handle (frontier_* kernels);
+// per evaluation  a01[pattern][p] = Stot[p] + sum over the frontier of F[node][p].
+// (1) tiled: a CTA stages F[.][p0..p0+31] in shared memory (n_nodes x 512 B) and serves a range of patterns, one warp per
+//     pattern, lanes = parameter vectors; (2) big trees: the same from L2; (3) no lists (> 65,535 nodes): walk per call.
+__global__ void __launch_bounds__(256) class_sums_tiled_kernel(ModelDev m, TablesDev t, long long count, int pats_per_cta) {
+  extern __shared__ __align__(16) unsigned char cst_raw[];
+  double2* tile = reinterpret_cast<double2*>(cst_raw);  // [n_nodes][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int p0 = blockIdx.x * 32, p = p0 + lane;
+  const bool pv = p < t.P;
+  for (int v = warp; v < m.n_nodes; v += wpc) tile[v * 32 + lane] = pv ? t.clsT[(size_t)v * t.P + p] : make_double2(0., 0.);
+  double s0 = 0., s1 = 0.;
+  if (pv) { const double* sc = t.scal + (size_t)p * SC_COUNT; s0 = sc[SC_STOT0]; s1 = sc[SC_STOT1]; }
+  __syncthreads();
+  const long long j0 = (long long)blockIdx.y * pats_per_cta;
+  const long long j1 = j0 + pats_per_cta < count ? j0 + pats_per_cta : count;
+  for (long long pat = j0 + warp; pat < j1; pat += wpc) {
+    const uint32_t o0 = m.fr_off[pat], o1 = m.fr_off[pat + 1];
+    double a0 = s0, a1 = s1;
+    for (uint32_t k = o0; k < o1; k++) {
+      const double2 f = tile[(int)m.fr_nodes[k] * 32 + lane];
+      a0 += f.x; a1 += f.y;
+    }
+    if (pv) t.a01[(size_t)pat * t.P + p] = make_double2(a0, a1);
+  }
+}
+__global__ void __launch_bounds__(256) class_sums_list_kernel(ModelDev m, TablesDev t, long long count) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const long long pat = (long long)blockIdx.x * wpc + warp;
+  if (pat >= count) return;
+  const uint32_t o0 = m.fr_off[pat], o1 = m.fr_off[pat + 1];
+  for (int p = lane; p < t.P; p += 32) {
+    const double* sc = t.scal + (size_t)p * SC_COUNT;
+    double a0 = sc[SC_STOT0], a1 = sc[SC_STOT1];
+    for (uint32_t k = o0; k < o1; k++) {
+      const double2 f = t.clsT[(size_t)m.fr_nodes[k] * t.P + p];
+      a0 += f.x; a1 += f.y;
+    }
+    t.a01[(size_t)pat * t.P + p] = make_double2(a0, a1);
+  }
+}
+// one warp per pattern walks the node ops (class_frontier); MODE 0: count, 1: fill the lists, 2: no lists, sum right away
+template <int MODE>
+__global__ void __launch_bounds__(256) class_walk_kernel(ModelDev m, TablesDev t, long long count, uint32_t* nf_out, const uint32_t* off,
+                                                         uint16_t* nodes_out) {
   extern __shared__ uint32_t cs_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int zwords = (m.n_nodes + 31) >> 5, fwords = (m.n_nodes + 1) >> 1;
@@ -38,7 +81,9 @@ __global__ void __launch_bounds__(256) class_sums_kernel(ModelDev m, TablesDev t
   if (pat >= count) return;
   const int nf = class_frontier(m, m.words + pat, (size_t)m.n_pat_pad, zbits, frontier);
   __syncwarp();
-  for (int p = lane; p < t.P; p += 32) t.a01[(size_t)p * m.n_pat_pad + pat] = class_sums(t, p, frontier, nf);
+  if (MODE == 0) { if (lane == 0) nf_out[pat] = (uint32_t)nf; }
+  else if (MODE == 1) { for (int k = lane; k < nf; k += 32) nodes_out[off[pat] + k] = frontier[k]; }
+  else { for (int p = lane; p < t.P; p += 32) t.a01[(size_t)pat * t.P + p] = class_sums(t, p, frontier, nf); }
 }
 
 __global__ void __launch_bounds__(256) zero_row_kernel(ModelDev m, TablesDev t) {
@@ -308,14 +353,51 @@ void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }
+static void walk_geometry(const ModelDev& m, long long count, int& wpc, size_t& smem, dim3& g) {
+  const size_t per_warp = ((size_t)((m.n_nodes + 31) / 32) + (size_t)((m.n_nodes + 1) / 2)) * sizeof(uint32_t);
+  wpc = (int)std::min<size_t>(8, (48 * 1024) / per_warp);
+  if (wpc < 1) wpc = 1;
+  smem = per_warp * wpc;
+  g = dim3((unsigned)((count + wpc - 1) / wpc));
+}
+void launch_frontier_count(const ModelDev& m, long long count, uint32_t* nf_out, cudaStream_t s) {
+  if (count <= 0) return;
+  int wpc; size_t smem; dim3 g;
+  walk_geometry(m, count, wpc, smem, g);
+  class_walk_kernel<0><<<g, wpc * 32, smem, s>>>(m, TablesDev{}, count, nf_out, nullptr, nullptr);
+}
+void launch_frontier_fill(const ModelDev& m, long long count, const uint32_t* off, uint16_t* nodes_out, cudaStream_t s) {
+  if (count <= 0) return;
+  int wpc; size_t smem; dim3 g;
+  walk_geometry(m, count, wpc, smem, g);
+  class_walk_kernel<1><<<g, wpc * 32, smem, s>>>(m, TablesDev{}, count, nullptr, off, nodes_out);
+}
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s) {
   (void)first;
   if (count <= 0) return;
-  const size_t per_warp = ((size_t)((m.n_nodes + 31) / 32) + (size_t)((m.n_nodes + 1) / 2)) * sizeof(uint32_t);
-  int wpc = (int)std::min<size_t>(8, (48 * 1024) / per_warp);
-  if (wpc < 1) wpc = 1;
-  dim3 g((unsigned)((count + wpc - 1) / wpc));
-  class_sums_kernel<<<g, wpc * 32, per_warp * wpc, s>>>(m, t, count);
+  if (!m.fr_off) {  // no lists: walk per call
+    int wpc; size_t smem; dim3 g;
+    walk_geometry(m, count, wpc, smem, g);
+    class_walk_kernel<2><<<g, wpc * 32, smem, s>>>(m, t, count, nullptr, nullptr, nullptr);
+    return;
+  }
+  const size_t tile = (size_t)m.n_nodes * 32 * sizeof(double2);
+  if (tile <= 200 * 1024) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaFuncSetAttribute(class_sums_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const int chunks = (t.P + 31) / 32;
+    long long groups = std::max<long long>(1, (2LL * 148 + chunks - 1) / chunks);  // about two CTAs per SM in total
+    long long per = std::max<long long>(8, (count + groups - 1) / groups);
+    groups = (count + per - 1) / per;
+    class_sums_tiled_kernel<<<dim3((unsigned)chunks, (unsigned)groups), 256, tile, s>>>(m, t, count, (int)per);
+  } else {
+    class_sums_list_kernel<<<(unsigned)((count + 7) / 8), 256, 0, s>>>(m, t, count);
+  }
 }
 void launch_zero_row(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
   zero_row_kernel<<<t.P, 256, 0, s>>>(m, t);

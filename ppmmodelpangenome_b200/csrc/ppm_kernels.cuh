@@ -75,6 +75,9 @@ struct ModelDev {
   int word_stride;  // 0: every warp item copies its pattern words to shared memory [n_words][32]; else the sweep reads the device
                     // rows in place with this stride (= n_pat_pad; big trees, where the copy would cost resident warps)
   const int* counts; const int* mrca; const int* freq;
+  // frontier of every pattern (roots of its maximal all-zero subtrees; class sums), computed once per handle:
+  const uint32_t* fr_off;    // [n_pat + 1] offsets into fr_nodes, or null (trees with more than 65,535 nodes: walked per call)
+  const uint16_t* fr_nodes;
   const uint32_t* zero_words;  // n_words * 32 zeros (the all-zero row of add0(), objects.cpp:274-281)
 };
 
@@ -93,7 +96,7 @@ struct TablesDev {
   double2* cherry;       // [P][n_cherries][4] (a, d) of a cherry node for the 4 observation pairs (left | right << 1)
   double4* pairq;        // [P][n_pairs][4] pair term = q.x + q.y*u + q.z*u^2 for the 4 bit combinations (A | B<<1)
   double2* clsT;         // [n_nodes][P] {cat0, cat1} frontier factors F_c = T_c - sum of S over the subtree of c
-  double2* a01;          // [P][n_pat_pad] log p1(root) of the two pure-loss categories per (parameter vector, pattern)
+  double2* a01;          // [n_pat_pad][P] log p1(root) of the two pure-loss categories per (pattern, parameter vector)
   double* scal;          // [P][SC_COUNT]
   double* zeta;          // [P][6][n_nodes] scratch of the node prepass
   double2* zrow;         // [P][n_nodes] Mobile partials (a, d) of the ALL-ZERO row per node, mantissa-normalised ...
@@ -124,6 +127,9 @@ enum { DS_PAIRQ = 1, DS_SLICES = 2, DS_CHERRY = 4, DS_LEAFAB = 8, DS_OPS = 16 };
 void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s);
+// once per handle: frontier sizes per pattern (nf_out) and, given their prefix sums, the lists themselves
+void launch_frontier_count(const ModelDev& m, long long count, uint32_t* nf_out, cudaStream_t s);
+void launch_frontier_fill(const ModelDev& m, long long count, const uint32_t* off, uint16_t* nodes_out, cudaStream_t s);
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s);
 // all-zero row of computeI2/getPobs2 (functions.cpp:300-333): slices spread over the threads; writes SC_IZ_M / SC_IZ_E
 void launch_zero_row(const ModelDev& m, const TablesDev& t, cudaStream_t s);

@@ -110,7 +110,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     auto run = [&](int mode, int nP, double* ll, double* comp, signed char* cat, bool force, double* dist = nullptr) {
       SweepArgs a{};
       a.dist = dist;
-      a.m = md; a.t = t; a.t.P = nP; a.mode = mode; a.first = 0; a.count = count;
+      a.m = md; a.t = t; a.mode = mode; a.first = 0; a.count = count;
       a.n_batches = a.count; a.n_items = a.n_batches * nP; a.comp = comp; a.cat = cat; a.force = force;
       for (int p = 0; p < nP; p++) {
         double s = 0;
@@ -146,7 +146,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
       for (int i = 0; i < md.n_entries + 1 + md.n_blocks * md.R + md.n_ops + md.n_leaves + md.n_pairs + md.n_cherries; i++) prepass_tables_body(md, t, p, i);
     for (long long j = 0; j < count; j++) {
       const int nf = class_frontier(md, md.words + j, (size_t)md.n_pat_pad, zbits.data(), frontier.data());
-      for (int p = 0; p < P; p++) a01[(size_t)p * count + j] = class_sums(t, p, frontier.data(), nf);
+      for (int p = 0; p < P; p++) a01[(size_t)j * P + p] = class_sums(t, p, frontier.data(), nf);
     }
     for (int p = 0; p < P; p++) zero_row_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
