@@ -432,14 +432,17 @@ PPM_HD void zero_row_slice(const ModelDev& m, const TablesDev& t, int p, int j) 
 PPM_HD void zero_row_body(const ModelDev& m, const TablesDev& t, int p, int tid, int nt) {
   int* zxb = t.zxb + (size_t)p * (m.n_blocks + 1);
   const int* zk = t.zk + (size_t)p * m.n_nodes;
-  if (tid == 0) {
+  for (int b = tid; b <= m.n_blocks; b += nt) {  // shifts of the nodes formed in each block ...
     int acc = 0;
-    for (int b = 0; b <= m.n_blocks; b++) {
-      zxb[b] = acc;
-      const BlockDesc bd = m.blk[b];
-      for (int o = bd.op0; o < bd.op1; o++)
-        if (m.sops[o].dst >= 0) acc += zk[m.ops[o].node];
-    }
+    const BlockDesc bd = m.blk[b];
+    for (int o = bd.op0; o < bd.op1; o++)
+      if (m.sops[o].dst >= 0) acc += zk[m.ops[o].node];
+    zxb[b] = acc;
+  }
+  PPM_CTA_BARRIER();
+  if (tid == 0) {  // ... turned into the sum over all earlier blocks
+    int run = 0;
+    for (int b = 0; b <= m.n_blocks; b++) { const int v = zxb[b]; zxb[b] = run; run += v; }
   }
   PPM_CTA_BARRIER();
   for (int j = tid; j < m.n_slices; j += nt) zero_row_slice(m, t, p, j);
