@@ -79,6 +79,9 @@ struct ppm_engine {
   long long first = 0, count = 0;  // this shard's pattern slice
   std::string err;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;    // class sums run here, next to the table prepass and the zero row (they only need the node prepass)
+  cudaEvent_t ev_nodes = nullptr, ev_class = nullptr;
+  bool class_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   double n_launches = 0;
@@ -114,6 +117,9 @@ struct ppm_engine {
     peers.clear();
     if (device >= 0 && cudaSetDevice(device) != cudaSuccess) cudaGetLastError();  // never leave a sticky error behind
     if (ev_done) cudaEventDestroy(ev_done);
+    if (ev_nodes) cudaEventDestroy(ev_nodes);
+    if (ev_class) cudaEventDestroy(ev_class);
+    if (side) cudaStreamDestroy(side);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -134,6 +140,9 @@ struct ppm_engine {
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_nodes, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_class, cudaEventDisableTiming));
   }
 
   void upload_model() { upload_model_impl(false); if (!ppm::sweep_is_staged(md)) upload_model_impl(true); }
@@ -253,8 +262,17 @@ struct ppm_engine {
   }
 
   // prepass + zero row + i2 (functions.cpp:334-344).  After this, scal[p] is complete.
-  void run_prepass(const ppm::TablesDev& t, const double* d_i2_ovr, cudaStream_t s) {
+  // with_class_sums: a sweep follows; its class sums (which need the node prepass only) run on the side stream meanwhile
+  void run_prepass(const ppm::TablesDev& t, const double* d_i2_ovr, cudaStream_t s, bool with_class_sums = false) {
     ppm::launch_prepass_nodes(md, t, s);
+    if (with_class_sums && count > 0) {
+      CK(cudaEventRecord(ev_nodes, s));
+      CK(cudaStreamWaitEvent(side, ev_nodes, 0));
+      ppm::launch_class_sums(md, t, 0, count, side);
+      CK(cudaEventRecord(ev_class, side));
+      class_pending = true;
+      n_launches += 1;
+    }
     ppm::launch_prepass_tables(md, t, s);
     ppm::launch_zero_row(md, t, s);  // the all-zero row of computeI2: slices over threads, not a sweep item
     ppm::launch_prepass_i2(md, t, d_i2_ovr, s);
@@ -273,8 +291,8 @@ struct ppm_engine {
     if (need > partial_cap) { d_partial.alloc(need); partial_cap = need; }
     a.partial = d_partial.p;
     if (a.n_items > 0) {
-      ppm::launch_class_sums(md, t, 0, count, s);
-      n_launches += 1;
+      if (class_pending) { CK(cudaStreamWaitEvent(s, ev_class, 0)); class_pending = false; }
+      else { ppm::launch_class_sums(md, t, 0, count, s); n_launches += 1; }
       ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm, d_dist_out != nullptr);
       d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
       CK(cudaEventRecord(ev0, s));
@@ -472,7 +490,7 @@ int ppm_loglik_device(ppm_handle h, const double* d_params, int32_t P, double* d
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   h->n_launches = 0;
   ppm::TablesDev t = h->tables(P, d_params);
-  h->run_prepass(t, nullptr, s);
+  h->run_prepass(t, nullptr, s, true);
   h->run_sweep(t, 0, d_out_partial, nullptr, nullptr, s);
   if (d_out_i2) h->extract_i2(t, d_out_i2, nullptr, s);
   return PPM_OK;
@@ -585,7 +603,7 @@ static int eval_shard(ppm_handle h, const double* params8, double i2, signed cha
   CK(cudaMemcpyAsync(h->d_params.p, params8, sizeof(double) * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_i2_override.p, &i2, sizeof(double), cudaMemcpyHostToDevice, h->stream));
   ppm::TablesDev t = h->tables(1, h->d_params.p);
-  h->run_prepass(t, h->d_i2_override.p, h->stream);
+  h->run_prepass(t, h->d_i2_override.p, h->stream, true);
   h->d_cat.alloc((size_t)std::max<long long>(h->count, 1));
   h->d_comp.alloc((size_t)std::max<long long>(h->count, 1) * 3);
   h->run_sweep(t, 2, h->d_ll.p, h->d_cat.p, h->d_comp.p, h->stream);
