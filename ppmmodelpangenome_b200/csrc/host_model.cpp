@@ -587,6 +587,15 @@ Program build_program(const Tree& t, int R, bool deep) {
         if (!folded) keep.push_back(e);
       }
       ent[b].swap(keep);
+      // a child's prefix [0,i0) and the new node's suffix [i0,end) partition the block: one update, operands chosen per slice
+      const uint32_t all = (1u << nsl) - 1u;
+      for (int o = pg.blk[b].opc; o < pg.blk[b].op1 && deep; o++) {  // (used by the global-memory variant only)
+        SweepOp& sp = pg.sops[o];
+        if (!sp.mself || sp.dst < 0) continue;
+        const uint32_t ms = (uint32_t)sp.mself, l = (uint32_t)sp.ml, r = (uint32_t)sp.mr;
+        if (l && (l & ms) == 0 && ((l | ms) & all) == all) sp.comb = 1;
+        else if (r && (r & ms) == 0 && ((r | ms) & all) == all) sp.comb = 2;
+      }
     }
   }
   for (int b = 0; b < nb; b++) {

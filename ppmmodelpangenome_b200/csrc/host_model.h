@@ -75,7 +75,8 @@ struct SweepOp {
   // is born inside the block, and the alive slices of a child that dies with this op after being born in an EARLIER block
   // (a prefix of the block).  These lineages have no entry record in that block.
   int32_t mself, ml, mr;
-  int32_t pad_;
+  int32_t comb;  // 1 / 2: the left / right child's prefix and the new node's suffix are complementary and cover the block: one
+                 // update with per-slice operands serves both (general ops only)
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
   int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end;

@@ -27,7 +27,7 @@ struct NodeOpDev {  // == ppm::NodeOp
 };
 struct __align__(16) SweepOpDev {  // == ppm::SweepOp (host_model.h): what the sweep reads per node op
   int32_t lslot, rslot, lbit, rbit, dst, i0, flags, pair;
-  int32_t mself, ml, mr, pad_;  // slice masks of the events folded into the op (host_model.h)
+  int32_t mself, ml, mr, comb;  // slice masks of the events folded into the op, and which child shares an update with the node (host_model.h)
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
   // [e_slot0,e_pair0)   internal lineages alive in every slice (partials in slots)
