@@ -549,6 +549,7 @@ Program build_program(const Tree& t, int R, bool deep) {
     }
   }
   double fp64 = 0;
+  long long n_generic = 0;  // entries served by the generic loops (K/Y-form leaves, partial records)
   // Events folded into node ops: a lineage born inside block b multiplies its alive slices of b at its own op (its
   // partials are in registers there), a lineage that dies inside block b -- when its parent is formed -- multiplies its
   // prefix of b at the parent's op (the merge has just loaded its partials).  Those entries leave the block's lists; what
@@ -639,6 +640,7 @@ Program build_program(const Tree& t, int R, bool deep) {
       int c = cls_of(e), at = (int)pg.entry_ref.size();
       for (int k = 0; k <= c; k++) if (seg0[k] < 0) seg0[k] = at;
       if (c >= 4) pg.n_partial++; else pg.n_full++;
+      if (c >= 3) n_generic++;
       const bool padrec = (c == 0 && e.ref == kPadRef);
       if (!padrec) fp64 += (c == 1) ? 3 * (e.i1 - e.i0) : (c == 2 ? 2 * (e.i1 - e.i0) : 1 + 2 * (e.i1 - e.i0));
       const uint32_t live = (((1u << e.i1) - 1u) & ~((1u << e.i0) - 1u));
@@ -678,6 +680,7 @@ Program build_program(const Tree& t, int R, bool deep) {
   // + general node ops (8 per merge; cherries come from a table), block ends (~3 per slice), epilogue (~60)
   int n_cherry_ops = 0;
   for (const NodeOp& op : pg.ops) n_cherry_ops += op.pair >= 0;
+  pg.lean = n_generic == 0;
   pg.fp64_instr_per_eval = fp64 + 8.0 * ((double)pg.ops.size() - n_cherry_ops) + 3.0 * S + 60;
   return pg;
 }

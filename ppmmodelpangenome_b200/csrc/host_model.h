@@ -101,6 +101,7 @@ struct Program {
   int n_pairs = 0, n_cherries = 0;
   bool leaf_u = false;                            // leaves are (numerically) at height 0: u-form entries are used
   int64_t n_full = 0, n_partial = 0;
+  bool lean = false;                              // no K/Y-form leaf entries, no partial entry records (see sweep_items LEAN)
   // modelled FP64 instruction count per pattern-eval of the main kernel
   double fp64_instr_per_eval = 0;
 };

@@ -47,12 +47,11 @@ struct DevBuf {
 
 }  // namespace
 
-// slices per block of the sweep program: 8 (default), 12 or 16; PPM_R overrides (tuning knob; 16 halves the record and
-// lineage-slot traffic per term of the global-memory variant but its register need costs as much: no gain measured)
-static int program_R(bool = false) {
+// slices per block of the sweep program: 8; PPM_R=16 is a tuning knob of the global-memory variant (it halves the record
+// and lineage-slot traffic per term but its register need costs as much: no gain measured)
+static int program_R(bool deep = false) {
   const char* e = std::getenv("PPM_R");
-  int r = e ? std::atoi(e) : 8;
-  return (r == 16 || r == 12) ? r : 8;
+  return (deep && e && std::atoi(e) == 16) ? 16 : 8;
 }
 
 struct ppm_engine {
@@ -210,6 +209,7 @@ struct ppm_engine {
     // warp at 10,000 genomes: 5 warps; measured 11.3 -> 15.6 TFLOP/s), so the sweep reads the rows in place; the leaf-pair
     // records then carry byte offsets into the rows, which must fit 31 bits.  Smaller trees keep the copy (5,000 genomes:
     // 11.9 TFLOP/s with the copy and 10 warps, 9.9 in place).
+    md.lean = (prog.lean && prog.R == 8 && !std::getenv("PPM_NO_LEAN")) ? 1 : 0;
     md.word_stride = 0;
     if (deep && prog.R == 8 && (size_t)pat.n_words * 128 > 24 * 1024 && (size_t)pat.n_words * (size_t)n_pat_pad * 4 < (1ull << 31) &&
         !std::getenv("PPM_WORDS_SMEM"))

@@ -183,7 +183,7 @@ template <int MODE> struct SlotsOf { typedef SlotsMem type; };
 template <> struct SlotsOf<1> { typedef SlotsTmem type; };
 template <> struct SlotsOf<3> { typedef SlotsTmem type; };  // MODE 3 = MODE 1 compiled for 12 warps (168 registers)
 
-template <int R, int NI, int MODE, bool DIST = false, bool WG = false>  // WG: pattern rows read in place (global-memory variant, big trees)
+template <int R, int NI, int MODE, bool DIST = false, bool WG = false, bool LEAN = false>  // WG: pattern rows read in place (global-memory variant, big trees); LEAN: see sweep_items
 __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
         for (int q = 0; q < NI; q++) mem[q].sw = m.words + (a.first + (batch0 + q) * 32);
       }
       double contrib[NI];
-      sweep_items<R, NI, !STAGED, Slots, DIST, WG>(a, T, p, batch0, lane, mem, contrib, wrec);
+      sweep_items<R, NI, !STAGED, Slots, DIST, WG, LEAN>(a, T, p, batch0, lane, mem, contrib, wrec);
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
       for (int q = 0; q < NI; q++) {
@@ -440,7 +440,7 @@ SweepPlan plan_sweep(const ModelDev& m, long long n_batches, int P, int n_sm, bo
       if (L.total + (size_t)w * NI * (head + ovf * slot_row) <= budget) { w1 = w; pw1 = NI * (head + ovf * slot_row); }
     }
   }
-  if (m.deep) { w0 = 0; w1 = 0; }  // a program built for the global-memory variant (padded segments, rows read in place) stays there
+  if (m.deep || m.R != 8) { w0 = 0; w1 = 0; }  // (R = 16 kernels exist for the global-memory variant only)  // a program built for the global-memory variant (padded segments, rows read in place) stays there
   const long long groups = (n_batches + NI - 1) / NI;  // warp-level work items per parameter vector
   const long long total = groups * (long long)P;
   const char* force = std::getenv("PPM_FORCE_TMEM");
@@ -485,16 +485,16 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
   return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * (m.n_slots + 1) * 32;
 }
 
-template <int R, int MODE, bool DIST = false, bool WG = false>
+template <int R, int MODE, bool DIST = false, bool WG = false, bool LEAN = false>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured[64] = {};  // the attribute is per device (group handles launch on several)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+  sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG, LEAN><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
 
 template <int R>
@@ -518,9 +518,15 @@ void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
     else launch_sweep_t<8, 4, true>(a, pl, s);
     return;
   }
-  if (a.m.R == 16) launch_sweep_r<16>(a, pl, s);
-  else if (a.m.R == 12) launch_sweep_r<12>(a, pl, s);
-  else launch_sweep_r<8>(a, pl, s);
+  if (a.m.lean && a.m.R == 8) {  // lean programs (the usual case): kernels without the generic loops
+    if (pl.mode == 0) { launch_sweep_t<8, 0, false, false, true>(a, pl, s); return; }
+    if (pl.mode == 1) { launch_sweep_t<8, 1, false, false, true>(a, pl, s); return; }
+    if (pl.mode == 3) { launch_sweep_t<8, 3, false, false, true>(a, pl, s); return; }
+    if (pl.mode == 4) { launch_sweep_t<8, 4, false, false, true>(a, pl, s); return; }
+  }
+  if (a.m.R == 16) {  // tuning knob (PPM_R=16): global-memory variant only
+    if (pl.mode == 4) launch_sweep_t<16, 4>(a, pl, s); else launch_sweep_t<16, 2>(a, pl, s);
+  } else launch_sweep_r<8>(a, pl, s);
 }
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s) {
   reduce_kernel<<<P, 256, 0, s>>>(partial, nx, out);

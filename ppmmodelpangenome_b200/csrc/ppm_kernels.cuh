@@ -72,6 +72,7 @@ struct ModelDev {
   const int* entry_ref; const uint32_t* entry_mask; const int* entry_node; const int* entry_block;  // [n_entries]
   // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq
   const uint32_t* words; long long n_pat, n_pat_pad;
+  int lean;         // the program has no K/Y-form leaf entries and no partial entry records: LEAN kernels apply
   int word_stride;  // 0: every warp item copies its pattern words to shared memory [n_words][32]; else the sweep reads the device
                     // rows in place with this stride (= n_pat_pad; big trees, where the copy would cost resident warps)
   const int* counts; const int* mrca; const int* freq;
