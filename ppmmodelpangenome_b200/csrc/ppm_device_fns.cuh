@@ -692,9 +692,11 @@ PPM_HD void live_update(double (&prod)[NI][R], const double (&Y)[R], const doubl
 // DEEP (the variant whose tables and lineage slots live in global memory): the records of the fully-alive entries
 // are streamed through a per-warp shared-memory ring (wrec, 3 chunks of 32 records, cp.async two chunks ahead) and
 // lineage partials are fetched four entries ahead, so L2/HBM latency is covered by ~140 cycles of FP64 work each.
-// LEAN: the program has no K/Y-form leaves and no partial entry records (ultrametric trees with folded events): the three
-// generic loops that serve them are compiled out (8 KB less code, 7 fewer registers: +1.4 % on configs[1]).
-template <int R, int NI, bool DEEP, class Slots, bool DIST = false, bool WG = false, bool LEAN = false>
+// HOT: the instantiation for the objective itself (mode 0) on programs without K/Y-form leaves and partial entry records
+// (ultrametric trees with folded events) and parameter vectors that do not need the factored leaf pairs (pi1 <= 0.95): the
+// generic loops, the factored paths and the per-pattern outputs are compiled out (12 KB less code, 14 fewer registers:
+// +3 % on configs[1]).  Factored parameter vectors of the same launch go through the generic instantiation.
+template <int R, int NI, bool DEEP, class Slots, bool DIST = false, bool WG = false, bool HOT = false>
 PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long long batch0, int lane,
                         const ItemMem<Slots> (&mem)[NI], double (&contrib)[NI], EntryRec* wrec) {
   const ModelDev& m = a.m;
@@ -727,7 +729,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   double Im[NI]; int Ie[NI];  // Mobile integral = Im * 2^-Ie (exponent of an empty sum: +inf)
   double prod[NI][R], Y[R], U[R];
   int ex[NI][R];
-  const bool factored = sc[SC_FACTORED] != 0.;
+  const bool factored = HOT ? false : (sc[SC_FACTORED] != 0.);
 #pragma unroll
   for (int q = 0; q < NI; q++) { X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
 
@@ -995,7 +997,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     }
     // (2) single leaves alive in every slice in block-relative K/Y form (only trees whose leaves are not at height 0):
     // ref = word | next word << 16, mk = the leaf's bit in that word
-    for (int e = bd.e_leaf0; e < bd.e_pleaf0 && !LEAN;) {
+    for (int e = bd.e_leaf0; e < bd.e_pleaf0 && !HOT;) {
       const int ce = (e + 16 < bd.e_pleaf0) ? e + 16 : bd.e_pleaf0;
       double K; uint32_t ref, mk;
       load_rec(T.recs, e, K, ref, mk);
@@ -1233,7 +1235,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
     }
     // (3) leaves merged inside the block: ref = bit position | next << 16, mk = code | live slices << 16
-    if (bd.e_pleaf0 < bd.e_pslot0 && !LEAN) {
+    if (bd.e_pleaf0 < bd.e_pslot0 && !HOT) {
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_pleaf0, K, ref, mk);
       uint32_t wv[NI];
@@ -1257,7 +1259,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       }
     }
     // (4) internal lineages born and/or merged inside the block: ref = slot | next slot << 16
-    if (bd.e_pslot0 < bd.e_end && !LEAN) {
+    if (bd.e_pslot0 < bd.e_end && !HOT) {
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_pslot0, K, ref, mk);
       double2 ad[NI];
@@ -1283,7 +1285,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
     for (int q = 0; q < NI; q++) {
       // (every loop above ends with a range check of its own; the generic partial loops and the deep variant's tails do not)
-      if (DEEP || (!LEAN && bd.e_pleaf0 < bd.e_end))
+      if (DEEP || (!HOT && bd.e_pleaf0 < bd.e_end))
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
       if (DIST) {  // expectedTime2_aux (functions.cpp:713-746): the integrand exp(f_aux) of every slice
         if (a.dist && active[q]) {
@@ -1331,7 +1333,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       double mx = fmax(lik0, fmax(lik1, lik2));
       double tot = (mx == -INFINITY) ? -INFINITY : mx + log(exp(lik0 - mx) + exp(lik1 - mx) + exp(lik2 - mx));
       contrib[q] = tot * (double)m.counts[pat[q]];
-      if (a.mode == 2) {
+      if (!HOT && a.mode == 2) {
         int c = 0;
         if (lik1 > lik0) c = 1;
         if (lik2 > (c ? lik1 : lik0)) c = 2;

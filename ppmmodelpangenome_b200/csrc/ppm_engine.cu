@@ -81,6 +81,7 @@ struct ppm_engine {
   cudaStream_t side = nullptr;    // class sums run here, next to the table prepass and the zero row (they only need the node prepass)
   cudaEvent_t ev_nodes = nullptr, ev_class = nullptr;
   bool class_pending = false;
+  bool hint_no_factored = false;  // set by the host-pointer entry points when no parameter vector has pi1 > 0.95
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   double n_launches = 0;
@@ -287,6 +288,7 @@ struct ppm_engine {
     a.m = md; a.t = t; a.mode = mode; a.first = 0; a.count = count;
     a.n_batches = (count + 31) / 32; a.n_items = a.n_batches * t.P;
     a.cat = d_cat_out; a.comp = d_comp_out; a.force = (mode == 2);
+    a.no_factored = hint_no_factored ? 1 : 0;
     size_t need = (size_t)std::max<long long>(a.n_items, 1);
     if (need > partial_cap) { d_partial.alloc(need); partial_cap = need; }
     a.partial = d_partial.p;
@@ -317,6 +319,16 @@ struct ppm_engine {
     }
   }
 };
+
+// pi1 = g2/(g2+l2) > 0.95 selects the factored leaf pairs (prepass: SC_FACTORED); known on the host for host-pointer calls
+static bool none_factored(const double* params, int P) {
+  for (int p = 0; p < P; p++) {
+    const double g2 = params[8 * p + 4], l2 = params[8 * p + 5];
+    const double pi1 = (g2 == 0.) ? 0. : g2 / (g2 + l2);
+    if (!(pi1 <= 0.95)) return false;
+  }
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------------- C ABI
 #define GUARD_BEGIN try { if (h->device < 0) { h->err = "host-only handle (created with device < 0): no compute"; return PPM_ESTATE; }
@@ -525,7 +537,9 @@ static int group_loglik(ppm_handle h, const double* params, int32_t P, double* o
     CK(cudaSetDevice(e->device));
     e->tables(P, nullptr);
     CK(cudaMemcpyAsync(e->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, e->stream));
+    e->hint_no_factored = none_factored(params, P);
     int rc = ppm_loglik_device(e, e->d_params.p, P, e->d_ll.p, e->d_i2.p, e->stream);
+    e->hint_no_factored = false;
     if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
   }
   CK(cudaSetDevice(h->device));
@@ -561,7 +575,9 @@ int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, do
   CK(cudaSetDevice(h->device));
   h->tables(P, nullptr);
   CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, h->stream));
+  h->hint_no_factored = none_factored(params, P);
   int rc = ppm_loglik_device(h, h->d_params.p, P, h->d_ll.p, h->d_i2.p, h->stream);
+  h->hint_no_factored = false;
   if (rc) return rc;
   std::vector<double> i2(P);
   CK(cudaMemcpyAsync(out_ll, h->d_ll.p, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));

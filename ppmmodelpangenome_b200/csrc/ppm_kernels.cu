@@ -183,7 +183,7 @@ template <int MODE> struct SlotsOf { typedef SlotsMem type; };
 template <> struct SlotsOf<1> { typedef SlotsTmem type; };
 template <> struct SlotsOf<3> { typedef SlotsTmem type; };  // MODE 3 = MODE 1 compiled for 12 warps (168 registers)
 
-template <int R, int NI, int MODE, bool DIST = false, bool WG = false, bool LEAN = false>  // WG: pattern rows read in place (global-memory variant, big trees); LEAN: see sweep_items
+template <int R, int NI, int MODE, bool DIST = false, bool WG = false, bool HOT = false>  // WG: pattern rows read in place (global-memory variant, big trees); HOT: see sweep_items
 __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 512, 1) sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
@@ -240,6 +240,10 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
     const long long b_begin = g0 - (long long)p * groups;
     const long long b_end = (g_end - g0 < groups - b_begin) ? b_begin + (g_end - g0) : groups;
     g0 += b_end - b_begin;
+    if (a.fact_filter) {  // (warp-uniform, CTA-uniform) this launch serves only one kind of parameter vector
+      const bool fu = a.t.scal[(size_t)p * SC_COUNT + SC_FACTORED] != 0.;
+      if ((a.fact_filter == 1) == fu) continue;
+    }
     ItemTables T;
     __syncthreads();  // the previous unit's readers (tables, work counter) are done
     if (threadIdx.x == 0) next_group = 0;
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
         for (int q = 0; q < NI; q++) mem[q].sw = m.words + (a.first + (batch0 + q) * 32);
       }
       double contrib[NI];
-      sweep_items<R, NI, !STAGED, Slots, DIST, WG, LEAN>(a, T, p, batch0, lane, mem, contrib, wrec);
+      sweep_items<R, NI, !STAGED, Slots, DIST, WG, HOT>(a, T, p, batch0, lane, mem, contrib, wrec);
       // fixed-order warp reduction -> partial[p][batch]; reduce_kernel sums the batches in a fixed order too
 #pragma unroll
       for (int q = 0; q < NI; q++) {
@@ -485,16 +489,16 @@ size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl) {
   return pl.staged ? 0 : (size_t)pl.grid_x * pl.warps * kItemsPerWarp * (m.n_slots + 1) * 32;
 }
 
-template <int R, int MODE, bool DIST = false, bool WG = false, bool LEAN = false>
+template <int R, int MODE, bool DIST = false, bool WG = false, bool HOT = false>
 static void launch_sweep_t(const SweepArgs& a, const SweepPlan& pl, cudaStream_t s) {
   static bool configured[64] = {};  // the attribute is per device (group handles launch on several)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
+    cudaFuncSetAttribute(sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);  // static shared memory takes a few bytes
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG, LEAN><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
+  sweep_kernel<R, kItemsPerWarp, MODE, DIST, WG, HOT><<<pl.grid_x, pl.warps * 32, pl.smem_bytes, s>>>(a);
 }
 
 template <int R>
@@ -518,11 +522,16 @@ void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
     else launch_sweep_t<8, 4, true>(a, pl, s);
     return;
   }
-  if (a.m.lean && a.m.R == 8) {  // lean programs (the usual case): kernels without the generic loops
-    if (pl.mode == 0) { launch_sweep_t<8, 0, false, false, true>(a, pl, s); return; }
-    if (pl.mode == 1) { launch_sweep_t<8, 1, false, false, true>(a, pl, s); return; }
-    if (pl.mode == 3) { launch_sweep_t<8, 3, false, false, true>(a, pl, s); return; }
-    if (pl.mode == 4) { launch_sweep_t<8, 4, false, false, true>(a, pl, s); return; }
+  if (a.m.lean && a.m.R == 8 && a.mode == 0 && pl.mode != 2) {
+    // the objective on a lean program (the usual case): HOT kernel for the parameter vectors that are not factored, then
+    // the generic kernel for the factored ones (it exits at once when there are none; skipped when the host knows)
+    a.fact_filter = 1;
+    if (pl.mode == 0) launch_sweep_t<8, 0, false, false, true>(a, pl, s);
+    else if (pl.mode == 1) launch_sweep_t<8, 1, false, false, true>(a, pl, s);
+    else if (pl.mode == 3) launch_sweep_t<8, 3, false, false, true>(a, pl, s);
+    else launch_sweep_t<8, 4, false, false, true>(a, pl, s);
+    if (a.no_factored) return;
+    a.fact_filter = 2;
   }
   if (a.m.R == 16) {  // tuning knob (PPM_R=16): global-memory variant only
     if (pl.mode == 4) launch_sweep_t<16, 4>(a, pl, s); else launch_sweep_t<16, 2>(a, pl, s);

@@ -72,7 +72,7 @@ struct ModelDev {
   const int* entry_ref; const uint32_t* entry_mask; const int* entry_node; const int* entry_block;  // [n_entries]
   // patterns (this shard): words [n_words][n_pat_pad] (word-major), counts, mrca, freq
   const uint32_t* words; long long n_pat, n_pat_pad;
-  int lean;         // the program has no K/Y-form leaf entries and no partial entry records: LEAN kernels apply
+  int lean;         // the program has no K/Y-form leaf entries and no partial entry records: HOT kernels apply
   int word_stride;  // 0: every warp item copies its pattern words to shared memory [n_words][32]; else the sweep reads the device
                     // rows in place with this stride (= n_pat_pad; big trees, where the copy would cost resident warps)
   const int* counts; const int* mrca; const int* freq;
@@ -120,6 +120,8 @@ struct SweepArgs {
   double2* gslots;       // global slot storage when slots do not fit in shared memory
   int force;             // evaluate even when i2 < 0
   double* dist;          // [count][n_slices+1] per-slice Mobile integrand + the integral (expectedTime2_aux; DIST kernels only)
+  int fact_filter;       // 0: every parameter vector; 1: only those with SC_FACTORED == 0 (HOT kernels); 2: only the factored ones
+  int no_factored;       // host hint: no parameter vector of this launch is factored (skips the second launch)
   int stage_mask;        // global-memory variant: which small tables are staged in shared memory anyway (DS_* bits)
 };
 // small tables the global-memory variant stages per parameter vector when they fit (priority order)
