@@ -974,7 +974,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       double2 ad[NI];
 #pragma unroll
       for (int q = 0; q < NI; q++) ad[q] = mem[q].slots.ld((int)(ref & 0xffffu), lane);
-#pragma unroll 2
+#pragma unroll 4
       for (; e < ce; e++) {
         double2 an[NI];
 #pragma unroll
