@@ -742,7 +742,8 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
       for (int q = 0; q < NI; q++)
 #pragma unroll
-        for (int i = 0; i < R; i++) { prod[q][i] = 1.; ex[q][i] = X[q]; }
+        for (int i = 0; i < R; i++) { prod[q][i] = DIST ? 1. : T.wt[b * R + i]; ex[q][i] = X[q]; }  // the slice weight goes in first
+        // (w/nSub of functions.cpp:273-275; padding slices carry weight 0); the DIST output wants the bare integrand
     }
     // ---- node ops: form every node born before the end of this block.
     // store a new lineage (a, d); when it has become small its mantissa is brought back to [0.5,1) and the shift
@@ -1301,7 +1302,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       if (ppm_all(same)) {  // usual case: one common exponent, one scaled add; pairwise sum keeps the chain short
         double t[R];
 #pragma unroll
-        for (int i = 0; i < R; i++) t[i] = prod[q][i] * T.wt[b * R + i];  // padding slices carry weight 0
+        for (int i = 0; i < R; i++) t[i] = DIST ? prod[q][i] * T.wt[b * R + i] : prod[q][i];
 #pragma unroll
         for (int st = 1; st < R; st *= 2)
 #pragma unroll
@@ -1309,7 +1310,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         scaled_add(Im[q], Ie[q], t[0], ex[q][0]);
       } else {
 #pragma unroll
-        for (int i = 0; i < R; i++) scaled_add(Im[q], Ie[q], prod[q][i] * T.wt[b * R + i], ex[q][i]);
+        for (int i = 0; i < R; i++) scaled_add(Im[q], Ie[q], DIST ? prod[q][i] * T.wt[b * R + i] : prod[q][i], ex[q][i]);
       }
     }
   }
