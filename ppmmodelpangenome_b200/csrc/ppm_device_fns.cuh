@@ -807,6 +807,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     }
     // general merges: a leaf child comes from the two-entry leaf table (picked by its pattern bit), an internal one
     // from its slot; both are fetched, the record's flags keep one (no branches in this latency-bound chain)
+#pragma unroll 2
     for (int o = bd.opc; o < bd.op1; o++) {
       const SweepOpDev op = opn;
       opn = T.ops[o + 1];
