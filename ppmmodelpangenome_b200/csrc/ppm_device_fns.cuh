@@ -770,7 +770,6 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     for (int o = bd.op0; o < bd.opc; o++) {
       const SweepOpDev op = opn;
       opn = T.ops[o + 1];
-#pragma unroll
       double av[NI], dd[NI];
 #pragma unroll
       for (int q = 0; q < NI; q++) {
