@@ -1,0 +1,56 @@
+// "Band" program of the slice-parallel sweep (big trees): topology only, built once per tree on the host.
+//
+// The Mobile integral of likRep2 (reference source/functions.cpp:245-279) is a band matrix: lineage s multiplies
+// the slices [js0(s), js1(s)) of the time grid.  The band kernel gives one (pattern, parameter vector) to a CTA of G
+// warps and maps LANES TO SLICES: a tile is 32*R consecutive slices, lane l / register k holds slice 32k + l of the
+// tile.  Phase A prunes the tree level by level (objects.cpp:427-435 in the linear domain) and leaves one 16-byte record
+// (a, -d e^{lam h}) per internal lineage in shared memory; phase B walks, per tile, typed lists of lineage records:
+//   FULL   alive in every slice of the tile          -> all R registers, no masks
+//   F_k    alive in every slice of sub-tile k only    -> register k, no mask
+//   M_k    born and/or merged inside sub-tile k       -> register k, lanes [lo, hi)
+// Leaves alive together as a static pair (host_model.h: Program::leaf_perm) enter as ONE quadratic in u = 1 - e^{-lam t}.
+// Every warp's work is one flat descriptor list (tile begin / record chunks of <= 32 / tile end), so the kernel's
+// control flow is a single loop with the next chunk's records gathered while the current one is multiplied in.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "host_model.h"
+
+namespace ppm {
+
+struct BandOp {          // phase A: one internal, non-root node
+  uint16_t lref, rref;   // child: index of its record in the node array, or (leaf) its pattern bit position
+  uint16_t dst;          // index of this node's record = its birth order among the internal non-root nodes
+  uint16_t flags;        // bit 0: left child is a leaf, bit 1: right child is a leaf
+};
+enum {  // descriptor codes: op | variant << 4 | k << 6 | count << 9
+  BD_TILE_BEGIN = 0, BD_TILE_END = 1, BD_INT = 2, BD_SGL = 3, BD_PAIR = 4, BD_END = 5,
+  BV_FULL = 0, BV_F = 1, BV_M = 2
+};
+struct BandDesc { uint32_t code, off; };  // off: first entry of the chunk, or the tile index for BD_TILE_BEGIN
+
+struct BandProgram {
+  bool ok = false;         // false: the tree is not served by the band kernel (why: `why`)
+  const char* why = "";
+  int R = 4, G = 1, T = 128;
+  int n_tiles = 0, S_pad = 0;
+  int n_int = 0;           // internal non-root nodes
+  int n_levels = 0;
+  std::vector<BandOp> ops;          // grouped by level (children before parents), [lev_off[l], lev_off[l+1])
+  std::vector<int32_t> op_nodes;    // [n_ops][3] node, left child, right child (preorder ids; per-parameter constants)
+  std::vector<int32_t> lev_off;
+  std::vector<uint16_t> nborn;      // [S_pad] internal non-root nodes born at or before each slice (prefix index of the shifts)
+  std::vector<double> wt, slice_t;  // [S_pad] slice weights (0 for padding slices) and midpoints
+  std::vector<BandDesc> desc;       // the G flat descriptor lists, each closed by BD_END
+  std::vector<int32_t> warp_off;    // [G+1]
+  std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 (M records: lanes [lo, hi), hi in 1..32)
+  double fp64_instr_per_eval = 0;   // modelled FP64 instructions per pattern-eval (phase A + phase B)
+  double cost_max = 0, cost_sum = 0;  // modelled phase B cost of the busiest warp / of all warps (balance = sum / (G max))
+  long long n_full16 = 0, n_full32 = 0, n_f16 = 0, n_f32 = 0, n_m16 = 0;
+};
+
+// pg: the handle's sweep program (it fixes the device bit positions of the leaves and the static pairs).
+BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G);
+
+}  // namespace ppm

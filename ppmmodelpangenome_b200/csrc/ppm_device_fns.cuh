@@ -196,6 +196,9 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     sc[SC_LOG1ME2] = log_1me2;
     sc[SC_STOT0] = ss0[0]; sc[SC_STOT1] = ss1[0];
     sc[SC_FACTORED] = (pi1 > 0.95) ? 1. : 0.;
+    // band kernel (big trees): expanded leaf-pair quadratics need pi1 <= 0.95, and its exp tables are taken relative to
+    // the mid-height of the tree, so lam * H / 2 must stay well inside the double range
+    sc[SC_BAND] = (pi1 <= 0.95 && lam * m.H * 0.5 < 600.) ? 1. : 0.;
     sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
     sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
     z0[0] = 0.; z1[0] = 0.;
@@ -335,6 +338,49 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
       double av, d;
       merge_children(leaftab[x & 1], leaftab[x >> 1], orc, pi1, av, d);
       t.cherry[((size_t)p * m.n_cherries + c) * 4 + x] = make_double2(av, d);
+    }
+  }
+}
+
+// Band kernel tables (ppm_kernels.cuh: BandTables), one thread per (parameter vector, i).  Times are taken relative to
+// T0 = H/2 so that exp(+-lam (t - T0)) stays in range: a lineage record holds nbn = -d exp(lam (h - T0)) and a slice
+// Y' = pi1 exp(-lam (t - T0)), hence  a + nbn Y' = m0 + pi1 d (1 - exp(-lam (t - h)))  (functions.cpp:227-240, 269-270).
+// A child's merge factors (objects.cpp:427-435: m0 = a - k0 d, m1 = a + k1 d along its branch, k0 = pi1 E, k1 = (1-pi1) E)
+// are pre-divided by the child's exp(lam (h - T0)) when the child is internal (its record carries nbn, not d).
+PPM_HD void prepass_band_body(const ModelDev& m, const TablesDev& t, const BandDev& b, const BandTables& bt, int p, int i) {
+  const double* par = t.params + 8 * (size_t)p;
+  const double g2 = par[4], l2 = par[5], e2 = par[6], e1 = par[7];
+  const double lam = g2 + l2;
+  const double pi1 = (g2 == 0.) ? 0. : g2 / lam;
+  const double T0 = 0.5 * m.H;
+  if (i < b.n_ops) {
+    const int v = b.op_nodes[3 * i], l = b.op_nodes[3 * i + 1], r = b.op_nodes[3 * i + 2];
+    double* o = bt.bop + ((size_t)p * b.n_ops + i) * BOP_DOUBLES;
+    auto child = [&](int c, double& c0, double& c1) {
+      if (m.left[c] < 0) {  // leaf: applied to d
+        const double E = exp(-lam * m.bl[c]);
+        c0 = -pi1 * E; c1 = (1 - pi1) * E;
+      } else {              // internal: applied to nbn = -d exp(lam (h_c - T0))
+        const double Es = exp(-lam * (m.bl[c] + (m.height[c] - T0)));
+        c0 = pi1 * Es; c1 = -(1 - pi1) * Es;
+      }
+    };
+    child(l, o[0], o[1]);
+    child(r, o[2], o[3]);
+    o[4] = -exp(lam * (m.height[v] - T0));
+    o[5] = 0.;
+  } else if (i < b.n_ops + b.S_pad) {
+    const int j = i - b.n_ops;
+    const double tj = b.slice_t[j];
+    bt.bY[(size_t)p * b.S_pad + j] = pi1 * exp(-lam * (tj - T0));
+    bt.bU[(size_t)p * b.S_pad + j] = 1. - exp(-lam * tj);
+  } else if (i < b.n_ops + b.S_pad + m.n_leaves) {
+    const int pos = i - b.n_ops - b.S_pad;
+    const double hs = m.height[m.leaf_node[pos]];
+    const double Eh = exp(lam * (hs - T0));
+    for (int x = 0; x < 2; x++) {
+      const double m0 = x ? e1 : 1 - e1, m1 = x ? 1 - e2 : e2, d = m1 - m0;  // objects.cpp:407-408
+      bt.bleaf[((size_t)p * m.n_leaves + pos) * 2 + x] = make_double2(m0 + pi1 * d, -d * Eh);
     }
   }
 }

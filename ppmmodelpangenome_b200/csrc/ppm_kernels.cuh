@@ -17,10 +17,11 @@ enum {
   SC_IZ_M, SC_IZ_E,  // zero-row Mobile integral as mantissa * 2^-exp
   SC_FACTORED,         // != 0: evaluate leaf pairs as two linear factors (pi1 close to 1: the expanded quadratic loses digits)
   SC_STOT0, SC_STOT1,  // sum over all branches of the "active" log factor S, categories 0 / 1
-  SC_COUNT = 20  // even: keeps the (a,d) pairs 16-byte aligned in every row
+  SC_BAND,             // != 0: this parameter vector can be served by the band kernel (pi1 <= 0.95 and (g2+l2) H / 2 < 600)
+  SC_COUNT = 22  // even: keeps the (a,d) pairs 16-byte aligned in every row
 };
 
-static_assert(SC_IZ_E < SC_COUNT && SC_COUNT % 2 == 0 && SC_LA0 % 2 == 0, "scal row layout");
+static_assert(SC_BAND < SC_COUNT && SC_COUNT % 2 == 0 && SC_LA0 % 2 == 0, "scal row layout");
 
 struct NodeOpDev {  // == ppm::NodeOp
   int32_t node, lnode, rnode, lref, rref, dst, i0, pair;
@@ -107,6 +108,33 @@ struct TablesDev {
   double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 
+// ---- band kernel (slice-parallel sweep for big trees; band_program.h) ------------------------------------------------
+struct BandOpDev { uint16_t lref, rref, dst, flags; };   // == ppm::BandOp
+struct BandDescDev { uint32_t code, off; };              // == ppm::BandDesc
+enum { BOP_DOUBLES = 6 };  // per (parameter vector, band op): c0_l c1_l c0_r c1_r (child branch factors, see prepass_band_body),
+                           // -exp(lam (h_node - H/2)), unused
+struct BandDev {
+  int R, G, T, n_tiles, S_pad, n_int, n_ops, n_levels, n_desc, n_entries;
+  const BandOpDev* ops; const int* op_nodes; const int* lev_off;
+  const uint16_t* nborn; const double* wt; const double* slice_t;
+  const BandDescDev* desc; const int* warp_off; const uint32_t* entries;
+};
+struct BandTables {     // one row per parameter vector, written by prepass_band
+  double* bop;          // [P][n_ops][BOP_DOUBLES]
+  double* bY;           // [P][S_pad]  pi1 * exp(-lam (t_j - H/2))
+  double* bU;           // [P][S_pad]  u_j = 1 - exp(-lam t_j)
+  double2* bleaf;       // [P][n_leaves][2]  single leaf at bit position pos observed 0 / 1: (a, -d exp(lam (h_leaf - H/2)))
+};
+struct BandArgs {
+  ModelDev m; TablesDev t; BandDev b; BandTables bt;
+  long long count;       // patterns of this shard
+  int n_chunks;          // pattern chunks per parameter vector; unit = (parameter vector, chunk)
+  long long chunk;       // patterns per chunk
+  double* partial;       // [P][n_chunks]
+  int force;
+};
+struct BandPlan { int grid_x, G, n_chunks; long long chunk; size_t smem_bytes; int ctas_per_sm; };
+
 struct SweepArgs {
   ModelDev m;
   TablesDev t;
@@ -120,7 +148,8 @@ struct SweepArgs {
   double2* gslots;       // global slot storage when slots do not fit in shared memory
   int force;             // evaluate even when i2 < 0
   double* dist;          // [count][n_slices+1] per-slice Mobile integrand + the integral (expectedTime2_aux; DIST kernels only)
-  int fact_filter;       // 0: every parameter vector; 1: only those with SC_FACTORED == 0 (HOT kernels); 2: only the factored ones
+  int fact_filter;       // 0: every parameter vector; 1: only those with SC_FACTORED == 0 (HOT kernels); 2: only the factored ones;
+                         // 3: only those the band kernel did not serve (SC_BAND == 0)
   int no_factored;       // host hint: no parameter vector of this launch is factored (skips the second launch)
   int stage_mask;        // global-memory variant: which small tables are staged in shared memory anyway (DS_* bits)
 };
@@ -143,6 +172,12 @@ bool sweep_is_staged(const ModelDev& m);  // depends on the tree/program sizes o
 size_t sweep_scratch_elems(const ModelDev& m, const SweepPlan& pl);  // double2 elements of global slot scratch (0 if staged)
 void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s);
 void launch_reduce(const double* partial, int P, int nx, double* out, cudaStream_t s);
+// band path: out[p] = SC_BAND[p] ? sum(band_partial[p][0..nb)) : sum(partial[p][0..nx))
+void launch_reduce2(const double* partial, int nx, const double* band_partial, int nb, const double* scal, int P, double* out, cudaStream_t s);
+void launch_prepass_band(const ModelDev& m, const TablesDev& t, const BandDev& b, const BandTables& bt, cudaStream_t s);
+BandPlan plan_band(const ModelDev& m, const BandDev& b, long long count, int P, int n_sm);
+size_t band_smem_bytes(const ModelDev& m, const BandDev& b);
+void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
 void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s);  // [n][P] -> [P], rank order
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]

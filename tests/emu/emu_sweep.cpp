@@ -13,7 +13,9 @@
 #include <vector>
 
 #include "../../ppmmodelpangenome_b200/csrc/host_model.h"
+#include "../../ppmmodelpangenome_b200/csrc/band_program.h"
 #include "../../ppmmodelpangenome_b200/csrc/ppm_device_fns.cuh"
+#include "../../ppmmodelpangenome_b200/csrc/band_fns.cuh"
 
 using namespace ppm;
 
@@ -28,6 +30,78 @@ extern "C" void emu_set_posterior_outputs(double* et1, double* dist, double gain
   g_et1 = et1; g_dist = dist; g_gains_g2 = gains_g2; g_gains = gains;
 }
 
+// Scalar interpreter of the band program (band_program.h) for one (pattern, parameter vector): the same records, masks,
+// exponent bookkeeping and tables as the CUDA band kernel, lanes and registers as plain loops.
+static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandProgram& bp, const BandTables& bt, int p, long long pat,
+                            double* comp3) {
+  const double* sc = t.scal + (size_t)p * SC_COUNT;
+  const double pi1 = sc[SC_PI1];
+  auto bit = [&](int pos) { return (int)((md.words[(size_t)(pos >> 5) * md.n_pat_pad + pat] >> (pos & 31)) & 1u); };
+  const double2* leaftab = reinterpret_cast<const double2*>(sc + SC_LA0);
+  std::vector<double2> node(std::max(bp.n_int, 1));
+  std::vector<int> xcum(bp.n_int + 1, 0);
+  const int n_ops = (int)bp.ops.size();
+  for (int o = 0; o < n_ops; o++) {
+    const BandOp& op = bp.ops[o];
+    double xl, yl, xr, yr;
+    if (op.flags & 1) { const double2 v = leaftab[bit(op.lref)]; xl = v.x; yl = v.y; } else { xl = node[op.lref].x; yl = node[op.lref].y; }
+    if (op.flags & 2) { const double2 v = leaftab[bit(op.rref)]; xr = v.x; yr = v.y; } else { xr = node[op.rref].x; yr = node[op.rref].y; }
+    int k;
+    node[op.dst] = band_merge(xl, yl, xr, yr, bt.bop + ((size_t)p * n_ops + o) * BOP_DOUBLES, pi1, k);
+    xcum[op.dst + 1] = k;
+  }
+  for (int i = 0; i < bp.n_int; i++) xcum[i + 1] += xcum[i];
+  const int R = bp.R, T = bp.T;
+  double Im = 0.; int Ie = 0x3fffffff;
+  std::vector<double> prod(32 * R), Y(32 * R), U(32 * R);
+  std::vector<int> ex(32 * R);
+  for (int w = 0; w < bp.G; w++) {
+    int tau = -1;
+    for (int di = bp.warp_off[w];; di++) {
+      const BandDesc d = bp.desc[di];
+      const int op = d.code & 15, var = (d.code >> 4) & 3, k = (d.code >> 6) & 7, cnt = (d.code >> 9) & 63;
+      if (op == BD_END) break;
+      if (op == BD_TILE_BEGIN) {
+        tau = (int)d.off;
+        for (int kk = 0; kk < R; kk++)
+          for (int l = 0; l < 32; l++) {
+            const int j = tau * T + 32 * kk + l;
+            prod[kk * 32 + l] = 1.; ex[kk * 32 + l] = xcum[bp.nborn[j]];
+            Y[kk * 32 + l] = bt.bY[(size_t)p * bp.S_pad + j]; U[kk * 32 + l] = bt.bU[(size_t)p * bp.S_pad + j];
+          }
+        continue;
+      }
+      if (op == BD_TILE_END) {
+        for (int kk = 0; kk < R; kk++)
+          for (int l = 0; l < 32; l++) {
+            const int j = tau * T + 32 * kk + l;
+            scaled_add(Im, Ie, prod[kk * 32 + l] * bp.wt[j], ex[kk * 32 + l]);
+          }
+        continue;
+      }
+      for (int e = 0; e < cnt; e++) {
+        const uint32_t ent = bp.entries[d.off + e];
+        const int ref = ent & 0xffff, lo = (ent >> 16) & 31, hi = (ent >> 21) & 63;
+        double4 q = make_double4(1., 0., 0., 0.);
+        double2 r = make_double2(1., 0.);
+        if (op == BD_INT) r = node[ref];
+        else if (op == BD_SGL) r = bt.bleaf[((size_t)p * md.n_leaves + ref) * 2 + bit(ref)];
+        else q = t.pairq[((size_t)p * md.n_pairs + ref) * 4 + (bit(2 * ref) | (bit(2 * ref + 1) << 1))];
+        for (int kk = (var == BV_FULL ? 0 : k); kk < (var == BV_FULL ? R : k + 1); kk++)
+          for (int l = (var == BV_M ? lo : 0); l < (var == BV_M ? hi : 32); l++) {
+            const int x = kk * 32 + l;
+            prod[x] *= (op == BD_PAIR) ? fma(fma(q.z, U[x], q.y), U[x], q.x) : fma(r.y, Y[x], r.x);
+          }
+      }
+      for (int x = 0; x < 32 * R; x++) {
+        const int be = biased_exp(prod[x]);
+        if (be != 0 && be < 1023 - 400) { prod[x] *= pow2i(400); ex[x] += 400; }
+      }
+    }
+  }
+  return band_mixture(md, t, p, pat, Im, Ie, comp3);
+}
+
 // out_ll[P], out_i2[P], out_parts[P][4]; out_comp [n_patterns][3] / out_cat [n_patterns] for params[0] (may be NULL)
 // i2_override: NULL, or the i2 to use for comp/cat (as assignCat receives MLEi2)
 // R < 0 selects the deep-prefetch code path (global-memory variant) with |R| slices per block
@@ -37,9 +111,17 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
   try {
     Tree tree = read_tree_file(tree_path);
     Patterns pat = read_matrix_file(tree, pa_path, dedupe != 0);
+    // R >= 1000: the band program (slice-parallel sweep), R = 1000 + 100 * G + slices-per-lane
+    const int band_code = R >= 1000 ? R - 1000 : 0;
+    if (band_code) R = 8;
     const bool deep = R < 0;
     if (deep) R = -R;
     Program prog = build_program(tree, R, deep);
+    BandProgram bp;
+    if (band_code) {
+      bp = build_band_program(tree, prog, band_code % 100, band_code / 100);
+      if (!bp.ok) throw std::runtime_error(std::string("band program: ") + bp.why);
+    }
     const long long count = pat.n_patterns;
     if (out_npat) *out_npat = count;
     std::vector<uint32_t> wm((size_t)pat.n_words * count);
@@ -150,12 +232,35 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     }
     for (int p = 0; p < P; p++) zero_row_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
+    BandDev bd{}; BandTables bt{};
+    std::vector<double> bop, bY, bU; std::vector<double2> bleaf;
+    if (band_code) {
+      static_assert(sizeof(BandOpDev) == sizeof(BandOp) && sizeof(BandDescDev) == sizeof(BandDesc), "layout");
+      bd.R = bp.R; bd.G = bp.G; bd.T = bp.T; bd.n_tiles = bp.n_tiles; bd.S_pad = bp.S_pad; bd.n_int = bp.n_int; bd.n_ops = (int)bp.ops.size();
+      bd.n_levels = bp.n_levels; bd.op_nodes = bp.op_nodes.data(); bd.slice_t = bp.slice_t.data(); bd.wt = bp.wt.data();
+      bop.resize((size_t)P * std::max(bd.n_ops, 1) * BOP_DOUBLES); bY.resize((size_t)P * bp.S_pad); bU.resize((size_t)P * bp.S_pad);
+      bleaf.resize((size_t)P * tree.n_leaves * 2);
+      bt.bop = bop.data(); bt.bY = bY.data(); bt.bU = bU.data(); bt.bleaf = bleaf.data();
+      for (int p = 0; p < P; p++)
+        for (int i = 0; i < bd.n_ops + bd.S_pad + md.n_leaves; i++) prepass_band_body(md, t, bd, bt, p, i);
+      for (int p = 0; p < P; p++) {
+        if (scal[(size_t)p * SC_COUNT + SC_BAND] == 0.) throw std::runtime_error("band emulation: parameter vector not eligible (pi1 > 0.95 or lam*H/2 >= 600)");
+        double s = 0;
+        if (!(scal[(size_t)p * SC_COUNT + SC_I2] < 0.))
+          for (long long j = 0; j < count; j++) s += band_item_emu(md, t, bp, bt, p, j, nullptr);
+        out_ll[p] = s;
+      }
+    } else
     run(0, P, out_ll, nullptr, nullptr, false);
     for (int p = 0; p < P; p++) {
       const double* s = &scal[(size_t)p * SC_COUNT];
       out_i2[p] = s[SC_I2];
       if (out_parts) { out_parts[4 * p] = s[SC_P0]; out_parts[4 * p + 1] = s[SC_P1]; out_parts[4 * p + 2] = s[SC_A]; out_parts[4 * p + 3] = s[SC_B]; }
       if (s[SC_I2] < 0.) out_ll[p] = -1e9 * 1. + s[SC_I2];
+    }
+    if (band_code && out_comp) {
+      for (long long j = 0; j < count; j++) band_item_emu(md, t, bp, bt, 0, j, out_comp + 3 * j);
+      out_comp = nullptr;
     }
     if (out_comp || out_cat || g_dist) {
       std::vector<double> dummy(1);
