@@ -185,6 +185,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
     for (int k = 0; k < 3; k++) bp.desc.push_back(BandDesc{desc_code(BD_END, 0, 0, 0), 0u});  // (the kernel reads two descriptors ahead)
     bp.warp_off.push_back((int)bp.desc.size());
   }
+  for (int k = 0; k < 96; k++) bp.desc.push_back(BandDesc{desc_code(BD_END, 0, 0, 0), 0u});  // the kernel's descriptor window reads ahead
   for (int k = 0; k < 64; k++) bp.entries.push_back(0u);  // the gather of the chunk after the last one reads (and ignores) these
   bp.fp64_instr_per_eval = fp64 + 32.0 * fp64_warp + 60;
   bp.ok = true;

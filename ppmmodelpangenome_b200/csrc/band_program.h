@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "band_codes.h"
 #include "host_model.h"
 
 namespace ppm {
@@ -23,10 +24,6 @@ struct BandOp {          // phase A: one internal, non-root node
   uint16_t lref, rref;   // child: index of its record in the node array, or (leaf) its pattern bit position
   uint16_t dst;          // index of this node's record = its birth order among the internal non-root nodes
   uint16_t flags;        // bit 0: left child is a leaf, bit 1: right child is a leaf
-};
-enum {  // descriptor codes: op | variant << 4 | k << 6 | count << 9
-  BD_TILE_BEGIN = 0, BD_TILE_END = 1, BD_INT = 2, BD_SGL = 3, BD_PAIR = 4, BD_END = 5,
-  BV_FULL = 0, BV_F = 1, BV_M = 2
 };
 struct BandDesc { uint32_t code, off; };  // off: first entry of the chunk, or the tile index for BD_TILE_BEGIN
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/ppm_b200.h"
+#include "band_program.h"
 #include "host_model.h"
 #include "ppm_kernels.cuh"
 
@@ -82,6 +83,21 @@ struct ppm_engine {
   cudaEvent_t ev_nodes = nullptr, ev_class = nullptr;
   bool class_pending = false;
   bool hint_no_factored = false;  // set by the host-pointer entry points when no parameter vector has pi1 > 0.95
+  bool hint_all_band = false;     // ... and when every parameter vector is served by the band kernel (SC_BAND)
+  // band kernel (slice-parallel sweep of big trees, band_program.h)
+  ppm::BandProgram band;
+  bool use_band = false;
+  ppm::BandDev bdev{};
+  DevBuf<ppm::BandOpDev> d_bops;
+  DevBuf<int> d_bop_nodes, d_blev_off, d_bwarp_off;
+  DevBuf<uint16_t> d_bnborn;
+  DevBuf<double> d_bwt, d_bslice_t, d_bop, d_bY, d_bU, d_partial_b;
+  DevBuf<ppm::BandDescDev> d_bdesc;
+  DevBuf<uint32_t> d_bentries;
+  DevBuf<double2> d_bleaf;
+  size_t partial_b_cap = 0;
+  int last_sweep_kind = 0;        // 0: lane-per-pattern sweep, 1: band kernel (+ fallback launch), for ppm_get_counters
+  int last_sweep_mode = -1;       // SweepPlan::mode of the last lane-per-pattern launch
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   double n_launches = 0;
@@ -145,7 +161,75 @@ struct ppm_engine {
     CK(cudaEventCreateWithFlags(&ev_class, cudaEventDisableTiming));
   }
 
-  void upload_model() { upload_model_impl(false); if (!ppm::sweep_is_staged(md)) upload_model_impl(true); }
+  void upload_model() {
+    upload_model_impl(false);
+    const bool staged = ppm::sweep_is_staged(md);
+    if (!staged) upload_model_impl(true);
+    setup_band(staged);
+  }
+
+  // Band kernel: chosen where the lane-per-pattern sweep would keep its lineage partials in global memory (or when forced),
+  // unless the tree is so deep (caterpillar) that the level-by-level pruning of one item would dominate its integral.
+  void setup_band(bool staged) {
+    use_band = false;
+    const char* no = std::getenv("PPM_NO_BAND");
+    const char* force = std::getenv("PPM_FORCE_BAND");
+    const bool forced = force && std::atoi(force) != 0;
+    if ((no && std::atoi(no) != 0) || (staged && !forced) || count <= 0) return;
+    int R = 4;
+    if (const char* e = std::getenv("PPM_BAND_R")) { const int v = std::atoi(e); if (v == 2 || v == 4 || v == 8) R = v; }
+    // warps per item: the smallest G that still leaves >= 8 resident warps per SM, else the one with the most warps
+    int bestG = 1, best_warps = 0;
+    ppm::BandProgram probe = ppm::build_band_program(tree, prog, R, 1);
+    if (!probe.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", probe.why); return; }
+    for (int G : {1, 2, 4, 8}) {
+      ppm::BandDev b{}; b.n_int = probe.n_int; b.G = G;
+      const size_t sm = ppm::band_smem_bytes(md, b);
+      if (sm + 1024 > 227 * 1024) continue;
+      const int ctas = (int)std::min<size_t>(std::min<size_t>(32, 64 / G), (227 * 1024) / (sm + 1024));
+      const int warps = ctas * G;
+      if (warps >= 8 && best_warps < 8) { bestG = G; best_warps = warps; }
+      else if (best_warps < 8 && warps > best_warps) { bestG = G; best_warps = warps; }
+    }
+    if (const char* e = std::getenv("PPM_BAND_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) bestG = v; }
+    if (best_warps == 0) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: node records do not fit shared memory\n"); return; }
+    band = bestG == 1 ? std::move(probe) : ppm::build_band_program(tree, prog, R, bestG);
+    {
+      // modelled efficiency: phase A (latency-bound, one barrier per level) against phase B, with the resident warps of an SM
+      ppm::BandDev b{}; b.n_int = band.n_int; b.G = bestG;
+      const size_t sm = ppm::band_smem_bytes(md, b);
+      const int ctas = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(32, 64 / bestG), (227 * 1024) / (sm + 1024)));
+      const double A = 300.0 * band.n_levels + 60.0 * band.n_int / (32.0 * bestG);
+      const double B = std::max(band.cost_max, 1.0) * 2.0;
+      const double eff = std::min(1.0, (ctas * bestG / 4.0) * B / (A + B));
+      if (std::getenv("PPM_PLAN_DEBUG"))
+        fprintf(stderr, "[ppm band] R %d G %d: %d levels, %d tiles, balance %.3f, modelled efficiency %.2f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
+                R, bestG, band.n_levels, band.n_tiles, band.cost_sum / (bestG * std::max(band.cost_max, 1.0)), eff, band.n_full16, band.n_full32,
+                band.n_f16, band.n_f32, band.n_m16);
+      if (eff < 0.7 && !forced) return;
+    }
+    static_assert(sizeof(ppm::BandOpDev) == sizeof(ppm::BandOp) && sizeof(ppm::BandDescDev) == sizeof(ppm::BandDesc), "band layouts");
+    std::vector<ppm::BandOpDev> ops(band.ops.size());
+    if (!ops.empty()) std::memcpy(ops.data(), band.ops.data(), ops.size() * sizeof(ppm::BandOp));
+    d_bops.upload(ops, stream);
+    d_bop_nodes.upload(band.op_nodes, stream); d_blev_off.upload(band.lev_off, stream); d_bwarp_off.upload(band.warp_off, stream);
+    d_bnborn.upload(band.nborn, stream); d_bwt.upload(band.wt, stream); d_bslice_t.upload(band.slice_t, stream);
+    std::vector<ppm::BandDescDev> desc(band.desc.size());
+    std::memcpy(desc.data(), band.desc.data(), desc.size() * sizeof(ppm::BandDesc));
+    d_bdesc.upload(desc, stream);
+    d_bentries.upload(band.entries, stream);
+    CK(cudaStreamSynchronize(stream));
+    bdev.R = band.R; bdev.G = band.G; bdev.T = band.T; bdev.n_tiles = band.n_tiles; bdev.S_pad = band.S_pad; bdev.n_int = band.n_int;
+    bdev.n_ops = (int)band.ops.size(); bdev.n_levels = band.n_levels; bdev.n_desc = (int)band.desc.size(); bdev.n_entries = (int)band.entries.size();
+    bdev.ops = d_bops.p; bdev.op_nodes = d_bop_nodes.p; bdev.lev_off = d_blev_off.p; bdev.nborn = d_bnborn.p; bdev.wt = d_bwt.p;
+    bdev.slice_t = d_bslice_t.p; bdev.desc = d_bdesc.p; bdev.warp_off = d_bwarp_off.p; bdev.entries = d_bentries.p;
+    use_band = true;
+  }
+  ppm::BandTables band_tables() const {
+    ppm::BandTables bt{};
+    bt.bop = d_bop.p; bt.bY = d_bY.p; bt.bU = d_bU.p; bt.bleaf = d_bleaf.p;
+    return bt;
+  }
 
   void upload_model_impl(bool deep) {
     prog = ppm::build_program(tree, program_R(deep), deep);
@@ -253,6 +337,11 @@ struct ppm_engine {
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       d_zrow.alloc((size_t)P * nn); d_zk.alloc((size_t)P * nn); d_zxb.alloc((size_t)P * (std::max(prog.n_blocks, 1) + 1));
       d_zpart.alloc((size_t)P * std::max(tree.n_slices, 1));
+      if (use_band) {
+        d_bop.alloc((size_t)P * std::max<size_t>(band.ops.size(), 1) * ppm::BOP_DOUBLES);
+        d_bY.alloc((size_t)P * band.S_pad); d_bU.alloc((size_t)P * band.S_pad);
+        d_bleaf.alloc((size_t)P * tree.n_leaves * 2);
+      }
       P_cap = P;
     }
     ppm::TablesDev t{};
@@ -275,6 +364,7 @@ struct ppm_engine {
       n_launches += 1;
     }
     ppm::launch_prepass_tables(md, t, s);
+    if (use_band && with_class_sums) { ppm::launch_prepass_band(md, t, bdev, band_tables(), s); n_launches += 1; }
     ppm::launch_zero_row(md, t, s);  // the all-zero row of computeI2: slices over threads, not a sweep item
     ppm::launch_prepass_i2(md, t, d_i2_ovr, s);
     n_launches += 4;
@@ -292,10 +382,41 @@ struct ppm_engine {
     size_t need = (size_t)std::max<long long>(a.n_items, 1);
     if (need > partial_cap) { d_partial.alloc(need); partial_cap = need; }
     a.partial = d_partial.p;
+    const bool band_now = use_band && mode == 0 && d_dist_out == nullptr && a.n_items > 0;
+    last_sweep_kind = band_now ? 1 : 0;
+    if (band_now) {
+      // band kernel for every parameter vector it can serve (SC_BAND), then the lane-per-pattern sweep for the others
+      if (class_pending) { CK(cudaStreamWaitEvent(s, ev_class, 0)); class_pending = false; }
+      else { ppm::launch_class_sums(md, t, 0, count, s); n_launches += 1; }
+      ppm::BandArgs ba{};
+      ba.m = md; ba.t = t; ba.b = bdev; ba.bt = band_tables(); ba.count = count; ba.force = 0;
+      const ppm::BandPlan bpl = ppm::plan_band(md, bdev, count, t.P, n_sm);
+      const size_t needb = (size_t)t.P * bpl.n_chunks;
+      if (needb > partial_b_cap) { d_partial_b.alloc(needb); partial_b_cap = needb; }
+      ba.partial = d_partial_b.p;
+      CK(cudaEventRecord(ev0, s));
+      ppm::launch_band(ba, bpl, s);
+      n_launches += 1;
+      if (!hint_all_band) {
+        ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm, false);
+        d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
+        a.fact_filter = 3;
+        ppm::launch_sweep(a, pl, s);
+        last_sweep_mode = pl.mode;
+        n_launches += 1;
+      }
+      CK(cudaEventRecord(ev1, s));
+      timed = true;
+      ppm::launch_reduce2(d_partial.p, (int)a.n_batches, d_partial_b.p, bpl.n_chunks, d_scal.p, t.P, d_out, s);
+      n_launches += 1;
+      CK(cudaGetLastError());
+      return;
+    }
     if (a.n_items > 0) {
       if (class_pending) { CK(cudaStreamWaitEvent(s, ev_class, 0)); class_pending = false; }
       else { ppm::launch_class_sums(md, t, 0, count, s); n_launches += 1; }
       ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm, d_dist_out != nullptr);
+      last_sweep_mode = pl.mode;
       d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
       CK(cudaEventRecord(ev0, s));
       ppm::launch_sweep(a, pl, s);
@@ -320,6 +441,16 @@ struct ppm_engine {
   }
 };
 
+// every parameter vector eligible for the band kernel (prepass: SC_BAND); known on the host for host-pointer calls
+static bool all_band(const double* params, int P, double H) {
+  for (int p = 0; p < P; p++) {
+    const double g2 = params[8 * p + 4], l2 = params[8 * p + 5];
+    const double lam = g2 + l2;
+    const double pi1 = (g2 == 0.) ? 0. : g2 / lam;
+    if (!(pi1 <= 0.95 && lam * H * 0.5 < 600.)) return false;
+  }
+  return true;
+}
 // pi1 = g2/(g2+l2) > 0.95 selects the factored leaf pairs (prepass: SC_FACTORED); known on the host for host-pointer calls
 static bool none_factored(const double* params, int P) {
   for (int p = 0; p < P; p++) {
@@ -538,8 +669,9 @@ static int group_loglik(ppm_handle h, const double* params, int32_t P, double* o
     e->tables(P, nullptr);
     CK(cudaMemcpyAsync(e->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, e->stream));
     e->hint_no_factored = none_factored(params, P);
+    e->hint_all_band = all_band(params, P, e->tree.H);
     int rc = ppm_loglik_device(e, e->d_params.p, P, e->d_ll.p, e->d_i2.p, e->stream);
-    e->hint_no_factored = false;
+    e->hint_no_factored = false; e->hint_all_band = false;
     if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
   }
   CK(cudaSetDevice(h->device));
@@ -576,8 +708,9 @@ int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, do
   h->tables(P, nullptr);
   CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, h->stream));
   h->hint_no_factored = none_factored(params, P);
+  h->hint_all_band = all_band(params, P, h->tree.H);
   int rc = ppm_loglik_device(h, h->d_params.p, P, h->d_ll.p, h->d_i2.p, h->stream);
-  h->hint_no_factored = false;
+  h->hint_no_factored = false; h->hint_all_band = false;
   if (rc) return rc;
   std::vector<double> i2(P);
   CK(cudaMemcpyAsync(out_ll, h->d_ll.p, sizeof(double) * P, cudaMemcpyDeviceToHost, h->stream));
@@ -764,9 +897,28 @@ int ppm_get_counters(ppm_handle h, double* out4) {
   out4[1] = ms;
   const ppm::Tree& t = h->tree;
   out4[2] = 5.0 * (double)t.n_terms + 28.0 * (t.n_leaves - 1) + 2.0 * t.n_slices;
-  out4[3] = h->prog.fp64_instr_per_eval;
+  out4[3] = (h->use_band && h->last_sweep_kind == 1) ? h->band.fp64_instr_per_eval : h->prog.fp64_instr_per_eval;
   return PPM_OK;
   GUARD_END(h)
+}
+
+int ppm_get_plan(ppm_handle h, int32_t* out16) {
+  if (!h || !out16) return PPM_EINVAL;
+  for (int k = 0; k < 16; k++) out16[k] = 0;
+  out16[0] = h->use_band ? 1 : 0;
+  out16[1] = h->use_band ? h->band.R : 0;
+  out16[2] = h->use_band ? h->band.G : 0;
+  out16[3] = h->last_sweep_kind;
+  out16[4] = h->last_sweep_mode;
+  out16[5] = h->md.word_stride ? 1 : 0;
+  out16[6] = h->md.deep ? 1 : 0;
+  out16[7] = h->md.lean ? 1 : 0;
+  out16[8] = h->use_band ? h->band.n_levels : (int32_t)h->tree.lev_up_off.size() - 1;
+  out16[9] = h->use_band ? h->band.n_tiles : 0;
+  out16[10] = h->prog.n_blocks;
+  out16[11] = h->prog.n_slots;
+  out16[12] = h->prog.leaf_u ? 1 : 0;
+  return PPM_OK;
 }
 
 int ppm_measure_fp64_peak(int device, double* out_tflops) {

@@ -240,7 +240,9 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
     const long long b_begin = g0 - (long long)p * groups;
     const long long b_end = (g_end - g0 < groups - b_begin) ? b_begin + (g_end - g0) : groups;
     g0 += b_end - b_begin;
-    if (a.fact_filter) {  // (warp-uniform, CTA-uniform) this launch serves only one kind of parameter vector
+    if (a.fact_filter == 3) {  // the band kernel has served every parameter vector it can: this launch takes the others
+      if (a.t.scal[(size_t)p * SC_COUNT + SC_BAND] != 0.) continue;
+    } else if (a.fact_filter) {  // (warp-uniform, CTA-uniform) this launch serves only one kind of parameter vector
       const bool fu = a.t.scal[(size_t)p * SC_COUNT + SC_FACTORED] != 0.;
       if ((a.fact_filter == 1) == fu) continue;
     }
@@ -522,7 +524,7 @@ void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
     else launch_sweep_t<8, 4, true>(a, pl, s);
     return;
   }
-  if (a.m.lean && a.m.R == 8 && a.mode == 0 && pl.mode != 2) {
+  if (a.m.lean && a.m.R == 8 && a.mode == 0 && pl.mode != 2 && a.fact_filter != 3) {
     // the objective on a lean program (the usual case): HOT kernel for the parameter vectors that are not factored, then
     // the generic kernel for the factored ones (it exits at once when there are none; skipped when the host knows)
     a.fact_filter = 1;

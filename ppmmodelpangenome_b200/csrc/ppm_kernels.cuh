@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "band_codes.h"
+
 namespace ppm {
 
 // Per-parameter-vector scalars written by the prepass (index into ParamScal::v)

@@ -33,7 +33,7 @@ class Info(C.Structure):
 SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_create_group", "ppm_create_group_from_files", "ppm_destroy", "ppm_last_error", "ppm_get_info",
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
            "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_expected_time1",
-           "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters",
+           "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters", "ppm_get_plan",
            "ppm_measure_fp64_peak"]
 
 
@@ -44,9 +44,12 @@ def lib():
         path = _build.LIB
         try:
             path = _build.build_lib()
-        except Exception:
-            if not os.path.exists(path):
+        except Exception as e:
+            # a stale library would silently run old kernels: only a box without nvcc may use the prebuilt one
+            if not os.path.exists(path) or os.path.exists(_build.NVCC):
                 raise
+            import warnings
+            warnings.warn("ppm_b200: could not rebuild %s (%r); loading the prebuilt library" % (path, e))
         L = C.CDLL(path)
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         L.ppm_create.argtypes = [vp, vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -72,6 +75,7 @@ def lib():
         L.ppm_expected_time2.argtypes = [vp, vp, vp, vp]
         L.ppm_expected_gains.argtypes = [vp, dbl, vp]
         L.ppm_get_counters.argtypes = [vp, vp]
+        L.ppm_get_plan.argtypes = [vp, vp]
         L.ppm_measure_fp64_peak.argtypes = [C.c_int, vp]
         _LIB = L
     return _LIB
@@ -271,6 +275,14 @@ class Inference:
 
     def finalize_device(self, d_i2_ptr, d_ll_ptr, P, stream_ptr=None):
         self._ck(lib().ppm_finalize_ll_device(self._h, d_i2_ptr, d_ll_ptr, P, stream_ptr))
+
+    def plan(self):
+        """Which kernels serve this handle (ppm_get_plan)."""
+        a = np.zeros(16, np.int32)
+        self._ck(lib().ppm_get_plan(self._h, a.ctypes.data))
+        keys = ("band", "band_R", "band_G", "last_kind", "last_mode", "rows_in_place", "deep", "lean", "levels", "band_tiles",
+                "blocks", "slots", "leaf_u")
+        return dict(zip(keys, (int(x) for x in a)))
 
     def counters(self):
         a = np.zeros(4)
