@@ -1,9 +1,12 @@
 // Descriptor codes of the band program, shared by the host builder (band_program.h) and the kernel (band_kernel.cu):
-// code = op | variant << 4 | k << 6 | count << 9
+// one 32-bit word per descriptor: op | variant << 4 | k << 6 | count << 9 | tile << 16 (tile: BD_TILE_BEGIN / BD_TILE_END)
 #pragma once
 namespace ppm {
 enum {
-  BD_TILE_BEGIN = 0, BD_TILE_END = 1, BD_INT = 2, BD_SGL = 3, BD_PAIR = 4, BD_END = 5,  // op
-  BV_FULL = 0, BV_F = 1, BV_M = 2                                                       // variant
+  BD_TILE_BEGIN = 0, BD_TILE_END = 1,
+  BD_REC = 2,    // 16-byte records (a, nbn): internal lineages (node array) and single leaves (entry bit 31), factor a + nbn Y'
+  BD_PAIR = 4,   // 32-byte records: a static leaf pair as one quadratic in u
+  BD_END = 5,
+  BV_FULL = 0, BV_F = 1, BV_M = 2   // variant: every register / register k, all lanes / register k, lanes [lo, hi)
 };
 }  // namespace ppm

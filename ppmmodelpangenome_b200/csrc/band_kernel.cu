@@ -30,7 +30,9 @@ void launch_prepass_band(const ModelDev& m, const TablesDev& t, const BandDev& b
 }
 
 static __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
-enum { BAND_BUF_BYTES = 1024, BAND_WARP_BYTES = 2 * BAND_BUF_BYTES + 2 * 128 };
+// per-warp ring of record chunks: BAND_NB slots of 32 records x 32 B + 32 lane masks; a chunk is gathered BAND_D
+// descriptors ahead of its use (cp.async for the per-parameter leaf tables, which come from L2)
+enum { BAND_NB = 5, BAND_D = 3, BAND_SLOT_BYTES = 1024 + 128, BAND_WARP_BYTES = BAND_NB * BAND_SLOT_BYTES };
 struct BandSmem { size_t node, xk, pw, warp, red, total; };
 static __host__ __device__ inline BandSmem band_layout(int n_int, int n_words, int G) {
   BandSmem L;
@@ -40,12 +42,21 @@ static __host__ __device__ inline BandSmem band_layout(int n_int, int n_words, i
   L.pw = o;   o += al16((size_t)n_words * sizeof(uint32_t));
   L.warp = o; o += (size_t)G * BAND_WARP_BYTES;
   L.red = o;  o += al16((size_t)G * 16);
+  o += 256;  // the software-pipelined record loops read one group of records past a chunk
   L.total = o;
   return L;
 }
 size_t band_smem_bytes(const ModelDev& m, const BandDev& b) { return band_layout(b.n_int, m.n_words, b.G).total; }
 
 template <bool MULTI> __device__ __forceinline__ void item_sync() { if (MULTI) __syncthreads(); else __syncwarp(); }
+
+__device__ __forceinline__ void band_cp16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// t *= f on the lanes of the mask only (a predicated DMUL: no select instructions)
+__device__ __forceinline__ void band_pmul(double& t, double f, uint32_t mask, uint32_t lanebit) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 x;\n\tand.b32 x, %2, %3;\n\tsetp.ne.u32 p, x, 0;\n\t@p mul.f64 %0, %0, %1;\n\t}" : "+d"(t) : "d"(f), "r"(mask), "r"(lanebit));
+}
 
 template <int R>
 __device__ __forceinline__ void band_rescale(double (&prod)[R], int (&ex)[R]) {
@@ -62,7 +73,7 @@ __device__ __forceinline__ void band_rescale(double (&prod)[R], int (&ex)[R]) {
 }
 
 template <int R, bool MULTI>
-__global__ void __launch_bounds__(MULTI ? 256 : 32) band_kernel(BandArgs a) {
+__global__ void __launch_bounds__(MULTI ? 512 : 32) band_kernel(BandArgs a) {
   extern __shared__ __align__(16) unsigned char band_smem[];
   const ModelDev& m = a.m;
   const BandDev& b = a.b;
@@ -71,11 +82,12 @@ __global__ void __launch_bounds__(MULTI ? 256 : 32) band_kernel(BandArgs a) {
   double2* node = reinterpret_cast<double2*>(band_smem + L.node);
   int* xk = reinterpret_cast<int*>(band_smem + L.xk);
   uint32_t* pw = reinterpret_cast<uint32_t*>(band_smem + L.pw);
-  unsigned char* wbuf = band_smem + L.warp + (size_t)warp * BAND_WARP_BYTES;
-  uint32_t* wmask = reinterpret_cast<uint32_t*>(wbuf + 2 * BAND_BUF_BYTES);
+  unsigned char* wring = band_smem + L.warp + (size_t)warp * BAND_WARP_BYTES;
   double* red = reinterpret_cast<double*>(band_smem + L.red);
   const uint32_t lanebit = 1u << lane;
   const int T = 32 * R;
+  const uint32_t* dl = b.desc + b.warp_off[warp];
+  const uint32_t* el0 = b.entries + b.warp_ent_off[warp];
 
   const long long total = (long long)a.t.P * a.n_chunks;
   for (long long unit = blockIdx.x; unit < total; unit += gridDim.x) {
@@ -101,21 +113,37 @@ __global__ void __launch_bounds__(MULTI ? 256 : 32) band_kernel(BandArgs a) {
       if (tid == 0) xk[0] = 0;
       item_sync<MULTI>();
       // ---------------------------------------------------------------- phase A: pruning, level by level
-      for (int lv = 0; lv < b.n_levels; lv++) {
-        const int o1 = b.lev_off[lv + 1];
-        for (int o = b.lev_off[lv] + tid; o < o1; o += nthr) {
-          const BandOpDev op = b.ops[o];
-          const double2* oc2 = reinterpret_cast<const double2*>(bop + (size_t)o * BOP_DOUBLES);
-          const double2 c01 = oc2[0], c23 = oc2[1], c45 = oc2[2];
+      {
+        // rounds of 32*G ops; the next round's topology record and branch constants are fetched (L2) while this one computes
+        uint32_t rd = b.rounds[0];
+        BandOpDev op = {};
+        double2 c01 = {}, c23 = {}, c45 = {};
+        auto fetch = [&](uint32_t r) {
+          if (tid < (int)((r >> 16) & 0x3ffu)) {
+            const int o = (int)(r & 0xffffu) + tid;
+            op = b.ops[o];
+            const double2* oc2 = reinterpret_cast<const double2*>(bop + (size_t)o * BOP_DOUBLES);
+            c01 = oc2[0]; c23 = oc2[1]; c45 = oc2[2];
+          }
+        };
+        fetch(rd);
+        for (int r = 0; r < b.n_rounds; r++) {
+          const uint32_t rn = b.rounds[r + 1];
+          const BandOpDev o = op;
           const double oc[5] = {c01.x, c01.y, c23.x, c23.y, c45.x};
-          double2 Lc, Rc;
-          if (op.flags & 1) Lc = ((pw[op.lref >> 5] >> (op.lref & 31)) & 1u) ? leaf1 : leaf0; else Lc = node[op.lref];
-          if (op.flags & 2) Rc = ((pw[op.rref >> 5] >> (op.rref & 31)) & 1u) ? leaf1 : leaf0; else Rc = node[op.rref];
-          int k;
-          node[op.dst] = band_merge(Lc.x, Lc.y, Rc.x, Rc.y, oc, pi1, k);
-          xk[op.dst + 1] = k;
+          const bool act = tid < (int)((rd >> 16) & 0x3ffu);
+          fetch(rn);
+          if (act) {
+            double2 Lc, Rc;
+            if (o.flags & 1) Lc = ((pw[o.lref >> 5] >> (o.lref & 31)) & 1u) ? leaf1 : leaf0; else Lc = node[o.lref];
+            if (o.flags & 2) Rc = ((pw[o.rref >> 5] >> (o.rref & 31)) & 1u) ? leaf1 : leaf0; else Rc = node[o.rref];
+            int k;
+            node[o.dst] = band_merge(Lc.x, Lc.y, Rc.x, Rc.y, oc, pi1, k);
+            xk[o.dst + 1] = k;
+          }
+          if (rd >> 30) item_sync<MULTI>();
+          rd = rn;
         }
-        item_sync<MULTI>();
       }
       // shifts -> prefix sums in birth order (xk[i] = sum of the shifts of the first i nodes)
       if (warp == 0) {
@@ -133,94 +161,117 @@ __global__ void __launch_bounds__(MULTI ? 256 : 32) band_kernel(BandArgs a) {
       // ---------------------------------------------------------------- phase B: this warp's tiles
       double prod[R], Y[R], U[R];
       int ex[R];
+#pragma unroll
+      for (int k = 0; k < R; k++) { prod[k] = 1.; Y[k] = 0.; U[k] = 0.; ex[k] = 0; }
       double Im = 0.; int Ie = 0x3fffffff;
       int tau = 0;
-      const BandDescDev* dl = b.desc + b.warp_off[warp];
-      // descriptor window: lane l holds descriptor wbase + l; the next window is prefetched
+      // descriptor window: lane l holds descriptor wbase + l; the next 32 are prefetched
       int wbase = 0;
-      BandDescDev dw = dl[lane], dn = dl[32 + lane];
-      auto desc_at = [&](int i, uint32_t& code, uint32_t& off) {
-        code = __shfl_sync(0xffffffffu, dw.code, i - wbase);
-        off = __shfl_sync(0xffffffffu, dw.off, i - wbase);
-      };
-      // gather registers of the NEXT chunk
-      double4 g = make_double4(1., 0., 0., 0.);
-      uint32_t gm = 0u;
-      uint32_t ent_next = 0u;  // this lane's entry of the chunk after the current one
-      {
-        uint32_t c1, o1; desc_at(1, c1, o1);
-        ent_next = ((c1 & 15u) >= BD_INT && (c1 & 15u) <= BD_PAIR) ? b.entries[o1 + lane] : 0u;
-      }
-      for (int di = 0;; di++) {
-        if (di - wbase >= 30) {  // keep di, di+1, di+2 inside the window
-          // (the lists end with three BD_END descriptors and the array is padded, so reading ahead is safe)
-          const int shift = di - wbase;
-          // rebuild the window at wbase' = di: lanes take from dw (upper part) or dn (lower part)
-          const int src = lane + shift;
-          BandDescDev nw;
-          const uint32_t c_a = __shfl_sync(0xffffffffu, dw.code, src & 31), o_a = __shfl_sync(0xffffffffu, dw.off, src & 31);
-          const uint32_t c_b = __shfl_sync(0xffffffffu, dn.code, src & 31), o_b = __shfl_sync(0xffffffffu, dn.off, src & 31);
-          nw.code = src < 32 ? c_a : c_b; nw.off = src < 32 ? o_a : o_b;
-          dw = nw;
-          wbase = di;
-          dn = dl[wbase + 32 + lane];
+      uint32_t dw = dl[lane], dn = dl[32 + lane];
+      const uint32_t* el = el0;
+      uint32_t q0 = 0u, q1 = 0u;  // this lane's entries of the chunks gathered in this and in the next iteration
+      int sG = 0, sC = 2;         // ring slots: gather stage (descriptor di+3), compute stage (descriptor di)
+      for (int di = -(BAND_D + 2);; di++) {
+        {
+          const int lo = di < 0 ? 0 : di;
+          if (lo + BAND_D + 2 - wbase >= 32) {  // slide the window to start at descriptor `lo`
+            const int src = lane + (lo - wbase);
+            const uint32_t c_a = __shfl_sync(0xffffffffu, dw, src & 31), c_b = __shfl_sync(0xffffffffu, dn, src & 31);
+            dw = src < 32 ? c_a : c_b;
+            wbase = lo;
+            dn = dl[wbase + 32 + lane];
+          }
         }
-        uint32_t code, off, code1, off1, code2, off2;
-        desc_at(di, code, off);
-        desc_at(di + 1, code1, off1);
-        desc_at(di + 2, code2, off2);
-        const int op = code & 15;
-        if (op == BD_END) break;
-        // ---- issue the gather of chunk di+1 (its entry was loaded one iteration ago) and the entry load of chunk di+2
-        const int op1 = code1 & 15, cnt1 = (code1 >> 9) & 63, var1 = (code1 >> 4) & 3;
-        const uint32_t ent = ent_next;
-        ent_next = ((code2 & 15u) >= BD_INT && (code2 & 15u) <= BD_PAIR) ? b.entries[off2 + lane] : 0u;
-        if (op1 >= BD_INT && op1 <= BD_PAIR) {
-          const bool valid = lane < cnt1;
-          const uint32_t ref = ent & 0xffffu;
-          g = make_double4(1., 0., 0., 0.);
-          if (valid) {
-            if (op1 == BD_INT) { const double2 r = node[ref]; g.x = r.x; g.y = r.y; }
-            else if (op1 == BD_SGL) {
-              const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
-              const double2 r = bleaf[ref * 2 + bt1]; g.x = r.x; g.y = r.y;
+        // ---- E stage: this lane's entry of the chunk BAND_D + 2 descriptors ahead
+        const uint32_t cE = __shfl_sync(0xffffffffu, dw, di + BAND_D + 2 - wbase);
+        uint32_t e_new = 0u;
+        if (((cE & 15u) | 2u) == 6u || (cE & 15u) == BD_REC) {  // BD_REC (2) or BD_PAIR (4)
+          e_new = el[lane];
+          el += (cE >> 9) & 63u;
+        }
+        // ---- G stage: gather the chunk BAND_D descriptors ahead into its ring slot
+        if (di + BAND_D >= 0) {
+          const uint32_t cG = __shfl_sync(0xffffffffu, dw, di + BAND_D - wbase);
+          const uint32_t opG = cG & 15u;
+          if (opG == BD_REC || opG == BD_PAIR) {
+            const bool valid = lane < (int)((cG >> 9) & 63u);
+            const uint32_t ref = q0 & 0xffffu;
+            unsigned char* slot = wring + sG * BAND_SLOT_BYTES;
+            if (opG == BD_REC) {
+              double2* dst = reinterpret_cast<double2*>(slot) + lane;
+              if (valid && (q0 >> 31)) {
+                const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
+                band_cp16(dst, bleaf + ref * 2 + bt1);
+              } else {
+                *dst = valid ? node[ref] : make_double2(1., 0.);
+              }
+              if (((cG >> 4) & 3u) == BV_M) {
+                const uint32_t lo = (q0 >> 16) & 31u, len = ((q0 >> 21) & 63u) - lo;
+                reinterpret_cast<uint32_t*>(slot + 1024)[lane] = valid ? ((len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo) : 0u;
+              }
             } else {
-              const uint32_t bits = (pw[ref >> 4] >> (2u * (ref & 15u))) & 3u;
-              g = pairq[ref * 4 + bits];
+              double4* dst = reinterpret_cast<double4*>(slot) + lane;
+              if (valid) {
+                const uint32_t bits = (pw[ref >> 4] >> (2u * (ref & 15u))) & 3u;
+                const double4* src = pairq + ref * 4 + bits;
+                band_cp16(dst, src);
+                band_cp16(reinterpret_cast<unsigned char*>(dst) + 16, reinterpret_cast<const unsigned char*>(src) + 16);
+              } else {
+                *dst = make_double4(1., 0., 0., 0.);
+              }
             }
           }
-          if (var1 == BV_M) {
-            const uint32_t lo = (ent >> 16) & 31u, len = ((ent >> 21) & 63u) - lo;
-            gm = valid ? ((len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo) : 0u;
-          }
         }
-        // ---- the current descriptor
-        const unsigned char* buf = wbuf + (size_t)(di & 1) * BAND_BUF_BYTES;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        q0 = q1; q1 = e_new;
+        sG = sG == BAND_NB - 1 ? 0 : sG + 1;
+        if (di < 0) continue;
+        static_assert(BAND_D == 3, "wait_group literal below");
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
+        __syncwarp();
+        // ---- C stage: the current descriptor
+        const uint32_t code = __shfl_sync(0xffffffffu, dw, di - wbase);
+        const int op = code & 15;
+        if (op == BD_END) break;
+        const unsigned char* buf = wring + sC * BAND_SLOT_BYTES;
+        sC = sC == BAND_NB - 1 ? 0 : sC + 1;
         const int var = (code >> 4) & 3, kk = (code >> 6) & 7, cnt = (code >> 9) & 63;
         if (op == BD_TILE_BEGIN) {
-          tau = (int)off;
+          tau = (int)(code >> 16);
 #pragma unroll
           for (int k = 0; k < R; k++) {
             const int j = tau * T + 32 * k + lane;
             prod[k] = 1.; Y[k] = bY[j]; U[k] = bU[j];
             ex[k] = xk[b.nborn[j]];
           }
-        } else if (op == BD_TILE_END) {
+          continue;
+        }
+        if (op == BD_TILE_END) {
 #pragma unroll
           for (int k = 0; k < R; k++) {
             const int j = tau * T + 32 * k + lane;
             scaled_add(Im, Ie, prod[k] * b.wt[j], ex[k]);
           }
-        } else if (op == BD_PAIR) {
+          continue;
+        }
+        if (op == BD_PAIR) {
           const double4* rb = reinterpret_cast<const double4*>(buf);
           if (var == BV_FULL) {
+            double4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = rb[u];
+#pragma unroll 1
             for (int i = 0; i < cnt; i += 4) {
+              double4 qn[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) qn[u] = rb[i + 4 + u];  // next group (past the chunk: read and dropped)
 #pragma unroll
               for (int u = 0; u < 4; u++) {
-                const double4 q = rb[i + u];
 #pragma unroll
-                for (int k = 0; k < R; k++) prod[k] *= fma(fma(q.z, U[k], q.y), U[k], q.x);
+                for (int k = 0; k < R; k++) prod[k] *= fma(fma(q[u].z, U[k], q[u].y), U[k], q[u].x);
               }
+#pragma unroll
+              for (int u = 0; u < 4; u++) q[u] = qn[u];
               if (i == 12 && cnt > 16) band_rescale<R>(prod, ex);
             }
           } else {
@@ -228,27 +279,38 @@ __global__ void __launch_bounds__(MULTI ? 256 : 32) band_kernel(BandArgs a) {
             for (int k = 0; k < R; k++) {
               if (k == kk) {
                 double t0 = 1., t1 = 1., t2 = 1., t3 = 1.;
+                double4 q0r = rb[0], q1r = rb[1], q2r = rb[2], q3r = rb[3];
+#pragma unroll 1
                 for (int i = 0; i < cnt; i += 4) {
-                  const double4 q0 = rb[i], q1 = rb[i + 1], q2 = rb[i + 2], q3 = rb[i + 3];
-                  t0 *= fma(fma(q0.z, U[k], q0.y), U[k], q0.x);
-                  t1 *= fma(fma(q1.z, U[k], q1.y), U[k], q1.x);
-                  t2 *= fma(fma(q2.z, U[k], q2.y), U[k], q2.x);
-                  t3 *= fma(fma(q3.z, U[k], q3.y), U[k], q3.x);
+                  const double4 n0 = rb[i + 4], n1 = rb[i + 5], n2 = rb[i + 6], n3 = rb[i + 7];
+                  t0 *= fma(fma(q0r.z, U[k], q0r.y), U[k], q0r.x);
+                  t1 *= fma(fma(q1r.z, U[k], q1r.y), U[k], q1r.x);
+                  t2 *= fma(fma(q2r.z, U[k], q2r.y), U[k], q2r.x);
+                  t3 *= fma(fma(q3r.z, U[k], q3r.y), U[k], q3r.x);
+                  q0r = n0; q1r = n1; q2r = n2; q3r = n3;
                 }
                 prod[k] *= (t0 * t1) * (t2 * t3);
               }
             }
           }
-        } else {  // BD_INT / BD_SGL: 16-byte records (a, nbn), factor a + nbn * Y'
+        } else {  // BD_REC: 16-byte records (a, nbn), factor a + nbn * Y'
           const double2* rb = reinterpret_cast<const double2*>(buf);
           if (var == BV_FULL) {
+            double2 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) r[u] = rb[u];
+#pragma unroll 1
             for (int i = 0; i < cnt; i += 4) {
+              double2 rn[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) rn[u] = rb[i + 4 + u];
 #pragma unroll
               for (int u = 0; u < 4; u++) {
-                const double2 r = rb[i + u];
 #pragma unroll
-                for (int k = 0; k < R; k++) prod[k] *= fma(r.y, Y[k], r.x);
+                for (int k = 0; k < R; k++) prod[k] *= fma(r[u].y, Y[k], r[u].x);
               }
+#pragma unroll
+              for (int u = 0; u < 4; u++) r[u] = rn[u];
               if (i == 12 && cnt > 16) band_rescale<R>(prod, ex);
             }
           } else if (var == BV_F) {
@@ -256,46 +318,45 @@ __global__ void __launch_bounds__(MULTI ? 256 : 32) band_kernel(BandArgs a) {
             for (int k = 0; k < R; k++) {
               if (k == kk) {
                 double t0 = 1., t1 = 1., t2 = 1., t3 = 1.;
+                double2 r0 = rb[0], r1 = rb[1], r2 = rb[2], r3 = rb[3];
+#pragma unroll 1
                 for (int i = 0; i < cnt; i += 4) {
-                  const double2 r0 = rb[i], r1 = rb[i + 1], r2 = rb[i + 2], r3 = rb[i + 3];
+                  const double2 n0 = rb[i + 4], n1 = rb[i + 5], n2 = rb[i + 6], n3 = rb[i + 7];
                   t0 *= fma(r0.y, Y[k], r0.x);
                   t1 *= fma(r1.y, Y[k], r1.x);
                   t2 *= fma(r2.y, Y[k], r2.x);
                   t3 *= fma(r3.y, Y[k], r3.x);
+                  r0 = n0; r1 = n1; r2 = n2; r3 = n3;
                 }
                 prod[k] *= (t0 * t1) * (t2 * t3);
               }
             }
           } else {
-            const uint32_t* mb = wmask + (di & 1) * 32;
+            const uint32_t* mb = reinterpret_cast<const uint32_t*>(buf + 1024);
 #pragma unroll
             for (int k = 0; k < R; k++) {
               if (k == kk) {
                 double t0 = 1., t1 = 1., t2 = 1., t3 = 1.;
+                double2 r0 = rb[0], r1 = rb[1], r2 = rb[2], r3 = rb[3];
+                uint4 mk = *reinterpret_cast<const uint4*>(mb);
+#pragma unroll 1
                 for (int i = 0; i < cnt; i += 4) {
-                  const double2 r0 = rb[i], r1 = rb[i + 1], r2 = rb[i + 2], r3 = rb[i + 3];
-                  const uint4 mk = *reinterpret_cast<const uint4*>(mb + i);
-                  const double f0 = fma(r0.y, Y[k], r0.x), f1 = fma(r1.y, Y[k], r1.x), f2 = fma(r2.y, Y[k], r2.x), f3 = fma(r3.y, Y[k], r3.x);
-                  t0 *= (mk.x & lanebit) ? f0 : 1.;
-                  t1 *= (mk.y & lanebit) ? f1 : 1.;
-                  t2 *= (mk.z & lanebit) ? f2 : 1.;
-                  t3 *= (mk.w & lanebit) ? f3 : 1.;
+                  const double2 n0 = rb[i + 4], n1 = rb[i + 5], n2 = rb[i + 6], n3 = rb[i + 7];
+                  const uint4 mn = *reinterpret_cast<const uint4*>(mb + i + 4);
+                  band_pmul(t0, fma(r0.y, Y[k], r0.x), mk.x, lanebit);
+                  band_pmul(t1, fma(r1.y, Y[k], r1.x), mk.y, lanebit);
+                  band_pmul(t2, fma(r2.y, Y[k], r2.x), mk.z, lanebit);
+                  band_pmul(t3, fma(r3.y, Y[k], r3.x), mk.w, lanebit);
+                  r0 = n0; r1 = n1; r2 = n2; r3 = n3; mk = mn;
                 }
                 prod[k] *= (t0 * t1) * (t2 * t3);
               }
             }
           }
         }
-        if (op >= BD_INT) band_rescale<R>(prod, ex);
-        // ---- land the gathered records of chunk di+1 in the other buffer
-        if (op1 >= BD_INT && op1 <= BD_PAIR) {
-          unsigned char* nb = wbuf + (size_t)((di + 1) & 1) * BAND_BUF_BYTES;
-          if (op1 == BD_PAIR) reinterpret_cast<double4*>(nb)[lane] = g;
-          else reinterpret_cast<double2*>(nb)[lane] = make_double2(g.x, g.y);
-          if (var1 == BV_M) wmask[((di + 1) & 1) * 32 + lane] = gm;
-        }
-        __syncwarp();
+        band_rescale<R>(prod, ex);
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       // ---------------------------------------------------------------- reduction and mixture
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -330,9 +391,9 @@ BandPlan plan_band(const ModelDev& m, const BandDev& b, long long count, int P, 
   if (const char* e = std::getenv("PPM_BAND_CTAS")) { const int v = std::atoi(e); if (v >= 1) ctas = std::min(ctas, v); }
   pl.ctas_per_sm = std::max(ctas, 1);
   const long long slots = (long long)n_sm * pl.ctas_per_sm;
-  // units = (parameter vector, pattern chunk): about 16 units per resident CTA, chunks of at most 64 patterns
-  long long want = std::max<long long>(1, slots * 16 / std::max(P, 1));
-  long long chunk = std::max<long long>(1, std::min<long long>(64, (count + want - 1) / want));
+  // units = (parameter vector, pattern chunk).  The chunk size depends on the shard only (not on P), so a pattern's place
+  // in the summation order -- and with it the result, bit for bit -- is the same whatever else shares the launch.
+  long long chunk = std::max<long long>(1, std::min<long long>(64, (count + slots * 8 - 1) / (slots * 8)));
   pl.chunk = chunk;
   pl.n_chunks = (int)std::max<long long>(1, (count + chunk - 1) / chunk);
   pl.grid_x = (int)std::max<long long>(1, std::min<long long>(slots, (long long)pl.n_chunks * P));

@@ -63,6 +63,15 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
   }
   bp.lev_off.push_back((int)by_level.size());
   bp.n_levels = (int)bp.lev_off.size() - 1;
+  // phase A rounds: a level is served 32*G ops at a time; the CTA synchronises after the last round of a level only
+  for (int l = 0; l < bp.n_levels; l++)
+    for (int o = bp.lev_off[l]; o < bp.lev_off[l + 1]; o += 32 * G) {
+      const int n = std::min(32 * G, bp.lev_off[l + 1] - o);
+      const bool last = o + 32 * G >= bp.lev_off[l + 1];
+      bp.rounds.push_back((uint32_t)o | ((uint32_t)n << 16) | (last ? 1u << 30 : 0u));
+    }
+  bp.n_rounds = (int)bp.rounds.size();
+  bp.rounds.push_back(0u);  // (the kernel prefetches one round ahead)
 
   bp.n_tiles = (S + T - 1) / T;
   bp.S_pad = bp.n_tiles * T;
@@ -101,67 +110,64 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
     }
   }
 
-  // descriptor chunks per tile
-  struct Chunk { uint32_t code, off; double cost; };
+  // descriptor chunks per tile.  Internal lineages and single leaves share the 16-byte record lists (entry bit 31 = leaf).
+  struct Chunk { uint32_t code; std::vector<uint32_t> ents; double cost; };
   std::vector<std::vector<Chunk>> tchunks(bp.n_tiles);
   std::vector<double> tcost(bp.n_tiles, 0.);
-  double fp64 = 10.0 * bp.n_int * 32.0 / 32.0;  // phase A: ~10 FP64 per merge, one lane each (counted per lane below)
-  double fp64_warp = 0;                          // phase B: FP64 warp instructions
+  double fp64 = 10.0 * bp.n_int;  // phase A: ~10 FP64 per merge, one lane each
+  double fp64_warp = 0;           // phase B: FP64 warp instructions
   std::vector<int> members(std::max(pg.n_pairs, 1));
+  const uint32_t kLeaf = 1u << 31;
   for (int tau = 0; tau < bp.n_tiles; tau++) {
     TileLists& tl = tiles[tau];
     auto emit = [&](int op, int variant, int k, const std::vector<uint32_t>& ents, double per_rec, double fp_per_rec) {
       for (size_t i = 0; i < ents.size(); i += 32) {
         const int cnt = (int)std::min<size_t>(32, ents.size() - i);
-        Chunk c{desc_code(op, variant, k, cnt), (uint32_t)bp.entries.size(), cnt * per_rec + 14.};
-        for (int j = 0; j < cnt; j++) bp.entries.push_back(ents[i + j]);
-        while (bp.entries.size() % 4) bp.entries.push_back(0u);  // (chunks start 16-byte aligned)
-        tchunks[tau].push_back(c);
+        Chunk c{desc_code(op, variant, k, cnt), std::vector<uint32_t>(ents.begin() + i, ents.begin() + i + cnt), cnt * per_rec + 60.};
         tcost[tau] += c.cost;
+        tchunks[tau].push_back(std::move(c));
         fp64_warp += cnt * fp_per_rec;
       }
     };
     // leaves -> pairs (both members in the same list) and singles
-    auto split_leaves = [&](std::vector<int>& leaves, std::vector<uint32_t>& pairs, std::vector<uint32_t>& singles) {
+    auto split_leaves = [&](std::vector<int>& leaves, std::vector<uint32_t>& pairs, std::vector<uint32_t>& recs) {
       std::sort(leaves.begin(), leaves.end());
       for (int pos : leaves) if (pair_of(pos) >= 0) members[pair_of(pos)] = 0;
       for (int pos : leaves) if (pair_of(pos) >= 0) members[pair_of(pos)]++;
       for (int pos : leaves) {
         const int pr = pair_of(pos);
         if (pr >= 0 && members[pr] == 2) { if ((pos & 1) == 0) pairs.push_back((uint32_t)pr); }
-        else singles.push_back((uint32_t)pos);
+        else recs.push_back((uint32_t)pos | kLeaf);
       }
     };
-    std::vector<uint32_t> ints, pairs, singles;
+    std::vector<uint32_t> recs, pairs;
     std::sort(tl.full_int.begin(), tl.full_int.end());
-    for (int r : tl.full_int) ints.push_back((uint32_t)r);
-    split_leaves(tl.full_leaf, pairs, singles);
-    bp.n_full16 += (long long)ints.size() + (long long)singles.size(); bp.n_full32 += (long long)pairs.size();
-    emit(BD_INT, BV_FULL, 0, ints, 2.0 * R, 2.0 * R);
-    emit(BD_PAIR, BV_FULL, 0, pairs, 3.0 * R, 3.0 * R);
-    emit(BD_SGL, BV_FULL, 0, singles, 2.0 * R, 2.0 * R);
+    for (int r : tl.full_int) recs.push_back((uint32_t)r);
+    split_leaves(tl.full_leaf, pairs, recs);
+    bp.n_full16 += (long long)recs.size(); bp.n_full32 += (long long)pairs.size();
+    emit(BD_PAIR, BV_FULL, 0, pairs, 3.0 * R + 2, 3.0 * R);
+    emit(BD_REC, BV_FULL, 0, recs, 2.0 * R + 1, 2.0 * R);
     for (int k = 0; k < R; k++) {
-      ints.clear(); pairs.clear(); singles.clear();
+      recs.clear(); pairs.clear();
       std::sort(tl.f_int[k].begin(), tl.f_int[k].end());
-      for (int r : tl.f_int[k]) ints.push_back((uint32_t)r);
-      split_leaves(tl.f_leaf[k], pairs, singles);
-      bp.n_f16 += (long long)ints.size() + (long long)singles.size(); bp.n_f32 += (long long)pairs.size();
-      emit(BD_INT, BV_F, k, ints, 2.2, 2.0);
-      emit(BD_PAIR, BV_F, k, pairs, 3.2, 3.0);
-      emit(BD_SGL, BV_F, k, singles, 2.2, 2.0);
+      for (int r : tl.f_int[k]) recs.push_back((uint32_t)r);
+      split_leaves(tl.f_leaf[k], pairs, recs);
+      bp.n_f16 += (long long)recs.size(); bp.n_f32 += (long long)pairs.size();
+      emit(BD_PAIR, BV_F, k, pairs, 5.5, 3.0);
+      emit(BD_REC, BV_F, k, recs, 3.5, 2.0);
       auto pack = [](const MEnt& e) { return (uint32_t)e.ref | ((uint32_t)e.lo << 16) | ((uint32_t)e.hi << 21); };
-      ints.clear(); singles.clear();
-      for (const MEnt& e : tl.m_int[k]) ints.push_back(pack(e));
-      for (const MEnt& e : tl.m_leaf[k]) singles.push_back(pack(e));
-      bp.n_m16 += (long long)ints.size() + (long long)singles.size();
-      emit(BD_INT, BV_M, k, ints, 3.5, 2.0);
-      emit(BD_SGL, BV_M, k, singles, 3.5, 2.0);
+      recs.clear();
+      for (const MEnt& e : tl.m_int[k]) recs.push_back(pack(e));
+      for (const MEnt& e : tl.m_leaf[k]) recs.push_back(pack(e) | kLeaf);
+      bp.n_m16 += (long long)recs.size();
+      emit(BD_REC, BV_M, k, recs, 5.5, 2.0);
     }
-    tcost[tau] += 12.0 * R + 40.;  // tile begin / end
+    tcost[tau] += 12.0 * R + 60.;  // tile begin / end
     fp64_warp += 3.0 * R;
   }
 
-  // tiles -> warps: longest-processing-time-first (the tiles near the leaves are the big ones), then ascending per warp
+  // tiles -> warps: longest-processing-time-first (the tiles near the leaves are the big ones), then ascending per warp.
+  // Per warp: one flat list of one-word descriptors and, in the same order, the entries of its chunks back to back.
   std::vector<int> order(bp.n_tiles);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tcost[a] > tcost[b]; });
@@ -175,18 +181,23 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
   bp.cost_max = *std::max_element(load.begin(), load.end());
   bp.cost_sum = std::accumulate(load.begin(), load.end(), 0.);
   bp.warp_off.push_back(0);
+  bp.warp_ent_off.push_back(0);
   for (int w = 0; w < G; w++) {
     std::sort(mine[w].begin(), mine[w].end());
     for (int tau : mine[w]) {
-      bp.desc.push_back(BandDesc{desc_code(BD_TILE_BEGIN, 0, 0, 0), (uint32_t)tau});
-      for (const Chunk& c : tchunks[tau]) bp.desc.push_back(BandDesc{c.code, c.off});
-      bp.desc.push_back(BandDesc{desc_code(BD_TILE_END, 0, 0, 0), (uint32_t)tau});
+      bp.desc.push_back(desc_code(BD_TILE_BEGIN, 0, 0, 0) | ((uint32_t)tau << 16));
+      for (const Chunk& c : tchunks[tau]) {
+        bp.desc.push_back(c.code);
+        bp.entries.insert(bp.entries.end(), c.ents.begin(), c.ents.end());
+      }
+      bp.desc.push_back(desc_code(BD_TILE_END, 0, 0, 0) | ((uint32_t)tau << 16));
     }
-    for (int k = 0; k < 3; k++) bp.desc.push_back(BandDesc{desc_code(BD_END, 0, 0, 0), 0u});  // (the kernel reads two descriptors ahead)
+    for (int k = 0; k < 8; k++) bp.desc.push_back(desc_code(BD_END, 0, 0, 0));  // (the kernel looks five descriptors ahead)
     bp.warp_off.push_back((int)bp.desc.size());
+    bp.warp_ent_off.push_back((int)bp.entries.size());
   }
-  for (int k = 0; k < 96; k++) bp.desc.push_back(BandDesc{desc_code(BD_END, 0, 0, 0), 0u});  // the kernel's descriptor window reads ahead
-  for (int k = 0; k < 64; k++) bp.entries.push_back(0u);  // the gather of the chunk after the last one reads (and ignores) these
+  for (int k = 0; k < 96; k++) bp.desc.push_back(desc_code(BD_END, 0, 0, 0));  // the kernel's descriptor window reads ahead
+  for (int k = 0; k < 64; k++) bp.entries.push_back(0u);  // a chunk's entry load always reads 32 entries
   bp.fp64_instr_per_eval = fp64 + 32.0 * fp64_warp + 60;
   bp.ok = true;
   return bp;

@@ -25,7 +25,6 @@ struct BandOp {          // phase A: one internal, non-root node
   uint16_t dst;          // index of this node's record = its birth order among the internal non-root nodes
   uint16_t flags;        // bit 0: left child is a leaf, bit 1: right child is a leaf
 };
-struct BandDesc { uint32_t code, off; };  // off: first entry of the chunk, or the tile index for BD_TILE_BEGIN
 
 struct BandProgram {
   bool ok = false;         // false: the tree is not served by the band kernel (why: `why`)
@@ -37,11 +36,14 @@ struct BandProgram {
   std::vector<BandOp> ops;          // grouped by level (children before parents), [lev_off[l], lev_off[l+1])
   std::vector<int32_t> op_nodes;    // [n_ops][3] node, left child, right child (preorder ids; per-parameter constants)
   std::vector<int32_t> lev_off;
+  std::vector<uint32_t> rounds;     // phase A: first op | ops << 16 | (last round of its level) << 30; one padding word
+  int n_rounds = 0;
   std::vector<uint16_t> nborn;      // [S_pad] internal non-root nodes born at or before each slice (prefix index of the shifts)
   std::vector<double> wt, slice_t;  // [S_pad] slice weights (0 for padding slices) and midpoints
-  std::vector<BandDesc> desc;       // the G flat descriptor lists, each closed by BD_END
-  std::vector<int32_t> warp_off;    // [G+1]
-  std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 (M records: lanes [lo, hi), hi in 1..32)
+  std::vector<uint32_t> desc;       // the G flat descriptor lists (band_codes.h), each closed by BD_END
+  std::vector<int32_t> warp_off;    // [G+1] first descriptor of each warp
+  std::vector<int32_t> warp_ent_off;  // [G+1] first entry of each warp; a warp's chunks own consecutive entries, in list order
+  std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 | leaf << 31 (M records: lanes [lo, hi), hi in 1..32)
   double fp64_instr_per_eval = 0;   // modelled FP64 instructions per pattern-eval (phase A + phase B)
   double cost_max = 0, cost_sum = 0;  // modelled phase B cost of the busiest warp / of all warps (balance = sum / (G max))
   long long n_full16 = 0, n_full32 = 0, n_f16 = 0, n_f32 = 0, n_m16 = 0;

@@ -92,8 +92,8 @@ struct ppm_engine {
   DevBuf<int> d_bop_nodes, d_blev_off, d_bwarp_off;
   DevBuf<uint16_t> d_bnborn;
   DevBuf<double> d_bwt, d_bslice_t, d_bop, d_bY, d_bU, d_partial_b;
-  DevBuf<ppm::BandDescDev> d_bdesc;
-  DevBuf<uint32_t> d_bentries;
+  DevBuf<uint32_t> d_bdesc, d_bentries, d_brounds;
+  DevBuf<int> d_bwarp_ent_off;
   DevBuf<double2> d_bleaf;
   size_t partial_b_cap = 0;
   int last_sweep_kind = 0;        // 0: lane-per-pattern sweep, 1: band kernel (+ fallback launch), for ppm_get_counters
@@ -176,53 +176,64 @@ struct ppm_engine {
     const char* force = std::getenv("PPM_FORCE_BAND");
     const bool forced = force && std::atoi(force) != 0;
     if ((no && std::atoi(no) != 0) || (staged && !forced) || count <= 0) return;
-    int R = 4;
-    if (const char* e = std::getenv("PPM_BAND_R")) { const int v = std::atoi(e); if (v == 2 || v == 4 || v == 8) R = v; }
-    // warps per item: the smallest G that still leaves >= 8 resident warps per SM, else the one with the most warps
-    int bestG = 1, best_warps = 0;
-    ppm::BandProgram probe = ppm::build_band_program(tree, prog, R, 1);
-    if (!probe.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", probe.why); return; }
-    for (int G : {1, 2, 4, 8}) {
-      ppm::BandDev b{}; b.n_int = probe.n_int; b.G = G;
-      const size_t sm = ppm::band_smem_bytes(md, b);
-      if (sm + 1024 > 227 * 1024) continue;
-      const int ctas = (int)std::min<size_t>(std::min<size_t>(32, 64 / G), (227 * 1024) / (sm + 1024));
-      const int warps = ctas * G;
-      if (warps >= 8 && best_warps < 8) { bestG = G; best_warps = warps; }
-      else if (best_warps < 8 && warps > best_warps) { bestG = G; best_warps = warps; }
+    // Measured crossover on B200 (20,000 genes, fraction of the FP64 peak, band | lane-per-pattern): 1,000 genomes 0.38 | 0.53,
+    // 1,500 0.50 | 0.40, 2,000 0.54 | 0.39, 3,000 0.64 | 0.39, 5,000 0.73 | 0.30 -- below ~1,200 genomes a tile of 128 slices
+    // sees too many births and deaths (per-chunk overhead), above it the lane-per-pattern sweep drowns in its global scratch.
+    int min_leaves = 1200;
+    if (const char* e = std::getenv("PPM_BAND_MIN")) min_leaves = std::atoi(e);
+    if (tree.n_leaves < min_leaves && !forced) return;
+    // Candidates: slices per lane R in {4, 2}, warps per item G in {1, 2, 4, 8, 16}.  The kernel is latency-bound below ~16
+    // resident warps per SM (measured: 1,000 genomes 110 ms at 8 warps, 79 ms at 20), and a CTA's warps own whole tiles, so
+    // the score is (resident warps, capped at 16) x (tile balance over the G warps); ties go to the smaller G, then R = 4.
+    const char* eR = std::getenv("PPM_BAND_R");
+    const char* eG = std::getenv("PPM_BAND_G");
+    const int fixR = eR ? std::atoi(eR) : 0, fixG = eG ? std::atoi(eG) : 0;
+    double best = -1;
+    int ctas_best = 0;
+    bool any = false;
+    for (int R : {4, 2, 8}) {
+      if (fixR ? R != fixR : R != 4) continue;  // R = 4 measured best at 1,000 and 5,000 genomes (R = 2 doubles the chunks, R = 8 turns FULL records into per-register ones)
+      for (int G : {1, 2, 4, 8, 16}) {
+        if (fixG && G != fixG) continue;
+        ppm::BandProgram cand = ppm::build_band_program(tree, prog, R, G);
+        if (!cand.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", cand.why); return; }
+        ppm::BandDev b{}; b.n_int = cand.n_int; b.G = G;
+        const size_t sm = ppm::band_smem_bytes(md, b);
+        if (sm + 1024 > 227 * 1024) continue;
+        const int ctas = (int)std::min<size_t>(std::min<size_t>(32, 64 / G), (227 * 1024) / (sm + 1024));
+        const double balance = cand.cost_sum / (G * std::max(cand.cost_max, 1.0));
+        const double score = std::min(ctas * G, 16) / 16.0 * balance;
+        if (score > best * 1.02) { best = score; band = std::move(cand); ctas_best = ctas; any = true; }
+      }
     }
-    if (const char* e = std::getenv("PPM_BAND_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) bestG = v; }
-    if (best_warps == 0) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: node records do not fit shared memory\n"); return; }
-    band = bestG == 1 ? std::move(probe) : ppm::build_band_program(tree, prog, R, bestG);
+    if (!any) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: node records do not fit shared memory\n"); return; }
     {
       // modelled efficiency: phase A (latency-bound, one barrier per level) against phase B, with the resident warps of an SM
-      ppm::BandDev b{}; b.n_int = band.n_int; b.G = bestG;
-      const size_t sm = ppm::band_smem_bytes(md, b);
-      const int ctas = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(32, 64 / bestG), (227 * 1024) / (sm + 1024)));
+      const int bestG = band.G;
       const double A = 300.0 * band.n_levels + 60.0 * band.n_int / (32.0 * bestG);
       const double B = std::max(band.cost_max, 1.0) * 2.0;
-      const double eff = std::min(1.0, (ctas * bestG / 4.0) * B / (A + B));
+      const double eff = std::min(1.0, (ctas_best * bestG / 4.0) * B / (A + B));
       if (std::getenv("PPM_PLAN_DEBUG"))
-        fprintf(stderr, "[ppm band] R %d G %d: %d levels, %d tiles, balance %.3f, modelled efficiency %.2f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
-                R, bestG, band.n_levels, band.n_tiles, band.cost_sum / (bestG * std::max(band.cost_max, 1.0)), eff, band.n_full16, band.n_full32,
+        fprintf(stderr, "[ppm band] R %d G %d (%d CTAs/SM): %d levels, %d tiles, balance %.3f, modelled efficiency %.2f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
+                band.R, bestG, ctas_best, band.n_levels, band.n_tiles, band.cost_sum / (bestG * std::max(band.cost_max, 1.0)), eff, band.n_full16, band.n_full32,
                 band.n_f16, band.n_f32, band.n_m16);
       if (eff < 0.7 && !forced) return;
     }
-    static_assert(sizeof(ppm::BandOpDev) == sizeof(ppm::BandOp) && sizeof(ppm::BandDescDev) == sizeof(ppm::BandDesc), "band layouts");
+    static_assert(sizeof(ppm::BandOpDev) == sizeof(ppm::BandOp), "band layouts");
     std::vector<ppm::BandOpDev> ops(band.ops.size());
     if (!ops.empty()) std::memcpy(ops.data(), band.ops.data(), ops.size() * sizeof(ppm::BandOp));
     d_bops.upload(ops, stream);
     d_bop_nodes.upload(band.op_nodes, stream); d_blev_off.upload(band.lev_off, stream); d_bwarp_off.upload(band.warp_off, stream);
     d_bnborn.upload(band.nborn, stream); d_bwt.upload(band.wt, stream); d_bslice_t.upload(band.slice_t, stream);
-    std::vector<ppm::BandDescDev> desc(band.desc.size());
-    std::memcpy(desc.data(), band.desc.data(), desc.size() * sizeof(ppm::BandDesc));
-    d_bdesc.upload(desc, stream);
+    d_bdesc.upload(band.desc, stream);
     d_bentries.upload(band.entries, stream);
+    d_brounds.upload(band.rounds, stream); d_bwarp_ent_off.upload(band.warp_ent_off, stream);
     CK(cudaStreamSynchronize(stream));
     bdev.R = band.R; bdev.G = band.G; bdev.T = band.T; bdev.n_tiles = band.n_tiles; bdev.S_pad = band.S_pad; bdev.n_int = band.n_int;
     bdev.n_ops = (int)band.ops.size(); bdev.n_levels = band.n_levels; bdev.n_desc = (int)band.desc.size(); bdev.n_entries = (int)band.entries.size();
     bdev.ops = d_bops.p; bdev.op_nodes = d_bop_nodes.p; bdev.lev_off = d_blev_off.p; bdev.nborn = d_bnborn.p; bdev.wt = d_bwt.p;
     bdev.slice_t = d_bslice_t.p; bdev.desc = d_bdesc.p; bdev.warp_off = d_bwarp_off.p; bdev.entries = d_bentries.p;
+    bdev.rounds = d_brounds.p; bdev.n_rounds = band.n_rounds; bdev.warp_ent_off = d_bwarp_ent_off.p;
     use_band = true;
   }
   ppm::BandTables band_tables() const {

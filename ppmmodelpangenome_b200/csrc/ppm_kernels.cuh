@@ -112,14 +112,13 @@ struct TablesDev {
 
 // ---- band kernel (slice-parallel sweep for big trees; band_program.h) ------------------------------------------------
 struct BandOpDev { uint16_t lref, rref, dst, flags; };   // == ppm::BandOp
-struct BandDescDev { uint32_t code, off; };              // == ppm::BandDesc
 enum { BOP_DOUBLES = 6 };  // per (parameter vector, band op): c0_l c1_l c0_r c1_r (child branch factors, see prepass_band_body),
                            // -exp(lam (h_node - H/2)), unused
 struct BandDev {
-  int R, G, T, n_tiles, S_pad, n_int, n_ops, n_levels, n_desc, n_entries;
-  const BandOpDev* ops; const int* op_nodes; const int* lev_off;
+  int R, G, T, n_tiles, S_pad, n_int, n_ops, n_levels, n_rounds, n_desc, n_entries;
+  const BandOpDev* ops; const int* op_nodes; const int* lev_off; const uint32_t* rounds;
   const uint16_t* nborn; const double* wt; const double* slice_t;
-  const BandDescDev* desc; const int* warp_off; const uint32_t* entries;
+  const uint32_t* desc; const int* warp_off; const int* warp_ent_off; const uint32_t* entries;
 };
 struct BandTables {     // one row per parameter vector, written by prepass_band
   double* bop;          // [P][n_ops][BOP_DOUBLES]

@@ -57,12 +57,13 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
   std::vector<int> ex(32 * R);
   for (int w = 0; w < bp.G; w++) {
     int tau = -1;
+    size_t eoff = bp.warp_ent_off[w];
     for (int di = bp.warp_off[w];; di++) {
-      const BandDesc d = bp.desc[di];
-      const int op = d.code & 15, var = (d.code >> 4) & 3, k = (d.code >> 6) & 7, cnt = (d.code >> 9) & 63;
+      const uint32_t code = bp.desc[di];
+      const int op = code & 15, var = (code >> 4) & 3, k = (code >> 6) & 7, cnt = (code >> 9) & 63;
       if (op == BD_END) break;
       if (op == BD_TILE_BEGIN) {
-        tau = (int)d.off;
+        tau = (int)(code >> 16);
         for (int kk = 0; kk < R; kk++)
           for (int l = 0; l < 32; l++) {
             const int j = tau * T + 32 * kk + l;
@@ -80,12 +81,11 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
         continue;
       }
       for (int e = 0; e < cnt; e++) {
-        const uint32_t ent = bp.entries[d.off + e];
+        const uint32_t ent = bp.entries[eoff + e];
         const int ref = ent & 0xffff, lo = (ent >> 16) & 31, hi = (ent >> 21) & 63;
         double4 q = make_double4(1., 0., 0., 0.);
         double2 r = make_double2(1., 0.);
-        if (op == BD_INT) r = node[ref];
-        else if (op == BD_SGL) r = bt.bleaf[((size_t)p * md.n_leaves + ref) * 2 + bit(ref)];
+        if (op == BD_REC) r = (ent >> 31) ? bt.bleaf[((size_t)p * md.n_leaves + ref) * 2 + bit(ref)] : node[ref];
         else q = t.pairq[((size_t)p * md.n_pairs + ref) * 4 + (bit(2 * ref) | (bit(2 * ref + 1) << 1))];
         for (int kk = (var == BV_FULL ? 0 : k); kk < (var == BV_FULL ? R : k + 1); kk++)
           for (int l = (var == BV_M ? lo : 0); l < (var == BV_M ? hi : 32); l++) {
@@ -93,6 +93,7 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
             prod[x] *= (op == BD_PAIR) ? fma(fma(q.z, U[x], q.y), U[x], q.x) : fma(r.y, Y[x], r.x);
           }
       }
+      eoff += cnt;
       for (int x = 0; x < 32 * R; x++) {
         const int be = biased_exp(prod[x]);
         if (be != 0 && be < 1023 - 400) { prod[x] *= pow2i(400); ex[x] += 400; }
@@ -235,7 +236,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     BandDev bd{}; BandTables bt{};
     std::vector<double> bop, bY, bU; std::vector<double2> bleaf;
     if (band_code) {
-      static_assert(sizeof(BandOpDev) == sizeof(BandOp) && sizeof(BandDescDev) == sizeof(BandDesc), "layout");
+      static_assert(sizeof(BandOpDev) == sizeof(BandOp), "layout");
       bd.R = bp.R; bd.G = bp.G; bd.T = bp.T; bd.n_tiles = bp.n_tiles; bd.S_pad = bp.S_pad; bd.n_int = bp.n_int; bd.n_ops = (int)bp.ops.size();
       bd.n_levels = bp.n_levels; bd.op_nodes = bp.op_nodes.data(); bd.slice_t = bp.slice_t.data(); bd.wt = bp.wt.data();
       bop.resize((size_t)P * std::max(bd.n_ops, 1) * BOP_DOUBLES); bY.resize((size_t)P * bp.S_pad); bU.resize((size_t)P * bp.S_pad);
