@@ -114,10 +114,13 @@ int ppm_get_double_array(ppm_handle h, int which, double* out, int64_t capacity)
  * partials over shards, then call ppm_finalize_ll.  out_i2 may be NULL.  Host pointers. */
 int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, double* out_i2);
 
-/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the
- * handle's own stream): d_params [P][8], d_out_partial [P] per-shard partial sums (no penalty),
+/* Same with DEVICE pointers, asynchronous on `stream`: a cudaStream_t passed as void*.  NULL is the legacy default
+ * stream, exactly as in the CUDA runtime (work is ordered against the caller's own default-stream work); pass
+ * PPM_STREAM_OWN to use the handle's private non-blocking stream instead -- then the caller must order its reads and
+ * writes of the buffers itself.  d_params [P][8], d_out_partial [P] per-shard partial sums (no penalty),
  * d_out_i2 [P].  This is the entry used with inputs resident in HBM and with an external all-reduce
  * (NCCL through torch.distributed) between it and ppm_finalize_ll_device. */
+#define PPM_STREAM_OWN ((void*)(intptr_t)-1)
 int ppm_loglik_device(ppm_handle h, const double* d_params, int32_t P, double* d_out_partial, double* d_out_i2,
                       void* stream);
 /* ll[p] = i2[p] < 0 ? -1e9 + i2[p] : ll[p]   (functions.cpp:362-364), in place. */
@@ -174,6 +177,17 @@ int ppm_get_counters(ppm_handle h, double* out4);
 int ppm_get_plan(ppm_handle h, int32_t* out16);
 /* DFMA micro-benchmark: measured FP64 FMA throughput of the device in TFLOP/s (2 flop per FMA). */
 int ppm_measure_fp64_peak(int device, double* out_tflops);
+
+/* ---- input generation (benchmarks; host code, no GPU) ----------------------------------------------------- */
+
+/* PPM gene simulator: the model of the reference's R scripts (simulation_aux.R: sim.N :92-118, sim.I1 :121-170, sim.I2
+ * :173-238; run_simulations.R:63-78) on a flat preorder tree.  frac3 = fractions of Persistent / Private / Mobile genes
+ * (genes are kept in that order), rates_L = {l0, l1, g2, l2} times the tree length L (the reference's parametrisation:
+ * 1, 20, 50, 2500), s_10 / s_01 the observation error rates; all-zero genes are redrawn.  out_rows: n_genes rows of
+ * ceil(n_leaves/32) uint32 in the ppm_create format; out_truth10 (may be NULL): N0 l0 i1 l1 g2 l2 s_10 s_01 H L of the
+ * simulation.  Gene g uses its own random stream (seed, g): the result does not depend on n_threads (0 = all cores). */
+int ppm_simulate_genes(const ppm_tree* tree, int64_t n_genes, uint64_t seed, const double* frac3, const double* rates_L,
+                       double s_10, double s_01, int32_t n_threads, uint32_t* out_rows, double* out_truth10);
 
 #ifdef __cplusplus
 }

@@ -373,7 +373,10 @@ Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
       for (const char* q = p; *q; q++) n_genes += (*q == ',');
       rows.assign((size_t)n_genes * nw, 0u);
     }
-    if (it == leaf_of.end()) continue;  // genome not in the tree: unused by the likelihood
+    // A genome that is no leaf of the tree: the reference keeps such a row in `matrix`, where it changes freq[], meanGenes (hence
+    // the optimiser's bounds and start) and pattern identity, and leaves mrca uninitialised (functions.cpp:51,64,117-127).  Nothing
+    // sensible can be reproduced from that, so the input is rejected.
+    if (it == leaf_of.end()) throw std::runtime_error("matrix: genome row '" + name + "' is not a leaf of the tree");
     int k = it->second;
     if (seen[k]) {  // a later row with the same name wins (std::map assignment, objects.cpp:195)
       for (int64_t g = 0; g < n_genes; g++) rows[(size_t)g * nw + (k >> 5)] &= ~(1u << (k & 31));

@@ -317,6 +317,7 @@ struct ppm_engine {
       DevBuf<uint32_t> d_nf;
       d_nf.alloc((size_t)count);
       ppm::launch_frontier_count(md, count, d_nf.p, stream);
+      CK(cudaGetLastError());  // (a failed launch would leave nf uninitialised)
       std::vector<uint32_t> nf((size_t)count), off((size_t)count + 1, 0u);
       CK(cudaMemcpyAsync(nf.data(), d_nf.p, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
@@ -490,6 +491,8 @@ static void finish_one(ppm_engine* e, int device, int rank, int world) {
     e->first = np * rank / world;
     e->count = np * (rank + 1) / world - e->first;
   } else {
+    // node ids travel as 16 bits through the frontier lists, the sweep records and the band program
+    if (e->tree.n_nodes > 65535) throw std::runtime_error("trees with more than 32,768 genomes (65,535 nodes) are not supported on the device");
     e->init_device(device);
     e->upload_model();
   }
@@ -641,7 +644,8 @@ int ppm_loglik_device(ppm_handle h, const double* d_params, int32_t P, double* d
   if (!h || !d_params || !d_out_partial || P < 1) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
   GUARD_BEGIN
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  // NULL is the legacy default stream, as everywhere in CUDA; PPM_STREAM_OWN selects the handle's private stream
+  cudaStream_t s = (stream == PPM_STREAM_OWN) ? h->stream : (cudaStream_t)stream;
   h->n_launches = 0;
   ppm::TablesDev t = h->tables(P, d_params);
   h->run_prepass(t, nullptr, s, true);
@@ -662,7 +666,7 @@ int ppm_finalize_ll_device(ppm_handle h, const double* d_i2, double* d_ll, int32
   if (!h || !d_i2 || !d_ll) return PPM_EINVAL;
   GUARD_BEGIN
   CK(cudaSetDevice(h->device));
-  ppm::launch_finalize(d_i2, d_ll, P, stream ? (cudaStream_t)stream : h->stream);
+  ppm::launch_finalize(d_i2, d_ll, P, (stream == PPM_STREAM_OWN) ? h->stream : (cudaStream_t)stream);
   CK(cudaGetLastError());
   return PPM_OK;
   GUARD_END(h)
@@ -681,7 +685,7 @@ static int group_loglik(ppm_handle h, const double* params, int32_t P, double* o
     CK(cudaMemcpyAsync(e->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, e->stream));
     e->hint_no_factored = none_factored(params, P);
     e->hint_all_band = all_band(params, P, e->tree.H);
-    int rc = ppm_loglik_device(e, e->d_params.p, P, e->d_ll.p, e->d_i2.p, e->stream);
+    int rc = ppm_loglik_device(e, e->d_params.p, P, e->d_ll.p, e->d_i2.p, (void*)e->stream);
     e->hint_no_factored = false; e->hint_all_band = false;
     if (rc) { if (e != h) h->err = "shard " + std::to_string(e->shard_rank) + ": " + e->err; return rc; }
   }
@@ -720,7 +724,7 @@ int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, do
   CK(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * 8 * P, cudaMemcpyHostToDevice, h->stream));
   h->hint_no_factored = none_factored(params, P);
   h->hint_all_band = all_band(params, P, h->tree.H);
-  int rc = ppm_loglik_device(h, h->d_params.p, P, h->d_ll.p, h->d_i2.p, h->stream);
+  int rc = ppm_loglik_device(h, h->d_params.p, P, h->d_ll.p, h->d_i2.p, (void*)h->stream);
   h->hint_no_factored = false; h->hint_all_band = false;
   if (rc) return rc;
   std::vector<double> i2(P);

@@ -359,23 +359,35 @@ void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s
   dim3 g((n + 255) / 256, t.P);
   prepass_tables_kernel<<<g, 256, 0, s>>>(m, t);
 }
+// per warp: one bit per node + up to n_nodes 16-bit frontier ids (2.1 bytes per node: 139 KB at the 65,535-node limit the
+// engine accepts).  Above 48 KB the kernel needs the opt-in attribute, set per device and instantiation.
+template <int MODE>
 static void walk_geometry(const ModelDev& m, long long count, int& wpc, size_t& smem, dim3& g) {
   const size_t per_warp = ((size_t)((m.n_nodes + 31) / 32) + (size_t)((m.n_nodes + 1) / 2)) * sizeof(uint32_t);
-  wpc = (int)std::min<size_t>(8, (48 * 1024) / per_warp);
-  if (wpc < 1) wpc = 1;
+  const size_t budget = 200 * 1024;
+  wpc = (int)std::min<size_t>(8, std::max<size_t>(1, (per_warp * 8 <= 48 * 1024 ? 48 * 1024 : budget) / per_warp));
   smem = per_warp * wpc;
+  if (smem > 48 * 1024) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaFuncSetAttribute(class_walk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+  }
   g = dim3((unsigned)((count + wpc - 1) / wpc));
 }
 void launch_frontier_count(const ModelDev& m, long long count, uint32_t* nf_out, cudaStream_t s) {
   if (count <= 0) return;
   int wpc; size_t smem; dim3 g;
-  walk_geometry(m, count, wpc, smem, g);
+  walk_geometry<0>(m, count, wpc, smem, g);
   class_walk_kernel<0><<<g, wpc * 32, smem, s>>>(m, TablesDev{}, count, nf_out, nullptr, nullptr);
 }
 void launch_frontier_fill(const ModelDev& m, long long count, const uint32_t* off, uint16_t* nodes_out, cudaStream_t s) {
   if (count <= 0) return;
   int wpc; size_t smem; dim3 g;
-  walk_geometry(m, count, wpc, smem, g);
+  walk_geometry<1>(m, count, wpc, smem, g);
   class_walk_kernel<1><<<g, wpc * 32, smem, s>>>(m, TablesDev{}, count, nullptr, off, nodes_out);
 }
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s) {
@@ -383,7 +395,7 @@ void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, l
   if (count <= 0) return;
   if (!m.fr_off) {  // no lists: walk per call
     int wpc; size_t smem; dim3 g;
-    walk_geometry(m, count, wpc, smem, g);
+    walk_geometry<2>(m, count, wpc, smem, g);
     class_walk_kernel<2><<<g, wpc * 32, smem, s>>>(m, t, count, nullptr, nullptr, nullptr);
     return;
   }

@@ -33,7 +33,7 @@ class Info(C.Structure):
 SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_create_group", "ppm_create_group_from_files", "ppm_destroy", "ppm_last_error", "ppm_get_info",
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
            "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_expected_time1",
-           "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters", "ppm_get_plan",
+           "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters", "ppm_get_plan", "ppm_simulate_genes",
            "ppm_measure_fp64_peak"]
 
 
@@ -76,6 +76,7 @@ def lib():
         L.ppm_expected_gains.argtypes = [vp, dbl, vp]
         L.ppm_get_counters.argtypes = [vp, vp]
         L.ppm_get_plan.argtypes = [vp, vp]
+        L.ppm_simulate_genes.argtypes = [vp, i64, C.c_uint64, vp, vp, dbl, dbl, i32, vp, vp]
         L.ppm_measure_fp64_peak.argtypes = [C.c_int, vp]
         _LIB = L
     return _LIB
@@ -87,6 +88,25 @@ def measure_fp64_peak(device=0):
     if rc:
         raise PPMError(rc, "DFMA micro-benchmark failed")
     return v.value
+
+
+def simulate_genes(left, right, branch_len, n_genes, seed, frac=(0.25, 0.35, 0.40), rates_L=(1.0, 20.0, 50.0, 2500.0),
+                   s_10=0.01, s_01=0.01, threads=0):
+    """C++ PPM gene simulator (ppm_simulate_genes): bit-packed rows [n_genes][ceil(n/32)] for ppm_create + the truth dict.
+    Host code; used by bench.py for the 1M-gene workloads (the numpy simulator in simulate.py serves the small ones)."""
+    left = np.ascontiguousarray(left, np.int32); right = np.ascontiguousarray(right, np.int32)
+    bl = np.ascontiguousarray(branch_len, np.float64)
+    t = _Tree(len(left), left.ctypes.data, right.ctypes.data, bl.ctypes.data)
+    nw = ((len(left) + 1) // 2 + 31) // 32
+    rows = np.zeros((int(n_genes), nw), np.uint32)
+    fr = np.ascontiguousarray(frac, np.float64); rt = np.ascontiguousarray(rates_L, np.float64)
+    truth = np.zeros(10)
+    rc = lib().ppm_simulate_genes(C.byref(t), int(n_genes), int(seed), fr.ctypes.data, rt.ctypes.data, float(s_10), float(s_01),
+                                  int(threads), rows.ctypes.data, truth.ctypes.data)
+    if rc:
+        raise PPMError(rc, "ppm_simulate_genes failed")
+    keys = ("N0", "l0", "i1", "l1", "g2", "l2", "s_10", "s_01", "H", "L")
+    return rows, dict(zip(keys, truth.tolist()))
 
 
 def _params(p, P=None):
@@ -270,6 +290,8 @@ class Inference:
         return v.value
 
     # device-pointer entry points (bench / multi-GPU plumbing)
+    STREAM_OWN = C.c_void_p(-1)  # PPM_STREAM_OWN: the handle's private stream; None / 0 is the legacy default stream
+
     def loglik_device(self, d_params_ptr, P, d_out_ptr, d_i2_ptr, stream_ptr=None):
         self._ck(lib().ppm_loglik_device(self._h, d_params_ptr, P, d_out_ptr, d_i2_ptr, stream_ptr))
 

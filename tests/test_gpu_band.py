@@ -40,7 +40,7 @@ class _Env:
 
 
 @pytest.mark.parametrize("name", ["syn100", "syn300", "cat40"])
-@pytest.mark.parametrize("R,G", [(4, 1), (2, 1), (8, 1), (4, 2), (4, 4), (2, 8)])
+@pytest.mark.parametrize("R,G", [(4, 1), (2, 1), (8, 1), (4, 2), (4, 4), (2, 8), (4, 16)])
 def test_band_kernel_against_reference_golden(ppm, golden, name, R, G):
     g = golden(name)
     with _Env(PPM_FORCE_BAND=1, PPM_BAND_R=R, PPM_BAND_G=G):
@@ -74,7 +74,7 @@ def _seeded(ppm, tmp_path, n, genes, seed):
     return tp, pp, P, truth
 
 
-@pytest.mark.parametrize("n,genes", [(1000, 120), (5000, 16)])
+@pytest.mark.parametrize("n,genes", [(1500, 80), (5000, 16)])
 def test_band_kernel_big_trees_against_oracle(ppm, tmp_path, n, genes):
     """Default plan: the band kernel is chosen on its own for these trees (the oracle on a sample it can hold)."""
     from oracle import cport, model
@@ -102,11 +102,13 @@ def test_band_kernel_big_trees_against_oracle(ppm, tmp_path, n, genes):
 
 def test_band_kernel_shards_add_up(ppm, tmp_path):
     tp, pp, P, truth = _seeded(ppm, tmp_path, 1000, 200, 77)
-    one = ppm.Inference(tp, pp, dedupe=True, device=0)
+    with _Env(PPM_FORCE_BAND=1):
+        one = ppm.Inference(tp, pp, dedupe=True, device=0)
     ll, i2 = one.loglik_batch(P, return_i2=True)
     tot = np.zeros(len(P))
     for rk in range(3):
-        s = ppm.Inference(tp, pp, dedupe=True, device=0, shard_rank=rk, shard_world=3)
+        with _Env(PPM_FORCE_BAND=1):
+            s = ppm.Inference(tp, pp, dedupe=True, device=0, shard_rank=rk, shard_world=3)
         assert s.plan()["band"] == 1
         part, i2s = s.loglik_batch(P, return_i2=True)
         assert np.array_equal(i2s, i2)
@@ -114,7 +116,8 @@ def test_band_kernel_shards_add_up(ppm, tmp_path):
         s.close()
     tot = np.where(i2 < 0, -1e9 + i2, tot)
     assert np.allclose(tot, ll, rtol=1e-13, atol=0)
-    grp = ppm.Inference(tp, pp, dedupe=True, devices=[0, 0])
+    with _Env(PPM_FORCE_BAND=1):
+        grp = ppm.Inference(tp, pp, dedupe=True, devices=[0, 0])
     assert np.allclose(grp.loglik_batch(P), ll, rtol=1e-13, atol=0)
     grp.close(); one.close()
 
