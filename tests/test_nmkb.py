@@ -39,6 +39,20 @@ def test_trajectory_identical_to_reference_optimiser(driver, which, speculate):
         assert ev == gold["n_lines"] - 1
 
 
+@pytest.mark.parametrize("which", [0, 1, 2])
+@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("multi", [False, True])
+def test_speculation_levels_and_interleaved_multistart_keep_the_trajectory(driver, which, level, multi):
+    """Level 1 = the 4 trial points of an iteration per launch, level 2 = + its 8 shrink points (12 per launch); `multi`
+    serves three trajectories round by round as the CLI's multi-start driver does.  Every logical evaluation sequence is
+    the reference optimiser's, bit for bit."""
+    gold = json.load(open(os.path.join(GOLD, "nm_trajectory.json")))[str(which)]
+    r = subprocess.run([driver, str(which), "1", str(level)] + (["multi"] if multi else []), capture_output=True, text=True, check=True)
+    assert hashlib.sha256(r.stdout.encode()).hexdigest() == gold["sha256"]
+    ev, la = [int(x) for x in r.stderr.split() if x.isdigit()]
+    assert la < gold["n_lines"]  # fewer launches than logical evaluations
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "nm_ref_driver")), reason="reference optimiser driver not built")
 @pytest.mark.parametrize("which", [0, 1, 2])
 def test_golden_is_what_the_reference_header_produces(which):
