@@ -63,3 +63,27 @@ def test_fixed_start_and_append(tmp_path):
     assert out[3].startswith("1th iteration: 262 0.0432618 114 8.01477 1.60832 159.089 0.00586003 0.00260816 -13657.3532")
     out2, mle2, _ = _run(tmp_path, ["0"] + start)
     assert mle2 == mle + mle and mle.startswith("0 ")   # ios::app (functions.cpp:472)
+
+
+def test_multistart_equals_consecutive_single_runs(tmp_path):
+    """PPM_STARTS=3: seeds 1, 2, 3 fitted together (their trial and shrink points share the launches).  Every trajectory
+    is its own serial run, bit for bit: same stdout block, same mle_param.txt line; inf_cat.txt is the last seed's."""
+    singles = []
+    for seed in ("1", "2", "3"):
+        d = tmp_path / ("s" + seed)
+        d.mkdir()
+        singles.append(_run(d, [seed]))
+    for level in ("1", "2", "0"):
+        d = tmp_path / ("m" + level)
+        d.mkdir()
+        out, mle, cat = _run(d, ["1"], {"PPM_STARTS": "3", "PPM_SPECULATE": level})
+        assert mle == "".join(s[1] for s in singles)
+        assert cat == singles[2][2]
+        body = lambda ls: [l for l in ls if not l.startswith(("tree OK", "matrix OK", "inference initialization OK", "DONE"))]
+        assert body(out) == sum((body(s[0]) for s in singles), [])
+
+
+def test_usage_errors(tmp_path):
+    r = subprocess.run([CLI, "0", os.path.join(GOLD, "ref_test.nwk"), os.path.join(GOLD, "ref_test.pa.txt"), str(tmp_path / "a"), str(tmp_path / "b")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr     # seed 0 without the 8 start values
