@@ -169,11 +169,13 @@ int ppm_expected_gains(ppm_handle h, double g2, double* out);
  * kernel's arithmetic (model count). */
 int ppm_get_counters(ppm_handle h, double* out4);
 /* Which kernels serve this handle (tests assert that every variant is exercised; nothing in the reference corresponds):
- * [0] band kernel in use (slice-parallel sweep of big trees), [1] its slices per lane R, [2] warps per item G,
+ * [0] band kernel in use (slice-parallel sweep of big trees), [1] its slices per lane R, [2] work units (stream layout)
+ * or warps (one-CTA layout) per item G,
  * [3] kind of the last objective launch (0 lane-per-pattern sweep, 1 band kernel + fallback launch),
  * [4] variant of the last lane-per-pattern sweep (0 shared memory, 1/3 tensor memory, 2/4 global memory; -1 none yet),
  * [5] pattern rows read in place, [6] program built for the global-memory variant, [7] lean program (HOT kernels),
- * [8] pruning levels, [9] band tiles, [10] sweep blocks, [11] lineage slots, [12] leaves at height 0; [13..15] reserved. */
+ * [8] pruning levels, [9] band tiles, [10] sweep blocks, [11] lineage slots, [12] leaves at height 0,
+ * [13] band kernels in the stream layout (prune / integral / mixture, band_stream.cu); [14..15] reserved. */
 int ppm_get_plan(ppm_handle h, int32_t* out16);
 /* DFMA micro-benchmark: measured FP64 FMA throughput of the device in TFLOP/s (2 flop per FMA). */
 int ppm_measure_fp64_peak(int device, double* out_tflops);

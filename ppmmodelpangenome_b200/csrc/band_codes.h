@@ -1,5 +1,5 @@
 // Descriptor codes of the band program, shared by the host builder (band_program.h) and the kernel (band_kernel.cu):
-// one 32-bit word per descriptor: op | variant << 4 | k << 6 | count << 9 | tile << 16 (tile: BD_TILE_BEGIN / BD_TILE_END)
+// one 32-bit word per descriptor: op | variant << 4 | k << 6 | count << 9 (7 bits) | tile << 16 (tile: BD_TILE_BEGIN / BD_TILE_END)
 #pragma once
 namespace ppm {
 enum {
@@ -9,4 +9,6 @@ enum {
   BD_END = 5,
   BV_FULL = 0, BV_F = 1, BV_M = 2   // variant: every register / register k, all lanes / register k, lanes [lo, hi)
 };
+enum { kBandStreamChunk = 64, kBandBlockWords = 68 };  // stream layout: records per chunk (two per lane); the one-CTA layout uses 32
+static const unsigned kBandPadEntry = 0xffffffffu;  // stream layout: padding entry of a chunk (identity record)
 }  // namespace ppm

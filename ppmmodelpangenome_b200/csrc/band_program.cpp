@@ -19,14 +19,14 @@ inline uint32_t desc_code(int op, int variant, int k, int count) {
 }
 }  // namespace
 
-BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
+BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, bool stream) {
   BandProgram bp;
-  bp.R = R; bp.G = G; bp.T = 32 * R;
+  bp.R = R; bp.G = G; bp.T = 32 * R; bp.stream = stream;
   const int nn = t.n_nodes, nl = t.n_leaves, S = t.n_slices, T = bp.T;
   if (!pg.leaf_u) { bp.why = "leaves are not at height 0"; return bp; }
   if (nn > 65535) { bp.why = "more than 65,535 nodes"; return bp; }
   if (nl < 4 || S < 1) { bp.why = "tree too small"; return bp; }
-  if (R < 1 || R > 8 || G < 1 || G > 32) { bp.why = "bad R/G"; return bp; }
+  if (R < 1 || R > 8 || G < 1 || G > (stream ? 4096 : 32)) { bp.why = "bad R/G"; return bp; }
 
   // alive slice range of every non-root lineage (functions.cpp:130-141, 250-262), as in build_program
   std::vector<int> js0(nn, S), js1(nn, S);
@@ -47,11 +47,13 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
     if (t.left[v] >= 0) lev[v] = 1 + std::max(lev[t.left[v]], lev[t.right[v]]);
   std::vector<int> by_level;
   for (int v = 1; v < nn; v++) if (t.left[v] >= 0) by_level.push_back(v);
-  std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return lev[a] != lev[b] ? lev[a] < lev[b] : idx[a] < idx[b]; });
+  // stream layout: birth order (children are born before their parents), so that an op's record index is its own index
+  if (stream) std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return idx[a] < idx[b]; });
+  else std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return lev[a] != lev[b] ? lev[a] < lev[b] : idx[a] < idx[b]; });
   bp.lev_off.push_back(0);
   for (size_t i = 0; i < by_level.size(); i++) {
     const int v = by_level[i], l = t.left[v], r = t.right[v];
-    if (i > 0 && lev[v] != lev[by_level[i - 1]]) bp.lev_off.push_back((int)i);
+    if (!stream && i > 0 && lev[v] != lev[by_level[i - 1]]) bp.lev_off.push_back((int)i);
     BandOp op{};
     const bool ll = t.left[l] < 0, rl = t.left[r] < 0;
     op.lref = (uint16_t)(ll ? dpos(l) : idx[l]);
@@ -63,8 +65,9 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
   }
   bp.lev_off.push_back((int)by_level.size());
   bp.n_levels = (int)bp.lev_off.size() - 1;
+  if (stream) { bp.n_levels = 0; for (int v = 0; v < nn; v++) bp.n_levels = std::max(bp.n_levels, lev[v]); }
   // phase A rounds: a level is served 32*G ops at a time; the CTA synchronises after the last round of a level only
-  for (int l = 0; l < bp.n_levels; l++)
+  for (int l = 0; !stream && l < bp.n_levels; l++)
     for (int o = bp.lev_off[l]; o < bp.lev_off[l + 1]; o += 32 * G) {
       const int n = std::min(32 * G, bp.lev_off[l + 1] - o);
       const bool last = o + 32 * G >= bp.lev_off[l + 1];
@@ -121,9 +124,11 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
   for (int tau = 0; tau < bp.n_tiles; tau++) {
     TileLists& tl = tiles[tau];
     auto emit = [&](int op, int variant, int k, const std::vector<uint32_t>& ents, double per_rec, double fp_per_rec) {
-      for (size_t i = 0; i < ents.size(); i += 32) {
-        const int cnt = (int)std::min<size_t>(32, ents.size() - i);
+      const size_t ch = stream ? (size_t)kBandStreamChunk : 32;
+      for (size_t i = 0; i < ents.size(); i += ch) {
+        const int cnt = (int)std::min<size_t>(ch, ents.size() - i);
         Chunk c{desc_code(op, variant, k, cnt), std::vector<uint32_t>(ents.begin() + i, ents.begin() + i + cnt), cnt * per_rec + 60.};
+        if (stream) c.ents.resize(ch, kBandPadEntry);  // every chunk owns a full set of entries: the gather needs no bounds
         tcost[tau] += c.cost;
         tchunks[tau].push_back(std::move(c));
         fp64_warp += cnt * fp_per_rec;
@@ -196,8 +201,41 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G) {
     bp.warp_off.push_back((int)bp.desc.size());
     bp.warp_ent_off.push_back((int)bp.entries.size());
   }
+  if (stream) {
+    // device form of the lists: one block of kBandBlockWords words per descriptor = its kBandStreamChunk entries + its code.
+    // A tile-begin block carries, instead of entries, the shift-prefix index of each of its slices (nborn), packed so that
+    // lane l finds slices l, 32 + l, ... in words 2l, 2l + 1.  Every list is followed by END blocks (the kernel reads ahead).
+    if (R > 4) { bp.why = "stream layout: at most 4 slices per lane"; return bp; }
+    for (int w = 0; w < G; w++) {
+      bp.unit_blk_off.push_back((int32_t)(bp.blocks.size() / kBandBlockWords));
+      size_t eoff = bp.warp_ent_off[w];
+      for (int di = bp.warp_off[w];; di++) {
+        const uint32_t code = bp.desc[di];
+        const int op = code & 15;
+        std::vector<uint32_t> blk(kBandBlockWords, kBandPadEntry);
+        blk[kBandStreamChunk] = code;
+        if (op == BD_REC || op == BD_PAIR) {
+          std::copy(bp.entries.begin() + eoff, bp.entries.begin() + eoff + kBandStreamChunk, blk.begin());
+          eoff += kBandStreamChunk;
+        } else if (op == BD_TILE_BEGIN) {
+          const int tau = (int)(code >> 16);
+          for (int l = 0; l < 32; l++) {
+            uint32_t h[4] = {0, 0, 0, 0};
+            for (int k = 0; k < R; k++) h[k] = bp.nborn[tau * T + 32 * k + l];
+            blk[2 * l] = h[0] | (h[1] << 16);
+            blk[2 * l + 1] = h[2] | (h[3] << 16);
+          }
+        }
+        bp.blocks.insert(bp.blocks.end(), blk.begin(), blk.end());
+        if (op == BD_END) break;
+      }
+      std::vector<uint32_t> endblk(kBandBlockWords, kBandPadEntry);
+      endblk[kBandStreamChunk] = desc_code(BD_END, 0, 0, 0);
+      for (int k = 0; k < 5; k++) bp.blocks.insert(bp.blocks.end(), endblk.begin(), endblk.end());
+    }
+  }
   for (int k = 0; k < 96; k++) bp.desc.push_back(desc_code(BD_END, 0, 0, 0));  // the kernel's descriptor window reads ahead
-  for (int k = 0; k < 64; k++) bp.entries.push_back(0u);  // a chunk's entry load always reads 32 entries
+  for (int k = 0; k < 128; k++) bp.entries.push_back(stream ? kBandPadEntry : 0u);  // a chunk's entry load always reads a full set
   bp.fp64_instr_per_eval = fp64 + 32.0 * fp64_warp + 60;
   bp.ok = true;
   return bp;

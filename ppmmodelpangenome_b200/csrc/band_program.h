@@ -30,6 +30,8 @@ struct BandProgram {
   bool ok = false;         // false: the tree is not served by the band kernel (why: `why`)
   const char* why = "";
   int R = 4, G = 1, T = 128;
+  bool stream = false;     // stream layout (band_stream.cu): ops in birth order (dst = own index), G = work units per item,
+                           // every chunk owns exactly kBandStreamChunk entries (padded with kBandPadEntry)
   int n_tiles = 0, S_pad = 0;
   int n_int = 0;           // internal non-root nodes
   int n_levels = 0;
@@ -43,6 +45,8 @@ struct BandProgram {
   std::vector<uint32_t> desc;       // the G flat descriptor lists (band_codes.h), each closed by BD_END
   std::vector<int32_t> warp_off;    // [G+1] first descriptor of each warp
   std::vector<int32_t> warp_ent_off;  // [G+1] first entry of each warp; a warp's chunks own consecutive entries, in list order
+  std::vector<uint32_t> blocks;     // stream layout, device form: [block][kBandBlockWords] = a descriptor's entries + its code
+  std::vector<int32_t> unit_blk_off;  // [G] first block of each unit's list
   std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 | leaf << 31 (M records: lanes [lo, hi), hi in 1..32)
   double fp64_instr_per_eval = 0;   // modelled FP64 instructions per pattern-eval (phase A + phase B)
   double cost_max = 0, cost_sum = 0;  // modelled phase B cost of the busiest warp / of all warps (balance = sum / (G max))
@@ -50,6 +54,6 @@ struct BandProgram {
 };
 
 // pg: the handle's sweep program (it fixes the device bit positions of the leaves and the static pairs).
-BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G);
+BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, bool stream = false);
 
 }  // namespace ppm

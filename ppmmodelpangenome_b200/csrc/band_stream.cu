@@ -1,0 +1,430 @@
+// Band kernels, stream layout: the slice-parallel sweep for big trees as THREE kernels per batch of items (sm_100a, FP64
+// CUDA cores).  An item is one (pattern, parameter vector); a batch is a contiguous range of items, 32-item blocks.
+//
+//   band_prune_kernel     LANE = ITEM.  Each thread prunes its item's Mobile category (objects.cpp:427-435, linear domain)
+//                         op by op in birth order -- the op list is topology only, so the warp never diverges and no level
+//                         barrier exists (a 10,000-level caterpillar costs what a balanced tree costs) -- and leaves one
+//                         16-byte record (a, -d e^{lam (h - H/2)}) per internal lineage in a global scratch laid out
+//                         [block][lineage][32 items] (coalesced), plus the running sum of its renormalisation shifts.
+//   band_integral_kernel  LANES = SLICES of the Mobile integral (functions.cpp:245-279).  A warp owns one work unit = one
+//                         item x one of the program's G descriptor lists (whole tiles of 32*R slices, balanced by the
+//                         builder); units are handed out item-major from a global counter, so the lineage records of the
+//                         items in flight stay in L2.  Per chunk of <= 32 records: entries -> cp.async gather (lineage
+//                         records from the scratch, leaf / leaf-pair records from the per-parameter tables by pattern bit)
+//                         into a per-warp ring, BS_D chunks ahead of their use; then one broadcast LDS.128 per record and
+//                         R x (DFMA + DMUL) with R independent dependency chains (leaf pairs: one quadratic in u, 3 FP64 per
+//                         slice for two terms).  No CTA-level synchronisation at all: warps are independent.
+//   band_mixture_kernel   lane = item: sum of the item's G unit integrals in list order (exponent-aligned), 3-way mixture
+//                         (functions.cpp:345-358), x count, fixed-order warp sum -> partial[p][32-pattern block].
+// Results do not depend on the dynamic unit hand-out: every sum runs in a fixed order.
+#include "band_fns.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace ppm {
+
+// Per warp: a ring of BS_NB record slots (BS_CH records x 32 B + 512 B of lane masks / tile tables) and a ring of BS_NB block
+// slots (a descriptor's entries + code, band_codes.h).  Everything the walk needs from global memory arrives by cp.async:
+// iteration di issues the block of descriptor di + 4 and -- from the block that has arrived by then -- the record gather of
+// descriptor di + 2, waits for the group issued two iterations earlier and multiplies in descriptor di.  The software-pipelined
+// FULL loops read one group of records past a slot (BS_PAD).
+enum { BS_CH = kBandStreamChunk, BS_NB = 3, BS_SLOT_BYTES = BS_CH * 32 + 512, BS_BLK_BYTES = kBandBlockWords * 4, BS_PAD = 256,
+       BS_RING_BYTES = BS_NB * BS_SLOT_BYTES + BS_PAD, BS_BRING_BYTES = BS_NB * BS_BLK_BYTES, BS_WARPS = 4, BS_NOP = 15 };
+static_assert(BS_CH == 64 && BS_BLK_BYTES % 16 == 0 && BS_BLK_BYTES / 16 <= 32, "two records per lane and chunk; a block is copied by <= 32 lanes");
+
+static __host__ __device__ inline int bs_pw_words(int n_words) { return (n_words + 1 + 3) & ~3; }
+static __host__ __device__ inline size_t bs_warp_bytes(int n_words) { return (size_t)BS_RING_BYTES + BS_BRING_BYTES + 4 * (size_t)bs_pw_words(n_words); }
+
+__device__ __forceinline__ bool bs_served(const double* sc, int force) {
+  return sc[SC_BAND] != 0. && (force || !(sc[SC_I2] < 0.));  // i2 < 0: penalty branch, no pattern work (functions.cpp:362-364)
+}
+
+// ------------------------------------------------------------------------------------------------ prune (lane = item)
+__global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int blk = blockIdx.x * BS_WARPS + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.counter = 0u;  // the integral kernel of this batch follows on the same stream
+  if (blk >= a.n_blk) return;
+  const long long item = a.item0 + 32ll * blk;
+  const int p = (int)(item / a.count_pad);
+  const long long pat = item - (long long)p * a.count_pad + lane;  // < n_pat_pad: the word rows are zero-padded
+  const double* sc = a.t.scal + (size_t)p * SC_COUNT;
+  if (!bs_served(sc, a.force)) return;
+  const double pi1 = sc[SC_PI1];
+  const double2 leaf0 = make_double2(sc[SC_LA0], sc[SC_LD0]), leaf1 = make_double2(sc[SC_LA1], sc[SC_LD1]);
+  const int n_ops = a.b.n_ops, n_int = a.b.n_int;
+  const BandOpDev* ops = a.b.ops;
+  const double2* bop = reinterpret_cast<const double2*>(a.bt.bop + (size_t)p * n_ops * BOP_DOUBLES);
+  const uint32_t* words = a.m.words + pat;
+  const size_t wstride = (size_t)a.m.n_pat_pad;
+  double2* nodes = a.nodes + (size_t)blk * n_int * 32 + lane;
+  int* xk = a.xk + (size_t)blk * (n_int + 1) * 32 + lane;
+  xk[0] = 0;
+  int run = 0;
+  double2 prev = make_double2(1., 0.);
+  BandOpDev o = ops[0];
+  double2 c01 = bop[0], c23 = bop[1], c45 = bop[2];
+  for (int i = 0; i < n_ops; i++) {
+    const int in = i + 1 < n_ops ? i + 1 : i;  // next op's topology record and branch constants (warp-uniform loads)
+    const BandOpDev on = ops[in];
+    const double2 n01 = bop[3 * in], n23 = bop[3 * in + 1], n45 = bop[3 * in + 2];
+    double2 Lc, Rc;
+    if (o.flags & 1) Lc = ((words[(size_t)(o.lref >> 5) * wstride] >> (o.lref & 31)) & 1u) ? leaf1 : leaf0;
+    else if ((int)o.lref == i - 1) Lc = prev;  // (a caterpillar's chain stays in registers)
+    else Lc = nodes[(size_t)o.lref * 32];
+    if (o.flags & 2) Rc = ((words[(size_t)(o.rref >> 5) * wstride] >> (o.rref & 31)) & 1u) ? leaf1 : leaf0;
+    else if ((int)o.rref == i - 1) Rc = prev;
+    else Rc = nodes[(size_t)o.rref * 32];
+    const double oc[5] = {c01.x, c01.y, c23.x, c23.y, c45.x};
+    int k;
+    prev = band_merge(Lc.x, Lc.y, Rc.x, Rc.y, oc, pi1, k);
+    nodes[(size_t)i * 32] = prev;  // stream layout: op i writes record i (birth order)
+    run += k;
+    xk[(size_t)(i + 1) * 32] = run;
+    o = on; c01 = n01; c23 = n23; c45 = n45;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ integral (lanes = slices)
+__device__ __forceinline__ void bs_cp16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bs_cp8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bs_cp4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// t *= f on the lanes of the mask only (a predicated DMUL: no select instructions)
+__device__ __forceinline__ void bs_pmul(double& t, double f, uint32_t mask, uint32_t lanebit) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 x;\n\tand.b32 x, %2, %3;\n\tsetp.ne.u32 p, x, 0;\n\t@p mul.f64 %0, %0, %1;\n\t}" : "+d"(t) : "d"(f), "r"(mask), "r"(lanebit));
+}
+template <int R>
+__device__ __forceinline__ void bs_rescale(double (&prod)[R], int (&ex)[R]) {
+  int mn = __double2hiint(prod[0]);
+#pragma unroll
+  for (int k = 1; k < R; k++) { const int h = __double2hiint(prod[k]); mn = h < mn ? h : mn; }
+  if (mn < ((1023 - 300) << 20)) {  // rare: some product of this lane has drifted below 2^-300 (or is an exact zero)
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const int be = biased_exp(prod[k]);
+      if (be != 0 && be < 1023 - 300) { prod[k] *= pow2i(300); ex[k] += 300; }
+    }
+  }
+}
+
+// FULL chunks: every record multiplies all R registers of the lane.  Eight records per iteration in two register sets (A, B):
+// set B is loaded while A is multiplied in and vice versa (no register rotation); the reads run one group past the chunk.
+template <int R>
+__device__ __forceinline__ void bs_pairs_full(const double4* rb, int cnt, const double (&U)[R], double (&prod)[R], int (&ex)[R]) {
+  double4 A0 = rb[0], A1 = rb[1], A2 = rb[2], A3 = rb[3];
+#pragma unroll 1
+  for (int i = 0; i < cnt; i += 8) {
+    const double4 B0 = rb[i + 4], B1 = rb[i + 5], B2 = rb[i + 6], B3 = rb[i + 7];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      prod[k] *= fma(fma(A0.z, U[k], A0.y), U[k], A0.x);
+      prod[k] *= fma(fma(A1.z, U[k], A1.y), U[k], A1.x);
+      prod[k] *= fma(fma(A2.z, U[k], A2.y), U[k], A2.x);
+      prod[k] *= fma(fma(A3.z, U[k], A3.y), U[k], A3.x);
+    }
+    A0 = rb[i + 8]; A1 = rb[i + 9]; A2 = rb[i + 10]; A3 = rb[i + 11];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      prod[k] *= fma(fma(B0.z, U[k], B0.y), U[k], B0.x);
+      prod[k] *= fma(fma(B1.z, U[k], B1.y), U[k], B1.x);
+      prod[k] *= fma(fma(B2.z, U[k], B2.y), U[k], B2.x);
+      prod[k] *= fma(fma(B3.z, U[k], B3.y), U[k], B3.x);
+    }
+    if ((i & 8) && i + 8 < cnt) bs_rescale<R>(prod, ex);  // every 16 records (the chunk's end checks too)
+  }
+}
+template <int R>
+__device__ __forceinline__ void bs_recs_full(const double2* rb, int cnt, const double (&Y)[R], double (&prod)[R], int (&ex)[R]) {
+  double2 A0 = rb[0], A1 = rb[1], A2 = rb[2], A3 = rb[3];
+#pragma unroll 1
+  for (int i = 0; i < cnt; i += 8) {
+    const double2 B0 = rb[i + 4], B1 = rb[i + 5], B2 = rb[i + 6], B3 = rb[i + 7];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      prod[k] *= fma(A0.y, Y[k], A0.x);
+      prod[k] *= fma(A1.y, Y[k], A1.x);
+      prod[k] *= fma(A2.y, Y[k], A2.x);
+      prod[k] *= fma(A3.y, Y[k], A3.x);
+    }
+    A0 = rb[i + 8]; A1 = rb[i + 9]; A2 = rb[i + 10]; A3 = rb[i + 11];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      prod[k] *= fma(B0.y, Y[k], B0.x);
+      prod[k] *= fma(B1.y, Y[k], B1.x);
+      prod[k] *= fma(B2.y, Y[k], B2.x);
+      prod[k] *= fma(B3.y, Y[k], B3.x);
+    }
+    if ((i & 8) && i + 8 < cnt) bs_rescale<R>(prod, ex);
+  }
+}
+// per-register chunks: the records multiply one register of the lane; four independent chains
+__device__ __forceinline__ double bs_pairs_one(const double4* rb, int cnt, double u) {
+  double t0 = 1., t1 = 1., t2 = 1., t3 = 1.;
+#pragma unroll 2
+  for (int i = 0; i < cnt; i += 4) {
+    const double4 q0 = rb[i], q1 = rb[i + 1], q2 = rb[i + 2], q3 = rb[i + 3];
+    t0 *= fma(fma(q0.z, u, q0.y), u, q0.x);
+    t1 *= fma(fma(q1.z, u, q1.y), u, q1.x);
+    t2 *= fma(fma(q2.z, u, q2.y), u, q2.x);
+    t3 *= fma(fma(q3.z, u, q3.y), u, q3.x);
+  }
+  return (t0 * t1) * (t2 * t3);
+}
+__device__ __forceinline__ double bs_recs_one(const double2* rb, int cnt, double y) {
+  double t0 = 1., t1 = 1., t2 = 1., t3 = 1.;
+#pragma unroll 2
+  for (int i = 0; i < cnt; i += 4) {
+    const double2 r0 = rb[i], r1 = rb[i + 1], r2 = rb[i + 2], r3 = rb[i + 3];
+    t0 *= fma(r0.y, y, r0.x);
+    t1 *= fma(r1.y, y, r1.x);
+    t2 *= fma(r2.y, y, r2.x);
+    t3 *= fma(r3.y, y, r3.x);
+  }
+  return (t0 * t1) * (t2 * t3);
+}
+__device__ __forceinline__ double bs_recs_masked(const double2* rb, const uint32_t* mb, int cnt, double y, uint32_t lanebit) {
+  double t0 = 1., t1 = 1., t2 = 1., t3 = 1.;
+#pragma unroll 2
+  for (int i = 0; i < cnt; i += 4) {
+    const double2 r0 = rb[i], r1 = rb[i + 1], r2 = rb[i + 2], r3 = rb[i + 3];
+    const uint4 mk = *reinterpret_cast<const uint4*>(mb + i);
+    bs_pmul(t0, fma(r0.y, y, r0.x), mk.x, lanebit);
+    bs_pmul(t1, fma(r1.y, y, r1.x), mk.y, lanebit);
+    bs_pmul(t2, fma(r2.y, y, r2.x), mk.z, lanebit);
+    bs_pmul(t3, fma(r3.y, y, r3.x), mk.w, lanebit);
+  }
+  return (t0 * t1) * (t2 * t3);
+}
+
+template <int R>
+__global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStreamArgs a) {
+  static_assert(R <= 4, "a tile-begin block carries four shift indices per lane");
+  extern __shared__ __align__(16) unsigned char bs_smem[];
+  const ModelDev& m = a.m;
+  const BandDev& b = a.b;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wring = bs_smem + (size_t)warp * bs_warp_bytes(m.n_words);
+  unsigned char* bring = wring + BS_RING_BYTES;
+  uint32_t* pw = reinterpret_cast<uint32_t*>(bring + BS_BRING_BYTES);
+  const uint32_t lanebit = 1u << lane;
+  const int T = 32 * R, G = b.G, n_int = b.n_int;
+  const unsigned total = (unsigned)a.n_blk * 32u * (unsigned)G;
+
+  unsigned u = 0;
+  if (lane == 0) u = atomicAdd(a.counter, 1u);
+  u = __shfl_sync(0xffffffffu, u, 0);
+  while (u < total) {
+    unsigned u_next = 0;
+    if (lane == 0) u_next = atomicAdd(a.counter, 1u);  // its latency hides behind this unit
+    const int il = (int)(u / (unsigned)G), w = (int)(u - (unsigned)il * (unsigned)G);
+    const long long item = a.item0 + il;
+    const int p = (int)(item / a.count_pad);
+    const long long pat = item - (long long)p * a.count_pad;
+    const double* sc = a.t.scal + (size_t)p * SC_COUNT;
+    if (pat < a.count && bs_served(sc, a.force)) {
+      const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
+      const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
+      const double* bY = a.bt.bY + (size_t)p * b.S_pad;
+      const double* bU = a.bt.bU + (size_t)p * b.S_pad;
+      const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
+      const double4* pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
+      __syncwarp();  // (the previous unit's reads of pw are done)
+      for (int x = lane; x < m.n_words; x += 32) pw[x] = m.words[(size_t)x * m.n_pat_pad + pat];
+      if (lane == 0) pw[m.n_words] = 0u;
+
+      const unsigned char* blocks = reinterpret_cast<const unsigned char*>(b.blocks) + (size_t)b.unit_blk_off[w] * BS_BLK_BYTES;
+      double prod[R], Y[R], U[R];
+      int ex[R];
+#pragma unroll
+      for (int k = 0; k < R; k++) { prod[k] = 1.; Y[k] = 0.; U[k] = 0.; ex[k] = 0; }
+      double Im = 0.; int Ie = 0x3fffffff;
+      int tau = 0;
+      uint32_t c0 = BS_NOP, c1 = BS_NOP;  // codes of descriptors di (compute stage) and di + 1
+      int s0 = 0, s2 = 2, s4 = 1;         // ring slots of descriptors di, di + 2 (gather stage), di + 4 (block stage): index mod BS_NB
+      static_assert(BS_NB == 3, "slot arithmetic below");
+      for (int di = -4;; di++) {
+        // the group issued two iterations ago has landed: records of descriptor di, block of descriptor di + 2
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        // ---- block stage: the block of descriptor di + 4
+        if (lane < BS_BLK_BYTES / 16) bs_cp16(bring + s4 * BS_BLK_BYTES + 16 * lane, blocks + (size_t)(di + 4) * BS_BLK_BYTES + 16 * lane);
+        // ---- gather stage: the records of descriptor di + 2 into their slot (records 2 lane and 2 lane + 1)
+        uint32_t c2 = BS_NOP;
+        if (di >= -2) {
+          const uint32_t* blk = reinterpret_cast<const uint32_t*>(bring + s2 * BS_BLK_BYTES);
+          c2 = blk[BS_CH];
+          const uint2 e2 = *reinterpret_cast<const uint2*>(blk + 2 * lane);
+          const uint32_t opG = c2 & 15u;
+          unsigned char* slot = wring + s2 * BS_SLOT_BYTES;
+          if (opG == BD_REC) {
+            const bool masks = ((c2 >> 4) & 3u) == BV_M;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const uint32_t q = h ? e2.y : e2.x;
+              const bool pad = q == kBandPadEntry;
+              const uint32_t ref = pad ? 0u : (q & 0xffffu);
+              const double2* src = nodes + (size_t)ref * 32;
+              if (q >> 31) {
+                const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
+                src = bleaf + ref * 2 + bt1;
+              }
+              double2* dst = reinterpret_cast<double2*>(slot) + 2 * lane + h;
+              if (pad) *dst = make_double2(1., 0.);  // (never from global memory: one hot sector would serialise the whole GPU)
+              else bs_cp16(dst, src);
+              if (masks) {
+                const uint32_t lo = (q >> 16) & 31u, len = ((q >> 21) & 63u) - lo;
+                reinterpret_cast<uint32_t*>(slot + BS_CH * 32)[2 * lane + h] = pad ? 0u : ((len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo);
+              }
+            }
+          } else if (opG == BD_PAIR) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const uint32_t q = h ? e2.y : e2.x;
+              const bool pad = q == kBandPadEntry;
+              const uint32_t ref = pad ? 0u : (q & 0xffffu);
+              const uint32_t bits = (pw[ref >> 4] >> (2u * (ref & 15u))) & 3u;
+              const double2* src = reinterpret_cast<const double2*>(pairq + ref * 4 + bits);
+              double2* dst = reinterpret_cast<double2*>(slot) + 2 * (2 * lane + h);
+              if (pad) { dst[0] = make_double2(1., 0.); dst[1] = make_double2(0., 0.); }
+              else { bs_cp16(dst, src); bs_cp16(dst + 1, src + 1); }
+            }
+          } else if (opG == BD_TILE_BEGIN) {  // the tile's slice tables: Y' | u | exponent prefix, [k][lane] each
+            const int tb = (int)(c2 >> 16) * T + lane;
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+              const uint32_t nb = ((k < 2 ? e2.x : e2.y) >> (16 * (k & 1))) & 0xffffu;
+              bs_cp8(slot + (k * 32 + lane) * 8, bY + tb + 32 * k);
+              bs_cp8(slot + 1024 + (k * 32 + lane) * 8, bU + tb + 32 * k);
+              bs_cp4(slot + 2048 + (k * 32 + lane) * 4, xk + (size_t)nb * 32);
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const uint32_t code = c0;
+        c0 = c1; c1 = c2;
+        const unsigned char* buf = wring + s0 * BS_SLOT_BYTES;
+        s0 = s0 == BS_NB - 1 ? 0 : s0 + 1; s2 = s2 == BS_NB - 1 ? 0 : s2 + 1; s4 = s4 == BS_NB - 1 ? 0 : s4 + 1;
+        // ---- compute stage: descriptor di
+        const int op = code & 15;
+        if (op == BD_END) break;
+        const int var = (code >> 4) & 3, kk = (code >> 6) & 7, cnt = (code >> 9) & 127;
+        if (op == BD_TILE_BEGIN) {
+          tau = (int)(code >> 16);
+#pragma unroll
+          for (int k = 0; k < R; k++) {
+            prod[k] = b.wt[tau * T + 32 * k + lane];  // the slice weights enter the products here (0 for padding slices)
+            Y[k] = *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8);
+            U[k] = *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8);
+            ex[k] = *reinterpret_cast<const int*>(buf + 2048 + (k * 32 + lane) * 4);
+          }
+          continue;
+        }
+        if (op == BD_TILE_END) {
+#pragma unroll
+          for (int k = 0; k < R; k++) scaled_add(Im, Ie, prod[k], ex[k]);
+          continue;
+        }
+        if (op == BD_PAIR) {
+          const double4* rb = reinterpret_cast<const double4*>(buf);
+          if (var == BV_FULL) {
+            bs_pairs_full<R>(rb, cnt, U, prod, ex);
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; k++)
+              if (k == kk) prod[k] *= bs_pairs_one(rb, cnt, U[k]);
+          }
+        } else if (op == BD_REC) {  // 16-byte records (a, nbn), factor a + nbn * Y'
+          const double2* rb = reinterpret_cast<const double2*>(buf);
+          if (var == BV_FULL) {
+            bs_recs_full<R>(rb, cnt, Y, prod, ex);
+          } else if (var == BV_F) {
+#pragma unroll
+            for (int k = 0; k < R; k++)
+              if (k == kk) prod[k] *= bs_recs_one(rb, cnt, Y[k]);
+          } else {
+            const uint32_t* mb = reinterpret_cast<const uint32_t*>(buf + BS_CH * 32);
+#pragma unroll
+            for (int k = 0; k < R; k++)
+              if (k == kk) prod[k] *= bs_recs_masked(rb, mb, cnt, Y[k], lanebit);
+          }
+        } else {
+          continue;  // BS_NOP
+        }
+        bs_rescale<R>(prod, ex);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double vm = __shfl_down_sync(0xffffffffu, Im, o);
+        const int ve = __shfl_down_sync(0xffffffffu, Ie, o);
+        scaled_add(Im, Ie, vm, ve);
+      }
+      if (lane == 0) a.unit_I[(size_t)il * G + w] = make_double2(Im, (double)Ie);
+    }
+    u = __shfl_sync(0xffffffffu, u_next, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ mixture (lane = item)
+__global__ void __launch_bounds__(128) band_mixture_kernel(BandStreamArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int blk = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (blk >= a.n_blk) return;
+  const long long item = a.item0 + 32ll * blk;
+  const int p = (int)(item / a.count_pad);
+  const long long pat0 = item - (long long)p * a.count_pad;
+  const long long pat = pat0 + lane;
+  const double* sc = a.t.scal + (size_t)p * SC_COUNT;
+  double v = 0.;
+  if (pat < a.count && bs_served(sc, a.force)) {
+    const double2* ui = a.unit_I + ((size_t)blk * 32 + lane) * a.b.G;
+    double Im = 0.; int Ie = 0x3fffffff;
+    for (int w = 0; w < a.b.G; w++) { const double2 x = ui[w]; scaled_add(Im, Ie, x.x, (int)x.y); }
+    v = band_mixture(a.m, a.t, p, pat, Im, Ie, nullptr);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) a.partial[(size_t)p * (a.count_pad / 32) + pat0 / 32] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+size_t band_stream_block_bytes(const BandDev& b) {  // scratch per 32-item block
+  return (size_t)b.n_int * 32 * sizeof(double2) + (size_t)(b.n_int + 1) * 32 * sizeof(int) + (size_t)32 * b.G * sizeof(double2);
+}
+
+template <int R>
+static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaFuncSetAttribute(band_integral_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const size_t smem = (size_t)BS_WARPS * bs_warp_bytes(a.m.n_words);
+  int ctas = (int)std::min<size_t>(5, (227 * 1024) / (smem + 1024));
+  if (const char* e = std::getenv("PPM_BAND_CTAS")) { const int v = std::atoi(e); if (v >= 1) ctas = std::min(ctas, v); }
+  const long long units = (long long)a.n_blk * 32 * a.b.G;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)n_sm * ctas, (units + BS_WARPS - 1) / BS_WARPS));
+  band_integral_kernel<R><<<grid, 32 * BS_WARPS, smem, s>>>(a);
+}
+
+void launch_band_stream(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
+  const int cta_blocks = (a.n_blk + BS_WARPS - 1) / BS_WARPS;
+  band_prune_kernel<<<cta_blocks, 32 * BS_WARPS, 0, s>>>(a);
+  switch (a.b.R) {
+    case 2: launch_integral_t<2>(a, n_sm, s); break;
+    default: launch_integral_t<4>(a, n_sm, s); break;
+  }
+  band_mixture_kernel<<<cta_blocks, 128, 0, s>>>(a);
+}
+
+}  // namespace ppm

@@ -95,6 +95,13 @@ struct ppm_engine {
   DevBuf<uint32_t> d_bdesc, d_bentries, d_brounds;
   DevBuf<int> d_bwarp_ent_off;
   DevBuf<double2> d_bleaf;
+  // stream layout (band_stream.cu): per-batch scratch
+  DevBuf<double2> d_bs_nodes, d_bs_unit, d_bs_ident;
+  DevBuf<int> d_bs_xk;
+  DevBuf<unsigned int> d_bs_counter;
+  DevBuf<uint32_t> d_bs_blocks;
+  DevBuf<int> d_bs_unit_off;
+  int bs_blk_cap = 0;             // 32-item blocks the scratch holds
   size_t partial_b_cap = 0;
   int last_sweep_kind = 0;        // 0: lane-per-pattern sweep, 1: band kernel (+ fallback launch), for ppm_get_counters
   int last_sweep_mode = -1;       // SweepPlan::mode of the last lane-per-pattern launch
@@ -182,42 +189,63 @@ struct ppm_engine {
     int min_leaves = 1200;
     if (const char* e = std::getenv("PPM_BAND_MIN")) min_leaves = std::atoi(e);
     if (tree.n_leaves < min_leaves && !forced) return;
-    // Candidates: slices per lane R in {4, 2}, warps per item G in {1, 2, 4, 8, 16}.  The kernel is latency-bound below ~16
-    // resident warps per SM (measured: 1,000 genomes 110 ms at 8 warps, 79 ms at 20), and a CTA's warps own whole tiles, so
-    // the score is (resident warps, capped at 16) x (tile balance over the G warps); ties go to the smaller G, then R = 4.
     const char* eR = std::getenv("PPM_BAND_R");
     const char* eG = std::getenv("PPM_BAND_G");
     const int fixR = eR ? std::atoi(eR) : 0, fixG = eG ? std::atoi(eG) : 0;
-    double best = -1;
-    int ctas_best = 0;
-    bool any = false;
-    for (int R : {4, 2, 8}) {
-      if (fixR ? R != fixR : R != 4) continue;  // R = 4 measured best at 1,000 and 5,000 genomes (R = 2 doubles the chunks, R = 8 turns FULL records into per-register ones)
-      for (int G : {1, 2, 4, 8, 16}) {
-        if (fixG && G != fixG) continue;
-        ppm::BandProgram cand = ppm::build_band_program(tree, prog, R, G);
-        if (!cand.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", cand.why); return; }
-        ppm::BandDev b{}; b.n_int = cand.n_int; b.G = G;
-        const size_t sm = ppm::band_smem_bytes(md, b);
-        if (sm + 1024 > 227 * 1024) continue;
-        const int ctas = (int)std::min<size_t>(std::min<size_t>(32, 64 / G), (227 * 1024) / (sm + 1024));
-        const double balance = cand.cost_sum / (G * std::max(cand.cost_max, 1.0));
-        const double score = std::min(ctas * G, 16) / 16.0 * balance;
-        if (score > best * 1.02) { best = score; band = std::move(cand); ctas_best = ctas; any = true; }
-      }
-    }
-    if (!any) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: node records do not fit shared memory\n"); return; }
-    {
-      // modelled efficiency: phase A (latency-bound, one barrier per level) against phase B, with the resident warps of an SM
-      const int bestG = band.G;
-      const double A = 300.0 * band.n_levels + 60.0 * band.n_int / (32.0 * bestG);
-      const double B = std::max(band.cost_max, 1.0) * 2.0;
-      const double eff = std::min(1.0, (ctas_best * bestG / 4.0) * B / (A + B));
+    const char* eV = std::getenv("PPM_BAND_V");
+    const bool stream_layout = !(eV && std::atoi(eV) == 1);
+    if (stream_layout) {
+      // Stream layout (band_stream.cu): prune (lane = item) -> integral (warp = item x descriptor list) -> mixture.  G = work
+      // units per item.  Units are handed out item-major, so about (resident warps / G) items are in flight; their lineage
+      // records (16 B x internal nodes each) should stay in L2 (a third of it at most), which asks for G >= warps x bytes / 40 MB.
+      const int R = fixR ? fixR : 4;
+      ppm::BandProgram probe = ppm::build_band_program(tree, prog, R, 1, true);
+      if (!probe.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", probe.why); return; }
+      const double item_bytes = 20.0 * probe.n_int;
+      int G = (int)std::ceil(n_sm * 20.0 * item_bytes / 40e6);
+      G = std::max(2, std::min(G, std::max(1, probe.n_tiles / 2)));
+      if (fixG) G = fixG;
+      G = std::max(1, std::min(G, probe.n_tiles));
+      band = G == 1 ? std::move(probe) : ppm::build_band_program(tree, prog, R, G, true);
       if (std::getenv("PPM_PLAN_DEBUG"))
-        fprintf(stderr, "[ppm band] R %d G %d (%d CTAs/SM): %d levels, %d tiles, balance %.3f, modelled efficiency %.2f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
-                band.R, bestG, ctas_best, band.n_levels, band.n_tiles, band.cost_sum / (bestG * std::max(band.cost_max, 1.0)), eff, band.n_full16, band.n_full32,
-                band.n_f16, band.n_f32, band.n_m16);
-      if (eff < 0.7 && !forced) return;
+        fprintf(stderr, "[ppm band] stream layout: R %d, %d units per item, %d tiles, balance %.3f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
+                band.R, band.G, band.n_tiles, band.cost_sum / (band.G * std::max(band.cost_max, 1.0)), band.n_full16, band.n_full32, band.n_f16,
+                band.n_f32, band.n_m16);
+    } else {
+      // Candidates: slices per lane R in {4, 2}, warps per item G in {1, 2, 4, 8, 16}.  The kernel is latency-bound below ~16
+      // resident warps per SM (measured: 1,000 genomes 110 ms at 8 warps, 79 ms at 20), and a CTA's warps own whole tiles, so
+      // the score is (resident warps, capped at 16) x (tile balance over the G warps); ties go to the smaller G, then R = 4.
+      double best = -1;
+      int ctas_best = 0;
+      bool any = false;
+      for (int R : {4, 2, 8}) {
+        if (fixR ? R != fixR : R != 4) continue;  // R = 4 measured best at 1,000 and 5,000 genomes (R = 2 doubles the chunks, R = 8 turns FULL records into per-register ones)
+        for (int G : {1, 2, 4, 8, 16}) {
+          if (fixG && G != fixG) continue;
+          ppm::BandProgram cand = ppm::build_band_program(tree, prog, R, G);
+          if (!cand.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", cand.why); return; }
+          ppm::BandDev b{}; b.n_int = cand.n_int; b.G = G;
+          const size_t sm = ppm::band_smem_bytes(md, b);
+          if (sm + 1024 > 227 * 1024) continue;
+          const int ctas = (int)std::min<size_t>(std::min<size_t>(32, 64 / G), (227 * 1024) / (sm + 1024));
+          const double balance = cand.cost_sum / (G * std::max(cand.cost_max, 1.0));
+          const double score = std::min(ctas * G, 16) / 16.0 * balance;
+          if (score > best * 1.02) { best = score; band = std::move(cand); ctas_best = ctas; any = true; }
+        }
+      }
+      if (!any) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: node records do not fit shared memory\n"); return; }
+      {
+        // modelled efficiency: phase A (latency-bound, one barrier per level) against phase B, with the resident warps of an SM
+        const int bestG = band.G;
+        const double A = 300.0 * band.n_levels + 60.0 * band.n_int / (32.0 * bestG);
+        const double B = std::max(band.cost_max, 1.0) * 2.0;
+        const double eff = std::min(1.0, (ctas_best * bestG / 4.0) * B / (A + B));
+        if (std::getenv("PPM_PLAN_DEBUG"))
+          fprintf(stderr, "[ppm band] R %d G %d (%d CTAs/SM): %d levels, %d tiles, balance %.3f, modelled efficiency %.2f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
+                  band.R, bestG, ctas_best, band.n_levels, band.n_tiles, band.cost_sum / (bestG * std::max(band.cost_max, 1.0)), eff, band.n_full16, band.n_full32,
+                  band.n_f16, band.n_f32, band.n_m16);
+        if (eff < 0.7 && !forced) return;
+      }
     }
     static_assert(sizeof(ppm::BandOpDev) == sizeof(ppm::BandOp), "band layouts");
     std::vector<ppm::BandOpDev> ops(band.ops.size());
@@ -228,12 +256,20 @@ struct ppm_engine {
     d_bdesc.upload(band.desc, stream);
     d_bentries.upload(band.entries, stream);
     d_brounds.upload(band.rounds, stream); d_bwarp_ent_off.upload(band.warp_ent_off, stream);
+    const std::vector<double2> ident{make_double2(1., 0.), make_double2(0., 0.)};
+    if (band.stream) {
+      d_bs_ident.upload(ident, stream);
+      d_bs_counter.alloc(1);
+      d_bs_blocks.upload(band.blocks, stream);
+      d_bs_unit_off.upload(band.unit_blk_off, stream);
+    }
     CK(cudaStreamSynchronize(stream));
     bdev.R = band.R; bdev.G = band.G; bdev.T = band.T; bdev.n_tiles = band.n_tiles; bdev.S_pad = band.S_pad; bdev.n_int = band.n_int;
     bdev.n_ops = (int)band.ops.size(); bdev.n_levels = band.n_levels; bdev.n_desc = (int)band.desc.size(); bdev.n_entries = (int)band.entries.size();
     bdev.ops = d_bops.p; bdev.op_nodes = d_bop_nodes.p; bdev.lev_off = d_blev_off.p; bdev.nborn = d_bnborn.p; bdev.wt = d_bwt.p;
     bdev.slice_t = d_bslice_t.p; bdev.desc = d_bdesc.p; bdev.warp_off = d_bwarp_off.p; bdev.entries = d_bentries.p;
     bdev.rounds = d_brounds.p; bdev.n_rounds = band.n_rounds; bdev.warp_ent_off = d_bwarp_ent_off.p;
+    bdev.blocks = d_bs_blocks.p; bdev.unit_blk_off = d_bs_unit_off.p;
     use_band = true;
   }
   ppm::BandTables band_tables() const {
@@ -400,15 +436,47 @@ struct ppm_engine {
       // band kernel for every parameter vector it can serve (SC_BAND), then the lane-per-pattern sweep for the others
       if (class_pending) { CK(cudaStreamWaitEvent(s, ev_class, 0)); class_pending = false; }
       else { ppm::launch_class_sums(md, t, 0, count, s); n_launches += 1; }
-      ppm::BandArgs ba{};
-      ba.m = md; ba.t = t; ba.b = bdev; ba.bt = band_tables(); ba.count = count; ba.force = 0;
-      const ppm::BandPlan bpl = ppm::plan_band(md, bdev, count, t.P, n_sm);
-      const size_t needb = (size_t)t.P * bpl.n_chunks;
-      if (needb > partial_b_cap) { d_partial_b.alloc(needb); partial_b_cap = needb; }
-      ba.partial = d_partial_b.p;
-      CK(cudaEventRecord(ev0, s));
-      ppm::launch_band(ba, bpl, s);
-      n_launches += 1;
+      int n_band_partials = 0;
+      if (band.stream) {
+        // batches of 32-item blocks through one scratch: prune -> integral -> mixture, back to back on the stream
+        const long long n_blk_total = (long long)t.P * (n_pat_pad / 32);
+        size_t budget = (size_t)2048 << 20;
+        if (const char* e = std::getenv("PPM_BAND_SCRATCH_MB")) budget = (size_t)std::max(1, std::atoi(e)) << 20;
+        const size_t per_blk = ppm::band_stream_block_bytes(bdev);
+        const int blk_batch = (int)std::max<long long>(1, std::min<long long>(n_blk_total, (long long)(budget / per_blk)));
+        if (blk_batch > bs_blk_cap) {
+          d_bs_nodes.alloc((size_t)blk_batch * bdev.n_int * 32);
+          d_bs_xk.alloc((size_t)blk_batch * (bdev.n_int + 1) * 32);
+          d_bs_unit.alloc((size_t)blk_batch * 32 * bdev.G);
+          bs_blk_cap = blk_batch;
+        }
+        n_band_partials = (int)(n_pat_pad / 32);
+        const size_t needb = (size_t)t.P * n_band_partials;
+        if (needb > partial_b_cap) { d_partial_b.alloc(needb); partial_b_cap = needb; }
+        ppm::BandStreamArgs sa{};
+        sa.m = md; sa.t = t; sa.b = bdev; sa.bt = band_tables(); sa.count = count; sa.count_pad = n_pat_pad; sa.force = 0;
+        sa.nodes = d_bs_nodes.p; sa.xk = d_bs_xk.p; sa.unit_I = d_bs_unit.p; sa.counter = d_bs_counter.p; sa.ident = d_bs_ident.p;
+        sa.partial = d_partial_b.p;
+        if (const char* e = std::getenv("PPM_BAND_DBG")) sa.dbg = std::atoi(e);
+        CK(cudaEventRecord(ev0, s));
+        for (long long b0 = 0; b0 < n_blk_total; b0 += blk_batch) {
+          sa.item0 = 32 * b0;
+          sa.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b0);
+          ppm::launch_band_stream(sa, n_sm, s);
+          n_launches += 3;
+        }
+      } else {
+        ppm::BandArgs ba{};
+        ba.m = md; ba.t = t; ba.b = bdev; ba.bt = band_tables(); ba.count = count; ba.force = 0;
+        const ppm::BandPlan bpl = ppm::plan_band(md, bdev, count, t.P, n_sm);
+        n_band_partials = bpl.n_chunks;
+        const size_t needb = (size_t)t.P * bpl.n_chunks;
+        if (needb > partial_b_cap) { d_partial_b.alloc(needb); partial_b_cap = needb; }
+        ba.partial = d_partial_b.p;
+        CK(cudaEventRecord(ev0, s));
+        ppm::launch_band(ba, bpl, s);
+        n_launches += 1;
+      }
       if (!hint_all_band) {
         ppm::SweepPlan pl = ppm::plan_sweep(md, a.n_batches, t.P, n_sm, false);
         d_gslots.alloc(ppm::sweep_scratch_elems(md, pl)); a.gslots = d_gslots.p;
@@ -419,7 +487,7 @@ struct ppm_engine {
       }
       CK(cudaEventRecord(ev1, s));
       timed = true;
-      ppm::launch_reduce2(d_partial.p, (int)a.n_batches, d_partial_b.p, bpl.n_chunks, d_scal.p, t.P, d_out, s);
+      ppm::launch_reduce2(d_partial.p, (int)a.n_batches, d_partial_b.p, n_band_partials, d_scal.p, t.P, d_out, s);
       n_launches += 1;
       CK(cudaGetLastError());
       return;
@@ -930,6 +998,7 @@ int ppm_get_plan(ppm_handle h, int32_t* out16) {
   out16[7] = h->md.lean ? 1 : 0;
   out16[8] = h->use_band ? h->band.n_levels : (int32_t)h->tree.lev_up_off.size() - 1;
   out16[9] = h->use_band ? h->band.n_tiles : 0;
+  out16[13] = (h->use_band && h->band.stream) ? 1 : 0;
   out16[10] = h->prog.n_blocks;
   out16[11] = h->prog.n_slots;
   out16[12] = h->prog.leaf_u ? 1 : 0;

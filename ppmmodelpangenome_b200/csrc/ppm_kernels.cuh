@@ -119,6 +119,7 @@ struct BandDev {
   const BandOpDev* ops; const int* op_nodes; const int* lev_off; const uint32_t* rounds;
   const uint16_t* nborn; const double* wt; const double* slice_t;
   const uint32_t* desc; const int* warp_off; const int* warp_ent_off; const uint32_t* entries;
+  const uint32_t* blocks; const int* unit_blk_off;  // stream layout: descriptor blocks (band_program.h)
 };
 struct BandTables {     // one row per parameter vector, written by prepass_band
   double* bop;          // [P][n_ops][BOP_DOUBLES]
@@ -135,6 +136,21 @@ struct BandArgs {
   int force;
 };
 struct BandPlan { int grid_x, G, n_chunks; long long chunk; size_t smem_bytes; int ctas_per_sm; };
+// stream layout (band_stream.cu): one batch = n_blk blocks of 32 consecutive items, item = p * count_pad + pattern
+struct BandStreamArgs {
+  ModelDev m; TablesDev t; BandDev b; BandTables bt;
+  long long count, count_pad;  // patterns of this shard; padded to a multiple of 32 (== ModelDev::n_pat_pad)
+  long long item0;             // first item of the batch (a multiple of 32)
+  int n_blk;
+  double2* nodes;              // scratch [n_blk][n_int][32]  lineage records (a, -d e^{lam (h - H/2)})
+  int* xk;                     // scratch [n_blk][n_int + 1][32]  running sums of the renormalisation shifts, birth order
+  double2* unit_I;             // scratch [n_blk * 32][G]  (mantissa, exponent) of every unit's share of the Mobile integral
+  unsigned int* counter;       // unit hand-out
+  const double2* ident;        // 32 bytes (1, 0, 0, 0): the record of a padding entry
+  double* partial;             // [P][count_pad / 32]
+  int force;
+  int dbg;                     // experiments (PPM_BAND_DBG): 1 = every gather reads the identity record (timing only)
+};
 
 struct SweepArgs {
   ModelDev m;
@@ -179,6 +195,8 @@ void launch_prepass_band(const ModelDev& m, const TablesDev& t, const BandDev& b
 BandPlan plan_band(const ModelDev& m, const BandDev& b, long long count, int P, int n_sm);
 size_t band_smem_bytes(const ModelDev& m, const BandDev& b);
 void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
+size_t band_stream_block_bytes(const BandDev& b);  // scratch per 32-item block
+void launch_band_stream(const BandStreamArgs& a, int n_sm, cudaStream_t s);  // prune + integral + mixture of one batch
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
 void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s);  // [n][P] -> [P], rank order
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]

@@ -60,7 +60,7 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
     size_t eoff = bp.warp_ent_off[w];
     for (int di = bp.warp_off[w];; di++) {
       const uint32_t code = bp.desc[di];
-      const int op = code & 15, var = (code >> 4) & 3, k = (code >> 6) & 7, cnt = (code >> 9) & 63;
+      const int op = code & 15, var = (code >> 4) & 3, k = (code >> 6) & 7, cnt = (code >> 9) & 127;
       if (op == BD_END) break;
       if (op == BD_TILE_BEGIN) {
         tau = (int)(code >> 16);
@@ -82,6 +82,7 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
       }
       for (int e = 0; e < cnt; e++) {
         const uint32_t ent = bp.entries[eoff + e];
+        if (bp.stream && ent == kBandPadEntry) continue;
         const int ref = ent & 0xffff, lo = (ent >> 16) & 31, hi = (ent >> 21) & 63;
         double4 q = make_double4(1., 0., 0., 0.);
         double2 r = make_double2(1., 0.);
@@ -93,7 +94,7 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
             prod[x] *= (op == BD_PAIR) ? fma(fma(q.z, U[x], q.y), U[x], q.x) : fma(r.y, Y[x], r.x);
           }
       }
-      eoff += cnt;
+      eoff += bp.stream ? kBandStreamChunk : cnt;
       for (int x = 0; x < 32 * R; x++) {
         const int be = biased_exp(prod[x]);
         if (be != 0 && be < 1023 - 400) { prod[x] *= pow2i(400); ex[x] += 400; }
@@ -113,14 +114,16 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     Tree tree = read_tree_file(tree_path);
     Patterns pat = read_matrix_file(tree, pa_path, dedupe != 0);
     // R >= 1000: the band program (slice-parallel sweep), R = 1000 + 100 * G + slices-per-lane
-    const int band_code = R >= 1000 ? R - 1000 : 0;
+    // R >= 3000: the same with the stream layout (band_stream.cu), G = work units per item
+    const bool band_stream = R >= 3000;
+    const int band_code = R >= 3000 ? R - 3000 : R >= 1000 ? R - 1000 : 0;
     if (band_code) R = 8;
     const bool deep = R < 0;
     if (deep) R = -R;
     Program prog = build_program(tree, R, deep);
     BandProgram bp;
     if (band_code) {
-      bp = build_band_program(tree, prog, band_code % 100, band_code / 100);
+      bp = build_band_program(tree, prog, band_code % 100, band_code / 100, band_stream);
       if (!bp.ok) throw std::runtime_error(std::string("band program: ") + bp.why);
     }
     const long long count = pat.n_patterns;

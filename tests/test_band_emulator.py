@@ -37,7 +37,8 @@ def emu():
 
 
 @pytest.mark.parametrize("name", ["syn12", "syn100", "cat40", "syn300"])
-@pytest.mark.parametrize("code", [1104, 1102, 1108, 1204, 1404, 1802, 2604])  # 1000 + 100 * (warps per item) + (slices per lane)
+# 1000 + 100 * (warps per item) + (slices per lane); 3000 + ...: stream layout (band_stream.cu), work units per item
+@pytest.mark.parametrize("code", [1104, 1102, 1108, 1204, 1404, 1802, 2604, 3104, 3204, 3302, 3404])
 def test_band_program_reproduces_reference_golden(golden, emu, name, code):
     g = golden(name)
     ll, i2, comp = emu(g.tree, g.pa, False, g.params, code, n_rows=g.meta["nRep"])
@@ -68,7 +69,7 @@ def test_band_program_against_oracle_600_genomes(emu, tmp_path):
     simulate.write_matrix(pp, names, M)
     orc = cport.Oracle(model.model_from_files(tp, pp))
     P = np.stack([simulate.start_params(truth, 24), simulate.start_params(truth, 24, rng)])
-    for code in (1104, 1404):
+    for code in (1104, 1404, 3304):
         ll, i2, _ = emu(tp, pp, True, P, code)
         for k in range(2):
             o = orc.eval(P[k], cats=False)

@@ -40,13 +40,16 @@ class _Env:
 
 
 @pytest.mark.parametrize("name", ["syn100", "syn300", "cat40"])
-@pytest.mark.parametrize("R,G", [(4, 1), (2, 1), (8, 1), (4, 2), (4, 4), (2, 8), (4, 16)])
-def test_band_kernel_against_reference_golden(ppm, golden, name, R, G):
+@pytest.mark.parametrize("V,R,G", [(2, 4, 1), (2, 2, 1), (2, 4, 2), (2, 2, 5), (2, 4, 3),
+                                   (1, 4, 1), (1, 2, 1), (1, 8, 1), (1, 4, 2), (1, 4, 4), (1, 2, 8), (1, 4, 16)])
+def test_band_kernel_against_reference_golden(ppm, golden, name, V, R, G):
+    """V = 2: stream layout (prune / integral / mixture kernels, G work units per item); V = 1: one CTA of G warps per item."""
     g = golden(name)
-    with _Env(PPM_FORCE_BAND=1, PPM_BAND_R=R, PPM_BAND_G=G):
+    with _Env(PPM_FORCE_BAND=1, PPM_BAND_R=R, PPM_BAND_G=G, PPM_BAND_V=V):
         inf = ppm.Inference(g.tree, g.pa, dedupe=True, device=0)
     pl = inf.plan()
-    assert pl["band"] == 1 and pl["band_R"] == R and pl["band_G"] == G
+    assert pl["band"] == 1 and pl["band_R"] == R and pl["band_stream"] == (V == 2)
+    assert pl["band_G"] == (min(G, pl["band_tiles"]) if V == 2 else G)
     ll, i2 = inf.loglik_batch(g.params, return_i2=True)
     assert inf.plan()["last_kind"] == 1
     for k, r in enumerate(g.results):
@@ -143,3 +146,18 @@ def test_band_kernel_penalty_and_zero_error_rates(ppm, tmp_path):
         if np.isfinite(o["ll"]):
             assert rel(ll[k], o["ll"]) <= RTOL, (k, ll[k], o["ll"])
     inf.close()
+
+
+def test_band_stream_batches_are_invisible(ppm, tmp_path):
+    """Stream layout: the scratch budget only sets how many items one prune/integral/mixture round serves; results are
+    bitwise the same with one batch and with many (PPM_BAND_SCRATCH_MB=1: a few 32-item blocks per batch)."""
+    tp, pp, P, truth = _seeded(ppm, tmp_path, 1300, 150, 11)
+    one = ppm.Inference(tp, pp, dedupe=True, device=0)
+    assert one.plan()["band"] == 1 and one.plan()["band_stream"] == 1
+    ll = one.loglik_batch(P)
+    n1 = one.counters()["launches"]
+    with _Env(PPM_BAND_SCRATCH_MB=1):
+        many = one.loglik_batch(P)
+        assert one.counters()["launches"] > n1
+    assert np.array_equal(ll, many)
+    one.close()
