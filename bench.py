@@ -245,6 +245,9 @@ class Dist:
 
 def kernel_name(inf):
     pl = inf.plan()
+    if pl["last_kind"] == 1 and pl.get("band_stream"):
+        # kernel_ms covers the whole band sequence of a step: per batch prune -> integral -> mixture (the integral is ~98 % of it)
+        return "ppm::band_integral_kernel<%d> (+ ppm::band_prune_kernel, ppm::band_mixture_kernel per batch)" % pl["band_R"], pl
     if pl["last_kind"] == 1:
         return "ppm::band_kernel<%d,%s>" % (pl["band_R"], "true" if pl["band_G"] > 1 else "false"), pl
     mode = pl["last_mode"]

@@ -1,6 +1,7 @@
 // Engine object behind the C ABI of include/ppm_b200.h: owns the device copy of the model, the per-launch
 // parameter tables, a stream and timing events.  No CPU fallback: every compute entry point needs an sm_100 GPU.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges are no-ops unless a profiler injects the NVTX library
 
 #include <algorithm>
 #include <cmath>
@@ -44,6 +45,12 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
+};
+
+// NVTX range for a scope (shows up in Nsight Systems / ncu --nvtx: "ppm:prepass", "ppm:sweep", ...)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
 };
 
 }  // namespace
@@ -169,6 +176,7 @@ struct ppm_engine {
   }
 
   void upload_model() {
+    NvtxRange r("ppm:upload_model");
     upload_model_impl(false);
     const bool staged = ppm::sweep_is_staged(md);
     if (!staged) upload_model_impl(true);
@@ -402,6 +410,7 @@ struct ppm_engine {
   // prepass + zero row + i2 (functions.cpp:334-344).  After this, scal[p] is complete.
   // with_class_sums: a sweep follows; its class sums (which need the node prepass only) run on the side stream meanwhile
   void run_prepass(const ppm::TablesDev& t, const double* d_i2_ovr, cudaStream_t s, bool with_class_sums = false) {
+    NvtxRange r("ppm:prepass");
     ppm::launch_prepass_nodes(md, t, s);
     if (with_class_sums && count > 0) {
       CK(cudaEventRecord(ev_nodes, s));
@@ -421,6 +430,7 @@ struct ppm_engine {
   // mode 0: partial sums into d_out[P]; mode 2: categories/components for P == 1
   void run_sweep(const ppm::TablesDev& t, int mode, double* d_out, signed char* d_cat_out, double* d_comp_out, cudaStream_t s,
                  double* d_dist_out = nullptr) {
+    NvtxRange r(use_band && mode == 0 && d_dist_out == nullptr ? "ppm:sweep(band)" : "ppm:sweep");
     ppm::SweepArgs a{};
     a.dist = d_dist_out;
     a.m = md; a.t = t; a.mode = mode; a.first = 0; a.count = count;
@@ -785,6 +795,7 @@ static int group_loglik(ppm_handle h, const double* params, int32_t P, double* o
 
 int ppm_loglik(ppm_handle h, const double* params, int32_t P, double* out_ll, double* out_i2) {
   if (!h || !params || !out_ll || P < 1) { if (h) h->err = "bad argument"; return PPM_EINVAL; }
+  NvtxRange r("ppm_loglik");
   if (h->is_group()) return group_loglik(h, params, P, out_ll, out_i2);
   GUARD_BEGIN
   CK(cudaSetDevice(h->device));
