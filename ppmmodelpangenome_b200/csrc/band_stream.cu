@@ -37,60 +37,146 @@ static_assert(BS_CH == 64 && BS_BLK_BYTES % 16 == 0 && BS_BLK_BYTES / 16 <= 32, 
 static __host__ __device__ inline int bs_pw_words(int n_words) { return (n_words + 1 + 3) & ~3; }
 static __host__ __device__ inline size_t bs_warp_bytes(int n_words) { return (size_t)BS_RING_BYTES + BS_BRING_BYTES + 4 * (size_t)bs_pw_words(n_words); }
 
+__device__ __forceinline__ void bs_cp16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
 __device__ __forceinline__ bool bs_served(const double* sc, int force) {
   return sc[SC_BAND] != 0. && (force || !(sc[SC_I2] < 0.));  // i2 < 0: penalty branch, no pattern work (functions.cpp:362-364)
 }
 
 // ------------------------------------------------------------------------------------------------ prune (lane = item)
+// One thread walks its item's ops in birth order.  The walk is a chain of global loads (a child's record, a leaf's pattern
+// word) in front of ~60 cycles of FP64 each, so it is software-pipelined: the operands of op i + BP_PF are requested while op i is
+// computed -- pattern words always, a child's record when it was written at least BP_PF ops ago; younger children are
+// forwarded from registers (a caterpillar's chain never touches memory).
+// loads whose destination registers are the pipeline slot itself (plain C++ loads went through a temporary quad and were
+// copied out at once -- a copy that waits for the load)
+__device__ __forceinline__ void bp_ldg(double2& d, const double2* p) {
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(d.x), "=d"(d.y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void bp_ldg(uint32_t& d, const uint32_t* p) {
+  asm volatile("ld.global.u32 %0, [%1];" : "=r"(d) : "l"(p) : "memory");
+}
+enum { BP_PF = 3, BP_OC = 2049 };  // request distance; op records staged per CTA in chunks of BP_OC (+ 8 of lookahead)
+static_assert(BP_OC % BP_PF == 0, "slots keep their phase across chunks");
 __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArgs a) {
+  __shared__ uint2 ops_s[BP_OC + 8];  // op records as raw words: lref | rref << 16, dst | flags << 16
+  // branch constants of the warp's parameter vector, 32 ops at a time, double-buffered by cp.async (3 x 16 bytes per op)
+  __shared__ __align__(16) double2 cst_s[BS_WARPS][2][32 * 3];
   const int lane = threadIdx.x & 31;
   const int blk = blockIdx.x * BS_WARPS + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.counter = 0u;  // the integral kernel of this batch follows on the same stream
-  if (blk >= a.n_blk) return;
-  const long long item = a.item0 + 32ll * blk;
+  const long long item = a.item0 + 32ll * (blk < a.n_blk ? blk : 0);
   const int p = (int)(item / a.count_pad);
   const long long pat = item - (long long)p * a.count_pad + lane;  // < n_pat_pad: the word rows are zero-padded
   const double* sc = a.t.scal + (size_t)p * SC_COUNT;
-  if (!bs_served(sc, a.force)) return;
+  const bool active = blk < a.n_blk && bs_served(sc, a.force);  // (idle warps still stage op records and meet the barriers)
   const double pi1 = sc[SC_PI1];
   const double2 leaf0 = make_double2(sc[SC_LA0], sc[SC_LD0]), leaf1 = make_double2(sc[SC_LA1], sc[SC_LD1]);
-  const int n_ops = a.b.n_ops, n_int = a.b.n_int;
-  const BandOpDev* ops = a.b.ops;
+  const int n_ops = a.b.n_ops, n_int = a.b.n_int, last = n_ops - 1;
+  const uint2* ops2 = reinterpret_cast<const uint2*>(a.b.ops);
   const double2* bop = reinterpret_cast<const double2*>(a.bt.bop + (size_t)p * n_ops * BOP_DOUBLES);
   const uint32_t* words = a.m.words + pat;
   const size_t wstride = (size_t)a.m.n_pat_pad;
-  double2* nodes = a.nodes + (size_t)blk * n_int * 32 + lane;
-  int* xk = a.xk + (size_t)blk * (n_int + 1) * 32 + lane;
-  xk[0] = 0;
+  double2* nodes = a.nodes + (size_t)(active ? blk : 0) * n_int * 32 + lane;
+  int* xk = a.xk + (size_t)(active ? blk : 0) * (n_int + 1) * 32 + lane;
+  if (active) xk[0] = 0;
   int run = 0;
-  double2 prev = make_double2(1., 0.);
-  BandOpDev o = ops[0];
-  double2 c01 = bop[0], c23 = bop[1], c45 = bop[2];
-  for (int i = 0; i < n_ops; i++) {
-    const int in = i + 1 < n_ops ? i + 1 : i;  // next op's topology record and branch constants (warp-uniform loads)
-    const BandOpDev on = ops[in];
-    const double2 n01 = bop[3 * in], n23 = bop[3 * in + 1], n45 = bop[3 * in + 2];
-    double2 Lc, Rc;
-    if (o.flags & 1) Lc = ((words[(size_t)(o.lref >> 5) * wstride] >> (o.lref & 31)) & 1u) ? leaf1 : leaf0;
-    else if ((int)o.lref == i - 1) Lc = prev;  // (a caterpillar's chain stays in registers)
-    else Lc = nodes[(size_t)o.lref * 32];
-    if (o.flags & 2) Rc = ((words[(size_t)(o.rref >> 5) * wstride] >> (o.rref & 31)) & 1u) ? leaf1 : leaf0;
-    else if ((int)o.rref == i - 1) Rc = prev;
-    else Rc = nodes[(size_t)o.rref * 32];
-    const double oc[5] = {c01.x, c01.y, c23.x, c23.y, c45.x};
-    int k;
-    prev = band_merge(Lc.x, Lc.y, Rc.x, Rc.y, oc, pi1, k);
-    nodes[(size_t)i * 32] = prev;  // stream layout: op i writes record i (birth order)
-    run += k;
-    xk[(size_t)(i + 1) * 32] = run;
-    o = on; c01 = n01; c23 = n23; c45 = n45;
+
+  // circular buffer of BP_PF slots with compile-time indices (the loop body is unrolled BP_PF times): slot s holds the
+  // requested operands of op j (j % BP_PF == s); once op j has read them the slot is refilled for op j + BP_PF.  Nothing that
+  // is still in flight is ever moved between registers.
+  uint2 so[BP_PF];                     // op record of the slot's op
+  uint32_t wl[BP_PF], wr[BP_PF];       // requested operands: pattern word of a leaf child ...
+  double2 nl[BP_PF], nr[BP_PF];        // ... or the record of an internal child written at least BP_PF ops before the slot's op
+  double2 prev[BP_PF];                 // prev[k] = record of op j - 1 - k (register forwarding of the youngest records)
+#pragma unroll
+  for (int k = 0; k < BP_PF; k++) {
+    prev[k] = make_double2(1., 0.);
+    so[k] = make_uint2(0u, 0u);
+    wl[k] = 0u; wr[k] = 0u; nl[k] = make_double2(1., 0.); nr[k] = make_double2(1., 0.);
+  }
+  auto request = [&](int j, const uint2 oj, uint32_t& w_l, uint32_t& w_r, double2& n_l, double2& n_r) {
+    const int lref = (int)(oj.x & 0xffffu), rref = (int)(oj.x >> 16), flags = (int)(oj.y >> 16);
+    if (flags & 1) bp_ldg(w_l, words + (size_t)(lref >> 5) * wstride);
+    else if (lref < j - BP_PF) bp_ldg(n_l, nodes + (size_t)lref * 32);
+    if (flags & 2) bp_ldg(w_r, words + (size_t)(rref >> 5) * wstride);
+    else if (rref < j - BP_PF) bp_ldg(n_r, nodes + (size_t)rref * 32);
+  };
+  double2* cst = &cst_s[threadIdx.x >> 5][0][0];
+  auto stage_consts = [&](int chunk) {  // ops [32 chunk, 32 chunk + 32) of this warp's parameter vector -> buffer chunk & 1
+    const int j = 32 * chunk + lane;
+    if (j < n_ops) {
+      double2* dst = cst + (chunk & 1) * 96 + 3 * lane;
+      const double2* src = bop + 3 * (size_t)j;
+      bs_cp16(dst, src); bs_cp16(dst + 1, src + 1); bs_cp16(dst + 2, src + 2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (active) stage_consts(0);
+  for (int c0 = 0; c0 < n_ops; c0 += BP_OC) {
+    __syncthreads();
+    for (int x = threadIdx.x; x < BP_OC + 8; x += blockDim.x) ops_s[x] = ops2[c0 + x < last ? c0 + x : last];
+    __syncthreads();
+    if (!active) continue;
+    if (c0 == 0) {
+#pragma unroll
+      for (int k = 0; k < BP_PF; k++) {
+        const int j = k < last ? k : last;
+        so[k] = ops_s[j];
+        request(k, so[k], wl[k], wr[k], nl[k], nr[k]);
+      }
+    }
+    const int c1 = c0 + BP_OC < n_ops ? c0 + BP_OC : n_ops;  // (BP_OC is a multiple of BP_PF: slots keep their phase)
+    for (int i = c0; i < c1; i += BP_PF) {
+#pragma unroll
+      for (int sl = 0; sl < BP_PF; sl++) {
+        const int j = i + sl;
+        if (j < c1) {
+          if ((j & 31) == 0) {  // this chunk's constants have landed; the next chunk's are requested
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            stage_consts((j >> 5) + 1);
+          }
+          const double2* cj = cst + ((j >> 5) & 1) * 96 + 3 * (j & 31);
+          const double2 k01 = cj[0], k23 = cj[1], k4 = cj[2];
+          // operands of op j out of the slot
+          const int lref = (int)(so[sl].x & 0xffffu), rref = (int)(so[sl].x >> 16), flags = (int)(so[sl].y >> 16);
+          double2 Lc, Rc;
+          if (flags & 1) Lc = ((wl[sl] >> (lref & 31)) & 1u) ? leaf1 : leaf0;
+          else {
+            Lc = nl[sl];
+#pragma unroll
+            for (int k = 0; k < BP_PF; k++) if (lref == j - 1 - k) Lc = prev[k];
+          }
+          if (flags & 2) Rc = ((wr[sl] >> (rref & 31)) & 1u) ? leaf1 : leaf0;
+          else {
+            Rc = nr[sl];
+#pragma unroll
+            for (int k = 0; k < BP_PF; k++) if (rref == j - 1 - k) Rc = prev[k];
+          }
+          const double occ[5] = {k01.x, k01.y, k23.x, k23.y, k4.x};
+          // refill the slot for op j + BP_PF (records up to j - 1 are written; the request takes those up to j - 1 only)
+          {
+            so[sl] = ops_s[j + BP_PF - c0];  // (clamped to the last op when staged)
+            request(j + BP_PF, so[sl], wl[sl], wr[sl], nl[sl], nr[sl]);
+          }
+          int k;
+          const double2 rec = band_merge(Lc.x, Lc.y, Rc.x, Rc.y, occ, pi1, k);
+          nodes[(size_t)j * 32] = rec;  // stream layout: op j writes record j (birth order)
+          run += k;
+          xk[(size_t)(j + 1) * 32] = run;
+#pragma unroll
+          for (int q = BP_PF - 1; q > 0; q--) prev[q] = prev[q - 1];
+          prev[0] = rec;
+        }
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ integral (lanes = slices)
-__device__ __forceinline__ void bs_cp16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void bs_cp8(void* dst_smem, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
@@ -417,14 +503,15 @@ static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s)
   band_integral_kernel<R><<<grid, 32 * BS_WARPS, smem, s>>>(a);
 }
 
-void launch_band_stream(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
-  const int cta_blocks = (a.n_blk + BS_WARPS - 1) / BS_WARPS;
-  band_prune_kernel<<<cta_blocks, 32 * BS_WARPS, 0, s>>>(a);
+void launch_band_prune(const BandStreamArgs& a, cudaStream_t s) {
+  band_prune_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 32 * BS_WARPS, 0, s>>>(a);
+}
+void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s) {  // + mixture
   switch (a.b.R) {
     case 2: launch_integral_t<2>(a, n_sm, s); break;
     default: launch_integral_t<4>(a, n_sm, s); break;
   }
-  band_mixture_kernel<<<cta_blocks, 128, 0, s>>>(a);
+  band_mixture_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 128, 0, s>>>(a);
 }
 
 }  // namespace ppm

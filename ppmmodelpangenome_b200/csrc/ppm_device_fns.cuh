@@ -474,8 +474,9 @@ PPM_HD void zero_row_slice(const ModelDev& m, const TablesDev& t, int p, int j) 
   t.zpart[(size_t)p * m.n_slices + j] = make_double2(prod * m.slice_wt_pad[j], (double)ex);
 }
 
-// CTA-wide: (1) shifts accumulated before each block, (2) the slices, (3) the fixed-order sum.  tid/nt as in the node prepass.
-PPM_HD void zero_row_body(const ModelDev& m, const TablesDev& t, int p, int tid, int nt) {
+// (1) shifts accumulated before each block (one CTA per parameter vector), (2) the slices (any number of CTAs: slices are
+// independent), (3) the fixed-order sum (one thread per parameter vector).  tid/nt as in the node prepass.
+PPM_HD void zero_row_prefix_body(const ModelDev& m, const TablesDev& t, int p, int tid, int nt) {
   int* zxb = t.zxb + (size_t)p * (m.n_blocks + 1);
   const int* zk = t.zk + (size_t)p * m.n_nodes;
   for (int b = tid; b <= m.n_blocks; b += nt) {  // shifts of the nodes formed in each block ...
@@ -490,16 +491,20 @@ PPM_HD void zero_row_body(const ModelDev& m, const TablesDev& t, int p, int tid,
     int run = 0;
     for (int b = 0; b <= m.n_blocks; b++) { const int v = zxb[b]; zxb[b] = run; run += v; }
   }
+}
+PPM_HD void zero_row_sum_body(const ModelDev& m, const TablesDev& t, int p) {  // sum of mantissa * 2^-exponent in slice order
+  double Im = 0.; int Ie = 0x3fffffff;
+  const double2* zp = t.zpart + (size_t)p * m.n_slices;
+  for (int j = 0; j < m.n_slices; j++) scaled_add(Im, Ie, zp[j].x, (int)zp[j].y);
+  double* scw = t.scal + (size_t)p * SC_COUNT;
+  scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
+}
+PPM_HD void zero_row_body(const ModelDev& m, const TablesDev& t, int p, int tid, int nt) {  // all three on one CTA (host emulation)
+  zero_row_prefix_body(m, t, p, tid, nt);
   PPM_CTA_BARRIER();
   for (int j = tid; j < m.n_slices; j += nt) zero_row_slice(m, t, p, j);
   PPM_CTA_BARRIER();
-  if (tid == 0) {  // sum of mantissa * 2^-exponent in slice order
-    double Im = 0.; int Ie = 0x3fffffff;
-    const double2* zp = t.zpart + (size_t)p * m.n_slices;
-    for (int j = 0; j < m.n_slices; j++) scaled_add(Im, Ie, zp[j].x, (int)zp[j].y);
-    double* scw = t.scal + (size_t)p * SC_COUNT;
-    scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
-  }
+  if (tid == 0) zero_row_sum_body(m, t, p);
 }
 
 // ------------------------------------------------------------------------------------------------ class sums

@@ -103,12 +103,14 @@ struct ppm_engine {
   DevBuf<int> d_bwarp_ent_off;
   DevBuf<double2> d_bleaf;
   // stream layout (band_stream.cu): per-batch scratch
-  DevBuf<double2> d_bs_nodes, d_bs_unit, d_bs_ident;
-  DevBuf<int> d_bs_xk;
+  DevBuf<double2> d_bs_nodes[2], d_bs_unit[2], d_bs_ident;
+  DevBuf<int> d_bs_xk[2];
+  cudaEvent_t ev_bs_tables = nullptr, ev_bs_pruned[2] = {nullptr, nullptr}, ev_bs_done[2] = {nullptr, nullptr};
   DevBuf<unsigned int> d_bs_counter;
   DevBuf<uint32_t> d_bs_blocks;
   DevBuf<int> d_bs_unit_off;
   int bs_blk_cap = 0;             // 32-item blocks the scratch holds
+  size_t bs_budget = 0;           // scratch budget in bytes (decided at the first band launch)
   size_t partial_b_cap = 0;
   int last_sweep_kind = 0;        // 0: lane-per-pattern sweep, 1: band kernel (+ fallback launch), for ppm_get_counters
   int last_sweep_mode = -1;       // SweepPlan::mode of the last lane-per-pattern launch
@@ -149,6 +151,11 @@ struct ppm_engine {
     if (ev_done) cudaEventDestroy(ev_done);
     if (ev_nodes) cudaEventDestroy(ev_nodes);
     if (ev_class) cudaEventDestroy(ev_class);
+    if (ev_bs_tables) cudaEventDestroy(ev_bs_tables);
+    for (int k = 0; k < 2; k++) {
+      if (ev_bs_pruned[k]) cudaEventDestroy(ev_bs_pruned[k]);
+      if (ev_bs_done[k]) cudaEventDestroy(ev_bs_done[k]);
+    }
     if (side) cudaStreamDestroy(side);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -173,6 +180,11 @@ struct ppm_engine {
     CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_nodes, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_class, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_bs_tables, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaEventCreateWithFlags(&ev_bs_pruned[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_bs_done[k], cudaEventDisableTiming));
+    }
   }
 
   void upload_model() {
@@ -267,7 +279,7 @@ struct ppm_engine {
     const std::vector<double2> ident{make_double2(1., 0.), make_double2(0., 0.)};
     if (band.stream) {
       d_bs_ident.upload(ident, stream);
-      d_bs_counter.alloc(1);
+      d_bs_counter.alloc(2);
       d_bs_blocks.upload(band.blocks, stream);
       d_bs_unit_off.upload(band.unit_blk_off, stream);
     }
@@ -424,7 +436,7 @@ struct ppm_engine {
     if (use_band && with_class_sums) { ppm::launch_prepass_band(md, t, bdev, band_tables(), s); n_launches += 1; }
     ppm::launch_zero_row(md, t, s);  // the all-zero row of computeI2: slices over threads, not a sweep item
     ppm::launch_prepass_i2(md, t, d_i2_ovr, s);
-    n_launches += 4;
+    n_launches += 6;
   }
 
   // mode 0: partial sums into d_out[P]; mode 2: categories/components for P == 1
@@ -450,14 +462,27 @@ struct ppm_engine {
       if (band.stream) {
         // batches of 32-item blocks through one scratch: prune -> integral -> mixture, back to back on the stream
         const long long n_blk_total = (long long)t.P * (n_pat_pad / 32);
-        size_t budget = (size_t)2048 << 20;
+        // scratch budget: every batch boundary drains the GPU once (~2 ms at 5,000 genomes), so batches should be big -- a
+        // sixth of the free device memory, at most 16 GB, unless PPM_BAND_SCRATCH_MB says otherwise
+        size_t budget = bs_budget;
+        if (budget == 0) {
+          size_t free_b = 0, total_b = 0;
+          CK(cudaMemGetInfo(&free_b, &total_b));
+          size_t have = 0;
+          for (int k = 0; k < 2; k++) have += d_bs_nodes[k].n * sizeof(double2) + d_bs_xk[k].n * sizeof(int) + d_bs_unit[k].n * sizeof(double2);
+          budget = bs_budget = std::min<size_t>((size_t)16 << 30, std::max<size_t>((size_t)1 << 30, (free_b + have) / 6));
+        }
         if (const char* e = std::getenv("PPM_BAND_SCRATCH_MB")) budget = (size_t)std::max(1, std::atoi(e)) << 20;
+        // Two scratch buffers: the prune kernel of batch b + 1 (latency-bound: one thread walks 5,000 dependent ops) runs on
+        // the side stream while the integral kernel of batch b fills the GPU.
         const size_t per_blk = ppm::band_stream_block_bytes(bdev);
-        const int blk_batch = (int)std::max<long long>(1, std::min<long long>(n_blk_total, (long long)(budget / per_blk)));
+        const int blk_batch = (int)std::max<long long>(1, std::min<long long>((n_blk_total + 1) / 2, (long long)(budget / 2 / per_blk)));
         if (blk_batch > bs_blk_cap) {
-          d_bs_nodes.alloc((size_t)blk_batch * bdev.n_int * 32);
-          d_bs_xk.alloc((size_t)blk_batch * (bdev.n_int + 1) * 32);
-          d_bs_unit.alloc((size_t)blk_batch * 32 * bdev.G);
+          for (int k = 0; k < 2; k++) {
+            d_bs_nodes[k].alloc((size_t)blk_batch * bdev.n_int * 32);
+            d_bs_xk[k].alloc((size_t)blk_batch * (bdev.n_int + 1) * 32);
+            d_bs_unit[k].alloc((size_t)blk_batch * 32 * bdev.G);
+          }
           bs_blk_cap = blk_batch;
         }
         n_band_partials = (int)(n_pat_pad / 32);
@@ -465,14 +490,32 @@ struct ppm_engine {
         if (needb > partial_b_cap) { d_partial_b.alloc(needb); partial_b_cap = needb; }
         ppm::BandStreamArgs sa{};
         sa.m = md; sa.t = t; sa.b = bdev; sa.bt = band_tables(); sa.count = count; sa.count_pad = n_pat_pad; sa.force = 0;
-        sa.nodes = d_bs_nodes.p; sa.xk = d_bs_xk.p; sa.unit_I = d_bs_unit.p; sa.counter = d_bs_counter.p; sa.ident = d_bs_ident.p;
-        sa.partial = d_partial_b.p;
+        sa.ident = d_bs_ident.p; sa.partial = d_partial_b.p;
         if (const char* e = std::getenv("PPM_BAND_DBG")) sa.dbg = std::atoi(e);
         CK(cudaEventRecord(ev0, s));
-        for (long long b0 = 0; b0 < n_blk_total; b0 += blk_batch) {
-          sa.item0 = 32 * b0;
-          sa.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b0);
-          ppm::launch_band_stream(sa, n_sm, s);
+        CK(cudaEventRecord(ev_bs_tables, s));            // the tables of this call are complete on s ...
+        CK(cudaStreamWaitEvent(side, ev_bs_tables, 0));  // ... before the side stream prunes with them
+        const long long n_batches = (n_blk_total + blk_batch - 1) / blk_batch;
+        auto batch_args = [&](long long b) {
+          ppm::BandStreamArgs x = sa;
+          const int k = (int)(b & 1);
+          x.nodes = d_bs_nodes[k].p; x.xk = d_bs_xk[k].p; x.unit_I = d_bs_unit[k].p; x.counter = d_bs_counter.p + k;
+          x.item0 = 32 * b * blk_batch;
+          x.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b * blk_batch);
+          return x;
+        };
+        ppm::launch_band_prune(batch_args(0), side);
+        CK(cudaEventRecord(ev_bs_pruned[0], side));
+        for (long long b = 0; b < n_batches; b++) {
+          const int k = (int)(b & 1);
+          if (b + 1 < n_batches) {
+            if (b >= 1) CK(cudaStreamWaitEvent(side, ev_bs_done[k ^ 1], 0));  // integral b - 1 has released that buffer
+            ppm::launch_band_prune(batch_args(b + 1), side);
+            CK(cudaEventRecord(ev_bs_pruned[k ^ 1], side));
+          }
+          CK(cudaStreamWaitEvent(s, ev_bs_pruned[k], 0));
+          ppm::launch_band_integral(batch_args(b), n_sm, s);
+          CK(cudaEventRecord(ev_bs_done[k], s));
           n_launches += 3;
         }
       } else {

@@ -86,8 +86,34 @@ __global__ void __launch_bounds__(256) class_walk_kernel(ModelDev m, TablesDev t
   else { for (int p = lane; p < t.P; p += 32) t.a01[(size_t)pat * t.P + p] = class_sums(t, p, frontier, nf); }
 }
 
-__global__ void __launch_bounds__(256) zero_row_kernel(ModelDev m, TablesDev t) {
-  zero_row_body(m, t, blockIdx.x, threadIdx.x, blockDim.x);
+// The all-zero row as three launches: shift prefixes (one CTA per parameter vector), slices (a grid over (slices, parameter
+// vectors): with few parameter vectors one CTA each left the GPU idle for 10 ms at 5,000 genomes), fixed-order sum.
+__global__ void __launch_bounds__(256) zero_row_prefix_kernel(ModelDev m, TablesDev t) {
+  zero_row_prefix_body(m, t, blockIdx.x, threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(128) zero_row_slices_kernel(ModelDev m, TablesDev t) {
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j < m.n_slices) zero_row_slice(m, t, blockIdx.x, j);
+}
+// fixed-shape sum of the slice values (mantissa * 2^-exponent): 256 contiguous chunks in slice order, then a binary tree
+__global__ void __launch_bounds__(256) zero_row_sum_kernel(ModelDev m, TablesDev t) {
+  __shared__ double sm[256];
+  __shared__ int se[256];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const double2* zp = t.zpart + (size_t)p * m.n_slices;
+  const int chunk = (m.n_slices + 255) / 256;
+  double Im = 0.; int Ie = 0x3fffffff;
+  for (int j = tid * chunk; j < min((tid + 1) * chunk, m.n_slices); j++) scaled_add(Im, Ie, zp[j].x, (int)zp[j].y);
+  sm[tid] = Im; se[tid] = Ie;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { scaled_add(Im, Ie, sm[tid + o], se[tid + o]); sm[tid] = Im; se[tid] = Ie; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double* scw = t.scal + (size_t)p * SC_COUNT;
+    scw[SC_IZ_M] = Im; scw[SC_IZ_E] = (double)Ie;
+  }
 }
 __global__ void prepass_i2_kernel(ModelDev m, TablesDev t, const double* i2_override) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,7 +444,9 @@ void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, l
   }
 }
 void launch_zero_row(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  zero_row_kernel<<<t.P, 256, 0, s>>>(m, t);
+  zero_row_prefix_kernel<<<t.P, 256, 0, s>>>(m, t);
+  zero_row_slices_kernel<<<dim3(t.P, (m.n_slices + 127) / 128), 128, 0, s>>>(m, t);
+  zero_row_sum_kernel<<<t.P, 256, 0, s>>>(m, t);
 }
 void launch_prepass_i2(const ModelDev& m, const TablesDev& t, const double* i2_override, cudaStream_t s) {
   prepass_i2_kernel<<<(t.P + 63) / 64, 64, 0, s>>>(m, t, i2_override);

@@ -196,7 +196,8 @@ BandPlan plan_band(const ModelDev& m, const BandDev& b, long long count, int P, 
 size_t band_smem_bytes(const ModelDev& m, const BandDev& b);
 void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
 size_t band_stream_block_bytes(const BandDev& b);  // scratch per 32-item block
-void launch_band_stream(const BandStreamArgs& a, int n_sm, cudaStream_t s);  // prune + integral + mixture of one batch
+void launch_band_prune(const BandStreamArgs& a, cudaStream_t s);                 // one batch: lineage records into the scratch
+void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);    // one batch: integral + mixture
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
 void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s);  // [n][P] -> [P], rank order
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]
