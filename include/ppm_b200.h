@@ -95,7 +95,11 @@ int ppm_create_group_from_files(ppm_handle* out, const char* tree_path, const ch
                                 const int32_t* gpu_ids, int32_t n_gpus);
 
 void ppm_destroy(ppm_handle h);
-const char* ppm_last_error(ppm_handle h); /* h may be NULL: error of the last failed create on this thread */
+const char* ppm_last_error(ppm_handle h); /* Writes the handle's unique patterns and their counts in the reference's compressed matrix format ("ccc,count,...": read by
+ * PAmatrix::PAmatrix, source/objects.cpp:175-187; produced by compress.rep, simulation_aux.R:247-252), so that a later run -- of this
+ * library or of the reference -- starts from the deduplicated matrix. */
+int ppm_write_ccc(ppm_handle h, const char* path);
+/* h may be NULL: error of the last failed create on this thread */
 int ppm_get_info(ppm_handle h, ppm_info* out);
 
 /* Integer model arrays for bit-exact checks against the reference's fields (functions.hpp:78-94):

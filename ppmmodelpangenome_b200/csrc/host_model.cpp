@@ -338,12 +338,12 @@ Patterns build_patterns(const Tree& t, const uint32_t* rows, const int32_t* coun
 
 // PAmatrix(path) (objects.cpp:164-214): first line = header (ignored) or "ccc,count,count,..."; then one
 // line per genome: name,v,v,...  Genome rows are matched to tree leaves by name (objects.cpp:240-249).
-Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
+int64_t read_matrix_rows(const Tree& t, const std::string& path, std::vector<uint32_t>& rows, std::vector<int32_t>& counts) {
   std::ifstream f(path);
   if (!f) throw std::runtime_error("cannot open matrix file " + path);
   std::string line;
   if (!std::getline(f, line)) throw std::runtime_error("matrix file is empty: " + path);
-  std::vector<int32_t> counts;
+  counts.clear();
   auto strip = [](std::string& s) { while (!s.empty() && (s.back() == '\r' || s.back() == '\n')) s.pop_back(); };
   strip(line);
   if (line.size() >= 3 && line[0] == 'c' && line[1] == 'c' && line[2] == 'c') {
@@ -356,7 +356,7 @@ Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
   std::unordered_map<std::string, int> leaf_of;
   for (int k = 0; k < t.n_leaves; k++) leaf_of[t.label[t.leaf_node[k]]] = k;
   const int nw = (t.n_leaves + 31) / 32;
-  std::vector<uint32_t> rows;
+  rows.clear();
   int64_t n_genes = -1;
   std::vector<char> seen(t.n_leaves, 0);
   while (std::getline(f, line)) {
@@ -415,7 +415,36 @@ Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
   for (int k = 0; k < t.n_leaves; k++)
     if (!seen[k]) throw std::runtime_error("matrix: no row for tree leaf '" + t.label[t.leaf_node[k]] + "'");
   if (!counts.empty() && (int64_t)counts.size() != n_genes) throw std::runtime_error("matrix: ccc header length differs from the rows");
+  return n_genes;
+}
+
+Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe) {
+  std::vector<uint32_t> rows;
+  std::vector<int32_t> counts;
+  const int64_t n_genes = read_matrix_rows(t, path, rows, counts);
   return build_patterns(t, rows.data(), counts.empty() ? nullptr : counts.data(), n_genes, dedupe);
+}
+
+// The compressed matrix format of the reference (objects.cpp:175-187 reads it, simulation_aux.R:247-252 compress.rep makes
+// it): first line "ccc,count,count,...", then one line per genome "name,v,v,..." with one column per unique pattern.
+void write_ccc_file(const Tree& t, const Patterns& p, const std::string& path) {
+  std::ofstream f(path);
+  if (!f) throw std::runtime_error("cannot open " + path + " for writing");
+  std::string line = "ccc";
+  for (int64_t j = 0; j < p.n_patterns; j++) { line += ','; line += std::to_string(p.counts[j]); }
+  line += '\n';
+  f << line;
+  for (int k = 0; k < t.n_leaves; k++) {
+    line = t.label[t.leaf_node[k]];
+    line.reserve(line.size() + 2 * (size_t)p.n_patterns + 2);
+    for (int64_t j = 0; j < p.n_patterns; j++) {
+      line += ',';
+      line += ((p.words[(size_t)j * p.n_words + (k >> 5)] >> (k & 31)) & 1u) ? '1' : '0';
+    }
+    line += '\n';
+    f << line;
+  }
+  if (!f) throw std::runtime_error("write error on " + path);
 }
 
 // ---------------------------------------------------------------------------------------------------------

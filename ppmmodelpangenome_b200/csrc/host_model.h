@@ -50,6 +50,13 @@ struct Patterns {
 // rows: n_rows x n_words packed rows; counts may be null (all ones)
 Patterns build_patterns(const Tree& t, const uint32_t* rows, const int32_t* counts, int64_t n_rows, bool dedupe);
 Patterns read_matrix_file(const Tree& t, const std::string& path, bool dedupe);
+// the parsing half of read_matrix_file: gene rows [n_genes][n_words] bit-packed (bit k = k-th leaf in preorder), the counts of a
+// "ccc" header (empty otherwise); returns n_genes
+int64_t read_matrix_rows(const Tree& t, const std::string& path, std::vector<uint32_t>& rows, std::vector<int32_t>& counts);
+// unique patterns + counts in the reference's compressed ("ccc") matrix format
+void write_ccc_file(const Tree& t, const Patterns& p, const std::string& path);
+// build_patterns (dedupe = true) on the GPU (pattern_kernels.cu); false: two different rows share a hash, use the host path
+bool build_patterns_device(const Tree& t, const uint32_t* rows, const int32_t* counts, int64_t n_rows, int device, Patterns& p);
 
 // ---- sweep program ---------------------------------------------------------------------------------------
 // The tree is swept once in height order.  Slices of the Mobile integral are grouped into blocks of at most

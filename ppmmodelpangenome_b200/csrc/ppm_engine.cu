@@ -192,6 +192,7 @@ struct ppm_engine {
     upload_model_impl(false);
     const bool staged = ppm::sweep_is_staged(md);
     if (!staged) upload_model_impl(true);
+    upload_patterns();
     setup_band(staged);
   }
 
@@ -329,15 +330,7 @@ struct ppm_engine {
     d_entry_ref.upload(prog.entry_ref, stream); d_entry_mask.upload(prog.entry_mask, stream);
     d_entry_node.upload(prog.entry_node, stream); d_entry_block.upload(prog.entry_block, stream);
     d_leaf_node.upload(prog.leaf_node_dev, stream);
-    // patterns of this shard, word-major so that lanes (= consecutive patterns) read consecutive addresses
-    n_pat_pad = (count + 31) / 32 * 32;
-    std::vector<uint32_t> wm((size_t)pat.n_words * std::max<long long>(n_pat_pad, 32), 0u);
-    {  // bits in program leaf order (host_model.h: Program::leaf_perm)
-      const std::vector<uint32_t> rows = ppm::permute_patterns(prog, pat.words.data() + (size_t)first * pat.n_words, count, pat.n_words);
-      for (long long j = 0; j < count; j++)
-        for (int w = 0; w < pat.n_words; w++) wm[(size_t)w * n_pat_pad + j] = rows[(size_t)j * pat.n_words + w];
-    }
-    d_words.upload(wm, stream);
+    n_pat_pad = (count + 31) / 32 * 32;  // (the pattern words themselves: upload_patterns, once the program is final)
     std::vector<uint32_t> zeros((size_t)pat.n_words * 32, 0u);
     d_zero_words.upload(zeros, stream);
     std::vector<int> c(pat.counts.begin() + first, pat.counts.begin() + first + count);
@@ -367,6 +360,29 @@ struct ppm_engine {
         !std::getenv("PPM_WORDS_SMEM"))
       md.word_stride = (int)n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
+  }
+
+  // Patterns of this shard on the device: word-major (lanes = consecutive patterns read consecutive addresses), bits in
+  // PROGRAM leaf order (host_model.h: Program::leaf_perm).  The rows go up as they are (row-major, preorder leaf order); a
+  // kernel permutes the bits and transposes (on the host this cost 4 s per million patterns of 5,000 genomes).
+  void upload_patterns() {
+    NvtxRange r("ppm:upload_patterns");
+    const int nw = pat.n_words;
+    d_words.alloc((size_t)nw * std::max<long long>(n_pat_pad, 32));
+    CK(cudaMemsetAsync(d_words.p, 0, sizeof(uint32_t) * (size_t)nw * std::max<long long>(n_pat_pad, 32), stream));
+    if (count > 0) {
+      std::vector<int> inv((size_t)nw * 32, -1);  // device bit position -> preorder leaf index
+      for (int k = 0; k < tree.n_leaves; k++) inv[prog.leaf_perm[k]] = k;
+      DevBuf<int> d_inv;
+      DevBuf<uint32_t> d_rows;
+      d_inv.upload(inv, stream);
+      d_rows.alloc((size_t)count * nw);
+      CK(cudaMemcpyAsync(d_rows.p, pat.words.data() + (size_t)first * nw, sizeof(uint32_t) * (size_t)count * nw, cudaMemcpyHostToDevice, stream));
+      ppm::launch_permute_words(d_rows.p, d_inv.p, count, nw, n_pat_pad, d_words.p, stream);
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaGetLastError());
+    }
+    md.words = d_words.p;
     // frontier lists of the class sums: pattern-only, so once per handle (count, prefix sums on the host, fill)
     md.fr_off = nullptr; md.fr_nodes = nullptr;
     if (tree.n_nodes <= 65535 && count > 0) {
@@ -602,6 +618,27 @@ static bool none_factored(const double* params, int P) {
   catch (const std::bad_alloc&) { (h)->err = "out of host memory"; return PPM_ENOMEM; } \
   catch (const std::exception& e) { (h)->err = e.what(); return PPM_EINVAL; }
 
+// Unique patterns of a gene-row matrix.  With a device and enough rows the dedupe runs on the GPU (pattern_kernels.cu: hash,
+// stable radix sort, verified runs); it is bit-identical to the host path, which remains for host-only handles, small
+// inputs, dedupe = 0 and the (detected, never observed) case of a 64-bit hash collision.  PPM_GPU_DEDUPE_MIN: row threshold.
+static ppm::Patterns make_patterns(const ppm::Tree& t, const uint32_t* rows, const int32_t* counts, int64_t n_rows, bool dedupe, int device) {
+  long long min_rows = 50000;
+  if (const char* e = std::getenv("PPM_GPU_DEDUPE_MIN")) min_rows = std::atoll(e);
+  if (device >= 0 && dedupe && n_rows >= min_rows) {
+    NvtxRange r("ppm:dedupe(gpu)");
+    ppm::Patterns p;
+    if (ppm::build_patterns_device(t, rows, counts, n_rows, device, p)) return p;
+  }
+  NvtxRange r("ppm:dedupe(host)");
+  return ppm::build_patterns(t, rows, counts, n_rows, dedupe);
+}
+static ppm::Patterns make_patterns_from_file(const ppm::Tree& t, const char* path, bool dedupe, int device) {
+  std::vector<uint32_t> rows;
+  std::vector<int32_t> counts;
+  const int64_t n = ppm::read_matrix_rows(t, path, rows, counts);
+  return make_patterns(t, rows.data(), counts.empty() ? nullptr : counts.data(), n, dedupe, device);
+}
+
 static void finish_one(ppm_engine* e, int device, int rank, int world) {
   if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad shard rank/world");
   e->shard_rank = rank; e->shard_world = world;
@@ -654,7 +691,7 @@ int ppm_create(ppm_handle* out, const ppm_tree* tree, const uint32_t* packed, co
   std::unique_ptr<ppm_engine> e(new ppm_engine);
   try {
     e->tree = ppm::tree_from_arrays(tree->n_nodes, tree->left, tree->right, tree->branch_len);
-    e->pat = ppm::build_patterns(e->tree, packed, counts, n_patterns, dedupe != 0);
+    e->pat = make_patterns(e->tree, packed, counts, n_patterns, dedupe != 0, device);
     return finish_create(out, e, device, shard_rank, shard_world);
   } catch (const CudaError& x) { g_create_error = x.what(); return PPM_ECUDA; }
   catch (const std::bad_alloc&) { g_create_error = "out of host memory"; return PPM_ENOMEM; }
@@ -669,7 +706,7 @@ int ppm_create_from_files(ppm_handle* out, const char* tree_path, const char* ma
   try {
     try {
       e->tree = ppm::read_tree_file(tree_path);
-      e->pat = ppm::read_matrix_file(e->tree, matrix_path, dedupe != 0);
+      e->pat = make_patterns_from_file(e->tree, matrix_path, dedupe != 0, device);
     } catch (const std::runtime_error& x) {
       g_create_error = x.what();
       return (g_create_error.rfind("cannot open", 0) == 0) ? PPM_EIO : PPM_EINVAL;
@@ -687,7 +724,7 @@ int ppm_create_group(ppm_handle* out, const ppm_tree* tree, const uint32_t* pack
   std::unique_ptr<ppm_engine> e(new ppm_engine);
   try {
     e->tree = ppm::tree_from_arrays(tree->n_nodes, tree->left, tree->right, tree->branch_len);
-    e->pat = ppm::build_patterns(e->tree, packed, counts, n_patterns, dedupe != 0);
+    e->pat = make_patterns(e->tree, packed, counts, n_patterns, dedupe != 0, (gpu_ids && n_gpus > 0) ? gpu_ids[0] : -1);
     return finish_create_group(out, e, gpu_ids, n_gpus);
   } catch (const CudaError& x) { g_create_error = x.what(); return PPM_ECUDA; }
   catch (const std::bad_alloc&) { g_create_error = "out of host memory"; return PPM_ENOMEM; }
@@ -702,7 +739,7 @@ int ppm_create_group_from_files(ppm_handle* out, const char* tree_path, const ch
   try {
     try {
       e->tree = ppm::read_tree_file(tree_path);
-      e->pat = ppm::read_matrix_file(e->tree, matrix_path, dedupe != 0);
+      e->pat = make_patterns_from_file(e->tree, matrix_path, dedupe != 0, (gpu_ids && n_gpus > 0) ? gpu_ids[0] : -1);
     } catch (const std::runtime_error& x) {
       g_create_error = x.what();
       return (g_create_error.rfind("cannot open", 0) == 0) ? PPM_EIO : PPM_EINVAL;
@@ -720,6 +757,14 @@ void ppm_destroy(ppm_handle h) {
 }
 
 const char* ppm_last_error(ppm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ppm_write_ccc(ppm_handle h, const char* path) {
+  if (!h || !path) return PPM_EINVAL;
+  try {
+    ppm::write_ccc_file(h->tree, h->pat, path);
+    return PPM_OK;
+  } catch (const std::exception& x) { h->err = x.what(); return PPM_EIO; }
+}
 
 int ppm_get_info(ppm_handle h, ppm_info* o) {
   if (!h || !o) return PPM_EINVAL;

@@ -86,6 +86,28 @@ __global__ void __launch_bounds__(256) class_walk_kernel(ModelDev m, TablesDev t
   else { for (int p = lane; p < t.P; p += 32) t.a01[(size_t)pat * t.P + p] = class_sums(t, p, frontier, nf); }
 }
 
+// Pattern rows (row-major, bit k = k-th leaf in preorder) -> device layout: word-major, bits in program leaf order.  One thread
+// per (pattern, destination word), patterns fastest: the 32 source bits of a word come from anywhere in the thread's own row
+// (L1), the store is coalesced.
+__global__ void __launch_bounds__(256) permute_words_kernel(const uint32_t* __restrict__ rows, const int* __restrict__ inv, long long count,
+                                                            int nw, long long n_pat_pad, uint32_t* __restrict__ out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = blockIdx.y;
+  if (j >= count) return;
+  const uint32_t* row = rows + (size_t)j * nw;
+  uint32_t v = 0u;
+#pragma unroll 8
+  for (int b = 0; b < 32; b++) {
+    const int k = inv[w * 32 + b];
+    if (k >= 0) v |= ((row[k >> 5] >> (k & 31)) & 1u) << b;
+  }
+  out[(size_t)w * n_pat_pad + j] = v;
+}
+void launch_permute_words(const uint32_t* rows, const int* inv, long long count, int nw, long long n_pat_pad, uint32_t* out, cudaStream_t s) {
+  if (count <= 0) return;
+  permute_words_kernel<<<dim3((unsigned)((count + 255) / 256), nw), 256, 0, s>>>(rows, inv, count, nw, n_pat_pad, out);
+}
+
 // The all-zero row as three launches: shift prefixes (one CTA per parameter vector), slices (a grid over (slices, parameter
 // vectors): with few parameter vectors one CTA each left the GPU idle for 10 ms at 5,000 genomes), fixed-order sum.
 __global__ void __launch_bounds__(256) zero_row_prefix_kernel(ModelDev m, TablesDev t) {

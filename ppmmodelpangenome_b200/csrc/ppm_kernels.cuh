@@ -173,6 +173,9 @@ struct SweepArgs {
 // small tables the global-memory variant stages per parameter vector when they fit (priority order)
 enum { DS_PAIRQ = 1, DS_SLICES = 2, DS_CHERRY = 4, DS_LEAFAB = 8, DS_OPS = 16 };
 
+// rows [count][nw] row-major in preorder leaf order -> out [nw][n_pat_pad] word-major in program leaf order; inv [nw * 32]:
+// device bit position -> preorder leaf index (-1: no leaf)
+void launch_permute_words(const uint32_t* rows, const int* inv, long long count, int nw, long long n_pat_pad, uint32_t* out, cudaStream_t s);
 void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s);
 void launch_class_sums(const ModelDev& m, const TablesDev& t, long long first, long long count, cudaStream_t s);

@@ -61,6 +61,7 @@ def lib():
         L.ppm_last_error.argtypes = [vp]
         L.ppm_last_error.restype = C.c_char_p
         L.ppm_get_info.argtypes = [vp, vp]
+        L.ppm_write_ccc.argtypes = [vp, C.c_char_p]
         L.ppm_get_int_array.argtypes = [vp, C.c_int, vp, i64]
         L.ppm_get_double_array.argtypes = [vp, C.c_int, vp, i64]
         L.ppm_loglik.argtypes = [vp, vp, i32, vp, vp]
@@ -297,6 +298,10 @@ class Inference:
 
     def finalize_device(self, d_i2_ptr, d_ll_ptr, P, stream_ptr=None):
         self._ck(lib().ppm_finalize_ll_device(self._h, d_i2_ptr, d_ll_ptr, P, stream_ptr))
+
+    def write_ccc(self, path):
+        """Unique patterns + counts in the reference's compressed matrix format (ppm_write_ccc)."""
+        self._ck(lib().ppm_write_ccc(self._h, str(path).encode()))
 
     def plan(self):
         """Which kernels serve this handle (ppm_get_plan)."""
