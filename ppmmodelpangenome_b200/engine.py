@@ -34,7 +34,7 @@ SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_create_group", "ppm_creat
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
            "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_expected_time1",
            "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters", "ppm_get_plan", "ppm_simulate_genes",
-           "ppm_measure_fp64_peak"]
+           "ppm_measure_fp64_peak", "ppm_write_ccc"]
 
 
 def lib():
