@@ -149,7 +149,13 @@ struct BandStreamArgs {
   const double2* ident;        // 32 bytes (1, 0, 0, 0): the record of a padding entry
   double* partial;             // [P][count_pad / 32]
   int force;
-  int dbg;                     // experiments (PPM_BAND_DBG): 1 = every gather reads the identity record (timing only)
+  int dbg;                     // experiments (PPM_BAND_DBG)
+  // sparse evaluation: only the pattern's DIRTY lineages (a present leaf below) are multiplied, as a ratio
+  // against the all-zero row whose per-slice integrand the prepass already has (TablesDev::zpart)
+  int sparse;
+  uint32_t* dirty;             // scratch [n_blk][(n_int + 31) / 32][32]  one bit per internal lineage, written by the prune kernel
+  const double2* nodes0;       // [P][n_int][32]  lineage records of the all-zero row per parameter vector (copy 0 of 32 is read)
+  const int* xk0;              // [P][n_int + 1][32]  its shift prefixes
 };
 
 struct SweepArgs {
@@ -201,6 +207,8 @@ void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
 size_t band_stream_block_bytes(const BandDev& b);  // scratch per 32-item block
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s);                 // one batch: lineage records into the scratch
 void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);    // one batch: integral + mixture
+// sparse evaluation: records of the all-zero row for every parameter vector (a.nodes / a.xk must hold P blocks)
+void launch_band_prune_zero_row(BandStreamArgs a, cudaStream_t s);
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
 void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s);  // [n][P] -> [P], rank order
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]

@@ -137,3 +137,21 @@ def test_deep_caterpillar_parses_without_recursion():
     assert inf.nLeaves == 3000 and inf.info.n_slices >= 2999
     assert inf.mrca[1] == 0 or inf.freq[1] == 2
     inf.close()
+
+
+def test_ccc_writer_round_trip_on_the_host(golden, tmp_path):
+    """ppm_write_ccc: unique patterns + counts in the reference's compressed format (objects.cpp:175-187); reading the file
+    back (dedupe off: the header carries the multiplicities) gives the same model, and the oracle's own reader agrees."""
+    g = golden("syn100")
+    a = ppm.Inference(g.tree, g.pa, dedupe=True, device=-1)
+    out = str(tmp_path / "compressed.txt")
+    a.write_ccc(out)
+    first = open(out).readline().strip().split(",")
+    assert first[0] == "ccc" and [int(x) for x in first[1:]] == list(a.counts)
+    b = ppm.Inference(g.tree, out, dedupe=False, device=-1)
+    assert (b.nRep, b.nObs, b.meanGenes) == (a.nRep, a.nObs, a.meanGenes)
+    assert np.array_equal(a.counts, b.counts) and np.array_equal(a.mrca, b.mrca) and np.array_equal(a.freq, b.freq)
+    from oracle import model
+    names, M, counts = model.read_matrix(out)
+    assert M.shape[1] == a.nRep and list(counts) == list(a.counts)
+    a.close(); b.close()
