@@ -95,7 +95,12 @@ int ppm_create_group_from_files(ppm_handle* out, const char* tree_path, const ch
                                 const int32_t* gpu_ids, int32_t n_gpus);
 
 void ppm_destroy(ppm_handle h);
-const char* ppm_last_error(ppm_handle h); /* Writes the handle's unique patterns and their counts in the reference's compressed matrix format ("ccc,count,...": read by
+const char* ppm_last_error(ppm_handle h); /* Sparse evaluation of the Mobile integral (nothing in the reference corresponds -- it is the reference's result by a
+ * cheaper route): on trees served by the band kernels, a pattern's lineages without a present leaf below are not multiplied one
+ * by one but taken from the all-zero row the prepass evaluates anyway (Inference::getPobs2, functions.cpp:300-333).  Off by default:
+ * the dense evaluation is what the roofline numbers refer to.  Results agree with the dense evaluation to rounding (tests). */
+int ppm_set_sparse(ppm_handle h, int on);
+/* Writes the handle's unique patterns and their counts in the reference's compressed matrix format ("ccc,count,...": read by
  * PAmatrix::PAmatrix, source/objects.cpp:175-187; produced by compress.rep, simulation_aux.R:247-252), so that a later run -- of this
  * library or of the reference -- starts from the deduplicated matrix. */
 int ppm_write_ccc(ppm_handle h, const char* path);

@@ -534,6 +534,9 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 3) band_integral_sparse_kernel(
       const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
       const double4* pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
       const double2* zpart = a.t.zpart + (size_t)p * m.n_slices;
+      // a pattern present in more than an eighth of the genomes has few clean lineages: it is evaluated densely (every entry
+      // counts as dirty, no denominators, slice weights instead of Z) -- the ratio form would cost it twice the dense work
+      const bool all_dirty = (long long)m.freq[pat] * 8 > m.n_leaves;
       __syncwarp();
       for (int x = lane; x < m.n_words; x += 32) pw[x] = m.words[(size_t)x * m.n_pat_pad + pat];
       if (lane == 0) pw[m.n_words] = 0u;
@@ -572,16 +575,16 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 3) band_integral_sparse_kernel(
                 const uint32_t bits = (pw[ref >> 4] >> (2u * (ref & 15u))) & 3u;
                 sd[h] = reinterpret_cast<const double2*>(pairq + ref * 4);
                 sn[h] = sd[h] + 2 * bits;
-                dty[h] = !pad && bits != 0u;
+                dty[h] = !pad && (bits != 0u || all_dirty);
               } else if (q >> 31) {
                 const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
                 sd[h] = bleaf + ref * 2;
-                sn[h] = sd[h] + 1;
-                dty[h] = !pad && bt1 != 0u;
+                sn[h] = sd[h] + bt1;
+                dty[h] = !pad && (bt1 != 0u || all_dirty);
               } else {
                 sd[h] = nodes0 + (size_t)ref * 32;
                 sn[h] = nodes + (size_t)ref * 32;
-                dty[h] = !pad && ((dm[ref >> 5] >> (ref & 31u)) & 1u) != 0u;
+                dty[h] = !pad && (((dm[ref >> 5] >> (ref & 31u)) & 1u) != 0u || all_dirty);
               }
             }
             const uint32_t m0 = __ballot_sync(0xffffffffu, dty[0]), m1 = __ballot_sync(0xffffffffu, dty[1]);
@@ -593,8 +596,12 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 3) band_integral_sparse_kernel(
                 const int pos = h ? n0 + __popc(m1 & lt) : __popc(m0 & lt);
                 double2* dn = reinterpret_cast<double2*>(slot) + rs * pos;
                 double2* dd = reinterpret_cast<double2*>(slot + BSS_D_OFF) + rs * pos;
-                bs_cp16(dn, sn[h]); bs_cp16(dd, sd[h]);
-                if (pair) { bs_cp16(dn + 1, sn[h] + 1); bs_cp16(dd + 1, sd[h] + 1); }
+                bs_cp16(dn, sn[h]);
+                if (pair) bs_cp16(dn + 1, sn[h] + 1);
+                if (!all_dirty) {
+                  bs_cp16(dd, sd[h]);
+                  if (pair) bs_cp16(dd + 1, sd[h] + 1);
+                }
                 if (masks) {
                   const uint32_t q = h ? e2.y : e2.x;
                   const uint32_t lo = (q >> 16) & 31u, len = ((q >> 21) & 63u) - lo;
@@ -634,15 +641,17 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 3) band_integral_sparse_kernel(
         if (op == BD_END) break;
         const int var = (code >> 4) & 3, kk = (code >> 6) & 7;
         if (op == BD_TILE_BEGIN) {
+          const int tb0 = (int)(code >> 16) * T + lane;
 #pragma unroll
           for (int k = 0; k < R; k++) {
             Y[k] = *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8);
             U[k] = *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8);
             const double2 z = *(reinterpret_cast<const double2*>(buf + 2048) + (k * 32 + lane));
-            pn[k] = z.x; pd[k] = 1.;
-            en[k] = (int)z.y + *reinterpret_cast<const int*>(buf + 4096 + (k * 32 + lane) * 4) -
-                    *reinterpret_cast<const int*>(buf + 4608 + (k * 32 + lane) * 4);
-            ed[k] = 0;
+            const int xi = *reinterpret_cast<const int*>(buf + 4096 + (k * 32 + lane) * 4);
+            const int x0 = *reinterpret_cast<const int*>(buf + 4608 + (k * 32 + lane) * 4);
+            pd[k] = 1.; ed[k] = 0;
+            if (all_dirty) { pn[k] = b.wt[tb0 + 32 * k]; en[k] = xi; }
+            else { pn[k] = z.x; en[k] = (int)z.y + xi - x0; }
           }
           continue;
         }
@@ -659,27 +668,27 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 3) band_integral_sparse_kernel(
           const double4* rd = reinterpret_cast<const double4*>(buf + BSS_D_OFF);
           if (var == BV_FULL) {
             bs_pairs_full<R>(rn, cnt, U, pn, en);
-            bs_pairs_full<R>(rd, cnt, U, pd, ed);
+            if (!all_dirty) bs_pairs_full<R>(rd, cnt, U, pd, ed);
           } else {
 #pragma unroll
             for (int k = 0; k < R; k++)
-              if (k == kk) { pn[k] *= bs_pairs_one(rn, cnt, U[k]); pd[k] *= bs_pairs_one(rd, cnt, U[k]); }
+              if (k == kk) { pn[k] *= bs_pairs_one(rn, cnt, U[k]); if (!all_dirty) pd[k] *= bs_pairs_one(rd, cnt, U[k]); }
           }
         } else {
           const double2* rn = reinterpret_cast<const double2*>(buf);
           const double2* rd = reinterpret_cast<const double2*>(buf + BSS_D_OFF);
           if (var == BV_FULL) {
             bs_recs_full<R>(rn, cnt, Y, pn, en);
-            bs_recs_full<R>(rd, cnt, Y, pd, ed);
+            if (!all_dirty) bs_recs_full<R>(rd, cnt, Y, pd, ed);
           } else if (var == BV_F) {
 #pragma unroll
             for (int k = 0; k < R; k++)
-              if (k == kk) { pn[k] *= bs_recs_one(rn, cnt, Y[k]); pd[k] *= bs_recs_one(rd, cnt, Y[k]); }
+              if (k == kk) { pn[k] *= bs_recs_one(rn, cnt, Y[k]); if (!all_dirty) pd[k] *= bs_recs_one(rd, cnt, Y[k]); }
           } else {
             const uint32_t* mb = reinterpret_cast<const uint32_t*>(buf + BSS_MASK_OFF);
 #pragma unroll
             for (int k = 0; k < R; k++)
-              if (k == kk) { pn[k] *= bs_recs_masked(rn, mb, cnt, Y[k], lanebit); pd[k] *= bs_recs_masked(rd, mb, cnt, Y[k], lanebit); }
+              if (k == kk) { pn[k] *= bs_recs_masked(rn, mb, cnt, Y[k], lanebit); if (!all_dirty) pd[k] *= bs_recs_masked(rd, mb, cnt, Y[k], lanebit); }
           }
         }
         bs_rescale<R>(pn, en);

@@ -107,7 +107,10 @@ struct ppm_engine {
   DevBuf<int> d_bs_xk[2];
   cudaEvent_t ev_bs_tables = nullptr, ev_bs_pruned[2] = {nullptr, nullptr}, ev_bs_done[2] = {nullptr, nullptr};
   DevBuf<unsigned int> d_bs_counter;
-  DevBuf<uint32_t> d_bs_blocks;
+  DevBuf<uint32_t> d_bs_blocks, d_bs_dirty[2];
+  DevBuf<double2> d_bs_nodes0;    // sparse evaluation: records / shift prefixes of the all-zero row per parameter vector
+  DevBuf<int> d_bs_xk0;
+  bool sparse = false;            // ppm_set_sparse / PPM_SPARSE: the band kernels multiply dirty lineages only
   DevBuf<int> d_bs_unit_off;
   int bs_blk_cap = 0;             // 32-item blocks the scratch holds
   size_t bs_budget = 0;           // scratch budget in bytes (decided at the first band launch)
@@ -280,7 +283,8 @@ struct ppm_engine {
     const std::vector<double2> ident{make_double2(1., 0.), make_double2(0., 0.)};
     if (band.stream) {
       d_bs_ident.upload(ident, stream);
-      d_bs_counter.alloc(2);
+      d_bs_counter.alloc(3);
+      if (const char* e = std::getenv("PPM_SPARSE")) sparse = std::atoi(e) != 0;
       d_bs_blocks.upload(band.blocks, stream);
       d_bs_unit_off.upload(band.unit_blk_off, stream);
     }
@@ -501,6 +505,12 @@ struct ppm_engine {
           }
           bs_blk_cap = blk_batch;
         }
+        const bool sparse_now = sparse;
+        if (sparse_now) {
+          for (int k = 0; k < 2; k++) d_bs_dirty[k].alloc((size_t)bs_blk_cap * ((bdev.n_int + 31) / 32) * 32);
+          d_bs_nodes0.alloc((size_t)t.P * bdev.n_int * 32);
+          d_bs_xk0.alloc((size_t)t.P * (bdev.n_int + 1) * 32);
+        }
         n_band_partials = (int)(n_pat_pad / 32);
         const size_t needb = (size_t)t.P * n_band_partials;
         if (needb > partial_b_cap) { d_partial_b.alloc(needb); partial_b_cap = needb; }
@@ -516,10 +526,17 @@ struct ppm_engine {
           ppm::BandStreamArgs x = sa;
           const int k = (int)(b & 1);
           x.nodes = d_bs_nodes[k].p; x.xk = d_bs_xk[k].p; x.unit_I = d_bs_unit[k].p; x.counter = d_bs_counter.p + k;
+          x.sparse = sparse_now ? 1 : 0; x.dirty = d_bs_dirty[k].p; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p;
           x.item0 = 32 * b * blk_batch;
           x.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b * blk_batch);
           return x;
         };
+        if (sparse_now) {  // the all-zero row's records, once per call (P blocks)
+          ppm::BandStreamArgs z = sa;
+          z.nodes = d_bs_nodes0.p; z.xk = d_bs_xk0.p; z.counter = d_bs_counter.p + 2;
+          ppm::launch_band_prune_zero_row(z, side);
+          n_launches += 1;
+        }
         ppm::launch_band_prune(batch_args(0), side);
         CK(cudaEventRecord(ev_bs_pruned[0], side));
         for (long long b = 0; b < n_batches; b++) {
@@ -757,6 +774,12 @@ void ppm_destroy(ppm_handle h) {
 }
 
 const char* ppm_last_error(ppm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ppm_set_sparse(ppm_handle h, int on) {
+  if (!h) return PPM_EINVAL;
+  for (ppm_engine* e : h->members()) e->sparse = on != 0;
+  return PPM_OK;
+}
 
 int ppm_write_ccc(ppm_handle h, const char* path) {
   if (!h || !path) return PPM_EINVAL;

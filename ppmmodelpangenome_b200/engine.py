@@ -34,7 +34,7 @@ SYMBOLS = ["ppm_create", "ppm_create_from_files", "ppm_create_group", "ppm_creat
            "ppm_get_int_array", "ppm_get_double_array", "ppm_loglik", "ppm_loglik_device", "ppm_finalize_ll",
            "ppm_finalize_ll_device", "ppm_compute_i2", "ppm_assign_cat", "ppm_components", "ppm_proba_cat", "ppm_expected_time1",
            "ppm_expected_time2", "ppm_expected_gains", "ppm_get_counters", "ppm_get_plan", "ppm_simulate_genes",
-           "ppm_measure_fp64_peak", "ppm_write_ccc"]
+           "ppm_measure_fp64_peak", "ppm_write_ccc", "ppm_set_sparse"]
 
 
 def lib():
@@ -62,6 +62,7 @@ def lib():
         L.ppm_last_error.restype = C.c_char_p
         L.ppm_get_info.argtypes = [vp, vp]
         L.ppm_write_ccc.argtypes = [vp, C.c_char_p]
+        L.ppm_set_sparse.argtypes = [vp, C.c_int]
         L.ppm_get_int_array.argtypes = [vp, C.c_int, vp, i64]
         L.ppm_get_double_array.argtypes = [vp, C.c_int, vp, i64]
         L.ppm_loglik.argtypes = [vp, vp, i32, vp, vp]
@@ -298,6 +299,10 @@ class Inference:
 
     def finalize_device(self, d_i2_ptr, d_ll_ptr, P, stream_ptr=None):
         self._ck(lib().ppm_finalize_ll_device(self._h, d_i2_ptr, d_ll_ptr, P, stream_ptr))
+
+    def set_sparse(self, on=True):
+        """Sparse evaluation of the Mobile integral on band-kernel trees (ppm_set_sparse)."""
+        self._ck(lib().ppm_set_sparse(self._h, int(bool(on))))
 
     def write_ccc(self, path):
         """Unique patterns + counts in the reference's compressed matrix format (ppm_write_ccc)."""

@@ -161,3 +161,34 @@ def test_band_stream_batches_are_invisible(ppm, tmp_path):
         assert one.counters()["launches"] > n1
     assert np.array_equal(ll, many)
     one.close()
+
+
+@pytest.mark.parametrize("n,genes", [(1500, 300), (5000, 40)])
+def test_sparse_evaluation_equals_dense(ppm, tmp_path, n, genes):
+    """ppm_set_sparse: dirty lineages only, as a ratio against the all-zero row -- the dense result to rounding,
+    for parameter vectors the band kernels serve, for the penalty branch and for one they hand to the sweep."""
+    tp, pp, P, truth = _seeded(ppm, tmp_path, n, genes, 600 + n)
+    inf = ppm.Inference(tp, pp, dedupe=True, device=0)
+    assert inf.plan()["band_stream"] == 1
+    Q = np.vstack([P, P[:1], P[:1]])
+    Q[-2, 0] *= 50                      # i2 < 0
+    Q[-1, 4], Q[-1, 5] = 30.0, 1.0      # pi1 > 0.95: lane-per-pattern sweep
+    dense = inf.loglik_batch(Q)
+    inf.set_sparse(True)
+    sparse = inf.loglik_batch(Q)
+    assert np.array_equal(sparse, inf.loglik_batch(Q))  # reproducible
+    inf.set_sparse(False)
+    assert np.array_equal(dense, inf.loglik_batch(Q))
+    assert np.allclose(sparse, dense, rtol=1e-11, atol=0), (sparse, dense)
+    inf.close()
+
+
+@pytest.mark.parametrize("name", ["syn100", "syn300", "cat40"])
+def test_sparse_evaluation_against_reference_golden(ppm, golden, name):
+    g = golden(name)
+    with _Env(PPM_FORCE_BAND=1, PPM_SPARSE=1):
+        inf = ppm.Inference(g.tree, g.pa, dedupe=True, device=0)
+    ll, i2 = inf.loglik_batch(g.params, return_i2=True)
+    for k, r in enumerate(g.results):
+        assert rel(ll[k], r["ll"]) <= RTOL, (name, k, ll[k], r["ll"])
+    inf.close()

@@ -34,12 +34,14 @@ def main():
         env = {}
         if v == "noband":
             env["PPM_NO_BAND"] = "1"
+        elif v == "sparse":
+            env["PPM_SPARSE"] = "1"
         elif v != "default":
             for kv in v.split("+"):  # e.g. R=2+G=4+CTAS=3
                 k, val = kv.split("=")
                 env["PPM_BAND_" + k] = val
         for k in list(os.environ):
-            if k.startswith("PPM_BAND_") or k == "PPM_NO_BAND":
+            if k.startswith("PPM_BAND_") or k in ("PPM_NO_BAND", "PPM_SPARSE"):
                 del os.environ[k]
         os.environ.update(env)
         t0 = time.time()
