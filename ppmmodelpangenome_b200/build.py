@@ -24,7 +24,7 @@ def _newer(target, sources):
 
 
 def lib_sources():
-    return [os.path.join(CSRC, f) for f in ("host_model.cpp", "band_program.cpp", "simulator.cpp", "ppm_kernels.cu", "band_kernel.cu", "band_stream.cu", "pattern_kernels.cu", "ppm_engine.cu")]
+    return [os.path.join(CSRC, f) for f in ("host_model.cpp", "band_program.cpp", "simulator.cpp", "ppm_kernels.cu", "band_kernel.cu", "band_stream.cu", "pattern_kernels.cu", "band_sparse.cu", "ppm_engine.cu")]
 
 
 def all_inputs():

@@ -201,6 +201,12 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     bp.warp_off.push_back((int)bp.desc.size());
     bp.warp_ent_off.push_back((int)bp.entries.size());
   }
+  if (stream && S < 65536) {  // alive slices of every internal lineage (by record index) and leaf (by device bit position)
+    bp.op_span.assign(bp.ops.size(), 0u);
+    for (size_t i = 0; i < bp.ops.size(); i++) { const int v = bp.op_nodes[3 * i]; bp.op_span[i] = (uint32_t)js0[v] | ((uint32_t)js1[v] << 16); }
+    bp.leaf_span.assign(nl, 0u);
+    for (int v = 1; v < nn; v++) if (t.left[v] < 0) bp.leaf_span[dpos(v)] = (uint32_t)js0[v] | ((uint32_t)js1[v] << 16);
+  }
   if (stream) {
     // device form of the lists: one block of kBandBlockWords words per descriptor = its kBandStreamChunk entries + its code.
     // A tile-begin block carries, instead of entries, the shift-prefix index of each of its slices (nborn), packed so that

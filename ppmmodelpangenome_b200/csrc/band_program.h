@@ -47,6 +47,7 @@ struct BandProgram {
   std::vector<int32_t> warp_ent_off;  // [G+1] first entry of each warp; a warp's chunks own consecutive entries, in list order
   std::vector<uint32_t> blocks;     // stream layout, device form: [block][kBandBlockWords] = a descriptor's entries + its code
   std::vector<int32_t> unit_blk_off;  // [G] first block of each unit's list
+  std::vector<uint32_t> op_span, leaf_span;  // stream layout: alive slices js0 | js1 << 16 per internal lineage / per leaf bit (sparse lists)
   std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 | leaf << 31 (M records: lanes [lo, hi), hi in 1..32)
   double fp64_instr_per_eval = 0;   // modelled FP64 instructions per pattern-eval (phase A + phase B)
   double cost_max = 0, cost_sum = 0;  // modelled phase B cost of the busiest warp / of all warps (balance = sum / (G max))

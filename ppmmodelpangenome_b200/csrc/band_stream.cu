@@ -91,31 +91,18 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
   uint32_t wl[BP_PF], wr[BP_PF];       // requested operands: pattern word of a leaf child ...
   double2 nl[BP_PF], nr[BP_PF];        // ... or the record of an internal child written at least BP_PF ops before the slot's op
   double2 prev[BP_PF];                 // prev[k] = record of op j - 1 - k (register forwarding of the youngest records)
-  // sparse evaluation: one DIRTY bit per internal lineage (a present leaf below), 32 ops per word; a child's bit comes from the
-  // word being assembled, the word before it, or a word requested with the operands
-  const bool sparse = a.sparse != 0;
-  uint32_t* dirty = a.dirty ? a.dirty + (size_t)(active ? blk : 0) * ((n_int + 31) / 32) * 32 + lane : nullptr;
-  uint32_t dacc = 0u, dprev = 0u, dwl[BP_PF], dwr[BP_PF];
 #pragma unroll
   for (int k = 0; k < BP_PF; k++) {
-    dwl[k] = 0u; dwr[k] = 0u;
     prev[k] = make_double2(1., 0.);
     so[k] = make_uint2(0u, 0u);
     wl[k] = 0u; wr[k] = 0u; nl[k] = make_double2(1., 0.); nr[k] = make_double2(1., 0.);
   }
-  auto request = [&](int j, const uint2 oj, uint32_t& w_l, uint32_t& w_r, double2& n_l, double2& n_r, uint32_t& d_l, uint32_t& d_r) {
+  auto request = [&](int j, const uint2 oj, uint32_t& w_l, uint32_t& w_r, double2& n_l, double2& n_r) {
     const int lref = (int)(oj.x & 0xffffu), rref = (int)(oj.x >> 16), flags = (int)(oj.y >> 16);
-    const int gdone = j >= BP_PF ? (j - BP_PF) >> 5 : 0;  // dirty words below this group are complete in memory
     if (flags & 1) bp_ldg(w_l, words + (size_t)(lref >> 5) * wstride);
-    else if (lref < j - BP_PF) {
-      bp_ldg(n_l, nodes + (size_t)lref * 32);
-      if (sparse && (lref >> 5) < gdone) bp_ldg(d_l, dirty + (size_t)(lref >> 5) * 32);
-    }
+    else if (lref < j - BP_PF) bp_ldg(n_l, nodes + (size_t)lref * 32);
     if (flags & 2) bp_ldg(w_r, words + (size_t)(rref >> 5) * wstride);
-    else if (rref < j - BP_PF) {
-      bp_ldg(n_r, nodes + (size_t)rref * 32);
-      if (sparse && (rref >> 5) < gdone) bp_ldg(d_r, dirty + (size_t)(rref >> 5) * 32);
-    }
+    else if (rref < j - BP_PF) bp_ldg(n_r, nodes + (size_t)rref * 32);
   };
   double2* cst = &cst_s[threadIdx.x >> 5][0][0];
   auto stage_consts = [&](int chunk) {  // ops [32 chunk, 32 chunk + 32) of this warp's parameter vector -> buffer chunk & 1
@@ -138,7 +125,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
       for (int k = 0; k < BP_PF; k++) {
         const int j = k < last ? k : last;
         so[k] = ops_s[j];
-        request(k, so[k], wl[k], wr[k], nl[k], nr[k], dwl[k], dwr[k]);
+        request(k, so[k], wl[k], wr[k], nl[k], nr[k]);
       }
     }
     const int c1 = c0 + BP_OC < n_ops ? c0 + BP_OC : n_ops;  // (BP_OC is a multiple of BP_PF: slots keep their phase)
@@ -157,32 +144,23 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
           // operands of op j out of the slot
           const int lref = (int)(so[sl].x & 0xffffu), rref = (int)(so[sl].x >> 16), flags = (int)(so[sl].y >> 16);
           double2 Lc, Rc;
-          uint32_t dl, dr;  // dirty bits of the children
-          if (flags & 1) { dl = (wl[sl] >> (lref & 31)) & 1u; Lc = dl ? leaf1 : leaf0; }
+          if (flags & 1) Lc = ((wl[sl] >> (lref & 31)) & 1u) ? leaf1 : leaf0;
           else {
             Lc = nl[sl];
 #pragma unroll
             for (int k = 0; k < BP_PF; k++) if (lref == j - 1 - k) Lc = prev[k];
-            const uint32_t dw = (lref >> 5) == (j >> 5) ? dacc : ((lref >> 5) == (j >> 5) - 1 ? dprev : dwl[sl]);
-            dl = (dw >> (lref & 31)) & 1u;
           }
-          if (flags & 2) { dr = (wr[sl] >> (rref & 31)) & 1u; Rc = dr ? leaf1 : leaf0; }
+          if (flags & 2) Rc = ((wr[sl] >> (rref & 31)) & 1u) ? leaf1 : leaf0;
           else {
             Rc = nr[sl];
 #pragma unroll
             for (int k = 0; k < BP_PF; k++) if (rref == j - 1 - k) Rc = prev[k];
-            const uint32_t dw = (rref >> 5) == (j >> 5) ? dacc : ((rref >> 5) == (j >> 5) - 1 ? dprev : dwr[sl]);
-            dr = (dw >> (rref & 31)) & 1u;
-          }
-          if (sparse) {
-            dacc |= (dl | dr) << (j & 31);
-            if ((j & 31) == 31 || j == last) { dirty[(size_t)(j >> 5) * 32] = dacc; dprev = dacc; dacc = 0u; }
           }
           const double occ[5] = {k01.x, k01.y, k23.x, k23.y, k4.x};
           // refill the slot for op j + BP_PF (records up to j - 1 are written; the request takes those up to j - 1 only)
           {
             so[sl] = ops_s[j + BP_PF - c0];  // (clamped to the last op when staged)
-            request(j + BP_PF, so[sl], wl[sl], wr[sl], nl[sl], nr[sl], dwl[sl], dwr[sl]);
+            request(j + BP_PF, so[sl], wl[sl], wr[sl], nl[sl], nr[sl]);
           }
           int k;
           const double2 rec = band_merge(Lc.x, Lc.y, Rc.x, Rc.y, occ, pi1, k);
@@ -337,7 +315,8 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
     const int p = (int)(item / a.count_pad);
     const long long pat = item - (long long)p * a.count_pad;
     const double* sc = a.t.scal + (size_t)p * SC_COUNT;
-    if (pat < a.count && bs_served(sc, a.force)) {
+    // (sparse evaluation: the items with term lists belong to band_sparse_kernel)
+    if (pat < a.count && bs_served(sc, a.force) && !(a.sparse && bs_sparse_item(m, pat))) {
       const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
       const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
       const double* bY = a.bt.bY + (size_t)p * b.S_pad;
@@ -481,232 +460,6 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
   }
 }
 
-// ------------------------------------------------------------------------------------------------ sparse integral
-// Sparse evaluation.  A lineage whose subtree holds no present leaf multiplies every slice by
-// exactly what it multiplies for the ALL-ZERO row, whose per-slice integrand Z_j the prepass already has (zero_row_*).  Hence
-//   integrand_j = Z_j * prod over the pattern's DIRTY lineages s alive at j of f_s(j) / f0_s(j)
-// and only dirty lineages are multiplied: numerators from the item's records, denominators from the zero row's records (same
-// kernel arithmetic, per parameter vector), one division per slice at the tile's end.  The gather stage compacts a block's
-// entries to the dirty ones with two ballots (leaf: its pattern bit; pair: either bit; internal lineage: the prune kernel's
-// dirty mask); a block without dirty entries costs its descriptor handling only.  Renormalisation shifts: a clean node has
-// the zero row's shift, so the exponent of the ratio is the difference of the two shift prefixes at the slice.
-enum { BSS_REC = 72, BSS_D_OFF = BSS_REC * 32, BSS_MASK_OFF = 2 * BSS_REC * 32, BSS_CNT_OFF = BSS_MASK_OFF + BSS_REC * 4,
-       BSS_SLOT_BYTES = 5120, BSS_RING_BYTES = BS_NB * BSS_SLOT_BYTES + BS_PAD };
-static_assert(BSS_CNT_OFF + 16 <= BSS_SLOT_BYTES, "sparse slot layout");
-static __host__ __device__ inline size_t bss_warp_bytes(int n_words, int n_int) {
-  return (size_t)BSS_RING_BYTES + BS_BRING_BYTES + 4 * (size_t)bs_pw_words(n_words) + 4 * (size_t)(((n_int + 31) / 32 + 3) & ~3);
-}
-
-template <int R>
-__global__ void __launch_bounds__(32 * BS_WARPS, 3) band_integral_sparse_kernel(BandStreamArgs a) {
-  static_assert(R <= 4, "a tile-begin block carries four shift indices per lane");
-  extern __shared__ __align__(16) unsigned char bs_smem[];
-  const ModelDev& m = a.m;
-  const BandDev& b = a.b;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* wring = bs_smem + (size_t)warp * bss_warp_bytes(m.n_words, b.n_int);
-  unsigned char* bring = wring + BSS_RING_BYTES;
-  uint32_t* pw = reinterpret_cast<uint32_t*>(bring + BS_BRING_BYTES);
-  uint32_t* dm = pw + bs_pw_words(m.n_words);
-  const uint32_t lanebit = 1u << lane, lt = lanebit - 1u;
-  const int T = 32 * R, G = b.G, n_int = b.n_int, n_dw = (n_int + 31) / 32;
-  const unsigned total = (unsigned)a.n_blk * 32u * (unsigned)G;
-
-  unsigned u = 0;
-  if (lane == 0) u = atomicAdd(a.counter, 1u);
-  u = __shfl_sync(0xffffffffu, u, 0);
-  while (u < total) {
-    unsigned u_next = 0;
-    if (lane == 0) u_next = atomicAdd(a.counter, 1u);
-    const int il = (int)(u / (unsigned)G), w = (int)(u - (unsigned)il * (unsigned)G);
-    const long long item = a.item0 + il;
-    const int p = (int)(item / a.count_pad);
-    const long long pat = item - (long long)p * a.count_pad;
-    const double* sc = a.t.scal + (size_t)p * SC_COUNT;
-    if (pat < a.count && bs_served(sc, a.force)) {
-      const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
-      const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
-      const double2* nodes0 = a.nodes0 + (size_t)p * n_int * 32;
-      const int* xk0 = a.xk0 + (size_t)p * (n_int + 1) * 32;
-      const uint32_t* dirty = a.dirty + (size_t)(il >> 5) * n_dw * 32 + (il & 31);
-      const double* bY = a.bt.bY + (size_t)p * b.S_pad;
-      const double* bU = a.bt.bU + (size_t)p * b.S_pad;
-      const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
-      const double4* pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
-      const double2* zpart = a.t.zpart + (size_t)p * m.n_slices;
-      // a pattern present in more than an eighth of the genomes has few clean lineages: it is evaluated densely (every entry
-      // counts as dirty, no denominators, slice weights instead of Z) -- the ratio form would cost it twice the dense work
-      const bool all_dirty = (long long)m.freq[pat] * 8 > m.n_leaves;
-      __syncwarp();
-      for (int x = lane; x < m.n_words; x += 32) pw[x] = m.words[(size_t)x * m.n_pat_pad + pat];
-      if (lane == 0) pw[m.n_words] = 0u;
-      for (int x = lane; x < n_dw; x += 32) dm[x] = dirty[(size_t)x * 32];
-
-      const unsigned char* blocks = reinterpret_cast<const unsigned char*>(b.blocks) + (size_t)b.unit_blk_off[w] * BS_BLK_BYTES;
-      double pn[R], pd[R], Y[R], U[R];  // numerator / denominator products of the lane's R slices
-      int en[R], ed[R];
-#pragma unroll
-      for (int k = 0; k < R; k++) { pn[k] = 0.; pd[k] = 1.; Y[k] = 0.; U[k] = 0.; en[k] = 0; ed[k] = 0; }
-      double Im = 0.; int Ie = 0x3fffffff;
-      uint32_t c0 = BS_NOP, c1 = BS_NOP;
-      int s0 = 0, s2 = 2, s4 = 1;
-      for (int di = -4;; di++) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        if (lane < BS_BLK_BYTES / 16) bs_cp16(bring + s4 * BS_BLK_BYTES + 16 * lane, blocks + (size_t)(di + 4) * BS_BLK_BYTES + 16 * lane);
-        uint32_t c2 = BS_NOP;
-        if (di >= -2) {
-          const uint32_t* blk = reinterpret_cast<const uint32_t*>(bring + s2 * BS_BLK_BYTES);
-          c2 = blk[BS_CH];
-          const uint2 e2 = *reinterpret_cast<const uint2*>(blk + 2 * lane);
-          const uint32_t opG = c2 & 15u;
-          unsigned char* slot = wring + s2 * BSS_SLOT_BYTES;
-          if (opG == BD_REC || opG == BD_PAIR) {
-            const bool pair = opG == BD_PAIR;
-            const bool masks = !pair && ((c2 >> 4) & 3u) == BV_M;
-            const double2* sn[2]; const double2* sd[2];
-            bool dty[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const uint32_t q = h ? e2.y : e2.x;
-              const bool pad = q == kBandPadEntry;
-              const uint32_t ref = pad ? 0u : (q & 0xffffu);
-              if (pair) {
-                const uint32_t bits = (pw[ref >> 4] >> (2u * (ref & 15u))) & 3u;
-                sd[h] = reinterpret_cast<const double2*>(pairq + ref * 4);
-                sn[h] = sd[h] + 2 * bits;
-                dty[h] = !pad && (bits != 0u || all_dirty);
-              } else if (q >> 31) {
-                const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
-                sd[h] = bleaf + ref * 2;
-                sn[h] = sd[h] + bt1;
-                dty[h] = !pad && (bt1 != 0u || all_dirty);
-              } else {
-                sd[h] = nodes0 + (size_t)ref * 32;
-                sn[h] = nodes + (size_t)ref * 32;
-                dty[h] = !pad && (((dm[ref >> 5] >> (ref & 31u)) & 1u) != 0u || all_dirty);
-              }
-            }
-            const uint32_t m0 = __ballot_sync(0xffffffffu, dty[0]), m1 = __ballot_sync(0xffffffffu, dty[1]);
-            const int n0 = __popc(m0), cnt = n0 + __popc(m1);
-            const int rs = pair ? 2 : 1;  // record size in double2 units
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              if (dty[h]) {
-                const int pos = h ? n0 + __popc(m1 & lt) : __popc(m0 & lt);
-                double2* dn = reinterpret_cast<double2*>(slot) + rs * pos;
-                double2* dd = reinterpret_cast<double2*>(slot + BSS_D_OFF) + rs * pos;
-                bs_cp16(dn, sn[h]);
-                if (pair) bs_cp16(dn + 1, sn[h] + 1);
-                if (!all_dirty) {
-                  bs_cp16(dd, sd[h]);
-                  if (pair) bs_cp16(dd + 1, sd[h] + 1);
-                }
-                if (masks) {
-                  const uint32_t q = h ? e2.y : e2.x;
-                  const uint32_t lo = (q >> 16) & 31u, len = ((q >> 21) & 63u) - lo;
-                  reinterpret_cast<uint32_t*>(slot + BSS_MASK_OFF)[pos] = (len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo;
-                }
-              }
-            }
-            if (lane < 8) {  // identity records behind the compacted ones: the loops run in groups of 4 / 8
-              double2* dn = reinterpret_cast<double2*>(slot) + rs * (cnt + lane);
-              double2* dd = reinterpret_cast<double2*>(slot + BSS_D_OFF) + rs * (cnt + lane);
-              dn[0] = make_double2(1., 0.); dd[0] = make_double2(1., 0.);
-              if (pair) { dn[1] = make_double2(0., 0.); dd[1] = make_double2(0., 0.); }
-              reinterpret_cast<uint32_t*>(slot + BSS_MASK_OFF)[cnt + lane] = 0u;
-            }
-            if (lane == 0) *reinterpret_cast<int*>(slot + BSS_CNT_OFF) = cnt;
-          } else if (opG == BD_TILE_BEGIN) {  // Y' | u | Z (mantissa x weight, exponent) | shift prefixes of the item and of the zero row
-            const int tb = (int)(c2 >> 16) * T + lane;
-#pragma unroll
-            for (int k = 0; k < R; k++) {
-              const uint32_t nb = ((k < 2 ? e2.x : e2.y) >> (16 * (k & 1))) & 0xffffu;
-              const int j = tb + 32 * k;
-              bs_cp8(slot + (k * 32 + lane) * 8, bY + j);
-              bs_cp8(slot + 1024 + (k * 32 + lane) * 8, bU + j);
-              double2* zd = reinterpret_cast<double2*>(slot + 2048) + (k * 32 + lane);
-              if (j < m.n_slices) bs_cp16(zd, zpart + j); else *zd = make_double2(0., 0.);
-              bs_cp4(slot + 4096 + (k * 32 + lane) * 4, xk + (size_t)nb * 32);
-              bs_cp4(slot + 4608 + (k * 32 + lane) * 4, xk0 + (size_t)nb * 32);
-            }
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        const uint32_t code = c0;
-        c0 = c1; c1 = c2;
-        const unsigned char* buf = wring + s0 * BSS_SLOT_BYTES;
-        s0 = s0 == BS_NB - 1 ? 0 : s0 + 1; s2 = s2 == BS_NB - 1 ? 0 : s2 + 1; s4 = s4 == BS_NB - 1 ? 0 : s4 + 1;
-        const int op = code & 15;
-        if (op == BD_END) break;
-        const int var = (code >> 4) & 3, kk = (code >> 6) & 7;
-        if (op == BD_TILE_BEGIN) {
-          const int tb0 = (int)(code >> 16) * T + lane;
-#pragma unroll
-          for (int k = 0; k < R; k++) {
-            Y[k] = *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8);
-            U[k] = *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8);
-            const double2 z = *(reinterpret_cast<const double2*>(buf + 2048) + (k * 32 + lane));
-            const int xi = *reinterpret_cast<const int*>(buf + 4096 + (k * 32 + lane) * 4);
-            const int x0 = *reinterpret_cast<const int*>(buf + 4608 + (k * 32 + lane) * 4);
-            pd[k] = 1.; ed[k] = 0;
-            if (all_dirty) { pn[k] = b.wt[tb0 + 32 * k]; en[k] = xi; }
-            else { pn[k] = z.x; en[k] = (int)z.y + xi - x0; }
-          }
-          continue;
-        }
-        if (op == BD_TILE_END) {
-#pragma unroll
-          for (int k = 0; k < R; k++) scaled_add(Im, Ie, pn[k] / pd[k], en[k] - ed[k]);
-          continue;
-        }
-        if (op != BD_PAIR && op != BD_REC) continue;  // BS_NOP
-        const int cnt = *reinterpret_cast<const int*>(buf + BSS_CNT_OFF);
-        if (cnt == 0) continue;
-        if (op == BD_PAIR) {
-          const double4* rn = reinterpret_cast<const double4*>(buf);
-          const double4* rd = reinterpret_cast<const double4*>(buf + BSS_D_OFF);
-          if (var == BV_FULL) {
-            bs_pairs_full<R>(rn, cnt, U, pn, en);
-            if (!all_dirty) bs_pairs_full<R>(rd, cnt, U, pd, ed);
-          } else {
-#pragma unroll
-            for (int k = 0; k < R; k++)
-              if (k == kk) { pn[k] *= bs_pairs_one(rn, cnt, U[k]); if (!all_dirty) pd[k] *= bs_pairs_one(rd, cnt, U[k]); }
-          }
-        } else {
-          const double2* rn = reinterpret_cast<const double2*>(buf);
-          const double2* rd = reinterpret_cast<const double2*>(buf + BSS_D_OFF);
-          if (var == BV_FULL) {
-            bs_recs_full<R>(rn, cnt, Y, pn, en);
-            if (!all_dirty) bs_recs_full<R>(rd, cnt, Y, pd, ed);
-          } else if (var == BV_F) {
-#pragma unroll
-            for (int k = 0; k < R; k++)
-              if (k == kk) { pn[k] *= bs_recs_one(rn, cnt, Y[k]); if (!all_dirty) pd[k] *= bs_recs_one(rd, cnt, Y[k]); }
-          } else {
-            const uint32_t* mb = reinterpret_cast<const uint32_t*>(buf + BSS_MASK_OFF);
-#pragma unroll
-            for (int k = 0; k < R; k++)
-              if (k == kk) { pn[k] *= bs_recs_masked(rn, mb, cnt, Y[k], lanebit); if (!all_dirty) pd[k] *= bs_recs_masked(rd, mb, cnt, Y[k], lanebit); }
-          }
-        }
-        bs_rescale<R>(pn, en);
-        bs_rescale<R>(pd, ed);
-      }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double vm = __shfl_down_sync(0xffffffffu, Im, o);
-        const int ve = __shfl_down_sync(0xffffffffu, Ie, o);
-        scaled_add(Im, Ie, vm, ve);
-      }
-      if (lane == 0) a.unit_I[(size_t)il * G + w] = make_double2(Im, (double)Ie);
-    }
-    u = __shfl_sync(0xffffffffu, u_next, 0);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ mixture (lane = item)
 __global__ void __launch_bounds__(128) band_mixture_kernel(BandStreamArgs a) {
   const int lane = threadIdx.x & 31;
@@ -751,38 +504,17 @@ static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s)
   band_integral_kernel<R><<<grid, 32 * BS_WARPS, smem, s>>>(a);
 }
 
-template <int R>
-static void launch_integral_sparse_t(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(band_integral_sparse_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
-  const size_t smem = (size_t)BS_WARPS * bss_warp_bytes(a.m.n_words, a.b.n_int);
-  const int ctas = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (smem + 1024)));
-  const long long units = (long long)a.n_blk * 32 * a.b.G;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((long long)n_sm * ctas, (units + BS_WARPS - 1) / BS_WARPS));
-  band_integral_sparse_kernel<R><<<grid, 32 * BS_WARPS, smem, s>>>(a);
-}
-
 // all-zero row through the prune kernel: block p = 32 copies of the zero pattern under parameter vector p
 void launch_band_prune_zero_row(BandStreamArgs a, cudaStream_t s) {
   a.m.words = a.m.zero_words; a.m.n_pat_pad = 32;
   a.count = 32; a.count_pad = 32; a.item0 = 0; a.n_blk = a.t.P;
-  a.sparse = 0; a.dirty = nullptr; a.force = 1;
+  a.sparse = 0; a.force = 1;
   band_prune_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 32 * BS_WARPS, 0, s>>>(a);
 }
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s) {
   band_prune_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 32 * BS_WARPS, 0, s>>>(a);
 }
 void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s) {  // + mixture
-  if (a.sparse) {
-    if (a.b.R == 2) launch_integral_sparse_t<2>(a, n_sm, s); else launch_integral_sparse_t<4>(a, n_sm, s);
-    band_mixture_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 128, 0, s>>>(a);
-    return;
-  }
   switch (a.b.R) {
     case 2: launch_integral_t<2>(a, n_sm, s); break;
     default: launch_integral_t<4>(a, n_sm, s); break;

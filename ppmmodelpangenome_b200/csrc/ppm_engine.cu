@@ -107,7 +107,10 @@ struct ppm_engine {
   DevBuf<int> d_bs_xk[2];
   cudaEvent_t ev_bs_tables = nullptr, ev_bs_pruned[2] = {nullptr, nullptr}, ev_bs_done[2] = {nullptr, nullptr};
   DevBuf<unsigned int> d_bs_counter;
-  DevBuf<uint32_t> d_bs_blocks, d_bs_dirty[2];
+  DevBuf<uint32_t> d_bs_blocks, d_bs_op_span, d_bs_leaf_span, d_sp_off;
+  DevBuf<uint2> d_sp_recs;
+  bool sp_lists_ready = false, sp_lists_failed = false;
+  unsigned long long sp_total = 0;
   DevBuf<double2> d_bs_nodes0;    // sparse evaluation: records / shift prefixes of the all-zero row per parameter vector
   DevBuf<int> d_bs_xk0;
   bool sparse = false;            // ppm_set_sparse / PPM_SPARSE: the band kernels multiply dirty lineages only
@@ -283,9 +286,10 @@ struct ppm_engine {
     const std::vector<double2> ident{make_double2(1., 0.), make_double2(0., 0.)};
     if (band.stream) {
       d_bs_ident.upload(ident, stream);
-      d_bs_counter.alloc(3);
+      d_bs_counter.alloc(5);
       if (const char* e = std::getenv("PPM_SPARSE")) sparse = std::atoi(e) != 0;
       d_bs_blocks.upload(band.blocks, stream);
+      d_bs_op_span.upload(band.op_span, stream); d_bs_leaf_span.upload(band.leaf_span, stream);
       d_bs_unit_off.upload(band.unit_blk_off, stream);
     }
     CK(cudaStreamSynchronize(stream));
@@ -295,7 +299,20 @@ struct ppm_engine {
     bdev.slice_t = d_bslice_t.p; bdev.desc = d_bdesc.p; bdev.warp_off = d_bwarp_off.p; bdev.entries = d_bentries.p;
     bdev.rounds = d_brounds.p; bdev.n_rounds = band.n_rounds; bdev.warp_ent_off = d_bwarp_ent_off.p;
     bdev.blocks = d_bs_blocks.p; bdev.unit_blk_off = d_bs_unit_off.p;
+    bdev.op_span = d_bs_op_span.p; bdev.leaf_span = d_bs_leaf_span.p;
     use_band = true;
+  }
+  // Sparse evaluation: the term lists (pattern-only) of this shard, once per handle (band_sparse.cu).
+  void build_sparse_lists() {
+    NvtxRange r("ppm:sparse_lists");
+    sp_lists_failed = true;
+    if (band.op_span.empty() || count <= 0 || bdev.n_tiles > 256) return;
+    d_sp_off.alloc((size_t)count * bdev.n_tiles + 1);
+    sp_total = ppm::sparse_lists_count(md, bdev, count, d_sp_off.p, stream);
+    if (sp_total >= (1ull << 32)) return;  // (offsets are 32 bits)
+    d_sp_recs.alloc((size_t)std::max<unsigned long long>(sp_total, 1));
+    ppm::sparse_lists_fill(md, bdev, count, d_sp_off.p, d_sp_recs.p, stream);
+    sp_lists_ready = true; sp_lists_failed = false;
   }
   ppm::BandTables band_tables() const {
     ppm::BandTables bt{};
@@ -505,9 +522,9 @@ struct ppm_engine {
           }
           bs_blk_cap = blk_batch;
         }
-        const bool sparse_now = sparse;
+        if (sparse && !sp_lists_ready && !sp_lists_failed) build_sparse_lists();
+        const bool sparse_now = sparse && sp_lists_ready;
         if (sparse_now) {
-          for (int k = 0; k < 2; k++) d_bs_dirty[k].alloc((size_t)bs_blk_cap * ((bdev.n_int + 31) / 32) * 32);
           d_bs_nodes0.alloc((size_t)t.P * bdev.n_int * 32);
           d_bs_xk0.alloc((size_t)t.P * (bdev.n_int + 1) * 32);
         }
@@ -526,7 +543,8 @@ struct ppm_engine {
           ppm::BandStreamArgs x = sa;
           const int k = (int)(b & 1);
           x.nodes = d_bs_nodes[k].p; x.xk = d_bs_xk[k].p; x.unit_I = d_bs_unit[k].p; x.counter = d_bs_counter.p + k;
-          x.sparse = sparse_now ? 1 : 0; x.dirty = d_bs_dirty[k].p; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p;
+          x.sparse = sparse_now ? 1 : 0; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p;
+          x.lists.off = d_sp_off.p; x.lists.recs = d_sp_recs.p; x.counter2 = d_bs_counter.p + 3 + k;
           x.item0 = 32 * b * blk_batch;
           x.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b * blk_batch);
           return x;
@@ -547,6 +565,11 @@ struct ppm_engine {
             CK(cudaEventRecord(ev_bs_pruned[k ^ 1], side));
           }
           CK(cudaStreamWaitEvent(s, ev_bs_pruned[k], 0));
+          if (sparse_now) {  // the listed items first (short, many), then the dense ones; the mixture joins them
+            CK(cudaMemsetAsync(d_bs_counter.p + 3 + k, 0, sizeof(unsigned int), s));
+            ppm::launch_band_sparse(batch_args(b), n_sm, s);
+            n_launches += 1;
+          }
           ppm::launch_band_integral(batch_args(b), n_sm, s);
           CK(cudaEventRecord(ev_bs_done[k], s));
           n_launches += 3;

@@ -110,6 +110,8 @@ struct TablesDev {
   double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 
+__host__ __device__ inline bool bs_sparse_item(const ModelDev& m, long long pat) { return (long long)m.freq[pat] * 8 <= m.n_leaves; }
+
 // ---- band kernel (slice-parallel sweep for big trees; band_program.h) ------------------------------------------------
 struct BandOpDev { uint16_t lref, rref, dst, flags; };   // == ppm::BandOp
 enum { BOP_DOUBLES = 6 };  // per (parameter vector, band op): c0_l c1_l c0_r c1_r (child branch factors, see prepass_band_body),
@@ -120,6 +122,13 @@ struct BandDev {
   const uint16_t* nborn; const double* wt; const double* slice_t;
   const uint32_t* desc; const int* warp_off; const int* warp_ent_off; const uint32_t* entries;
   const uint32_t* blocks; const int* unit_blk_off;  // stream layout: descriptor blocks (band_program.h)
+  const uint32_t* op_span; const uint32_t* leaf_span;  // alive slices js0 | js1 << 16 of every internal lineage (by record index) / leaf (by bit position)
+};
+// sparse evaluation: which patterns have a term list.  Present in at most an eighth of the genomes: few dirty
+// lineages (a present leaf below), the all-zero row serves the rest; the others have few clean lineages and stay dense.
+struct SparseLists {       // pattern-only term lists, built once per handle (band_sparse.cu)
+  const uint32_t* off;     // [count * n_tiles + 1] first record of every (pattern, tile)
+  const uint2* recs;       // x: record index of an internal lineage, or leaf bit position | 1 << 31; y: s0 | s1 << 8 (slices [s0, s1) of the tile)
 };
 struct BandTables {     // one row per parameter vector, written by prepass_band
   double* bop;          // [P][n_ops][BOP_DOUBLES]
@@ -153,7 +162,8 @@ struct BandStreamArgs {
   // sparse evaluation: only the pattern's DIRTY lineages (a present leaf below) are multiplied, as a ratio
   // against the all-zero row whose per-slice integrand the prepass already has (TablesDev::zpart)
   int sparse;
-  uint32_t* dirty;             // scratch [n_blk][(n_int + 31) / 32][32]  one bit per internal lineage, written by the prune kernel
+  SparseLists lists;           // the handle's term lists
+  unsigned int* counter2;      // unit hand-out of the sparse kernel
   const double2* nodes0;       // [P][n_int][32]  lineage records of the all-zero row per parameter vector (copy 0 of 32 is read)
   const int* xk0;              // [P][n_int + 1][32]  its shift prefixes
 };
@@ -209,6 +219,10 @@ void launch_band_prune(const BandStreamArgs& a, cudaStream_t s);                
 void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);    // one batch: integral + mixture
 // sparse evaluation: records of the all-zero row for every parameter vector (a.nodes / a.xk must hold P blocks)
 void launch_band_prune_zero_row(BandStreamArgs a, cudaStream_t s);
+// term lists: count pass (cnt [count * n_tiles + 1], turned into offsets in place; returns the number of records) and fill pass
+unsigned long long sparse_lists_count(const ModelDev& m, const BandDev& b, long long count, uint32_t* cnt_off, cudaStream_t s);
+void sparse_lists_fill(const ModelDev& m, const BandDev& b, long long count, const uint32_t* off, uint2* recs, cudaStream_t s);
+void launch_band_sparse(const BandStreamArgs& a, int n_sm, cudaStream_t s);  // one batch: the items with term lists
 void launch_finalize(const double* i2, double* ll, int P, cudaStream_t s);
 void launch_sum_shards(const double* gather, int n, int P, double* out, cudaStream_t s);  // [n][P] -> [P], rank order
 void launch_gather(const double* table, const int* index, long long n, double* out, cudaStream_t s);  // out[j] = table[index[j]]
