@@ -396,8 +396,8 @@ def time_workload(D, wl, K, W, peak_tf, e2e_reps=3, check_unsharded=False, sampl
         out["sparse"] = {"value": pattern_evals / (sp_ms * 1e-3), "unit": UNIT, "ms_per_step": sp_ms, "steps": Ks,
                          "speedup_vs_dense": (total_ms / K) / sp_ms, "first_call_s": build_s,
                          "max_rel_vs_dense": float(np.max(np.abs(sparse_ll / dense_ll - 1))),
-                         "note": "ppm_set_sparse(1): patterns present in <= 1/8 of the genomes are evaluated from term lists of their dirty lineages "
-                                 "against the all-zero row (band_sparse_kernel); the others stay dense; not a roofline number"}
+                         "note": "ppm_set_sparse(1): patterns present (absent) in <= 1/8 of the genomes are evaluated from term lists of their dirty "
+                                 "lineages against the all-zero (all-ones) row (band_sparse_kernel); the others stay dense; not a roofline number"}
         inf.set_sparse(False)
     inf.close()
     del flush, d_params, d_ll, d_i2
@@ -497,8 +497,9 @@ def main():
                 "dtype": "f64", "data": "synthetic"}
         for k in ("config", "gene_evals_per_s", "wall_s_timed_region", "create_s", "generate_or_load_s", "e2e", "gpu_launches", "roofline"):
             line[k] = res[k]
-        if "sharded_vs_unsharded_rel" in res:
-            line["sharded_vs_unsharded_rel"] = res["sharded_vs_unsharded_rel"]
+        for k in ("sharded_vs_unsharded_rel", "sparse"):
+            if k in res:
+                line[k] = res[k]
         line["clocks"] = sampler.summary()
         if D.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(wl)

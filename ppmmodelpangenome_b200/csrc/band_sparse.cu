@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(128) sparse_lists_kernel(ModelDev m, BandDev b
   if ((pat & ~31ll) >= count) return;  // a warp with no pattern at all
   const int n_tiles = b.n_tiles, T = b.T, n_dw = (b.n_int + 31) / 32;
   uint32_t* dirty = dirty_scratch + (size_t)(pat >> 5) * n_dw * 32 + lane;
-  const bool live = pat < count && bs_sparse_item(m, pat);
+  const int base = pat < count ? bs_sparse_item(m, pat) : 0;  // 1: dirty = a PRESENT leaf below, 2: an ABSENT leaf below
+  const bool live = base != 0;
+  const uint32_t flip = base == 2 ? 0xffffffffu : 0u;
   uint32_t cur[SL_MAXT];
   for (int t = 0; t < n_tiles; t++) cur[t] = (FILL && live) ? cnt_off[(size_t)pat * n_tiles + t] : 0u;
   const long long pj = pat < m.n_pat_pad ? pat : 0;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(128) sparse_lists_kernel(ModelDev m, BandDev b
   };
   // present leaves
   for (int w = 0; w < m.n_words; w++) {
-    uint32_t bits = live ? words[(size_t)w * ws] : 0u;
+    uint32_t bits = live ? (words[(size_t)w * ws] ^ flip) : 0u;
     while (bits) {
       const int pos = 32 * w + __ffs(bits) - 1;
       bits &= bits - 1;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(128) sparse_lists_kernel(ModelDev m, BandDev b
   for (int i = 0; i < b.n_ops; i++) {
     const BandOpDev o = b.ops[i];
     auto child = [&](int ref, bool leaf) -> uint32_t {
-      if (leaf) return live ? (words[(size_t)(ref >> 5) * ws] >> (ref & 31)) & 1u : 0u;
+      if (leaf) return live ? ((words[(size_t)(ref >> 5) * ws] ^ flip) >> (ref & 31)) & 1u : 0u;
       const uint32_t wd = (ref >> 5) == (i >> 5) ? dacc : dirty[(size_t)(ref >> 5) * 32];
       return (wd >> (ref & 31)) & 1u;
     };
@@ -129,14 +131,16 @@ __global__ void __launch_bounds__(32 * SPW, 4) band_sparse_kernel(BandStreamArgs
     const long long pat = item - (long long)p * a.count_pad;
     const double* sc = a.t.scal + (size_t)p * SC_COUNT;
     const bool served = sc[SC_BAND] != 0. && (a.force || !(sc[SC_I2] < 0.));
-    if (pat < a.count && served && bs_sparse_item(m, pat)) {
+    const int base = (pat < a.count && served) ? bs_sparse_item(m, pat) : 0;
+    if (base != 0) {
+      const int ones = base == 2 ? 1 : 0;  // baseline row: all-zero / all-ones
       const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
       const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
-      const double2* nodes0 = a.nodes0 + (size_t)p * n_int * 32;
-      const int* xk0 = a.xk0 + (size_t)p * (n_int + 1) * 32;
+      const double2* nodes0 = a.nodes0 + ((size_t)ones * a.t.P + p) * n_int * 32;
+      const int* xk0 = a.xk0 + ((size_t)ones * a.t.P + p) * (n_int + 1) * 32;
       const double* bY = a.bt.bY + (size_t)p * b.S_pad;
       const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
-      const double2* zpart = a.t.zpart + (size_t)p * m.n_slices;
+      const double2* zpart = ones ? a.z1 + (size_t)p * b.S_pad : a.t.zpart + (size_t)p * m.n_slices;
       const uint32_t* off = a.lists.off + (size_t)pat * n_tiles;
       double Im = 0.; int Ie = 0x3fffffff;
       for (int tau = 0; tau < n_tiles; tau++) {
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(32 * SPW, 4) band_sparse_kernel(BandStreamArgs
             if (c + lane < end) {
               const uint2 r = a.lists.recs[c + lane];
               const uint32_t ref = r.x & 0x7fffffffu;
-              if (r.x >> 31) { rn = bleaf[ref * 2 + 1]; rd = bleaf[ref * 2]; }  // a listed leaf is present
+              if (r.x >> 31) { rn = bleaf[ref * 2 + 1 - ones]; rd = bleaf[ref * 2 + ones]; }  // a listed leaf differs from the baseline row
               else { rn = nodes[(size_t)ref * 32]; rd = nodes0[(size_t)ref * 32]; }
               rg = r.y;
             }

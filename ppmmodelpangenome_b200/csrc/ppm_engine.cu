@@ -111,8 +111,9 @@ struct ppm_engine {
   DevBuf<uint2> d_sp_recs;
   bool sp_lists_ready = false, sp_lists_failed = false;
   unsigned long long sp_total = 0;
-  DevBuf<double2> d_bs_nodes0;    // sparse evaluation: records / shift prefixes of the all-zero row per parameter vector
-  DevBuf<int> d_bs_xk0;
+  DevBuf<double2> d_bs_nodes0, d_bs_z1, d_bs_unit_base;  // sparse evaluation: records / shift prefixes of the all-zero and all-ones
+  DevBuf<int> d_bs_xk0;                                  // rows per parameter vector, per-slice integrand of the all-ones row
+  DevBuf<uint32_t> d_bs_ones;
   bool sparse = false;            // ppm_set_sparse / PPM_SPARSE: the band kernels multiply dirty lineages only
   DevBuf<int> d_bs_unit_off;
   int bs_blk_cap = 0;             // 32-item blocks the scratch holds
@@ -312,6 +313,11 @@ struct ppm_engine {
     if (sp_total >= (1ull << 32)) return;  // (offsets are 32 bits)
     d_sp_recs.alloc((size_t)std::max<unsigned long long>(sp_total, 1));
     ppm::sparse_lists_fill(md, bdev, count, d_sp_off.p, d_sp_recs.p, stream);
+    std::vector<uint32_t> ones((size_t)pat.n_words * 32, 0u);  // the all-ones pattern, 32 copies, word-major
+    for (int k = 0; k < tree.n_leaves; k++)
+      for (int c = 0; c < 32; c++) ones[(size_t)(k >> 5) * 32 + c] |= 1u << (k & 31);
+    d_bs_ones.upload(ones, stream);
+    CK(cudaStreamSynchronize(stream));
     sp_lists_ready = true; sp_lists_failed = false;
   }
   ppm::BandTables band_tables() const {
@@ -525,8 +531,10 @@ struct ppm_engine {
         if (sparse && !sp_lists_ready && !sp_lists_failed) build_sparse_lists();
         const bool sparse_now = sparse && sp_lists_ready;
         if (sparse_now) {
-          d_bs_nodes0.alloc((size_t)t.P * bdev.n_int * 32);
-          d_bs_xk0.alloc((size_t)t.P * (bdev.n_int + 1) * 32);
+          d_bs_nodes0.alloc((size_t)2 * t.P * bdev.n_int * 32);
+          d_bs_xk0.alloc((size_t)2 * t.P * (bdev.n_int + 1) * 32);
+          d_bs_z1.alloc((size_t)t.P * bdev.S_pad);
+          d_bs_unit_base.alloc((size_t)t.P * 32 * bdev.G);
         }
         n_band_partials = (int)(n_pat_pad / 32);
         const size_t needb = (size_t)t.P * n_band_partials;
@@ -543,17 +551,18 @@ struct ppm_engine {
           ppm::BandStreamArgs x = sa;
           const int k = (int)(b & 1);
           x.nodes = d_bs_nodes[k].p; x.xk = d_bs_xk[k].p; x.unit_I = d_bs_unit[k].p; x.counter = d_bs_counter.p + k;
-          x.sparse = sparse_now ? 1 : 0; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p;
+          x.sparse = sparse_now ? 1 : 0; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p; x.z1 = d_bs_z1.p;
           x.lists.off = d_sp_off.p; x.lists.recs = d_sp_recs.p; x.counter2 = d_bs_counter.p + 3 + k;
           x.item0 = 32 * b * blk_batch;
           x.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b * blk_batch);
           return x;
         };
-        if (sparse_now) {  // the all-zero row's records, once per call (P blocks)
+        if (sparse_now) {  // the baseline rows' records (and the all-ones row's per-slice integrand), once per call (P blocks each)
           ppm::BandStreamArgs z = sa;
-          z.nodes = d_bs_nodes0.p; z.xk = d_bs_xk0.p; z.counter = d_bs_counter.p + 2;
-          ppm::launch_band_prune_zero_row(z, side);
-          n_launches += 1;
+          z.nodes0 = d_bs_nodes0.p; z.xk0 = d_bs_xk0.p; z.z1 = d_bs_z1.p; z.unit_I = d_bs_unit_base.p; z.counter = d_bs_counter.p + 2;
+          ppm::launch_band_baseline_row(z, 0, d_bs_ones.p, n_sm, side);
+          ppm::launch_band_baseline_row(z, 1, d_bs_ones.p, n_sm, side);
+          n_launches += 3;
         }
         ppm::launch_band_prune(batch_args(0), side);
         CK(cudaEventRecord(ev_bs_pruned[0], side));

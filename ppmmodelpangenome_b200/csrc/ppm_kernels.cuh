@@ -110,7 +110,12 @@ struct TablesDev {
   double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 
-__host__ __device__ inline bool bs_sparse_item(const ModelDev& m, long long pat) { return (long long)m.freq[pat] * 8 <= m.n_leaves; }
+// sparse evaluation: 1 = term list against the all-zero row (present in at most an eighth of the genomes), 2 = against the
+// all-ones row (absent in at most an eighth), 0 = dense (too few clean lineages either way)
+__host__ __device__ inline int bs_sparse_item(const ModelDev& m, long long pat) {
+  const long long f = m.freq[pat];
+  return f * 8 <= m.n_leaves ? 1 : ((m.n_leaves - f) * 8 <= m.n_leaves ? 2 : 0);
+}
 
 // ---- band kernel (slice-parallel sweep for big trees; band_program.h) ------------------------------------------------
 struct BandOpDev { uint16_t lref, rref, dst, flags; };   // == ppm::BandOp
@@ -164,8 +169,10 @@ struct BandStreamArgs {
   int sparse;
   SparseLists lists;           // the handle's term lists
   unsigned int* counter2;      // unit hand-out of the sparse kernel
-  const double2* nodes0;       // [P][n_int][32]  lineage records of the all-zero row per parameter vector (copy 0 of 32 is read)
-  const int* xk0;              // [P][n_int + 1][32]  its shift prefixes
+  const double2* nodes0;       // [2][P][n_int][32]  lineage records of the all-zero / all-ones row per parameter vector (copy 0 of 32 is read)
+  const int* xk0;              // [2][P][n_int + 1][32]  their shift prefixes
+  double2* z1;                 // [P][S_pad]  per-slice integrand (mantissa x weight, exponent) of the all-ones row; the zero row's is TablesDev::zpart
+  int slice_out;               // != 0: the dense integral kernel serves copy 0 of every block only and stores its slices into z1
 };
 
 struct SweepArgs {
@@ -217,8 +224,9 @@ void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
 size_t band_stream_block_bytes(const BandDev& b);  // scratch per 32-item block
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s);                 // one batch: lineage records into the scratch
 void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);    // one batch: integral + mixture
-// sparse evaluation: records of the all-zero row for every parameter vector (a.nodes / a.xk must hold P blocks)
-void launch_band_prune_zero_row(BandStreamArgs a, cudaStream_t s);
+// sparse evaluation: records of the all-zero (which = 0) / all-ones (which = 1) row for every parameter vector into
+// a.nodes0 / a.xk0; for the all-ones row also its per-slice integrand into a.z1 (a.unit_I must hold P * 32 * G entries)
+void launch_band_baseline_row(BandStreamArgs a, int which, const uint32_t* ones_words, int n_sm, cudaStream_t s);
 // term lists: count pass (cnt [count * n_tiles + 1], turned into offsets in place; returns the number of records) and fill pass
 unsigned long long sparse_lists_count(const ModelDev& m, const BandDev& b, long long count, uint32_t* cnt_off, cudaStream_t s);
 void sparse_lists_fill(const ModelDev& m, const BandDev& b, long long count, const uint32_t* off, uint2* recs, cudaStream_t s);
