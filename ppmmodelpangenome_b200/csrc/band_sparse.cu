@@ -38,6 +38,8 @@ enum { SL_MAXT = 256 };  // tiles per tree the list builder supports (local coun
     if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+}  // namespace
+
 // lane = pattern.  FILL = false: cnt_off[pat * n_tiles + tile] = records; FILL = true: recs written at cnt_off[...] + running index.
 // dirty: scratch [warps][n_dw][32] one bit per internal lineage.
 template <bool FILL>
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(128) sparse_lists_kernel(ModelDev m, BandDev b
     for (int t = 0; t < n_tiles; t++) cnt_off[(size_t)pat * n_tiles + t] = live ? cur[t] : 0u;
 }
 
+namespace {
 template <int R>
 __device__ __forceinline__ void sp_rescale(double (&p)[R], int (&e)[R]) {
   int mn = __double2hiint(p[0]);
@@ -108,6 +111,7 @@ __device__ __forceinline__ void sp_rescale(double (&p)[R], int (&e)[R]) {
 
 enum { SPW = 4 };  // warps per CTA
 struct __align__(16) SpBuf { double2 n[32]; double2 d[32]; uint32_t rg[32]; };
+}  // namespace
 
 template <int R>
 __global__ void __launch_bounds__(32 * SPW, 4) band_sparse_kernel(BandStreamArgs a) {
@@ -203,7 +207,6 @@ __global__ void __launch_bounds__(32 * SPW, 4) band_sparse_kernel(BandStreamArgs
   }
 }
 
-}  // namespace
 
 unsigned long long sparse_lists_count(const ModelDev& m, const BandDev& b, long long count, uint32_t* cnt_off, cudaStream_t s) {
   if (b.n_tiles > SL_MAXT) throw std::runtime_error("sparse evaluation: too many tiles");

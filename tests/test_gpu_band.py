@@ -148,6 +148,23 @@ def test_band_kernel_penalty_and_zero_error_rates(ppm, tmp_path):
     inf.close()
 
 
+def test_sparse_evaluation_shards_add_up(ppm, tmp_path):
+    tp, pp, P, truth = _seeded(ppm, tmp_path, 1400, 200, 91)
+    one = ppm.Inference(tp, pp, dedupe=True, device=0)
+    ll, i2 = one.loglik_batch(P, return_i2=True)
+    tot = np.zeros(len(P))
+    for rk in range(2):
+        with _Env(PPM_SPARSE=1):
+            s = ppm.Inference(tp, pp, dedupe=True, device=0, shard_rank=rk, shard_world=2)
+        tot += s.loglik_batch(P)
+        s.close()
+    assert np.allclose(np.where(i2 < 0, -1e9 + i2, tot), ll, rtol=1e-12, atol=0)
+    with _Env(PPM_SPARSE=1):
+        grp = ppm.Inference(tp, pp, dedupe=True, devices=[0, 0, 0])
+    assert np.allclose(grp.loglik_batch(P), ll, rtol=1e-12, atol=0)
+    grp.close(); one.close()
+
+
 def test_band_stream_batches_are_invisible(ppm, tmp_path):
     """Stream layout: the scratch budget only sets how many items one prune/integral/mixture round serves; results are
     bitwise the same with one batch and with many (PPM_BAND_SCRATCH_MB=1: a few 32-item blocks per batch)."""

@@ -108,4 +108,9 @@ def test_north_star_tree_sizes_against_oracle(ppm, tmp_path, n, genes, cat):
     assert rel(ll[0], o["ll"]) <= RTOL, (n, ll[0], o["ll"])
     if o["i2"] > 0:
         assert np.array_equal(inf.assignCat(P[0], o["i2"]), o["cat"])
+    # the sparse evaluation (term lists against the all-zero / all-ones row) of the same handle: same bar
+    inf.set_sparse(True)
+    ll_s = inf.loglik_batch(P[:1])
+    assert rel(ll_s[0], o["ll"]) <= RTOL, (n, ll_s[0], o["ll"])
+    assert rel(ll_s[0], ll[0]) <= 1e-12
     inf.close()
