@@ -439,8 +439,12 @@ def fit_block():
 
     try:
         tree, pa = os.path.join(g, "ref_test.nwk"), os.path.join(g, "ref_test.pa.txt")
-        dt, lines, evals = run(cli, 1, tree, pa, tag="a")
-        out["configs[0]_seed1"] = {"fit_wall_s": dt, "evaluations": evals[0], "loglik": float(lines[-1].split()[-1])}
+        # process start + CUDA initialisation dominate this fit (0.3 s of kernels) and vary with the driver's state on the box
+        # (0.5 s warm, 2.5-3.7 s when the previous client has just released the GPU): three launches, the median is reported
+        runs = [run(cli, 1, tree, pa, tag="a") for _ in range(3)]
+        dt, lines, evals = sorted(runs, key=lambda r: r[0])[1]
+        out["configs[0]_seed1"] = {"fit_wall_s": dt, "fit_wall_s_runs": [r[0] for r in runs], "evaluations": evals[0],
+                                   "loglik": float(lines[-1].split()[-1])}
         ref_cli = os.path.join(ROOT, "oracle", "_ref", "inference_ref")
         if os.path.exists(ref_cli):
             dtr, lr, er = run(ref_cli, 1, tree, pa, env={"OMP_NUM_THREADS": str(len(os.sched_getaffinity(0)))}, tag="r")

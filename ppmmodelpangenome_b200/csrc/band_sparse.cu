@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(32 * SPW, 4) band_sparse_kernel(BandStreamArgs
       const int ones = base == 2 ? 1 : 0;  // baseline row: all-zero / all-ones
       const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
       const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
-      const double2* nodes0 = a.nodes0 + ((size_t)ones * a.t.P + p) * n_int * 32;
-      const int* xk0 = a.xk0 + ((size_t)ones * a.t.P + p) * (n_int + 1) * 32;
+      const double2* nodes0 = a.nodes0 + ((size_t)2 * p + ones) * n_int * 32;
+      const int* xk0 = a.xk0 + ((size_t)2 * p + ones) * (n_int + 1) * 32;
       const double* bY = a.bt.bY + (size_t)p * b.S_pad;
       const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
       const double2* zpart = ones ? a.z1 + (size_t)p * b.S_pad : a.t.zpart + (size_t)p * m.n_slices;

@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
     const long long pat = item - (long long)p * a.count_pad;
     const double* sc = a.t.scal + (size_t)p * SC_COUNT;
     // (sparse evaluation: the items with term lists belong to band_sparse_kernel)
-    if (pat < a.count && bs_served(sc, a.force) && !(a.sparse && bs_sparse_item(m, pat) != 0)) {
+    // (slice_out: the baseline rows of the sparse evaluation -- only copy 0 of the all-ones row is integrated)
+    const bool mine = a.slice_out ? pat == 32 : (pat < a.count && !(a.sparse && bs_sparse_item(m, pat) != 0));
+    if (mine && bs_served(sc, a.force)) {
       const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
       const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
       const double* bY = a.bt.bY + (size_t)p * b.S_pad;
@@ -508,19 +510,18 @@ static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s)
   band_integral_kernel<R><<<grid, 32 * BS_WARPS, smem, s>>>(a);
 }
 
-// baseline rows of the sparse evaluation through the band kernels themselves: block p = 32 copies of the all-zero / all-ones
-// pattern under parameter vector p (the prune kernel is lane = item); the all-ones row also runs the integral on copy 0
-void launch_band_baseline_row(BandStreamArgs a, int which, const uint32_t* ones_words, int n_sm, cudaStream_t s) {
-  const size_t P = (size_t)a.t.P;
-  a.m.words = which ? ones_words : a.m.zero_words; a.m.n_pat_pad = 32;
-  a.count = which ? 1 : 32; a.count_pad = 32; a.item0 = 0; a.n_blk = a.t.P;
-  a.nodes = const_cast<double2*>(a.nodes0) + (size_t)which * P * a.b.n_int * 32;
-  a.xk = const_cast<int*>(a.xk0) + (size_t)which * P * (a.b.n_int + 1) * 32;
-  a.sparse = 0; a.force = 1; a.slice_out = which;
+// Baseline rows of the sparse evaluation through the band kernels themselves.  base_words holds 64 pattern columns: 32 copies of
+// the all-zero pattern, then 32 of the all-ones pattern (the prune kernel is lane = item), so that with count_pad = 64 block 2p is
+// the zero row and block 2p + 1 the ones row of parameter vector p; the integral runs on copy 0 of the ones row only and stores
+// its per-slice integrand (slice_out).
+void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, int n_sm, cudaStream_t s) {
+  a.m.words = base_words; a.m.n_pat_pad = 64;
+  a.count = 64; a.count_pad = 64; a.item0 = 0; a.n_blk = 2 * a.t.P;
+  a.nodes = const_cast<double2*>(a.nodes0);
+  a.xk = const_cast<int*>(a.xk0);
+  a.sparse = 0; a.force = 1; a.slice_out = 1;
   band_prune_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 32 * BS_WARPS, 0, s>>>(a);
-  if (which) {
-    if (a.b.R == 2) launch_integral_t<2>(a, n_sm, s); else launch_integral_t<4>(a, n_sm, s);
-  }
+  if (a.b.R == 2) launch_integral_t<2>(a, n_sm, s); else launch_integral_t<4>(a, n_sm, s);
 }
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s) {
   band_prune_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 32 * BS_WARPS, 0, s>>>(a);

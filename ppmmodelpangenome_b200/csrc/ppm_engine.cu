@@ -313,9 +313,9 @@ struct ppm_engine {
     if (sp_total >= (1ull << 32)) return;  // (offsets are 32 bits)
     d_sp_recs.alloc((size_t)std::max<unsigned long long>(sp_total, 1));
     ppm::sparse_lists_fill(md, bdev, count, d_sp_off.p, d_sp_recs.p, stream);
-    std::vector<uint32_t> ones((size_t)pat.n_words * 32, 0u);  // the all-ones pattern, 32 copies, word-major
+    std::vector<uint32_t> ones((size_t)pat.n_words * 64, 0u);  // word-major: 32 all-zero columns, then 32 all-ones columns
     for (int k = 0; k < tree.n_leaves; k++)
-      for (int c = 0; c < 32; c++) ones[(size_t)(k >> 5) * 32 + c] |= 1u << (k & 31);
+      for (int c = 32; c < 64; c++) ones[(size_t)(k >> 5) * 64 + c] |= 1u << (k & 31);
     d_bs_ones.upload(ones, stream);
     CK(cudaStreamSynchronize(stream));
     sp_lists_ready = true; sp_lists_failed = false;
@@ -534,7 +534,7 @@ struct ppm_engine {
           d_bs_nodes0.alloc((size_t)2 * t.P * bdev.n_int * 32);
           d_bs_xk0.alloc((size_t)2 * t.P * (bdev.n_int + 1) * 32);
           d_bs_z1.alloc((size_t)t.P * bdev.S_pad);
-          d_bs_unit_base.alloc((size_t)t.P * 32 * bdev.G);
+          d_bs_unit_base.alloc((size_t)t.P * 64 * bdev.G);
         }
         n_band_partials = (int)(n_pat_pad / 32);
         const size_t needb = (size_t)t.P * n_band_partials;
@@ -557,12 +557,12 @@ struct ppm_engine {
           x.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b * blk_batch);
           return x;
         };
-        if (sparse_now) {  // the baseline rows' records (and the all-ones row's per-slice integrand), once per call (P blocks each)
+        if (sparse_now) {  // the baseline rows' records and the all-ones row's per-slice integrand, once per call, on the main
+                           // stream next to the first batch's prune on the side stream
           ppm::BandStreamArgs z = sa;
           z.nodes0 = d_bs_nodes0.p; z.xk0 = d_bs_xk0.p; z.z1 = d_bs_z1.p; z.unit_I = d_bs_unit_base.p; z.counter = d_bs_counter.p + 2;
-          ppm::launch_band_baseline_row(z, 0, d_bs_ones.p, n_sm, side);
-          ppm::launch_band_baseline_row(z, 1, d_bs_ones.p, n_sm, side);
-          n_launches += 3;
+          ppm::launch_band_baseline_rows(z, d_bs_ones.p, n_sm, s);
+          n_launches += 2;
         }
         ppm::launch_band_prune(batch_args(0), side);
         CK(cudaEventRecord(ev_bs_pruned[0], side));

@@ -169,8 +169,8 @@ struct BandStreamArgs {
   int sparse;
   SparseLists lists;           // the handle's term lists
   unsigned int* counter2;      // unit hand-out of the sparse kernel
-  const double2* nodes0;       // [2][P][n_int][32]  lineage records of the all-zero / all-ones row per parameter vector (copy 0 of 32 is read)
-  const int* xk0;              // [2][P][n_int + 1][32]  their shift prefixes
+  const double2* nodes0;       // [P][2][n_int][32]  lineage records of the all-zero / all-ones row per parameter vector (copy 0 of 32 is read)
+  const int* xk0;              // [P][2][n_int + 1][32]  their shift prefixes
   double2* z1;                 // [P][S_pad]  per-slice integrand (mantissa x weight, exponent) of the all-ones row; the zero row's is TablesDev::zpart
   int slice_out;               // != 0: the dense integral kernel serves copy 0 of every block only and stores its slices into z1
 };
@@ -224,9 +224,10 @@ void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
 size_t band_stream_block_bytes(const BandDev& b);  // scratch per 32-item block
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s);                 // one batch: lineage records into the scratch
 void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);    // one batch: integral + mixture
-// sparse evaluation: records of the all-zero (which = 0) / all-ones (which = 1) row for every parameter vector into
-// a.nodes0 / a.xk0; for the all-ones row also its per-slice integrand into a.z1 (a.unit_I must hold P * 32 * G entries)
-void launch_band_baseline_row(BandStreamArgs a, int which, const uint32_t* ones_words, int n_sm, cudaStream_t s);
+// sparse evaluation: records of the all-zero and all-ones rows for every parameter vector into a.nodes0 / a.xk0 ([P][2][...]),
+// per-slice integrand of the all-ones row into a.z1; base_words = [n_words][64] (32 zero columns, 32 all-ones columns);
+// a.unit_I must hold P * 64 * G entries
+void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, int n_sm, cudaStream_t s);
 // term lists: count pass (cnt [count * n_tiles + 1], turned into offsets in place; returns the number of records) and fill pass
 unsigned long long sparse_lists_count(const ModelDev& m, const BandDev& b, long long count, uint32_t* cnt_off, cudaStream_t s);
 void sparse_lists_fill(const ModelDev& m, const BandDev& b, long long count, const uint32_t* off, uint2* recs, cudaStream_t s);
