@@ -372,6 +372,18 @@ def time_workload(D, wl, K, W, peak_tf, e2e_reps=3, check_unsharded=False, sampl
     }
     if checked is not None:
         out["sharded_vs_unsharded_rel"] = checked
+    if not plan.get("band_stream") and wl["spec"]["genomes"] >= 256:
+        # below 1,200 genomes the dense evaluation stays on the lane-per-pattern sweep; a handle created with PPM_SPARSE=1 takes
+        # the band kernels (they carry the sparse evaluation) from 256 genomes
+        inf.close()
+        os.environ["PPM_SPARSE"] = "1"
+        try:
+            inf = Inference.from_arrays(wl["left"], wl["right"], wl["bl"], wl["rows"], dedupe=True, device=D.local,
+                                        shard_rank=D.rank, shard_world=D.world)
+        finally:
+            del os.environ["PPM_SPARSE"]
+        inf.set_sparse(False)
+        plan = inf.plan()
     if plan.get("band_stream"):
         # SEPARATE metric: the same objective with ppm_set_sparse -- dirty lineages only, as a ratio against the
         # all-zero row; the dense evaluation above stays the roofline contract.  Same inputs, same timing method.

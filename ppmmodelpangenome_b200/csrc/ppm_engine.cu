@@ -215,6 +215,9 @@ struct ppm_engine {
     // 1,500 0.50 | 0.40, 2,000 0.54 | 0.39, 3,000 0.64 | 0.39, 5,000 0.73 | 0.30 -- below ~1,200 genomes a tile of 128 slices
     // sees too many births and deaths (per-chunk overhead), above it the lane-per-pattern sweep drowns in its global scratch.
     int min_leaves = 1200;
+    // (a handle created for the sparse evaluation, PPM_SPARSE=1, takes the band kernels from 256 genomes: at 1,000 genomes the
+    // dense band kernels only match the sweep, the term lists beat both by 3.5 x)
+    if (const char* e = std::getenv("PPM_SPARSE")) { if (std::atoi(e) != 0) min_leaves = 256; }
     if (const char* e = std::getenv("PPM_BAND_MIN")) min_leaves = std::atoi(e);
     if (tree.n_leaves < min_leaves && !forced) return;
     const char* eR = std::getenv("PPM_BAND_R");
