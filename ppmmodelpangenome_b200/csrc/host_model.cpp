@@ -338,6 +338,23 @@ Patterns build_patterns(const Tree& t, const uint32_t* rows, const int32_t* coun
 
 // PAmatrix(path) (objects.cpp:164-214): first line = header (ignored) or "ccc,count,count,..."; then one
 // line per genome: name,v,v,...  Genome rows are matched to tree leaves by name (objects.cpp:240-249).
+// 32 x 32 bit transpose: out[j] bit i = in[i] bit j
+static void transpose32(const uint32_t* in, uint32_t* out) {
+  uint32_t a[32];
+  std::memcpy(a, in, sizeof(a));
+  for (int j = 16, m = 0x0000ffff; j; j >>= 1, m ^= m << j)
+    for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+      const uint32_t tt = ((a[k] >> j) ^ a[k + j]) & (uint32_t)m;
+      a[k] ^= tt << j;
+      a[k + j] ^= tt;
+    }
+  std::memcpy(out, a, sizeof(a));
+}
+
+// The matrix file is read one genome line at a time (2 MB per line at 1 M genes; the file is never held whole).  A genome's
+// values are packed ALONG THE GENES (sequential writes: 8 text bytes "v,v,v,v," become 4 bits with one multiply); once every
+// line is in, 32 x 32 bit tiles are transposed into the gene-major rows the patterns are built from.  The previous reader set one
+// bit per present value at a 628-byte stride (1.3e9 read-modify-writes for 5,000 genomes x 1 M genes).
 int64_t read_matrix_rows(const Tree& t, const std::string& path, std::vector<uint32_t>& rows, std::vector<int32_t>& counts) {
   std::ifstream f(path);
   if (!f) throw std::runtime_error("cannot open matrix file " + path);
@@ -357,7 +374,8 @@ int64_t read_matrix_rows(const Tree& t, const std::string& path, std::vector<uin
   for (int k = 0; k < t.n_leaves; k++) leaf_of[t.label[t.leaf_node[k]]] = k;
   const int nw = (t.n_leaves + 31) / 32;
   rows.clear();
-  int64_t n_genes = -1;
+  int64_t n_genes = -1, gw = 0;
+  std::vector<uint32_t> gm;  // genome-major bits: [nw * 32][gw], bit g & 31 of word g >> 5 = the genome's value for gene g
   std::vector<char> seen(t.n_leaves, 0);
   while (std::getline(f, line)) {
     strip(line);
@@ -367,47 +385,53 @@ int64_t read_matrix_rows(const Tree& t, const std::string& path, std::vector<uin
     std::string name = line.substr(0, c);
     auto it = leaf_of.find(name);
     const char* p = line.c_str() + c + 1;
+    const char* const end = line.c_str() + line.size();
     // count values on the first data line
     if (n_genes < 0) {
       n_genes = 1;
       for (const char* q = p; *q; q++) n_genes += (*q == ',');
-      rows.assign((size_t)n_genes * nw, 0u);
+      gw = (n_genes + 31) / 32;
+      gm.assign((size_t)nw * 32 * gw, 0u);
     }
     // A genome that is no leaf of the tree: the reference keeps such a row in `matrix`, where it changes freq[], meanGenes (hence
     // the optimiser's bounds and start) and pattern identity, and leaves mrca uninitialised (functions.cpp:51,64,117-127).  Nothing
     // sensible can be reproduced from that, so the input is rejected.
     if (it == leaf_of.end()) throw std::runtime_error("matrix: genome row '" + name + "' is not a leaf of the tree");
-    int k = it->second;
-    if (seen[k]) {  // a later row with the same name wins (std::map assignment, objects.cpp:195)
-      for (int64_t g = 0; g < n_genes; g++) rows[(size_t)g * nw + (k >> 5)] &= ~(1u << (k & 31));
-    }
+    const int k = it->second;
+    uint32_t* dst = gm.data() + (size_t)k * gw;
+    if (seen[k]) std::fill(dst, dst + gw, 0u);  // a later row with the same name wins (std::map assignment, objects.cpp:195)
     seen[k] = 1;
     int64_t g = 0;
-    // fast path: single-digit values separated by commas (what the reference's R scripts write); anything else falls
-    // through to the general strtol loop below at the position reached
-    {
-      uint32_t* col = rows.data() + (k >> 5);
-      const uint32_t bit = 1u << (k & 31);
-      while (g < n_genes && (p[0] == '0' || p[0] == '1') && (p[1] == ',' || p[1] == '\0')) {
-        if (p[0] == '1') col[(size_t)g * nw] |= bit;
-        g++;
-        if (p[1] == '\0') { p += 1; break; }
-        p += 2;
-      }
-      if (*p == '\0' && g > 0) {
-        if (g != n_genes) throw std::runtime_error("matrix: row " + name + " is shorter than the first row");
-        continue;
-      }
+    // fast path: single-digit values separated by commas (what the reference's R scripts write), four values per 8 bytes;
+    // anything else falls through to the general strtol loop below at the position reached
+    while (g + 4 <= n_genes && end - p >= 8) {
+      uint64_t x;
+      std::memcpy(&x, p, 8);
+      if ((x & 0xfffefffefffefffeull) != 0x2c302c302c302c30ull) break;  // "[01],[01],[01],[01],"
+      const uint64_t nib = (((x & 0x0001000100010001ull) * 0x0001000200040008ull) >> 48) & 0xfull;
+      dst[g >> 5] |= (uint32_t)nib << (g & 31);  // (g is a multiple of 4 here: the nibble never straddles a word)
+      g += 4;
+      p += 8;
+    }
+    while (g < n_genes && (p[0] == '0' || p[0] == '1') && (p[1] == ',' || p[1] == '\0')) {
+      if (p[0] == '1') dst[g >> 5] |= 1u << (g & 31);
+      g++;
+      if (p[1] == '\0') { p += 1; break; }
+      p += 2;
+    }
+    if (*p == '\0' && g > 0) {
+      if (g != n_genes) throw std::runtime_error("matrix: row " + name + " is shorter than the first row");
+      continue;
     }
     while (true) {
-      char* end;
-      long v = strtol(p, &end, 10);
-      if (end == p) throw std::runtime_error("matrix: empty value in row " + name);
+      char* e2;
+      long v = strtol(p, &e2, 10);
+      if (e2 == p) throw std::runtime_error("matrix: empty value in row " + name);
       if (v != 0 && v != 1) throw std::runtime_error("matrix: values must be 0 or 1 (row " + name + ")");
       if (g >= n_genes) throw std::runtime_error("matrix: row " + name + " is longer than the first row");
-      if (v) rows[(size_t)g * nw + (k >> 5)] |= 1u << (k & 31);
+      if (v) dst[g >> 5] |= 1u << (g & 31);
       g++;
-      if (*end == ',') p = end + 1; else break;
+      if (*e2 == ',') p = e2 + 1; else break;
     }
     if (g != n_genes) throw std::runtime_error("matrix: row " + name + " is shorter than the first row");
   }
@@ -415,6 +439,18 @@ int64_t read_matrix_rows(const Tree& t, const std::string& path, std::vector<uin
   for (int k = 0; k < t.n_leaves; k++)
     if (!seen[k]) throw std::runtime_error("matrix: no row for tree leaf '" + t.label[t.leaf_node[k]] + "'");
   if (!counts.empty() && (int64_t)counts.size() != n_genes) throw std::runtime_error("matrix: ccc header length differs from the rows");
+  // gene-major rows: rows[g][w] bit i = genome 32 w + i
+  rows.assign((size_t)n_genes * nw, 0u);
+  uint32_t tin[32], tout[32];
+  for (int w = 0; w < nw; w++)
+    for (int64_t gb = 0; gb < gw; gb++) {
+      uint32_t any = 0;
+      for (int i = 0; i < 32; i++) { tin[i] = gm[((size_t)w * 32 + i) * gw + gb]; any |= tin[i]; }
+      if (!any) continue;
+      transpose32(tin, tout);
+      const int64_t g1 = std::min<int64_t>(32, n_genes - 32 * gb);
+      for (int64_t j = 0; j < g1; j++) rows[(size_t)(32 * gb + j) * nw + w] = tout[j];
+    }
   return n_genes;
 }
 

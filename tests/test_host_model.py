@@ -155,3 +155,37 @@ def test_ccc_writer_round_trip_on_the_host(golden, tmp_path):
     names, M, counts = model.read_matrix(out)
     assert M.shape[1] == a.nRep and list(counts) == list(a.counts)
     a.close(); b.close()
+
+
+def test_matrix_reader_packed_fast_path_and_general_path_agree(tmp_path):
+    """The reader packs "v,v,v,v," eight text bytes at a time and transposes 32 x 32 bit tiles; rows it cannot take that way
+    (leading zeros, CRLF) go through strtol.  Sizes that are multiples of neither 4 nor 32, genome lines in shuffled order."""
+    rng = np.random.default_rng(3)
+    n, genes = 37, 1003
+    from ppmmodelpangenome_b200 import simulate
+    nwk = simulate.sim_tree(n, rng)
+    names = ["g%d" % (k + 1) for k in range(n)]
+    left, right, bl, labels = simulate.parse_newick(nwk)
+    leaves = [labels[v] for v in range(len(left)) if left[v] < 0]
+    M = (rng.random((n, genes)) < 0.3).astype(np.uint8)
+    M[:, M.sum(axis=0) == 0] = 1
+    order = rng.permutation(n)
+    tp, pp = tmp_path / "t.nwk", tmp_path / "m.txt"
+    tp.write_text(nwk + "\n")
+    with open(pp, "w") as f:
+        f.write("genome," + ",".join("c%d" % j for j in range(genes)) + "\n")
+        for k in order:
+            vals = [str(v) for v in M[k]]
+            if k % 5 == 0:
+                vals[7] = "0" + vals[7]            # a leading zero: the general path takes over mid-line
+            f.write(leaves[k] + "," + ",".join(vals) + ("\r\n" if k % 3 == 0 else "\n"))
+    inf = ppm.Inference(str(tp), str(pp), dedupe=False, device=-1)
+    assert inf.nRep == genes and inf.nLeaves == n
+    assert np.array_equal(inf.freq, M.sum(axis=0))
+    uniq = ppm.Inference(str(tp), str(pp), dedupe=True, device=-1)
+    cols = {}
+    for j in range(genes):
+        cols.setdefault(M[:, j].tobytes(), len(cols))
+    assert uniq.nRep == len(cols)
+    assert np.array_equal(uniq.gene_to_pattern, [cols[M[:, j].tobytes()] for j in range(genes)])
+    inf.close(); uniq.close()
