@@ -7,6 +7,8 @@ enum {
   BD_REC = 2,    // 16-byte records (a, nbn): internal lineages (node array) and single leaves (entry bit 31), factor a + nbn Y'
   BD_PAIR = 4,   // 32-byte records: a static leaf pair as one quadratic in u
   BD_END = 5,
+  BD_TILE_LP = 3,  // leaf-power program (band_program.h: leaf_pow): the tile's slices multiply in the product of ALL alive leaves as
+                   // one power per slice; variant 1 (first, only with leaf heights != 0): height tables, variant 0: count tables
   BV_FULL = 0, BV_F = 1, BV_M = 2   // variant: every register / register k, all lanes / register k, lanes [lo, hi)
 };
 enum { kBandStreamChunk = 64, kBandBlockWords = 68 };  // stream layout: records per chunk (two per lane); the one-CTA layout uses 32

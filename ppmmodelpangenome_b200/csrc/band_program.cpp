@@ -19,7 +19,7 @@ inline uint32_t desc_code(int op, int variant, int k, int count) {
 }
 }  // namespace
 
-BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, bool stream) {
+BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, bool stream, bool leaf_pow) {
   BandProgram bp;
   bp.R = R; bp.G = G; bp.T = 32 * R; bp.stream = stream;
   const int nn = t.n_nodes, nl = t.n_leaves, S = t.n_slices, T = bp.T;
@@ -27,6 +27,11 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
   if (nn > 65535) { bp.why = "more than 65,535 nodes"; return bp; }
   if (nl < 4 || S < 1) { bp.why = "tree too small"; return bp; }
   if (R < 1 || R > 8 || G < 1 || G > (stream ? 4096 : 32)) { bp.why = "bad R/G"; return bp; }
+  for (int k = 0; k < nl; k++) bp.max_leaf_h = std::max(bp.max_leaf_h, std::fabs(t.height[t.leaf_node[k]]));
+  // leaf powers: stream layout only, and only when the leaf heights are rounding noise of the tree file (the height correction is
+  // first order; the prepass checks n (lam max_h)^2 per parameter vector)
+  bp.leaf_pow = leaf_pow && stream && bp.max_leaf_h <= 1e-8 * t.H;
+  bp.has_s1 = bp.leaf_pow && bp.max_leaf_h > 0.;
 
   // alive slice range of every non-root lineage (functions.cpp:130-141, 250-262), as in build_program
   std::vector<int> js0(nn, S), js1(nn, S);
@@ -62,6 +67,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     op.flags = (uint16_t)((ll ? 1 : 0) | (rl ? 2 : 0));
     bp.ops.push_back(op);
     bp.op_nodes.push_back(v); bp.op_nodes.push_back(l); bp.op_nodes.push_back(r);
+    bp.op_leaf_h.push_back(ll ? t.height[l] : 0.); bp.op_leaf_h.push_back(rl ? t.height[r] : 0.);
   }
   bp.lev_off.push_back((int)by_level.size());
   bp.n_levels = (int)bp.lev_off.size() - 1;
@@ -93,12 +99,24 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     }
   }
 
+  if (bp.leaf_pow) {
+    bp.n_alive_leaves.assign(bp.S_pad, 0);
+    bp.htot.assign(bp.S_pad, 0.);
+    bp.leaf_h.assign(nl, 0.);
+    for (int v = 1; v < nn; v++) {
+      if (t.left[v] >= 0) continue;
+      bp.leaf_h[dpos(v)] = t.height[v];
+      for (int j = js0[v]; j < js1[v]; j++) { bp.n_alive_leaves[j]++; bp.htot[j] += t.height[v]; }
+    }
+  }
+
   // per tile: classify every lineage that is alive somewhere in it
   std::vector<TileLists> tiles(bp.n_tiles);
   for (auto& tl : tiles) { tl.f_int.resize(R); tl.f_leaf.resize(R); tl.m_int.resize(R); tl.m_leaf.resize(R); }
   for (int v = 1; v < nn; v++) {
     if (js0[v] >= js1[v]) continue;
     const bool leaf = t.left[v] < 0;
+    if (leaf && bp.leaf_pow) continue;  // the leaves enter as one power per slice
     const int ref = leaf ? dpos(v) : idx[v];
     for (int tau = js0[v] / T; tau <= (js1[v] - 1) / T; tau++) {
       const int s0 = std::max(js0[v], tau * T) - tau * T, s1 = std::min(js1[v], (tau + 1) * T) - tau * T;
@@ -169,6 +187,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     }
     tcost[tau] += 12.0 * R + 60.;  // tile begin / end
     fp64_warp += 3.0 * R;
+    if (bp.leaf_pow) { tcost[tau] += 30.0 * R + 60.; fp64_warp += 20.0 * R; }
   }
 
   // tiles -> warps: longest-processing-time-first (the tiles near the leaves are the big ones), then ascending per warp.
@@ -191,6 +210,8 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     std::sort(mine[w].begin(), mine[w].end());
     for (int tau : mine[w]) {
       bp.desc.push_back(desc_code(BD_TILE_BEGIN, 0, 0, 0) | ((uint32_t)tau << 16));
+      if (bp.has_s1) bp.desc.push_back(desc_code(BD_TILE_LP, 1, 0, 0) | ((uint32_t)tau << 16));
+      if (bp.leaf_pow) bp.desc.push_back(desc_code(BD_TILE_LP, 0, 0, 0) | ((uint32_t)tau << 16));
       for (const Chunk& c : tchunks[tau]) {
         bp.desc.push_back(c.code);
         bp.entries.insert(bp.entries.end(), c.ents.begin(), c.ents.end());
@@ -223,7 +244,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
         if (op == BD_REC || op == BD_PAIR) {
           std::copy(bp.entries.begin() + eoff, bp.entries.begin() + eoff + kBandStreamChunk, blk.begin());
           eoff += kBandStreamChunk;
-        } else if (op == BD_TILE_BEGIN) {
+        } else if (op == BD_TILE_BEGIN || op == BD_TILE_LP) {
           const int tau = (int)(code >> 16);
           for (int l = 0; l < 32; l++) {
             uint32_t h[4] = {0, 0, 0, 0};

@@ -49,12 +49,24 @@ struct BandProgram {
   std::vector<int32_t> unit_blk_off;  // [G] first block of each unit's list
   std::vector<uint32_t> op_span, leaf_span;  // stream layout: alive slices js0 | js1 << 16 per internal lineage / per leaf bit (sparse lists)
   std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 | leaf << 31 (M records: lanes [lo, hi), hi in 1..32)
+  // Leaf-power program (stream layout only).  Every leaf of an ultrametric tree sits at height 0, so at slice j a leaf observed x
+  // contributes f_x(u_j) whatever the leaf: the product over the alive leaves is f_0^n0 f_1^n1 with n1 = the number of PRESENT
+  // alive leaves of the pattern -- one exp2 per slice instead of one record per leaf (pair) and tile.  The lists then hold internal
+  // lineages only; the prune kernel counts the present leaves that have died before every op (and, when the leaf heights are only
+  // numerically 0, the sum of their heights: first-order correction), the integral kernel turns the counts into the power.
+  bool leaf_pow = false;
+  bool has_s1 = false;              // some leaf height != 0: the first-order height correction is carried along
+  std::vector<int32_t> n_alive_leaves;  // [S_pad] leaves alive at each slice
+  std::vector<double> htot;             // [S_pad] sum of the heights of the leaves alive at each slice
+  std::vector<double> op_leaf_h;        // [n_ops][2] heights of an op's leaf children (0 for an internal child)
+  std::vector<double> leaf_h;           // [n_leaves] height by device bit position
+  double max_leaf_h = 0;
   double fp64_instr_per_eval = 0;   // modelled FP64 instructions per pattern-eval (phase A + phase B)
   double cost_max = 0, cost_sum = 0;  // modelled phase B cost of the busiest warp / of all warps (balance = sum / (G max))
   long long n_full16 = 0, n_full32 = 0, n_f16 = 0, n_f32 = 0, n_m16 = 0;
 };
 
 // pg: the handle's sweep program (it fixes the device bit positions of the leaves and the static pairs).
-BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, bool stream = false);
+BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, bool stream = false, bool leaf_pow = false);
 
 }  // namespace ppm

@@ -62,8 +62,8 @@ enum { BP_PF = 3, BP_OC = 2049 };  // request distance; op records staged per CT
 static_assert(BP_OC % BP_PF == 0, "slots keep their phase across chunks");
 __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArgs a) {
   __shared__ uint2 ops_s[BP_OC + 8];  // op records as raw words: lref | rref << 16, dst | flags << 16
-  // branch constants of the warp's parameter vector, 32 ops at a time, double-buffered by cp.async (3 x 16 bytes per op)
-  __shared__ __align__(16) double2 cst_s[BS_WARPS][2][32 * 3];
+  // branch constants of the warp's parameter vector, 32 ops at a time, double-buffered by cp.async (4 x 16 bytes per op)
+  __shared__ __align__(16) double2 cst_s[BS_WARPS][2][32 * 4];
   const int lane = threadIdx.x & 31;
   const int blk = blockIdx.x * BS_WARPS + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.counter = 0u;  // the integral kernel of this batch follows on the same stream
@@ -83,6 +83,13 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
   int* xk = a.xk + (size_t)(active ? blk : 0) * (n_int + 1) * 32 + lane;
   if (active) xk[0] = 0;
   int run = 0;
+  // leaf powers: the present leaves that have died before each op (and the sum of their heights) travel with the shift prefixes
+  const bool lp = a.b.lp != 0, hs1 = a.b.has_s1 != 0;
+  int* n1k = a.n1k + (size_t)(active ? blk : 0) * (n_int + 1) * 32 + lane;
+  double* s1k = a.s1k + (size_t)(active && hs1 ? blk : 0) * (n_int + 1) * 32 + lane;
+  int n1d = 0;
+  double s1d = 0.;
+  if (active && lp) { n1k[0] = 0; if (hs1) s1k[0] = 0.; }
 
   // circular buffer of BP_PF slots with compile-time indices (the loop body is unrolled BP_PF times): slot s holds the
   // requested operands of op j (j % BP_PF == s); once op j has read them the slot is refilled for op j + BP_PF.  Nothing that
@@ -108,9 +115,10 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
   auto stage_consts = [&](int chunk) {  // ops [32 chunk, 32 chunk + 32) of this warp's parameter vector -> buffer chunk & 1
     const int j = 32 * chunk + lane;
     if (j < n_ops) {
-      double2* dst = cst + (chunk & 1) * 96 + 3 * lane;
-      const double2* src = bop + 3 * (size_t)j;
+      double2* dst = cst + (chunk & 1) * 128 + 4 * lane;
+      const double2* src = bop + 4 * (size_t)j;
       bs_cp16(dst, src); bs_cp16(dst + 1, src + 1); bs_cp16(dst + 2, src + 2);
+      if (lp) bs_cp16(dst + 3, src + 3);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -139,19 +147,25 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
             __syncwarp();
             stage_consts((j >> 5) + 1);
           }
-          const double2* cj = cst + ((j >> 5) & 1) * 96 + 3 * (j & 31);
+          const double2* cj = cst + ((j >> 5) & 1) * 128 + 4 * (j & 31);
           const double2 k01 = cj[0], k23 = cj[1], k4 = cj[2];
           // operands of op j out of the slot
           const int lref = (int)(so[sl].x & 0xffffu), rref = (int)(so[sl].x >> 16), flags = (int)(so[sl].y >> 16);
           double2 Lc, Rc;
-          if (flags & 1) Lc = ((wl[sl] >> (lref & 31)) & 1u) ? leaf1 : leaf0;
-          else {
+          if (flags & 1) {
+            const bool b1 = ((wl[sl] >> (lref & 31)) & 1u) != 0u;
+            Lc = b1 ? leaf1 : leaf0;
+            if (lp) { n1d += b1 ? 1 : 0; if (hs1) s1d += b1 ? k4.y : 0.; }
+          } else {
             Lc = nl[sl];
 #pragma unroll
             for (int k = 0; k < BP_PF; k++) if (lref == j - 1 - k) Lc = prev[k];
           }
-          if (flags & 2) Rc = ((wr[sl] >> (rref & 31)) & 1u) ? leaf1 : leaf0;
-          else {
+          if (flags & 2) {
+            const bool b1 = ((wr[sl] >> (rref & 31)) & 1u) != 0u;
+            Rc = b1 ? leaf1 : leaf0;
+            if (lp) { n1d += b1 ? 1 : 0; if (hs1) s1d += b1 ? cj[3].x : 0.; }
+          } else {
             Rc = nr[sl];
 #pragma unroll
             for (int k = 0; k < BP_PF; k++) if (rref == j - 1 - k) Rc = prev[k];
@@ -167,6 +181,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS) band_prune_kernel(BandStreamArg
           nodes[(size_t)j * 32] = rec;  // stream layout: op j writes record j (birth order)
           run += k;
           xk[(size_t)(j + 1) * 32] = run;
+          if (lp) { n1k[(size_t)(j + 1) * 32] = n1d; if (hs1) s1k[(size_t)(j + 1) * 32] = s1d; }
 #pragma unroll
           for (int q = BP_PF - 1; q > 0; q--) prev[q] = prev[q - 1];
           prev[0] = rec;
@@ -325,15 +340,26 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
       const double* bU = a.bt.bU + (size_t)p * b.S_pad;
       const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
       const double4* pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
+      const bool lp = b.lp != 0;
+      const int* n1k = a.n1k + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
+      const double* s1k = a.s1k + (size_t)(b.has_s1 ? (il >> 5) : 0) * (n_int + 1) * 32 + (il & 31);
+      const double* bLb = a.bt.bLb + (size_t)p * b.S_pad;
+      const double* bLc = a.bt.bLc + (size_t)p * b.S_pad;
+      const double* bLe = a.bt.bLe + (size_t)p * b.S_pad;
+      int n1_0 = 0;
+      double s1_0 = 0.;
+      if (lp) { n1_0 = a.n1_0[pat]; if (b.has_s1) s1_0 = a.s1_0[pat]; }
       __syncwarp();  // (the previous unit's reads of pw are done)
-      for (int x = lane; x < m.n_words; x += 32) pw[x] = m.words[(size_t)x * m.n_pat_pad + pat];
-      if (lane == 0) pw[m.n_words] = 0u;
+      if (!lp) {     // (a leaf-power program gathers no leaf records: no pattern bits needed)
+        for (int x = lane; x < m.n_words; x += 32) pw[x] = m.words[(size_t)x * m.n_pat_pad + pat];
+        if (lane == 0) pw[m.n_words] = 0u;
+      }
 
       const unsigned char* blocks = reinterpret_cast<const unsigned char*>(b.blocks) + (size_t)b.unit_blk_off[w] * BS_BLK_BYTES;
-      double prod[R], Y[R], U[R];
+      double prod[R], Y[R], U[R], lpacc[R];
       int ex[R];
 #pragma unroll
-      for (int k = 0; k < R; k++) { prod[k] = 1.; Y[k] = 0.; U[k] = 0.; ex[k] = 0; }
+      for (int k = 0; k < R; k++) { prod[k] = 1.; Y[k] = 0.; U[k] = 0.; ex[k] = 0; lpacc[k] = 0.; }
       double Im = 0.; int Ie = 0x3fffffff;
       int tau = 0;
       uint32_t c0 = BS_NOP, c1 = BS_NOP;  // codes of descriptors di (compute stage) and di + 1
@@ -394,6 +420,21 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
               bs_cp8(slot + 1024 + (k * 32 + lane) * 8, bU + tb + 32 * k);
               bs_cp4(slot + 2048 + (k * 32 + lane) * 4, xk + (size_t)nb * 32);
             }
+          } else if (opG == BD_TILE_LP) {  // leaf powers: count tables | dead present leaves (variant 0), height tables (variant 1)
+            const int tb = (int)(c2 >> 16) * T + lane;
+            const bool heights = ((c2 >> 4) & 3u) != 0u;
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+              const uint32_t nb = ((k < 2 ? e2.x : e2.y) >> (16 * (k & 1))) & 0xffffu;
+              if (heights) {
+                bs_cp8(slot + (k * 32 + lane) * 8, bLe + tb + 32 * k);
+                bs_cp8(slot + 1024 + (k * 32 + lane) * 8, s1k + (size_t)nb * 32);
+              } else {
+                bs_cp8(slot + (k * 32 + lane) * 8, bLb + tb + 32 * k);
+                bs_cp8(slot + 1024 + (k * 32 + lane) * 8, bLc + tb + 32 * k);
+                bs_cp4(slot + 2048 + (k * 32 + lane) * 4, n1k + (size_t)nb * 32);
+              }
+            }
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -413,6 +454,25 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
             Y[k] = *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8);
             U[k] = *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8);
             ex[k] = *reinterpret_cast<const int*>(buf + 2048 + (k * 32 + lane) * 4);
+          }
+          continue;
+        }
+        if (op == BD_TILE_LP) {
+          if (var) {  // heights first: S1 (g_1 - g_0)
+#pragma unroll
+            for (int k = 0; k < R; k++)
+              lpacc[k] = *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8) * (s1_0 - *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8));
+          } else {
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+              const int n1 = n1_0 - *reinterpret_cast<const int*>(buf + 2048 + (k * 32 + lane) * 4);
+              const double s2 = fma((double)n1, *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8),
+                                    *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8)) + lpacc[k];
+              int kx;
+              prod[k] *= lp_pow2(s2, kx);
+              ex[k] -= kx;
+              lpacc[k] = 0.;
+            }
           }
           continue;
         }
@@ -488,9 +548,25 @@ __global__ void __launch_bounds__(128) band_mixture_kernel(BandStreamArgs a) {
   if (lane == 0) a.partial[(size_t)p * (a.count_pad / 32) + pat0 / 32] = v;
 }
 
+// leaf powers, once per handle: sum of the heights of every pattern's present leaves
+__global__ void leaf_height_sums_kernel(ModelDev m, const double* leaf_h, long long count, double* s1_0) {
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pat >= count) return;
+  double s = 0.;
+  for (int w = 0; w < m.n_words; w++) {
+    uint32_t x = m.words[(size_t)w * m.n_pat_pad + pat];
+    while (x) { const int bq = __ffs((int)x) - 1; x &= x - 1u; s += leaf_h[32 * w + bq]; }
+  }
+  s1_0[pat] = s;
+}
+void launch_leaf_height_sums(const ModelDev& m, const double* leaf_h, long long count, double* s1_0, cudaStream_t s) {
+  if (count > 0) leaf_height_sums_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(m, leaf_h, count, s1_0);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 size_t band_stream_block_bytes(const BandDev& b) {  // scratch per 32-item block
-  return (size_t)b.n_int * 32 * sizeof(double2) + (size_t)(b.n_int + 1) * 32 * sizeof(int) + (size_t)32 * b.G * sizeof(double2);
+  return (size_t)b.n_int * 32 * sizeof(double2) + (size_t)(b.n_int + 1) * 32 * sizeof(int) + (size_t)32 * b.G * sizeof(double2) +
+         (b.lp ? (size_t)(b.n_int + 1) * 32 * sizeof(int) : 0) + (b.has_s1 ? (size_t)(b.n_int + 1) * 32 * sizeof(double) : 0);
 }
 
 template <int R>
@@ -514,8 +590,10 @@ static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s)
 // the all-zero pattern, then 32 of the all-ones pattern (the prune kernel is lane = item), so that with count_pad = 64 block 2p is
 // the zero row and block 2p + 1 the ones row of parameter vector p; the integral runs on copy 0 of the ones row only and stores
 // its per-slice integrand (slice_out).
-void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, int n_sm, cudaStream_t s) {
+void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, const int* base_n1, const double* base_s1, int n_sm, cudaStream_t s) {
   a.m.words = base_words; a.m.n_pat_pad = 64;
+  a.n1_0 = base_n1; a.s1_0 = base_s1;
+  a.n1k = const_cast<int*>(a.n1k0); a.s1k = const_cast<double*>(a.s1k0);
   a.count = 64; a.count_pad = 64; a.item0 = 0; a.n_blk = 2 * a.t.P;
   a.nodes = const_cast<double2*>(a.nodes0);
   a.xk = const_cast<int*>(a.xk0);

@@ -198,7 +198,8 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     sc[SC_FACTORED] = (pi1 > 0.95) ? 1. : 0.;
     // band kernel (big trees): expanded leaf-pair quadratics need pi1 <= 0.95, and its exp tables are taken relative to
     // the mid-height of the tree, so lam * H / 2 must stay well inside the double range
-    sc[SC_BAND] = (pi1 <= 0.95 && lam * m.H * 0.5 < 600.) ? 1. : 0.;
+    // (leaf-power program: the leaf heights enter to first order only)
+    sc[SC_BAND] = (pi1 <= 0.95 && lam * m.H * 0.5 < 600. && (double)m.n_leaves * (lam * m.lp_max_h) * (lam * m.lp_max_h) <= 1e-12) ? 1. : 0.;
     sc[SC_I2] = 1.;  // placeholder until prepass_i2 (the zero-row sweep must run regardless)
     sc[SC_IZ_M] = 0.; sc[SC_IZ_E] = 0.;
     z0[0] = 0.; z1[0] = 0.;
@@ -368,12 +369,32 @@ PPM_HD void prepass_band_body(const ModelDev& m, const TablesDev& t, const BandD
     child(l, o[0], o[1]);
     child(r, o[2], o[3]);
     o[4] = -exp(lam * (m.height[v] - T0));
-    o[5] = 0.;
+    o[5] = b.lp ? b.op_leaf_h[2 * i] : 0.;
+    o[6] = b.lp ? b.op_leaf_h[2 * i + 1] : 0.;
+    o[7] = 0.;
   } else if (i < b.n_ops + b.S_pad) {
     const int j = i - b.n_ops;
     const double tj = b.slice_t[j];
     bt.bY[(size_t)p * b.S_pad + j] = pi1 * exp(-lam * (tj - T0));
     bt.bU[(size_t)p * b.S_pad + j] = 1. - exp(-lam * tj);
+    if (b.lp) {
+      // Leaf powers.  A leaf at height h observed x contributes f_x = m0_x + pi1 d_x (1 - exp(-lam (t - h))) (functions.cpp:232-240);
+      // at h = 0 that is the same for every leaf, and to first order in h: log2 f_x(t; h) = log2 f_x(t; 0) + g_x(t) h,
+      // g_x = -pi1 d_x lam exp(-lam t) / (f_x ln 2).  Product over the alive leaves (n1 present, heights summing to S1 over the
+      // present ones): 2^(bLb + n1 bLc + S1 bLe).
+      const double E = exp(-lam * tj), u = 1. - E;
+      double lg[2], g[2];
+      for (int x = 0; x < 2; x++) {
+        const double m0 = x ? e1 : 1 - e1, m1 = x ? 1 - e2 : e2, d = m1 - m0;  // objects.cpp:407-408
+        const double f = fma(pi1 * d, u, m0);
+        lg[x] = f > 0. ? log2(f) : -1e7;  // (an impossible observation: any such leaf sends the product to 0)
+        g[x] = f > 0. ? -pi1 * d * lam * E / (f * 0.693147180559945309417232) : 0.;
+      }
+      const bool real = j < m.n_slices;
+      bt.bLb[(size_t)p * b.S_pad + j] = real ? (double)b.n_alive_leaves[j] * lg[0] + g[0] * b.htot[j] : 0.;
+      bt.bLc[(size_t)p * b.S_pad + j] = real ? lg[1] - lg[0] : 0.;
+      bt.bLe[(size_t)p * b.S_pad + j] = real ? g[1] - g[0] : 0.;
+    }
   } else if (i < b.n_ops + b.S_pad + m.n_leaves) {
     const int pos = i - b.n_ops - b.S_pad;
     const double hs = m.height[m.leaf_node[pos]];

@@ -114,6 +114,9 @@ struct ppm_engine {
   DevBuf<double2> d_bs_nodes0, d_bs_z1, d_bs_unit_base;  // sparse evaluation: records / shift prefixes of the all-zero and all-ones
   DevBuf<int> d_bs_xk0;                                  // rows per parameter vector, per-slice integrand of the all-ones row
   DevBuf<uint32_t> d_bs_ones;
+  // leaf powers (band_program.h: leaf_pow)
+  DevBuf<int> d_blp_alive, d_bs_n1k[2], d_bs_n1k0, d_bs_base_n1;
+  DevBuf<double> d_blp_htot, d_blp_op_h, d_blp_leaf_h, d_blp_s1_0, d_bLb, d_bLc, d_bLe, d_bs_s1k[2], d_bs_s1k0, d_bs_base_s1;
   bool sparse = false;            // ppm_set_sparse / PPM_SPARSE: the band kernels multiply dirty lineages only
   DevBuf<int> d_bs_unit_off;
   int bs_blk_cap = 0;             // 32-item blocks the scratch holds
@@ -230,18 +233,20 @@ struct ppm_engine {
       // units per item.  Units are handed out item-major, so about (resident warps / G) items are in flight; their lineage
       // records (16 B x internal nodes each) should stay in L2 (a third of it at most), which asks for G >= warps x bytes / 40 MB.
       const int R = fixR ? fixR : 4;
-      ppm::BandProgram probe = ppm::build_band_program(tree, prog, R, 1, true);
+      const char* eL = std::getenv("PPM_NO_LEAFPOW");
+      const bool leaf_pow = !(eL && std::atoi(eL) != 0);
+      ppm::BandProgram probe = ppm::build_band_program(tree, prog, R, 1, true, leaf_pow);
       if (!probe.ok) { if (std::getenv("PPM_PLAN_DEBUG")) fprintf(stderr, "[ppm band] not used: %s\n", probe.why); return; }
-      const double item_bytes = 20.0 * probe.n_int;
+      const double item_bytes = (probe.leaf_pow ? (probe.has_s1 ? 32.0 : 24.0) : 20.0) * probe.n_int;
       int G = (int)std::ceil(n_sm * 20.0 * item_bytes / 40e6);
       G = std::max(2, std::min(G, std::max(1, probe.n_tiles / 2)));
       if (fixG) G = fixG;
       G = std::max(1, std::min(G, probe.n_tiles));
-      band = G == 1 ? std::move(probe) : ppm::build_band_program(tree, prog, R, G, true);
+      band = G == 1 ? std::move(probe) : ppm::build_band_program(tree, prog, R, G, true, leaf_pow);
       if (std::getenv("PPM_PLAN_DEBUG"))
-        fprintf(stderr, "[ppm band] stream layout: R %d, %d units per item, %d tiles, balance %.3f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld\n",
+        fprintf(stderr, "[ppm band] stream layout: R %d, %d units per item, %d tiles, balance %.3f; records full16 %lld full32 %lld f16 %lld f32 %lld m16 %lld; leaf powers %d (heights %d, max |h| %.3g)\n",
                 band.R, band.G, band.n_tiles, band.cost_sum / (band.G * std::max(band.cost_max, 1.0)), band.n_full16, band.n_full32, band.n_f16,
-                band.n_f32, band.n_m16);
+                band.n_f32, band.n_m16, (int)band.leaf_pow, (int)band.has_s1, band.max_leaf_h);
     } else {
       // Candidates: slices per lane R in {4, 2}, warps per item G in {1, 2, 4, 8, 16}.  The kernel is latency-bound below ~16
       // resident warps per SM (measured: 1,000 genomes 110 ms at 8 warps, 79 ms at 20), and a CTA's warps own whole tiles, so
@@ -295,6 +300,10 @@ struct ppm_engine {
       d_bs_blocks.upload(band.blocks, stream);
       d_bs_op_span.upload(band.op_span, stream); d_bs_leaf_span.upload(band.leaf_span, stream);
       d_bs_unit_off.upload(band.unit_blk_off, stream);
+      if (band.leaf_pow) {
+        d_blp_alive.upload(band.n_alive_leaves, stream); d_blp_htot.upload(band.htot, stream);
+        d_blp_op_h.upload(band.op_leaf_h, stream); d_blp_leaf_h.upload(band.leaf_h, stream);
+      }
     }
     CK(cudaStreamSynchronize(stream));
     bdev.R = band.R; bdev.G = band.G; bdev.T = band.T; bdev.n_tiles = band.n_tiles; bdev.S_pad = band.S_pad; bdev.n_int = band.n_int;
@@ -304,6 +313,15 @@ struct ppm_engine {
     bdev.rounds = d_brounds.p; bdev.n_rounds = band.n_rounds; bdev.warp_ent_off = d_bwarp_ent_off.p;
     bdev.blocks = d_bs_blocks.p; bdev.unit_blk_off = d_bs_unit_off.p;
     bdev.op_span = d_bs_op_span.p; bdev.leaf_span = d_bs_leaf_span.p;
+    bdev.lp = band.leaf_pow ? 1 : 0; bdev.has_s1 = band.has_s1 ? 1 : 0;
+    bdev.n_alive_leaves = d_blp_alive.p; bdev.htot = d_blp_htot.p; bdev.op_leaf_h = d_blp_op_h.p;
+    md.lp_max_h = band.leaf_pow ? band.max_leaf_h : 0.;
+    if (band.has_s1) {  // sum of the heights of every pattern's present leaves, once per handle
+      d_blp_s1_0.alloc((size_t)std::max<long long>(n_pat_pad, 32));
+      CK(cudaMemsetAsync(d_blp_s1_0.p, 0, sizeof(double) * (size_t)std::max<long long>(n_pat_pad, 32), stream));
+      ppm::launch_leaf_height_sums(md, d_blp_leaf_h.p, count, d_blp_s1_0.p, stream);
+      CK(cudaStreamSynchronize(stream));
+    }
     use_band = true;
   }
   // Sparse evaluation: the term lists (pattern-only) of this shard, once per handle (band_sparse.cu).
@@ -320,12 +338,21 @@ struct ppm_engine {
     for (int k = 0; k < tree.n_leaves; k++)
       for (int c = 32; c < 64; c++) ones[(size_t)(k >> 5) * 64 + c] |= 1u << (k & 31);
     d_bs_ones.upload(ones, stream);
+    if (band.leaf_pow) {  // the baseline columns' present leaves and height sums
+      double hall = 0.;
+      for (double h : band.leaf_h) hall += h;
+      std::vector<int> bn(64, 0);
+      std::vector<double> bs(64, 0.);
+      for (int c = 32; c < 64; c++) { bn[c] = tree.n_leaves; bs[c] = hall; }
+      d_bs_base_n1.upload(bn, stream); d_bs_base_s1.upload(bs, stream);
+    }
     CK(cudaStreamSynchronize(stream));
     sp_lists_ready = true; sp_lists_failed = false;
   }
   ppm::BandTables band_tables() const {
     ppm::BandTables bt{};
     bt.bop = d_bop.p; bt.bY = d_bY.p; bt.bU = d_bU.p; bt.bleaf = d_bleaf.p;
+    bt.bLb = d_bLb.p; bt.bLc = d_bLc.p; bt.bLe = d_bLe.p;
     return bt;
   }
 
@@ -455,6 +482,7 @@ struct ppm_engine {
         d_bop.alloc((size_t)P * std::max<size_t>(band.ops.size(), 1) * ppm::BOP_DOUBLES);
         d_bY.alloc((size_t)P * band.S_pad); d_bU.alloc((size_t)P * band.S_pad);
         d_bleaf.alloc((size_t)P * tree.n_leaves * 2);
+        if (band.leaf_pow) { d_bLb.alloc((size_t)P * band.S_pad); d_bLc.alloc((size_t)P * band.S_pad); d_bLe.alloc((size_t)P * band.S_pad); }
       }
       P_cap = P;
     }
@@ -528,6 +556,8 @@ struct ppm_engine {
             d_bs_nodes[k].alloc((size_t)blk_batch * bdev.n_int * 32);
             d_bs_xk[k].alloc((size_t)blk_batch * (bdev.n_int + 1) * 32);
             d_bs_unit[k].alloc((size_t)blk_batch * 32 * bdev.G);
+            if (bdev.lp) d_bs_n1k[k].alloc((size_t)blk_batch * (bdev.n_int + 1) * 32);
+            if (bdev.has_s1) d_bs_s1k[k].alloc((size_t)blk_batch * (bdev.n_int + 1) * 32);
           }
           bs_blk_cap = blk_batch;
         }
@@ -536,6 +566,8 @@ struct ppm_engine {
         if (sparse_now) {
           d_bs_nodes0.alloc((size_t)2 * t.P * bdev.n_int * 32);
           d_bs_xk0.alloc((size_t)2 * t.P * (bdev.n_int + 1) * 32);
+          if (bdev.lp) d_bs_n1k0.alloc((size_t)2 * t.P * (bdev.n_int + 1) * 32);
+          if (bdev.has_s1) d_bs_s1k0.alloc((size_t)2 * t.P * (bdev.n_int + 1) * 32);
           d_bs_z1.alloc((size_t)t.P * bdev.S_pad);
           d_bs_unit_base.alloc((size_t)t.P * 64 * bdev.G);
         }
@@ -554,6 +586,8 @@ struct ppm_engine {
           ppm::BandStreamArgs x = sa;
           const int k = (int)(b & 1);
           x.nodes = d_bs_nodes[k].p; x.xk = d_bs_xk[k].p; x.unit_I = d_bs_unit[k].p; x.counter = d_bs_counter.p + k;
+          x.n1k = d_bs_n1k[k].p; x.s1k = d_bs_s1k[k].p; x.n1_0 = md.freq; x.s1_0 = d_blp_s1_0.p;
+          x.n1k0 = d_bs_n1k0.p; x.s1k0 = d_bs_s1k0.p;
           x.sparse = sparse_now ? 1 : 0; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p; x.z1 = d_bs_z1.p;
           x.lists.off = d_sp_off.p; x.lists.recs = d_sp_recs.p; x.counter2 = d_bs_counter.p + 3 + k;
           x.item0 = 32 * b * blk_batch;
@@ -564,7 +598,8 @@ struct ppm_engine {
                            // stream next to the first batch's prune on the side stream
           ppm::BandStreamArgs z = sa;
           z.nodes0 = d_bs_nodes0.p; z.xk0 = d_bs_xk0.p; z.z1 = d_bs_z1.p; z.unit_I = d_bs_unit_base.p; z.counter = d_bs_counter.p + 2;
-          ppm::launch_band_baseline_rows(z, d_bs_ones.p, n_sm, s);
+          z.n1k0 = d_bs_n1k0.p; z.s1k0 = d_bs_s1k0.p;
+          ppm::launch_band_baseline_rows(z, d_bs_ones.p, d_bs_base_n1.p, d_bs_base_s1.p, n_sm, s);
           n_launches += 2;
         }
         ppm::launch_band_prune(batch_args(0), side);

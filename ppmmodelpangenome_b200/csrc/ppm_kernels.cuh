@@ -83,6 +83,7 @@ struct ModelDev {
   const uint32_t* fr_off;    // [n_pat + 1] offsets into fr_nodes, or null (trees with more than 65,535 nodes: walked per call)
   const uint16_t* fr_nodes;
   const uint32_t* zero_words;  // n_words * 32 zeros (the all-zero row of add0(), objects.cpp:274-281)
+  double lp_max_h;  // leaf-power band program: largest |leaf height| (the prepass keeps parameter vectors with n (lam h)^2 > 1e-12 off it)
 };
 
 // Per-launch tables, one row per parameter vector
@@ -119,8 +120,8 @@ __host__ __device__ inline int bs_sparse_item(const ModelDev& m, long long pat) 
 
 // ---- band kernel (slice-parallel sweep for big trees; band_program.h) ------------------------------------------------
 struct BandOpDev { uint16_t lref, rref, dst, flags; };   // == ppm::BandOp
-enum { BOP_DOUBLES = 6 };  // per (parameter vector, band op): c0_l c1_l c0_r c1_r (child branch factors, see prepass_band_body),
-                           // -exp(lam (h_node - H/2)), unused
+enum { BOP_DOUBLES = 8 };  // per (parameter vector, band op): c0_l c1_l c0_r c1_r (child branch factors, see prepass_band_body),
+                           // -exp(lam (h_node - H/2)), height of a leaf left child, of a leaf right child (leaf powers), unused
 struct BandDev {
   int R, G, T, n_tiles, S_pad, n_int, n_ops, n_levels, n_rounds, n_desc, n_entries;
   const BandOpDev* ops; const int* op_nodes; const int* lev_off; const uint32_t* rounds;
@@ -128,6 +129,10 @@ struct BandDev {
   const uint32_t* desc; const int* warp_off; const int* warp_ent_off; const uint32_t* entries;
   const uint32_t* blocks; const int* unit_blk_off;  // stream layout: descriptor blocks (band_program.h)
   const uint32_t* op_span; const uint32_t* leaf_span;  // alive slices js0 | js1 << 16 of every internal lineage (by record index) / leaf (by bit position)
+  // leaf-power program (band_program.h): the lists hold internal lineages only
+  int lp, has_s1;
+  const int* n_alive_leaves; const double* htot;  // [S_pad] leaves alive at each slice and the sum of their heights
+  const double* op_leaf_h;                        // [n_ops][2]
 };
 // sparse evaluation: which patterns have a term list.  Present in at most an eighth of the genomes: few dirty
 // lineages (a present leaf below), the all-zero row serves the rest; the others have few clean lineages and stay dense.
@@ -140,6 +145,10 @@ struct BandTables {     // one row per parameter vector, written by prepass_band
   double* bY;           // [P][S_pad]  pi1 * exp(-lam (t_j - H/2))
   double* bU;           // [P][S_pad]  u_j = 1 - exp(-lam t_j)
   double2* bleaf;       // [P][n_leaves][2]  single leaf at bit position pos observed 0 / 1: (a, -d exp(lam (h_leaf - H/2)))
+  // leaf powers: log2 of the product of the alive leaves at slice j = bLb + n1 bLc + S1 bLe, n1 = present alive leaves, S1 = sum of their heights
+  double* bLb;          // [P][S_pad]  n_alive log2 f_0(u_j) + g_0(j) sum of the alive leaves' heights
+  double* bLc;          // [P][S_pad]  log2 f_1(u_j) - log2 f_0(u_j)
+  double* bLe;          // [P][S_pad]  g_1(j) - g_0(j), g_x = d log2 f_x / d (leaf height) at height 0
 };
 struct BandArgs {
   ModelDev m; TablesDev t; BandDev b; BandTables bt;
@@ -158,6 +167,10 @@ struct BandStreamArgs {
   int n_blk;
   double2* nodes;              // scratch [n_blk][n_int][32]  lineage records (a, -d e^{lam (h - H/2)})
   int* xk;                     // scratch [n_blk][n_int + 1][32]  running sums of the renormalisation shifts, birth order
+  int* n1k;                    // scratch [n_blk][n_int + 1][32]  leaf powers: present leaves that have died before each op ...
+  double* s1k;                 // scratch [n_blk][n_int + 1][32]  ... and the sum of their heights (has_s1 only)
+  const int* n1_0;             // [count_pad] present leaves of each pattern (ModelDev::freq; the baseline rows bring their own)
+  const double* s1_0;          // [count_pad] sum of the heights of the present leaves (has_s1 only)
   double2* unit_I;             // scratch [n_blk * 32][G]  (mantissa, exponent) of every unit's share of the Mobile integral
   unsigned int* counter;       // unit hand-out
   const double2* ident;        // 32 bytes (1, 0, 0, 0): the record of a padding entry
@@ -171,6 +184,7 @@ struct BandStreamArgs {
   unsigned int* counter2;      // unit hand-out of the sparse kernel
   const double2* nodes0;       // [P][2][n_int][32]  lineage records of the all-zero / all-ones row per parameter vector (copy 0 of 32 is read)
   const int* xk0;              // [P][2][n_int + 1][32]  their shift prefixes
+  const int* n1k0; const double* s1k0;  // [P][2][n_int + 1][32]  their dead-leaf counts / height sums (leaf powers)
   double2* z1;                 // [P][S_pad]  per-slice integrand (mantissa x weight, exponent) of the all-ones row; the zero row's is TablesDev::zpart
   int slice_out;               // != 0: the dense integral kernel serves copy 0 of every block only and stores its slices into z1
 };
@@ -227,7 +241,10 @@ void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);   
 // sparse evaluation: records of the all-zero and all-ones rows for every parameter vector into a.nodes0 / a.xk0 ([P][2][...]),
 // per-slice integrand of the all-ones row into a.z1; base_words = [n_words][64] (32 zero columns, 32 all-ones columns);
 // a.unit_I must hold P * 64 * G entries
-void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, int n_sm, cudaStream_t s);
+// base_n1 / base_s1 [64]: present leaves / sum of their heights of the 64 baseline columns (leaf powers)
+void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, const int* base_n1, const double* base_s1, int n_sm, cudaStream_t s);
+// leaf powers, once per handle: s1_0[pattern] = sum of leaf_h over the pattern's present leaves (leaf_h by device bit position)
+void launch_leaf_height_sums(const ModelDev& m, const double* leaf_h, long long count, double* s1_0, cudaStream_t s);
 // term lists: count pass (cnt [count * n_tiles + 1], turned into offsets in place; returns the number of records) and fill pass
 unsigned long long sparse_lists_count(const ModelDev& m, const BandDev& b, long long count, uint32_t* cnt_off, cudaStream_t s);
 void sparse_lists_fill(const ModelDev& m, const BandDev& b, long long count, const uint32_t* off, uint2* recs, cudaStream_t s);

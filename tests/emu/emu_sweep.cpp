@@ -39,7 +39,11 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
   auto bit = [&](int pos) { return (int)((md.words[(size_t)(pos >> 5) * md.n_pat_pad + pat] >> (pos & 31)) & 1u); };
   const double2* leaftab = reinterpret_cast<const double2*>(sc + SC_LA0);
   std::vector<double2> node(std::max(bp.n_int, 1));
-  std::vector<int> xcum(bp.n_int + 1, 0);
+  std::vector<int> xcum(bp.n_int + 1, 0), n1cum(bp.n_int + 1, 0);
+  std::vector<double> s1cum(bp.n_int + 1, 0.);
+  int n1_0 = 0; double s1_0 = 0.;
+  if (bp.leaf_pow)
+    for (int pos = 0; pos < md.n_leaves; pos++) if (bit(pos)) { n1_0++; s1_0 += bp.leaf_h[pos]; }
   const int n_ops = (int)bp.ops.size();
   for (int o = 0; o < n_ops; o++) {
     const BandOp& op = bp.ops[o];
@@ -49,8 +53,13 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
     int k;
     node[op.dst] = band_merge(xl, yl, xr, yr, bt.bop + ((size_t)p * n_ops + o) * BOP_DOUBLES, pi1, k);
     xcum[op.dst + 1] = k;
+    if (bp.leaf_pow) {  // present leaves that die with this op (stream layout: dst = birth order = op index)
+      const double* oc = bt.bop + ((size_t)p * n_ops + o) * BOP_DOUBLES;
+      if ((op.flags & 1) && bit(op.lref)) { n1cum[op.dst + 1]++; s1cum[op.dst + 1] += oc[5]; }
+      if ((op.flags & 2) && bit(op.rref)) { n1cum[op.dst + 1]++; s1cum[op.dst + 1] += oc[6]; }
+    }
   }
-  for (int i = 0; i < bp.n_int; i++) xcum[i + 1] += xcum[i];
+  for (int i = 0; i < bp.n_int; i++) { xcum[i + 1] += xcum[i]; n1cum[i + 1] += n1cum[i]; s1cum[i + 1] += s1cum[i]; }
   const int R = bp.R, T = bp.T;
   double Im = 0.; int Ie = 0x3fffffff;
   std::vector<double> prod(32 * R), Y(32 * R), U(32 * R);
@@ -69,6 +78,19 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
             const int j = tau * T + 32 * kk + l;
             prod[kk * 32 + l] = 1.; ex[kk * 32 + l] = xcum[bp.nborn[j]];
             Y[kk * 32 + l] = bt.bY[(size_t)p * bp.S_pad + j]; U[kk * 32 + l] = bt.bU[(size_t)p * bp.S_pad + j];
+          }
+        continue;
+      }
+      if (op == BD_TILE_LP) {
+        if (var) continue;  // (the height tables are read together with the counts below)
+        for (int kk = 0; kk < R; kk++)
+          for (int l = 0; l < 32; l++) {
+            const int j = tau * T + 32 * kk + l, nb = bp.nborn[j];
+            const size_t tj = (size_t)p * bp.S_pad + j;
+            const double s2 = fma((double)(n1_0 - n1cum[nb]), bt.bLc[tj], bt.bLb[tj]) + (bp.has_s1 ? bt.bLe[tj] * (s1_0 - s1cum[nb]) : 0.);
+            int kx;
+            prod[kk * 32 + l] *= lp_pow2(s2, kx);
+            ex[kk * 32 + l] -= kx;
           }
         continue;
       }
@@ -115,15 +137,18 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     Patterns pat = read_matrix_file(tree, pa_path, dedupe != 0);
     // R >= 1000: the band program (slice-parallel sweep), R = 1000 + 100 * G + slices-per-lane
     // R >= 3000: the same with the stream layout (band_stream.cu), G = work units per item
+    // R >= 5000: stream layout + leaf powers
+    const bool band_lp = R >= 5000;
     const bool band_stream = R >= 3000;
-    const int band_code = R >= 3000 ? R - 3000 : R >= 1000 ? R - 1000 : 0;
+    const int band_code = R >= 5000 ? R - 5000 : R >= 3000 ? R - 3000 : R >= 1000 ? R - 1000 : 0;
     if (band_code) R = 8;
     const bool deep = R < 0;
     if (deep) R = -R;
     Program prog = build_program(tree, R, deep);
     BandProgram bp;
     if (band_code) {
-      bp = build_band_program(tree, prog, band_code % 100, band_code / 100, band_stream);
+      bp = build_band_program(tree, prog, band_code % 100, band_code / 100, band_stream, band_lp);
+      if (band_lp && !bp.leaf_pow) throw std::runtime_error("band program: leaf powers refused (leaf heights)");
       if (!bp.ok) throw std::runtime_error(std::string("band program: ") + bp.why);
     }
     const long long count = pat.n_patterns;
@@ -140,6 +165,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<double> wt_pad((size_t)std::max(prog.n_blocks, 1) * prog.R, 0.);
     std::copy(tree.slice_wt.begin(), tree.slice_wt.end(), wt_pad.begin());
     ModelDev md{};
+    md.lp_max_h = (band_code && bp.leaf_pow) ? bp.max_leaf_h : 0.;
     md.n_nodes = tree.n_nodes; md.n_leaves = tree.n_leaves; md.n_words = pat.n_words; md.n_slices = tree.n_slices;
     md.n_blocks = prog.n_blocks; md.n_slots = prog.n_slots; md.n_entries = (int)prog.entry_ref.size();
     md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.H = tree.H; md.n_obs = pat.n_obs;
@@ -237,7 +263,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     for (int p = 0; p < P; p++) zero_row_body(md, t, p, 0, 1);
     for (int p = 0; p < P; p++) prepass_i2_body(md, t, nullptr, p);
     BandDev bd{}; BandTables bt{};
-    std::vector<double> bop, bY, bU; std::vector<double2> bleaf;
+    std::vector<double> bop, bY, bU, bLb, bLc, bLe; std::vector<double2> bleaf;
     if (band_code) {
       static_assert(sizeof(BandOpDev) == sizeof(BandOp), "layout");
       bd.R = bp.R; bd.G = bp.G; bd.T = bp.T; bd.n_tiles = bp.n_tiles; bd.S_pad = bp.S_pad; bd.n_int = bp.n_int; bd.n_ops = (int)bp.ops.size();
@@ -245,6 +271,10 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
       bop.resize((size_t)P * std::max(bd.n_ops, 1) * BOP_DOUBLES); bY.resize((size_t)P * bp.S_pad); bU.resize((size_t)P * bp.S_pad);
       bleaf.resize((size_t)P * tree.n_leaves * 2);
       bt.bop = bop.data(); bt.bY = bY.data(); bt.bU = bU.data(); bt.bleaf = bleaf.data();
+      bd.lp = bp.leaf_pow ? 1 : 0; bd.has_s1 = bp.has_s1 ? 1 : 0;
+      bd.n_alive_leaves = bp.n_alive_leaves.data(); bd.htot = bp.htot.data(); bd.op_leaf_h = bp.op_leaf_h.data();
+      bLb.resize((size_t)P * bp.S_pad); bLc.resize((size_t)P * bp.S_pad); bLe.resize((size_t)P * bp.S_pad);
+      bt.bLb = bLb.data(); bt.bLc = bLc.data(); bt.bLe = bLe.data();
       for (int p = 0; p < P; p++)
         for (int i = 0; i < bd.n_ops + bd.S_pad + md.n_leaves; i++) prepass_band_body(md, t, bd, bt, p, i);
       for (int p = 0; p < P; p++) {

@@ -38,7 +38,9 @@ def emu():
 
 @pytest.mark.parametrize("name", ["syn12", "syn100", "cat40", "syn300"])
 # 1000 + 100 * (warps per item) + (slices per lane); 3000 + ...: stream layout (band_stream.cu), work units per item
-@pytest.mark.parametrize("code", [1104, 1102, 1108, 1204, 1404, 1802, 2604, 3104, 3204, 3302, 3404])
+# 5000 + ...: stream layout with leaf powers (the alive leaves of a slice as one exp2; the golden trees carry ape's 10-digit
+# branch lengths, so the first-order height correction is exercised)
+@pytest.mark.parametrize("code", [1104, 1102, 1108, 1204, 1404, 1802, 2604, 3104, 3204, 3302, 3404, 5104, 5204, 5302, 5404])
 def test_band_program_reproduces_reference_golden(golden, emu, name, code):
     g = golden(name)
     ll, i2, comp = emu(g.tree, g.pa, False, g.params, code, n_rows=g.meta["nRep"])
