@@ -22,36 +22,6 @@ PPM_HD double2 band_merge(double xl, double yl, double xr, double yr, const doub
   return make_double2(a, d * o[4]);
 }
 
-// Leaf powers: 2^s = p * 2^k with p in [0.70, 1.42]; s <= ~0 is the log2 of a product of leaf terms (band_program.h: leaf_pow).
-// Round to nearest integer with the 1.5 * 2^52 trick, then exp(r ln 2) by its Taylor polynomial of degree 13 on |r| <= 1/2
-// (remainder < 5e-18).  s below -1e9 (an impossible observation) is clamped: the slice then weighs 2^-1e9.
-PPM_HD double lp_pow2(double s, int& k) {
-  s = fmax(s, -1.0e9);
-  const double magic = 6755399441055744.0;
-  const double t = s + magic;
-#if defined(__CUDA_ARCH__)
-  k = __double2loint(t);
-#else
-  { long long b; memcpy(&b, &t, 8); k = (int)(uint32_t)b; }
-#endif
-  const double x = (s - (t - magic)) * 0.693147180559945309417232;
-  double p = 1.6059043836821613e-10;           // 1/13!
-  p = fma(p, x, 2.08767569878681e-09);         // 1/12!
-  p = fma(p, x, 2.505210838544172e-08);        // 1/11!
-  p = fma(p, x, 2.755731922398589e-07);        // 1/10!
-  p = fma(p, x, 2.7557319223985893e-06);       // 1/9!
-  p = fma(p, x, 2.48015873015873e-05);         // 1/8!
-  p = fma(p, x, 0.0001984126984126984);        // 1/7!
-  p = fma(p, x, 0.001388888888888889);         // 1/6!
-  p = fma(p, x, 0.008333333333333333);         // 1/5!
-  p = fma(p, x, 0.041666666666666664);         // 1/4!
-  p = fma(p, x, 0.16666666666666666);          // 1/3!
-  p = fma(p, x, 0.5);
-  p = fma(p, x, 1.);
-  p = fma(p, x, 1.);
-  return p;
-}
-
 // Mixture of one (pattern, parameter vector) given its Mobile integral Im * 2^-Ie: functions.cpp:345-358 with the
 // pure-loss categories from the class-sum kernel (a01) and the Private below-root table (d1u).  Returns count * log-mixture.
 PPM_HD double band_mixture(const ModelDev& m, const TablesDev& t, int p, long long pat, double Im, int Ie, double* comp3) {

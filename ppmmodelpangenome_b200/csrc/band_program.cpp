@@ -32,6 +32,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
   // first order; the prepass checks n (lam max_h)^2 per parameter vector)
   bp.leaf_pow = leaf_pow && stream && bp.max_leaf_h <= 1e-8 * t.H;
   bp.has_s1 = bp.leaf_pow && bp.max_leaf_h > 0.;
+  const bool want_lp = bp.leaf_pow;
 
   // alive slice range of every non-root lineage (functions.cpp:130-141, 250-262), as in build_program
   std::vector<int> js0(nn, S), js1(nn, S);
@@ -39,6 +40,9 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     js0[v] = t.slice_start[std::max(t.rank[v], nl - 1)];
     js1[v] = t.slice_start[t.rank[t.parent[v]]];
   }
+  for (int v = 1; v < nn && bp.leaf_pow; v++)
+    if (t.left[v] < 0 && js0[v] != 0) bp.leaf_pow = false;  // (an internal node below a leaf's height: that leaf starts above the first slice)
+  if (want_lp && !bp.leaf_pow) bp.has_s1 = false;
   auto dpos = [&](int v) { return pg.leaf_perm[t.leaf_pos[v]]; };
   auto pair_of = [&](int pos) { return pos < 2 * pg.n_pairs ? pos / 2 : -1; };
 

@@ -484,7 +484,7 @@ void write_ccc_file(const Tree& t, const Patterns& p, const std::string& path) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-Program build_program(const Tree& t, int R, bool deep) {
+Program build_program(const Tree& t, int R, bool deep, bool leaf_pow) {
   Program pg;
   pg.R = R;
   pg.deep = deep;
@@ -507,6 +507,12 @@ Program build_program(const Tree& t, int R, bool deep) {
   double max_leaf_h = 0;
   for (int k = 0; k < nl; k++) max_leaf_h = std::max(max_leaf_h, std::fabs(t.height[t.leaf_node[k]]));
   pg.leaf_u = max_leaf_h <= 1e-6 * t.H;
+  pg.max_leaf_h = max_leaf_h;
+  // leaf powers: leaf heights that are rounding noise of the tree file only (the height correction is first order), folded events
+  pg.lp = leaf_pow && pg.leaf_u && max_leaf_h <= 1e-8 * t.H && std::getenv("PPM_NO_FOLD") == nullptr && nn > 1;
+  for (int v = 1; v < nn && pg.lp; v++)
+    if (t.left[v] < 0 && js0[v] != 0) pg.lp = false;  // (an internal node below a leaf's height: that leaf starts above the first slice)
+  pg.has_s1 = pg.lp && max_leaf_h > 0.;
   pg.leaf_perm.assign(nl, -1);
   pg.n_pairs = 0;
   if (pg.leaf_u) {
@@ -604,9 +610,20 @@ Program build_program(const Tree& t, int R, bool deep) {
   const int kPairRef = 1 << 21; // marks a leaf-pair entry (ref - kPairRef = pair id)
   if (deep && pg.n_slots + 1 > 65535) throw std::runtime_error("program: tree too large for 16-bit lineage references");
   std::vector<std::vector<Ent>> ent(nb);
+  if (pg.lp) {
+    pg.n_alive_leaves.assign(std::max(S, 1), 0);
+    pg.htot.assign(std::max(S, 1), 0.);
+    pg.leaf_h.assign(nl, 0.);
+    for (int v = 1; v < nn; v++) {
+      if (t.left[v] >= 0) continue;
+      pg.leaf_h[dpos(v)] = t.height[v];
+      for (int j = js0[v]; j < js1[v]; j++) { pg.n_alive_leaves[j]++; pg.htot[j] += t.height[v]; }
+    }
+  }
   for (int v = 1; v < nn; v++) {
     if (js0[v] >= js1[v]) continue;
     const bool leaf = t.left[v] < 0;
+    if (leaf && pg.lp) continue;  // leaf powers: the leaves enter as one power per slice
     for (int b = js0[v] / R; b <= (js1[v] - 1) / R; b++) {
       int jb = b * R, je = std::min(S, jb + R);
       Ent e;
@@ -750,6 +767,7 @@ Program build_program(const Tree& t, int R, bool deep) {
   for (const NodeOp& op : pg.ops) n_cherry_ops += op.pair >= 0;
   pg.lean = n_generic == 0;
   pg.fp64_instr_per_eval = fp64 + 8.0 * ((double)pg.ops.size() - n_cherry_ops) + 3.0 * S + 60;
+  if (pg.lp) pg.fp64_instr_per_eval += 19.0 * S + (pg.has_s1 ? 2.0 : 1.0) * R * nl * 0.67;  // one exp2 per slice; count updates at the leaves' deaths
   return pg;
 }
 

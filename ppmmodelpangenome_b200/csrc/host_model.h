@@ -109,12 +109,19 @@ struct Program {
   bool leaf_u = false;                            // leaves are (numerically) at height 0: u-form entries are used
   int64_t n_full = 0, n_partial = 0;
   bool lean = false;                              // no K/Y-form leaf entries, no partial entry records (see sweep_items LEAN)
+  // Leaf powers (see band_program.h): the program lists no leaf entries and folds no leaf events; the sweep keeps, per lane, the
+  // number of present alive leaves (and the sum of their heights) and multiplies every slice by one power at the block's end.
+  bool lp = false, has_s1 = false;
+  double max_leaf_h = 0;
+  std::vector<int32_t> n_alive_leaves;            // [n_slices]
+  std::vector<double> htot;                       // [n_slices] sum of the alive leaves' heights
+  std::vector<double> leaf_h;                     // [n_leaves] height by device bit position
   // modelled FP64 instruction count per pattern-eval of the main kernel
   double fp64_instr_per_eval = 0;
 };
 // deep: pad every block's fully-alive lineage segment to a multiple of 4 records with padding records that refer
 // to the constant row (slot index n_slots) -- needed by the global-memory sweep variant's four-deep prefetch
-Program build_program(const Tree& t, int R, bool deep = false);
+Program build_program(const Tree& t, int R, bool deep = false, bool leaf_pow = false);
 // rows: n row-major bit-packed patterns in preorder leaf order (Patterns::words) -> the same rows in program leaf order
 std::vector<uint32_t> permute_patterns(const Program& pg, const uint32_t* rows, long long n, int n_words);
 

@@ -72,6 +72,36 @@ PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) 
   }
 }
 
+// Leaf powers: 2^s = p * 2^k with p in [0.70, 1.42]; s <= ~0 is the log2 of a product of leaf terms (band_program.h: leaf_pow).
+// Round to nearest integer with the 1.5 * 2^52 trick, then exp(r ln 2) by its Taylor polynomial of degree 13 on |r| <= 1/2
+// (remainder < 5e-18).  s below -1e9 (an impossible observation) is clamped: the slice then weighs 2^-1e9.
+PPM_HD double lp_pow2(double s, int& k) {
+  s = fmax(s, -1.0e9);
+  const double magic = 6755399441055744.0;
+  const double t = s + magic;
+#if defined(__CUDA_ARCH__)
+  k = __double2loint(t);
+#else
+  { long long b; memcpy(&b, &t, 8); k = (int)(uint32_t)b; }
+#endif
+  const double x = (s - (t - magic)) * 0.693147180559945309417232;
+  double p = 1.6059043836821613e-10;           // 1/13!
+  p = fma(p, x, 2.08767569878681e-09);         // 1/12!
+  p = fma(p, x, 2.505210838544172e-08);        // 1/11!
+  p = fma(p, x, 2.755731922398589e-07);        // 1/10!
+  p = fma(p, x, 2.7557319223985893e-06);       // 1/9!
+  p = fma(p, x, 2.48015873015873e-05);         // 1/8!
+  p = fma(p, x, 0.0001984126984126984);        // 1/7!
+  p = fma(p, x, 0.001388888888888889);         // 1/6!
+  p = fma(p, x, 0.008333333333333333);         // 1/5!
+  p = fma(p, x, 0.041666666666666664);         // 1/4!
+  p = fma(p, x, 0.16666666666666666);          // 1/3!
+  p = fma(p, x, 0.5);
+  p = fma(p, x, 1.);
+  p = fma(p, x, 1.);
+  return p;
+}
+
 // Mobile merge of two child lineages (x, y) = (a, d): m0 = x - k0 y, m1 = x + k1 y along each child's branch, multiplied
 // (objects.cpp:427-435 in the linear domain); orc = {k0_l, k1_l, k0_r, k1_r}.  Returns the parent's (a, d), not renormalised.
 PPM_HD void merge_children(double2 L, double2 Rr, const double* orc, double pi1, double& av, double& d) {
@@ -287,6 +317,22 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     t.yy[(size_t)p * n_pad + j] = v;
     // u_j = 1 - exp(-(g2+l2) t_j) = p01(t_j)/pi1 (functions.cpp:227-231): the variable of the u-form leaf terms
     t.uu[(size_t)p * n_pad + j] = (j < m.n_slices) ? 1. - exp(-lam * m.slice_t[j]) : 0.;
+    if (m.lp) {  // leaf powers: see prepass_band_body
+      double lb = 0., lc = 0., le = 0.;
+      if (j < m.n_slices) {
+        const double e2 = par[6], e1 = par[7];
+        const double E = exp(-lam * m.slice_t[j]), u = 1. - E;
+        double lg[2], g[2];
+        for (int x = 0; x < 2; x++) {
+          const double m0 = x ? e1 : 1 - e1, m1 = x ? 1 - e2 : e2, d = m1 - m0;  // objects.cpp:407-408
+          const double f = fma(pi1 * d, u, m0);
+          lg[x] = f > 0. ? log2(f) : -1e7;
+          g[x] = f > 0. ? -pi1 * d * lam * E / (f * 0.693147180559945309417232) : 0.;
+        }
+        lb = (double)m.lp_alive[j] * lg[0] + g[0] * m.lp_htot[j]; lc = lg[1] - lg[0]; le = g[1] - g[0];
+      }
+      t.slb[(size_t)p * n_pad + j] = lb; t.slc[(size_t)p * n_pad + j] = lc; t.sle[(size_t)p * n_pad + j] = le;
+    }
   } else if (i <= m.n_entries + n_pad + m.n_ops) {
     // per-op record: the branch tables of the two children, contiguous (no dependent index loads in the sweep)
     int o = i - m.n_entries - n_pad - 1;
@@ -300,6 +346,10 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     r[5] = pi1 * exp(-lam * (tb - m.height[op.rnode]));
     r[6] = pi1 * exp(-lam * (tb - m.height[op.node]));
     r[7] = 0.;
+    if (m.lp) {  // leaf powers: a leaf child has no folded event; its slot carries the leaf's height (count updates at its death)
+      if (m.left[op.lnode] < 0) r[4] = m.height[op.lnode];
+      if (m.left[op.rnode] < 0) r[5] = m.height[op.rnode];
+    }
   } else if (i <= m.n_entries + n_pad + m.n_ops + m.n_leaves + m.n_pairs) {
     // u-form leaf terms.  A leaf s at height h_s (numerically 0) observed as x contributes, at time t,
     //   (1-q) m0_x + q m1_x,  q = pi1 (1 - exp(-lam (t - h_s)))                       (functions.cpp:232-240)
@@ -492,6 +542,11 @@ PPM_HD void zero_row_slice(const ModelDev& m, const TablesDev& t, int p, int j) 
     if ((recs[e].mask >> 16) & bit) mul(fma(ld0 * -recs[e].K, Y, la0));
   for (int e = bd.e_pslot0; e < bd.e_end; e++)
     if ((recs[e].mask >> 16) & bit) { const double2 ad = zr[m.entry_node[e]]; mul(fma(ad.y * -recs[e].K, Y, ad.x)); }
+  if (m.lp) {  // leaf powers: every alive leaf observed 0
+    int kx;
+    prod *= lp_pow2(t.slb[(size_t)p * nbR + j], kx);
+    ex -= kx;
+  }
   t.zpart[(size_t)p * m.n_slices + j] = make_double2(prod * m.slice_wt_pad[j], (double)ex);
 }
 
@@ -658,6 +713,7 @@ struct ItemTables {
   const double2* leafab;  // [n_leaves][2] u-form leaf terms {alpha, beta}
   const double4* pairq;   // [n_pairs][4] u-form pair quadratics
   const double2* cherry;  // [n_cherries][4] cherry node partials by observation pair
+  const double* lb; const double* lc; const double* le;  // [n_blocks * R] leaf powers (ModelDev::lp)
 };
 
 // the two 32-bit halves of a record's K field (leaf-pair records)
@@ -804,18 +860,58 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   const bool factored = HOT ? false : (sc[SC_FACTORED] != 0.);
 #pragma unroll
   for (int q = 0; q < NI; q++) { X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
+  // Leaf powers (Program::lp; HOT kernels serve such programs only): n1 = the lane's present leaves still alive at the start of
+  // the block, S1 = the sum of their heights; lpacc[i] = log2 of the product of the alive leaves at slice i, updated as leaves
+  // die at the node ops and turned into one factor per slice at the block's end.
+  const bool lp = HOT ? true : (m.lp != 0);
+  const bool hs1 = lp && m.has_s1 != 0;
+  int n1[NI]; double S1[NI], lpacc[NI][R];
+#pragma unroll
+  for (int q = 0; q < NI; q++) {
+    n1[q] = (lp && active[q]) ? m.freq[pat[q]] : 0;
+    S1[q] = (hs1 && active[q]) ? m.lp_s1_0[pat[q]] : 0.;
+#pragma unroll
+    for (int i = 0; i < R; i++) lpacc[q][i] = 0.;
+  }
+  // a node op whose leaf children (present: bl / br) die at slice i0 of the block
+  auto leaf_deaths = [&](int q, int b, bool real, int i0, uint32_t bl, uint32_t br, double hl, double hr) {
+    const int cnt = (int)(bl + br);
+    n1[q] -= cnt;
+    if (real) {
+      const double dn = -(double)cnt;
+#pragma unroll
+      for (int i = 0; i < R; i++) lpacc[q][i] = fma(i >= i0 ? dn : 0., T.lc[b * R + i], lpacc[q][i]);
+    }
+    if (hs1) {
+      const double dh = (bl ? hl : 0.) + (br ? hr : 0.);
+      S1[q] -= dh;
+      if (real) {
+#pragma unroll
+        for (int i = 0; i < R; i++) lpacc[q][i] = fma(i >= i0 ? -dh : 0., T.le[b * R + i], lpacc[q][i]);
+      }
+    }
+  };
 
   for (int b = 0; b <= m.n_blocks; b++) {
     const BlockDesc bd = T.blk[b];
     const bool real = b < m.n_blocks;
     if (real) {
 #pragma unroll
-      for (int i = 0; i < R; i++) { Y[i] = T.yy[b * R + i]; U[i] = T.uu[b * R + i]; }
+      for (int i = 0; i < R; i++) { Y[i] = T.yy[b * R + i]; U[i] = HOT ? 0. : T.uu[b * R + i]; }
 #pragma unroll
       for (int q = 0; q < NI; q++)
 #pragma unroll
         for (int i = 0; i < R; i++) { prod[q][i] = DIST ? 1. : T.wt[b * R + i]; ex[q][i] = X[q]; }  // the slice weight goes in first
         // (w/nSub of functions.cpp:273-275; padding slices carry weight 0); the DIST output wants the bare integrand
+      if (lp) {
+#pragma unroll
+        for (int q = 0; q < NI; q++)
+#pragma unroll
+          for (int i = 0; i < R; i++) {
+            lpacc[q][i] = fma((double)n1[q], T.lc[b * R + i], T.lb[b * R + i]);
+            if (hs1) lpacc[q][i] = fma(S1[q], T.le[b * R + i], lpacc[q][i]);
+          }
+      }
     }
     // ---- node ops: form every node born before the end of this block.
     // store a new lineage (a, d); when it has become small its mantissa is brought back to [0.5,1) and the shift
@@ -849,7 +945,11 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         const uint32_t sel = rotr32(w, (uint32_t)op.lbit) & 0x30u;  // observation pair x 16
         const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.cherry + op.pair * 4) + sel);
         av[q] = v.x; dd[q] = v.y;
-        if (op.ml) {  // the two leaves die here: their slices of this block as one quadratic in u (as in the pair loop)
+        if (lp) {
+          const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
+          leaf_deaths(q, b, real, op.i0, (sel >> 4) & 1u, sel >> 5, hs1 ? orc[4] : 0., hs1 ? orc[5] : 0.);
+        }
+        if (!HOT && op.ml) {  // the two leaves die here: their slices of this block as one quadratic in u (as in the pair loop)
           const double4 qv = *reinterpret_cast<const double4*>(reinterpret_cast<const char*>(T.pairq + op.pair * 4) + 2 * sel);
           if (!factored) {
 #pragma unroll
@@ -897,6 +997,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         mem[q].slots.wait_async(rs);
         L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
         Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
+        if (lp && (op.flags & 3))
+          leaf_deaths(q, b, real, op.i0, lleaf ? (rotr32(wl, (uint32_t)op.lbit) >> 4) & 1u : 0u, rleaf ? (rotr32(wr, (uint32_t)op.rbit) >> 4) & 1u : 0u,
+                      hs1 ? orc[4] : 0., hs1 ? orc[5] : 0.);
       }
       // a child that dies with this op multiplies its slices of the block here (it has no entry record) -- unless its
       // prefix and the new node's suffix partition the block (op.comb): then one update serves both, below.  (Global-memory
@@ -1101,7 +1204,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
     // ---- u-form leaves (all variants).  Pairs: one record per two leaves, their two pattern bits pick one of four
     // quadratics q.x + q.y u + q.z u^2 (3 FP64 per slice for two leaf terms, no selects); the next record's bits and
     // table row are fetched while the current products run.
-    if (bd.e_pair0 < bd.e_leafu0) {
+    if (!HOT && bd.e_pair0 < bd.e_leafu0) {
       const int pmax = m.n_pairs - 1;
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_pair0, K, ref, mk);
@@ -1272,7 +1375,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       }
     }
     // single leaves in u-form: ref = bit position | next << 16; the term alpha + beta u comes from a per-lane table row
-    if (bd.e_leafu0 < bd.e_leaf0) {
+    if (!HOT && bd.e_leafu0 < bd.e_leaf0) {
       double K; uint32_t ref, mk;
       load_rec(T.recs, bd.e_leafu0, K, ref, mk);
       double2 fv[NI];
@@ -1360,6 +1463,14 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       // (every loop above ends with a range check of its own; the generic partial loops and the deep variant's tails do not)
       if (DEEP || (!HOT && bd.e_pleaf0 < bd.e_end))
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
+      if (lp) {  // the alive leaves of every slice as one power: 2^lpacc = mantissa in [0.70, 1.42] x 2^k
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          int kx;
+          prod[q][i] *= lp_pow2(lpacc[q][i], kx);
+          ex[q][i] -= kx;
+        }
+      }
       if (DIST) {  // expectedTime2_aux (functions.cpp:713-746): the integrand exp(f_aux) of every slice
         if (a.dist && active[q]) {
           double* row = a.dist + (size_t)(pat[q] - a.first) * (m.n_slices + 1);
@@ -1367,6 +1478,20 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
           for (int i = 0; i < R; i++)
             if (b * R + i < m.n_slices) row[b * R + i] = ldexp(prod[q][i], -ex[q][i]);
         }
+      }
+      if (lp) {  // the slices' exponents differ as a rule: align them to the smallest (zero products -- padding slices -- aside)
+        int emin = 0x3fffffff;
+#pragma unroll
+        for (int i = 0; i < R; i++) { const int e = prod[q][i] != 0. ? ex[q][i] : 0x3fffffff; emin = e < emin ? e : emin; }
+        double tsum = 0.;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+          int d = ex[q][i] - emin;
+          d = d < 0 ? 0 : (d > 1000 ? 1000 : d);
+          tsum = fma(DIST ? prod[q][i] * T.wt[b * R + i] : prod[q][i], pow2i(-d), tsum);
+        }
+        scaled_add(Im[q], Ie[q], tsum, emin);
+        continue;
       }
       bool same = true;
 #pragma unroll

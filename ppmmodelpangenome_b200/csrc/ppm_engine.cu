@@ -57,6 +57,7 @@ struct NvtxRange {
 
 // slices per block of the sweep program: 8; PPM_R=16 is a tuning knob of the global-memory variant (it halves the record
 // and lineage-slot traffic per term but its register need costs as much: no gain measured)
+static bool leaf_pow_enabled() { const char* e = std::getenv("PPM_NO_LEAFPOW"); return !(e && std::atoi(e) != 0); }
 static int program_R(bool deep = false) {
   const char* e = std::getenv("PPM_R");
   return (deep && e && std::atoi(e) == 16) ? 16 : 8;
@@ -115,7 +116,8 @@ struct ppm_engine {
   DevBuf<int> d_bs_xk0;                                  // rows per parameter vector, per-slice integrand of the all-ones row
   DevBuf<uint32_t> d_bs_ones;
   // leaf powers (band_program.h: leaf_pow)
-  DevBuf<int> d_blp_alive, d_bs_n1k[2], d_bs_n1k0, d_bs_base_n1;
+  DevBuf<int> d_blp_alive, d_bs_n1k[2], d_bs_n1k0, d_bs_base_n1, d_lp_alive;
+  DevBuf<double> d_lp_htot, d_slb, d_slc, d_sle;
   DevBuf<double> d_blp_htot, d_blp_op_h, d_blp_leaf_h, d_blp_s1_0, d_bLb, d_bLc, d_bLe, d_bs_s1k[2], d_bs_s1k0, d_bs_base_s1;
   bool sparse = false;            // ppm_set_sparse / PPM_SPARSE: the band kernels multiply dirty lineages only
   DevBuf<int> d_bs_unit_off;
@@ -316,7 +318,7 @@ struct ppm_engine {
     bdev.lp = band.leaf_pow ? 1 : 0; bdev.has_s1 = band.has_s1 ? 1 : 0;
     bdev.n_alive_leaves = d_blp_alive.p; bdev.htot = d_blp_htot.p; bdev.op_leaf_h = d_blp_op_h.p;
     md.lp_max_h = band.leaf_pow ? band.max_leaf_h : 0.;
-    if (band.has_s1) {  // sum of the heights of every pattern's present leaves, once per handle
+    if (band.has_s1 && !prog.has_s1) {  // sum of the heights of every pattern's present leaves, once per handle
       d_blp_s1_0.alloc((size_t)std::max<long long>(n_pat_pad, 32));
       CK(cudaMemsetAsync(d_blp_s1_0.p, 0, sizeof(double) * (size_t)std::max<long long>(n_pat_pad, 32), stream));
       ppm::launch_leaf_height_sums(md, d_blp_leaf_h.p, count, d_blp_s1_0.p, stream);
@@ -357,7 +359,7 @@ struct ppm_engine {
   }
 
   void upload_model_impl(bool deep) {
-    prog = ppm::build_program(tree, program_R(deep), deep);
+    prog = ppm::build_program(tree, program_R(deep), deep, leaf_pow_enabled());
     // shard: contiguous, equal-sized slices of the deduplicated patterns (work per pattern is uniform)
     long long np = pat.n_patterns;
     first = np * shard_rank / shard_world;
@@ -417,6 +419,9 @@ struct ppm_engine {
         !std::getenv("PPM_WORDS_SMEM"))
       md.word_stride = (int)n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
+    md.lp = prog.lp ? 1 : 0; md.has_s1 = prog.has_s1 ? 1 : 0;
+    if (prog.lp) { d_lp_alive.upload(prog.n_alive_leaves, stream); d_lp_htot.upload(prog.htot, stream); }
+    md.lp_alive = d_lp_alive.p; md.lp_htot = d_lp_htot.p;
   }
 
   // Patterns of this shard on the device: word-major (lanes = consecutive patterns read consecutive addresses), bits in
@@ -440,6 +445,15 @@ struct ppm_engine {
       CK(cudaGetLastError());
     }
     md.words = d_words.p;
+    md.lp_s1_0 = nullptr;
+    if (prog.has_s1) {  // leaf powers: sum of the heights of every pattern's present leaves, once per handle
+      d_blp_leaf_h.upload(prog.leaf_h, stream);
+      d_blp_s1_0.alloc((size_t)std::max<long long>(n_pat_pad, 32));
+      CK(cudaMemsetAsync(d_blp_s1_0.p, 0, sizeof(double) * (size_t)std::max<long long>(n_pat_pad, 32), stream));
+      ppm::launch_leaf_height_sums(md, d_blp_leaf_h.p, count, d_blp_s1_0.p, stream);
+      CK(cudaStreamSynchronize(stream));
+      md.lp_s1_0 = d_blp_s1_0.p;
+    }
     // frontier lists of the class sums: pattern-only, so once per handle (count, prefix sums on the host, fill)
     md.fr_off = nullptr; md.fr_nodes = nullptr;
     if (tree.n_nodes <= 65535 && count > 0) {
@@ -478,6 +492,7 @@ struct ppm_engine {
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       d_zrow.alloc((size_t)P * nn); d_zk.alloc((size_t)P * nn); d_zxb.alloc((size_t)P * (std::max(prog.n_blocks, 1) + 1));
       d_zpart.alloc((size_t)P * std::max(tree.n_slices, 1));
+      if (prog.lp) { const size_t nbr = (size_t)P * std::max(prog.n_blocks, 1) * prog.R; d_slb.alloc(nbr); d_slc.alloc(nbr); d_sle.alloc(nbr); }
       if (use_band) {
         d_bop.alloc((size_t)P * std::max<size_t>(band.ops.size(), 1) * ppm::BOP_DOUBLES);
         d_bY.alloc((size_t)P * band.S_pad); d_bU.alloc((size_t)P * band.S_pad);
@@ -490,6 +505,7 @@ struct ppm_engine {
     t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p; t.cherry = d_cherry.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p; t.et1 = nullptr;
     t.zrow = d_zrow.p; t.zk = d_zk.p; t.zxb = d_zxb.p; t.zpart = d_zpart.p;  // expectedTime1 tables only on request
+    t.slb = d_slb.p; t.slc = d_slc.p; t.sle = d_sle.p;
     return t;
   }
 
@@ -731,7 +747,7 @@ static void finish_one(ppm_engine* e, int device, int rank, int world) {
   e->shard_rank = rank; e->shard_world = world;
   if (device < 0) {  // host-only handle: model inspection, no compute
     e->device = -1;
-    e->prog = ppm::build_program(e->tree, program_R());
+    e->prog = ppm::build_program(e->tree, program_R(), false, leaf_pow_enabled());
     long long np = e->pat.n_patterns;
     e->first = np * rank / world;
     e->count = np * (rank + 1) / world - e->first;
@@ -1194,6 +1210,8 @@ int ppm_get_plan(ppm_handle h, int32_t* out16) {
   out16[10] = h->prog.n_blocks;
   out16[11] = h->prog.n_slots;
   out16[12] = h->prog.leaf_u ? 1 : 0;
+  out16[14] = h->prog.lp ? 1 : 0;
+  out16[15] = (h->use_band && h->band.leaf_pow) ? 1 : 0;
   return PPM_OK;
 }
 

@@ -153,7 +153,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 static const size_t kRecRingBytes = 3 * 32 * sizeof(EntryRec);  // per-warp record ring of the global-memory variant
 
 struct StageLayout {
-  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, cherry, leaf, total;
+  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, cherry, leaf, lb, lc, le, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
@@ -165,22 +165,26 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.yy = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.wt = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
   L.uu = o;   o += align16((size_t)m.n_blocks * m.R * sizeof(double));
-  L.leafab = o; o += align16((size_t)m.n_leaves * 2 * sizeof(double2));
-  L.pairq = o; o += align16((size_t)m.n_pairs * 4 * sizeof(double4));
+  // (a leaf-power program never reads the leaf / leaf-pair tables: three per-slice count tables instead)
+  L.leafab = o; o += m.lp ? 0 : align16((size_t)m.n_leaves * 2 * sizeof(double2));
+  L.pairq = o; o += m.lp ? 0 : align16((size_t)m.n_pairs * 4 * sizeof(double4));
+  L.lb = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double)) : 0;
+  L.lc = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double)) : 0;
+  L.le = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double)) : 0;
   L.cherry = o; o += align16((size_t)m.n_cherries * 4 * sizeof(double2));
   L.leaf = o; o += 32;
   L.total = o;
   return L;
 }
 // global-memory variant: the small tables named by `mask` (DS_* bits) are staged in shared memory all the same
-struct DeepStage { size_t pairq, yy, wt, uu, blk, cherry, leafab, oprec, ops, total; };
+struct DeepStage { size_t pairq, yy, wt, uu, blk, cherry, leafab, oprec, ops, lb, lc, le, total; };
 __host__ __device__ inline size_t deep_stage_bytes(const ModelDev& m, int bit) {
   const size_t nbR = (size_t)m.n_blocks * m.R;
   switch (bit) {
-    case DS_PAIRQ: return align16((size_t)m.n_pairs * 4 * sizeof(double4));
-    case DS_SLICES: return 3 * align16(nbR * sizeof(double)) + align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
+    case DS_PAIRQ: return m.lp ? 0 : align16((size_t)m.n_pairs * 4 * sizeof(double4));
+    case DS_SLICES: return (m.lp ? 6 : 3) * align16(nbR * sizeof(double)) + align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
     case DS_CHERRY: return align16((size_t)m.n_cherries * 4 * sizeof(double2));
-    case DS_LEAFAB: return align16((size_t)m.n_leaves * 2 * sizeof(double2));
+    case DS_LEAFAB: return m.lp ? 0 : align16((size_t)m.n_leaves * 2 * sizeof(double2));
     case DS_OPS: return align16((size_t)m.n_ops * OPREC_DOUBLES * sizeof(double)) + align16((size_t)(m.n_ops + 1) * sizeof(SweepOpDev));
   }
   return 0;
@@ -194,6 +198,11 @@ __host__ __device__ inline DeepStage deep_stage_layout(const ModelDev& m, int ma
     D.yy = o; o += align16(nbR * sizeof(double));
     D.wt = o; o += align16(nbR * sizeof(double));
     D.uu = o; o += align16(nbR * sizeof(double));
+    if (m.lp) {
+      D.lb = o; o += align16(nbR * sizeof(double));
+      D.lc = o; o += align16(nbR * sizeof(double));
+      D.le = o; o += align16(nbR * sizeof(double));
+    }
     D.blk = o; o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
   }
   if (mask & DS_CHERRY) { D.cherry = o; o += deep_stage_bytes(m, DS_CHERRY); }
@@ -305,8 +314,14 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       copy16(smem_raw + L.yy, a.t.yy + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.wt, m.slice_wt_pad, align16((size_t)nbR * sizeof(double)));
       copy16(smem_raw + L.uu, a.t.uu + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
-      copy16(smem_raw + L.leafab, a.t.leafab + (size_t)p * m.n_leaves * 2, align16((size_t)m.n_leaves * 2 * sizeof(double2)));
-      copy16(smem_raw + L.pairq, a.t.pairq + (size_t)p * m.n_pairs * 4, align16((size_t)m.n_pairs * 4 * sizeof(double4)));
+      if (!m.lp) {
+        copy16(smem_raw + L.leafab, a.t.leafab + (size_t)p * m.n_leaves * 2, align16((size_t)m.n_leaves * 2 * sizeof(double2)));
+        copy16(smem_raw + L.pairq, a.t.pairq + (size_t)p * m.n_pairs * 4, align16((size_t)m.n_pairs * 4 * sizeof(double4)));
+      } else {
+        copy16(smem_raw + L.lb, a.t.slb + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
+        copy16(smem_raw + L.lc, a.t.slc + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
+        copy16(smem_raw + L.le, a.t.sle + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
+      }
       copy16(smem_raw + L.cherry, a.t.cherry + (size_t)p * m.n_cherries * 4, align16((size_t)m.n_cherries * 4 * sizeof(double2)));
       copy16(smem_raw + L.leaf, a.t.scal + (size_t)p * SC_COUNT + SC_LA0, 32);
       __syncthreads();
@@ -321,6 +336,9 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       T.leafab = reinterpret_cast<const double2*>(smem_raw + L.leafab);
       T.pairq = reinterpret_cast<const double4*>(smem_raw + L.pairq);
       T.cherry = reinterpret_cast<const double2*>(smem_raw + L.cherry);
+      T.lb = reinterpret_cast<const double*>(smem_raw + L.lb);
+      T.lc = reinterpret_cast<const double*>(smem_raw + L.lc);
+      T.le = reinterpret_cast<const double*>(smem_raw + L.le);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
       T.blk = m.blk; T.ops = m.sops;
@@ -332,12 +350,18 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
       T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
       T.cherry = a.t.cherry + (size_t)p * m.n_cherries * 4;
+      T.lb = a.t.slb + (size_t)p * nbR; T.lc = a.t.slc + (size_t)p * nbR; T.le = a.t.sle + (size_t)p * nbR;
       const int sm = a.stage_mask;
       if (sm & DS_PAIRQ) { copy16(smem_raw + DS.pairq, T.pairq, deep_stage_bytes(m, DS_PAIRQ)); T.pairq = reinterpret_cast<const double4*>(smem_raw + DS.pairq); }
       if (sm & DS_SLICES) {
         copy16(smem_raw + DS.yy, T.yy, align16((size_t)nbR * sizeof(double))); T.yy = reinterpret_cast<const double*>(smem_raw + DS.yy);
         copy16(smem_raw + DS.wt, T.wt, align16((size_t)nbR * sizeof(double))); T.wt = reinterpret_cast<const double*>(smem_raw + DS.wt);
         copy16(smem_raw + DS.uu, T.uu, align16((size_t)nbR * sizeof(double))); T.uu = reinterpret_cast<const double*>(smem_raw + DS.uu);
+        if (m.lp) {
+          copy16(smem_raw + DS.lb, T.lb, align16((size_t)nbR * sizeof(double))); T.lb = reinterpret_cast<const double*>(smem_raw + DS.lb);
+          copy16(smem_raw + DS.lc, T.lc, align16((size_t)nbR * sizeof(double))); T.lc = reinterpret_cast<const double*>(smem_raw + DS.lc);
+          copy16(smem_raw + DS.le, T.le, align16((size_t)nbR * sizeof(double))); T.le = reinterpret_cast<const double*>(smem_raw + DS.le);
+        }
         copy16(smem_raw + DS.blk, T.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc))); T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + DS.blk);
       }
       if (sm & DS_CHERRY) { copy16(smem_raw + DS.cherry, T.cherry, deep_stage_bytes(m, DS_CHERRY)); T.cherry = reinterpret_cast<const double2*>(smem_raw + DS.cherry); }
@@ -586,16 +610,14 @@ void launch_sweep(SweepArgs a, const SweepPlan& pl, cudaStream_t s) {
     else launch_sweep_t<8, 4, true>(a, pl, s);
     return;
   }
-  if (a.m.lean && a.m.R == 8 && a.mode == 0 && pl.mode != 2 && a.fact_filter != 3) {
-    // the objective on a lean program (the usual case): HOT kernel for the parameter vectors that are not factored, then
-    // the generic kernel for the factored ones (it exits at once when there are none; skipped when the host knows)
-    a.fact_filter = 1;
+  if (a.m.lean && a.m.lp && a.m.R == 8 && a.mode == 0 && pl.mode != 2) {
+    // the objective on a lean leaf-power program (the usual case: ultrametric tree): HOT kernel, every parameter vector
+    // (leaf powers need no factored form: nothing is expanded); fact_filter 3 (the band kernel's leftovers) is kept
     if (pl.mode == 0) launch_sweep_t<8, 0, false, false, true>(a, pl, s);
     else if (pl.mode == 1) launch_sweep_t<8, 1, false, false, true>(a, pl, s);
     else if (pl.mode == 3) launch_sweep_t<8, 3, false, false, true>(a, pl, s);
     else launch_sweep_t<8, 4, false, false, true>(a, pl, s);
-    if (a.no_factored) return;
-    a.fact_filter = 2;
+    return;
   }
   if (a.m.R == 16) {  // tuning knob (PPM_R=16): global-memory variant only
     if (pl.mode == 4) launch_sweep_t<16, 4>(a, pl, s); else launch_sweep_t<16, 2>(a, pl, s);

@@ -83,6 +83,10 @@ struct ModelDev {
   const uint32_t* fr_off;    // [n_pat + 1] offsets into fr_nodes, or null (trees with more than 65,535 nodes: walked per call)
   const uint16_t* fr_nodes;
   const uint32_t* zero_words;  // n_words * 32 zeros (the all-zero row of add0(), objects.cpp:274-281)
+  // leaf-power sweep program (host_model.h: Program::lp): no leaf entries; per-slice count tables instead
+  int lp, has_s1;
+  const int* lp_alive; const double* lp_htot;  // [n_slices] leaves alive at each slice, sum of their heights
+  const double* lp_s1_0;                       // [n_pat_pad] sum of the heights of every pattern's present leaves (has_s1)
   double lp_max_h;  // leaf-power band program: largest |leaf height| (the prepass keeps parameter vectors with n (lam h)^2 > 1e-12 off it)
 };
 
@@ -108,6 +112,7 @@ struct TablesDev {
   int* zk;               // [P][n_nodes] ... and the renormalisation shift of each node (0 for leaves)
   int* zxb;              // [P][n_blocks+1] sum of the shifts of all nodes formed before each block
   double2* zpart;        // [P][n_slices] per-slice products of the all-zero row as (mantissa, exponent)
+  double* slb; double* slc; double* sle;  // [P][n_blocks*R] leaf powers (sweep program): see BandTables::bLb / bLc / bLe
   double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 

@@ -313,7 +313,7 @@ class Inference:
         a = np.zeros(16, np.int32)
         self._ck(lib().ppm_get_plan(self._h, a.ctypes.data))
         keys = ("band", "band_R", "band_G", "last_kind", "last_mode", "rows_in_place", "deep", "lean", "levels", "band_tiles",
-                "blocks", "slots", "leaf_u", "band_stream")
+                "blocks", "slots", "leaf_u", "band_stream", "sweep_lp", "band_lp")
         return dict(zip(keys, (int(x) for x in a)))
 
     def counters(self):

@@ -142,9 +142,14 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     const bool band_stream = R >= 3000;
     const int band_code = R >= 5000 ? R - 5000 : R >= 3000 ? R - 3000 : R >= 1000 ? R - 1000 : 0;
     if (band_code) R = 8;
+    // |R| in [100, 1000): the sweep program with leaf powers (host_model.h: Program::lp), |R| - 100 slices per block
+    bool sweep_lp = false;
+    if (R >= 100) { sweep_lp = true; R -= 100; }
+    if (R <= -100) { sweep_lp = true; R += 100; }
     const bool deep = R < 0;
     if (deep) R = -R;
-    Program prog = build_program(tree, R, deep);
+    Program prog = build_program(tree, R, deep, sweep_lp);
+    if (sweep_lp && !prog.lp) throw std::runtime_error("sweep program: leaf powers refused (leaf heights)");
     BandProgram bp;
     if (band_code) {
       bp = build_band_program(tree, prog, band_code % 100, band_code / 100, band_stream, band_lp);
@@ -188,6 +193,14 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     md.n_pairs = prog.n_pairs; md.leaf_node = prog.leaf_node_dev.data();
     md.words = wm.data(); md.n_pat = count; md.n_pat_pad = count;
     md.counts = pat.counts.data(); md.mrca = pat.mrca.data(); md.freq = pat.freq.data(); md.zero_words = zeros.data();
+    md.lp = prog.lp ? 1 : 0; md.has_s1 = prog.has_s1 ? 1 : 0;
+    md.lp_alive = prog.n_alive_leaves.data(); md.lp_htot = prog.htot.data();
+    std::vector<double> s1_0((size_t)std::max<long long>(count, 1), 0.);
+    if (prog.has_s1)
+      for (long long j = 0; j < count; j++)
+        for (int pos = 0; pos < tree.n_leaves; pos++)
+          if ((wm[(size_t)(pos >> 5) * count + j] >> (pos & 31)) & 1u) s1_0[j] += prog.leaf_h[pos];
+    md.lp_s1_0 = s1_0.data();
 
     const size_t nn = tree.n_nodes;
     std::vector<double4> cls(P * nn);
@@ -209,6 +222,8 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<double2> zrow((size_t)P * nn), zpart((size_t)P * std::max(tree.n_slices, 1));
     std::vector<int> zk((size_t)P * nn), zxb((size_t)P * (std::max(prog.n_blocks, 1) + 1));
     t.zrow = zrow.data(); t.zk = zk.data(); t.zxb = zxb.data(); t.zpart = zpart.data();
+    std::vector<double> slb((size_t)P * std::max(prog.n_blocks, 1) * prog.R), slc(slb.size()), sle(slb.size());
+    t.slb = slb.data(); t.slc = slc.data(); t.sle = sle.data();
 
     // two items per "warp" as on the device (NI = 2), one lane each
     const int NI = 2;
@@ -236,6 +251,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.leafab = leafab.data() + (size_t)p * md.n_leaves * 2;
           T.pairq = pairq.data() + (size_t)p * md.n_pairs * 4;
           T.cherry = cherry.data() + (size_t)p * md.n_cherries * 4;
+          T.lb = slb.data() + (size_t)p * md.n_blocks * md.R; T.lc = slc.data() + (size_t)p * md.n_blocks * md.R; T.le = sle.data() + (size_t)p * md.n_blocks * md.R;
           double c[2] = {0., 0.};
           if (dist && prog.R == 8 && deep) sweep_items<8, 2, true, SlotsMem, true>(a, T, p, bt, 0, mem, c, nullptr);
           else if (dist && prog.R == 8) sweep_items<8, 2, false, SlotsMem, true>(a, T, p, bt, 0, mem, c, nullptr);

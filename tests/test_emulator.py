@@ -39,10 +39,17 @@ def emu():
 
 
 @pytest.mark.parametrize("name", ["ref_test", "syn12", "syn100", "cat40", "syn300"])
-@pytest.mark.parametrize("R", [8, 4, 12, 16, -8, -16])  # < 0: the deep-prefetch path of the global-memory variant (default there: 16)
+# < 0: the deep-prefetch path of the global-memory variant (default there: 16); |R| > 100: the leaf-power program (the alive
+# leaves of a slice as one exp2 of count tables, first-order in the leaf heights: the golden trees carry ape's 10-digit lengths)
+@pytest.mark.parametrize("R", [8, 4, 12, 16, -8, -16, 108, 104, 116, -108, -116])
 def test_kernel_bodies_reproduce_reference_golden(golden, emu, name, R):
     g = golden(name)
-    ll, i2, parts, comp, cat = emu(g.tree, g.pa, False, g.params, R=R, n_rows=g.meta["nRep"])
+    try:
+        ll, i2, parts, comp, cat = emu(g.tree, g.pa, False, g.params, R=R, n_rows=g.meta["nRep"])
+    except RuntimeError as e:
+        if abs(R) > 100 and "refused" in str(e):
+            pytest.skip("leaf powers refused for this tree: " + str(e))
+        raise
     for k, r in enumerate(g.results):
         assert rel(ll[k], r["ll"]) <= 1e-12, (name, k, ll[k], r["ll"])
         assert rel(i2[k], r["i2"]) <= 1e-12
@@ -62,7 +69,7 @@ def test_deduplicated_input_gives_the_same_loglik(golden, emu):
 
 
 @pytest.mark.parametrize("name", ["ref_test", "syn12", "syn100", "cat40"])
-@pytest.mark.parametrize("R", [8, -8])
+@pytest.mark.parametrize("R", [8, -8, 108, -108])
 def test_posterior_outputs_reproduce_reference(golden, emu, name, R):
     """expectedTime1 / expectedTime2_aux / expectedGains (functions.cpp:582-757) from the kernel bodies against
     tests/golden/posterior_*.npz (written by the unmodified reference, oracle/gen_golden_posterior.py)."""
@@ -73,7 +80,12 @@ def test_posterior_outputs_reproduce_reference(golden, emu, name, R):
     for g2, want in zip(z["gains_g2"], z["gains"]):
         emu.lib.emu_set_posterior_outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         emu.lib.emu_set_posterior_outputs(et1.ctypes.data, dist.ctypes.data, float(g2), C.byref(gains))
-        emu(g.tree, g.pa, False, z["params"], R=R, want_comp=False)
+        try:
+            emu(g.tree, g.pa, False, z["params"], R=R, want_comp=False)
+        except RuntimeError as e:
+            if abs(R) > 100 and "refused" in str(e):
+                pytest.skip("leaf powers refused for this tree: " + str(e))
+            raise
         assert rel(gains.value, want) <= 1e-10, (g2, gains.value, want)
     assert np.allclose(et1, z["et1"], rtol=1e-9, atol=0)
     assert np.allclose(dist, z["dist"], rtol=1e-9, atol=1e-300)
