@@ -72,11 +72,10 @@ PPM_HD void scaled_add(double& Im, int& Ie, double v, int e) {  // (Im * 2^-Ie) 
   }
 }
 
-// Leaf powers: 2^s = p * 2^k with p in [0.70, 1.42]; s <= ~0 is the log2 of a product of leaf terms (band_program.h: leaf_pow).
-// Round to nearest integer with the 1.5 * 2^52 trick, then exp(r ln 2) by its Taylor polynomial of degree 13 on |r| <= 1/2
-// (remainder < 5e-18).  s below -1e9 (an impossible observation) is clamped: the slice then weighs 2^-1e9.
+// Leaf powers: 2^s = p * 2^k with p in [0.70, 1.42]; s is the log2 of a product of leaf terms (band_program.h: leaf_pow), |s| < 2^31
+// (the prepass clamps the log2 of an impossible observation at -1e4 per leaf).  Round to the nearest integer with the 1.5 * 2^52
+// trick, then 2^r on |r| <= 1/2 by the degree-10 Chebyshev interpolant (relative error 3.1e-16).
 PPM_HD double lp_pow2(double s, int& k) {
-  s = fmax(s, -1.0e9);
   const double magic = 6755399441055744.0;
   const double t = s + magic;
 #if defined(__CUDA_ARCH__)
@@ -84,22 +83,27 @@ PPM_HD double lp_pow2(double s, int& k) {
 #else
   { long long b; memcpy(&b, &t, 8); k = (int)(uint32_t)b; }
 #endif
-  const double x = (s - (t - magic)) * 0.693147180559945309417232;
-  double p = 1.6059043836821613e-10;           // 1/13!
-  p = fma(p, x, 2.08767569878681e-09);         // 1/12!
-  p = fma(p, x, 2.505210838544172e-08);        // 1/11!
-  p = fma(p, x, 2.755731922398589e-07);        // 1/10!
-  p = fma(p, x, 2.7557319223985893e-06);       // 1/9!
-  p = fma(p, x, 2.48015873015873e-05);         // 1/8!
-  p = fma(p, x, 0.0001984126984126984);        // 1/7!
-  p = fma(p, x, 0.001388888888888889);         // 1/6!
-  p = fma(p, x, 0.008333333333333333);         // 1/5!
-  p = fma(p, x, 0.041666666666666664);         // 1/4!
-  p = fma(p, x, 0.16666666666666666);          // 1/3!
-  p = fma(p, x, 0.5);
-  p = fma(p, x, 1.);
-  p = fma(p, x, 1.);
+  const double r = s - (t - magic);
+  double p = 7.072585949269223e-09;
+  p = fma(p, r, 1.0208690299958306e-07);
+  p = fma(p, r, 1.321544258792169e-06);
+  p = fma(p, r, 1.5252657260200837e-05);
+  p = fma(p, r, 0.0001540353044173605);
+  p = fma(p, r, 0.0013333558230164974);
+  p = fma(p, r, 0.009618129107606888);
+  p = fma(p, r, 0.05550410866444772);
+  p = fma(p, r, 0.24022650695910097);
+  p = fma(p, r, 0.69314718055995);
+  p = fma(p, r, 1.0);
   return p;
+}
+// acc += a * b on the slices at or after i0 (a predicated DFMA: no select instructions)
+PPM_HD void lp_fma_ge(double& acc, double a, double b, int i, int i0) {
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %3, %4;\n\t@p fma.rn.f64 %0, %1, %2, %0;\n\t}" : "+d"(acc) : "d"(a), "d"(b), "r"(i), "r"(i0));
+#else
+  if (i >= i0) acc = fma(a, b, acc);
+#endif
 }
 
 // Mobile merge of two child lineages (x, y) = (a, d): m0 = x - k0 y, m1 = x + k1 y along each child's branch, multiplied
@@ -319,19 +323,21 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
     t.uu[(size_t)p * n_pad + j] = (j < m.n_slices) ? 1. - exp(-lam * m.slice_t[j]) : 0.;
     if (m.lp) {  // leaf powers: see prepass_band_body
       double lb = 0., lc = 0., le = 0.;
-      if (j < m.n_slices) {
+      if (m.n_slices > 0) {
+        // (padding slices of the last block -- weight 0 -- copy the last real slice: the block's exponents stay close together)
+        const int jj = j < m.n_slices ? j : m.n_slices - 1;
         const double e2 = par[6], e1 = par[7];
-        const double E = exp(-lam * m.slice_t[j]), u = 1. - E;
+        const double E = exp(-lam * m.slice_t[jj]), u = 1. - E;
         double lg[2], g[2];
         for (int x = 0; x < 2; x++) {
           const double m0 = x ? e1 : 1 - e1, m1 = x ? 1 - e2 : e2, d = m1 - m0;  // objects.cpp:407-408
           const double f = fma(pi1 * d, u, m0);
-          lg[x] = f > 0. ? log2(f) : -1e7;
+          lg[x] = f > 0. ? fmax(log2(f), -1e4) : -1e4;
           g[x] = f > 0. ? -pi1 * d * lam * E / (f * 0.693147180559945309417232) : 0.;
         }
-        lb = (double)m.lp_alive[j] * lg[0] + g[0] * m.lp_htot[j]; lc = lg[1] - lg[0]; le = g[1] - g[0];
+        lb = (double)m.lp_alive[jj] * lg[0] + g[0] * m.lp_htot[jj]; lc = lg[1] - lg[0]; le = g[1] - g[0];
       }
-      t.slb[(size_t)p * n_pad + j] = lb; t.slc[(size_t)p * n_pad + j] = lc; t.sle[(size_t)p * n_pad + j] = le;
+      t.slb[(size_t)p * n_pad + j] = lb; t.slce[(size_t)p * n_pad + j] = make_double2(lc, le);
     }
   } else if (i <= m.n_entries + n_pad + m.n_ops) {
     // per-op record: the branch tables of the two children, contiguous (no dependent index loads in the sweep)
@@ -437,7 +443,7 @@ PPM_HD void prepass_band_body(const ModelDev& m, const TablesDev& t, const BandD
       for (int x = 0; x < 2; x++) {
         const double m0 = x ? e1 : 1 - e1, m1 = x ? 1 - e2 : e2, d = m1 - m0;  // objects.cpp:407-408
         const double f = fma(pi1 * d, u, m0);
-        lg[x] = f > 0. ? log2(f) : -1e7;  // (an impossible observation: any such leaf sends the product to 0)
+        lg[x] = f > 0. ? fmax(log2(f), -1e4) : -1e4;  // (an impossible observation: any such leaf sends the product to ~0)
         g[x] = f > 0. ? -pi1 * d * lam * E / (f * 0.693147180559945309417232) : 0.;
       }
       const bool real = j < m.n_slices;
@@ -713,7 +719,7 @@ struct ItemTables {
   const double2* leafab;  // [n_leaves][2] u-form leaf terms {alpha, beta}
   const double4* pairq;   // [n_pairs][4] u-form pair quadratics
   const double2* cherry;  // [n_cherries][4] cherry node partials by observation pair
-  const double* lb; const double* lc; const double* le;  // [n_blocks * R] leaf powers (ModelDev::lp)
+  const double* lb; const double2* lce;  // [n_blocks * R] leaf powers (ModelDev::lp): base | (count coefficient, height coefficient)
 };
 
 // the two 32-bit halves of a record's K field (leaf-pair records)
@@ -877,17 +883,15 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   auto leaf_deaths = [&](int q, int b, bool real, int i0, uint32_t bl, uint32_t br, double hl, double hr) {
     const int cnt = (int)(bl + br);
     n1[q] -= cnt;
+    const double dn = -(double)cnt;
+    double dh = 0.;
+    if (hs1) { dh = -((bl ? hl : 0.) + (br ? hr : 0.)); S1[q] += dh; }
     if (real) {
-      const double dn = -(double)cnt;
 #pragma unroll
-      for (int i = 0; i < R; i++) lpacc[q][i] = fma(i >= i0 ? dn : 0., T.lc[b * R + i], lpacc[q][i]);
-    }
-    if (hs1) {
-      const double dh = (bl ? hl : 0.) + (br ? hr : 0.);
-      S1[q] -= dh;
-      if (real) {
-#pragma unroll
-        for (int i = 0; i < R; i++) lpacc[q][i] = fma(i >= i0 ? -dh : 0., T.le[b * R + i], lpacc[q][i]);
+      for (int i = 0; i < R; i++) {
+        const double2 ce = T.lce[b * R + i];
+        lp_fma_ge(lpacc[q][i], dn, ce.x, i, i0);
+        if (hs1) lp_fma_ge(lpacc[q][i], dh, ce.y, i, i0);
       }
     }
   };
@@ -908,8 +912,9 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         for (int q = 0; q < NI; q++)
 #pragma unroll
           for (int i = 0; i < R; i++) {
-            lpacc[q][i] = fma((double)n1[q], T.lc[b * R + i], T.lb[b * R + i]);
-            if (hs1) lpacc[q][i] = fma(S1[q], T.le[b * R + i], lpacc[q][i]);
+            const double2 ce = T.lce[b * R + i];
+            lpacc[q][i] = fma((double)n1[q], ce.x, T.lb[b * R + i]);
+            if (hs1) lpacc[q][i] = fma(S1[q], ce.y, lpacc[q][i]);
           }
       }
     }
@@ -1480,14 +1485,15 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         }
       }
       if (lp) {  // the slices' exponents differ as a rule: align them to the smallest (zero products -- padding slices -- aside)
-        int emin = 0x3fffffff;
+        // (padding slices carry weight 0 and the tables of the last real slice, so their exponents do not stand out)
+        int emin = ex[q][0];
 #pragma unroll
-        for (int i = 0; i < R; i++) { const int e = prod[q][i] != 0. ? ex[q][i] : 0x3fffffff; emin = e < emin ? e : emin; }
+        for (int i = 1; i < R; i++) emin = ex[q][i] < emin ? ex[q][i] : emin;
         double tsum = 0.;
 #pragma unroll
         for (int i = 0; i < R; i++) {
           int d = ex[q][i] - emin;
-          d = d < 0 ? 0 : (d > 1000 ? 1000 : d);
+          d = d > 1000 ? 1000 : d;
           tsum = fma(DIST ? prod[q][i] * T.wt[b * R + i] : prod[q][i], pow2i(-d), tsum);
         }
         scaled_add(Im[q], Ie[q], tsum, emin);

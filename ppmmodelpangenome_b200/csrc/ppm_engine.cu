@@ -117,7 +117,8 @@ struct ppm_engine {
   DevBuf<uint32_t> d_bs_ones;
   // leaf powers (band_program.h: leaf_pow)
   DevBuf<int> d_blp_alive, d_bs_n1k[2], d_bs_n1k0, d_bs_base_n1, d_lp_alive;
-  DevBuf<double> d_lp_htot, d_slb, d_slc, d_sle;
+  DevBuf<double> d_lp_htot, d_slb;
+  DevBuf<double2> d_slce;
   DevBuf<double> d_blp_htot, d_blp_op_h, d_blp_leaf_h, d_blp_s1_0, d_bLb, d_bLc, d_bLe, d_bs_s1k[2], d_bs_s1k0, d_bs_base_s1;
   bool sparse = false;            // ppm_set_sparse / PPM_SPARSE: the band kernels multiply dirty lineages only
   DevBuf<int> d_bs_unit_off;
@@ -492,7 +493,7 @@ struct ppm_engine {
       d_params.alloc((size_t)P * 8); d_ll.alloc(P); d_i2.alloc(P); d_i2_override.alloc(P);
       d_zrow.alloc((size_t)P * nn); d_zk.alloc((size_t)P * nn); d_zxb.alloc((size_t)P * (std::max(prog.n_blocks, 1) + 1));
       d_zpart.alloc((size_t)P * std::max(tree.n_slices, 1));
-      if (prog.lp) { const size_t nbr = (size_t)P * std::max(prog.n_blocks, 1) * prog.R; d_slb.alloc(nbr); d_slc.alloc(nbr); d_sle.alloc(nbr); }
+      if (prog.lp) { const size_t nbr = (size_t)P * std::max(prog.n_blocks, 1) * prog.R; d_slb.alloc(nbr); d_slce.alloc(nbr); }
       if (use_band) {
         d_bop.alloc((size_t)P * std::max<size_t>(band.ops.size(), 1) * ppm::BOP_DOUBLES);
         d_bY.alloc((size_t)P * band.S_pad); d_bU.alloc((size_t)P * band.S_pad);
@@ -505,7 +506,7 @@ struct ppm_engine {
     t.P = P; t.params = d_par; t.cls = d_cls.p; t.kap = d_kap.p; t.d1u = d_d1u.p; t.recs = d_recs.p; t.yy = d_yy.p; t.oprec = d_oprec.p; t.clsT = d_clsT.p; t.a01 = d_a01.p; t.uu = d_uu.p; t.leafab = d_leafab.p; t.pairq = d_pairq.p; t.cherry = d_cherry.p;
     t.scal = d_scal.p; t.zeta = d_zeta.p; t.et1 = nullptr;
     t.zrow = d_zrow.p; t.zk = d_zk.p; t.zxb = d_zxb.p; t.zpart = d_zpart.p;  // expectedTime1 tables only on request
-    t.slb = d_slb.p; t.slc = d_slc.p; t.sle = d_sle.p;
+    t.slb = d_slb.p; t.slce = d_slce.p;
     return t;
   }
 

@@ -153,7 +153,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 static const size_t kRecRingBytes = 3 * 32 * sizeof(EntryRec);  // per-warp record ring of the global-memory variant
 
 struct StageLayout {
-  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, cherry, leaf, lb, lc, le, total;
+  size_t recs, blk, ops, oprec, yy, wt, uu, leafab, pairq, cherry, leaf, lb, lce, total;
 };
 __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   StageLayout L;
@@ -169,15 +169,14 @@ __host__ __device__ inline StageLayout stage_layout(const ModelDev& m) {
   L.leafab = o; o += m.lp ? 0 : align16((size_t)m.n_leaves * 2 * sizeof(double2));
   L.pairq = o; o += m.lp ? 0 : align16((size_t)m.n_pairs * 4 * sizeof(double4));
   L.lb = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double)) : 0;
-  L.lc = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double)) : 0;
-  L.le = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double)) : 0;
+  L.lce = o; o += m.lp ? align16((size_t)m.n_blocks * m.R * sizeof(double2)) : 0;
   L.cherry = o; o += align16((size_t)m.n_cherries * 4 * sizeof(double2));
   L.leaf = o; o += 32;
   L.total = o;
   return L;
 }
 // global-memory variant: the small tables named by `mask` (DS_* bits) are staged in shared memory all the same
-struct DeepStage { size_t pairq, yy, wt, uu, blk, cherry, leafab, oprec, ops, lb, lc, le, total; };
+struct DeepStage { size_t pairq, yy, wt, uu, blk, cherry, leafab, oprec, ops, lb, lce, total; };
 __host__ __device__ inline size_t deep_stage_bytes(const ModelDev& m, int bit) {
   const size_t nbR = (size_t)m.n_blocks * m.R;
   switch (bit) {
@@ -200,8 +199,7 @@ __host__ __device__ inline DeepStage deep_stage_layout(const ModelDev& m, int ma
     D.uu = o; o += align16(nbR * sizeof(double));
     if (m.lp) {
       D.lb = o; o += align16(nbR * sizeof(double));
-      D.lc = o; o += align16(nbR * sizeof(double));
-      D.le = o; o += align16(nbR * sizeof(double));
+      D.lce = o; o += align16(nbR * sizeof(double2));
     }
     D.blk = o; o += align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc));
   }
@@ -319,8 +317,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
         copy16(smem_raw + L.pairq, a.t.pairq + (size_t)p * m.n_pairs * 4, align16((size_t)m.n_pairs * 4 * sizeof(double4)));
       } else {
         copy16(smem_raw + L.lb, a.t.slb + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
-        copy16(smem_raw + L.lc, a.t.slc + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
-        copy16(smem_raw + L.le, a.t.sle + (size_t)p * nbR, align16((size_t)nbR * sizeof(double)));
+        copy16(smem_raw + L.lce, a.t.slce + (size_t)p * nbR, align16((size_t)nbR * sizeof(double2)));
       }
       copy16(smem_raw + L.cherry, a.t.cherry + (size_t)p * m.n_cherries * 4, align16((size_t)m.n_cherries * 4 * sizeof(double2)));
       copy16(smem_raw + L.leaf, a.t.scal + (size_t)p * SC_COUNT + SC_LA0, 32);
@@ -337,8 +334,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       T.pairq = reinterpret_cast<const double4*>(smem_raw + L.pairq);
       T.cherry = reinterpret_cast<const double2*>(smem_raw + L.cherry);
       T.lb = reinterpret_cast<const double*>(smem_raw + L.lb);
-      T.lc = reinterpret_cast<const double*>(smem_raw + L.lc);
-      T.le = reinterpret_cast<const double*>(smem_raw + L.le);
+      T.lce = reinterpret_cast<const double2*>(smem_raw + L.lce);
     } else {
       T.recs = a.t.recs + (size_t)p * (m.n_entries + 1);
       T.blk = m.blk; T.ops = m.sops;
@@ -350,7 +346,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
       T.leafab = a.t.leafab + (size_t)p * m.n_leaves * 2;
       T.pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
       T.cherry = a.t.cherry + (size_t)p * m.n_cherries * 4;
-      T.lb = a.t.slb + (size_t)p * nbR; T.lc = a.t.slc + (size_t)p * nbR; T.le = a.t.sle + (size_t)p * nbR;
+      T.lb = a.t.slb + (size_t)p * nbR; T.lce = a.t.slce + (size_t)p * nbR;
       const int sm = a.stage_mask;
       if (sm & DS_PAIRQ) { copy16(smem_raw + DS.pairq, T.pairq, deep_stage_bytes(m, DS_PAIRQ)); T.pairq = reinterpret_cast<const double4*>(smem_raw + DS.pairq); }
       if (sm & DS_SLICES) {
@@ -359,8 +355,7 @@ __global__ void __launch_bounds__((MODE == 0 || MODE == 3 || MODE == 4) ? 384 : 
         copy16(smem_raw + DS.uu, T.uu, align16((size_t)nbR * sizeof(double))); T.uu = reinterpret_cast<const double*>(smem_raw + DS.uu);
         if (m.lp) {
           copy16(smem_raw + DS.lb, T.lb, align16((size_t)nbR * sizeof(double))); T.lb = reinterpret_cast<const double*>(smem_raw + DS.lb);
-          copy16(smem_raw + DS.lc, T.lc, align16((size_t)nbR * sizeof(double))); T.lc = reinterpret_cast<const double*>(smem_raw + DS.lc);
-          copy16(smem_raw + DS.le, T.le, align16((size_t)nbR * sizeof(double))); T.le = reinterpret_cast<const double*>(smem_raw + DS.le);
+          copy16(smem_raw + DS.lce, T.lce, align16((size_t)nbR * sizeof(double2))); T.lce = reinterpret_cast<const double2*>(smem_raw + DS.lce);
         }
         copy16(smem_raw + DS.blk, T.blk, align16((size_t)(m.n_blocks + 1) * sizeof(BlockDesc))); T.blk = reinterpret_cast<const BlockDesc*>(smem_raw + DS.blk);
       }

@@ -112,7 +112,7 @@ struct TablesDev {
   int* zk;               // [P][n_nodes] ... and the renormalisation shift of each node (0 for leaves)
   int* zxb;              // [P][n_blocks+1] sum of the shifts of all nodes formed before each block
   double2* zpart;        // [P][n_slices] per-slice products of the all-zero row as (mantissa, exponent)
-  double* slb; double* slc; double* sle;  // [P][n_blocks*R] leaf powers (sweep program): see BandTables::bLb / bLc / bLe
+  double* slb; double2* slce;  // [P][n_blocks*R] leaf powers (sweep program): BandTables::bLb | (bLc, bLe)
   double* et1;           // [P][n_nodes] expected introduction time of a Private gene whose MRCA is the node (expectedTime1)
 };
 

@@ -222,8 +222,9 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     std::vector<double2> zrow((size_t)P * nn), zpart((size_t)P * std::max(tree.n_slices, 1));
     std::vector<int> zk((size_t)P * nn), zxb((size_t)P * (std::max(prog.n_blocks, 1) + 1));
     t.zrow = zrow.data(); t.zk = zk.data(); t.zxb = zxb.data(); t.zpart = zpart.data();
-    std::vector<double> slb((size_t)P * std::max(prog.n_blocks, 1) * prog.R), slc(slb.size()), sle(slb.size());
-    t.slb = slb.data(); t.slc = slc.data(); t.sle = sle.data();
+    std::vector<double> slb((size_t)P * std::max(prog.n_blocks, 1) * prog.R);
+    std::vector<double2> slce(slb.size());
+    t.slb = slb.data(); t.slce = slce.data();
 
     // two items per "warp" as on the device (NI = 2), one lane each
     const int NI = 2;
@@ -251,7 +252,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
           T.leafab = leafab.data() + (size_t)p * md.n_leaves * 2;
           T.pairq = pairq.data() + (size_t)p * md.n_pairs * 4;
           T.cherry = cherry.data() + (size_t)p * md.n_cherries * 4;
-          T.lb = slb.data() + (size_t)p * md.n_blocks * md.R; T.lc = slc.data() + (size_t)p * md.n_blocks * md.R; T.le = sle.data() + (size_t)p * md.n_blocks * md.R;
+          T.lb = slb.data() + (size_t)p * md.n_blocks * md.R; T.lce = slce.data() + (size_t)p * md.n_blocks * md.R;
           double c[2] = {0., 0.};
           if (dist && prog.R == 8 && deep) sweep_items<8, 2, true, SlotsMem, true>(a, T, p, bt, 0, mem, c, nullptr);
           else if (dist && prog.R == 8) sweep_items<8, 2, false, SlotsMem, true>(a, T, p, bt, 0, mem, c, nullptr);
