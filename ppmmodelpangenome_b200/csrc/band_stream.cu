@@ -559,6 +559,19 @@ __global__ void leaf_height_sums_kernel(ModelDev m, const double* leaf_h, long l
   }
   s1_0[pat] = s;
 }
+__global__ void leaf_height_sums_q_kernel(ModelDev m, const int* leaf_hq, long long count, int* s1q_0) {
+  const long long pat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pat >= count) return;
+  int s = 0;
+  for (int w = 0; w < m.n_words; w++) {
+    uint32_t x = m.words[(size_t)w * m.n_pat_pad + pat];
+    while (x) { const int bq = __ffs((int)x) - 1; x &= x - 1u; s += leaf_hq[32 * w + bq]; }
+  }
+  s1q_0[pat] = s;
+}
+void launch_leaf_height_sums_q(const ModelDev& m, const int* leaf_hq, long long count, int* s1q_0, cudaStream_t s) {
+  if (count > 0) leaf_height_sums_q_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(m, leaf_hq, count, s1q_0);
+}
 void launch_leaf_height_sums(const ModelDev& m, const double* leaf_h, long long count, double* s1_0, cudaStream_t s) {
   if (count > 0) leaf_height_sums_kernel<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(m, leaf_h, count, s1_0);
 }

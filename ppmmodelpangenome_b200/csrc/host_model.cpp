@@ -603,6 +603,17 @@ Program build_program(const Tree& t, int R, bool deep, bool leaf_pow) {
     }
   }
   pg.n_slots = std::max(n_slots, 1);
+  if (pg.lp) {  // leaf heights as integers: |h| / hunit <= 2^14, so the sum over 65,535 leaves stays inside 31 bits
+    pg.hunit = pg.has_s1 ? max_leaf_h / 16384. : 0.;
+    auto hq = [&](int v) { return pg.has_s1 ? (int32_t)std::lround(t.height[v] / pg.hunit) : 0; };
+    pg.leaf_hq.assign(nl, 0);
+    for (int v = 0; v < nn; v++) if (t.left[v] < 0 && nn > 1) pg.leaf_hq[dpos(v)] = hq(v);
+    for (size_t o = 0; o < pg.ops.size(); o++) {
+      const NodeOp& op = pg.ops[o];
+      pg.sops[o].hlq = op.lref < 0 ? hq(op.lnode) : 0;
+      pg.sops[o].hrq = op.rref < 0 ? hq(op.rnode) : 0;
+    }
+  }
 
   // entries: per block, four typed segments (see BlockDesc), each sorted by reference
   struct Ent { int ref, i0, i1, node; bool leaf; };

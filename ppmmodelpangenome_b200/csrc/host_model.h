@@ -84,6 +84,8 @@ struct SweepOp {
   int32_t mself, ml, mr;
   int32_t comb;  // 1 / 2: the left / right child's prefix and the new node's suffix are complementary and cover the block: one
                  // update with per-slice operands serves both (general ops only)
+  int32_t hlq, hrq;  // leaf powers: heights of a leaf left / right child in units of Program::hunit (0 for an internal child)
+  int32_t pad0, pad1;
 };
 struct BlockDescHost {  // entry segments: see BlockDesc in ppm_kernels.cuh
   int32_t slice0, nslices, op0, op1, e_slot0, e_pair0, e_leafu0, e_leaf0, e_pleaf0, e_pslot0, e_end;
@@ -116,6 +118,8 @@ struct Program {
   std::vector<int32_t> n_alive_leaves;            // [n_slices]
   std::vector<double> htot;                       // [n_slices] sum of the alive leaves' heights
   std::vector<double> leaf_h;                     // [n_leaves] height by device bit position
+  double hunit = 0;                               // the sweep counts leaf heights in integer units of max_leaf_h / 2^14
+  std::vector<int32_t> leaf_hq;                   // [n_leaves] height by device bit position, in units of hunit
   // modelled FP64 instruction count per pattern-eval of the main kernel
   double fp64_instr_per_eval = 0;
 };

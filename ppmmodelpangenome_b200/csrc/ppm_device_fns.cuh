@@ -97,6 +97,14 @@ PPM_HD double lp_pow2(double s, int& k) {
   p = fma(p, r, 1.0);
   return p;
 }
+// int -> double on the FP64 pipe (one DADD): 2^52 + 2^31 + n assembled from its two words, minus the bias
+PPM_HD double lp_i2d(int n) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(0x43300000, n ^ (int)0x80000000) - 4503601774854144.0;
+#else
+  return (double)n;
+#endif
+}
 // acc += a * b on the slices at or after i0 (a predicated DFMA: no select instructions)
 PPM_HD void lp_fma_ge(double& acc, double a, double b, int i, int i0) {
 #if defined(__CUDA_ARCH__)
@@ -337,7 +345,7 @@ PPM_HD void prepass_tables_body(const ModelDev& m, const TablesDev& t, int p, in
         }
         lb = (double)m.lp_alive[jj] * lg[0] + g[0] * m.lp_htot[jj]; lc = lg[1] - lg[0]; le = g[1] - g[0];
       }
-      t.slb[(size_t)p * n_pad + j] = lb; t.slce[(size_t)p * n_pad + j] = make_double2(lc, le);
+      t.slb[(size_t)p * n_pad + j] = lb; t.slce[(size_t)p * n_pad + j] = make_double2(lc, le * m.lp_hunit);  // (the sweep counts heights in units of lp_hunit)
     }
   } else if (i <= m.n_entries + n_pad + m.n_ops) {
     // per-op record: the branch tables of the two children, contiguous (no dependent index loads in the sweep)
@@ -866,33 +874,30 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
   const bool factored = HOT ? false : (sc[SC_FACTORED] != 0.);
 #pragma unroll
   for (int q = 0; q < NI; q++) { X[q] = 0; Im[q] = 0.; Ie[q] = 0x3fffffff; }
-  // Leaf powers (Program::lp; HOT kernels serve such programs only): n1 = the lane's present leaves still alive at the start of
-  // the block, S1 = the sum of their heights; lpacc[i] = log2 of the product of the alive leaves at slice i, updated as leaves
-  // die at the node ops and turned into one factor per slice at the block's end.
+  // Leaf powers (Program::lp; HOT kernels serve such programs only): the product of the alive leaves of a slice is one exp2 of
+  // count tables x (present alive leaves, sum of their heights).
   const bool lp = HOT ? true : (m.lp != 0);
   const bool hs1 = lp && m.has_s1 != 0;
-  int n1[NI]; double S1[NI], lpacc[NI][R];
+  // n1 / s1q: the lane's present leaves still alive at the start of the block and the sum of their heights (integer units of
+  // lp_hunit); nv / sv: the same per slice of the block, lowered as leaves die at the node ops -- integer work only, one exp2 per
+  // slice at the block's end
+  int n1[NI], s1q[NI], nv[NI][R], sv[NI][R];
 #pragma unroll
   for (int q = 0; q < NI; q++) {
     n1[q] = (lp && active[q]) ? m.freq[pat[q]] : 0;
-    S1[q] = (hs1 && active[q]) ? m.lp_s1_0[pat[q]] : 0.;
+    s1q[q] = (hs1 && active[q]) ? m.lp_s1q_0[pat[q]] : 0;
 #pragma unroll
-    for (int i = 0; i < R; i++) lpacc[q][i] = 0.;
+    for (int i = 0; i < R; i++) { nv[q][i] = 0; sv[q][i] = 0; }
   }
   // a node op whose leaf children (present: bl / br) die at slice i0 of the block
-  auto leaf_deaths = [&](int q, int b, bool real, int i0, uint32_t bl, uint32_t br, double hl, double hr) {
+  auto leaf_deaths = [&](int q, int i0, uint32_t bl, uint32_t br, int hlq, int hrq) {
     const int cnt = (int)(bl + br);
-    n1[q] -= cnt;
-    const double dn = -(double)cnt;
-    double dh = 0.;
-    if (hs1) { dh = -((bl ? hl : 0.) + (br ? hr : 0.)); S1[q] += dh; }
-    if (real) {
+    const int dq = (bl ? hlq : 0) + (br ? hrq : 0);
+    n1[q] -= cnt; s1q[q] -= dq;
 #pragma unroll
-      for (int i = 0; i < R; i++) {
-        const double2 ce = T.lce[b * R + i];
-        lp_fma_ge(lpacc[q][i], dn, ce.x, i, i0);
-        if (hs1) lp_fma_ge(lpacc[q][i], dh, ce.y, i, i0);
-      }
+    for (int i = 0; i < R; i++) {
+      nv[q][i] -= i >= i0 ? cnt : 0;
+      sv[q][i] -= i >= i0 ? dq : 0;
     }
   };
 
@@ -911,11 +916,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
 #pragma unroll
         for (int q = 0; q < NI; q++)
 #pragma unroll
-          for (int i = 0; i < R; i++) {
-            const double2 ce = T.lce[b * R + i];
-            lpacc[q][i] = fma((double)n1[q], ce.x, T.lb[b * R + i]);
-            if (hs1) lpacc[q][i] = fma(S1[q], ce.y, lpacc[q][i]);
-          }
+          for (int i = 0; i < R; i++) { nv[q][i] = n1[q]; sv[q][i] = s1q[q]; }
       }
     }
     // ---- node ops: form every node born before the end of this block.
@@ -950,10 +951,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         const uint32_t sel = rotr32(w, (uint32_t)op.lbit) & 0x30u;  // observation pair x 16
         const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(T.cherry + op.pair * 4) + sel);
         av[q] = v.x; dd[q] = v.y;
-        if (lp) {
-          const double* orc = T.oprec + (size_t)o * OPREC_DOUBLES;
-          leaf_deaths(q, b, real, op.i0, (sel >> 4) & 1u, sel >> 5, hs1 ? orc[4] : 0., hs1 ? orc[5] : 0.);
-        }
+        if (lp) leaf_deaths(q, op.i0, (sel >> 4) & 1u, sel >> 5, op.hlq, op.hrq);
         if (!HOT && op.ml) {  // the two leaves die here: their slices of this block as one quadratic in u (as in the pair loop)
           const double4 qv = *reinterpret_cast<const double4*>(reinterpret_cast<const char*>(T.pairq + op.pair * 4) + 2 * sel);
           if (!factored) {
@@ -1003,8 +1001,7 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
         L[q].x = lleaf ? lt.x : ls.x;  L[q].y = lleaf ? lt.y : ls.y;
         Rr[q].x = rleaf ? rt.x : rs.x; Rr[q].y = rleaf ? rt.y : rs.y;
         if (lp && (op.flags & 3))
-          leaf_deaths(q, b, real, op.i0, lleaf ? (rotr32(wl, (uint32_t)op.lbit) >> 4) & 1u : 0u, rleaf ? (rotr32(wr, (uint32_t)op.rbit) >> 4) & 1u : 0u,
-                      hs1 ? orc[4] : 0., hs1 ? orc[5] : 0.);
+          leaf_deaths(q, op.i0, lleaf ? (rotr32(wl, (uint32_t)op.lbit) >> 4) & 1u : 0u, rleaf ? (rotr32(wr, (uint32_t)op.rbit) >> 4) & 1u : 0u, op.hlq, op.hrq);
       }
       // a child that dies with this op multiplies its slices of the block here (it has no entry record) -- unless its
       // prefix and the new node's suffix partition the block (op.comb): then one update serves both, below.  (Global-memory
@@ -1468,11 +1465,14 @@ PPM_HD void sweep_items(const SweepArgs& a, const ItemTables& T, int p, long lon
       // (every loop above ends with a range check of its own; the generic partial loops and the deep variant's tails do not)
       if (DEEP || (!HOT && bd.e_pleaf0 < bd.e_end))
         if (ppm_any(products_small<R>(prod[q]))) rescale_products<R>(prod[q], ex[q]);
-      if (lp) {  // the alive leaves of every slice as one power: 2^lpacc = mantissa in [0.70, 1.42] x 2^k
+      if (lp) {  // the alive leaves of every slice as one power: mantissa in [0.70, 1.42] x 2^k
 #pragma unroll
         for (int i = 0; i < R; i++) {
+          const double2 ce = T.lce[b * R + i];
+          double s2 = fma(lp_i2d(nv[q][i]), ce.x, T.lb[b * R + i]);
+          if (hs1) s2 = fma(lp_i2d(sv[q][i]), ce.y, s2);
           int kx;
-          prod[q][i] *= lp_pow2(lpacc[q][i], kx);
+          prod[q][i] *= lp_pow2(s2, kx);
           ex[q][i] -= kx;
         }
       }

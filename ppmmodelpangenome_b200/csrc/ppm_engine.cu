@@ -117,6 +117,7 @@ struct ppm_engine {
   DevBuf<uint32_t> d_bs_ones;
   // leaf powers (band_program.h: leaf_pow)
   DevBuf<int> d_blp_alive, d_bs_n1k[2], d_bs_n1k0, d_bs_base_n1, d_lp_alive;
+  DevBuf<int> d_lp_leaf_hq, d_lp_s1q_0;
   DevBuf<double> d_lp_htot, d_slb;
   DevBuf<double2> d_slce;
   DevBuf<double> d_blp_htot, d_blp_op_h, d_blp_leaf_h, d_blp_s1_0, d_bLb, d_bLc, d_bLe, d_bs_s1k[2], d_bs_s1k0, d_bs_base_s1;
@@ -420,7 +421,7 @@ struct ppm_engine {
         !std::getenv("PPM_WORDS_SMEM"))
       md.word_stride = (int)n_pat_pad;
     md.counts = d_counts.p; md.mrca = d_mrca.p; md.freq = d_freq.p; md.zero_words = d_zero_words.p;
-    md.lp = prog.lp ? 1 : 0; md.has_s1 = prog.has_s1 ? 1 : 0;
+    md.lp = prog.lp ? 1 : 0; md.has_s1 = prog.has_s1 ? 1 : 0; md.lp_hunit = prog.hunit;
     if (prog.lp) { d_lp_alive.upload(prog.n_alive_leaves, stream); d_lp_htot.upload(prog.htot, stream); }
     md.lp_alive = d_lp_alive.p; md.lp_htot = d_lp_htot.p;
   }
@@ -446,7 +447,7 @@ struct ppm_engine {
       CK(cudaGetLastError());
     }
     md.words = d_words.p;
-    md.lp_s1_0 = nullptr;
+    md.lp_s1_0 = nullptr; md.lp_s1q_0 = nullptr;
     if (prog.has_s1) {  // leaf powers: sum of the heights of every pattern's present leaves, once per handle
       d_blp_leaf_h.upload(prog.leaf_h, stream);
       d_blp_s1_0.alloc((size_t)std::max<long long>(n_pat_pad, 32));
@@ -454,6 +455,14 @@ struct ppm_engine {
       ppm::launch_leaf_height_sums(md, d_blp_leaf_h.p, count, d_blp_s1_0.p, stream);
       CK(cudaStreamSynchronize(stream));
       md.lp_s1_0 = d_blp_s1_0.p;
+      std::vector<int> hq((size_t)nw * 32, 0);
+      std::copy(prog.leaf_hq.begin(), prog.leaf_hq.end(), hq.begin());
+      d_lp_leaf_hq.upload(hq, stream);
+      d_lp_s1q_0.alloc((size_t)std::max<long long>(n_pat_pad, 32));
+      CK(cudaMemsetAsync(d_lp_s1q_0.p, 0, sizeof(int) * (size_t)std::max<long long>(n_pat_pad, 32), stream));
+      ppm::launch_leaf_height_sums_q(md, d_lp_leaf_hq.p, count, d_lp_s1q_0.p, stream);
+      CK(cudaStreamSynchronize(stream));
+      md.lp_s1q_0 = d_lp_s1q_0.p;
     }
     // frontier lists of the class sums: pattern-only, so once per handle (count, prefix sums on the host, fill)
     md.fr_off = nullptr; md.fr_nodes = nullptr;

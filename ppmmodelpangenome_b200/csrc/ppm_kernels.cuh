@@ -31,6 +31,7 @@ struct NodeOpDev {  // == ppm::NodeOp
 struct __align__(16) SweepOpDev {  // == ppm::SweepOp (host_model.h): what the sweep reads per node op
   int32_t lslot, rslot, lbit, rbit, dst, i0, flags, pair;
   int32_t mself, ml, mr, comb;  // slice masks of the events folded into the op, and which child shares an update with the node (host_model.h)
+  int32_t hlq, hrq, pad0, pad1; // leaf powers: quantised heights of leaf children
 };
 struct BlockDesc {  // == ppm::BlockDescHost; entry segments of a block, in order:
   // [e_slot0,e_pair0)   internal lineages alive in every slice (partials in slots)
@@ -86,7 +87,9 @@ struct ModelDev {
   // leaf-power sweep program (host_model.h: Program::lp): no leaf entries; per-slice count tables instead
   int lp, has_s1;
   const int* lp_alive; const double* lp_htot;  // [n_slices] leaves alive at each slice, sum of their heights
-  const double* lp_s1_0;                       // [n_pat_pad] sum of the heights of every pattern's present leaves (has_s1)
+  const double* lp_s1_0;                       // [n_pat_pad] sum of the heights of every pattern's present leaves (has_s1; band kernels)
+  const int* lp_s1q_0;                         // [n_pat_pad] the same in integer units of lp_hunit (lane-per-pattern sweep)
+  double lp_hunit;
   double lp_max_h;  // leaf-power band program: largest |leaf height| (the prepass keeps parameter vectors with n (lam h)^2 > 1e-12 off it)
 };
 
@@ -250,6 +253,7 @@ void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);   
 void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, const int* base_n1, const double* base_s1, int n_sm, cudaStream_t s);
 // leaf powers, once per handle: s1_0[pattern] = sum of leaf_h over the pattern's present leaves (leaf_h by device bit position)
 void launch_leaf_height_sums(const ModelDev& m, const double* leaf_h, long long count, double* s1_0, cudaStream_t s);
+void launch_leaf_height_sums_q(const ModelDev& m, const int* leaf_hq, long long count, int* s1q_0, cudaStream_t s);
 // term lists: count pass (cnt [count * n_tiles + 1], turned into offsets in place; returns the number of records) and fill pass
 unsigned long long sparse_lists_count(const ModelDev& m, const BandDev& b, long long count, uint32_t* cnt_off, cudaStream_t s);
 void sparse_lists_fill(const ModelDev& m, const BandDev& b, long long count, const uint32_t* off, uint2* recs, cudaStream_t s);

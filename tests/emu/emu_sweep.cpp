@@ -201,6 +201,12 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
         for (int pos = 0; pos < tree.n_leaves; pos++)
           if ((wm[(size_t)(pos >> 5) * count + j] >> (pos & 31)) & 1u) s1_0[j] += prog.leaf_h[pos];
     md.lp_s1_0 = s1_0.data();
+    std::vector<int> s1q_0((size_t)std::max<long long>(count, 1), 0);
+    if (prog.has_s1)
+      for (long long j = 0; j < count; j++)
+        for (int pos = 0; pos < tree.n_leaves; pos++)
+          if ((wm[(size_t)(pos >> 5) * count + j] >> (pos & 31)) & 1u) s1q_0[j] += prog.leaf_hq[pos];
+    md.lp_s1q_0 = s1q_0.data(); md.lp_hunit = prog.hunit;
 
     const size_t nn = tree.n_nodes;
     std::vector<double4> cls(P * nn);
