@@ -171,7 +171,12 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   PPM_CTA_BARRIER();
   // (B) bottom-up by levels: zero-row log p1 per node (objects.cpp:404-426 on the all-zero row) and the frontier
   //     factor T = LSE(lost on the branch, kept and unobserved below)
+  // (levels of at most 32 nodes -- every level of a caterpillar -- are served by warp 0 alone; a run of them is kept in step by
+  // __syncwarp instead of the CTA barrier: 10,000 levels cost 35 ms with the barrier)
   for (int lv = 0; lv < m.n_lev_up; lv++) {
+    const bool small_lv = PPM_LANES == 32 && m.lev_up_off[lv + 1] - m.lev_up_off[lv] <= 32;
+    const bool next_small = small_lv && lv + 1 < m.n_lev_up && m.lev_up_off[lv + 2] - m.lev_up_off[lv + 1] <= 32;
+    if (!small_lv || tid < 32)
     for (int k = m.lev_up_off[lv] + tid; k < m.lev_up_off[lv + 1]; k += nt) {
       const int v = m.lev_up_nodes[k];
       const bool leaf = m.left[v] < 0;
@@ -220,7 +225,7 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       const double lost = 1 - exp(-l1 * bl);
       ta[v] = leaf ? lost * (1 - e2) : lost * (1 - exp(zl1));
     }
-    PPM_CTA_BARRIER();
+    if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
   }
   // (C) computeI2 pieces that do not need the Mobile integral (functions.cpp:337-341), summed in the reference's order
   if (tid == 0) {
@@ -256,6 +261,9 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   //     U(child of root) = lost_v) and log V(v) = sum over the path of log sigma_c + T(sib c).
   //     z0 is reused as log V, z1 as U: a node's own zero-row values are dead once level (B) is complete.
   for (int lv = 1; lv < m.n_lev_dn; lv++) {
+    const bool small_lv = PPM_LANES == 32 && m.lev_dn_off[lv + 1] - m.lev_dn_off[lv] <= 32;
+    const bool next_small = small_lv && lv + 1 < m.n_lev_dn && m.lev_dn_off[lv + 2] - m.lev_dn_off[lv + 1] <= 32;
+    if (!small_lv || tid < 32)
     for (int k = m.lev_dn_off[lv] + tid; k < m.lev_dn_off[lv + 1]; k += nt) {
       const int v = m.lev_dn_nodes[k];
       const int par_ = m.parent[v];
@@ -273,7 +281,7 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
         t.et1[(size_t)p * nn + v] = (1. / l1 - sig * (b + 1. / l1)) + sT * (Np + b * Dp);
       }
     }
-    PPM_CTA_BARRIER();
+    if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
   }
   if (t.et1) {
     for (int v = tid; v < nn; v += nt) t.et1[(size_t)p * nn + v] /= ss0[v];

@@ -191,7 +191,12 @@ struct ppm_engine {
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    {  // the side stream carries short latency-bound kernels (prune of the next batch, class sums) that must get their SMs
+       // ahead of the persistent kernels of the main stream: highest priority
+      int prio_lo = 0, prio_hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+    }
     CK(cudaEventCreateWithFlags(&ev_nodes, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_class, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_bs_tables, cudaEventDisableTiming));
@@ -563,14 +568,15 @@ struct ppm_engine {
         // batches of 32-item blocks through one scratch: prune -> integral -> mixture, back to back on the stream
         const long long n_blk_total = (long long)t.P * (n_pat_pad / 32);
         // scratch budget: every batch boundary drains the GPU once (~2 ms at 5,000 genomes), so batches should be big -- a
-        // sixth of the free device memory, at most 16 GB, unless PPM_BAND_SCRATCH_MB says otherwise
+        // third of the free device memory, at most 48 GB, unless PPM_BAND_SCRATCH_MB says otherwise
         size_t budget = bs_budget;
         if (budget == 0) {
           size_t free_b = 0, total_b = 0;
           CK(cudaMemGetInfo(&free_b, &total_b));
           size_t have = 0;
           for (int k = 0; k < 2; k++) have += d_bs_nodes[k].n * sizeof(double2) + d_bs_xk[k].n * sizeof(int) + d_bs_unit[k].n * sizeof(double2);
-          budget = bs_budget = std::min<size_t>((size_t)16 << 30, std::max<size_t>((size_t)1 << 30, (free_b + have) / 6));
+          for (int k = 0; k < 2; k++) have += d_bs_n1k[k].n * sizeof(int) + d_bs_s1k[k].n * sizeof(double);
+          budget = bs_budget = std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)1 << 30, (free_b + have) / 3));
         }
         if (const char* e = std::getenv("PPM_BAND_SCRATCH_MB")) budget = (size_t)std::max(1, std::atoi(e)) << 20;
         // Two scratch buffers: the prune kernel of batch b + 1 (latency-bound: one thread walks 5,000 dependent ops) runs on
