@@ -58,6 +58,13 @@ VARIANTS = [
     ("band kernels, stream layout", 1500, False, {}, dict(band=1, band_stream=1, last_kind=1)),
     ("band kernel, one CTA per item", 1500, False, {"PPM_BAND_V": 1}, dict(band=1, band_stream=0, last_kind=1)),
     ("band kernels on a small tree (forced)", 300, False, {"PPM_FORCE_BAND": 1}, dict(band=1, band_stream=1, last_kind=1)),
+    # leaf powers are what the variants above run with (the simulated trees carry ape's 10-digit
+    # branch lengths: the first-order height correction is live); the same kernels on programs with per-leaf terms:
+    ("leaf powers are the default", 100, False, {}, dict(sweep_lp=1, band=0, last_mode=0)),
+    ("band kernels with leaf powers", 1500, False, {}, dict(band=1, band_lp=1, sweep_lp=1)),
+    ("per-leaf terms, shared-memory slots", 100, False, {"PPM_NO_LEAFPOW": 1}, dict(sweep_lp=0, band=0, last_mode=0)),
+    ("per-leaf terms, global-memory slots", 400, False, {"PPM_NO_LEAFPOW": 1}, dict(sweep_lp=0, band=0, last_mode=4)),
+    ("per-leaf terms, band kernels", 1500, False, {"PPM_NO_LEAFPOW": 1}, dict(sweep_lp=0, band=1, band_lp=0, last_kind=1)),
 ]
 
 
@@ -114,3 +121,30 @@ def test_north_star_tree_sizes_against_oracle(ppm, tmp_path, n, genes, cat):
     assert rel(ll_s[0], o["ll"]) <= RTOL, (n, ll_s[0], o["ll"])
     assert rel(ll_s[0], ll[0]) <= 1e-12
     inf.close()
+
+
+@pytest.mark.parametrize("n,cat", [(100, False), (400, False), (1500, False), (3000, True)], ids=["100", "400", "1500", "caterpillar 3000"])
+def test_leaf_powers_equal_per_leaf_terms(ppm, tmp_path, n, cat):
+    """The same handle inputs evaluated with leaf powers (one exp2 per slice from the count of present alive leaves and the
+    sum of their heights) and with per-leaf terms (PPM_NO_LEAFPOW=1): log-likelihood, i2, per-pattern components and
+    categories.  The trees are written with 10 significant digits, so the leaf heights are +-1e-10 H: what is compared is
+    the first-order treatment of those heights against the exact one."""
+    tp, pp, P = _seeded(tmp_path, n, 300 if n <= 400 else 40, 77000 + n, cat)
+    out = []
+    for env in ({}, {"PPM_NO_LEAFPOW": 1}):
+        with _Env(**env):
+            inf = ppm.Inference(tp, pp, dedupe=True, device=0)
+            ll, i2 = inf.loglik_batch(P, return_i2=True)
+            plan = inf.plan()
+            comp = inf.components(P[0], i2[0])
+            cats = inf.assignCat(P[0], i2[0])
+            out.append((ll, i2, comp, cats, plan))
+            inf.close()
+    (ll_a, i2_a, comp_a, cat_a, plan_a), (ll_b, i2_b, comp_b, cat_b, plan_b) = out
+    assert plan_a["sweep_lp"] == 1 and plan_b["sweep_lp"] == 0 and plan_b["band_lp"] == 0, (plan_a, plan_b)
+    assert np.allclose(i2_a, i2_b, rtol=1e-12, atol=0)
+    assert np.allclose(ll_a, ll_b, rtol=1e-12, atol=0), (ll_a, ll_b)
+    fin = np.isfinite(comp_b)
+    assert np.array_equal(np.isfinite(comp_a), fin)
+    assert np.allclose(comp_a[fin], comp_b[fin], rtol=1e-10, atol=1e-10)
+    assert np.mean(cat_a == cat_b) >= 0.999  # (an exact tie between two categories may fall either way)
