@@ -617,11 +617,12 @@ void launch_band_baseline_rows(BandStreamArgs a, const uint32_t* base_words, con
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s) {
   band_prune_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 32 * BS_WARPS, 0, s>>>(a);
 }
-void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s) {  // + mixture
+void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s, cudaEvent_t before_mixture) {  // + mixture
   switch (a.b.R) {
     case 2: launch_integral_t<2>(a, n_sm, s); break;
     default: launch_integral_t<4>(a, n_sm, s); break;
   }
+  if (before_mixture) cudaStreamWaitEvent(s, before_mixture, 0);  // (the class sums of this evaluation, on their own stream)
   band_mixture_kernel<<<(a.n_blk + BS_WARPS - 1) / BS_WARPS, 128, 0, s>>>(a);
 }
 

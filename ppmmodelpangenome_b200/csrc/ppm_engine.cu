@@ -87,7 +87,8 @@ struct ppm_engine {
   long long first = 0, count = 0;  // this shard's pattern slice
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;    // class sums run here, next to the table prepass and the zero row (they only need the node prepass)
+  cudaStream_t side2 = nullptr;   // the class sums of an evaluation (next to the table prepass, the zero row and the first batch's prune)
+  cudaStream_t side = nullptr;    // (until round 2: class sums run here, next to the table prepass and the zero row (they only need the node prepass)
   cudaEvent_t ev_nodes = nullptr, ev_class = nullptr;
   bool class_pending = false;
   bool hint_no_factored = false;  // set by the host-pointer entry points when no parameter vector has pi1 > 0.95
@@ -171,6 +172,7 @@ struct ppm_engine {
       if (ev_bs_done[k]) cudaEventDestroy(ev_bs_done[k]);
     }
     if (side) cudaStreamDestroy(side);
+    if (side2) cudaStreamDestroy(side2);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -196,6 +198,7 @@ struct ppm_engine {
       int prio_lo = 0, prio_hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
       CK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+      CK(cudaStreamCreateWithPriority(&side2, cudaStreamNonBlocking, prio_hi));
     }
     CK(cudaEventCreateWithFlags(&ev_nodes, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_class, cudaEventDisableTiming));
@@ -531,9 +534,9 @@ struct ppm_engine {
     ppm::launch_prepass_nodes(md, t, s);
     if (with_class_sums && count > 0) {
       CK(cudaEventRecord(ev_nodes, s));
-      CK(cudaStreamWaitEvent(side, ev_nodes, 0));
-      ppm::launch_class_sums(md, t, 0, count, side);
-      CK(cudaEventRecord(ev_class, side));
+      CK(cudaStreamWaitEvent(side2, ev_nodes, 0));
+      ppm::launch_class_sums(md, t, 0, count, side2);
+      CK(cudaEventRecord(ev_class, side2));
       class_pending = true;
       n_launches += 1;
     }
@@ -560,8 +563,11 @@ struct ppm_engine {
     const bool band_now = use_band && mode == 0 && d_dist_out == nullptr && a.n_items > 0;
     last_sweep_kind = band_now ? 1 : 0;
     if (band_now) {
-      // band kernel for every parameter vector it can serve (SC_BAND), then the lane-per-pattern sweep for the others
-      if (class_pending) { CK(cudaStreamWaitEvent(s, ev_class, 0)); class_pending = false; }
+      // band kernel for every parameter vector it can serve (SC_BAND), then the lane-per-pattern sweep for the others.
+      // The class sums (4.4 ms at 5,000 genomes, on their own stream) are needed by the first MIXTURE only: the first batch's
+      // prune (4 ms, latency-bound) and integral do not wait for them.
+      bool class_wait = false;
+      if (class_pending) { class_wait = band.stream; if (!class_wait) CK(cudaStreamWaitEvent(s, ev_class, 0)); class_pending = false; }
       else { ppm::launch_class_sums(md, t, 0, count, s); n_launches += 1; }
       int n_band_partials = 0;
       if (band.stream) {
@@ -649,7 +655,8 @@ struct ppm_engine {
             ppm::launch_band_sparse(batch_args(b), n_sm, s);
             n_launches += 1;
           }
-          ppm::launch_band_integral(batch_args(b), n_sm, s);
+          ppm::launch_band_integral(batch_args(b), n_sm, s, class_wait ? ev_class : nullptr);
+          class_wait = false;
           CK(cudaEventRecord(ev_bs_done[k], s));
           n_launches += 3;
         }

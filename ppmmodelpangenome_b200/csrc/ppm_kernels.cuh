@@ -245,7 +245,7 @@ size_t band_smem_bytes(const ModelDev& m, const BandDev& b);
 void launch_band(BandArgs a, const BandPlan& pl, cudaStream_t s);
 size_t band_stream_block_bytes(const BandDev& b);  // scratch per 32-item block
 void launch_band_prune(const BandStreamArgs& a, cudaStream_t s);                 // one batch: lineage records into the scratch
-void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s);    // one batch: integral + mixture
+void launch_band_integral(const BandStreamArgs& a, int n_sm, cudaStream_t s, cudaEvent_t before_mixture = nullptr);  // one batch: integral + mixture (which waits for the event)
 // sparse evaluation: records of the all-zero and all-ones rows for every parameter vector into a.nodes0 / a.xk0 ([P][2][...]),
 // per-slice integrand of the all-ones row into a.z1; base_words = [n_words][64] (32 zero columns, 32 all-ones columns);
 // a.unit_I must hold P * 64 * G entries
