@@ -22,6 +22,14 @@ PPM_HD double2 band_merge(double xl, double yl, double xr, double yr, const doub
   return make_double2(a, d * o[4]);
 }
 
+// sparse evaluation: is this pattern served from its term list?  (0: dense; 1 / 2: against the all-zero / all-ones row)
+PPM_HD int bs_sparse_use(const ModelDev& m, const SparseLists& l, int n_tiles, unsigned int max_len, long long pat) {
+  const int base = bs_sparse_item(m, pat);
+  if (base == 0) return 0;
+  const unsigned int len = l.off[(size_t)(pat + 1) * n_tiles] - l.off[(size_t)pat * n_tiles];
+  return len <= max_len ? base : 0;
+}
+
 // Mixture of one (pattern, parameter vector) given its Mobile integral Im * 2^-Ie: functions.cpp:345-358 with the
 // pure-loss categories from the class-sum kernel (a01) and the Private below-root table (d1u).  Returns count * log-mixture.
 PPM_HD double band_mixture(const ModelDev& m, const TablesDev& t, int p, long long pat, double Im, int Ie, double* comp3) {

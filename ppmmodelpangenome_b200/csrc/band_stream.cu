@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
     const double* sc = a.t.scal + (size_t)p * SC_COUNT;
     // (sparse evaluation: the items with term lists belong to band_sparse_kernel)
     // (slice_out: the baseline rows of the sparse evaluation -- only copy 0 of the all-ones row is integrated)
-    const bool mine = a.slice_out ? pat == 32 : (pat < a.count && !(a.sparse && bs_sparse_item(m, pat) != 0));
+    const bool mine = a.slice_out ? pat == 32 : (pat < a.count && !(a.sparse && bs_sparse_use(m, a.lists, b.n_tiles, a.sparse_max_len, pat) != 0));
     if (mine && bs_served(sc, a.force)) {
       const double2* nodes = a.nodes + (size_t)(il >> 5) * n_int * 32 + (il & 31);
       const int* xk = a.xk + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);

@@ -628,6 +628,9 @@ struct ppm_engine {
           x.n1k0 = d_bs_n1k0.p; x.s1k0 = d_bs_s1k0.p;
           x.sparse = sparse_now ? 1 : 0; x.nodes0 = d_bs_nodes0.p; x.xk0 = d_bs_xk0.p; x.z1 = d_bs_z1.p;
           x.lists.off = d_sp_off.p; x.lists.recs = d_sp_recs.p; x.counter2 = d_bs_counter.p + 3 + k;
+          // a sparse record costs about three dense ones (numerator and denominator, masked, every register)
+          x.sparse_max_len = (unsigned int)std::max<long long>(64, (band.n_full16 + band.n_full32 + band.n_f16 + band.n_f32 + band.n_m16) / 3);
+          if (const char* e = std::getenv("PPM_SPARSE_MAX_LEN")) x.sparse_max_len = (unsigned int)std::atoll(e);
           x.item0 = 32 * b * blk_batch;
           x.n_blk = (int)std::min<long long>(blk_batch, n_blk_total - b * blk_batch);
           return x;

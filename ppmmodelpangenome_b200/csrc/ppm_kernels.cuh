@@ -189,6 +189,8 @@ struct BandStreamArgs {
   // against the all-zero row whose per-slice integrand the prepass already has (TablesDev::zpart)
   int sparse;
   SparseLists lists;           // the handle's term lists
+  unsigned int sparse_max_len; // a listed pattern is served by band_sparse_kernel only when its list holds at most this many records
+                               // (a long list -- every ancestor of a present leaf on a caterpillar -- costs more than the dense walk)
   unsigned int* counter2;      // unit hand-out of the sparse kernel
   const double2* nodes0;       // [P][2][n_int][32]  lineage records of the all-zero / all-ones row per parameter vector (copy 0 of 32 is read)
   const int* xk0;              // [P][2][n_int + 1][32]  their shift prefixes
