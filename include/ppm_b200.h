@@ -184,7 +184,9 @@ int ppm_get_counters(ppm_handle h, double* out4);
  * [4] variant of the last lane-per-pattern sweep (0 shared memory, 1/3 tensor memory, 2/4 global memory; -1 none yet),
  * [5] pattern rows read in place, [6] program built for the global-memory variant, [7] lean program (HOT kernels),
  * [8] pruning levels, [9] band tiles, [10] sweep blocks, [11] lineage slots, [12] leaves at height 0,
- * [13] band kernels in the stream layout (prune / integral / mixture, band_stream.cu); [14..15] reserved. */
+ * [13] band kernels in the stream layout (prune / integral / mixture, band_stream.cu),
+ * [14] / [15] the lane-per-pattern sweep program / the band program use leaf powers (the alive leaves of a slice as one power of
+ * the count of present alive leaves; ultrametric trees). */
 int ppm_get_plan(ppm_handle h, int32_t* out16);
 /* DFMA micro-benchmark: measured FP64 FMA throughput of the device in TFLOP/s (2 flop per FMA). */
 int ppm_measure_fp64_peak(int device, double* out_tflops);
