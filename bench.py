@@ -247,11 +247,12 @@ def kernel_name(inf):
     pl = inf.plan()
     if pl["last_kind"] == 1 and pl.get("band_stream"):
         # kernel_ms covers the whole band sequence of a step: per batch prune -> integral -> mixture (the integral is ~98 % of it)
-        return "ppm::band_integral_kernel<%d> (+ ppm::band_prune_kernel, ppm::band_mixture_kernel per batch)" % pl["band_R"], pl
+        return "ppm::band_integral_kernel<%d,%s> (+ ppm::band_prune_kernel, ppm::band_mixture_kernel per batch)" % (
+            pl["band_R"], "true" if pl.get("band_lp") else "false"), pl
     if pl["last_kind"] == 1:
         return "ppm::band_kernel<%d,%s>" % (pl["band_R"], "true" if pl["band_G"] > 1 else "false"), pl
     mode = pl["last_mode"]
-    hot = "true" if (pl["lean"] and mode != 2) else "false"
+    hot = "true" if (pl["lean"] and pl.get("sweep_lp") and mode != 2 and not pl["rows_in_place"]) else "false"
     return "ppm::sweep_kernel<8,1,%d,false,%s,%s>" % (mode, "true" if pl["rows_in_place"] else "false", hot), pl
 
 

@@ -305,7 +305,9 @@ __device__ __forceinline__ double bs_recs_masked(const double2* rb, const uint32
   return (t0 * t1) * (t2 * t3);
 }
 
-template <int R>
+// LP: the instantiation for leaf-power programs (band_program.h): no leaf or leaf-pair records, hence no pattern words, no
+// leaf tables, no u table -- the paths that gather and multiply them are compiled out
+template <int R, bool LP>
 __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStreamArgs a) {
   static_assert(R <= 4, "a tile-begin block carries four shift indices per lane");
   extern __shared__ __align__(16) unsigned char bs_smem[];
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
       const double* bU = a.bt.bU + (size_t)p * b.S_pad;
       const double2* bleaf = a.bt.bleaf + (size_t)p * m.n_leaves * 2;
       const double4* pairq = a.t.pairq + (size_t)p * m.n_pairs * 4;
-      const bool lp = b.lp != 0;
+      constexpr bool lp = LP;
       const int* n1k = a.n1k + (size_t)(il >> 5) * (n_int + 1) * 32 + (il & 31);
       const double* s1k = a.s1k + (size_t)(b.has_s1 ? (il >> 5) : 0) * (n_int + 1) * 32 + (il & 31);
       const double* bLb = a.bt.bLb + (size_t)p * b.S_pad;
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
               const bool pad = q == kBandPadEntry;
               const uint32_t ref = pad ? 0u : (q & 0xffffu);
               const double2* src = nodes + (size_t)ref * 32;
-              if (q >> 31) {
+              if (!LP && (q >> 31)) {
                 const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
                 src = bleaf + ref * 2 + bt1;
               }
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
                 reinterpret_cast<uint32_t*>(slot + BS_CH * 32)[2 * lane + h] = pad ? 0u : ((len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo);
               }
             }
-          } else if (opG == BD_PAIR) {
+          } else if (!LP && opG == BD_PAIR) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
               const uint32_t q = h ? e2.y : e2.x;
@@ -417,10 +419,10 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
             for (int k = 0; k < R; k++) {
               const uint32_t nb = ((k < 2 ? e2.x : e2.y) >> (16 * (k & 1))) & 0xffffu;
               bs_cp8(slot + (k * 32 + lane) * 8, bY + tb + 32 * k);
-              bs_cp8(slot + 1024 + (k * 32 + lane) * 8, bU + tb + 32 * k);
+              if (!LP) bs_cp8(slot + 1024 + (k * 32 + lane) * 8, bU + tb + 32 * k);
               bs_cp4(slot + 2048 + (k * 32 + lane) * 4, xk + (size_t)nb * 32);
             }
-          } else if (opG == BD_TILE_LP) {  // leaf powers: count tables | dead present leaves (variant 0), height tables (variant 1)
+          } else if (LP && opG == BD_TILE_LP) {  // leaf powers: count tables | dead present leaves (variant 0), height tables (variant 1)
             const int tb = (int)(c2 >> 16) * T + lane;
             const bool heights = ((c2 >> 4) & 3u) != 0u;
 #pragma unroll
@@ -452,12 +454,12 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
           for (int k = 0; k < R; k++) {
             prod[k] = b.wt[tau * T + 32 * k + lane];  // the slice weights enter the products here (0 for padding slices)
             Y[k] = *reinterpret_cast<const double*>(buf + (k * 32 + lane) * 8);
-            U[k] = *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8);
+            U[k] = LP ? 0. : *reinterpret_cast<const double*>(buf + 1024 + (k * 32 + lane) * 8);
             ex[k] = *reinterpret_cast<const int*>(buf + 2048 + (k * 32 + lane) * 4);
           }
           continue;
         }
-        if (op == BD_TILE_LP) {
+        if (LP && op == BD_TILE_LP) {
           if (var) {  // heights first: S1 (g_1 - g_0)
 #pragma unroll
             for (int k = 0; k < R; k++)
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
           }
           continue;
         }
-        if (op == BD_PAIR) {
+        if (!LP && op == BD_PAIR) {
           const double4* rb = reinterpret_cast<const double4*>(buf);
           if (var == BV_FULL) {
             bs_pairs_full<R>(rb, cnt, U, prod, ex);
@@ -582,13 +584,13 @@ size_t band_stream_block_bytes(const BandDev& b) {  // scratch per 32-item block
          (b.lp ? (size_t)(b.n_int + 1) * 32 * sizeof(int) : 0) + (b.has_s1 ? (size_t)(b.n_int + 1) * 32 * sizeof(double) : 0);
 }
 
-template <int R>
-static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
+template <int R, bool LP>
+static void launch_integral_tl(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(band_integral_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(band_integral_kernel<R, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const size_t smem = (size_t)BS_WARPS * bs_warp_bytes(a.m.n_words);
@@ -596,7 +598,11 @@ static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s)
   if (const char* e = std::getenv("PPM_BAND_CTAS")) { const int v = std::atoi(e); if (v >= 1) ctas = std::min(ctas, v); }
   const long long units = (long long)a.n_blk * 32 * a.b.G;
   const int grid = (int)std::max<long long>(1, std::min<long long>((long long)n_sm * ctas, (units + BS_WARPS - 1) / BS_WARPS));
-  band_integral_kernel<R><<<grid, 32 * BS_WARPS, smem, s>>>(a);
+  band_integral_kernel<R, LP><<<grid, 32 * BS_WARPS, smem, s>>>(a);
+}
+template <int R>
+static void launch_integral_t(const BandStreamArgs& a, int n_sm, cudaStream_t s) {
+  if (a.b.lp) launch_integral_tl<R, true>(a, n_sm, s); else launch_integral_tl<R, false>(a, n_sm, s);
 }
 
 // Baseline rows of the sparse evaluation through the band kernels themselves.  base_words holds 64 pattern columns: 32 copies of
