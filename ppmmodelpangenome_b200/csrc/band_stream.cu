@@ -35,7 +35,8 @@ enum { BS_CH = kBandStreamChunk, BS_NB = 3, BS_SLOT_BYTES = BS_CH * 32 + 512, BS
 static_assert(BS_CH == 64 && BS_BLK_BYTES % 16 == 0 && BS_BLK_BYTES / 16 <= 32, "two records per lane and chunk; a block is copied by <= 32 lanes");
 
 static __host__ __device__ inline int bs_pw_words(int n_words) { return (n_words + 1 + 3) & ~3; }
-static __host__ __device__ inline size_t bs_warp_bytes(int n_words) { return (size_t)BS_RING_BYTES + BS_BRING_BYTES + 4 * (size_t)bs_pw_words(n_words); }
+// (a leaf-power program reads no pattern words)
+static __host__ __device__ inline size_t bs_warp_bytes(int n_words, bool lp) { return (size_t)BS_RING_BYTES + BS_BRING_BYTES + (lp ? 0 : 4 * (size_t)bs_pw_words(n_words)); }
 
 __device__ __forceinline__ void bs_cp16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
@@ -308,13 +309,15 @@ __device__ __forceinline__ double bs_recs_masked(const double2* rb, const uint32
 // LP: the instantiation for leaf-power programs (band_program.h): no leaf or leaf-pair records, hence no pattern words, no
 // leaf tables, no u table -- the paths that gather and multiply them are compiled out
 template <int R, bool LP>
+// (6 CTAs per SM at 80 registers, which the leaf-power instantiation's smaller shared memory allows, measured: configs[3] 556 -> 615 ms,
+// configs[4] 112 -> 149 ms -- more items in flight than L2 holds records for)
 __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStreamArgs a) {
   static_assert(R <= 4, "a tile-begin block carries four shift indices per lane");
   extern __shared__ __align__(16) unsigned char bs_smem[];
   const ModelDev& m = a.m;
   const BandDev& b = a.b;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* wring = bs_smem + (size_t)warp * bs_warp_bytes(m.n_words);
+  unsigned char* wring = bs_smem + (size_t)warp * bs_warp_bytes(m.n_words, LP);
   unsigned char* bring = wring + BS_RING_BYTES;
   uint32_t* pw = reinterpret_cast<uint32_t*>(bring + BS_BRING_BYTES);
   const uint32_t lanebit = 1u << lane;
@@ -593,7 +596,7 @@ static void launch_integral_tl(const BandStreamArgs& a, int n_sm, cudaStream_t s
     cudaFuncSetAttribute(band_integral_kernel<R, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const size_t smem = (size_t)BS_WARPS * bs_warp_bytes(a.m.n_words);
+  const size_t smem = (size_t)BS_WARPS * bs_warp_bytes(a.m.n_words, LP);
   int ctas = (int)std::min<size_t>(5, (227 * 1024) / (smem + 1024));
   if (const char* e = std::getenv("PPM_BAND_CTAS")) { const int v = std::atoi(e); if (v >= 1) ctas = std::min(ctas, v); }
   const long long units = (long long)a.n_blk * 32 * a.b.G;
