@@ -369,7 +369,11 @@ def time_workload(D, wl, K, W, peak_tf, e2e_reps=3, check_unsharded=False, sampl
                      "traffic": traffic, "kernel": kname, "kernel_ms": sweep, "plan": plan,
                      "peak_source": "DFMA micro-benchmark measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flops_per_pattern_eval": F, "fp64_pipe_tflops_issued": pipe,
-                     "fp64_pipe_frac": (pipe / peak_tf) if pipe else None},
+                     "fp64_pipe_frac": (pipe / peak_tf) if pipe else None,
+                     "frac_note": "achieved = ALGORITHMIC flops (SURVEY 8d: F = 5W + 28(n-1) + 2S per pattern-eval, the reference's dense "
+                                  "formulation) / kernel time; frac > 1 means the kernels do less arithmetic than F counts (leaf powers: "
+                                  "one exp2 per slice instead of one term per alive leaf) -- fp64_pipe_frac (modelled FP64 instructions "
+                                  "issued x 2 / peak) and ncu sm__inst_executed_pipe_fp64 in profiles/ are the pipe utilisation"},
     }
     if checked is not None:
         out["sharded_vs_unsharded_rel"] = checked
