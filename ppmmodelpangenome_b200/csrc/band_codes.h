@@ -11,6 +11,9 @@ enum {
                    // one power per slice; variant 1 (first, only with leaf heights != 0): height tables, variant 0: count tables
   BV_FULL = 0, BV_F = 1, BV_M = 2   // variant: every register / register k, all lanes / register k, lanes [lo, hi)
 };
-enum { kBandStreamChunk = 64, kBandBlockWords = 68 };  // stream layout: records per chunk (two per lane); the one-CTA layout uses 32
+// stream layout: records per chunk -- 64 (two per lane; 32-byte leaf-pair records fit a ring slot), 128 for leaf-power programs (16-byte
+// records only: half as many descriptors); a block = the chunk's entries + 4 words (the code first); the one-CTA layout uses 32.
+// A record chunk's 7-bit count field holds count & 127: 0 stands for 128.
+enum { kBandStreamChunk = 64, kBandStreamChunkLP = 128 };
 static const unsigned kBandPadEntry = 0xffffffffu;  // stream layout: padding entry of a chunk (identity record)
 }  // namespace ppm

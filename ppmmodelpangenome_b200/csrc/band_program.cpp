@@ -14,8 +14,8 @@ struct TileLists {
   std::vector<std::vector<int>> f_int, f_leaf;      // per sub-tile k
   std::vector<std::vector<MEnt>> m_int, m_leaf;     // per sub-tile k
 };
-inline uint32_t desc_code(int op, int variant, int k, int count) {
-  return (uint32_t)op | ((uint32_t)variant << 4) | ((uint32_t)k << 6) | ((uint32_t)count << 9);
+inline uint32_t desc_code(int op, int variant, int k, int count) {  // (count 128 -> field 0)
+  return (uint32_t)op | ((uint32_t)variant << 4) | ((uint32_t)k << 6) | ((uint32_t)(count & 127) << 9);
 }
 }  // namespace
 
@@ -43,6 +43,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
   for (int v = 1; v < nn && bp.leaf_pow; v++)
     if (t.left[v] < 0 && js0[v] != 0) bp.leaf_pow = false;  // (an internal node below a leaf's height: that leaf starts above the first slice)
   if (want_lp && !bp.leaf_pow) bp.has_s1 = false;
+  bp.chunk = bp.leaf_pow ? kBandStreamChunkLP : kBandStreamChunk;
   auto dpos = [&](int v) { return pg.leaf_perm[t.leaf_pos[v]]; };
   auto pair_of = [&](int pos) { return pos < 2 * pg.n_pairs ? pos / 2 : -1; };
 
@@ -146,7 +147,7 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
   for (int tau = 0; tau < bp.n_tiles; tau++) {
     TileLists& tl = tiles[tau];
     auto emit = [&](int op, int variant, int k, const std::vector<uint32_t>& ents, double per_rec, double fp_per_rec) {
-      const size_t ch = stream ? (size_t)kBandStreamChunk : 32;
+      const size_t ch = stream ? (size_t)bp.chunk : 32;
       for (size_t i = 0; i < ents.size(); i += ch) {
         const int cnt = (int)std::min<size_t>(ch, ents.size() - i);
         Chunk c{desc_code(op, variant, k, cnt), std::vector<uint32_t>(ents.begin() + i, ents.begin() + i + cnt), cnt * per_rec + 60.};
@@ -233,21 +234,21 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
     for (int v = 1; v < nn; v++) if (t.left[v] < 0) bp.leaf_span[dpos(v)] = (uint32_t)js0[v] | ((uint32_t)js1[v] << 16);
   }
   if (stream) {
-    // device form of the lists: one block of kBandBlockWords words per descriptor = its kBandStreamChunk entries + its code.
+    // device form of the lists: one block of chunk + 4 words per descriptor = its `chunk` entries + its code.
     // A tile-begin block carries, instead of entries, the shift-prefix index of each of its slices (nborn), packed so that
     // lane l finds slices l, 32 + l, ... in words 2l, 2l + 1.  Every list is followed by END blocks (the kernel reads ahead).
     if (R > 4) { bp.why = "stream layout: at most 4 slices per lane"; return bp; }
     for (int w = 0; w < G; w++) {
-      bp.unit_blk_off.push_back((int32_t)(bp.blocks.size() / kBandBlockWords));
+      bp.unit_blk_off.push_back((int32_t)(bp.blocks.size() / (bp.chunk + 4)));
       size_t eoff = bp.warp_ent_off[w];
       for (int di = bp.warp_off[w];; di++) {
         const uint32_t code = bp.desc[di];
         const int op = code & 15;
-        std::vector<uint32_t> blk(kBandBlockWords, kBandPadEntry);
-        blk[kBandStreamChunk] = code;
+        std::vector<uint32_t> blk(bp.chunk + 4, kBandPadEntry);
+        blk[bp.chunk] = code;
         if (op == BD_REC || op == BD_PAIR) {
-          std::copy(bp.entries.begin() + eoff, bp.entries.begin() + eoff + kBandStreamChunk, blk.begin());
-          eoff += kBandStreamChunk;
+          std::copy(bp.entries.begin() + eoff, bp.entries.begin() + eoff + bp.chunk, blk.begin());
+          eoff += bp.chunk;
         } else if (op == BD_TILE_BEGIN || op == BD_TILE_LP) {
           const int tau = (int)(code >> 16);
           for (int l = 0; l < 32; l++) {
@@ -260,13 +261,13 @@ BandProgram build_band_program(const Tree& t, const Program& pg, int R, int G, b
         bp.blocks.insert(bp.blocks.end(), blk.begin(), blk.end());
         if (op == BD_END) break;
       }
-      std::vector<uint32_t> endblk(kBandBlockWords, kBandPadEntry);
-      endblk[kBandStreamChunk] = desc_code(BD_END, 0, 0, 0);
+      std::vector<uint32_t> endblk(bp.chunk + 4, kBandPadEntry);
+      endblk[bp.chunk] = desc_code(BD_END, 0, 0, 0);
       for (int k = 0; k < 5; k++) bp.blocks.insert(bp.blocks.end(), endblk.begin(), endblk.end());
     }
   }
   for (int k = 0; k < 96; k++) bp.desc.push_back(desc_code(BD_END, 0, 0, 0));  // the kernel's descriptor window reads ahead
-  for (int k = 0; k < 128; k++) bp.entries.push_back(stream ? kBandPadEntry : 0u);  // a chunk's entry load always reads a full set
+  for (int k = 0; k < 256; k++) bp.entries.push_back(stream ? kBandPadEntry : 0u);  // a chunk's entry load always reads a full set
   bp.fp64_instr_per_eval = fp64 + 32.0 * fp64_warp + 60;
   bp.ok = true;
   return bp;

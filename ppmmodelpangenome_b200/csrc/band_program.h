@@ -31,7 +31,7 @@ struct BandProgram {
   const char* why = "";
   int R = 4, G = 1, T = 128;
   bool stream = false;     // stream layout (band_stream.cu): ops in birth order (dst = own index), G = work units per item,
-                           // every chunk owns exactly kBandStreamChunk entries (padded with kBandPadEntry)
+                           // every chunk owns exactly `chunk` entries (padded with kBandPadEntry)
   int n_tiles = 0, S_pad = 0;
   int n_int = 0;           // internal non-root nodes
   int n_levels = 0;
@@ -45,7 +45,7 @@ struct BandProgram {
   std::vector<uint32_t> desc;       // the G flat descriptor lists (band_codes.h), each closed by BD_END
   std::vector<int32_t> warp_off;    // [G+1] first descriptor of each warp
   std::vector<int32_t> warp_ent_off;  // [G+1] first entry of each warp; a warp's chunks own consecutive entries, in list order
-  std::vector<uint32_t> blocks;     // stream layout, device form: [block][kBandBlockWords] = a descriptor's entries + its code
+  std::vector<uint32_t> blocks;     // stream layout, device form: [block][chunk + 4] = a descriptor's entries + its code
   std::vector<int32_t> unit_blk_off;  // [G] first block of each unit's list
   std::vector<uint32_t> op_span, leaf_span;  // stream layout: alive slices js0 | js1 << 16 per internal lineage / per leaf bit (sparse lists)
   std::vector<uint32_t> entries;    // ref | lo << 16 | hi << 21 | leaf << 31 (M records: lanes [lo, hi), hi in 1..32)
@@ -55,6 +55,7 @@ struct BandProgram {
   // lineages only; the prune kernel counts the present leaves that have died before every op (and, when the leaf heights are only
   // numerically 0, the sum of their heights: first-order correction), the integral kernel turns the counts into the power.
   bool leaf_pow = false;
+  int chunk = kBandStreamChunk;     // stream layout: entries per chunk (kBandStreamChunkLP for a leaf-power program); a block = chunk + 4 words
   bool has_s1 = false;              // some leaf height != 0: the first-order height correction is carried along
   std::vector<int32_t> n_alive_leaves;  // [S_pad] leaves alive at each slice
   std::vector<double> htot;             // [S_pad] sum of the heights of the leaves alive at each slice

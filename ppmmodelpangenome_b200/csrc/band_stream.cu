@@ -25,18 +25,21 @@
 
 namespace ppm {
 
-// Per warp: a ring of BS_NB record slots (BS_CH records x 32 B + 512 B of lane masks / tile tables) and a ring of BS_NB block
+// Per warp: a ring of BS_NB record slots (64 records x 32 B or 128 x 16 B + 512 B of lane masks / tile tables) and a ring of BS_NB block
 // slots (a descriptor's entries + code, band_codes.h).  Everything the walk needs from global memory arrives by cp.async:
 // iteration di issues the block of descriptor di + 4 and -- from the block that has arrived by then -- the record gather of
 // descriptor di + 2, waits for the group issued two iterations earlier and multiplies in descriptor di.  The software-pipelined
 // FULL loops read one group of records past a slot (BS_PAD).
-enum { BS_CH = kBandStreamChunk, BS_NB = 3, BS_SLOT_BYTES = BS_CH * 32 + 512, BS_BLK_BYTES = kBandBlockWords * 4, BS_PAD = 256,
-       BS_RING_BYTES = BS_NB * BS_SLOT_BYTES + BS_PAD, BS_BRING_BYTES = BS_NB * BS_BLK_BYTES, BS_WARPS = 4, BS_NOP = 15 };
-static_assert(BS_CH == 64 && BS_BLK_BYTES % 16 == 0 && BS_BLK_BYTES / 16 <= 32, "two records per lane and chunk; a block is copied by <= 32 lanes");
+enum { BS_NB = 3, BS_SLOT_BYTES = kBandStreamChunk * 32 + 512, BS_MASK_OFF = kBandStreamChunk * 32, BS_PAD = 256,
+       BS_RING_BYTES = BS_NB * BS_SLOT_BYTES + BS_PAD, BS_WARPS = 4, BS_NOP = 15 };
+// a slot holds 64 records of 32 bytes or 128 of 16 (leaf-power programs), then 512 bytes of lane masks
+static_assert(kBandStreamChunkLP * 16 == BS_MASK_OFF && kBandStreamChunkLP * 4 <= 512, "a leaf-power chunk fills a slot exactly");
+static __host__ __device__ inline int bs_chunk(bool lp) { return lp ? (int)kBandStreamChunkLP : (int)kBandStreamChunk; }
+static __host__ __device__ inline int bs_blk_bytes(bool lp) { return (bs_chunk(lp) + 4) * 4; }
 
 static __host__ __device__ inline int bs_pw_words(int n_words) { return (n_words + 1 + 3) & ~3; }
 // (a leaf-power program reads no pattern words)
-static __host__ __device__ inline size_t bs_warp_bytes(int n_words, bool lp) { return (size_t)BS_RING_BYTES + BS_BRING_BYTES + (lp ? 0 : 4 * (size_t)bs_pw_words(n_words)); }
+static __host__ __device__ inline size_t bs_warp_bytes(int n_words, bool lp) { return (size_t)BS_RING_BYTES + BS_NB * bs_blk_bytes(lp) + (lp ? 0 : 4 * (size_t)bs_pw_words(n_words)); }
 
 __device__ __forceinline__ void bs_cp16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
@@ -319,7 +322,10 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wring = bs_smem + (size_t)warp * bs_warp_bytes(m.n_words, LP);
   unsigned char* bring = wring + BS_RING_BYTES;
-  uint32_t* pw = reinterpret_cast<uint32_t*>(bring + BS_BRING_BYTES);
+  constexpr int CH = LP ? (int)kBandStreamChunkLP : (int)kBandStreamChunk;  // records per chunk
+  constexpr int NPL = CH / 32;                                               // ... and per lane
+  constexpr int BLK_BYTES = (CH + 4) * 4;
+  uint32_t* pw = reinterpret_cast<uint32_t*>(bring + BS_NB * BLK_BYTES);
   const uint32_t lanebit = 1u << lane;
   const int T = 32 * R, G = b.G, n_int = b.n_int;
   const unsigned total = (unsigned)a.n_blk * 32u * (unsigned)G;
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
         if (lane == 0) pw[m.n_words] = 0u;
       }
 
-      const unsigned char* blocks = reinterpret_cast<const unsigned char*>(b.blocks) + (size_t)b.unit_blk_off[w] * BS_BLK_BYTES;
+      const unsigned char* blocks = reinterpret_cast<const unsigned char*>(b.blocks) + (size_t)b.unit_blk_off[w] * BLK_BYTES;
       double prod[R], Y[R], U[R], lpacc[R];
       int ex[R];
 #pragma unroll
@@ -375,20 +381,28 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         // ---- block stage: the block of descriptor di + 4
-        if (lane < BS_BLK_BYTES / 16) bs_cp16(bring + s4 * BS_BLK_BYTES + 16 * lane, blocks + (size_t)(di + 4) * BS_BLK_BYTES + 16 * lane);
+#pragma unroll
+        for (int x = lane; x < BLK_BYTES / 16; x += 32) bs_cp16(bring + s4 * BLK_BYTES + 16 * x, blocks + (size_t)(di + 4) * BLK_BYTES + 16 * x);
         // ---- gather stage: the records of descriptor di + 2 into their slot (records 2 lane and 2 lane + 1)
         uint32_t c2 = BS_NOP;
         if (di >= -2) {
-          const uint32_t* blk = reinterpret_cast<const uint32_t*>(bring + s2 * BS_BLK_BYTES);
-          c2 = blk[BS_CH];
-          const uint2 e2 = *reinterpret_cast<const uint2*>(blk + 2 * lane);
+          const uint32_t* blk = reinterpret_cast<const uint32_t*>(bring + s2 * BLK_BYTES);
+          c2 = blk[CH];
+          const uint2 e2 = *reinterpret_cast<const uint2*>(blk + 2 * lane);  // (tile begin: shift-prefix indices of the lane's slices)
           const uint32_t opG = c2 & 15u;
           unsigned char* slot = wring + s2 * BS_SLOT_BYTES;
           if (opG == BD_REC) {
             const bool masks = ((c2 >> 4) & 3u) == BV_M;
+            // record h * 32 + lane; a short list (boundary lists hold ~60 records, a caterpillar's ~30) skips the empty rounds.
+            // The compute loops read whole groups of 8 / 4 records: the pad entries up to the next multiple of 8 become identities.
+            int cnt2 = (int)((c2 >> 9) & 127u);
+            if (LP && cnt2 == 0) cnt2 = 128;
+            const int cnt2r = (cnt2 + 7) & ~7;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const uint32_t q = h ? e2.y : e2.x;
+            for (int h = 0; h < NPL; h++) {
+              if (h * 32 >= cnt2r) break;
+              const int x = h * 32 + lane;
+              const uint32_t q = blk[x];
               const bool pad = q == kBandPadEntry;
               const uint32_t ref = pad ? 0u : (q & 0xffffu);
               const double2* src = nodes + (size_t)ref * 32;
@@ -396,12 +410,12 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
                 const uint32_t bt1 = (pw[ref >> 5] >> (ref & 31u)) & 1u;
                 src = bleaf + ref * 2 + bt1;
               }
-              double2* dst = reinterpret_cast<double2*>(slot) + 2 * lane + h;
+              double2* dst = reinterpret_cast<double2*>(slot) + x;
               if (pad) *dst = make_double2(1., 0.);  // (never from global memory: one hot sector would serialise the whole GPU)
               else bs_cp16(dst, src);
               if (masks) {
                 const uint32_t lo = (q >> 16) & 31u, len = ((q >> 21) & 63u) - lo;
-                reinterpret_cast<uint32_t*>(slot + BS_CH * 32)[2 * lane + h] = pad ? 0u : ((len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo);
+                reinterpret_cast<uint32_t*>(slot + BS_MASK_OFF)[x] = pad ? 0u : ((len >= 32u ? 0xffffffffu : ((1u << len) - 1u)) << lo);
               }
             }
           } else if (!LP && opG == BD_PAIR) {
@@ -450,7 +464,9 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
         // ---- compute stage: descriptor di
         const int op = code & 15;
         if (op == BD_END) break;
-        const int var = (code >> 4) & 3, kk = (code >> 6) & 7, cnt = (code >> 9) & 127;
+        const int var = (code >> 4) & 3, kk = (code >> 6) & 7;
+        int cnt = (code >> 9) & 127;
+        if (LP && cnt == 0) cnt = 128;  // (7-bit field; only record chunks use it)
         if (op == BD_TILE_BEGIN) {
           tau = (int)(code >> 16);
 #pragma unroll
@@ -508,7 +524,7 @@ __global__ void __launch_bounds__(32 * BS_WARPS, 5) band_integral_kernel(BandStr
             for (int k = 0; k < R; k++)
               if (k == kk) prod[k] *= bs_recs_one(rb, cnt, Y[k]);
           } else {
-            const uint32_t* mb = reinterpret_cast<const uint32_t*>(buf + BS_CH * 32);
+            const uint32_t* mb = reinterpret_cast<const uint32_t*>(buf + BS_MASK_OFF);
 #pragma unroll
             for (int k = 0; k < R; k++)
               if (k == kk) prod[k] *= bs_recs_masked(rb, mb, cnt, Y[k], lanebit);

@@ -325,7 +325,7 @@ struct ppm_engine {
     bdev.rounds = d_brounds.p; bdev.n_rounds = band.n_rounds; bdev.warp_ent_off = d_bwarp_ent_off.p;
     bdev.blocks = d_bs_blocks.p; bdev.unit_blk_off = d_bs_unit_off.p;
     bdev.op_span = d_bs_op_span.p; bdev.leaf_span = d_bs_leaf_span.p;
-    bdev.lp = band.leaf_pow ? 1 : 0; bdev.has_s1 = band.has_s1 ? 1 : 0;
+    bdev.lp = band.leaf_pow ? 1 : 0; bdev.has_s1 = band.has_s1 ? 1 : 0; bdev.chunk = band.chunk;
     bdev.n_alive_leaves = d_blp_alive.p; bdev.htot = d_blp_htot.p; bdev.op_leaf_h = d_blp_op_h.p;
     md.lp_max_h = band.leaf_pow ? band.max_leaf_h : 0.;
     if (band.has_s1 && !prog.has_s1) {  // sum of the heights of every pattern's present leaves, once per handle

@@ -139,6 +139,7 @@ struct BandDev {
   const uint32_t* op_span; const uint32_t* leaf_span;  // alive slices js0 | js1 << 16 of every internal lineage (by record index) / leaf (by bit position)
   // leaf-power program (band_program.h): the lists hold internal lineages only
   int lp, has_s1;
+  int chunk;  // stream layout: entries per chunk (band_codes.h)
   const int* n_alive_leaves; const double* htot;  // [S_pad] leaves alive at each slice and the sum of their heights
   const double* op_leaf_h;                        // [n_ops][2]
 };

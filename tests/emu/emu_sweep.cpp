@@ -69,7 +69,9 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
     size_t eoff = bp.warp_ent_off[w];
     for (int di = bp.warp_off[w];; di++) {
       const uint32_t code = bp.desc[di];
-      const int op = code & 15, var = (code >> 4) & 3, k = (code >> 6) & 7, cnt = (code >> 9) & 127;
+      const int op = code & 15, var = (code >> 4) & 3, k = (code >> 6) & 7;
+      int cnt = (code >> 9) & 127;
+      if ((op == BD_REC || op == BD_PAIR) && cnt == 0) cnt = 128;  // (7-bit field)
       if (op == BD_END) break;
       if (op == BD_TILE_BEGIN) {
         tau = (int)(code >> 16);
@@ -116,7 +118,7 @@ static double band_item_emu(const ModelDev& md, const TablesDev& t, const BandPr
             prod[x] *= (op == BD_PAIR) ? fma(fma(q.z, U[x], q.y), U[x], q.x) : fma(r.y, Y[x], r.x);
           }
       }
-      eoff += bp.stream ? kBandStreamChunk : cnt;
+      eoff += bp.stream ? bp.chunk : cnt;
       for (int x = 0; x < 32 * R; x++) {
         const int be = biased_exp(prod[x]);
         if (be != 0 && be < 1023 - 400) { prod[x] *= pow2i(400); ex[x] += 400; }
