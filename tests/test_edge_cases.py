@@ -92,8 +92,9 @@ def emu():
     return L
 
 
+@pytest.mark.parametrize("R", [8, 108], ids=["per-leaf terms", "leaf powers"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_edge_cases_emulated_kernels(tmp_path, emu, name):
+def test_edge_cases_emulated_kernels(tmp_path, emu, name, R):
     tp, pp = _write(tmp_path, name)
     m, exp = _expected(tp, pp, name != "zero_length_branch")
     assert m["freq"].min() >= 0
@@ -101,8 +102,11 @@ def test_edge_cases_emulated_kernels(tmp_path, emu, name):
     P = len(p)
     ll, i2, parts = np.zeros(P), np.zeros(P), np.zeros((P, 4))
     npat = C.c_longlong()
-    rc = emu.emu_eval(tp.encode(), pp.encode(), 0, 8, p.ctypes.data, P, ll.ctypes.data, i2.ctypes.data, parts.ctypes.data,
+    rc = emu.emu_eval(tp.encode(), pp.encode(), 0, R, p.ctypes.data, P, ll.ctypes.data, i2.ctypes.data, parts.ctypes.data,
                       None, None, C.byref(npat))
+    if R > 100 and name == "tall_leaf":  # leaves above height 0: the program builder must refuse leaf powers
+        assert rc != 0 and b"refused" in emu.emu_error()
+        return
     assert rc == 0, emu.emu_error()
     _check(name, ll, i2, exp)
 
