@@ -173,21 +173,32 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   //     factor T = LSE(lost on the branch, kept and unobserved below)
   // (levels of at most 32 nodes -- every level of a caterpillar -- are served by warp 0 alone; a run of them is kept in step by
   // __syncwarp instead of the CTA barrier: 10,000 levels cost 35 ms with the barrier)
+  // A chain (caterpillar: 10,000 one-node levels) is walked by ONE thread whose every step would wait for three dependent index
+  // loads and for the results it stored a moment ago to come back from L2.  So (1) the thread keeps the node it has just
+  // finished in registers and forwards it to the parent, (2) the next level's node and child ids are requested one level ahead.
+  int fv = -1;                       // the node this thread finished last ...
+  double4 fc = make_double4(0., 0., 0., 0.); double2 fzr = make_double2(0., 0.); double fs0 = 0., fs1 = 0.;  // ... and what its parent reads
+  int nk_ = -1, nv_ = 0, na_ = 0, nb_ = 0;  // ids requested ahead for list position nk_
   for (int lv = 0; lv < m.n_lev_up; lv++) {
     const bool small_lv = PPM_LANES == 32 && m.lev_up_off[lv + 1] - m.lev_up_off[lv] <= 32;
     const bool next_small = small_lv && lv + 1 < m.n_lev_up && m.lev_up_off[lv + 2] - m.lev_up_off[lv + 1] <= 32;
     if (!small_lv || tid < 32)
     for (int k = m.lev_up_off[lv] + tid; k < m.lev_up_off[lv + 1]; k += nt) {
-      const int v = m.lev_up_nodes[k];
-      const bool leaf = m.left[v] < 0;
+      int v, a, b;
+      if (k == nk_) { v = nv_; a = na_; b = nb_; }
+      else { v = m.lev_up_nodes[k]; a = m.left[v]; b = m.right[v]; }
+      if (lv + 1 < m.n_lev_up) {  // this thread's first node of the next level
+        const int kn = m.lev_up_off[lv + 1] + tid;
+        if (kn < m.lev_up_off[lv + 2]) { nk_ = kn; nv_ = m.lev_up_nodes[kn]; na_ = m.left[nv_]; nb_ = m.right[nv_]; }
+      }
+      const bool leaf = a < 0;
+      double4 ca = make_double4(0., 0., 0., 0.), cb = ca;
+      if (!leaf) { ca = a == fv ? fc : cls[a]; cb = b == fv ? fc : cls[b]; }
       double zl0, zl1;
       if (leaf) { zl0 = log_e2; zl1 = log_e2; }
-      else {
-        const int a = m.left[v], b = m.right[v];
-        zl0 = cls[a].y + cls[b].y;
-        zl1 = cls[a].w + cls[b].w;
-      }
+      else { zl0 = ca.y + cb.y; zl1 = ca.w + cb.w; }
       z0[v] = zl0; z1[v] = zl1;
+      double2 zrv = make_double2(0., 0.);
       if (t.zrow) {
         // Mobile partials of the all-zero row (the zero-row integral no longer runs through the sweep): leaves observe 0
         // (objects.cpp:407-408), internal nodes merge their children as the sweep does, renormalised the same way
@@ -195,18 +206,19 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
         int* zk = t.zk + (size_t)p * nn;
         if (leaf) {
           const double m0 = 1 - e1, m1 = e2;
-          zr[v] = make_double2(m0 + pi1 * (m1 - m0), m1 - m0); zk[v] = 0;
+          zrv = make_double2(m0 + pi1 * (m1 - m0), m1 - m0);
+          zr[v] = zrv; zk[v] = 0;
         } else {
-          const int a = m.left[v], b = m.right[v];
           const double orc[4] = {kap[a].x, kap[a].y, kap[b].x, kap[b].y};
           double av, d;
-          merge_children(zr[a], zr[b], orc, pi1, av, d);
+          merge_children(a == fv ? fzr : zr[a], b == fv ? fzr : zr[b], orc, pi1, av, d);
           const int ha = ppm_double2hiint(av) & 0x7fffffff, hd = ppm_double2hiint(d) & 0x7fffffff;
           const int h = ha > hd ? ha : hd;
           const bool small = (uint32_t)(h - 0x00100000) < (uint32_t)(((1023 - 40) << 20) - 0x00100000);
-          const int k = small ? 1022 - (h >> 20) : 0;
-          const double sfac = pow2i(k);
-          zr[v] = make_double2(av * sfac, d * sfac); zk[v] = k;
+          const int kk = small ? 1022 - (h >> 20) : 0;
+          const double sfac = pow2i(kk);
+          zrv = make_double2(av * sfac, d * sfac);
+          zr[v] = zrv; zk[v] = kk;
         }
       }
       const double bl = m.bl[v];
@@ -217,16 +229,20 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       cls[v] = c;
       // class-sum tables: with Stot = sum of S over ALL branches, log p1(root) = Stot + sum over the maximal all-zero
       // subtrees c of F_c, F_c = T_c - (sum of S over the subtree of c)
-      const double s0 = c.x + (leaf ? 0. : ss0[m.left[v]] + ss0[m.right[v]]);
-      const double s1 = c.z + (leaf ? 0. : ss1[m.left[v]] + ss1[m.right[v]]);
+      const double s0 = c.x + (leaf ? 0. : (a == fv ? fs0 : ss0[a]) + (b == fv ? fs0 : ss0[b]));
+      const double s1 = c.z + (leaf ? 0. : (a == fv ? fs1 : ss1[a]) + (b == fv ? fs1 : ss1[b]));
       ss0[v] = s0; ss1[v] = s1;
       t.clsT[(size_t)v * t.P + p] = make_double2(c.y - s0, c.w - s1);
-      // getPobs1 term (functions.cpp:284-299)
-      const double lost = 1 - exp(-l1 * bl);
-      ta[v] = leaf ? lost * (1 - e2) : lost * (1 - exp(zl1));
+      fv = v; fc = c; fzr = zrv; fs0 = s0; fs1 = s1;
     }
     if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
   }
+  // getPobs1 terms (functions.cpp:284-299): off the chain above (two of its six transcendentals per node), one node per thread
+  for (int v = tid; v < nn; v += nt) {
+    const double lost = 1 - exp(-l1 * m.bl[v]);
+    ta[v] = m.left[v] < 0 ? lost * (1 - e2) : lost * (1 - exp(z1[v]));
+  }
+  PPM_CTA_BARRIER();
   // (C) computeI2 pieces that do not need the Mobile integral (functions.cpp:337-341), summed in the reference's order
   if (tid == 0) {
     double p0 = (l0 == 0.) ? 1 - pow(e2, (double)m.n_leaves) : 1 - exp(z0[0]);
@@ -260,28 +276,58 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   // (D) top-down by levels: U (likUpper1, functions.cpp:176-209, as U(v) = lost_v + sigma_v*T(sib)*U(parent),
   //     U(child of root) = lost_v) and log V(v) = sum over the path of log sigma_c + T(sib c).
   //     z0 is reused as log V, z1 as U: a node's own zero-row values are dead once level (B) is complete.
+  // The transcendentals of a node do not depend on its parent: sigma_v = exp(-l1 bl_v) and sigma_v T(sib v) are taken first, one
+  // node per thread (sg: the sixth scratch array; ta is dead after (C)); the chain itself is two FMAs and two additions per node
+  // (10,000 levels: a few ms instead of 14); log U and the table entry follow, again one node per thread.  Same operations on the
+  // same operands as the one-pass form: bitwise the same tables.
+  double* sg = ss1 + nn;
+  for (int v = 1 + tid; v < nn; v += nt) {
+    const int par_ = m.parent[v];
+    const int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];
+    const double sig = exp(-l1 * m.bl[v]);
+    sg[v] = sig;
+    ta[v] = sig * exp(cls[sib].w);
+  }
+  PPM_CTA_BARRIER();
+  // (forwarding and requests one level ahead as in (B): here a node reads its PARENT, finished by the same thread on a chain)
+  fv = -1; nk_ = -1;
+  double fU = 0., fV = 0., fD = 0., fN = 0.;
+  int np_ = 0, ns_ = 0;
   for (int lv = 1; lv < m.n_lev_dn; lv++) {
     const bool small_lv = PPM_LANES == 32 && m.lev_dn_off[lv + 1] - m.lev_dn_off[lv] <= 32;
     const bool next_small = small_lv && lv + 1 < m.n_lev_dn && m.lev_dn_off[lv + 2] - m.lev_dn_off[lv + 1] <= 32;
     if (!small_lv || tid < 32)
     for (int k = m.lev_dn_off[lv] + tid; k < m.lev_dn_off[lv + 1]; k += nt) {
-      const int v = m.lev_dn_nodes[k];
-      const int par_ = m.parent[v];
-      const int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];
-      const double sig = exp(-l1 * m.bl[v]);
-      const double U = (1 - sig) + sig * exp(cls[sib].w) * z1[par_];
-      const double logV = z0[par_] + (-l1 * m.bl[v]) + cls[sib].w;
-      z1[v] = U; z0[v] = logV;
-      const double logU = log(U);
-      d1u[v] = make_double2(lse2(logV, logU) - logV, logU);
-      if (t.et1) {  // ss0 is dead after level (B)/(C): reused as D
-        const double b = m.bl[v], sT = sig * exp(cls[sib].w);
-        const double Dp = ss0[par_], Np = t.et1[(size_t)p * nn + par_];
-        ss0[v] = (1 - sig) + sT * Dp;
-        t.et1[(size_t)p * nn + v] = (1. / l1 - sig * (b + 1. / l1)) + sT * (Np + b * Dp);
+      int v, par_, sib;
+      if (k == nk_) { v = nv_; par_ = np_; sib = ns_; }
+      else { v = m.lev_dn_nodes[k]; par_ = m.parent[v]; sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_]; }
+      if (lv + 1 < m.n_lev_dn) {
+        const int kn = m.lev_dn_off[lv + 1] + tid;
+        if (kn < m.lev_dn_off[lv + 2]) {
+          nk_ = kn; nv_ = m.lev_dn_nodes[kn]; np_ = m.parent[nv_];
+          ns_ = (m.left[np_] == nv_) ? m.right[np_] : m.left[np_];
+        }
       }
+      const double blv = m.bl[v], Tsib = cls[sib].w;
+      const double sig = sg[v], sT = ta[v];
+      const double U = (1 - sig) + sT * (par_ == fv ? fU : z1[par_]);
+      const double logV = (par_ == fv ? fV : z0[par_]) + (-l1 * blv) + Tsib;
+      z1[v] = U; z0[v] = logV;
+      double Dv = 0., Nv = 0.;
+      if (t.et1) {  // ss0 is dead after level (B)/(C): reused as D
+        const double Dp = par_ == fv ? fD : ss0[par_], Np = par_ == fv ? fN : t.et1[(size_t)p * nn + par_];
+        Dv = (1 - sig) + sT * Dp;
+        Nv = (1. / l1 - sig * (blv + 1. / l1)) + sT * (Np + blv * Dp);
+        ss0[v] = Dv;
+        t.et1[(size_t)p * nn + v] = Nv;
+      }
+      fv = v; fU = U; fV = logV; fD = Dv; fN = Nv;
     }
     if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
+  }
+  for (int v = 1 + tid; v < nn; v += nt) {
+    const double logV = z0[v], logU = log(z1[v]);
+    d1u[v] = make_double2(lse2(logV, logU) - logV, logU);
   }
   if (t.et1) {
     for (int v = tid; v < nn; v += nt) t.et1[(size_t)p * nn + v] /= ss0[v];
