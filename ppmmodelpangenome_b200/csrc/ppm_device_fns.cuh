@@ -154,7 +154,7 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   const double log_e2 = log(e2), log_1me2 = log(1 - e2);
 
   // (A) per node, independent: branch survival logs and the Mobile branch factors.
-  //     cls[v] = {S0, log(1-sigma0), S1, log(1-sigma1)} for now; .y/.w become T0/T1 in (B)
+  //     cls[v] = {S0, -, S1, -}; .y/.w become log T0 / log T1 after (B); d1u[v] = (sigma0, sigma1) until (D) ends
   for (int v = tid; v < nn; v += nt) {
     const bool leaf = m.left[v] < 0;
     const double bl = m.bl[v];
@@ -162,23 +162,38 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     // active branch (a present leaf below): survive the branch; a leaf adds its own log(1-e2)   (objects.cpp:408,423)
     c.x = -l0 * bl + (leaf ? log_1me2 : 0.);
     c.z = -l1 * bl + (leaf ? log_1me2 : 0.);
-    c.y = log(1 - exp(-l0 * bl));
-    c.w = log(1 - exp(-l1 * bl));
+    const double sg0 = exp(-l0 * bl), sg1 = exp(-l1 * bl);
+    c.y = 0.; c.w = 0.;  // (T0 / T1: written after (B))
     cls[v] = c;
+    d1u[v] = make_double2(sg0, sg1);  // branch survival, read by (B) (d1u is written for good at the end of (D))
     const double E = exp(-lam * bl);
     kap[v] = make_double2(pi1 * E, pi0 * E);
   }
   PPM_CTA_BARRIER();
-  // (B) bottom-up by levels: zero-row log p1 per node (objects.cpp:404-426 on the all-zero row) and the frontier
-  //     factor T = LSE(lost on the branch, kept and unobserved below)
+  // (B) bottom-up by levels: the frontier factor T_v = (1 - sigma_v) + sigma_v Z_v, Z_v = T_a T_b (a leaf: Z = e2) -- the
+  //     reference's LSE(lost on the branch, kept and unobserved below) of objects.cpp:404-426 on the all-zero row -- in the
+  //     LINEAR domain with an integer exponent (value = tm 2^-te): a product over thousands of leaves leaves the double range,
+  //     and a chain of 10,000 dependent log1p(exp()) pairs is what a caterpillar's node prepass used to wait for.  The logs
+  //     (cls.y/.w, z0/z1) are taken afterwards, one node per thread.  During the walk z0/z1 hold tm, ta/sg hold te.
   // (levels of at most 32 nodes -- every level of a caterpillar -- are served by warp 0 alone; a run of them is kept in step by
-  // __syncwarp instead of the CTA barrier: 10,000 levels cost 35 ms with the barrier)
-  // A chain (caterpillar: 10,000 one-node levels) is walked by ONE thread whose every step would wait for three dependent index
-  // loads and for the results it stored a moment ago to come back from L2.  So (1) the thread keeps the node it has just
-  // finished in registers and forwards it to the parent, (2) the next level's node and child ids are requested one level ahead.
+  // __syncwarp instead of the CTA barrier)
+  // A chain is walked by ONE thread: it keeps the node it has just finished in registers and forwards it to the parent, and
+  // requests the next level's node and child ids one level ahead.
+  double* sg = ss1 + nn;             // sixth scratch array
   int fv = -1;                       // the node this thread finished last ...
-  double4 fc = make_double4(0., 0., 0., 0.); double2 fzr = make_double2(0., 0.); double fs0 = 0., fs1 = 0.;  // ... and what its parent reads
+  double ftm0 = 0., ftm1 = 0.; int fte0 = 0, fte1 = 0;  // ... and what its parent reads
+  double2 fzr = make_double2(0., 0.); double fs0 = 0., fs1 = 0.;
   int nk_ = -1, nv_ = 0, na_ = 0, nb_ = 0;  // ids requested ahead for list position nk_
+  // T = (1 - sigma) + sigma Zm 2^-Ze, renormalised when it has become small
+  auto frontier_lin = [&](double sig, double Zm, int Ze, double& tm, int& te) {
+    const double A = 1 - sig;
+    double Im = A; int Ie = (A != 0.) ? 0 : 0x3fffffff;
+    scaled_add(Im, Ie, sig * Zm, Ze);
+    if (Im == 0.) Ie = 0;
+    const int be = biased_exp(Im);
+    if (be != 0 && be < 1023 - 400) { Im *= pow2i(400); Ie += 400; }
+    tm = Im; te = Ie;
+  };
   for (int lv = 0; lv < m.n_lev_up; lv++) {
     const bool small_lv = PPM_LANES == 32 && m.lev_up_off[lv + 1] - m.lev_up_off[lv] <= 32;
     const bool next_small = small_lv && lv + 1 < m.n_lev_up && m.lev_up_off[lv + 2] - m.lev_up_off[lv + 1] <= 32;
@@ -192,12 +207,18 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
         if (kn < m.lev_up_off[lv + 2]) { nk_ = kn; nv_ = m.lev_up_nodes[kn]; na_ = m.left[nv_]; nb_ = m.right[nv_]; }
       }
       const bool leaf = a < 0;
-      double4 ca = make_double4(0., 0., 0., 0.), cb = ca;
-      if (!leaf) { ca = a == fv ? fc : cls[a]; cb = b == fv ? fc : cls[b]; }
-      double zl0, zl1;
-      if (leaf) { zl0 = log_e2; zl1 = log_e2; }
-      else { zl0 = ca.y + cb.y; zl1 = ca.w + cb.w; }
-      z0[v] = zl0; z1[v] = zl1;
+      double Zm0 = e2, Zm1 = e2; int Ze0 = 0, Ze1 = 0;
+      if (!leaf) {
+        const bool fa = a == fv, fb = b == fv;
+        Zm0 = (fa ? ftm0 : z0[a]) * (fb ? ftm0 : z0[b]); Ze0 = (fa ? fte0 : (int)ta[a]) + (fb ? fte0 : (int)ta[b]);
+        Zm1 = (fa ? ftm1 : z1[a]) * (fb ? ftm1 : z1[b]); Ze1 = (fa ? fte1 : (int)sg[a]) + (fb ? fte1 : (int)sg[b]);
+      }
+      const double2 sgv = d1u[v];
+      double tm0, tm1; int te0, te1;
+      frontier_lin(sgv.x, Zm0, Ze0, tm0, te0);
+      frontier_lin(sgv.y, Zm1, Ze1, tm1, te1);
+      if (v == 0) { tm0 = 1.; tm1 = 1.; te0 = 0; te1 = 0; }  // (the root has no branch: T = 1)
+      z0[v] = tm0; z1[v] = tm1; ta[v] = (double)te0; sg[v] = (double)te1;
       double2 zrv = make_double2(0., 0.);
       if (t.zrow) {
         // Mobile partials of the all-zero row (the zero-row integral no longer runs through the sweep): leaves observe 0
@@ -221,26 +242,38 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
           zr[v] = zrv; zk[v] = kk;
         }
       }
-      const double bl = m.bl[v];
-      double4 c = cls[v];
-      c.y = lse2(c.y, -l0 * bl + zl0);
-      c.w = lse2(c.w, -l1 * bl + zl1);
-      if (v == 0) c = make_double4(0., 0., 0., 0.);
-      cls[v] = c;
       // class-sum tables: with Stot = sum of S over ALL branches, log p1(root) = Stot + sum over the maximal all-zero
       // subtrees c of F_c, F_c = T_c - (sum of S over the subtree of c)
-      const double s0 = c.x + (leaf ? 0. : (a == fv ? fs0 : ss0[a]) + (b == fv ? fs0 : ss0[b]));
-      const double s1 = c.z + (leaf ? 0. : (a == fv ? fs1 : ss1[a]) + (b == fv ? fs1 : ss1[b]));
+      const double4 c = cls[v];
+      const double cx = v == 0 ? 0. : c.x, cz = v == 0 ? 0. : c.z;
+      const double s0 = cx + (leaf ? 0. : (a == fv ? fs0 : ss0[a]) + (b == fv ? fs0 : ss0[b]));
+      const double s1 = cz + (leaf ? 0. : (a == fv ? fs1 : ss1[a]) + (b == fv ? fs1 : ss1[b]));
       ss0[v] = s0; ss1[v] = s1;
-      t.clsT[(size_t)v * t.P + p] = make_double2(c.y - s0, c.w - s1);
-      fv = v; fc = c; fzr = zrv; fs0 = s0; fs1 = s1;
+      fv = v; ftm0 = tm0; ftm1 = tm1; fte0 = te0; fte1 = te1; fzr = zrv; fs0 = s0; fs1 = s1;
     }
     if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
   }
-  // getPobs1 terms (functions.cpp:284-299): off the chain above (two of its six transcendentals per node), one node per thread
+  // the logs, one node per thread: T0 / T1 into cls ...
   for (int v = tid; v < nn; v += nt) {
+    double4 c = cls[v];
+    c.y = log(z0[v]) - ta[v] * 0.693147180559945309417232;
+    c.w = log(z1[v]) - sg[v] * 0.693147180559945309417232;
+    if (v == 0) c = make_double4(0., 0., 0., 0.);
+    cls[v] = c;
+  }
+  PPM_CTA_BARRIER();
+  // ... then, per node, the zero-row log p1 (the children's T), the class-sum table entry and the getPobs1 term
+  // (functions.cpp:284-299)
+  for (int v = tid; v < nn; v += nt) {
+    const int a = m.left[v], b = m.right[v];
+    const bool leaf = a < 0;
+    const double zl0 = leaf ? log_e2 : cls[a].y + cls[b].y;
+    const double zl1 = leaf ? log_e2 : cls[a].w + cls[b].w;
+    const double4 c = cls[v];
+    t.clsT[(size_t)v * t.P + p] = make_double2(c.y - ss0[v], c.w - ss1[v]);
     const double lost = 1 - exp(-l1 * m.bl[v]);
-    ta[v] = m.left[v] < 0 ? lost * (1 - e2) : lost * (1 - exp(z1[v]));
+    const double tav = leaf ? lost * (1 - e2) : lost * (1 - exp(zl1));
+    z0[v] = zl0; z1[v] = zl1; ta[v] = tav;
   }
   PPM_CTA_BARRIER();
   // (C) computeI2 pieces that do not need the Mobile integral (functions.cpp:337-341), summed in the reference's order
@@ -280,7 +313,6 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   // node per thread (sg: the sixth scratch array; ta is dead after (C)); the chain itself is two FMAs and two additions per node
   // (10,000 levels: a few ms instead of 14); log U and the table entry follow, again one node per thread.  Same operations on the
   // same operands as the one-pass form: bitwise the same tables.
-  double* sg = ss1 + nn;
   for (int v = 1 + tid; v < nn; v += nt) {
     const int par_ = m.parent[v];
     const int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];

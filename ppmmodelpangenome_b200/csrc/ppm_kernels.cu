@@ -21,7 +21,7 @@
 namespace ppm {
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(128) prepass_nodes_kernel(ModelDev m, TablesDev t) {
+__global__ void __launch_bounds__(512) prepass_nodes_kernel(ModelDev m, TablesDev t) {
   prepass_nodes_body(m, t, blockIdx.x, threadIdx.x, blockDim.x);
 }
 __global__ void prepass_tables_kernel(ModelDev m, TablesDev t) {
@@ -419,7 +419,9 @@ __global__ void finalize_kernel(const double* i2, double* ll, int P) {
 
 // ------------------------------------------------------------------------------------------------ launchers
 void launch_prepass_nodes(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
-  prepass_nodes_kernel<<<t.P, 128, 0, s>>>(m, t);
+  // one CTA per parameter vector; big trees with few parameter vectors want the wide CTA (5,000 genomes, P = 1: 0.77 ms with 128 threads)
+  const int threads = (m.n_nodes >= 2048 && t.P <= 296) ? 512 : 128;
+  prepass_nodes_kernel<<<t.P, threads, 0, s>>>(m, t);
 }
 void launch_prepass_tables(const ModelDev& m, const TablesDev& t, cudaStream_t s) {
   int n = m.n_entries + 1 + m.n_blocks * m.R + m.n_ops + m.n_leaves + m.n_pairs + m.n_cherries;
