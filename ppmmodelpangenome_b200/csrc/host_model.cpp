@@ -198,6 +198,14 @@ static void finish_tree(Tree& t) {
     };
     bucket(up, t.lev_up_off, t.lev_up_nodes);
     bucket(dn, t.lev_dn_off, t.lev_dn_nodes);
+    const int nld = (int)t.lev_dn_off.size() - 1;
+    std::vector<int> n_internal(nld + 1, 0);
+    for (int l = 0; l < nld; l++) {
+      auto first = t.lev_dn_nodes.begin() + t.lev_dn_off[l], last = t.lev_dn_nodes.begin() + t.lev_dn_off[l + 1];
+      n_internal[l] = (int)(std::stable_partition(first, last, [&](int v) { return t.left[v] >= 0; }) - first);
+    }
+    t.lev_dn_chain.assign(nld + 1, 0);
+    for (int l = 0; l + 1 < nld; l++) t.lev_dn_chain[l] = (n_internal[l] == 1 && n_internal[l + 1] == 1) ? 1 : 0;
   }
 
   // breadth-first last node (what computeMRCA returns for an all-zero pattern, functions.cpp:52-64)

@@ -20,6 +20,9 @@ struct Tree {
   std::vector<int> leaf_node;            // bit position -> node id
   // level lists for level-synchronous recursions: up = by height in edges (leaves first), dn = by depth (root first)
   std::vector<int> lev_up_off, lev_up_nodes, lev_dn_off, lev_dn_nodes;
+  // top-down lists: internal nodes first inside a level (leaves read their parent after the walk); lev_dn_chain[l] = 1 when
+  // levels l and l + 1 hold exactly one internal node each (a caterpillar: one thread walks them without synchronising)
+  std::vector<int> lev_dn_chain;
   int bfs_last = 0;                      // last node of a breadth-first walk (computeMRCA of an empty pattern)
   double H = 0, L = 0;                   // functions.cpp:108, objects.cpp:115-122
   // Mobile integral grid (functions.cpp:250-260)

@@ -251,7 +251,11 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       ss0[v] = s0; ss1[v] = s1;
       fv = v; ftm0 = tm0; ftm1 = tm1; fte0 = te0; fte1 = te1; fzr = zrv; fs0 = s0; fs1 = s1;
     }
-    if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
+    // (between two one-node levels nothing is exchanged between threads: thread 0 walks the chain in program order, and the
+    //  fence a __syncwarp implies -- every store of the level performed before the next level's loads issue -- is what a
+    //  10,000-level chain used to pay 3 us per level for)
+    const bool chain = next_small && m.lev_up_off[lv + 1] - m.lev_up_off[lv] == 1 && m.lev_up_off[lv + 2] - m.lev_up_off[lv + 1] == 1;
+    if (chain) {} else if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
   }
   // the logs, one node per thread: T0 / T1 into cls ...
   for (int v = tid; v < nn; v += nt) {
@@ -340,6 +344,7 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
           ns_ = (m.left[np_] == nv_) ? m.right[np_] : m.left[np_];
         }
       }
+      if (m.left[v] < 0) continue;  // a leaf has no children to serve: it reads its parent after the walk
       const double blv = m.bl[v], Tsib = cls[sib].w;
       const double sig = sg[v], sT = ta[v];
       const double U = (1 - sig) + sT * (par_ == fv ? fU : z1[par_]);
@@ -355,8 +360,26 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       }
       fv = v; fU = U; fV = logV; fD = Dv; fN = Nv;
     }
-    if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
+    // (the lists hold the internal nodes of a level first: one internal node per level = thread 0 walks a chain)
+    const bool chain = next_small && m.lev_dn_chain[lv] != 0;
+    if (chain) {} else if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
   }
+  // the leaves, one per thread, from their parents' finished values (same formulas)
+  for (int v = 1 + tid; v < nn; v += nt) {
+    if (m.left[v] >= 0) continue;
+    const int par_ = m.parent[v];
+    const int sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_];
+    const double blv = m.bl[v], Tsib = cls[sib].w;
+    const double sig = sg[v], sT = ta[v];
+    z1[v] = (1 - sig) + sT * z1[par_];
+    z0[v] = z0[par_] + (-l1 * blv) + Tsib;
+    if (t.et1) {
+      const double Dp = ss0[par_], Np = t.et1[(size_t)p * nn + par_];
+      ss0[v] = (1 - sig) + sT * Dp;
+      t.et1[(size_t)p * nn + v] = (1. / l1 - sig * (blv + 1. / l1)) + sT * (Np + blv * Dp);
+    }
+  }
+  PPM_CTA_BARRIER();
   for (int v = 1 + tid; v < nn; v += nt) {
     const double logV = z0[v], logU = log(z1[v]);
     d1u[v] = make_double2(lse2(logV, logU) - logV, logU);

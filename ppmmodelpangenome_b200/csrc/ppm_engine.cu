@@ -134,7 +134,7 @@ struct ppm_engine {
   double n_launches = 0;
 
   // device model
-  DevBuf<int> d_leaf_node, d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes;
+  DevBuf<int> d_leaf_node, d_left, d_right, d_parent, d_entry_ref, d_entry_node, d_entry_block, d_lev_up_off, d_lev_up_nodes, d_lev_dn_off, d_lev_dn_nodes, d_lev_dn_chain;
   DevBuf<ppm::BlockDesc> d_blk;
   DevBuf<uint32_t> d_entry_mask;
   DevBuf<double> d_bl, d_height, d_slice_t, d_slice_wt, d_op_tb;
@@ -377,7 +377,7 @@ struct ppm_engine {
     d_left.upload(tree.left, stream); d_right.upload(tree.right, stream); d_parent.upload(tree.parent, stream);
     d_bl.upload(tree.bl, stream); d_height.upload(tree.height, stream);
     d_lev_up_off.upload(tree.lev_up_off, stream); d_lev_up_nodes.upload(tree.lev_up_nodes, stream);
-    d_lev_dn_off.upload(tree.lev_dn_off, stream); d_lev_dn_nodes.upload(tree.lev_dn_nodes, stream);
+    d_lev_dn_off.upload(tree.lev_dn_off, stream); d_lev_dn_nodes.upload(tree.lev_dn_nodes, stream); d_lev_dn_chain.upload(tree.lev_dn_chain, stream);
     d_slice_t.upload(tree.slice_t, stream);
     std::vector<double> wt_pad((size_t)std::max(prog.n_blocks, 1) * prog.R, 0.);
     std::copy(tree.slice_wt.begin(), tree.slice_wt.end(), wt_pad.begin());
@@ -413,7 +413,7 @@ struct ppm_engine {
     md.n_ops = (int)prog.ops.size(); md.R = prog.R; md.deep = prog.deep ? 1 : 0; md.H = tree.H; md.n_obs = pat.n_obs;
     md.left = d_left.p; md.right = d_right.p; md.parent = d_parent.p; md.bl = d_bl.p; md.height = d_height.p;
     md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
-    md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p;
+    md.lev_up_off = d_lev_up_off.p; md.lev_up_nodes = d_lev_up_nodes.p; md.lev_dn_off = d_lev_dn_off.p; md.lev_dn_nodes = d_lev_dn_nodes.p; md.lev_dn_chain = d_lev_dn_chain.p;
     md.slice_t = d_slice_t.p; md.slice_wt_pad = d_slice_wt.p;
     md.blk = d_blk.p; md.ops = d_ops.p; md.sops = d_sops.p; md.op_tb = d_op_tb.p; md.cherry_op = d_cherry_op.p; md.n_cherries = prog.n_cherries;
     md.n_pairs = prog.n_pairs; md.leaf_node = d_leaf_node.p;

@@ -65,6 +65,7 @@ struct ModelDev {
   // node levels for the prepass recursions: bottom-up (leaves = level 0) and top-down (root = level 0)
   int n_lev_up, n_lev_dn;
   const int* lev_up_off; const int* lev_up_nodes; const int* lev_dn_off; const int* lev_dn_nodes;
+  const int* lev_dn_chain;  // [n_lev_dn + 1] levels l and l + 1 hold one internal node each (host_model.h)
   // slices
   const double* slice_t; const double* slice_wt_pad;  // [n_slices], [n_blocks*R] (0 for padding slices)
   // program

@@ -180,7 +180,7 @@ extern "C" int emu_eval(const char* tree_path, const char* pa_path, int dedupe, 
     md.bl = tree.bl.data(); md.height = tree.height.data();
     md.n_lev_up = (int)tree.lev_up_off.size() - 1; md.n_lev_dn = (int)tree.lev_dn_off.size() - 1;
     md.lev_up_off = tree.lev_up_off.data(); md.lev_up_nodes = tree.lev_up_nodes.data();
-    md.lev_dn_off = tree.lev_dn_off.data(); md.lev_dn_nodes = tree.lev_dn_nodes.data();
+    md.lev_dn_off = tree.lev_dn_off.data(); md.lev_dn_nodes = tree.lev_dn_nodes.data(); md.lev_dn_chain = tree.lev_dn_chain.data();
     md.slice_t = tree.slice_t.data(); md.slice_wt_pad = wt_pad.data();
     md.blk = reinterpret_cast<const BlockDesc*>(prog.blk.data());
     md.ops = reinterpret_cast<const NodeOpDev*>(prog.ops.data());
