@@ -194,17 +194,21 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     if (be != 0 && be < 1023 - 400) { Im *= pow2i(400); Ie += 400; }
     tm = Im; te = Ie;
   };
+  // (the level offsets travel in registers, the next one requested a level ahead: a load of lev_up_off at the head of every
+  //  level cost every warp an L2 round trip per level -- half of the 3 us a caterpillar's level took)
+  int uo0 = m.lev_up_off[0], uo1 = m.lev_up_off[1], uo2 = m.n_lev_up >= 2 ? m.lev_up_off[2] : uo1;
   for (int lv = 0; lv < m.n_lev_up; lv++) {
-    const bool small_lv = PPM_LANES == 32 && m.lev_up_off[lv + 1] - m.lev_up_off[lv] <= 32;
-    const bool next_small = small_lv && lv + 1 < m.n_lev_up && m.lev_up_off[lv + 2] - m.lev_up_off[lv + 1] <= 32;
+    const int uo3 = lv + 3 <= m.n_lev_up ? m.lev_up_off[lv + 3] : uo2;  // (used from the next level on)
+    const bool small_lv = PPM_LANES == 32 && uo1 - uo0 <= 32;
+    const bool next_small = small_lv && lv + 1 < m.n_lev_up && uo2 - uo1 <= 32;
     if (!small_lv || tid < 32)
-    for (int k = m.lev_up_off[lv] + tid; k < m.lev_up_off[lv + 1]; k += nt) {
+    for (int k = uo0 + tid; k < uo1; k += nt) {
       int v, a, b;
       if (k == nk_) { v = nv_; a = na_; b = nb_; }
       else { v = m.lev_up_nodes[k]; a = m.left[v]; b = m.right[v]; }
       if (lv + 1 < m.n_lev_up) {  // this thread's first node of the next level
-        const int kn = m.lev_up_off[lv + 1] + tid;
-        if (kn < m.lev_up_off[lv + 2]) { nk_ = kn; nv_ = m.lev_up_nodes[kn]; na_ = m.left[nv_]; nb_ = m.right[nv_]; }
+        const int kn = uo1 + tid;
+        if (kn < uo2) { nk_ = kn; nv_ = m.lev_up_nodes[kn]; na_ = m.left[nv_]; nb_ = m.right[nv_]; }
       }
       const bool leaf = a < 0;
       double Zm0 = e2, Zm1 = e2; int Ze0 = 0, Ze1 = 0;
@@ -254,8 +258,9 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
     // (between two one-node levels nothing is exchanged between threads: thread 0 walks the chain in program order, and the
     //  fence a __syncwarp implies -- every store of the level performed before the next level's loads issue -- is what a
     //  10,000-level chain used to pay 3 us per level for)
-    const bool chain = next_small && m.lev_up_off[lv + 1] - m.lev_up_off[lv] == 1 && m.lev_up_off[lv + 2] - m.lev_up_off[lv + 1] == 1;
+    const bool chain = next_small && uo1 - uo0 == 1 && uo2 - uo1 == 1;
     if (chain) {} else if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
+    uo0 = uo1; uo1 = uo2; uo2 = uo3;
   }
   // the logs, one node per thread: T0 / T1 into cls ...
   for (int v = tid; v < nn; v += nt) {
@@ -329,17 +334,21 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
   fv = -1; nk_ = -1;
   double fU = 0., fV = 0., fD = 0., fN = 0.;
   int np_ = 0, ns_ = 0;
+  int do0 = m.n_lev_dn >= 1 ? m.lev_dn_off[1] : 0, do1 = m.n_lev_dn >= 2 ? m.lev_dn_off[2] : do0, do2 = m.n_lev_dn >= 3 ? m.lev_dn_off[3] : do1;
+  int dc0 = m.n_lev_dn >= 2 ? m.lev_dn_chain[1] : 0;
   for (int lv = 1; lv < m.n_lev_dn; lv++) {
-    const bool small_lv = PPM_LANES == 32 && m.lev_dn_off[lv + 1] - m.lev_dn_off[lv] <= 32;
-    const bool next_small = small_lv && lv + 1 < m.n_lev_dn && m.lev_dn_off[lv + 2] - m.lev_dn_off[lv + 1] <= 32;
+    const int do3 = lv + 3 <= m.n_lev_dn ? m.lev_dn_off[lv + 3] : do2;
+    const int dc1 = lv + 1 < m.n_lev_dn ? m.lev_dn_chain[lv + 1] : 0;
+    const bool small_lv = PPM_LANES == 32 && do1 - do0 <= 32;
+    const bool next_small = small_lv && lv + 1 < m.n_lev_dn && do2 - do1 <= 32;
     if (!small_lv || tid < 32)
-    for (int k = m.lev_dn_off[lv] + tid; k < m.lev_dn_off[lv + 1]; k += nt) {
+    for (int k = do0 + tid; k < do1; k += nt) {
       int v, par_, sib;
       if (k == nk_) { v = nv_; par_ = np_; sib = ns_; }
       else { v = m.lev_dn_nodes[k]; par_ = m.parent[v]; sib = (m.left[par_] == v) ? m.right[par_] : m.left[par_]; }
       if (lv + 1 < m.n_lev_dn) {
-        const int kn = m.lev_dn_off[lv + 1] + tid;
-        if (kn < m.lev_dn_off[lv + 2]) {
+        const int kn = do1 + tid;
+        if (kn < do2) {
           nk_ = kn; nv_ = m.lev_dn_nodes[kn]; np_ = m.parent[nv_];
           ns_ = (m.left[np_] == nv_) ? m.right[np_] : m.left[np_];
         }
@@ -361,8 +370,9 @@ PPM_HD void prepass_nodes_body(const ModelDev& m, const TablesDev& t, int p, int
       fv = v; fU = U; fV = logV; fD = Dv; fN = Nv;
     }
     // (the lists hold the internal nodes of a level first: one internal node per level = thread 0 walks a chain)
-    const bool chain = next_small && m.lev_dn_chain[lv] != 0;
+    const bool chain = next_small && dc0 != 0;
     if (chain) {} else if (next_small) { if (tid < 32) ppm_syncwarp(); } else PPM_CTA_BARRIER();
+    do0 = do1; do1 = do2; do2 = do3; dc0 = dc1;
   }
   // the leaves, one per thread, from their parents' finished values (same formulas)
   for (int v = 1 + tid; v < nn; v += nt) {
